@@ -1,0 +1,134 @@
+"""Synthetic workloads of the shapes BASELINE.json names (host side, numpy).
+
+The reference obtains its traces from the EVM kernel interpreter inside ``evm_arithmetization``
+(``generate_traces``; reached from /root/reference/ops/src/lib.rs:52), which needs a real witness from
+an Ethereum RPC node (/root/reference/leader/src/lib.rs:158-535) and is out of scope.  These
+generators stand in for it: counter-based (SplitMix64), so every rank / the CPU baseline can rebuild
+the same data from ``(seed, shape)`` without transfers.
+
+* ``random_columns``      — config 2 (commit microbench): uniform Goldilocks columns.
+* ``fibonacci_trace``     — starky's FibonacciStark example table (2 columns, 3 public inputs).
+* ``memory_trace``        — config 3: a constraint-satisfying trace for the memory-shaped table
+                            (21 columns; SURVEY.md Appendix A sketch of evm_arithmetization's MemoryStark).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+# memory table column indices (evm_arithmetization/src/memory/columns.rs, recalled order)
+M_FILTER, M_TIMESTAMP, M_IS_READ, M_CTX, M_SEG, M_VIRT, M_VALUE0 = 0, 1, 2, 3, 4, 5, 6
+M_CFC, M_SFC, M_VFC, M_INIT_AUX, M_RANGE_CHECK, M_COUNTER, M_FREQ = 14, 15, 16, 17, 18, 19, 20
+MEMORY_COLUMNS = 21
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = (x.astype(np.uint64) + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def _rand(seed: int, stream: int, n: int) -> np.ndarray:
+    base = splitmix64(np.array([seed * 0x1000003 + stream], dtype=np.uint64))[0]
+    with np.errstate(over="ignore"):
+        return splitmix64(np.arange(n, dtype=np.uint64) * np.uint64(0x2545F4914F6CDD1D) + base)
+
+
+def random_columns(n_cols: int, log_n: int, seed: int = 0xB200) -> np.ndarray:
+    """(n_cols, 2^log_n) canonical Goldilocks elements, column c keyed by seed + c."""
+    n = 1 << log_n
+    out = np.empty((n_cols, n), dtype=np.uint64)
+    for c in range(n_cols):
+        x = _rand(seed + c, 0, n)
+        out[c] = np.where(x >= np.uint64(P), x - np.uint64(P), x)
+    return out
+
+
+def fibonacci_trace(log_n: int, seed: int = 1):
+    """Returns (trace (2, n), public_inputs [x0, x1, x1_last])."""
+    n = 1 << log_n
+    x0, x1 = (seed * 3 + 1) % P, (seed * 5 + 2) % P
+    pi = [x0, x1]
+    t = np.zeros((2, n), dtype=np.uint64)
+    for i in range(n):
+        t[0, i], t[1, i] = x0, x1
+        x0, x1 = x1, (x0 + x1) % P
+    pi.append(int(t[1, n - 1]))
+    return t, pi
+
+
+def _segmented_cumsum(incr: np.ndarray, start_mask: np.ndarray, start_val: np.ndarray) -> np.ndarray:
+    """out[i] = start_val[s] + sum(incr[s+1..i]) where s = last index <= i with start_mask set (index 0 is a start)."""
+    n = incr.size
+    idx = np.where(start_mask, np.arange(n), 0)
+    idx = np.maximum.accumulate(idx)
+    inc = np.where(start_mask, 0, incr).astype(np.int64)
+    cs = np.cumsum(inc)
+    return start_val[idx].astype(np.int64) + cs - cs[idx]
+
+
+def memory_trace(log_n: int, seed: int = 7, dummy_rows: int | None = None) -> np.ndarray:
+    """A (21, 2^log_n) trace satisfying every constraint of the memory-shaped table, including the
+    logUp range check of RANGE_CHECK against COUNTER with multiplicities FREQUENCIES."""
+    n = 1 << log_n
+    assert n >= 32
+    if dummy_rows is None:
+        dummy_rows = max(1, n // 16)
+    real = n - dummy_rows
+    r_kind = (_rand(seed, 1, n) & np.uint64(0xFF)).astype(np.int64)
+    r_a = _rand(seed, 2, n)
+    r_b = _rand(seed, 3, n)
+    # kind[i] describes how row i differs from row i-1: 0 unchanged, 1 virt, 2 seg, 3 ctx change
+    kind = np.where(r_kind < 160, 0, np.where(r_kind < 232, 1, np.where(r_kind < 250, 2, 3)))
+    kind[0] = 3
+    kind[real:] = 0  # dummy rows repeat the last address
+    is_first = kind != 0
+    d_ctx = np.where(kind == 3, 1 + (r_a % np.uint64(3)).astype(np.int64), 0)
+    d_ctx[0] = 0
+    ctx = np.cumsum(d_ctx)
+    seg = _segmented_cumsum(np.where(kind == 2, 1 + ((r_a >> np.uint64(8)) % np.uint64(2)).astype(np.int64), 0),
+                            kind == 3, ((r_b >> np.uint64(4)) % np.uint64(4)).astype(np.int64))
+    virt = _segmented_cumsum(np.where(kind == 1, 1 + ((r_a >> np.uint64(16)) % np.uint64(8)).astype(np.int64), 0),
+                             kind >= 2, ((r_b >> np.uint64(12)) % np.uint64(64)).astype(np.int64))
+    d_ts = 1 + ((r_a >> np.uint64(24)) % np.uint64(4)).astype(np.int64)
+    d_ts[real:] = 0
+    ts = _segmented_cumsum(np.where(kind == 0, d_ts, 0), is_first, ((r_b >> np.uint64(20)) % np.uint64(16)).astype(np.int64))
+    # reads / writes
+    coin = (r_b >> np.uint64(32)) & np.uint64(3)
+    is_read = np.where(is_first, coin == 0, coin < 2)
+    is_read[real:] = True
+    # value definition points: writes, and first-op reads (value 0)
+    is_def = is_first | ~is_read
+    def_idx = np.maximum.accumulate(np.where(is_def, np.arange(n), 0))
+    t = np.zeros((MEMORY_COLUMNS, n), dtype=np.uint64)
+    for limb in range(8):
+        v = _rand(seed, 10 + limb, n) & np.uint64(0xFFFFFFFF)
+        v = np.where(is_first & is_read, np.uint64(0), v)
+        t[M_VALUE0 + limb] = v[def_idx]
+    t[M_FILTER, :real] = 1
+    t[M_TIMESTAMP] = ts.astype(np.uint64)
+    t[M_IS_READ] = is_read.astype(np.uint64)
+    t[M_CTX] = ctx.astype(np.uint64)
+    t[M_SEG] = seg.astype(np.uint64)
+    t[M_VIRT] = virt.astype(np.uint64)
+    # flags on row i describe the step i -> i+1; last row: all zero
+    nk = np.concatenate([kind[1:], [0]])
+    t[M_CFC] = (nk == 3).astype(np.uint64)
+    t[M_SFC] = (nk == 2).astype(np.uint64)
+    t[M_VFC] = (nk == 1).astype(np.uint64)
+    nxt = lambda a: np.concatenate([a[1:], a[-1:]])
+    rc = np.where(nk == 3, nxt(ctx) - ctx - 1, np.where(nk == 2, nxt(seg) - seg - 1,
+                  np.where(nk == 1, nxt(virt) - virt - 1, nxt(ts) - ts)))
+    rc[-1] = 0
+    assert rc.min() >= 0 and rc.max() < n
+    t[M_RANGE_CHECK] = rc.astype(np.uint64)
+    init_aux = nxt(seg) * (nk != 0) * nxt(is_read.astype(np.int64))
+    init_aux[-1] = 0
+    t[M_INIT_AUX] = init_aux.astype(np.uint64)
+    t[M_COUNTER] = np.arange(n, dtype=np.uint64)
+    t[M_FREQ] = np.bincount(rc, minlength=n).astype(np.uint64)
+    return t

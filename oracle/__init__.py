@@ -1,0 +1,316 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes loader for ``oracle/liboracle.so``, the CPU restatement (C11 + OpenMP) of the plonky2/starky
+proving hot path reached from the reference at ``/root/reference/ops/src/lib.rs:52``.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs
+may import this module, and only as the checker or the timed CPU baseline.  Nothing under
+``eth_tx_proof_b200/`` imports it.
+
+Parity status: Poseidon constants + permutation pinned by upstream known-answer vectors
+(``tests/golden/poseidon_kat.json``); everything composed above is "parity unpinned" against real
+plonky2 output (no Rust toolchain, no upstream sources; see ``oracle/oracle.h``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+P = 0xFFFFFFFF00000001
+TABLE_FIBONACCI = 0
+TABLE_MEMORY = 1
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc + OpenMP). Building the checker is not using it."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, env=env,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_u64p = C.POINTER(C.c_uint64)
+
+
+def _ptr(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_u64p)
+
+
+class Challenger(C.Structure):
+    _fields_ = [("state", C.c_uint64 * 12), ("inb", C.c_uint64 * 8), ("n_in", C.c_int),
+                ("out", C.c_uint64 * 8), ("n_out", C.c_int)]
+
+
+class _Batch(C.Structure):
+    _fields_ = [("n_cols", C.c_size_t), ("log_n", C.c_int), ("rate_bits", C.c_int), ("cap_height", C.c_int),
+                ("coeffs", _u64p), ("leaves", _u64p), ("digests", _u64p), ("cap", _u64p)]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        build()
+        L = C.CDLL(_LIB_PATH)
+    except (OSError, subprocess.CalledProcessError):
+        build(force=True)
+        L = C.CDLL(_LIB_PATH)
+    sz = C.c_size_t
+    L.orc_poseidon_constants.argtypes = [_u64p]
+    L.orc_poseidon_permute.argtypes = [_u64p]
+    L.orc_hash_no_pad.argtypes = [_u64p, sz, _u64p]
+    L.orc_hash_or_noop.argtypes = [_u64p, sz, _u64p]
+    L.orc_two_to_one.argtypes = [_u64p, _u64p, _u64p]
+    L.orc_challenger_init.argtypes = [C.POINTER(Challenger)]
+    L.orc_challenger_observe.argtypes = [C.POINTER(Challenger), _u64p, sz]
+    L.orc_challenger_get.argtypes = [C.POINTER(Challenger)]
+    L.orc_challenger_get.restype = C.c_uint64
+    for f in (L.orc_fft, L.orc_ifft):
+        f.argtypes = [_u64p, C.c_int]
+    for f in (L.orc_coset_fft, L.orc_coset_ifft):
+        f.argtypes = [_u64p, C.c_int, C.c_uint64]
+    L.orc_lde.argtypes = [_u64p, C.c_int, C.c_int, _u64p]
+    L.orc_merkle_new.argtypes = [_u64p, sz, sz, C.c_int, _u64p, _u64p]
+    L.orc_merkle_prove.argtypes = [_u64p, sz, C.c_int, sz, _u64p]
+    L.orc_merkle_verify.argtypes = [_u64p, sz, sz, _u64p, C.c_int, _u64p, C.c_int]
+    L.orc_merkle_verify.restype = C.c_int
+    for f in (L.orc_batch_from_values, L.orc_batch_from_coeffs):
+        f.argtypes = [_u64p, sz, C.c_int, C.c_int, C.c_int]
+        f.restype = C.POINTER(_Batch)
+    L.orc_batch_free.argtypes = [C.POINTER(_Batch)]
+    L.orc_batch_num_digests.argtypes = [C.POINTER(_Batch)]
+    L.orc_batch_num_digests.restype = sz
+    for f in (L.orc_table_num_columns, L.orc_table_constraint_degree, L.orc_table_num_public_inputs,
+              L.orc_table_uses_lookup):
+        f.argtypes = [C.c_int]
+        f.restype = C.c_int
+    L.orc_table_num_aux_columns.argtypes = [C.c_int, C.c_int]
+    L.orc_table_num_aux_columns.restype = C.c_int
+    L.orc_table_check_constraints.argtypes = [C.c_int, C.c_int, _u64p, _u64p]
+    L.orc_table_check_constraints.restype = C.c_long
+    L.orc_stark_proof_words.argtypes = [C.c_int, C.c_int]
+    L.orc_stark_proof_words.restype = sz
+    L.orc_stark_prove.argtypes = [C.c_int, C.c_int, _u64p, _u64p, _u64p]
+    L.orc_stark_prove.restype = C.c_int
+    L.orc_lookup_helper_columns.argtypes = [C.c_int, C.c_int, _u64p, _u64p, C.c_int, _u64p]
+    L.orc_compute_quotient_polys.argtypes = [C.c_int, C.c_int, C.POINTER(_Batch), C.POINTER(_Batch), _u64p,
+                                             _u64p, _u64p, C.c_int, _u64p]
+    L.orc_pow_grind.argtypes = [_u64p, C.c_int, C.c_int]
+    L.orc_pow_grind.restype = C.c_uint64
+    L.orc_fri_fold_coeffs.argtypes = [_u64p, sz, C.c_int, _u64p, _u64p]
+    L.orc_num_threads.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+# ---------------------------------------------------------------- thin numpy wrappers
+def poseidon_constants() -> np.ndarray:
+    out = np.zeros(360, dtype=np.uint64)
+    lib().orc_poseidon_constants(_ptr(out))
+    return out
+
+
+def poseidon_permute(state) -> np.ndarray:
+    s = _u64(state).copy()
+    assert s.shape == (12,)
+    lib().orc_poseidon_permute(_ptr(s))
+    return s
+
+
+def hash_no_pad(x) -> np.ndarray:
+    x = _u64(x).ravel()
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_hash_no_pad(_ptr(x) if x.size else None, x.size, _ptr(out))
+    return out
+
+
+def hash_or_noop(x) -> np.ndarray:
+    x = _u64(x).ravel()
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_hash_or_noop(_ptr(x) if x.size else None, x.size, _ptr(out))
+    return out
+
+
+def two_to_one(l, r) -> np.ndarray:
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_two_to_one(_ptr(_u64(l)), _ptr(_u64(r)), _ptr(out))
+    return out
+
+
+def fft(a) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().orc_fft(_ptr(a), int(a.size).bit_length() - 1)
+    return a
+
+
+def ifft(a) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().orc_ifft(_ptr(a), int(a.size).bit_length() - 1)
+    return a
+
+
+def coset_fft(a, shift=7) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().orc_coset_fft(_ptr(a), int(a.size).bit_length() - 1, shift)
+    return a
+
+
+def coset_ifft(a, shift=7) -> np.ndarray:
+    a = _u64(a).copy()
+    lib().orc_coset_ifft(_ptr(a), int(a.size).bit_length() - 1, shift)
+    return a
+
+
+def lde(coeffs, rate_bits) -> np.ndarray:
+    c = _u64(coeffs)
+    out = np.zeros(c.size << rate_bits, dtype=np.uint64)
+    lib().orc_lde(_ptr(c), int(c.size).bit_length() - 1, rate_bits, _ptr(out))
+    return out
+
+
+def merkle_new(leaves, cap_height):
+    """leaves: (n_leaves, leaf_len) -> (digests (nd,4) in plonky2 layout, cap (2^h,4))"""
+    lv = _u64(leaves)
+    n, ll = lv.shape
+    nd = 2 * (n - (1 << cap_height))
+    digests = np.zeros((max(nd, 1), 4), dtype=np.uint64)
+    cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+    lib().orc_merkle_new(_ptr(lv), n, ll, cap_height, _ptr(digests), _ptr(cap))
+    return digests[:nd], cap
+
+
+def merkle_prove(digests, n_leaves, cap_height, leaf_index) -> np.ndarray:
+    d = _u64(digests)
+    ns = (int(n_leaves).bit_length() - 1) - cap_height
+    sib = np.zeros((max(ns, 1), 4), dtype=np.uint64)
+    lib().orc_merkle_prove(_ptr(d) if d.size else None, n_leaves, cap_height, leaf_index, _ptr(sib))
+    return sib[:ns]
+
+
+def merkle_verify(leaf, leaf_index, siblings, cap) -> bool:
+    leaf = _u64(leaf).ravel()
+    sib = _u64(siblings).reshape(-1, 4)
+    cap = _u64(cap).reshape(-1, 4)
+    return bool(lib().orc_merkle_verify(_ptr(leaf) if leaf.size else None, leaf.size, leaf_index,
+                                        _ptr(sib) if sib.size else None, sib.shape[0], _ptr(cap),
+                                        int(cap.shape[0]).bit_length() - 1))
+
+
+class Batch:
+    """PolynomialBatch on the CPU (oracle)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        b = handle.contents
+        self.n_cols, self.log_n, self.rate_bits, self.cap_height = b.n_cols, b.log_n, b.rate_bits, b.cap_height
+
+    @classmethod
+    def from_values(cls, values, rate_bits, cap_height):
+        v = _u64(values)
+        c, n = v.shape
+        return cls(lib().orc_batch_from_values(_ptr(v), c, int(n).bit_length() - 1, rate_bits, cap_height))
+
+    @classmethod
+    def from_coeffs(cls, coeffs, rate_bits, cap_height):
+        v = _u64(coeffs)
+        c, n = v.shape
+        return cls(lib().orc_batch_from_coeffs(_ptr(v), c, int(n).bit_length() - 1, rate_bits, cap_height))
+
+    def _arr(self, p, shape):
+        n = int(np.prod(shape))
+        if n == 0:
+            return np.zeros(shape, dtype=np.uint64)
+        return np.ctypeslib.as_array(p, shape=(n,)).reshape(shape).copy()
+
+    @property
+    def coeffs(self):
+        return self._arr(self._h.contents.coeffs, (self.n_cols, 1 << self.log_n))
+
+    @property
+    def leaves(self):
+        return self._arr(self._h.contents.leaves, (1 << (self.log_n + self.rate_bits), self.n_cols))
+
+    @property
+    def digests(self):
+        return self._arr(self._h.contents.digests, (lib().orc_batch_num_digests(self._h), 4))
+
+    @property
+    def cap(self):
+        return self._arr(self._h.contents.cap, (1 << self.cap_height, 4))
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and _lib is not None:
+            _lib.orc_batch_free(self._h)
+            self._h = None
+
+
+def check_constraints(table, trace, public_inputs=()) -> int:
+    t = _u64(trace)
+    pi = _u64(list(public_inputs) + [0])
+    return int(lib().orc_table_check_constraints(table, int(t.shape[1]).bit_length() - 1, _ptr(t), _ptr(pi)))
+
+
+def stark_prove(table, trace, public_inputs=()) -> np.ndarray:
+    t = _u64(trace)
+    log_n = int(t.shape[1]).bit_length() - 1
+    pi = _u64(list(public_inputs) + [0])
+    out = np.zeros(lib().orc_stark_proof_words(table, log_n), dtype=np.uint64)
+    rc = lib().orc_stark_prove(table, log_n, _ptr(t), _ptr(pi), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle stark_prove failed rc={rc}")
+    return out
+
+
+def lookup_helper_columns(table, trace, challenges) -> np.ndarray:
+    t = _u64(trace)
+    ch = _u64(challenges)
+    na = lib().orc_table_num_aux_columns(table, ch.size)
+    aux = np.zeros((na, t.shape[1]), dtype=np.uint64)
+    lib().orc_lookup_helper_columns(table, int(t.shape[1]).bit_length() - 1, _ptr(t), _ptr(ch), ch.size, _ptr(aux))
+    return aux
+
+
+def compute_quotient_polys(table, trace_batch: Batch, aux_batch, lookup_challenges, public_inputs, alphas):
+    L = lib()
+    deg = L.orc_table_constraint_degree(table)
+    factor = max(1, deg - 1)
+    al = _u64(alphas)
+    out = np.zeros((factor * al.size, 1 << trace_batch.log_n), dtype=np.uint64)
+    lc = _u64(list(lookup_challenges) + [0, 0])
+    pi = _u64(list(public_inputs) + [0])
+    L.orc_compute_quotient_polys(table, trace_batch.log_n, trace_batch._h, aux_batch._h if aux_batch else None,
+                                 _ptr(lc), _ptr(pi), _ptr(al), al.size, _ptr(out))
+    return out
+
+
+def pow_grind(state, pos, bits) -> int:
+    return int(lib().orc_pow_grind(_ptr(_u64(state)), pos, bits))
+
+
+def fri_fold_coeffs(coeffs, arity_bits, beta) -> np.ndarray:
+    c = _u64(coeffs).reshape(-1, 2)
+    out = np.zeros((c.shape[0] >> arity_bits, 2), dtype=np.uint64)
+    lib().orc_fri_fold_coeffs(_ptr(c), c.shape[0], arity_bits, _ptr(_u64(beta)), _ptr(out))
+    return out
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())

@@ -1,0 +1,168 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY (see goldilocks.h header).
+ *
+ * Poseidon-12 over Goldilocks as used by PoseidonGoldilocksConfig, the sponge helpers and the
+ * Fiat-Shamir Challenger.  Restates (plonky2 0.2.2, /root/reference/Cargo.lock:3441-3445; not on disk):
+ *   plonky2/src/hash/poseidon.rs            Poseidon trait: 4 + 22 + 4 rounds, x^7, circulant MDS
+ *   plonky2/src/hash/poseidon_goldilocks.rs MDS_MATRIX_CIRC / DIAG, ALL_ROUND_CONSTANTS, test_vectors
+ *   plonky2/src/hash/hashing.rs             hash_n_to_m_no_pad (overwrite mode, no padding), compress
+ *   plonky2/src/iop/challenger.rs           Challenger (duplex sponge, pop-from-end)
+ * Reference call site that reaches them: /root/reference/ops/src/lib.rs:52.
+ *
+ * PINNING: the 360 round constants are re-derived from ChaCha8Rng::seed_from_u64(0) (rand 0.8.5 /
+ * rand_chacha 0.3.1, /root/reference/Cargo.lock:3687-3712) and checked against the SHA-256 recorded
+ * in SURVEY.md section 8(c) (tests/golden/poseidon_kat.json); the permutation is checked against the
+ * three upstream known-answer vectors (poseidon_goldilocks.rs test_vectors).  The NAIVE round
+ * structure is used here on purpose: it is the definition, the upstream "fast" partial rounds are an
+ * algebraic refactoring with identical output.
+ */
+#include "oracle.h"
+#include <string.h>
+
+static uint64_t RC[360];
+static int rc_ready = 0;
+static const uint64_t MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+static const uint64_t MDS_DIAG[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+/* ---- ChaCha8Rng::seed_from_u64(0) + gen_range(0..p), rand 0.8.5 semantics ---- */
+static inline uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+#define QR(a, b, c, d) \
+  a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); \
+  a += b; d ^= a; d = rotl32(d, 8);  c += d; b ^= c; b = rotl32(b, 7);
+static void chacha8_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+  uint32_t s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574, key[0], key[1], key[2], key[3],
+                    key[4], key[5], key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32), 0, 0};
+  uint32_t x[16];
+  memcpy(x, s, sizeof x);
+  for (int i = 0; i < 4; i++) { /* 8 rounds = 4 double rounds */
+    QR(x[0], x[4], x[8], x[12]) QR(x[1], x[5], x[9], x[13]) QR(x[2], x[6], x[10], x[14]) QR(x[3], x[7], x[11], x[15])
+    QR(x[0], x[5], x[10], x[15]) QR(x[1], x[6], x[11], x[12]) QR(x[2], x[7], x[8], x[13]) QR(x[3], x[4], x[9], x[14])
+  }
+  for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
+}
+typedef struct { uint32_t key[8]; uint64_t ctr; uint32_t buf[16]; int idx; } chacha8_rng;
+static void rng_seed_from_u64(chacha8_rng *r, uint64_t state) {
+  /* rand_core 0.6 SeedableRng::seed_from_u64: PCG32 expands the u64 into the 32-byte key */
+  const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
+  for (int i = 0; i < 8; i++) {
+    state = state * MUL + INC;
+    uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+    uint32_t rot = (uint32_t)(state >> 59);
+    r->key[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+  }
+  r->ctr = 0; r->idx = 16;
+}
+static uint32_t rng_next_u32(chacha8_rng *r) {
+  if (r->idx == 16) { chacha8_block(r->key, r->ctr++, r->buf); r->idx = 0; }
+  return r->buf[r->idx++];
+}
+static uint64_t rng_next_u64(chacha8_rng *r) {
+  uint64_t lo = rng_next_u32(r), hi = rng_next_u32(r);
+  return lo | (hi << 32);
+}
+static uint64_t rng_gen_range_p(chacha8_rng *r) {
+  /* UniformInt<u64>::sample_single_inclusive(0, p-1): range = p, zone = (p << lz(p)) - 1 = p - 1 */
+  const uint64_t zone = GL_P - 1;
+  for (;;) {
+    uint64_t v = rng_next_u64(r);
+    __uint128_t m = (__uint128_t)v * GL_P;
+    uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+    if (lo <= zone) return hi;
+  }
+}
+static void ensure_rc(void) {
+  if (__atomic_load_n(&rc_ready, __ATOMIC_ACQUIRE)) return;
+#pragma omp critical(orc_rc)
+  if (!rc_ready) {
+    chacha8_rng r;
+    rng_seed_from_u64(&r, 0);
+    for (int i = 0; i < 360; i++) RC[i] = rng_gen_range_p(&r);
+    __atomic_store_n(&rc_ready, 1, __ATOMIC_RELEASE);
+  }
+}
+void orc_poseidon_constants(uint64_t out[360]) { ensure_rc(); memcpy(out, RC, sizeof RC); }
+
+/* ---- permutation (naive definition) ---- */
+static inline uint64_t sbox7(uint64_t x) {
+  uint64_t x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x, x2);
+  return gl_mul(x3, x4);
+}
+static inline void mds_layer(uint64_t s[12]) {
+  uint64_t o[12];
+  for (int r = 0; r < 12; r++) {
+    /* mds_row_shf: sum_i s[(i+r)%12]*CIRC[i] + s[r]*DIAG[r]; 12 * 2^64 * 41 + ... < 2^74 fits u128 */
+    __uint128_t acc = 0;
+    for (int i = 0; i < 12; i++) acc += (__uint128_t)s[(i + r) % 12] * MDS_CIRC[i];
+    acc += (__uint128_t)s[r] * MDS_DIAG[r];
+    o[r] = gl_reduce128(acc);
+  }
+  memcpy(s, o, sizeof o);
+}
+void orc_poseidon_permute(uint64_t s[12]) {
+  ensure_rc();
+  int rc = 0;
+  for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], RC[rc++]));
+    mds_layer(s);
+  }
+  for (int r = 0; r < 22; r++) {
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], RC[rc++]);
+    s[0] = sbox7(s[0]);
+    mds_layer(s);
+  }
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], RC[rc++]));
+    mds_layer(s);
+  }
+}
+
+/* hash_n_to_m_no_pad with m = 4: zero state, overwrite rate lanes chunk by chunk, permute each chunk */
+void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
+  uint64_t st[12] = {0};
+  for (size_t off = 0; off < n; off += 8) {
+    size_t len = n - off < 8 ? n - off : 8;
+    for (size_t i = 0; i < len; i++) st[i] = gl_canon(in[off + i]);
+    orc_poseidon_permute(st);
+  }
+  memcpy(out, st, 4 * sizeof(uint64_t));
+}
+/* PoseidonHash::hash_or_noop: inputs of <= 4 elements are copied and zero padded, not hashed */
+void orc_hash_or_noop(const uint64_t *in, size_t n, uint64_t out[4]) {
+  if (n <= 4) {
+    for (size_t i = 0; i < 4; i++) out[i] = i < n ? gl_canon(in[i]) : 0;
+  } else {
+    orc_hash_no_pad(in, n, out);
+  }
+}
+/* PoseidonHash::two_to_one = compress(l, r): state = l || r || 0000 */
+void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
+  uint64_t st[12] = {0};
+  for (int i = 0; i < 4; i++) { st[i] = gl_canon(l[i]); st[4 + i] = gl_canon(r[i]); }
+  orc_poseidon_permute(st);
+  memcpy(out, st, 4 * sizeof(uint64_t));
+}
+
+/* ---- Challenger (plonky2/src/iop/challenger.rs) ---- */
+void orc_challenger_init(orc_challenger *c) { memset(c, 0, sizeof *c); }
+static void duplexing(orc_challenger *c) {
+  for (int i = 0; i < c->n_in; i++) c->state[i] = c->in[i];
+  c->n_in = 0;
+  orc_poseidon_permute(c->state);
+  memcpy(c->out, c->state, 8 * sizeof(uint64_t));
+  c->n_out = 8;
+}
+void orc_challenger_observe(orc_challenger *c, const uint64_t *e, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    c->n_out = 0; /* any buffered outputs are now invalid */
+    c->in[c->n_in++] = gl_canon(e[i]);
+    if (c->n_in == 8) duplexing(c);
+  }
+}
+uint64_t orc_challenger_get(orc_challenger *c) {
+  if (c->n_in != 0 || c->n_out == 0) duplexing(c);
+  return c->out[--c->n_out]; /* pop from the END of the output buffer */
+}
+void orc_challenger_get_n(orc_challenger *c, size_t n, uint64_t *out) {
+  for (size_t i = 0; i < n; i++) out[i] = orc_challenger_get(c);
+}
