@@ -1,0 +1,397 @@
+"""ctypes binding of ``libetp_b200.so`` shaped like plonky2's operator surface.
+
+Mirrors (names, argument meaning, panics -> ``EtpError``):
+  plonky2::fri::oracle::PolynomialBatch::{from_values, from_coeffs, get_lde_values}, .polynomials,
+      .merkle_tree.{leaves, digests, cap, prove}
+  plonky2::hash::merkle_tree::MerkleTree::{new, prove}
+  starky::prover::{prove, compute_quotient_polys}, starky::lookup::lookup_helper_columns
+(plonky2 0.2.2 / starky 0.4.0, /root/reference/Cargo.lock:3441,4529; reached from the reference's
+worker at /root/reference/ops/src/lib.rs:52).  numpy arrays are host memory; ``torch`` CUDA tensors
+(int64 storage viewed as u64) can be passed to the ``*_dev`` variants by their ``data_ptr()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+TABLE_FIBONACCI = 0
+TABLE_MEMORY = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_u64p = C.POINTER(C.c_uint64)
+
+
+class EtpError(RuntimeError):
+    """A failed library call (upstream: panic / FatalError at /root/reference/ops/src/lib.rs:52)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"etp_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libetp_b200.so")
+
+
+def load_library():
+    """Loads the CUDA library. Fails loudly: there is no CPU or PyTorch fallback for this path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EtpError(-2, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). The CUDA extension is the only implementation of this path.")
+    L = C.CDLL(path)
+    sz, vp, i32 = C.c_size_t, C.c_void_p, C.c_int
+    pp = C.POINTER(vp)
+    sig = {
+        "etp_version": (C.c_char_p, []),
+        "etp_device_count": (i32, []),
+        "etp_ctx_create": (i32, [i32, pp]),
+        "etp_ctx_destroy": (None, [vp]),
+        "etp_last_error": (C.c_char_p, [vp]),
+        "etp_ctx_synchronize": (i32, [vp]),
+        "etp_ctx_stream": (vp, [vp]),
+        "etp_ctx_launch_count": (C.c_uint64, [vp]),
+        "etp_dev_alloc": (i32, [vp, sz, pp]),
+        "etp_dev_free": (i32, [vp, vp]),
+        "etp_dev_upload": (i32, [vp, vp, vp, sz]),
+        "etp_dev_download": (i32, [vp, vp, vp, sz]),
+        "etp_poseidon_permute_host": (i32, [vp, _u64p, sz]),
+        "etp_ifft_host": (i32, [vp, _u64p, sz, i32]),
+        "etp_fft_host": (i32, [vp, _u64p, sz, i32]),
+        "etp_coset_lde_host": (i32, [vp, _u64p, sz, i32, i32, C.c_uint64, _u64p]),
+        "etp_coset_ifft_host": (i32, [vp, _u64p, sz, i32, C.c_uint64]),
+        "etp_merkle_new_host": (i32, [vp, _u64p, sz, sz, i32, pp]),
+        "etp_tree_free": (None, [vp]),
+        "etp_tree_num_digests": (sz, [vp]),
+        "etp_tree_cap": (i32, [vp, _u64p]),
+        "etp_tree_digests": (i32, [vp, _u64p]),
+        "etp_tree_prove": (i32, [vp, sz, _u64p]),
+        "etp_batch_from_values_host": (i32, [vp, C.POINTER(_u64p), sz, i32, i32, i32, i32, pp]),
+        "etp_batch_from_coeffs_host": (i32, [vp, C.POINTER(_u64p), sz, i32, i32, i32, i32, pp]),
+        "etp_batch_from_values_dev": (i32, [vp, vp, sz, sz, i32, i32, i32, i32, pp]),
+        "etp_batch_from_coeffs_dev": (i32, [vp, vp, sz, sz, i32, i32, i32, i32, pp]),
+        "etp_batch_recommit_values_dev": (i32, [vp, vp, sz]),
+        "etp_batch_free": (None, [vp]),
+        "etp_batch_num_cols": (sz, [vp]),
+        "etp_batch_degree_log": (i32, [vp]),
+        "etp_batch_num_digests": (sz, [vp]),
+        "etp_batch_cap": (i32, [vp, _u64p]),
+        "etp_batch_download_coeffs": (i32, [vp, _u64p]),
+        "etp_batch_download_leaves": (i32, [vp, _u64p]),
+        "etp_batch_download_digests": (i32, [vp, _u64p]),
+        "etp_batch_leaves_at": (i32, [vp, _u64p, sz, _u64p]),
+        "etp_batch_get_lde_values": (i32, [vp, sz, sz, _u64p]),
+        "etp_batch_prove": (i32, [vp, sz, _u64p]),
+        "etp_batch_lde_dev": (vp, [vp, C.POINTER(sz)]),
+        "etp_batch_coeffs_dev": (vp, [vp, C.POINTER(sz)]),
+        "etp_table_num_columns": (i32, [i32]),
+        "etp_table_constraint_degree": (i32, [i32]),
+        "etp_table_num_public_inputs": (i32, [i32]),
+        "etp_table_num_aux_columns": (i32, [i32, i32]),
+        "etp_table_quotient_degree_factor": (i32, [i32]),
+        "etp_lookup_helper_columns_dev": (i32, [vp, i32, i32, vp, sz, _u64p, i32, vp]),
+        "etp_compute_quotient_polys_dev": (i32, [vp, i32, vp, vp, _u64p, i32, _u64p, _u64p, i32, vp]),
+        "etp_pow_grind": (i32, [vp, _u64p, i32, i32, _u64p]),
+        "etp_stark_proof_words": (sz, [i32, i32]),
+        "etp_stark_prove_host": (i32, [vp, i32, i32, _u64p, _u64p, _u64p]),
+        "etp_stark_prove_dev": (i32, [vp, i32, i32, vp, sz, _u64p, _u64p]),
+        "etp_last_prove_timings": (i32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    L._etp_signatures = sig
+    return L
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"], "need a C-contiguous uint64 array"
+    return a.ctypes.data_as(_u64p)
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+class Context:
+    """One CUDA device + stream + scratch pools (one per worker thread / Paladin worker)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.etp_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise EtpError(rc, f"etp_ctx_create(device={device}) failed: no usable CUDA device "
+                               f"(devices visible: {self.L.etp_device_count()}); there is no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise EtpError(rc, self.L.etp_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.etp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.check(self.L.etp_ctx_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.etp_ctx_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.etp_ctx_launch_count(self.h))
+
+    # ---- primitives (parity tests)
+    def poseidon_permute(self, states) -> np.ndarray:
+        s = _u64(states).reshape(-1, 12).copy()
+        self.check(self.L.etp_poseidon_permute_host(self.h, _p(s), s.shape[0]))
+        return s
+
+    def ifft(self, cols) -> np.ndarray:
+        a = np.atleast_2d(_u64(cols)).copy()
+        self.check(self.L.etp_ifft_host(self.h, _p(a), a.shape[0], int(a.shape[1]).bit_length() - 1))
+        return a
+
+    def fft(self, cols) -> np.ndarray:
+        a = np.atleast_2d(_u64(cols)).copy()
+        self.check(self.L.etp_fft_host(self.h, _p(a), a.shape[0], int(a.shape[1]).bit_length() - 1))
+        return a
+
+    def coset_lde(self, coeffs, rate_bits, shift=7) -> np.ndarray:
+        a = np.atleast_2d(_u64(coeffs))
+        out = np.zeros((a.shape[0], a.shape[1] << rate_bits), dtype=np.uint64)
+        self.check(self.L.etp_coset_lde_host(self.h, _p(a), a.shape[0], int(a.shape[1]).bit_length() - 1, rate_bits,
+                                             shift, _p(out)))
+        return out
+
+    def coset_ifft(self, cols, shift=7) -> np.ndarray:
+        a = np.atleast_2d(_u64(cols)).copy()
+        self.check(self.L.etp_coset_ifft_host(self.h, _p(a), a.shape[0], int(a.shape[1]).bit_length() - 1, shift))
+        return a
+
+    def pow_grind(self, state, pos, bits) -> int:
+        out = C.c_uint64()
+        self.check(self.L.etp_pow_grind(self.h, _p(_u64(state)), pos, bits, C.byref(out)))
+        return int(out.value)
+
+    # ---- starky
+    def stark_proof_words(self, table, log_n) -> int:
+        return int(self.L.etp_stark_proof_words(table, log_n))
+
+    def stark_prove(self, table, trace, public_inputs=()) -> np.ndarray:
+        """starky::prover::prove(stark, &StarkConfig::standard_fast_config(), trace, public_inputs)."""
+        t = _u64(trace)
+        log_n = int(t.shape[1]).bit_length() - 1
+        pi = _u64(list(public_inputs) + [0])
+        out = np.zeros(self.stark_proof_words(table, log_n), dtype=np.uint64)
+        self.check(self.L.etp_stark_prove_host(self.h, table, log_n, _p(t), _p(pi), _p(out)))
+        return out
+
+    def stark_prove_dev(self, table, log_n, trace_ptr, col_stride, public_inputs=()) -> np.ndarray:
+        pi = _u64(list(public_inputs) + [0])
+        out = np.zeros(self.stark_proof_words(table, log_n), dtype=np.uint64)
+        self.check(self.L.etp_stark_prove_dev(self.h, table, log_n, C.c_void_p(trace_ptr), col_stride, _p(pi), _p(out)))
+        return out
+
+    def last_prove_timings(self) -> dict:
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = self.L.etp_last_prove_timings(self.h, names, ms, 32)
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    def lookup_helper_columns_dev(self, table, log_n, trace_ptr, col_stride, challenges, aux_ptr):
+        ch = _u64(challenges)
+        self.check(self.L.etp_lookup_helper_columns_dev(self.h, table, log_n, C.c_void_p(trace_ptr), col_stride, _p(ch),
+                                                        ch.size, C.c_void_p(aux_ptr)))
+
+    def compute_quotient_polys(self, table, trace_batch, aux_batch, lookup_challenges, public_inputs, alphas) -> np.ndarray:
+        """starky::prover::compute_quotient_polys -> quotient chunks (factor * n_alphas, n), host copy."""
+        al = _u64(alphas)
+        lc = _u64(list(lookup_challenges) + [0])
+        pi = _u64(list(public_inputs) + [0])
+        factor = self.L.etp_table_quotient_degree_factor(table)
+        n = 1 << trace_batch.degree_log
+        out = np.zeros((factor * al.size, n), dtype=np.uint64)
+        d = C.c_void_p()
+        self.check(self.L.etp_dev_alloc(self.h, out.nbytes, C.byref(d)))
+        try:
+            self.check(self.L.etp_compute_quotient_polys_dev(self.h, table, trace_batch.h, aux_batch.h if aux_batch else None,
+                                                             _p(lc), len(lookup_challenges), _p(pi), _p(al), al.size, d))
+            self.check(self.L.etp_dev_download(self.h, out.ctypes.data_as(C.c_void_p), d, out.nbytes))
+        finally:
+            self.L.etp_dev_free(self.h, d)
+        return out
+
+
+class MerkleTree:
+    """plonky2::hash::merkle_tree::MerkleTree<GoldilocksField, PoseidonHash>."""
+
+    def __init__(self, ctx: Context, handle, n_leaves, cap_height):
+        self.ctx, self.h, self.n_leaves, self.cap_height = ctx, handle, n_leaves, cap_height
+
+    @classmethod
+    def new(cls, ctx: Context, leaves, cap_height: int) -> "MerkleTree":
+        lv = _u64(leaves)
+        assert lv.ndim == 2
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_merkle_new_host(ctx.h, _p(lv) if lv.size else None, lv.shape[0], lv.shape[1], cap_height,
+                                            C.byref(h)))
+        return cls(ctx, h, lv.shape[0], cap_height)
+
+    @property
+    def cap(self) -> np.ndarray:
+        out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_tree_cap(self.h, _p(out)))
+        return out
+
+    @property
+    def digests(self) -> np.ndarray:
+        nd = int(self.ctx.L.etp_tree_num_digests(self.h))
+        out = np.zeros((max(nd, 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_tree_digests(self.h, _p(out)))
+        return out[:nd]
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        ns = (int(self.n_leaves).bit_length() - 1) - self.cap_height
+        out = np.zeros((max(ns, 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_tree_prove(self.h, leaf_index, _p(out)))
+        return out[:ns]
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.etp_tree_free(self.h)
+            self.h = None
+
+
+class PolynomialBatch:
+    """plonky2::fri::oracle::PolynomialBatch<GoldilocksField, PoseidonGoldilocksConfig, 2>, device resident.
+
+    The public fields of the upstream struct are lazy host views here: ``polynomials`` (coefficients),
+    ``leaves`` / ``digests`` / ``cap`` of ``merkle_tree``.
+    """
+
+    def __init__(self, ctx: Context, handle, n_cols, log_n, rate_bits, cap_height):
+        self.ctx, self.h = ctx, handle
+        self.n_cols, self.degree_log, self.rate_bits, self.cap_height = n_cols, log_n, rate_bits, cap_height
+
+    @staticmethod
+    def _cols(a):
+        a = _u64(a)
+        assert a.ndim == 2
+        ptrs = (_u64p * max(a.shape[0], 1))()
+        for c in range(a.shape[0]):
+            ptrs[c] = a[c].ctypes.data_as(_u64p)
+        return a, ptrs
+
+    @classmethod
+    def from_values(cls, ctx: Context, values, rate_bits: int, blinding: bool, cap_height: int) -> "PolynomialBatch":
+        a, ptrs = cls._cols(values)
+        log_n = int(a.shape[1]).bit_length() - 1
+        assert a.shape[1] == 1 << log_n
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_batch_from_values_host(ctx.h, ptrs, a.shape[0], log_n, rate_bits, int(blinding), cap_height,
+                                                   C.byref(h)))
+        return cls(ctx, h, a.shape[0], log_n, rate_bits, cap_height)
+
+    @classmethod
+    def from_coeffs(cls, ctx: Context, coeffs, rate_bits: int, blinding: bool, cap_height: int) -> "PolynomialBatch":
+        a, ptrs = cls._cols(coeffs)
+        log_n = int(a.shape[1]).bit_length() - 1
+        assert a.shape[1] == 1 << log_n
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_batch_from_coeffs_host(ctx.h, ptrs, a.shape[0], log_n, rate_bits, int(blinding), cap_height,
+                                                   C.byref(h)))
+        return cls(ctx, h, a.shape[0], log_n, rate_bits, cap_height)
+
+    @classmethod
+    def from_values_dev(cls, ctx: Context, ptr: int, col_stride: int, n_cols: int, log_n: int, rate_bits: int,
+                        blinding: bool, cap_height: int) -> "PolynomialBatch":
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_batch_from_values_dev(ctx.h, C.c_void_p(ptr), col_stride, n_cols, log_n, rate_bits,
+                                                  int(blinding), cap_height, C.byref(h)))
+        return cls(ctx, h, n_cols, log_n, rate_bits, cap_height)
+
+    @classmethod
+    def from_coeffs_dev(cls, ctx: Context, ptr: int, col_stride: int, n_cols: int, log_n: int, rate_bits: int,
+                        blinding: bool, cap_height: int) -> "PolynomialBatch":
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_batch_from_coeffs_dev(ctx.h, C.c_void_p(ptr), col_stride, n_cols, log_n, rate_bits,
+                                                  int(blinding), cap_height, C.byref(h)))
+        return cls(ctx, h, n_cols, log_n, rate_bits, cap_height)
+
+    def recommit_values_dev(self, ptr: int, col_stride: int):
+        self.ctx.check(self.ctx.L.etp_batch_recommit_values_dev(self.h, C.c_void_p(ptr), col_stride))
+
+    @property
+    def n(self):
+        return 1 << self.degree_log
+
+    @property
+    def lde_n(self):
+        return 1 << (self.degree_log + self.rate_bits)
+
+    @property
+    def cap(self) -> np.ndarray:
+        out = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_cap(self.h, _p(out)))
+        return out
+
+    @property
+    def polynomials(self) -> np.ndarray:
+        out = np.zeros((self.n_cols, self.n), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_download_coeffs(self.h, _p(out)))
+        return out
+
+    @property
+    def leaves(self) -> np.ndarray:
+        out = np.zeros((self.lde_n, self.n_cols), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_download_leaves(self.h, _p(out)))
+        return out
+
+    @property
+    def digests(self) -> np.ndarray:
+        nd = int(self.ctx.L.etp_batch_num_digests(self.h))
+        out = np.zeros((max(nd, 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_download_digests(self.h, _p(out)))
+        return out[:nd]
+
+    def leaves_at(self, idx) -> np.ndarray:
+        idx = _u64(idx).ravel()
+        out = np.zeros((idx.size, max(self.n_cols, 1)), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_leaves_at(self.h, _p(idx), idx.size, _p(out)))
+        return out[:, :self.n_cols]
+
+    def get_lde_values(self, index: int, step: int) -> np.ndarray:
+        out = np.zeros(max(self.n_cols, 1), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_get_lde_values(self.h, index, step, _p(out)))
+        return out[:self.n_cols]
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        ns = self.degree_log + self.rate_bits - self.cap_height
+        out = np.zeros((max(ns, 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_prove(self.h, leaf_index, _p(out)))
+        return out[:ns]
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.etp_batch_free(self.h)
+            self.h = None

@@ -1,0 +1,153 @@
+// Context, error plumbing, power tables and the NTT / Merkle host drivers shared by the C ABI files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/etp_b200.h"
+#include "gl.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+struct DevPowTable {
+  uint64_t* lo = nullptr;
+  uint64_t* hi = nullptr;
+  int lo_bits = 0;
+};
+
+struct etp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  // (base, bits, scale) -> device tables
+  std::map<std::tuple<uint64_t, int, uint64_t>, DevPowTable> pow_tables;
+  // last prove timings
+  std::vector<std::pair<const char*, float>> timings;
+  uint64_t* d_pow_result = nullptr;  // PoW grind result slot
+};
+
+inline int etp_fail(etp_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define ETP_CUDA(ctx, call)                                                                                  \
+  do {                                                                                                       \
+    cudaError_t e__ = (call);                                                                                \
+    if (e__ != cudaSuccess)                                                                                  \
+      return etp_fail((ctx), ETP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                      __LINE__);                                                                             \
+  } while (0)
+#define ETP_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != ETP_OK) return rc__; \
+  } while (0)
+#define ETP_LAUNCH_CHECK(ctx)    \
+  do {                           \
+    (ctx)->launches++;           \
+    ETP_CUDA((ctx), cudaGetLastError()); \
+  } while (0)
+
+inline int dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 8;
+  ETP_CUDA(ctx, cudaSetDevice(ctx->device));
+  ETP_CUDA(ctx, cudaMallocAsync(out, bytes, ctx->stream));
+  return ETP_OK;
+}
+inline void dev_free(etp_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+template <class T>
+struct DevBuf {  // RAII scratch on the context's stream-ordered pool
+  etp_ctx* ctx;
+  T* p = nullptr;
+  explicit DevBuf(etp_ctx* c) : ctx(c) {}
+  int alloc(size_t n) { return dev_alloc(ctx, n * sizeof(T), (void**)&p); }
+  ~DevBuf() { dev_free(ctx, p); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// ---- power tables --------------------------------------------------------------------------------
+// lookup(e) = scale * base^e for e < 2^bits
+int get_pow_table(etp_ctx* ctx, uint64_t base, int bits, uint64_t scale, ntt::PowTable* out);
+
+// ---- NTT driver ------------------------------------------------------------------------------------
+struct NttArgs {
+  const uint64_t* in = nullptr;
+  size_t in_stride = 0;
+  uint32_t n_in = 0;           // number of (non-zero) inputs, <= 2^log_n
+  uint64_t* out = nullptr;
+  size_t out_stride = 0;
+  uint64_t* scratch = nullptr; // needed when natural_out and more than one pass (size n_cols x 2^log_n)
+  size_t scratch_stride = 0;
+  int log_n = 0;
+  size_t n_cols = 0;
+  bool inverse = false;
+  bool natural_out = false;    // false: position p holds out[bitrev(p)]
+  uint64_t coset_shift = 0;    // 0: plain; forward: in[j] *= shift^j; inverse: out[k] *= shift^-k
+};
+int ntt_num_passes(int log_n);
+int ntt_run(etp_ctx* ctx, const NttArgs& a);
+
+// ---- Merkle driver -----------------------------------------------------------------------------------
+inline size_t levels_words(size_t n_leaves, int cap_height) {
+  size_t w = 0;
+  for (size_t n = n_leaves; n >= ((size_t)1 << cap_height); n >>= 1) { w += 4 * n; if (n == 1) break; }
+  return w;
+}
+inline size_t level_offset(size_t n_leaves, int level) {
+  size_t w = 0;
+  for (int i = 0; i < level; i++) w += 4 * (n_leaves >> i);
+  return w;
+}
+// levels[0] must already hold the leaf digests; hashes up to the cap level and copies the cap to host
+int merkle_build_levels(etp_ctx* ctx, uint64_t* levels, size_t n_leaves, int cap_height, uint64_t* cap_host);
+int merkle_prove_from_levels(etp_ctx* ctx, const uint64_t* levels, size_t n_leaves, int cap_height, size_t leaf_index,
+                             uint64_t* siblings_out_host);
+int merkle_download_digests(etp_ctx* ctx, const uint64_t* levels, size_t n_leaves, int cap_height, uint64_t* out_host);
+
+inline int log2_exact(size_t n) {
+  if (n == 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+
+struct etp_tree {
+  etp_ctx* ctx;
+  size_t n_leaves, leaf_len;
+  int cap_height;
+  uint64_t* levels = nullptr;
+  std::vector<uint64_t> cap;
+};
+
+struct etp_batch {
+  etp_ctx* ctx;
+  size_t n_cols;
+  int log_n, rate_bits, cap_height;
+  uint64_t* coeffs = nullptr;  // n_cols x n
+  uint64_t* lde = nullptr;     // n_cols x (n << rate_bits), bit-reversed row order
+  uint64_t* levels = nullptr;
+  std::vector<uint64_t> cap;
+  size_t n() const { return (size_t)1 << log_n; }
+  size_t lde_n() const { return (size_t)1 << (log_n + rate_bits); }
+};
+int batch_create(etp_ctx* ctx, size_t n_cols, int log_n, int rate_bits, int blinding, int cap_height, etp_batch** out);
+// coeffs already in b->coeffs: LDE + leaf hashing + tree
+int batch_commit_from_coeffs(etp_batch* b);
+// values (device, natural order) -> coeffs -> commit
+int batch_commit_from_values(etp_batch* b, const uint64_t* values_dev, size_t col_stride);

@@ -1,0 +1,597 @@
+// libetp_b200: context, transforms, Merkle trees and PolynomialBatch behind the C ABI of
+// include/etp_b200.h.  See that header for the upstream plonky2 item each entry point replaces
+// (plonky2/src/fri/oracle.rs, hash/merkle_tree.rs, field/src/fft.rs; reached from
+// /root/reference/ops/src/lib.rs:52).  Product code: no oracle, no CPU fallback.
+#include "ctx.cuh"
+
+// =================================================================================================
+// context
+// =================================================================================================
+extern "C" const char* etp_version(void) { return "etp_b200 0.1 (sm_100a)"; }
+
+extern "C" int etp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int etp_ctx_create(int device, etp_ctx** out) {
+  if (!out) return ETP_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return ETP_ERR_CUDA;
+  etp_ctx* ctx = new etp_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return ETP_ERR_CUDA;
+  }
+  // keep freed blocks in the stream-ordered pool: repeated commits of the same shape do not re-allocate
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaFuncSetAttribute(ntt::pass_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(ntt::pass_last, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (cudaMalloc((void**)&ctx->d_pow_result, 16) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ETP_ERR_CUDA;
+  }
+  *out = ctx;
+  return ETP_OK;
+}
+
+extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+  cudaFree(ctx->d_pow_result);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* etp_last_error(const etp_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" int etp_ctx_synchronize(etp_ctx* ctx) {
+  if (!ctx) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+extern "C" void* etp_ctx_stream(etp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t etp_ctx_launch_count(const etp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int etp_dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaSetDevice(ctx->device));
+  ETP_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 8));
+  return ETP_OK;
+}
+extern "C" int etp_dev_free(etp_ctx* ctx, void* ptr) {
+  if (!ctx) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ETP_CUDA(ctx, cudaFree(ptr));
+  return ETP_OK;
+}
+extern "C" int etp_dev_upload(etp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+extern "C" int etp_dev_download(etp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+// =================================================================================================
+// power tables
+// =================================================================================================
+int get_pow_table(etp_ctx* ctx, uint64_t base, int bits, uint64_t scale, ntt::PowTable* out) {
+  auto key = std::make_tuple(base, bits, scale);
+  auto it = ctx->pow_tables.find(key);
+  if (it == ctx->pow_tables.end()) {
+    DevPowTable t;
+    t.lo_bits = (bits + 1) / 2;
+    const size_t n_lo = (size_t)1 << t.lo_bits, n_hi = (size_t)1 << (bits - t.lo_bits);
+    std::vector<uint64_t> lo(n_lo), hi(n_hi);
+    uint64_t cur = 1;
+    for (size_t i = 0; i < n_lo; i++) { lo[i] = gl::canon(cur); cur = gl::mul(cur, base); }
+    const uint64_t step = gl::canon(cur);  // base^(2^lo_bits)
+    cur = gl::canon(scale);
+    for (size_t i = 0; i < n_hi; i++) { hi[i] = gl::canon(cur); cur = gl::mul(cur, step); }
+    ETP_CUDA(ctx, cudaMalloc((void**)&t.lo, n_lo * 8));
+    ETP_CUDA(ctx, cudaMalloc((void**)&t.hi, n_hi * 8));
+    ETP_CUDA(ctx, cudaMemcpyAsync(t.lo, lo.data(), n_lo * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaMemcpyAsync(t.hi, hi.data(), n_hi * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die here
+    it = ctx->pow_tables.emplace(key, t).first;
+  }
+  out->lo = it->second.lo;
+  out->hi = it->second.hi;
+  out->lo_bits = it->second.lo_bits;
+  out->mask = (1u << it->second.lo_bits) - 1;
+  return ETP_OK;
+}
+
+// =================================================================================================
+// NTT driver
+// =================================================================================================
+static int plan_digits(int L, int b[3]) {
+  if (L <= 12) { b[0] = L; return 1; }
+  if (L <= 23) {
+    int last = (L + 1) / 2;
+    if (last > 12) last = 12;
+    b[0] = L - last; b[1] = last;
+    return 2;
+  }
+  int rest = L - 12;
+  b[0] = (rest + 1) / 2; b[1] = rest - b[0]; b[2] = 12;
+  return 3;
+}
+int ntt_num_passes(int log_n) { int b[3]; return plan_digits(log_n, b); }
+
+int ntt_run(etp_ctx* ctx, const NttArgs& a) {
+  if (a.log_n < 0 || a.log_n > 31) return etp_fail(ctx, ETP_ERR_INVALID, "ntt: log_n %d out of range", a.log_n);
+  if (a.n_cols == 0) return ETP_OK;
+  const int L = a.log_n;
+  int b[3];
+  const int m = plan_digits(L, b);
+  if (a.natural_out && m > 1 && !a.scratch) return etp_fail(ctx, ETP_ERR_INVALID, "ntt: scratch required");
+  ntt::PassParams p{};
+  p.log_n = L;
+  p.inverse = a.inverse ? 1 : 0;
+  ETP_TRY(get_pow_table(ctx, gl::root_of_unity(L), L, 1, &p.tw));
+  ntt::PowTable in_pow{}, out_pow{};
+  const uint64_t n_inv = gl::inv((uint64_t)1 << L);
+  if (a.coset_shift && !a.inverse) ETP_TRY(get_pow_table(ctx, a.coset_shift, L, 1, &in_pow));
+  if (a.coset_shift && a.inverse) ETP_TRY(get_pow_table(ctx, gl::inv(a.coset_shift), L, n_inv, &out_pow));
+  int s = L;
+  for (int j = 0; j < m; j++) {
+    s -= b[j];
+    const bool first = j == 0, last = j == m - 1;
+    // buffers: forward/bitrev: in -> out, then in place. natural: in -> scratch ... -> out
+    const uint64_t* src; size_t src_stride; uint64_t* dst; size_t dst_stride;
+    if (first) { src = a.in; src_stride = a.in_stride; }
+    else if (a.natural_out) { src = a.scratch; src_stride = a.scratch_stride; }
+    else { src = a.out; src_stride = a.out_stride; }
+    if (a.natural_out && !last) { dst = a.scratch; dst_stride = a.scratch_stride; }
+    else { dst = a.out; dst_stride = a.out_stride; }
+    p.in = src; p.in_col_stride = src_stride; p.out = dst; p.out_col_stride = dst_stride;
+    p.s = s; p.b = b[j];
+    p.n_in = first ? a.n_in : (1u << L);
+    p.in_scale = (first && a.coset_shift && !a.inverse) ? 1 : 0;
+    p.in_pow = in_pow;
+    p.natural_out = (last && a.natural_out) ? 1 : 0;
+    p.out_scale = 0;
+    if (last && a.inverse) {
+      if (a.coset_shift) { p.out_scale = 1; p.out_pow = out_pow; }
+      else { p.out_scale = 2; p.out_const = n_inv; }
+    }
+    const int R = 1 << b[j];
+    if (!last) {
+      const int ul = b[j] >= 11 ? 2 : 3;
+      const size_t smem = ((size_t)(R >> 1) + ((size_t)R << ul)) * 8;
+      dim3 grid((unsigned)(((size_t)1 << (L - b[j])) >> ul), (unsigned)a.n_cols);
+      ntt::pass_strided<<<grid, ntt::THREADS, smem, ctx->stream>>>(p, ul);
+    } else {
+      const int pb = L - b[j];
+      int ul = b[j] >= 12 ? 1 : (b[j] == 11 ? 2 : 3);
+      if (ul > pb) ul = pb;
+      const size_t smem = ((size_t)(R >> 1) + (size_t)ntt::last_pitch(b[j]) * ((size_t)1 << ul)) * 8;
+      dim3 grid((unsigned)(((size_t)1 << pb) >> ul), (unsigned)a.n_cols);
+      ntt::pass_last<<<grid, ntt::THREADS, smem, ctx->stream>>>(p, ul);
+    }
+    ETP_LAUNCH_CHECK(ctx);
+  }
+  return ETP_OK;
+}
+
+// =================================================================================================
+// Merkle driver
+// =================================================================================================
+int merkle_build_levels(etp_ctx* ctx, uint64_t* levels, size_t n_leaves, int cap_height, uint64_t* cap_host) {
+  size_t n = n_leaves;
+  uint64_t* cur = levels;
+  while (n > ((size_t)1 << cap_height)) {
+    uint64_t* nxt = cur + 4 * n;
+    const uint32_t parents = (uint32_t)(n >> 1);
+    merkle::hash_level<<<(parents + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
+        cur, parents, nxt);
+    ETP_LAUNCH_CHECK(ctx);
+    cur = nxt;
+    n >>= 1;
+  }
+  ETP_CUDA(ctx, cudaMemcpyAsync(cap_host, cur, ((size_t)32) << cap_height, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+int merkle_prove_from_levels(etp_ctx* ctx, const uint64_t* levels, size_t n_leaves, int cap_height, size_t leaf_index,
+                             uint64_t* out) {
+  const int num_layers = log2_exact(n_leaves) - cap_height;
+  if (leaf_index >= n_leaves) return etp_fail(ctx, ETP_ERR_INVALID, "prove: leaf index out of range");
+  for (int i = 0; i < num_layers; i++) {
+    const size_t node = (leaf_index >> i) ^ 1;
+    ETP_CUDA(ctx, cudaMemcpyAsync(out + 4 * i, levels + level_offset(n_leaves, i) + 4 * node, 32, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+  }
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+int merkle_download_digests(etp_ctx* ctx, const uint64_t* levels, size_t n_leaves, int cap_height, uint64_t* out_host) {
+  const int num_layers = log2_exact(n_leaves) - cap_height;
+  const size_t nd = 2 * (n_leaves - ((size_t)1 << cap_height));
+  if (nd == 0) return ETP_OK;
+  DevBuf<uint64_t> tmp(ctx);
+  ETP_TRY(tmp.alloc(nd * 4));
+  for (int i = 0; i < num_layers; i++) {
+    const uint32_t nodes = (uint32_t)(n_leaves >> i);
+    merkle::scatter_to_plonky2_layout<<<(nodes + 255) / 256, 256, 0, ctx->stream>>>(levels + level_offset(n_leaves, i), i,
+                                                                                    nodes, num_layers, tmp.p);
+    ETP_LAUNCH_CHECK(ctx);
+  }
+  ETP_CUDA(ctx, cudaMemcpyAsync(out_host, tmp.p, nd * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+// =================================================================================================
+// primitives exposed for parity tests
+// =================================================================================================
+__global__ void k_permute_states(uint64_t* st, size_t n) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = st[12 * t + i];
+  poseidon::permute(s);
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[12 * t + i] = gl::canon(s[i]);
+}
+
+extern "C" int etp_poseidon_permute_host(etp_ctx* ctx, uint64_t* states, size_t n) {
+  if (!ctx || (!states && n)) return ETP_ERR_INVALID;
+  if (n == 0) return ETP_OK;
+  DevBuf<uint64_t> d(ctx);
+  ETP_TRY(d.alloc(12 * n));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d.p, states, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
+  k_permute_states<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d.p, n);
+  ETP_LAUNCH_CHECK(ctx);
+  ETP_CUDA(ctx, cudaMemcpyAsync(states, d.p, 96 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+static int transform_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n, bool inverse, uint64_t shift) {
+  if (!ctx) return ETP_ERR_INVALID;
+  if (log_n < 0 || log_n > 31 || (!cols && n_cols)) return etp_fail(ctx, ETP_ERR_INVALID, "transform: bad arguments");
+  if (n_cols == 0) return ETP_OK;
+  const size_t n = (size_t)1 << log_n;
+  DevBuf<uint64_t> a(ctx), b(ctx), c(ctx);
+  ETP_TRY(a.alloc(n_cols * n));
+  ETP_TRY(b.alloc(n_cols * n));
+  ETP_TRY(c.alloc(n_cols * n));
+  ETP_CUDA(ctx, cudaMemcpyAsync(a.p, cols, n_cols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  NttArgs args;
+  args.in = a.p; args.in_stride = n; args.n_in = (uint32_t)n; args.out = b.p; args.out_stride = n;
+  args.scratch = c.p; args.scratch_stride = n; args.log_n = log_n; args.n_cols = n_cols;
+  args.inverse = inverse; args.natural_out = true; args.coset_shift = shift;
+  ETP_TRY(ntt_run(ctx, args));
+  ETP_CUDA(ctx, cudaMemcpyAsync(cols, b.p, n_cols * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+extern "C" int etp_ifft_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n) {
+  return transform_host(ctx, cols, n_cols, log_n, true, 0);
+}
+extern "C" int etp_fft_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n) {
+  return transform_host(ctx, cols, n_cols, log_n, false, 0);
+}
+extern "C" int etp_coset_ifft_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n, uint64_t shift) {
+  if (gl::canon(shift) == 0) return etp_fail(ctx, ETP_ERR_INVALID, "coset shift must be non-zero");
+  return transform_host(ctx, cols, n_cols, log_n, true, gl::canon(shift));
+}
+extern "C" int etp_coset_lde_host(etp_ctx* ctx, const uint64_t* coeffs, size_t n_cols, int log_n, int rate_bits,
+                                  uint64_t shift, uint64_t* out) {
+  if (!ctx) return ETP_ERR_INVALID;
+  if (log_n < 0 || rate_bits < 0 || log_n + rate_bits > 31 || gl::canon(shift) == 0)
+    return etp_fail(ctx, ETP_ERR_INVALID, "coset_lde: bad arguments");
+  if (n_cols == 0) return ETP_OK;
+  const size_t n = (size_t)1 << log_n, big = n << rate_bits;
+  DevBuf<uint64_t> a(ctx), b(ctx), c(ctx);
+  ETP_TRY(a.alloc(n_cols * n));
+  ETP_TRY(b.alloc(n_cols * big));
+  ETP_TRY(c.alloc(n_cols * big));
+  ETP_CUDA(ctx, cudaMemcpyAsync(a.p, coeffs, n_cols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  NttArgs args;
+  args.in = a.p; args.in_stride = n; args.n_in = (uint32_t)n; args.out = b.p; args.out_stride = big;
+  args.scratch = c.p; args.scratch_stride = big; args.log_n = log_n + rate_bits; args.n_cols = n_cols;
+  args.natural_out = true; args.coset_shift = gl::canon(shift);
+  ETP_TRY(ntt_run(ctx, args));
+  ETP_CUDA(ctx, cudaMemcpyAsync(out, b.p, n_cols * big * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+// =================================================================================================
+// MerkleTree::new
+// =================================================================================================
+extern "C" int etp_merkle_new_host(etp_ctx* ctx, const uint64_t* leaves, size_t n_leaves, size_t leaf_len, int cap_height,
+                                   etp_tree** out) {
+  if (!ctx || !out) return ETP_ERR_INVALID;
+  *out = nullptr;
+  const int lg = log2_exact(n_leaves);
+  if (lg < 0) return etp_fail(ctx, ETP_ERR_INVALID, "MerkleTree::new: number of leaves must be a power of two");
+  if (cap_height < 0 || cap_height > lg)
+    return etp_fail(ctx, ETP_ERR_INVALID, "cap_height=%d should be at most log2(leaves.len())=%d", cap_height, lg);
+  if (n_leaves > ((size_t)1 << 31)) return etp_fail(ctx, ETP_ERR_INVALID, "too many leaves");
+  etp_tree* t = new etp_tree();
+  t->ctx = ctx; t->n_leaves = n_leaves; t->leaf_len = leaf_len; t->cap_height = cap_height;
+  t->cap.resize((size_t)4 << cap_height);
+  int rc = dev_alloc(ctx, levels_words(n_leaves, cap_height) * 8, (void**)&t->levels);
+  if (rc != ETP_OK) { delete t; return rc; }
+  DevBuf<uint64_t> d(ctx);
+  rc = d.alloc(n_leaves * leaf_len);
+  if (rc != ETP_OK) { etp_tree_free(t); return rc; }
+  cudaError_t e = cudaMemcpyAsync(d.p, leaves, n_leaves * leaf_len * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { etp_tree_free(t); return etp_fail(ctx, ETP_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
+  merkle::hash_leaves_rowmajor<<<(unsigned)((n_leaves + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS), merkle::HASH_THREADS, 0,
+                                 ctx->stream>>>(d.p, (int)leaf_len, (uint32_t)n_leaves, t->levels);
+  ctx->launches++;
+  rc = merkle_build_levels(ctx, t->levels, n_leaves, cap_height, t->cap.data());
+  if (rc != ETP_OK) { etp_tree_free(t); return rc; }
+  *out = t;
+  return ETP_OK;
+}
+extern "C" void etp_tree_free(etp_tree* t) {
+  if (!t) return;
+  dev_free(t->ctx, t->levels);
+  delete t;
+}
+extern "C" size_t etp_tree_num_digests(const etp_tree* t) { return t ? 2 * (t->n_leaves - ((size_t)1 << t->cap_height)) : 0; }
+extern "C" int etp_tree_cap(etp_tree* t, uint64_t* cap_out) {
+  if (!t || !cap_out) return ETP_ERR_INVALID;
+  memcpy(cap_out, t->cap.data(), t->cap.size() * 8);
+  return ETP_OK;
+}
+extern "C" int etp_tree_digests(etp_tree* t, uint64_t* out) {
+  if (!t || (!out && etp_tree_num_digests(t))) return ETP_ERR_INVALID;
+  return merkle_download_digests(t->ctx, t->levels, t->n_leaves, t->cap_height, out);
+}
+extern "C" int etp_tree_prove(etp_tree* t, size_t leaf_index, uint64_t* out) {
+  if (!t) return ETP_ERR_INVALID;
+  return merkle_prove_from_levels(t->ctx, t->levels, t->n_leaves, t->cap_height, leaf_index, out);
+}
+
+// =================================================================================================
+// PolynomialBatch
+// =================================================================================================
+int batch_create(etp_ctx* ctx, size_t n_cols, int log_n, int rate_bits, int blinding, int cap_height, etp_batch** out) {
+  *out = nullptr;
+  if (blinding) return etp_fail(ctx, ETP_ERR_INVALID, "blinding is not supported (the STARK path commits with blinding=false)");
+  if (log_n < 0 || rate_bits < 0 || log_n + rate_bits > 31) return etp_fail(ctx, ETP_ERR_INVALID, "bad degree / rate");
+  if (cap_height < 0 || cap_height > log_n + rate_bits)
+    return etp_fail(ctx, ETP_ERR_INVALID, "cap_height=%d should be at most log2(leaves.len())=%d", cap_height, log_n + rate_bits);
+  if (n_cols > 65535) return etp_fail(ctx, ETP_ERR_INVALID, "too many polynomials");
+  etp_batch* b = new etp_batch();
+  b->ctx = ctx; b->n_cols = n_cols; b->log_n = log_n; b->rate_bits = rate_bits; b->cap_height = cap_height;
+  b->cap.resize((size_t)4 << cap_height);
+  int rc = dev_alloc(ctx, n_cols * b->n() * 8, (void**)&b->coeffs);
+  if (rc == ETP_OK) rc = dev_alloc(ctx, n_cols * b->lde_n() * 8, (void**)&b->lde);
+  if (rc == ETP_OK) rc = dev_alloc(ctx, levels_words(b->lde_n(), cap_height) * 8, (void**)&b->levels);
+  if (rc != ETP_OK) { etp_batch_free(b); return rc; }
+  *out = b;
+  return ETP_OK;
+}
+
+int batch_commit_from_coeffs(etp_batch* b) {
+  etp_ctx* ctx = b->ctx;
+  // "FFT + blinding": zero-pad to n << rate_bits, coset_fft(7); bit-reversed order comes for free
+  NttArgs args;
+  args.in = b->coeffs; args.in_stride = b->n(); args.n_in = (uint32_t)b->n();
+  args.out = b->lde; args.out_stride = b->lde_n();
+  args.log_n = b->log_n + b->rate_bits; args.n_cols = b->n_cols;
+  args.coset_shift = gl::GENERATOR;
+  ETP_TRY(ntt_run(ctx, args));
+  // "build Merkle tree"
+  const uint32_t nl = (uint32_t)b->lde_n();
+  merkle::hash_leaves_colmajor<<<(nl + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
+      b->lde, b->lde_n(), (int)b->n_cols, nl, b->levels);
+  ETP_LAUNCH_CHECK(ctx);
+  return merkle_build_levels(ctx, b->levels, b->lde_n(), b->cap_height, b->cap.data());
+}
+
+int batch_commit_from_values(etp_batch* b, const uint64_t* values_dev, size_t col_stride) {
+  // "IFFT": natural -> natural; the LDE buffer doubles as scratch for the multi-pass transform
+  NttArgs args;
+  args.in = values_dev; args.in_stride = col_stride; args.n_in = (uint32_t)b->n();
+  args.out = b->coeffs; args.out_stride = b->n();
+  args.scratch = b->lde; args.scratch_stride = b->lde_n();
+  args.log_n = b->log_n; args.n_cols = b->n_cols; args.inverse = true; args.natural_out = true;
+  ETP_TRY(ntt_run(b->ctx, args));
+  return batch_commit_from_coeffs(b);
+}
+
+__global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* dst, size_t n, size_t n_cols) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n * n_cols) return;
+  const size_t c = t / n, i = t % n;
+  dst[t] = gl::canon(src[c * src_stride + i]);
+}
+
+static int upload_columns(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, size_t n, uint64_t* dst) {
+  for (size_t c = 0; c < n_cols; c++) {
+    if (!cols[c]) return etp_fail(ctx, ETP_ERR_INVALID, "null column %zu", c);
+    ETP_CUDA(ctx, cudaMemcpyAsync(dst + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return ETP_OK;
+}
+
+extern "C" int etp_batch_from_values_host(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, int log_n, int rate_bits,
+                                          int blinding, int cap_height, etp_batch** out) {
+  if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
+  etp_batch* b;
+  ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
+  DevBuf<uint64_t> stage_buf(ctx);
+  int rc = stage_buf.alloc(n_cols * b->n());
+  uint64_t* stage = stage_buf.p;
+  if (rc == ETP_OK) rc = upload_columns(ctx, cols, n_cols, b->n(), stage);
+  if (rc == ETP_OK) rc = batch_commit_from_values(b, stage, b->n());
+  if (rc != ETP_OK) { etp_batch_free(b); return rc; }
+  *out = b;
+  return ETP_OK;
+}
+
+extern "C" int etp_batch_from_coeffs_host(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, int log_n, int rate_bits,
+                                          int blinding, int cap_height, etp_batch** out) {
+  if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
+  etp_batch* b;
+  ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
+  int rc = upload_columns(ctx, cols, n_cols, b->n(), b->coeffs);
+  const size_t tot = n_cols * b->n();
+  if (rc == ETP_OK && tot) {
+    k_canon_copy<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(b->coeffs, b->n(), b->coeffs, b->n(), n_cols);
+    ctx->launches++;
+  }
+  if (rc == ETP_OK) rc = batch_commit_from_coeffs(b);
+  if (rc != ETP_OK) { etp_batch_free(b); return rc; }
+  *out = b;
+  return ETP_OK;
+}
+
+extern "C" int etp_batch_from_values_dev(etp_ctx* ctx, const uint64_t* values_dev, size_t col_stride, size_t n_cols, int log_n,
+                                         int rate_bits, int blinding, int cap_height, etp_batch** out) {
+  if (!ctx || !out || (!values_dev && n_cols)) return ETP_ERR_INVALID;
+  etp_batch* b;
+  ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
+  int rc = batch_commit_from_values(b, values_dev, col_stride);
+  if (rc != ETP_OK) { etp_batch_free(b); return rc; }
+  *out = b;
+  return ETP_OK;
+}
+
+extern "C" int etp_batch_from_coeffs_dev(etp_ctx* ctx, const uint64_t* coeffs_dev, size_t col_stride, size_t n_cols, int log_n,
+                                         int rate_bits, int blinding, int cap_height, etp_batch** out) {
+  if (!ctx || !out || (!coeffs_dev && n_cols)) return ETP_ERR_INVALID;
+  etp_batch* b;
+  ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
+  int rc = ETP_OK;
+  const size_t tot = n_cols * b->n();
+  if (tot) {
+    k_canon_copy<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(coeffs_dev, col_stride, b->coeffs, b->n(), n_cols);
+    ctx->launches++;
+  }
+  if (rc == ETP_OK) rc = batch_commit_from_coeffs(b);
+  if (rc != ETP_OK) { etp_batch_free(b); return rc; }
+  *out = b;
+  return ETP_OK;
+}
+
+extern "C" int etp_batch_recommit_values_dev(etp_batch* b, const uint64_t* values_dev, size_t col_stride) {
+  if (!b || !values_dev) return ETP_ERR_INVALID;
+  return batch_commit_from_values(b, values_dev, col_stride);
+}
+
+extern "C" void etp_batch_free(etp_batch* b) {
+  if (!b) return;
+  dev_free(b->ctx, b->coeffs);
+  dev_free(b->ctx, b->lde);
+  dev_free(b->ctx, b->levels);
+  delete b;
+}
+extern "C" size_t etp_batch_num_cols(const etp_batch* b) { return b ? b->n_cols : 0; }
+extern "C" int etp_batch_degree_log(const etp_batch* b) { return b ? b->log_n : -1; }
+extern "C" size_t etp_batch_num_digests(const etp_batch* b) { return b ? 2 * (b->lde_n() - ((size_t)1 << b->cap_height)) : 0; }
+extern "C" int etp_batch_cap(etp_batch* b, uint64_t* cap_out) {
+  if (!b || !cap_out) return ETP_ERR_INVALID;
+  memcpy(cap_out, b->cap.data(), b->cap.size() * 8);
+  return ETP_OK;
+}
+extern "C" int etp_batch_download_coeffs(etp_batch* b, uint64_t* out) {
+  if (!b || (!out && b->n_cols)) return ETP_ERR_INVALID;
+  if (b->n_cols == 0) return ETP_OK;
+  ETP_CUDA(b->ctx, cudaMemcpyAsync(out, b->coeffs, b->n_cols * b->n() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
+  ETP_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+  return ETP_OK;
+}
+
+// rows[i][c] = lde[c][i]  (tiled transpose through shared memory)
+__global__ void k_transpose_to_rows(const uint64_t* __restrict__ lde, size_t col_stride, int n_cols, size_t n_rows,
+                                    uint64_t* __restrict__ rows) {
+  __shared__ uint64_t tile[32][33];
+  const size_t r0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const int c = c0 + k;
+    const size_t r = r0 + threadIdx.x;
+    if (c < n_cols && r < n_rows) tile[k][threadIdx.x] = lde[(size_t)c * col_stride + r];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    const size_t r = r0 + k;
+    const int c = c0 + threadIdx.x;
+    if (c < n_cols && r < n_rows) rows[r * n_cols + c] = gl::canon(tile[threadIdx.x][k]);
+  }
+}
+
+extern "C" int etp_batch_download_leaves(etp_batch* b, uint64_t* out) {
+  if (!b || (!out && b->n_cols)) return ETP_ERR_INVALID;
+  if (b->n_cols == 0) return ETP_OK;
+  etp_ctx* ctx = b->ctx;
+  DevBuf<uint64_t> rows(ctx);
+  ETP_TRY(rows.alloc(b->n_cols * b->lde_n()));
+  dim3 grid((unsigned)((b->lde_n() + 31) / 32), (unsigned)((b->n_cols + 31) / 32)), block(32, 8);
+  k_transpose_to_rows<<<grid, block, 0, ctx->stream>>>(b->lde, b->lde_n(), (int)b->n_cols, b->lde_n(), rows.p);
+  ETP_LAUNCH_CHECK(ctx);
+  ETP_CUDA(ctx, cudaMemcpyAsync(out, rows.p, b->n_cols * b->lde_n() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+extern "C" int etp_batch_download_digests(etp_batch* b, uint64_t* out) {
+  if (!b) return ETP_ERR_INVALID;
+  return merkle_download_digests(b->ctx, b->levels, b->lde_n(), b->cap_height, out);
+}
+extern "C" int etp_batch_leaves_at(etp_batch* b, const uint64_t* idx, size_t n_idx, uint64_t* rows_out) {
+  if (!b || (!idx && n_idx)) return ETP_ERR_INVALID;
+  if (n_idx == 0 || b->n_cols == 0) return ETP_OK;
+  etp_ctx* ctx = b->ctx;
+  for (size_t q = 0; q < n_idx; q++)
+    if (idx[q] >= b->lde_n()) return etp_fail(ctx, ETP_ERR_INVALID, "leaf index out of range");
+  DevBuf<uint64_t> d_idx(ctx), d_rows(ctx);
+  ETP_TRY(d_idx.alloc(n_idx));
+  ETP_TRY(d_rows.alloc(n_idx * b->n_cols));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_idx.p, idx, n_idx * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t tot = n_idx * b->n_cols;
+  merkle::gather_rows_colmajor<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(b->lde, b->lde_n(), (int)b->n_cols, d_idx.p,
+                                                                                      (int)n_idx, d_rows.p);
+  ETP_LAUNCH_CHECK(ctx);
+  ETP_CUDA(ctx, cudaMemcpyAsync(rows_out, d_rows.p, tot * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+extern "C" int etp_batch_get_lde_values(etp_batch* b, size_t index, size_t step, uint64_t* row_out) {
+  if (!b) return ETP_ERR_INVALID;
+  const size_t i = index * step;
+  if (i >= b->lde_n()) return etp_fail(b->ctx, ETP_ERR_INVALID, "get_lde_values: index out of range");
+  uint64_t pos = gl::bitrev32((uint32_t)i, b->log_n + b->rate_bits);
+  return etp_batch_leaves_at(b, &pos, 1, row_out);
+}
+extern "C" int etp_batch_prove(etp_batch* b, size_t leaf_index, uint64_t* out) {
+  if (!b) return ETP_ERR_INVALID;
+  return merkle_prove_from_levels(b->ctx, b->levels, b->lde_n(), b->cap_height, leaf_index, out);
+}
+extern "C" const uint64_t* etp_batch_lde_dev(const etp_batch* b, size_t* col_stride) {
+  if (!b) return nullptr;
+  if (col_stride) *col_stride = b->lde_n();
+  return b->lde;
+}
+extern "C" const uint64_t* etp_batch_coeffs_dev(const etp_batch* b, size_t* col_stride) {
+  if (!b) return nullptr;
+  if (col_stride) *col_stride = b->n();
+  return b->coeffs;
+}

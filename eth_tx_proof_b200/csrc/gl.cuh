@@ -1,0 +1,179 @@
+// Goldilocks field F_p, p = 2^64 - 2^32 + 1, and F_p[X]/(X^2 - 7) for sm_100a (K1 in SURVEY.md 2.4).
+//
+// Replaces plonky2_field 0.2.2 `GoldilocksField` / `QuadraticExtension<GoldilocksField>`
+// (field/src/goldilocks_field.rs, field/src/extension/quadratic.rs; crate pinned at
+// /root/reference/Cargo.lock:3466, reached from /root/reference/ops/src/lib.rs:52).
+//
+// Representation: one u64 per element. Like upstream, values in memory may be any u64
+// ("non-canonical"); every device function accepts any u64 unless its comment says otherwise.
+// Results that leave the library are canonicalised with gl_canon().
+//
+// 64x64->128 products use mul.lo/mul.hi.u64, which ptxas lowers to IMAD.WIDE.U32 chains on the
+// FMA pipe; the reduction uses 2^64 == 2^32 - 1 and 2^96 == -1 (mod p) with carry-chain adds on the
+// ALU pipe. Tensor cores are deliberately unused.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GL_HD __host__ __device__ __forceinline__
+#define GL_D __device__ __forceinline__
+#else
+#define GL_HD inline
+#define GL_D inline
+#endif
+
+namespace gl {
+
+constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
+constexpr uint64_t EPS = 0xFFFFFFFFULL;  // 2^64 mod p
+constexpr uint64_t GENERATOR = 7ULL;     // MULTIPLICATIVE_GROUP_GENERATOR == coset_shift()
+constexpr uint64_t POWER_OF_TWO_GENERATOR = 1753635133440165772ULL;
+constexpr int TWO_ADICITY = 32;
+
+GL_HD uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
+
+#if defined(__CUDA_ARCH__)
+// ---- device versions: explicit carry chains -------------------------------------------------
+// a, b: any u64. Result: any u64, == a + b (mod p).
+GL_D uint64_t add(uint64_t a, uint64_t b) {
+  uint64_t s;
+  uint32_t c;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(s), "=r"(c) : "l"(a), "l"(b));
+  // +2^64 wrapped away == +EPS; the fix itself can wrap once more when both inputs were >= p
+  asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+l"(s), "=r"(c) : "l"((uint64_t)(0u - c)));
+  return s + (uint64_t)(0u - c);
+}
+// a: any u64, b: CANONICAL (< p) or at least one of the two < p. One fix-up suffices.
+GL_D uint64_t add_c(uint64_t a, uint64_t b) {
+  uint64_t s;
+  uint32_t c;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(s), "=r"(c) : "l"(a), "l"(b));
+  return s + (uint64_t)(0u - c);
+}
+// a, b: any u64. Result any u64 == a - b (mod p).
+GL_D uint64_t sub(uint64_t a, uint64_t b) {
+  uint64_t d;
+  uint32_t br;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(d), "=r"(br) : "l"(a), "l"(b));
+  // br = 0xffffffff on borrow == EPS as a u64
+  asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u32 %1, 0, 0;" : "+l"(d), "=r"(br) : "l"((uint64_t)br));
+  return d - (uint64_t)br;
+}
+// a: any u64, b: CANONICAL (< p).
+GL_D uint64_t sub_c(uint64_t a, uint64_t b) {
+  uint64_t d;
+  uint32_t br;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(d), "=r"(br) : "l"(a), "l"(b));
+  return d - (uint64_t)br;
+}
+// 128-bit (hi:lo) -> any u64 == value (mod p).  goldilocks_field.rs reduce128.
+GL_D uint64_t reduce128(uint64_t lo, uint64_t hi) {
+  uint32_t hl = (uint32_t)hi, hh = (uint32_t)(hi >> 32);
+  uint64_t t0;
+  uint32_t br, c;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(t0), "=r"(br) : "l"(lo), "l"((uint64_t)hh));
+  t0 -= (uint64_t)br;                              // borrowed 2^64 == EPS: cannot underflow again
+  uint64_t t1 = (uint64_t)hl * (uint64_t)0xFFFFFFFFu;  // IMAD.WIDE.U32 on the FMA pipe
+  uint64_t t2;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(t2), "=r"(c) : "l"(t0), "l"(t1));
+  return t2 + (uint64_t)(0u - c);                  // cannot overflow again (t1 <= EPS^2)
+}
+// same, but the result is CANONICAL: t0 + t1 < 2p, so one conditional subtraction of p is exact.
+GL_D uint64_t reduce128_canon(uint64_t lo, uint64_t hi) {
+  uint32_t hl = (uint32_t)hi, hh = (uint32_t)(hi >> 32);
+  uint64_t t0;
+  uint32_t br, c;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(t0), "=r"(br) : "l"(lo), "l"((uint64_t)hh));
+  t0 -= (uint64_t)br;
+  uint64_t t1 = (uint64_t)hl * (uint64_t)0xFFFFFFFFu;
+  uint64_t t2;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(t2), "=r"(c) : "l"(t0), "l"(t1));
+  return (c || t2 >= P) ? t2 + EPS : t2;           // -p == +EPS (mod 2^64)
+}
+GL_D uint64_t mul(uint64_t a, uint64_t b) { return reduce128(a * b, __umul64hi(a, b)); }
+GL_D uint64_t mul_canon(uint64_t a, uint64_t b) { return reduce128_canon(a * b, __umul64hi(a, b)); }
+#else
+// ---- host versions (used by the host-side Challenger / table setup; product code, not the oracle)
+GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+  uint64_t hh = hi >> 32, hl = hi & EPS;
+  uint64_t t0 = lo - hh;
+  if (lo < hh) t0 -= EPS;
+  uint64_t t1 = hl * EPS;
+  uint64_t t2 = t0 + t1;
+  if (t2 < t0) t2 += EPS;
+  return t2;
+}
+GL_HD uint64_t reduce128_canon(uint64_t lo, uint64_t hi) { return canon(reduce128(lo, hi)); }
+GL_HD uint64_t mul(uint64_t a, uint64_t b) {
+  unsigned __int128 x = (unsigned __int128)a * b;
+  return reduce128((uint64_t)x, (uint64_t)(x >> 64));
+}
+GL_HD uint64_t mul_canon(uint64_t a, uint64_t b) { return canon(mul(a, b)); }
+GL_HD uint64_t add(uint64_t a, uint64_t b) {
+  uint64_t s = a + b;
+  if (s < a) { uint64_t t = s + EPS; s = t < s ? t + EPS : t; }
+  return s;
+}
+GL_HD uint64_t add_c(uint64_t a, uint64_t b) { return add(a, b); }
+GL_HD uint64_t sub(uint64_t a, uint64_t b) {
+  uint64_t d = a - b;
+  if (a < b) { uint64_t t = d - EPS; d = d < EPS ? t - EPS : t; }
+  return d;
+}
+GL_HD uint64_t sub_c(uint64_t a, uint64_t b) { return sub(a, b); }
+#endif
+
+GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
+GL_HD uint64_t neg(uint64_t a) { a = canon(a); return a ? P - a : 0; }
+GL_HD uint64_t pow(uint64_t a, uint64_t e) {
+  uint64_t r = 1;
+  while (e) { if (e & 1) r = mul(r, a); a = sqr(a); e >>= 1; }
+  return r;
+}
+GL_HD uint64_t inv(uint64_t a) { return pow(a, P - 2); }
+// F::primitive_root_of_unity(n_log)
+GL_HD uint64_t root_of_unity(int n_log) {
+  uint64_t r = POWER_OF_TWO_GENERATOR;
+  for (int i = n_log; i < TWO_ADICITY; i++) r = sqr(r);
+  return canon(r);
+}
+
+// ---- quadratic extension, X^2 = 7 ---------------------------------------------------------------
+struct Ext {
+  uint64_t c0, c1;
+};
+GL_HD Ext ext(uint64_t a, uint64_t b) { Ext r; r.c0 = a; r.c1 = b; return r; }
+GL_HD Ext eadd(Ext a, Ext b) { return ext(add(a.c0, b.c0), add(a.c1, b.c1)); }
+GL_HD Ext esub(Ext a, Ext b) { return ext(sub(a.c0, b.c0), sub(a.c1, b.c1)); }
+GL_HD Ext emul(Ext a, Ext b) {
+  uint64_t t = mul(a.c1, b.c1);
+  // 7*t = 8t - t, done with field ops to stay exact
+  uint64_t t2 = add(t, t), t4 = add(t2, t2), t8 = add(t4, t4);
+  return ext(add(mul(a.c0, b.c0), sub(t8, t)), add(mul(a.c0, b.c1), mul(a.c1, b.c0)));
+}
+GL_HD Ext emul_base(Ext a, uint64_t s) { return ext(mul(a.c0, s), mul(a.c1, s)); }
+GL_HD Ext ecanon(Ext a) { return ext(canon(a.c0), canon(a.c1)); }
+GL_HD Ext epow(Ext a, uint64_t e) {
+  Ext r = ext(1, 0);
+  while (e) { if (e & 1) r = emul(r, a); a = emul(a, a); e >>= 1; }
+  return r;
+}
+GL_HD Ext einv(Ext a) {
+  uint64_t t = mul(a.c1, a.c1);
+  uint64_t t2 = add(t, t), t4 = add(t2, t2), t8 = add(t4, t4);
+  uint64_t norm = sub(mul(a.c0, a.c0), sub(t8, t));
+  uint64_t ni = inv(norm);
+  return ext(mul(a.c0, ni), mul(neg(a.c1), ni));
+}
+
+GL_HD uint32_t bitrev32(uint32_t x, int bits) {
+#if defined(__CUDA_ARCH__)
+  return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+  return r;
+#endif
+}
+
+}  // namespace gl

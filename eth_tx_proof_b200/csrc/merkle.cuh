@@ -1,0 +1,131 @@
+// Poseidon Merkle trees on device (K4/K5 in SURVEY.md 2.4).
+//
+// Replaces plonky2 0.2.2 `MerkleTree::new` / `fill_digests_buf` / `fill_subtree` / `prove`
+// (plonky2/src/hash/merkle_tree.rs) and `PoseidonHash::{hash_no_pad, hash_or_noop, two_to_one}`
+// (plonky2/src/hash/poseidon.rs, hashing.rs) — crate pinned at /root/reference/Cargo.lock:3441,
+// reached from /root/reference/ops/src/lib.rs:52 via PolynomialBatch::from_coeffs and fri_committed_trees.
+//
+// Device layout: digests are kept LEVEL BY LEVEL (level 0 = leaf digests, level i has n_leaves >> i
+// nodes, the last level is the cap), 4 x u64 per digest.  A sibling is then levels[i][(leaf>>i)^1].
+// plonky2's recursive `digests` layout (left subtree || left child || right child || right subtree,
+// per cap subtree) is produced on demand by scatter_to_plonky2_layout with the closed-form map
+//   node j of layer i  ->  2*(((j>>1) << (i+1)) + 2^i - 1) + (j&1)          (SURVEY.md 8(a), row M).
+//
+// Leaves are read straight from COLUMN-MAJOR matrices (leaf i = element i of every column), so the
+// "transpose LDEs" + "reverse_index_bits_in_place" steps of from_coeffs disappear: the NTT already
+// leaves every column in bit-reversed order and consecutive threads read consecutive addresses.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "poseidon.cuh"
+
+namespace merkle {
+
+constexpr int HASH_THREADS = 128;
+
+__device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[12]) {
+  ulonglong2 a, b;
+  a.x = gl::canon(s[0]); a.y = gl::canon(s[1]); b.x = gl::canon(s[2]); b.y = gl::canon(s[3]);
+  reinterpret_cast<ulonglong2*>(dst)[0] = a;
+  reinterpret_cast<ulonglong2*>(dst)[1] = b;
+}
+
+// leaf i = (cols[0][i], cols[1][i], ...), column c at base + c*col_stride.  hash_or_noop semantics.
+static __global__ void __launch_bounds__(HASH_THREADS) hash_leaves_colmajor(const uint64_t* __restrict__ base, size_t col_stride,
+                                                                     int n_cols, uint32_t n_leaves,
+                                                                     uint64_t* __restrict__ digests) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_leaves) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) s[k] = 0;
+  if (n_cols <= 4) {  // hash_or_noop: copy and zero-pad
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      if (c < n_cols) s[c] = base[(size_t)c * col_stride + i];
+    store_digest(digests + 4 * (size_t)i, s);
+    return;
+  }
+  int c = 0;
+  for (; c + 8 <= n_cols; c += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = __ldg(base + (size_t)(c + k) * col_stride + i);
+    poseidon::permute(s);
+  }
+  if (c < n_cols) {  // ragged last chunk overwrites only the first (n_cols - c) rate lanes
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (c + k < n_cols) s[k] = __ldg(base + (size_t)(c + k) * col_stride + i);
+    poseidon::permute(s);
+  }
+  store_digest(digests + 4 * (size_t)i, s);
+}
+
+// leaves stored row-major (n_leaves x leaf_len): MerkleTree::new on caller-provided rows, FRI layers.
+static __global__ void __launch_bounds__(HASH_THREADS) hash_leaves_rowmajor(const uint64_t* __restrict__ rows, int leaf_len,
+                                                                     uint32_t n_leaves, uint64_t* __restrict__ digests) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_leaves) return;
+  const uint64_t* row = rows + (size_t)i * leaf_len;
+  uint64_t s[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) s[k] = 0;
+  if (leaf_len <= 4) {
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      if (c < leaf_len) s[c] = row[c];
+    store_digest(digests + 4 * (size_t)i, s);
+    return;
+  }
+  int c = 0;
+  for (; c + 8 <= leaf_len; c += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = __ldg(row + c + k);
+    poseidon::permute(s);
+  }
+  if (c < leaf_len) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (c + k < leaf_len) s[k] = __ldg(row + c + k);
+    poseidon::permute(s);
+  }
+  store_digest(digests + 4 * (size_t)i, s);
+}
+
+// parent[j] = two_to_one(child[2j], child[2j+1])
+static __global__ void __launch_bounds__(HASH_THREADS) hash_level(const uint64_t* __restrict__ child, uint32_t n_parents,
+                                                           uint64_t* __restrict__ parent) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_parents) return;
+  const ulonglong2* c = reinterpret_cast<const ulonglong2*>(child + 8 * (size_t)j);
+  ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
+  uint64_t s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
+  poseidon::permute(s);
+  store_digest(parent + 4 * (size_t)j, s);
+}
+
+// level i (n_nodes nodes) -> plonky2 digest layout. num_layers = log2(n_leaves) - cap_height.
+static __global__ void scatter_to_plonky2_layout(const uint64_t* __restrict__ level, int i, uint32_t n_nodes, int num_layers,
+                                          uint64_t* __restrict__ digests) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes) return;
+  const uint32_t per_sub_log = num_layers - i;  // nodes of this level per cap subtree
+  const uint32_t sub = t >> per_sub_log, j = t & ((1u << per_sub_log) - 1);
+  const size_t sub_size = ((size_t)1 << (num_layers + 1)) - 2;
+  const size_t slot = sub * sub_size + 2 * ((((size_t)j >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (j & 1);
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(level + 4 * (size_t)t);
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(digests + 4 * slot);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+
+// rows[q][c] = cols[c][idx[q]]
+static __global__ void gather_rows_colmajor(const uint64_t* __restrict__ base, size_t col_stride, int n_cols,
+                                     const uint64_t* __restrict__ idx, int n_idx, uint64_t* __restrict__ rows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_idx * n_cols) return;
+  const int q = t / n_cols, c = t % n_cols;
+  rows[t] = gl::canon(base[(size_t)c * col_stride + idx[q]]);
+}
+
+}  // namespace merkle

@@ -1,0 +1,168 @@
+/*
+ * etp_b200 — C ABI of the B200-native STARK proving hot path (libetp_b200.so).
+ *
+ * The reference (0xPolygonZero/eth-tx-proof) has no FFI, plugin or backend trait on this path: its
+ * worker calls `generate_txn_proof` (/root/reference/ops/src/lib.rs:52; also :72, :95), which runs
+ * plonky2 0.2.2 / starky 0.4.0 (/root/reference/Cargo.lock:3441,4529; crates not on disk) on the CPU
+ * under `StarkConfig::standard_fast_config()` (/root/reference/common/src/prover_state/circuit.rs:204).
+ * The drop-in seam is Cargo source replacement of those crates; the entry points
+ * below are what a patched plonky2/starky would bind (rust/etp_b200_sys/src/lib.rs).
+ * Each one names the upstream Rust item it replaces.
+ *
+ * Conventions
+ *  - all field elements are Goldilocks u64, little endian; inputs may be non-canonical (>= p),
+ *    every output is canonical (< p);
+ *  - "columns" are column-major: column c is `n` contiguous u64 (upstream: Vec<PolynomialValues<F>> /
+ *    Vec<PolynomialCoeffs<F>>, one Vec per polynomial);
+ *  - every function returns ETP_OK (0) or a negative error code; etp_last_error() gives the message
+ *    for the calling context.  Upstream panics on misuse (assert!); the Rust glue turns a non-zero
+ *    status into a panic / FatalError.  No exception or unwind crosses this boundary;
+ *  - a context owns one CUDA device + stream + scratch pools.  Contexts are independent; one context
+ *    must not be used from two threads at once (upstream: one tokio worker task per op);
+ *  - *_host entry points take HOST pointers and copy; *_dev entry points take DEVICE pointers on the
+ *    context's device (used by the benches and by callers that keep traces resident);
+ *  - there is no CPU fallback: without a usable CUDA device etp_ctx_create fails.
+ */
+#ifndef ETP_B200_H
+#define ETP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ETP_OK 0
+#define ETP_ERR_INVALID -1   /* bad argument (upstream: assert! panic) */
+#define ETP_ERR_CUDA -2      /* CUDA runtime / launch failure, OOM        */
+#define ETP_ERR_STATE -3     /* object used in the wrong state            */
+#define ETP_ERR_PROOF -4     /* prover-side check failed (e.g. zeta in the subgroup, quotient not a polynomial) */
+
+typedef struct etp_ctx etp_ctx;
+typedef struct etp_batch etp_batch;   /* plonky2::fri::oracle::PolynomialBatch<GoldilocksField, PoseidonGoldilocksConfig, 2> */
+typedef struct etp_tree etp_tree;     /* plonky2::hash::merkle_tree::MerkleTree<GoldilocksField, PoseidonHash>              */
+
+/* ---- library / context ---------------------------------------------------------------------- */
+const char *etp_version(void);
+int etp_device_count(void);
+int etp_ctx_create(int device, etp_ctx **out);
+void etp_ctx_destroy(etp_ctx *ctx);
+const char *etp_last_error(const etp_ctx *ctx);
+int etp_ctx_synchronize(etp_ctx *ctx);
+/* the context's cudaStream_t, for callers that enqueue their own work or time with CUDA events */
+void *etp_ctx_stream(etp_ctx *ctx);
+/* number of kernel launches issued by this context since creation */
+uint64_t etp_ctx_launch_count(const etp_ctx *ctx);
+/* device memory helpers (cudaMalloc / cudaFree / cudaMemcpyAsync on the context's stream + sync) */
+int etp_dev_alloc(etp_ctx *ctx, size_t bytes, void **out);
+int etp_dev_free(etp_ctx *ctx, void *ptr);
+int etp_dev_upload(etp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int etp_dev_download(etp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* ---- hashing primitives: plonky2/src/hash/poseidon.rs, hashing.rs ---------------------------- */
+/* PoseidonPermutation::permute on n independent 12-lane states (host pointers, n x 12) */
+int etp_poseidon_permute_host(etp_ctx *ctx, uint64_t *states, size_t n);
+
+/* ---- transforms: plonky2_field field/src/fft.rs, polynomial/mod.rs --------------------------- */
+/* PolynomialValues::ifft on n_cols columns of 2^log_n values (host, in place, natural order) */
+int etp_ifft_host(etp_ctx *ctx, uint64_t *cols, size_t n_cols, int log_n);
+/* PolynomialCoeffs::fft */
+int etp_fft_host(etp_ctx *ctx, uint64_t *cols, size_t n_cols, int log_n);
+/* PolynomialCoeffs::lde(rate_bits).coset_fft(shift): out has n_cols x 2^(log_n+rate_bits), NATURAL order */
+int etp_coset_lde_host(etp_ctx *ctx, const uint64_t *coeffs, size_t n_cols, int log_n, int rate_bits,
+                       uint64_t shift, uint64_t *out);
+/* PolynomialValues::coset_ifft(shift), in place */
+int etp_coset_ifft_host(etp_ctx *ctx, uint64_t *cols, size_t n_cols, int log_n, uint64_t shift);
+
+/* ---- MerkleTree::new(leaves, cap_height): plonky2/src/hash/merkle_tree.rs ---------------------- */
+/* leaves: n_leaves x leaf_len row-major (upstream Vec<Vec<F>>), n_leaves a power of two,
+ * cap_height <= log2(n_leaves) (else ETP_ERR_INVALID, upstream asserts). */
+int etp_merkle_new_host(etp_ctx *ctx, const uint64_t *leaves, size_t n_leaves, size_t leaf_len, int cap_height,
+                        etp_tree **out);
+void etp_tree_free(etp_tree *t);
+size_t etp_tree_num_digests(const etp_tree *t);           /* 2 * (n_leaves - 2^cap_height)                 */
+int etp_tree_cap(etp_tree *t, uint64_t *cap_out);          /* MerkleTree.cap: 2^cap_height x 4              */
+int etp_tree_digests(etp_tree *t, uint64_t *digests_out);  /* MerkleTree.digests in plonky2's layout        */
+/* MerkleTree::prove(leaf_index): siblings_out has (log2(n_leaves) - cap_height) x 4 */
+int etp_tree_prove(etp_tree *t, size_t leaf_index, uint64_t *siblings_out);
+
+/* ---- PolynomialBatch: plonky2/src/fri/oracle.rs ------------------------------------------------ */
+/* from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table).
+ * blinding must be 0 (the STARK path never blinds; ETP_ERR_INVALID otherwise).
+ * cols: n_cols pointers, each to 2^log_n u64 (host). */
+int etp_batch_from_values_host(etp_ctx *ctx, const uint64_t *const *cols, size_t n_cols, int log_n, int rate_bits,
+                               int blinding, int cap_height, etp_batch **out);
+/* from_coeffs(polynomials, ...) */
+int etp_batch_from_coeffs_host(etp_ctx *ctx, const uint64_t *const *cols, size_t n_cols, int log_n, int rate_bits,
+                               int blinding, int cap_height, etp_batch **out);
+/* same with one device matrix (column c at values_dev + c * col_stride); the input is not modified */
+int etp_batch_from_values_dev(etp_ctx *ctx, const uint64_t *values_dev, size_t col_stride, size_t n_cols, int log_n,
+                              int rate_bits, int blinding, int cap_height, etp_batch **out);
+int etp_batch_from_coeffs_dev(etp_ctx *ctx, const uint64_t *coeffs_dev, size_t col_stride, size_t n_cols, int log_n,
+                              int rate_bits, int blinding, int cap_height, etp_batch **out);
+/* re-run the commit into an existing batch of the same shape (no allocation; benches) */
+int etp_batch_recommit_values_dev(etp_batch *b, const uint64_t *values_dev, size_t col_stride);
+void etp_batch_free(etp_batch *b);
+size_t etp_batch_num_cols(const etp_batch *b);
+int etp_batch_degree_log(const etp_batch *b);
+size_t etp_batch_num_digests(const etp_batch *b);
+/* merkle_tree.cap */
+int etp_batch_cap(etp_batch *b, uint64_t *cap_out);
+/* lazy host views of the public fields (plonky2 layouts): polynomials (n_cols x n, column-major),
+ * merkle_tree.leaves ((n << rate_bits) x n_cols row-major, row i = point bitrev(i)), merkle_tree.digests */
+int etp_batch_download_coeffs(etp_batch *b, uint64_t *out);
+int etp_batch_download_leaves(etp_batch *b, uint64_t *out);
+int etp_batch_download_digests(etp_batch *b, uint64_t *out);
+/* merkle_tree.leaves[idx[q]] for q < n_idx: rows_out n_idx x n_cols */
+int etp_batch_leaves_at(etp_batch *b, const uint64_t *idx, size_t n_idx, uint64_t *rows_out);
+/* get_lde_values(index, step): leaves[bitrev(index * step)] */
+int etp_batch_get_lde_values(etp_batch *b, size_t index, size_t step, uint64_t *row_out);
+/* merkle_tree.prove(leaf_index) */
+int etp_batch_prove(etp_batch *b, size_t leaf_index, uint64_t *siblings_out);
+/* device views for fused callers: LDE matrix (column-major, column c at ptr + c*stride, bit-reversed
+ * row order) and coefficients */
+const uint64_t *etp_batch_lde_dev(const etp_batch *b, size_t *col_stride);
+const uint64_t *etp_batch_coeffs_dev(const etp_batch *b, size_t *col_stride);
+
+/* ---- starky: tables, compute_quotient_polys, prove ------------------------------------------- */
+#define ETP_TABLE_FIBONACCI 0 /* starky/src/fibonacci_stark.rs                                        */
+#define ETP_TABLE_MEMORY 1    /* evm_arithmetization/src/memory/memory_stark.rs (shape) */
+int etp_table_num_columns(int table);
+int etp_table_constraint_degree(int table);
+int etp_table_num_public_inputs(int table);
+int etp_table_num_aux_columns(int table, int num_challenges);
+int etp_table_quotient_degree_factor(int table);
+
+/* starky::lookup::lookup_helper_columns for every lookup of the table and every challenge:
+ * aux_dev gets etp_table_num_aux_columns columns of 2^log_n (column-major, stride 2^log_n). */
+int etp_lookup_helper_columns_dev(etp_ctx *ctx, int table, int log_n, const uint64_t *trace_dev, size_t col_stride,
+                                  const uint64_t *challenges, int n_challenges, uint64_t *aux_dev);
+/* starky::prover::compute_quotient_polys: returns the quotient chunks
+ * (quotient_degree_factor * n_alphas polynomials of 2^log_n coefficients, column-major) in out_dev. */
+int etp_compute_quotient_polys_dev(etp_ctx *ctx, int table, etp_batch *trace, etp_batch *aux /* may be NULL */,
+                                   const uint64_t *lookup_challenges, int n_lookup_challenges,
+                                   const uint64_t *public_inputs, const uint64_t *alphas, int n_alphas,
+                                   uint64_t *out_dev);
+
+/* plonky2::fri::prover::fri_proof_of_work: SMALLEST witness w such that the duplex response has
+ * `bits` leading zeros; state = sponge state with the pending inputs already overwritten in,
+ * pos = index the candidate is written to. */
+int etp_pow_grind(etp_ctx *ctx, const uint64_t state[12], int pos, int bits, uint64_t *witness_out);
+
+/* starky::prover::prove under StarkConfig::standard_fast_config(): trace commit, auxiliary columns,
+ * quotient, openings, FRI (commit phase, PoW, 84 query rounds).  proof_out: etp_stark_proof_words()
+ * u64 in the flat wire format of DESIGN.md.  The trace (n_cols x 2^log_n column-major) is a host or a
+ * device matrix. */
+size_t etp_stark_proof_words(int table, int log_n);
+int etp_stark_prove_host(etp_ctx *ctx, int table, int log_n, const uint64_t *trace, const uint64_t *public_inputs,
+                         uint64_t *proof_out);
+int etp_stark_prove_dev(etp_ctx *ctx, int table, int log_n, const uint64_t *trace_dev, size_t col_stride,
+                        const uint64_t *public_inputs, uint64_t *proof_out);
+/* per-phase device times (ms) of the last etp_stark_prove_* on this context, named after plonky2's
+ * TimingTree scopes; returns the number of entries written (<= max). */
+int etp_last_prove_timings(const etp_ctx *ctx, const char **names, float *ms, int max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
