@@ -1,5 +1,5 @@
-// Poseidon-12 over Goldilocks for sm_100a: one thread per permutation, state and MDS accumulators in
-// registers, round constants in constant memory (K4/K5 building block).
+// Poseidon-12 over Goldilocks for sm_100a: one thread per permutation, state in registers, round
+// constants in constant memory (K4/K5 building block).
 //
 // Replaces plonky2 0.2.2 `impl Poseidon for GoldilocksField` / `PoseidonPermutation`
 // (plonky2/src/hash/poseidon.rs, poseidon_goldilocks.rs) and the sponge helpers of
@@ -9,10 +9,19 @@
 // Round structure (identical output to upstream's naive and "fast" forms): 4 full + 22 partial + 4
 // full rounds; each round = add 12 constants, S-box x^7 (all lanes / lane 0), circulant MDS
 //   out[r] = sum_i in[(i+r)%12]*CIRC[i] + in[r]*DIAG[r].
-// Here the NEXT round's constants are folded into the MDS accumulators, so a round is
-//   S-box -> (MDS + RC_next) with one 96-bit reduction per lane.
-// The MDS works on the 32-bit halves of each lane with IMAD.WIDE.U32 accumulation (coefficients
-// < 2^6, so 12-term sums stay below 2^42) — integer pipe work, no tensor cores.
+//
+// B200 mapping (measured, tools/microbench/pipes.cu + profiles/):
+//  * S-box: 4 Goldilocks multiplications, IMAD.WIDE (FMA pipe) + carry chains (ALU pipe).
+//  * MDS: the coefficients are < 2^6, so on the 32-bit halves of the lanes every 12-term sum is an
+//    integer < 2^42 — exactly representable in binary64.  B200 issues DFMA at the same rate as
+//    IMAD and on its own pipe, and a DFMA accumulates for free (IMAD.WIDE with a 64-bit addend
+//    runs at ~5 clk/warp), so the layer is 2 x 144 DFMA on the FP64 pipe, overlapping the integer
+//    pipes.  u32 -> f64 is the 2^52 trick (one DADD); the next round's constants and the 2^52 bias
+//    are pre-folded into the accumulator's initial value (constant-bank operand), and the integer
+//    comes back as the mantissa bits.  Every step is exact integer arithmetic; no rounding occurs.
+//  * One rolled loop over the 30 rounds (full-round S-boxes behind a warp-uniform branch) keeps the
+//    hot code inside the instruction cache (the fully unrolled version stalled on instruction fetch).
+// Tensor cores are deliberately unused (64-bit modular arithmetic).
 #pragma once
 #include "gl.cuh"
 #include "poseidon_constants.h"
@@ -24,34 +33,46 @@ constexpr int WIDTH = 12, RATE = 8, HALF_FULL = 4, PARTIAL = 22, ROUNDS = 30;
 
 #if defined(__CUDACC__)
 static __constant__ uint64_t RC[360] = ETP_POSEIDON_RC_TABLE;
+static __constant__ uint64_t RC_F64[30 * 24] = ETP_POSEIDON_RC_F64_TABLE;
 
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
-  uint64_t x2 = gl::sqr(x);
-  uint64_t x4 = gl::sqr(x2);
+  uint64_t x2 = gl::mul(x, x);
+  uint64_t x4 = gl::mul(x2, x2);
   uint64_t x3 = gl::mul(x, x2);
   return gl::mul(x3, x4);
 }
 
-// s <- MDS(s) + rc[0..12] (rc == nullptr: no constants, used after the last round)
-__device__ __forceinline__ void mds_add_rc(uint64_t (&s)[12], const uint64_t* __restrict__ rc) {
-  constexpr uint32_t C[12] = ETP_MDS_CIRC;
-  uint32_t lo[12], hi[12];
+// exact u32 -> f64: the double with bit pattern (0x43300000 : x) is 2^52 + x
+__device__ __forceinline__ double u32_to_f64(uint32_t x) {
+  return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+}
+
+// s <- MDS(s) + next round constants; rcd = 24 f64 bit patterns (2^52 + lo32, 2^52 + hi32) per lane
+__device__ __forceinline__ void mds_add_rc_f64(uint64_t (&s)[12], const uint64_t* __restrict__ rcd) {
+  constexpr double C[12] = ETP_MDS_CIRC;
+  double xl[12], xh[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) { lo[i] = (uint32_t)s[i]; hi[i] = (uint32_t)(s[i] >> 32); }
+  for (int i = 0; i < 12; i++) {
+    xl[i] = u32_to_f64((uint32_t)s[i]);
+    xh[i] = u32_to_f64((uint32_t)(s[i] >> 32));
+  }
 #pragma unroll
   for (int r = 0; r < 12; r++) {
-    uint64_t k = rc ? rc[r] : 0;
-    uint64_t al = (uint32_t)k, ah = k >> 32;
+    double al = __longlong_as_double((long long)rcd[2 * r]);
+    double ah = __longlong_as_double((long long)rcd[2 * r + 1]);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-      al += (uint64_t)lo[(i + r) % 12] * C[i];
-      ah += (uint64_t)hi[(i + r) % 12] * C[i];
+      const double c = (r == 0 && i == 0) ? C[0] + 8.0 : C[i];  // MDS_MATRIX_DIAG[0] = 8
+      al = fma(xl[(i + r) % 12], c, al);
+      ah = fma(xh[(i + r) % 12], c, ah);
     }
-    if (r == 0) { al += (uint64_t)lo[0] * 8u; ah += (uint64_t)hi[0] * 8u; }  // MDS_MATRIX_DIAG[0] = 8
-    // value = al + ah*2^32, al, ah < 2^42.  ah = h1*2^32 + h0  =>  == al + h1*EPS + h0*2^32 (mod p)
-    uint32_t h0 = (uint32_t)ah, h1 = (uint32_t)(ah >> 32);
-    uint64_t t = al + (uint64_t)h1 * 0xFFFFFFFFu;  // < 2^43, no overflow
-    s[r] = gl::add_c(t, (uint64_t)h0 << 32);       // h0 << 32 < p: one fix-up is exact
+    // al = 2^52 + L, ah = 2^52 + H with L, H < 2^43: the mantissa bits ARE the integers
+    const uint64_t L = (uint64_t)__double_as_longlong(al) & 0xFFFFFFFFFFFFFull;
+    const uint64_t H = (uint64_t)__double_as_longlong(ah) & 0xFFFFFFFFFFFFFull;
+    // value = L + H*2^32,  H = h1*2^32 + h0  =>  == L + h1*EPS + h0*2^32  (mod p)
+    const uint32_t h0 = (uint32_t)H, h1 = (uint32_t)(H >> 32);
+    const uint64_t t = L + (((uint64_t)h1 << 32) - h1);  // < 2^44, no overflow
+    s[r] = gl::add_c(t, (uint64_t)h0 << 32);              // h0 << 32 < p: one fix-up is exact
   }
 }
 
@@ -59,27 +80,15 @@ __device__ __forceinline__ void mds_add_rc(uint64_t (&s)[12], const uint64_t* __
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_c(s[i], RC[i]);
-  int r = 0;
 #pragma unroll 1
-  for (; r < HALF_FULL; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-    mds_add_rc(s, RC + 12 * (r + 1));
-  }
-#pragma unroll 1
-  for (; r < HALF_FULL + PARTIAL; r++) {
+  for (int r = 0; r < ROUNDS; r++) {
     s[0] = sbox7(s[0]);
-    mds_add_rc(s, RC + 12 * (r + 1));
-  }
-#pragma unroll 1
-  for (; r < ROUNDS - 1; r++) {
+    if (r < HALF_FULL || r >= HALF_FULL + PARTIAL) {  // warp-uniform
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-    mds_add_rc(s, RC + 12 * (r + 1));
+      for (int i = 1; i < 12; i++) s[i] = sbox7(s[i]);
+    }
+    mds_add_rc_f64(s, RC_F64 + 24 * r);
   }
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
-  mds_add_rc(s, nullptr);
 }
 #endif  // __CUDACC__
 
