@@ -1,0 +1,483 @@
+// Device kernels of the starky / FRI part of the path (K6, K7, K8 in SURVEY.md 2.4).
+//
+// Replaces (third-party crates, not on disk; pins at /root/reference/Cargo.lock:3441,4529,1675; reached
+// from /root/reference/ops/src/lib.rs:52):
+//   starky 0.4.0   src/prover.rs              compute_quotient_polys
+//                  src/constraint_consumer.rs ConstraintConsumer
+//                  src/lookup.rs              lookup_helper_columns, eval_packed_lookups_generic
+//                  src/proof.rs               StarkOpeningSet::new
+//                  src/fibonacci_stark.rs     FibonacciStark::eval_packed_generic
+//   evm_arithmetization 0.1.3 src/memory/memory_stark.rs  (memory-shaped table)
+//   plonky2 0.2.2  src/fri/oracle.rs          prove_openings (reduce_polys_base, divide_by_linear, lde)
+//                  src/fri/prover.rs          fri_committed_trees (fold), fri_proof_of_work
+// All matrices are column-major; LDE matrices are in bit-reversed row order (position p <-> point
+// index bitrev(p)), which is plonky2's leaf order.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gl.cuh"
+#include "ntt.cuh"
+#include "poseidon.cuh"
+
+namespace stark {
+
+constexpr int MAX_CHALLENGES = 2;
+constexpr uint64_t MEM_TRIE_DATA_SEGMENT = 13;
+enum { M_FILTER = 0, M_TIMESTAMP, M_IS_READ, M_CTX, M_SEG, M_VIRT, M_VALUE0, M_CFC = 14, M_SFC, M_VFC, M_INIT_AUX,
+       M_RANGE_CHECK, M_COUNTER, M_FREQ };
+
+// ---- ConstraintConsumer ------------------------------------------------------------------------
+struct Consumer {
+  uint64_t alphas[MAX_CHALLENGES], acc[MAX_CHALLENGES];
+  uint64_t z_last, lagrange_first, lagrange_last;
+  int n;
+  __device__ __forceinline__ void constraint(uint64_t c) {
+#pragma unroll
+    for (int j = 0; j < MAX_CHALLENGES; j++)
+      if (j < n) acc[j] = gl::add(gl::mul(acc[j], alphas[j]), c);
+  }
+  __device__ __forceinline__ void transition(uint64_t c) { constraint(gl::mul(c, z_last)); }
+  __device__ __forceinline__ void first_row(uint64_t c) { constraint(gl::mul(c, lagrange_first)); }
+  __device__ __forceinline__ void last_row(uint64_t c) { constraint(gl::mul(c, lagrange_last)); }
+};
+
+template <int TABLE>
+struct Table;
+
+// starky/src/fibonacci_stark.rs
+template <>
+struct Table<0> {
+  static constexpr int COLS = 2, AUX = 0;
+  __device__ static __forceinline__ void eval(const uint64_t* lv, const uint64_t* nv, const uint64_t* pi, Consumer& c) {
+    c.first_row(gl::sub(lv[0], pi[0]));
+    c.first_row(gl::sub(lv[1], pi[1]));
+    c.last_row(gl::sub(lv[1], pi[2]));
+    c.transition(gl::sub(nv[0], lv[1]));
+    c.transition(gl::sub(gl::sub(nv[1], lv[0]), lv[1]));
+  }
+  __device__ static __forceinline__ void eval_lookups(const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, int, Consumer&) {}
+};
+
+// memory-shaped table: constraint list and order of SURVEY.md Appendix A
+template <>
+struct Table<1> {
+  static constexpr int COLS = 21, AUX = 4;
+  __device__ static __forceinline__ void eval(const uint64_t* lv, const uint64_t* nv, const uint64_t*, Consumer& c) {
+    const uint64_t one = 1;
+    const uint64_t filter = lv[M_FILTER];
+    c.constraint(gl::mul(filter, gl::sub(filter, one)));
+    c.constraint(gl::mul(gl::sub(one, filter), gl::sub(one, lv[M_IS_READ])));
+    const uint64_t cfc = lv[M_CFC], sfc = lv[M_SFC], vfc = lv[M_VFC];
+    const uint64_t unchanged = gl::sub(gl::sub(gl::sub(one, cfc), sfc), vfc);
+    c.constraint(gl::mul(cfc, gl::sub(one, cfc)));
+    c.constraint(gl::mul(sfc, gl::sub(one, sfc)));
+    c.constraint(gl::mul(vfc, gl::sub(one, vfc)));
+    c.constraint(gl::mul(unchanged, gl::sub(one, unchanged)));
+    const uint64_t d_ctx = gl::sub(nv[M_CTX], lv[M_CTX]), d_seg = gl::sub(nv[M_SEG], lv[M_SEG]);
+    const uint64_t d_virt = gl::sub(nv[M_VIRT], lv[M_VIRT]), d_ts = gl::sub(nv[M_TIMESTAMP], lv[M_TIMESTAMP]);
+    c.transition(gl::mul(sfc, d_ctx));
+    c.transition(gl::mul(vfc, d_ctx));
+    c.transition(gl::mul(vfc, d_seg));
+    c.transition(gl::mul(unchanged, d_ctx));
+    c.transition(gl::mul(unchanged, d_seg));
+    c.transition(gl::mul(unchanged, d_virt));
+    const uint64_t computed =
+        gl::add(gl::add(gl::mul(cfc, gl::sub(d_ctx, one)), gl::mul(sfc, gl::sub(d_seg, one))),
+                gl::add(gl::mul(vfc, gl::sub(d_virt, one)), gl::mul(unchanged, d_ts)));
+    c.transition(gl::sub(lv[M_RANGE_CHECK], computed));
+    const uint64_t init_aux = lv[M_INIT_AUX];
+    c.transition(gl::sub(init_aux, gl::mul(gl::mul(nv[M_SEG], gl::sub(one, unchanged)), nv[M_IS_READ])));
+    const uint64_t read_unchanged = gl::mul(nv[M_IS_READ], unchanged);
+    const uint64_t ctx_init = gl::mul(nv[M_CTX], init_aux);
+    const uint64_t seg_init = gl::mul(gl::sub(nv[M_SEG], MEM_TRIE_DATA_SEGMENT), init_aux);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint64_t v = lv[M_VALUE0 + i], nvv = nv[M_VALUE0 + i];
+      c.transition(gl::mul(read_unchanged, gl::sub(nvv, v)));
+      c.transition(gl::mul(ctx_init, nvv));
+      c.transition(gl::mul(seg_init, nvv));
+    }
+    c.first_row(lv[M_COUNTER]);
+    c.transition(gl::sub(gl::sub(nv[M_COUNTER], lv[M_COUNTER]), one));
+  }
+  // eval_packed_lookups_generic: one lookup (RANGE_CHECK in COUNTER, multiplicities FREQUENCIES), per challenge
+  // one helper column h = 1/(f + ch) and one Z column
+  __device__ static __forceinline__ void eval_lookups(const uint64_t* lv, const uint64_t* al, const uint64_t* an,
+                                                      const uint64_t* challenges, int n_ch, Consumer& c) {
+#pragma unroll
+    for (int k = 0; k < MAX_CHALLENGES; k++) {
+      if (k >= n_ch) break;
+      const uint64_t ch = challenges[k];
+      const uint64_t h = al[2 * k], z = al[2 * k + 1], next_z = an[2 * k + 1];
+      c.constraint(gl::sub(gl::mul(gl::add(lv[M_RANGE_CHECK], ch), h), 1));
+      const uint64_t twc = gl::add(lv[M_COUNTER], ch);
+      const uint64_t y = gl::sub(gl::mul(h, twc), lv[M_FREQ]);
+      c.first_row(z);
+      c.constraint(gl::sub(gl::mul(gl::sub(next_z, z), twc), y));
+    }
+  }
+};
+
+struct QuotientParams {
+  const uint64_t* trace;  // LDE, bit-reversed rows
+  size_t trace_stride;
+  const uint64_t* aux;
+  size_t aux_stride;
+  int log_lde;      // degree_bits + rate_bits
+  int log_size;     // degree_bits + quotient_degree_bits
+  int step_log;     // rate_bits - quotient_degree_bits
+  int next_step;    // 1 << quotient_degree_bits
+  ntt::PowTable coset;  // 7 * w_size^i
+  const uint64_t* lag_first;  // per position p < size: L_first, L_last at the point of position p
+  const uint64_t* lag_last;
+  uint64_t zh_inv[4];    // 1/Z_H per (i mod 2^qbits)
+  uint64_t last;         // g^-1
+  uint64_t alphas[MAX_CHALLENGES];
+  int n_alphas;
+  uint64_t lookup_ch[MAX_CHALLENGES];
+  int n_lookup_ch;
+  uint64_t pi[4];
+  uint64_t* out;  // n_alphas columns x size, NATURAL order (input of coset_ifft)
+};
+
+// One thread per position p of the quotient coset inside the LDE (p < size): local row = LDE row p,
+// next row = the row of point index k + next_step*step.
+template <int TABLE>
+static __global__ void __launch_bounds__(128) quotient_kernel(QuotientParams q) {
+  using T = Table<TABLE>;
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t size = 1u << q.log_size;
+  if (p >= size) return;
+  const uint32_t k = gl::bitrev32(p, q.log_lde);                 // LDE point index, multiple of step
+  const uint32_t i = k >> q.step_log;                              // index on the quotient coset
+  const uint32_t i_next = (i + q.next_step) & (size - 1);
+  const uint32_t p_next = gl::bitrev32(i_next << q.step_log, q.log_lde);
+  uint64_t lv[T::COLS], nv[T::COLS];
+#pragma unroll
+  for (int c = 0; c < T::COLS; c++) {
+    lv[c] = __ldg(q.trace + (size_t)c * q.trace_stride + p);
+    nv[c] = __ldg(q.trace + (size_t)c * q.trace_stride + p_next);
+  }
+  Consumer cs;
+  cs.n = q.n_alphas;
+#pragma unroll
+  for (int j = 0; j < MAX_CHALLENGES; j++) { cs.alphas[j] = q.alphas[j]; cs.acc[j] = 0; }
+  const uint64_t x = q.coset.get(i);
+  cs.z_last = gl::sub(x, q.last);
+  cs.lagrange_first = q.lag_first[p];
+  cs.lagrange_last = q.lag_last[p];
+  T::eval(lv, nv, q.pi, cs);
+  if (T::AUX > 0) {
+    uint64_t al[T::AUX > 0 ? T::AUX : 1], an[T::AUX > 0 ? T::AUX : 1];
+#pragma unroll
+    for (int c = 0; c < T::AUX; c++) {
+      al[c] = __ldg(q.aux + (size_t)c * q.aux_stride + p);
+      an[c] = __ldg(q.aux + (size_t)c * q.aux_stride + p_next);
+    }
+    T::eval_lookups(lv, al, an, q.lookup_ch, q.n_lookup_ch, cs);
+  }
+  const uint64_t dinv = q.zh_inv[i & (q.next_step - 1)];
+#pragma unroll
+  for (int j = 0; j < MAX_CHALLENGES; j++)
+    if (j < q.n_alphas) q.out[(size_t)j * size + i] = gl::mul(cs.acc[j], dinv);
+}
+
+// ---- Lagrange selectors on the coset: L_first(x) = Z_H(x) / (n (x - 1)), L_last(x) = Z_H(x) / (n (g x - 1)) ----
+// step 1: denominators (two per position), step 2: batch inverse, step 3: multiply by Z_H(x)
+static __global__ void lagrange_denominators(int log_lde, int log_size, int step_log, ntt::PowTable coset, uint64_t n_field,
+                                             uint64_t g, uint64_t* den /* 2 x size */) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t size = 1u << log_size;
+  if (p >= size) return;
+  const uint32_t i = gl::bitrev32(p, log_lde) >> step_log;
+  const uint64_t x = coset.get(i);
+  den[p] = gl::mul(n_field, gl::sub(x, 1));
+  den[size + p] = gl::mul(n_field, gl::sub(gl::mul(g, x), 1));
+}
+struct ZhVals { uint64_t v[4]; };  // Z_H(x_i) per (i mod 2^qbits)
+static __global__ void lagrange_finish(int log_lde, int log_size, int step_log, int qmask, ZhVals zhv,
+                                       uint64_t* inv /* 2 x size, in place */) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t size = 1u << log_size;
+  if (p >= size) return;
+  const uint32_t i = gl::bitrev32(p, log_lde) >> step_log;
+  const uint64_t z = zhv.v[i & qmask];
+  inv[p] = gl::canon(gl::mul(inv[p], z));
+  inv[size + p] = gl::canon(gl::mul(inv[size + p], z));
+}
+
+// ---- batch inverse (Montgomery's trick inside each thread, K strided elements per thread) ----------
+// All inputs must be non-zero (callers guarantee it or report ETP_ERR_PROOF).
+constexpr int INV_K = 8;
+static __global__ void batch_inverse(const uint64_t* in, uint64_t* out, size_t n) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint64_t v[INV_K], pre[INV_K];
+  uint64_t acc = 1;
+#pragma unroll
+  for (int k = 0; k < INV_K; k++) {
+    const size_t idx = t + k * stride;
+    v[k] = idx < n ? in[idx] : 1;
+    pre[k] = acc;
+    acc = gl::mul(acc, v[k]);
+  }
+  uint64_t inv = gl::inv(acc);
+#pragma unroll
+  for (int k = INV_K - 1; k >= 0; k--) {
+    const size_t idx = t + k * stride;
+    if (idx < n) out[idx] = gl::canon(gl::mul(inv, pre[k]));
+    inv = gl::mul(inv, v[k]);
+  }
+}
+
+// ---- lookup helper columns -----------------------------------------------------------------------
+// den[0][i] = looking[i] + ch, den[1][i] = table[i] + ch
+static __global__ void lookup_denominators(const uint64_t* __restrict__ looking, const uint64_t* __restrict__ table, uint64_t ch,
+                                           size_t n, uint64_t* __restrict__ den) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  den[i] = gl::add(looking[i], ch);
+  den[n + i] = gl::add(table[i], ch);
+}
+// term[i] = h[i] - freq[i] * tinv[i]
+static __global__ void lookup_terms(const uint64_t* __restrict__ inv /* 2 x n */, const uint64_t* __restrict__ freq, size_t n,
+                                    uint64_t* __restrict__ h_out, uint64_t* __restrict__ term) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t h = inv[i];
+  h_out[i] = h;
+  term[i] = gl::canon(gl::sub(h, gl::mul(freq[i], inv[n + i])));
+}
+// exclusive prefix sum over the field, 3 phases; SCAN_BLOCK elements per block
+constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_PER_THREAD;
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums(const uint64_t* __restrict__ in, size_t n, uint64_t* __restrict__ sums) {
+  __shared__ uint64_t sh[SCAN_THREADS];
+  const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+  uint64_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER_THREAD; k++)
+    if (base + k < n) acc = gl::add(acc, in[base + k]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = SCAN_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = gl::add(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[blockIdx.x] = gl::canon(sh[0]);
+}
+static __global__ void scan_sums_serial(uint64_t* sums, size_t n_blocks) {  // tiny: exclusive scan in place
+  if (blockIdx.x || threadIdx.x) return;
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n_blocks; i++) { const uint64_t v = sums[i]; sums[i] = acc; acc = gl::canon(gl::add(acc, v)); }
+}
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_finish(const uint64_t* __restrict__ in, size_t n, const uint64_t* __restrict__ sums,
+                                                                   uint64_t* __restrict__ out) {
+  __shared__ uint64_t sh[SCAN_THREADS];
+  const size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_PER_THREAD;
+  uint64_t v[SCAN_PER_THREAD];
+  uint64_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER_THREAD; k++) { v[k] = base + k < n ? in[base + k] : 0; acc = gl::add(acc, v[k]); }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  // exclusive scan of the per-thread sums (Hillis-Steele; 256 entries)
+  uint64_t mine = acc;
+  for (int s = 1; s < SCAN_THREADS; s <<= 1) {
+    uint64_t add = threadIdx.x >= s ? sh[threadIdx.x - s] : 0;
+    __syncthreads();
+    mine = gl::add(mine, add);
+    sh[threadIdx.x] = mine;
+    __syncthreads();
+  }
+  uint64_t run = gl::add(sums[blockIdx.x], gl::sub(mine, acc));  // exclusive prefix of this thread
+#pragma unroll
+  for (int k = 0; k < SCAN_PER_THREAD; k++) {
+    if (base + k < n) out[base + k] = gl::canon(run);
+    run = gl::add(run, v[k]);
+  }
+}
+
+// ---- openings: evaluate every polynomial of a batch at two extension points ------------------------
+// partial[block][poly][point] (ext).  pw0 / pw1: powers of the two points via two-level ext tables.
+struct ExtPowTable {
+  const uint64_t* lo;  // interleaved ext, 2^lo_bits entries
+  const uint64_t* hi;
+  int lo_bits;
+  __device__ __forceinline__ gl::Ext get(uint32_t e) const {
+    const uint32_t a = e >> lo_bits, b = e & ((1u << lo_bits) - 1);
+    return gl::emul(gl::ext(hi[2 * a], hi[2 * a + 1]), gl::ext(lo[2 * b], lo[2 * b + 1]));
+  }
+};
+constexpr int OPEN_THREADS = 256, OPEN_CHUNK = 16, OPEN_POLYS = 8;
+// grid: (n / (OPEN_THREADS*OPEN_CHUNK), ceil(n_polys / OPEN_POLYS)); each thread walks OPEN_CHUNK consecutive
+// coefficients, keeping z^i for both points, for OPEN_POLYS polynomials at once.
+static __global__ void __launch_bounds__(OPEN_THREADS) eval_polys_at_two_points(const uint64_t* __restrict__ coeffs, size_t col_stride,
+                                                                                int n_polys, uint32_t n, ExtPowTable t0, ExtPowTable t1,
+                                                                                gl::Ext z0, gl::Ext z1, uint64_t* __restrict__ partial) {
+  __shared__ uint64_t sh[OPEN_THREADS * 4];
+  const int poly0 = blockIdx.y * OPEN_POLYS;
+  const uint32_t start = (blockIdx.x * OPEN_THREADS + threadIdx.x) * OPEN_CHUNK;
+  gl::Ext a0[OPEN_POLYS], a1[OPEN_POLYS];
+#pragma unroll
+  for (int q = 0; q < OPEN_POLYS; q++) { a0[q] = gl::ext(0, 0); a1[q] = gl::ext(0, 0); }
+  if (start < n) {
+    gl::Ext p0 = t0.get(start), p1 = t1.get(start);
+    for (int k = 0; k < OPEN_CHUNK; k++) {
+#pragma unroll
+      for (int q = 0; q < OPEN_POLYS; q++) {
+        if (poly0 + q < n_polys) {
+          const uint64_t c = __ldg(coeffs + (size_t)(poly0 + q) * col_stride + start + k);
+          a0[q] = gl::eadd(a0[q], gl::emul_base(p0, c));
+          a1[q] = gl::eadd(a1[q], gl::emul_base(p1, c));
+        }
+      }
+      p0 = gl::emul(p0, z0);
+      p1 = gl::emul(p1, z1);
+    }
+  }
+  // block reduction, one polynomial at a time
+  for (int q = 0; q < OPEN_POLYS; q++) {
+    if (poly0 + q >= n_polys) break;
+    sh[4 * threadIdx.x + 0] = a0[q].c0; sh[4 * threadIdx.x + 1] = a0[q].c1;
+    sh[4 * threadIdx.x + 2] = a1[q].c0; sh[4 * threadIdx.x + 3] = a1[q].c1;
+    __syncthreads();
+    for (int s = OPEN_THREADS / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s)
+        for (int w = 0; w < 4; w++) sh[4 * threadIdx.x + w] = gl::add(sh[4 * threadIdx.x + w], sh[4 * (threadIdx.x + s) + w]);
+      __syncthreads();
+    }
+    if (threadIdx.x < 4) partial[((size_t)blockIdx.x * n_polys + poly0 + q) * 4 + threadIdx.x] = gl::canon(sh[threadIdx.x]);
+    __syncthreads();
+  }
+}
+
+// ---- prove_openings in evaluation form -----------------------------------------------------------
+// final(x) = alpha^shift0 * (sum_{k<n0} alpha^k f_k(x) - y0) / (x - z0) + (sum_{k<n1} alpha^k f_k(x) - y1) / (x - z1)
+// over the LDE coset, where the n1 polynomials of the second batch are a PREFIX of the n0 of the first
+// (trace ++ aux ++ quotient at zeta; trace ++ aux at g*zeta).  This equals coset_fft(final_poly.lde())
+// of upstream's coefficient-form computation point by point.
+struct CombineParams {
+  const uint64_t* cols[3];   // LDE matrices (trace, aux, quotient), bit-reversed rows
+  size_t strides[3];
+  int n_cols[3];
+  int n1;                    // columns in the second batch (prefix)
+  int log_lde;
+  ntt::PowTable coset;       // 7 * w^k
+  const uint64_t* alpha_pows;  // device: (n0 + 1) ext, interleaved; alpha^k
+  gl::Ext y0, y1, z0, z1, shift0;  // shift0 = alpha^n1
+  uint64_t seven_z0c1_sq, seven_z1c1_sq;
+  uint64_t* den;   // 2 x lde_n: norms to invert (phase 1) / inverted norms (phase 2)
+  uint64_t* out;   // lde_n ext interleaved, bit-reversed order
+};
+static __global__ void combine_norms(CombineParams c) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = 1u << c.log_lde;
+  if (p >= n) return;
+  const uint64_t x = c.coset.get(gl::bitrev32(p, c.log_lde));
+  // norm of (x - z) = (x - z.c0)^2 - 7 z.c1^2   (7 z.c1^2 is precomputed on the host)
+  const uint64_t a0 = gl::sub(x, c.z0.c0), a1 = gl::sub(x, c.z1.c0);
+  c.den[p] = gl::canon(gl::sub(gl::mul(a0, a0), c.seven_z0c1_sq));
+  c.den[n + p] = gl::canon(gl::sub(gl::mul(a1, a1), c.seven_z1c1_sq));
+}
+static __global__ void __launch_bounds__(128) combine_values(CombineParams c) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = 1u << c.log_lde;
+  if (p >= n) return;
+  gl::Ext acc = gl::ext(0, 0), acc1 = gl::ext(0, 0);
+  int k = 0;
+  for (int m = 0; m < 3; m++) {
+    for (int col = 0; col < c.n_cols[m]; col++, k++) {
+      if (k == c.n1) acc1 = acc;
+      const uint64_t v = __ldg(c.cols[m] + (size_t)col * c.strides[m] + p);
+      const gl::Ext a = gl::ext(c.alpha_pows[2 * k], c.alpha_pows[2 * k + 1]);
+      acc = gl::eadd(acc, gl::emul_base(a, v));
+    }
+  }
+  if (k == c.n1) acc1 = acc;
+  const uint64_t x = c.coset.get(gl::bitrev32(p, c.log_lde));
+  // 1/(x - z) = conj(x - z) / norm
+  const uint64_t i0 = c.den[p], i1 = c.den[n + p];
+  const gl::Ext inv0 = gl::ext(gl::mul(gl::sub(x, c.z0.c0), i0), gl::mul(c.z0.c1, i0));   // (x - z0.c0, -(-z0.c1)) / norm
+  const gl::Ext inv1 = gl::ext(gl::mul(gl::sub(x, c.z1.c0), i1), gl::mul(c.z1.c1, i1));
+  const gl::Ext q0 = gl::emul(gl::esub(acc, c.y0), inv0);
+  const gl::Ext q1 = gl::emul(gl::esub(acc1, c.y1), inv1);
+  const gl::Ext f = gl::ecanon(gl::eadd(gl::emul(q0, c.shift0), q1));
+  c.out[2 * (size_t)p] = f.c0;
+  c.out[2 * (size_t)p + 1] = f.c1;
+}
+
+// ---- FRI fold in evaluation form (arity 2^4) -------------------------------------------------------
+// Leaf j of a layer holds the 16 values at points x0 * w16^bitrev4(t), x0 = shift * w_n^bitrev(j).
+// With u = IDFT16(values in natural order m), the folded value at y = x0^16 is sum_i (beta/x0)^i u_i —
+// the value at y of upstream's reduce_with_powers(coefficient chunks, beta).  Output position j is the
+// bit-reversed position of y in the next layer.
+struct FoldParams {
+  const uint64_t* in;   // n ext interleaved
+  uint64_t* out;        // n/16 ext interleaved
+  int log_n;            // current layer size
+  ntt::PowTable x0_inv; // shift^-1 * (w_n^-1)^k
+  gl::Ext beta;
+  uint64_t w16_inv_pows[16];  // (w16^-1)^e
+  uint64_t inv16;
+};
+static __global__ void __launch_bounds__(128) fri_fold16(FoldParams f) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_out = 1u << (f.log_n - 4);
+  if (j >= n_out) return;
+  gl::Ext v[16];
+#pragma unroll
+  for (int t = 0; t < 16; t++) {
+    const ulonglong2 e = reinterpret_cast<const ulonglong2*>(f.in)[16 * (size_t)j + t];
+    v[gl::bitrev32(t, 4)] = gl::ext(e.x, e.y);  // natural order m = bitrev4(t)
+  }
+  const gl::Ext gamma = gl::emul_base(f.beta, f.x0_inv.get(gl::bitrev32(j, f.log_n - 4)));
+  // result = (1/16) * sum_i gamma^i * sum_m v_m w16^(-i m): Horner over i from 15 down to 0
+  gl::Ext acc = gl::ext(0, 0);
+#pragma unroll 1
+  for (int i = 15; i >= 0; i--) {
+    gl::Ext u = gl::ext(0, 0);
+#pragma unroll
+    for (int m = 0; m < 16; m++) u = gl::eadd(u, gl::emul_base(v[m], f.w16_inv_pows[(i * m) & 15]));
+    acc = gl::eadd(gl::emul(acc, gamma), u);
+  }
+  acc = gl::ecanon(gl::emul_base(acc, f.inv16));
+  reinterpret_cast<ulonglong2*>(f.out)[j] = make_ulonglong2(acc.c0, acc.c1);
+}
+
+// ---- proof of work --------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(128) pow_grind(const uint64_t* __restrict__ state, int pos, int bits, uint64_t base,
+                                                        unsigned long long* __restrict__ result) {
+  const uint64_t cand = base + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (cand >= gl::P) return;
+  uint64_t s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = (i == pos) ? cand : state[i];
+  poseidon::permute(s);
+  const uint64_t resp = gl::canon(s[7]);
+  if (bits == 0 || (resp >> (64 - bits)) == 0) atomicMin(result, (unsigned long long)cand);
+}
+
+// ---- gathers for the query phase --------------------------------------------------------------------
+// out[q][i] = levels[i][(idx[q] >> i) ^ 1], i < num_layers
+static __global__ void gather_paths(const uint64_t* __restrict__ levels, uint32_t n_leaves, int num_layers,
+                                    const uint64_t* __restrict__ idx, int n_idx, uint64_t* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_idx * num_layers) return;
+  const int q = t / num_layers, i = t % num_layers;
+  size_t off = 0;
+  for (int l = 0; l < i; l++) off += 4 * (size_t)(n_leaves >> l);
+  const uint64_t node = (idx[q] >> i) ^ 1;
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(levels + off + 4 * node);
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + 4 * (size_t)t);
+  dst[0] = src[0];
+  dst[1] = src[1];
+}
+static __global__ void gather_rows_rowmajor(const uint64_t* __restrict__ rows, int row_len, const uint64_t* __restrict__ idx, int n_idx,
+                                            uint64_t* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_idx * row_len) return;
+  const int q = t / row_len, c = t % row_len;
+  out[t] = gl::canon(rows[(size_t)idx[q] * row_len + c]);
+}
+
+}  // namespace stark
