@@ -77,6 +77,7 @@ def load_library():
         "etp_batch_from_values_dev": (i32, [vp, vp, sz, sz, i32, i32, i32, i32, pp]),
         "etp_batch_from_coeffs_dev": (i32, [vp, vp, sz, sz, i32, i32, i32, i32, pp]),
         "etp_batch_recommit_values_dev": (i32, [vp, vp, sz]),
+        "etp_batch_last_commit_timings": (i32, [vp, C.POINTER(C.c_float)]),
         "etp_batch_free": (None, [vp]),
         "etp_batch_num_cols": (sz, [vp]),
         "etp_batch_degree_log": (i32, [vp]),
@@ -340,6 +341,12 @@ class PolynomialBatch:
 
     def recommit_values_dev(self, ptr: int, col_stride: int):
         self.ctx.check(self.ctx.L.etp_batch_recommit_values_dev(self.h, C.c_void_p(ptr), col_stride))
+
+    def last_commit_timings(self) -> dict:
+        ms = (C.c_float * 4)()
+        self.ctx.check(self.ctx.L.etp_batch_last_commit_timings(self.h, ms))
+        return {"IFFT": ms[0], "FFT + blinding": ms[1], "build Merkle tree (leaves)": ms[2],
+                "build Merkle tree (levels)": ms[3]}
 
     @property
     def n(self):

@@ -143,6 +143,8 @@ struct etp_batch {
   uint64_t* lde = nullptr;     // n_cols x (n << rate_bits), bit-reversed row order
   uint64_t* levels = nullptr;
   std::vector<uint64_t> cap;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last commit
+  bool timed_ifft = false;
   size_t n() const { return (size_t)1 << log_n; }
   size_t lde_n() const { return (size_t)1 << (log_n + rate_bits); }
 };

@@ -385,12 +385,15 @@ int batch_create(etp_ctx* ctx, size_t n_cols, int log_n, int rate_bits, int blin
   if (rc == ETP_OK) rc = dev_alloc(ctx, n_cols * b->lde_n() * 8, (void**)&b->lde);
   if (rc == ETP_OK) rc = dev_alloc(ctx, levels_words(b->lde_n(), cap_height) * 8, (void**)&b->levels);
   if (rc != ETP_OK) { etp_batch_free(b); return rc; }
+  for (auto& e : b->ev) cudaEventCreate(&e);
   *out = b;
   return ETP_OK;
 }
 
 int batch_commit_from_coeffs(etp_batch* b) {
   etp_ctx* ctx = b->ctx;
+  if (!b->timed_ifft) cudaEventRecord(b->ev[0], ctx->stream);
+  cudaEventRecord(b->ev[1], ctx->stream);
   // "FFT + blinding": zero-pad to n << rate_bits, coset_fft(7); bit-reversed order comes for free
   NttArgs args;
   args.in = b->coeffs; args.in_stride = b->n(); args.n_in = (uint32_t)b->n();
@@ -398,16 +401,35 @@ int batch_commit_from_coeffs(etp_batch* b) {
   args.log_n = b->log_n + b->rate_bits; args.n_cols = b->n_cols;
   args.coset_shift = gl::GENERATOR;
   ETP_TRY(ntt_run(ctx, args));
+  cudaEventRecord(b->ev[2], ctx->stream);
   // "build Merkle tree"
   const uint32_t nl = (uint32_t)b->lde_n();
   merkle::hash_leaves_colmajor<<<(nl + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
       b->lde, b->lde_n(), (int)b->n_cols, nl, b->levels);
   ETP_LAUNCH_CHECK(ctx);
-  return merkle_build_levels(ctx, b->levels, b->lde_n(), b->cap_height, b->cap.data());
+  cudaEventRecord(b->ev[3], ctx->stream);
+  b->timed_ifft = false;
+  // the cap copy inside merkle_build_levels synchronises; record the end marker before it
+  size_t n = b->lde_n();
+  uint64_t* cur = b->levels;
+  while (n > ((size_t)1 << b->cap_height)) {
+    uint64_t* nxt = cur + 4 * n;
+    const uint32_t parents = (uint32_t)(n >> 1);
+    merkle::hash_level<<<(parents + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(cur, parents, nxt);
+    ETP_LAUNCH_CHECK(ctx);
+    cur = nxt;
+    n >>= 1;
+  }
+  cudaEventRecord(b->ev[4], ctx->stream);
+  ETP_CUDA(ctx, cudaMemcpyAsync(b->cap.data(), cur, ((size_t)32) << b->cap_height, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
 }
 
 int batch_commit_from_values(etp_batch* b, const uint64_t* values_dev, size_t col_stride) {
   // "IFFT": natural -> natural; the LDE buffer doubles as scratch for the multi-pass transform
+  cudaEventRecord(b->ev[0], b->ctx->stream);
+  b->timed_ifft = true;
   NttArgs args;
   args.in = values_dev; args.in_stride = col_stride; args.n_in = (uint32_t)b->n();
   args.out = b->coeffs; args.out_stride = b->n();
@@ -497,8 +519,17 @@ extern "C" int etp_batch_recommit_values_dev(etp_batch* b, const uint64_t* value
   return batch_commit_from_values(b, values_dev, col_stride);
 }
 
+extern "C" int etp_batch_last_commit_timings(const etp_batch* b, float ms_out[4]) {
+  if (!b || !ms_out) return ETP_ERR_INVALID;
+  for (int i = 0; i < 4; i++)
+    if (cudaEventElapsedTime(&ms_out[i], b->ev[i], b->ev[i + 1]) != cudaSuccess) return ETP_ERR_STATE;
+  return ETP_OK;
+}
+
 extern "C" void etp_batch_free(etp_batch* b) {
   if (!b) return;
+  for (auto& e : b->ev)
+    if (e) cudaEventDestroy(e);
   dev_free(b->ctx, b->coeffs);
   dev_free(b->ctx, b->lde);
   dev_free(b->ctx, b->levels);

@@ -102,6 +102,10 @@ int etp_batch_from_coeffs_dev(etp_ctx *ctx, const uint64_t *coeffs_dev, size_t c
                               int rate_bits, int blinding, int cap_height, etp_batch **out);
 /* re-run the commit into an existing batch of the same shape (no allocation; benches) */
 int etp_batch_recommit_values_dev(etp_batch *b, const uint64_t *values_dev, size_t col_stride);
+/* per-phase device times (ms, CUDA events on the context's stream) of the last commit into this batch,
+ * named after plonky2's TimingTree scopes: [0] "IFFT", [1] "FFT + blinding" (coset LDE),
+ * [2] "build Merkle tree": leaf hashing, [3] "build Merkle tree": inner levels + cap. */
+int etp_batch_last_commit_timings(const etp_batch *b, float ms_out[4]);
 void etp_batch_free(etp_batch *b);
 size_t etp_batch_num_cols(const etp_batch *b);
 int etp_batch_degree_log(const etp_batch *b);
