@@ -1,0 +1,79 @@
+"""World-size-2 test (gloo, CPU) of the multi-GPU host logic: independent jobs are sharded over ranks with
+no data-path collective, per-rank times reduce with MAX, results are gathered to every rank in job order.
+The per-job work here is the oracle's commit (CPU) — the same sharding code drives the CUDA path in
+bench.py under torchrun (one process per GPU, NCCL)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import oracle
+    from eth_tx_proof_b200 import parallel, synthetic as syn
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    jobs = parallel.shard_jobs(5, rank, world)
+    local = []
+    for j in jobs:
+        vals = syn.random_columns(9, 6, seed=100 + j)
+        local.append((j, oracle.Batch.from_values(vals, 1, 2).cap.tolist()))
+    merged = parallel.gather_results(local)
+    t = parallel.max_over_ranks(10.0 + rank)
+    dist.barrier()
+    q.put((rank, jobs, merged, t))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_reduce_gather():
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, ROOT)
+    import oracle
+    from eth_tx_proof_b200 import parallel, synthetic as syn
+
+    assert parallel.shard_jobs(5, 0, 2) == [0, 2, 4] and parallel.shard_jobs(5, 1, 2) == [1, 3]
+    assert sorted(parallel.shard_jobs(8, 0, 4) + parallel.shard_jobs(8, 1, 4) + parallel.shard_jobs(8, 2, 4)
+                  + parallel.shard_jobs(8, 3, 4)) == list(range(8))
+    with pytest.raises(ValueError):
+        parallel.shard_jobs(3, 2, 2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [(j, oracle.Batch.from_values(syn.random_columns(9, 6, seed=100 + j), 1, 2).cap.tolist()) for j in range(5)]
+    for rank, jobs, merged, t in res:
+        assert jobs == parallel.shard_jobs(5, rank, 2)
+        assert merged == want          # every rank sees all results, in job order
+        assert t == 11.0               # MAX over ranks
+
+
+def test_single_process_fallbacks():
+    sys.path.insert(0, ROOT)
+    from eth_tx_proof_b200 import parallel
+
+    assert parallel.max_over_ranks(3.5) == 3.5
+    assert parallel.gather_results([(1, "b"), (0, "a")]) == [(0, "a"), (1, "b")]
