@@ -28,6 +28,8 @@ struct etp_ctx {
   uint64_t launches = 0;
   // (base, bits, scale) -> device tables
   std::map<std::tuple<uint64_t, int, uint64_t>, DevPowTable> pow_tables;
+  // full-size tables: (log_n | -1, shift, s | n_in, B, inverse) -> device array
+  std::map<std::tuple<int, uint64_t, int, int, int>, uint64_t*> full_tables;
   // last prove timings
   std::vector<std::pair<const char*, float>> timings;
   uint64_t* d_pow_result = nullptr;  // PoW grind result slot

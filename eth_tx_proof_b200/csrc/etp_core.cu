@@ -32,8 +32,6 @@ extern "C" int etp_ctx_create(int device, etp_ctx** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  cudaFuncSetAttribute(ntt::pass_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(ntt::pass_last, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (cudaMalloc((void**)&ctx->d_pow_result, 16) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -48,6 +46,7 @@ extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
+  for (auto& kv : ctx->full_tables) cudaFree(kv.second);
   cudaFree(ctx->d_pow_result);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -117,37 +116,81 @@ int get_pow_table(etp_ctx* ctx, uint64_t base, int bits, uint64_t scale, ntt::Po
   return ETP_OK;
 }
 
+__global__ void k_canon_copy_strided(const uint64_t* src, size_t src_stride, uint64_t* dst, size_t dst_stride, size_t n_cols, int nonzero) {
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (c < n_cols) dst[c * dst_stride] = nonzero ? gl::canon(src[c * src_stride]) : 0;
+}
+
 // =================================================================================================
 // NTT driver
 // =================================================================================================
-static int plan_digits(int L, int b[3]) {
-  if (L <= 12) { b[0] = L; return 1; }
-  if (L <= 23) {
-    int last = (L + 1) / 2;
-    if (last > 12) last = 12;
-    b[0] = L - last; b[1] = last;
-    return 2;
-  }
-  int rest = L - 12;
-  b[0] = (rest + 1) / 2; b[1] = rest - b[0]; b[2] = 12;
-  return 3;
+static int plan_digits(int L, int b[8]) {
+  // digits of <= 8 bits, as even as possible, the larger ones last (the last pass wants long contiguous chunks)
+  const int m = (L + ntt::MAX_DIGIT_BITS - 1) / ntt::MAX_DIGIT_BITS;
+  const int base = L / m, extra = L % m;
+  for (int j = 0; j < m; j++) b[j] = base + (j >= m - extra ? 1 : 0);
+  return m;
 }
-int ntt_num_passes(int log_n) { int b[3]; return plan_digits(log_n, b); }
+int ntt_num_passes(int log_n) { int b[8]; return log_n <= 0 ? 1 : plan_digits(log_n, b); }
+
+template <int B>
+static void launch_strided(const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
+  ntt::pass_strided<B><<<grid, ntt::THREADS, ntt::Geo<B>::SMEM_WORDS_STRIDED * 8, st>>>(p, ul);
+}
+template <int B>
+static void launch_last(const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
+  ntt::pass_last<B><<<grid, ntt::THREADS, ntt::Geo<B>::SMEM_WORDS_LAST * 8, st>>>(p, ul);
+}
+static void dispatch_pass(bool last, int B, const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
+#define ETP_CASE(n) case n: if (last) launch_last<n>(p, ul, grid, st); else launch_strided<n>(p, ul, grid, st); break;
+  switch (B) { ETP_CASE(1) ETP_CASE(2) ETP_CASE(3) ETP_CASE(4) ETP_CASE(5) ETP_CASE(6) ETP_CASE(7) ETP_CASE(8) default: break; }
+#undef ETP_CASE
+}
+
+// cached full-size tables (inter-digit twiddles, coset shift powers); nullptr when too large to keep
+static const size_t kMaxFullTable = (size_t)1 << 24;
+static int get_full_table(etp_ctx* ctx, const std::tuple<int, uint64_t, int, int, int>& key, size_t n, uint64_t** out) {
+  auto it = ctx->full_tables.find(key);
+  if (it != ctx->full_tables.end()) { *out = it->second; return ETP_OK; }
+  uint64_t* d = nullptr;
+  ETP_CUDA(ctx, cudaMalloc((void**)&d, n * 8));
+  ctx->full_tables.emplace(key, d);
+  *out = d;
+  return 1;  // caller must fill it
+}
 
 int ntt_run(etp_ctx* ctx, const NttArgs& a) {
   if (a.log_n < 0 || a.log_n > 31) return etp_fail(ctx, ETP_ERR_INVALID, "ntt: log_n %d out of range", a.log_n);
   if (a.n_cols == 0) return ETP_OK;
   const int L = a.log_n;
-  int b[3];
+  if (L == 0) {  // size-1 transform: identity (1/n = 1, shift^0 = 1)
+    k_canon_copy_strided<<<(unsigned)((a.n_cols + 255) / 256), 256, 0, ctx->stream>>>(a.in, a.in_stride, a.out, a.out_stride, a.n_cols,
+                                                                                   a.n_in ? 1 : 0);
+    ETP_LAUNCH_CHECK(ctx);
+    return ETP_OK;
+  }
+  int b[8];
   const int m = plan_digits(L, b);
   if (a.natural_out && m > 1 && !a.scratch) return etp_fail(ctx, ETP_ERR_INVALID, "ntt: scratch required");
   ntt::PassParams p{};
   p.log_n = L;
+  p.n_cols = (uint32_t)a.n_cols;
   p.inverse = a.inverse ? 1 : 0;
   ETP_TRY(get_pow_table(ctx, gl::root_of_unity(L), L, 1, &p.tw));
   ntt::PowTable in_pow{}, out_pow{};
   const uint64_t n_inv = gl::inv((uint64_t)1 << L);
-  if (a.coset_shift && !a.inverse) ETP_TRY(get_pow_table(ctx, a.coset_shift, L, 1, &in_pow));
+  uint64_t* in_full = nullptr;
+  if (a.coset_shift && !a.inverse) {
+    ETP_TRY(get_pow_table(ctx, a.coset_shift, L, 1, &in_pow));
+    if (a.n_in <= kMaxFullTable) {
+      int rc = get_full_table(ctx, std::make_tuple(-1, a.coset_shift, (int)a.n_in, 0, 0), a.n_in, &in_full);
+      if (rc < 0) return rc;
+      if (rc == 1) {
+        ntt::fill_pow_full<<<(unsigned)((a.n_in + 255) / 256), 256, 0, ctx->stream>>>(in_pow, a.n_in, in_full);
+        ETP_LAUNCH_CHECK(ctx);
+      }
+    }
+  }
   if (a.coset_shift && a.inverse) ETP_TRY(get_pow_table(ctx, gl::inv(a.coset_shift), L, n_inv, &out_pow));
   int s = L;
   for (int j = 0; j < m; j++) {
@@ -161,29 +204,39 @@ int ntt_run(etp_ctx* ctx, const NttArgs& a) {
     if (a.natural_out && !last) { dst = a.scratch; dst_stride = a.scratch_stride; }
     else { dst = a.out; dst_stride = a.out_stride; }
     p.in = src; p.in_col_stride = src_stride; p.out = dst; p.out_col_stride = dst_stride;
-    p.s = s; p.b = b[j];
+    p.s = s;
     p.n_in = first ? a.n_in : (1u << L);
     p.in_scale = (first && a.coset_shift && !a.inverse) ? 1 : 0;
     p.in_pow = in_pow;
+    p.in_full = in_full;
     p.natural_out = (last && a.natural_out) ? 1 : 0;
     p.out_scale = 0;
+    p.tw_full = nullptr;
     if (last && a.inverse) {
       if (a.coset_shift) { p.out_scale = 1; p.out_pow = out_pow; }
       else { p.out_scale = 2; p.out_const = n_inv; }
     }
-    const int R = 1 << b[j];
+    const int B = b[j];
+    int ul = ntt::TILE_LOG - B;
     if (!last) {
-      const int ul = b[j] >= 11 ? 2 : 3;
-      const size_t smem = ((size_t)(R >> 1) + ((size_t)R << ul)) * 8;
-      dim3 grid((unsigned)(((size_t)1 << (L - b[j])) >> ul), (unsigned)a.n_cols);
-      ntt::pass_strided<<<grid, ntt::THREADS, smem, ctx->stream>>>(p, ul);
+      if (ul > s) ul = s;
+      if (((size_t)1 << (s + B)) <= kMaxFullTable) {
+        uint64_t* tab = nullptr;
+        int rc = get_full_table(ctx, std::make_tuple(L, (uint64_t)0, s, B, p.inverse), (size_t)1 << (s + B), &tab);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+          ntt::fill_pass_twiddles<<<(unsigned)((((size_t)1 << (s + B)) + 255) / 256), 256, 0, ctx->stream>>>(p, B, tab);
+          ETP_LAUNCH_CHECK(ctx);
+        }
+        p.tw_full = tab;
+      }
+      dim3 grid((unsigned)(a.n_cols * (((size_t)1 << (L - B)) >> ul)));
+      dispatch_pass(false, B, p, ul, grid, ctx->stream);
     } else {
-      const int pb = L - b[j];
-      int ul = b[j] >= 12 ? 1 : (b[j] == 11 ? 2 : 3);
+      const int pb = L - B;
       if (ul > pb) ul = pb;
-      const size_t smem = ((size_t)(R >> 1) + (size_t)ntt::last_pitch(b[j]) * ((size_t)1 << ul)) * 8;
-      dim3 grid((unsigned)(((size_t)1 << pb) >> ul), (unsigned)a.n_cols);
-      ntt::pass_last<<<grid, ntt::THREADS, smem, ctx->stream>>>(p, ul);
+      dim3 grid((unsigned)(a.n_cols * (((size_t)1 << pb) >> ul)));
+      dispatch_pass(true, B, p, ul, grid, ctx->stream);
     }
     ETP_LAUNCH_CHECK(ctx);
   }
