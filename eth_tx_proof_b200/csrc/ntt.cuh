@@ -75,6 +75,16 @@ __device__ __forceinline__ uint64_t tw_get(const PassParams& p, uint32_t e /* < 
   if (p.inverse && e) e = (1u << p.log_n) - e;
   return p.tw.get(e);
 }
+// out-of-line fallbacks for transforms whose full tables would not fit (keeps the hot code small:
+// the unrolled kernels otherwise overflow the instruction cache)
+static __device__ __noinline__ uint64_t slow_pow(const uint64_t* lo, const uint64_t* hi, int lo_bits, uint32_t mask, uint32_t e) {
+  return gl::mul(__ldg(hi + (e >> lo_bits)), __ldg(lo + (e & mask)));
+}
+static __device__ __noinline__ uint64_t slow_twiddle(const uint64_t* lo, const uint64_t* hi, int lo_bits, uint32_t mask, int inverse, int log_n,
+                                              uint32_t e) {
+  if (inverse && e) e = (1u << log_n) - e;
+  return gl::mul(__ldg(hi + (e >> lo_bits)), __ldg(lo + (e & mask)));
+}
 
 // 2^Q-point DIF with compile-time constant twiddles on registers v[0..2^Q), stride 1: output slot j holds
 // frequency bitrev_Q(j).  Twiddle of layer q, pair (j, j+half): w_{2^Q}^((j mod half) << q).
@@ -159,7 +169,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_strided(PassParams p, 
       uint64_t x = 0;
       if (u < U && pos < p.n_in) {
         x = in[pos];
-        if (p.in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : p.in_pow.get((uint32_t)pos));
+        if (p.in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : slow_pow(p.in_pow.lo, p.in_pow.hi, p.in_pow.lo_bits, p.in_pow.mask, (uint32_t)pos));
       }
       v[gi * (1 << G::Q1) + j] = x;
     }
@@ -197,7 +207,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_strided(PassParams p, 
       if (u < U) {
         uint64_t w;
         if (p.tw_full) w = __ldg(p.tw_full + (((size_t)d << s) | low));
-        else w = tw_get(p, (uint32_t)(((uint64_t)low * gl::bitrev32(d, B)) << (p.log_n - s - B)));
+        else w = slow_twiddle(p.tw.lo, p.tw.hi, p.tw.lo_bits, p.tw.mask, p.inverse, p.log_n, (uint32_t)(((uint64_t)low * gl::bitrev32(d, B)) << (p.log_n - s - B)));
         out[base | ((size_t)d << s) | u] = gl::mul(v[gi * (1 << QL) + j], w);
       }
     }
@@ -234,7 +244,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
       uint64_t x = 0;
       if (u < U && pos < p.n_in) {
         x = in[pos];
-        if (p.in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : p.in_pow.get((uint32_t)pos));
+        if (p.in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : slow_pow(p.in_pow.lo, p.in_pow.hi, p.in_pow.lo_bits, p.in_pow.mask, (uint32_t)pos));
       }
       v[gi * (1 << G::Q1) + j] = x;
     }
@@ -276,7 +286,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
           const uint32_t idx = (gl::bitrev32(d, B) << pb) | (q0 + u);
           uint64_t x = v[gi * (1 << QL) + j];
           if (p.out_scale == 2) x = gl::mul(x, p.out_const);
-          else if (p.out_scale == 1) x = gl::mul(x, p.out_pow.get(idx));
+          else if (p.out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, idx));
           out[idx] = gl::canon(x);
         }
       }
@@ -299,7 +309,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
           const size_t pos = ((size_t)(q0 + u) << B) | d;
           uint64_t x = sm[u * G::PITCH + d + (d >> 4)];
           if (p.out_scale == 2) x = gl::mul(x, p.out_const);
-          else if (p.out_scale == 1) x = gl::mul(x, p.out_pow.get(gl::bitrev32((uint32_t)pos, p.log_n)));
+          else if (p.out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, gl::bitrev32((uint32_t)pos, p.log_n)));
           out[pos] = gl::canon(x);
         }
       }
@@ -314,7 +324,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
             const size_t pos = ((size_t)(q0 + u) << B) | d;
             uint64_t x = v[gi * (1 << G::Q1) + j];
             if (p.out_scale == 2) x = gl::mul(x, p.out_const);
-            else if (p.out_scale == 1) x = gl::mul(x, p.out_pow.get(gl::bitrev32((uint32_t)pos, p.log_n)));
+            else if (p.out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, gl::bitrev32((uint32_t)pos, p.log_n)));
             out[pos] = gl::canon(x);
           }
         }

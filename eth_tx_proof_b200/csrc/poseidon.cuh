@@ -14,11 +14,12 @@
 //  * S-box: 4 Goldilocks multiplications, IMAD.WIDE (FMA pipe) + carry chains (ALU pipe).
 //  * MDS: the coefficients are < 2^6, so on the 32-bit halves of the lanes every 12-term sum is an
 //    integer < 2^42 — exactly representable in binary64.  B200 issues DFMA at the same rate as
-//    IMAD and on its own pipe, and a DFMA accumulates for free (IMAD.WIDE with a 64-bit addend
-//    runs at ~5 clk/warp), so the layer is 2 x 144 DFMA on the FP64 pipe, overlapping the integer
-//    pipes.  u32 -> f64 is the 2^52 trick (one DADD); the next round's constants and the 2^52 bias
-//    are pre-folded into the accumulator's initial value (constant-bank operand), and the integer
-//    comes back as the mantissa bits.  Every step is exact integer arithmetic; no rounding occurs.
+//    IMAD, and a DFMA accumulates for free (IMAD.WIDE with a 64-bit addend runs at ~5 clk/warp), so
+//    the layer runs on the FP64 pipe, in split-cyclic form (cyclic(6) + negacyclic(6): 220 FP64
+//    operations per layer instead of 312).  u32 -> f64 is the 2^52 bit trick; the next round's
+//    constants and the bias are pre-folded into the accumulators' initial values (constant-bank
+//    operands), and the integers come back as mantissa bits.  Every step is exact integer
+//    arithmetic; no rounding occurs.
 //  * One rolled loop over the 30 rounds (full-round S-boxes behind a warp-uniform branch) keeps the
 //    hot code inside the instruction cache (the fully unrolled version stalled on instruction fetch).
 // Tensor cores are deliberately unused (64-bit modular arithmetic).
@@ -42,40 +43,60 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
   return gl::mul(x3, x4);
 }
 
-// exact u32 -> f64: the double with bit pattern (0x43300000 : x) is 2^52 + x
-__device__ __forceinline__ double u32_to_f64(uint32_t x) {
-  return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+// ---- MDS layer on the FP64 pipe, split-cyclic form -------------------------------------------------
+// out = circ(C) * x (+ 8 x_0 on row 0) + next-round constants, on one 32-bit half ("plane") of the
+// lanes.  With S_k = x_k + x_{k+6}, D_k = x_k - x_{k+6} (k < 6):
+//   out_r + out_{r+6} = sum_k (C_k + C_{k+6}) S_{(k+r)%6}            (cyclic, length 6)
+//   out_r - out_{r+6} = sum_k (C_k - C_{k+6}) (+-)D_{(k+r)%6}        (negacyclic: minus when k + r >= 6)
+// and both coefficient vectors are even: (C_k + C_{k+6})/2 = {15,14,40,17,18,24},
+// (C_k - C_{k+6})/2 = {2,1,1,-1,-16,4}.  72 DFMA + 38 DADD per plane instead of 144 + 12, all on
+// integers below 2^53 (exact).  The u32 -> f64 conversions disappear into the S/D step: the double
+// with bit pattern (0x43300000 : w) is 2^52 + w, so S_k = d_k + (d_{k+6} - 2^53), D_k = d_k - d_{k+6}.
+// Accumulators start at 2^51 (+ constant), so out_r = Ah + Bh = 2^52 + value and the integer is read
+// back from the mantissa; out_{r+6} = (Ah - Bh) + (2^52 + k_{r+6} - k_r).
+struct PlaneOut {
+  double o[12];
+};
+__device__ __forceinline__ void mds_plane(const double (&d)[12], const uint64_t* __restrict__ tab, double (&o)[12]) {
+  constexpr double CA[6] = {15, 14, 40, 17, 18, 24};
+  constexpr double CB[6] = {2, 1, 1, -1, -16, 4};
+  double S[6], D[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const double e = d[k + 6] - 9007199254740992.0;  // 2^53
+    S[k] = d[k] + e;
+    D[k] = d[k] - d[k + 6];
+  }
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    double ah = __longlong_as_double((long long)tab[r]);
+    double bh = 2251799813685248.0;  // 2^51
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      ah = fma(S[(k + r) % 6], CA[k], ah);
+      bh = fma(D[(k + r) % 6], (k + r >= 6) ? -CB[k] : CB[k], bh);
+    }
+    o[r] = ah + bh;
+    o[r + 6] = (ah - bh) + __longlong_as_double((long long)tab[6 + r]);
+  }
+  o[0] = fma(d[0] - 4503599627370496.0, 8.0, o[0]);  // MDS_MATRIX_DIAG[0] = 8
 }
 
-// One MDS row on the FP64 pipe: sum_i x[(i+r)%12]*C[i] (+ 8*x[0] for r = 0) + next-round constant.
-template <int R>
-__device__ __forceinline__ uint64_t mds_row_f64(const double (&xl)[12], const double (&xh)[12],
-                                                const uint64_t* __restrict__ rcd) {
-  constexpr double C[12] = ETP_MDS_CIRC;
-  // initial value = 2^52 + constant half (f64 bit pattern from the constant bank)
-  double al = __longlong_as_double((long long)rcd[2 * R]);
-  double ah = __longlong_as_double((long long)rcd[2 * R + 1]);
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    const double c = (R == 0 && i == 0) ? C[0] + 8.0 : C[i];  // MDS_MATRIX_DIAG[0] = 8
-    al = fma(xl[(i + R) % 12], c, al);
-    ah = fma(xh[(i + R) % 12], c, ah);
-  }
-  // al = 2^52 + L, ah = 2^52 + H with L, H < 2^43: the mantissa bits ARE the integers
-  const uint64_t L = (uint64_t)__double_as_longlong(al) & 0xFFFFFFFFFFFFFull;
-  const uint64_t H = (uint64_t)__double_as_longlong(ah) & 0xFFFFFFFFFFFFFull;
-  // value = L + H*2^32,  H = h1*2^32 + h0  =>  == L + h1*EPS + h0*2^32  (mod p)
-  const uint32_t h0 = (uint32_t)H, h1 = (uint32_t)(H >> 32);
-  const uint64_t t = L + (((uint64_t)h1 << 32) - h1);  // < 2^44, no overflow
-  return gl::add_c(t, (uint64_t)h0 << 32);              // h0 << 32 < p: one fix-up is exact
+// (2^52 + L, 2^52 + H) -> L + H * 2^32 (mod p), L, H < 2^43.  With H = h1 * 2^32 + h0 and
+// M = L1 + h0 + h1 = c * 2^32 + m the value is ((m + c) : L0) - (c + h1), which can never borrow.
+__device__ __forceinline__ uint64_t combine_planes(double al, double ah) {
+  const uint32_t L0 = (uint32_t)__double2loint(al), L1 = (uint32_t)__double2hiint(al) & 0xFFFFFu;
+  const uint32_t h0 = (uint32_t)__double2loint(ah), h1 = (uint32_t)__double2hiint(ah) & 0xFFFFFu;
+  uint32_t m, c;
+  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(m), "=r"(c) : "r"(L1 + h1), "r"(h0));
+  const uint64_t v = ((uint64_t)(m + c) << 32) | L0;
+  return v - (uint64_t)(c + h1);
 }
 
 // In-place permutation. Input lanes: any u64. Output lanes: any u64 (canonicalise before exporting).
 //
 // Loop iteration r = [S-boxes of lanes 1..11 if round r is full] ; MDS of round r (+ constants of
-// round r+1) ; S-box of lane 0 for round r+1.  Lane 0's S-box — the only one in a partial round, a
-// serial chain of four multiplications — is issued right behind MDS row 0 so that it overlaps the
-// 264 DFMAs of rows 1..11 instead of stalling the warp in a basic block of its own.
+// round r+1) ; S-box of lane 0 for round r+1 (issued right behind row 0 so that it overlaps the rest).
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_c(s[i], RC[i]);
@@ -86,26 +107,19 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
 #pragma unroll
       for (int i = 1; i < 12; i++) s[i] = sbox7(s[i]);
     }
-    const uint64_t* __restrict__ rcd = RC_F64 + 24 * r;
-    double xl[12], xh[12];
+    const uint64_t* __restrict__ tab = RC_F64 + 24 * r;
+    double dl[12], dh[12], ol[12], oh[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-      xl[i] = u32_to_f64((uint32_t)s[i]);
-      xh[i] = u32_to_f64((uint32_t)(s[i] >> 32));
+      dl[i] = __hiloint2double(0x43300000, (int)(uint32_t)s[i]);
+      dh[i] = __hiloint2double(0x43300000, (int)(uint32_t)(s[i] >> 32));
     }
-    const uint64_t row0 = mds_row_f64<0>(xl, xh, rcd);
+    mds_plane(dl, tab, ol);
+    mds_plane(dh, tab + 12, oh);
+    const uint64_t row0 = combine_planes(ol[0], oh[0]);
     const uint64_t next0 = sbox7(row0);
-    s[1] = mds_row_f64<1>(xl, xh, rcd);
-    s[2] = mds_row_f64<2>(xl, xh, rcd);
-    s[3] = mds_row_f64<3>(xl, xh, rcd);
-    s[4] = mds_row_f64<4>(xl, xh, rcd);
-    s[5] = mds_row_f64<5>(xl, xh, rcd);
-    s[6] = mds_row_f64<6>(xl, xh, rcd);
-    s[7] = mds_row_f64<7>(xl, xh, rcd);
-    s[8] = mds_row_f64<8>(xl, xh, rcd);
-    s[9] = mds_row_f64<9>(xl, xh, rcd);
-    s[10] = mds_row_f64<10>(xl, xh, rcd);
-    s[11] = mds_row_f64<11>(xl, xh, rcd);
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = combine_planes(ol[i], oh[i]);
     s[0] = (r == ROUNDS - 1) ? row0 : next0;  // no S-box after the last round
   }
 }

@@ -69,11 +69,13 @@ def test_embedded_round_constants_are_the_pinned_ones():
     f64 = src.split("#define ETP_POSEIDON_RC_F64_TABLE")[1].split("}")[0]
     bits = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ULL", f64)]
     assert len(bits) == 720
+    as_f64 = lambda b: struct.unpack("<d", struct.pack("<Q", b))[0]
     for r in range(30):
-        for i in range(12):
-            k = vals[12 * (r + 1) + i] if r < 29 else 0
-            assert bits[24 * r + 2 * i] == 0x4330000000000000 | (k & 0xFFFFFFFF)
-            assert bits[24 * r + 2 * i + 1] == 0x4330000000000000 | (k >> 32)
+        for h in range(2):
+            ks = [((vals[12 * (r + 1) + i] >> (32 * h)) & 0xFFFFFFFF) if r < 29 else 0 for i in range(12)]
+            for i in range(6):
+                assert as_f64(bits[24 * r + 12 * h + i]) == float(2**51 + ks[i])
+                assert as_f64(bits[24 * r + 12 * h + 6 + i]) == float(2**52 + ks[i + 6] - ks[i])
 
 
 def test_synthetic_traces_are_deterministic_and_valid():
