@@ -93,7 +93,7 @@ __global__ void k_dfma(uint64_t* out, uint32_t a, uint32_t b) {
 __global__ void k_mix_dfma_iadd(uint64_t* out, uint32_t a, uint32_t b) {
   double acc[CHAINS]; uint32_t ia[CHAINS];
   double m = (double)b, c = (double)a;
-  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a; }
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a + threadIdx.x; }
   for (int it = 0; it < N_ITER; it++) {
 #pragma unroll
     for (int i = 0; i < CHAINS; i++) {
@@ -108,7 +108,7 @@ __global__ void k_mix_dfma_iadd(uint64_t* out, uint32_t a, uint32_t b) {
 __global__ void k_mix_dfma_imad(uint64_t* out, uint32_t a, uint32_t b) {
   double acc[CHAINS]; uint32_t ia[CHAINS];
   double m = (double)b, c = (double)a;
-  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a; }
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a + threadIdx.x; }
   for (int it = 0; it < N_ITER; it++) {
 #pragma unroll
     for (int i = 0; i < CHAINS; i++) {
@@ -123,7 +123,7 @@ __global__ void k_mix_dfma_imad(uint64_t* out, uint32_t a, uint32_t b) {
 __global__ void k_mix3(uint64_t* out, uint32_t a, uint32_t b) {  // DFMA + IMAD + IADD
   double acc[CHAINS]; uint32_t ia[CHAINS], ib[CHAINS];
   double m = (double)b, c = (double)a;
-  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a; ib[i] = i * 3 + a; }
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a + threadIdx.x; ib[i] = i * 3 + a + threadIdx.x; }
   for (int it = 0; it < N_ITER; it++) {
 #pragma unroll
     for (int i = 0; i < CHAINS; i++) {
@@ -138,7 +138,7 @@ __global__ void k_mix3(uint64_t* out, uint32_t a, uint32_t b) {  // DFMA + IMAD 
 }
 __global__ void k_mix_imad_iadd(uint64_t* out, uint32_t a, uint32_t b) {
   uint32_t ia[CHAINS], ib[CHAINS];
-  for (int i = 0; i < CHAINS; i++) { ia[i] = i + a; ib[i] = i * 3 + a; }
+  for (int i = 0; i < CHAINS; i++) { ia[i] = i + a + threadIdx.x; ib[i] = i * 3 + a + threadIdx.x; }
   for (int it = 0; it < N_ITER; it++) {
 #pragma unroll
     for (int i = 0; i < CHAINS; i++) {
@@ -148,6 +148,88 @@ __global__ void k_mix_imad_iadd(uint64_t* out, uint32_t a, uint32_t b) {
   }
   uint32_t t = 0;
   for (int i = 0; i < CHAINS; i++) t += ia[i] + ib[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
+
+// DFMA with three distinct register operands per instruction (register-file bandwidth check)
+__global__ void k_dfma3(uint64_t* out, uint32_t a, uint32_t b) {
+  double acc[CHAINS], x[CHAINS], y[CHAINS];
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; x[i] = 1.0 + i * 1e-9 + a * 1e-12; y[i] = 1.0 - i * 1e-9 + b * 1e-12; }
+  for (int it = 0; it < N_ITER; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(acc[i]) : "d"(x[i]), "d"(y[(i + 3) % CHAINS]));
+  }
+  double s = 0;
+  for (int i = 0; i < CHAINS; i++) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)s;
+}
+// the instruction mix of the hybrid Poseidon round: 2 DFMA : 3 IMAD (imm) : 4 IADD3 per group
+__global__ void k_mix_234(uint64_t* out, uint32_t a, uint32_t b) {
+  double acc[CHAINS]; uint32_t ia[CHAINS], ib[CHAINS], ic[CHAINS];
+  double m = (double)b, c = (double)a;
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ia[i] = i + a + threadIdx.x; ib[i] = i * 3 + a + threadIdx.x; ic[i] = i * 5 + b + threadIdx.x; }
+  for (int it = 0; it < N_ITER; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) {
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(m), "d"(c));
+      asm volatile("mad.lo.u32 %0, %1, 17, %0;" : "+r"(ia[i]) : "r"(ib[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ib[i]) : "r"(b));
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(ic[i]) : "r"(ib[i]));
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(c), "d"(m));
+      asm volatile("mad.lo.u32 %0, %1, 41, %0;" : "+r"(ia[i]) : "r"(ic[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ic[i]) : "r"(a));
+      asm volatile("mad.lo.u32 %0, %1, 13, %0;" : "+r"(ia[i]) : "r"(ib[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ib[i]) : "r"(ic[i]));
+    }
+  }
+  double s = 0; uint32_t t = 0;
+  for (int i = 0; i < CHAINS; i++) { s += acc[i]; t += ia[i] + ib[i] + ic[i]; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)s + t;
+}
+// the current mix: 6 DFMA/DADD : 2 IMAD.WIDE : 5 IADD3
+__global__ void k_mix_cur(uint64_t* out, uint32_t a, uint32_t b) {
+  double acc[CHAINS]; uint32_t ib[CHAINS], ic[CHAINS]; uint64_t w[CHAINS];
+  double m = (double)b, c = (double)a;
+  for (int i = 0; i < CHAINS; i++) { acc[i] = i + threadIdx.x; ib[i] = i * 3 + a + threadIdx.x; ic[i] = i * 5 + b + threadIdx.x; w[i] = i + threadIdx.x; }
+  for (int it = 0; it < N_ITER; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) {
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(m), "d"(c));
+      asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(ib[i]), "r"(ic[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ib[i]) : "r"((uint32_t)w[i]));
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(c), "d"(m));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ic[i]) : "r"((uint32_t)(w[i] >> 32)));
+      asm volatile("add.f64 %0, %0, %1;" : "+d"(acc[i]) : "d"(m));
+      asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(ic[i]), "r"(ib[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ib[i]) : "r"((uint32_t)w[i]));
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(m), "d"(c));
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(ic[i]) : "r"((uint32_t)(w[i] >> 32)));
+      asm volatile("add.f64 %0, %0, %1;" : "+d"(acc[i]) : "d"(c));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ib[i]) : "r"(ic[i]));
+      asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(c), "d"(c));
+    }
+  }
+  double s = 0; uint32_t t = 0;
+  for (int i = 0; i < CHAINS; i++) { s += acc[i]; t += ib[i] + ic[i] + (uint32_t)w[i]; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint64_t)s + t;
+}
+// integer only: 1 IMAD.WIDE : 1 IMAD : 3 IADD3
+__global__ void k_mix_int(uint64_t* out, uint32_t a, uint32_t b) {
+  uint32_t ia[CHAINS], ib[CHAINS], ic[CHAINS]; uint64_t w[CHAINS];
+  for (int i = 0; i < CHAINS; i++) { ia[i] = i + a + threadIdx.x; ib[i] = i * 3 + a + threadIdx.x; ic[i] = i * 5 + b + threadIdx.x; w[i] = i + threadIdx.x; }
+  for (int it = 0; it < N_ITER; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) {
+      asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(ib[i]), "r"(ic[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ib[i]) : "r"((uint32_t)w[i]));
+      asm volatile("mad.lo.u32 %0, %1, 41, %0;" : "+r"(ia[i]) : "r"(ic[i]));
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(ic[i]) : "r"((uint32_t)(w[i] >> 32)));
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(ib[i]) : "r"(ia[i]));
+    }
+  }
+  uint32_t t = 0;
+  for (int i = 0; i < CHAINS; i++) t += ia[i] + ib[i] + ic[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = t;
 }
 
@@ -184,5 +266,9 @@ int main() {
   run("dfma+imad", k_mix_dfma_imad, 2, d);
   run("dfma+imad+iadd", k_mix3, 3, d);
   run("imad+iadd", k_mix_imad_iadd, 2, d);
+  run("dfma 3 regs", k_dfma3, 1, d);
+  run("2dfma:3imad:4iadd", k_mix_234, 9, d);
+  run("6fp64:2imw:5iadd", k_mix_cur, 13, d);
+  run("1imw:1imad:3iadd", k_mix_int, 5, d);
   return 0;
 }
