@@ -131,6 +131,44 @@ GL_D uint64_t mul(uint64_t a, uint64_t b) {
       : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return ((uint64_t)r1 << 32) | r0;
 }
+// a*a: the two cross products are the same IMAD.WIDE
+GL_D uint64_t sqr(uint64_t a) {
+  uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+  uint32_t r0, r1;
+  asm("{\n\t"
+      ".reg .u64 p00, p01, p10, p11, u;\n\t"
+      ".reg .u32 w0, w1, w2, w3, l01, h01, l10, h10, l11, h11, t0, t1, br, u0, u1, c, m;\n\t"
+      "mul.wide.u32 p00, %2, %2;\n\t"
+      "mul.wide.u32 p01, %2, %3;\n\t"
+      "mul.wide.u32 p11, %3, %3;\n\t"
+      "mov.b64 {w0, w1}, p00;\n\t"
+      "mov.b64 {l01, h01}, p01;\n\t"
+      "mov.b64 {l10, h10}, p01;\n\t"
+      "mov.b64 {l11, h11}, p11;\n\t"
+      "add.cc.u32 w1, w1, l01;\n\t"
+      "addc.cc.u32 w2, h01, l11;\n\t"
+      "addc.u32 w3, h11, 0;\n\t"
+      "add.cc.u32 w1, w1, l10;\n\t"
+      "addc.cc.u32 w2, w2, h10;\n\t"
+      "addc.u32 w3, w3, 0;\n\t"
+      "sub.cc.u32 t0, w0, w3;\n\t"      // t = (w1:w0) - w3 ; a borrow of 2^64 is worth EPS
+      "subc.cc.u32 t1, w1, 0;\n\t"
+      "subc.u32 br, 0, 0;\n\t"
+      "sub.cc.u32 t0, t0, br;\n\t"
+      "subc.u32 t1, t1, 0;\n\t"
+      "mul.wide.u32 u, w2, 0xffffffff;\n\t"  // w2 * EPS
+      "mov.b64 {u0, u1}, u;\n\t"
+      "add.cc.u32 %0, t0, u0;\n\t"
+      "addc.cc.u32 %1, t1, u1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.u32 m, 0, c;\n\t"               // carry of 2^64 is worth EPS
+      "add.cc.u32 %0, %0, m;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(a0), "r"(a1));
+  return ((uint64_t)r1 << 32) | r0;
+}
 GL_D uint64_t mul_canon(uint64_t a, uint64_t b) { return canon(mul(a, b)); }
 #else
 // ---- host versions (used by the host-side Challenger / table setup; product code, not the oracle)
@@ -163,7 +201,9 @@ GL_HD uint64_t sub(uint64_t a, uint64_t b) {
 GL_HD uint64_t sub_c(uint64_t a, uint64_t b) { return sub(a, b); }
 #endif
 
+#if !defined(__CUDA_ARCH__)
 GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
+#endif
 GL_HD uint64_t neg(uint64_t a) { a = canon(a); return a ? P - a : 0; }
 GL_HD uint64_t pow(uint64_t a, uint64_t e) {
   uint64_t r = 1;

@@ -22,6 +22,9 @@
 namespace merkle {
 
 constexpr int HASH_THREADS = 128;
+#ifndef ETP_LEAF_MIN_BLOCKS
+#define ETP_LEAF_MIN_BLOCKS 7
+#endif
 
 __device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[12]) {
   ulonglong2 a, b;
@@ -31,7 +34,7 @@ __device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[
 }
 
 // leaf i = (cols[0][i], cols[1][i], ...), column c at base + c*col_stride.  hash_or_noop semantics.
-static __global__ void __launch_bounds__(HASH_THREADS) hash_leaves_colmajor(const uint64_t* __restrict__ base, size_t col_stride,
+static __global__ void __launch_bounds__(HASH_THREADS, ETP_LEAF_MIN_BLOCKS) hash_leaves_colmajor(const uint64_t* __restrict__ base, size_t col_stride,
                                                                      int n_cols, uint32_t n_leaves,
                                                                      uint64_t* __restrict__ digests) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,13 +49,9 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_leaves_colmajor(cons
     store_digest(digests + 4 * (size_t)i, s);
     return;
   }
-  int c = 0;
-  for (; c + 8 <= n_cols; c += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) s[k] = __ldg(base + (size_t)(c + k) * col_stride + i);
-    poseidon::permute(s);
-  }
-  if (c < n_cols) {  // ragged last chunk overwrites only the first (n_cols - c) rate lanes
+  // one call site for the permutation (instruction-cache footprint); a ragged last chunk overwrites
+  // only the first (n_cols - c) rate lanes
+  for (int c = 0; c < n_cols; c += 8) {
 #pragma unroll
     for (int k = 0; k < 8; k++)
       if (c + k < n_cols) s[k] = __ldg(base + (size_t)(c + k) * col_stride + i);
@@ -77,13 +76,7 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_leaves_rowmajor(cons
     store_digest(digests + 4 * (size_t)i, s);
     return;
   }
-  int c = 0;
-  for (; c + 8 <= leaf_len; c += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) s[k] = __ldg(row + c + k);
-    poseidon::permute(s);
-  }
-  if (c < leaf_len) {
+  for (int c = 0; c < leaf_len; c += 8) {
 #pragma unroll
     for (int k = 0; k < 8; k++)
       if (c + k < leaf_len) s[k] = __ldg(row + c + k);

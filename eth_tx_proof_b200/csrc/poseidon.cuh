@@ -37,10 +37,21 @@ static __constant__ uint64_t RC[360] = ETP_POSEIDON_RC_TABLE;
 static __constant__ uint64_t RC_F64[30 * 24] = ETP_POSEIDON_RC_F64_TABLE;
 
 __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
-  uint64_t x2 = gl::mul(x, x);
-  uint64_t x4 = gl::mul(x2, x2);
+  uint64_t x2 = gl::sqr(x);
+  uint64_t x4 = gl::sqr(x2);
   uint64_t x3 = gl::mul(x, x2);
   return gl::mul(x3, x4);
+}
+
+// Two S-boxes behind one call.  The full rounds go through this out-of-line copy so that the whole
+// permutation (full-round loop + paired partial-round loop) stays below the 32 KB instruction cache:
+// with the eleven S-boxes inlined the kernel stalled on instruction fetch (profiles/, no_instruction).
+// Arguments and results travel in registers (10 instructions of call overhead per pair).
+static __device__ __noinline__ ulonglong2 sbox7_pair(uint64_t a, uint64_t b) {
+  ulonglong2 r;
+  r.x = sbox7(a);
+  r.y = sbox7(b);
+  return r;
 }
 
 // ---- MDS layer on the FP64 pipe, split-cyclic form -------------------------------------------------
@@ -82,45 +93,90 @@ __device__ __forceinline__ void mds_plane(const double (&d)[12], const uint64_t*
   o[0] = fma(d[0] - 4503599627370496.0, 8.0, o[0]);  // MDS_MATRIX_DIAG[0] = 8
 }
 
-// (2^52 + L, 2^52 + H) -> L + H * 2^32 (mod p), L, H < 2^43.  With H = h1 * 2^32 + h0 and
-// M = L1 + h0 + h1 = c * 2^32 + m the value is ((m + c) : L0) - (c + h1), which can never borrow.
+// (2^52 + L, 2^52 + H) -> L + H * 2^32 (mod p) for L, H < 2^52.  With L = L1 * 2^32 + L0, H = h1 * 2^32 + h0
+// and M = L1 + h0 + h1 = c * 2^32 + m the value is ((m + c) : L0) - (c + h1), which can never borrow.
+// The high words of the doubles are 0x43300000 + L1 / + h1, so the exponent bits are removed by the
+// constants folded into the additions instead of being masked: 7 integer instructions.
 __device__ __forceinline__ uint64_t combine_planes(double al, double ah) {
-  const uint32_t L0 = (uint32_t)__double2loint(al), L1 = (uint32_t)__double2hiint(al) & 0xFFFFFu;
-  const uint32_t h0 = (uint32_t)__double2loint(ah), h1 = (uint32_t)__double2hiint(ah) & 0xFFFFFu;
-  uint32_t m, c;
-  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(m), "=r"(c) : "r"(L1 + h1), "r"(h0));
-  const uint64_t v = ((uint64_t)(m + c) << 32) | L0;
-  return v - (uint64_t)(c + h1);
+  const uint32_t L0 = (uint32_t)__double2loint(al), wL = (uint32_t)__double2hiint(al);
+  const uint32_t h0 = (uint32_t)__double2loint(ah), wH = (uint32_t)__double2hiint(ah);
+  uint32_t v0, v1;
+  asm("{\n\t"
+      ".reg .u32 x, m, mc, t;\n\t"
+      "add.u32 x, %2, %3;\n\t"
+      "add.u32 x, x, 0x79a00000;\n\t"     // - 2 * 0x43300000: x = L1 + h1
+      "add.cc.u32 m, x, %4;\n\t"          // + h0, carry c
+      "addc.u32 mc, m, 0;\n\t"            // m + c
+      "addc.u32 t, %3, 0xbcd00000;\n\t"   // h1 + c
+      "sub.cc.u32 %0, %5, t;\n\t"
+      "subc.u32 %1, mc, 0;\n\t"
+      "}"
+      : "=r"(v0), "=r"(v1)
+      : "r"(wL), "r"(wH), "r"(h0), "r"(L0));
+  return ((uint64_t)v1 << 32) | v0;
+}
+
+__device__ __forceinline__ double plane_lo(uint64_t x) { return __hiloint2double(0x43300000, (int)(uint32_t)x); }
+__device__ __forceinline__ double plane_hi(uint64_t x) { return __hiloint2double(0x43300000, (int)(uint32_t)(x >> 32)); }
+
+// One MDS layer (+ the next round's constants) on both planes: d -> o, all values biased by 2^52.
+__device__ __forceinline__ void mds_layer(const double (&dl)[12], const double (&dh)[12], int r, double (&ol)[12], double (&oh)[12]) {
+  const uint64_t* __restrict__ tab = RC_F64 + 24 * r;
+  mds_plane(dl, tab, ol);
+  mds_plane(dh, tab + 12, oh);
 }
 
 // In-place permutation. Input lanes: any u64. Output lanes: any u64 (canonicalise before exporting).
 //
-// Loop iteration r = [S-boxes of lanes 1..11 if round r is full] ; MDS of round r (+ constants of
-// round r+1) ; S-box of lane 0 for round r+1 (issued right behind row 0 so that it overlaps the rest).
+// Full round r: S-boxes of lanes 1..11 ; MDS of round r (+ constants of round r+1) ; combine ; S-box of
+// lane 0 for round r+1 (issued right behind row 0 so that it overlaps the rest).
+// Partial rounds run in pairs: after the first MDS only lane 0 is recombined (its S-box needs the field
+// element); lanes 1..11 enter the second MDS as the 41-bit plane values they are (the second layer's sums
+// stay below 2^49, still exact), and all lanes are recombined once per pair.
 __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_c(s[i], RC[i]);
   s[0] = sbox7(s[0]);
+  int r = 0;
 #pragma unroll 1
-  for (int r = 0; r < ROUNDS; r++) {
-    if (r < HALF_FULL || r >= HALF_FULL + PARTIAL) {  // warp-uniform
+  for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+    for (int i = 0; i < HALF_FULL; i++, r++) {
 #pragma unroll
-      for (int i = 1; i < 12; i++) s[i] = sbox7(s[i]);
+      for (int k = 1; k < 11; k += 2) {
+        const ulonglong2 q = sbox7_pair(s[k], s[k + 1]);
+        s[k] = q.x;
+        s[k + 1] = q.y;
+      }
+      s[11] = sbox7(s[11]);
+      double dl[12], dh[12], ol[12], oh[12];
+#pragma unroll
+      for (int k = 0; k < 12; k++) { dl[k] = plane_lo(s[k]); dh[k] = plane_hi(s[k]); }
+      mds_layer(dl, dh, r, ol, oh);
+      const uint64_t row0 = combine_planes(ol[0], oh[0]);
+      const uint64_t next0 = sbox7(row0);
+#pragma unroll
+      for (int k = 1; k < 12; k++) s[k] = combine_planes(ol[k], oh[k]);
+      s[0] = (r == ROUNDS - 1) ? row0 : next0;  // no S-box after the last round
     }
-    const uint64_t* __restrict__ tab = RC_F64 + 24 * r;
-    double dl[12], dh[12], ol[12], oh[12];
+    if (half == 0) {
+#pragma unroll 1
+      for (int i = 0; i < PARTIAL / 2; i++, r += 2) {
+        double dl[12], dh[12], ol[12], oh[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      dl[i] = __hiloint2double(0x43300000, (int)(uint32_t)s[i]);
-      dh[i] = __hiloint2double(0x43300000, (int)(uint32_t)(s[i] >> 32));
+        for (int k = 0; k < 12; k++) { dl[k] = plane_lo(s[k]); dh[k] = plane_hi(s[k]); }
+        mds_layer(dl, dh, r, ol, oh);
+        const uint64_t mid0 = sbox7(combine_planes(ol[0], oh[0]));
+        ol[0] = plane_lo(mid0);
+        oh[0] = plane_hi(mid0);
+        mds_layer(ol, oh, r + 1, dl, dh);
+        const uint64_t row0 = combine_planes(dl[0], dh[0]);
+        const uint64_t next0 = sbox7(row0);
+#pragma unroll
+        for (int k = 1; k < 12; k++) s[k] = combine_planes(dl[k], dh[k]);
+        s[0] = next0;
+      }
     }
-    mds_plane(dl, tab, ol);
-    mds_plane(dh, tab + 12, oh);
-    const uint64_t row0 = combine_planes(ol[0], oh[0]);
-    const uint64_t next0 = sbox7(row0);
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = combine_planes(ol[i], oh[i]);
-    s[0] = (r == ROUNDS - 1) ? row0 : next0;  // no S-box after the last round
   }
 }
 #endif  // __CUDACC__

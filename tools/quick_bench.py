@@ -23,4 +23,5 @@ for it in range(5):
     ctx.synchronize(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 bytes_ = 8 * cols * n * 4 + 32 * (2 * (2 * n - 16) + 16)
+print("phases ms:", {k: round(v, 3) for k, v in b.last_commit_timings().items()})
 print(f"commit 2^{log_n} x {cols}: ms {ts}  best {min(ts):.3f} ms  -> {bytes_ / min(ts) / 1e6:.1f} GB/s algorithmic")
