@@ -33,7 +33,8 @@ class EtpError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libetp_b200.so")
+    """In-tree library; ETP_B200_LIB selects another build of the same sources (kernel-variant A/B runs)."""
+    return os.environ.get("ETP_B200_LIB") or os.path.join(_HERE, "libetp_b200.so")
 
 
 def load_library():

@@ -32,6 +32,9 @@ constexpr int TWO_ADICITY = 32;
 
 GL_HD uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
 
+#if defined(__CUDACC__)
+static __constant__ int32_t MINUS_ONE = -1;  // read from the constant bank on purpose, see reduce_prod
+#endif
 #if defined(__CUDA_ARCH__)
 // ---- device versions: explicit carry chains -------------------------------------------------
 // a, b: any u64. Result: any u64, == a + b (mod p).
@@ -90,6 +93,45 @@ GL_D uint64_t reduce128_canon(uint64_t lo, uint64_t hi) {
   asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(t2), "=r"(c) : "l"(t0), "l"(t1));
   return (c || t2 >= P) ? t2 + EPS : t2;           // -p == +EPS (mod 2^64)
 }
+#ifndef ETP_MUL_V
+#define ETP_MUL_V 2
+#endif
+#if ETP_MUL_V == 2
+// a, b: any u64.  Result any u64 == a*b (mod p).
+// The ALU/FP64 issue port is what saturates in the Poseidon and NTT kernels while the FMA pipe idles
+// (profiles/), so the multiplication keeps its carries on the FMA pipe: the 128-bit product comes from
+// ptxas's own u128 lowering (IMAD.WIDE with carry-out / carry-in predicates), and the reduction
+//   V = (w1:w0) + w2*EPS - w3,   -2^32 < V < 2^65 - 2^33
+// is one wrapping multiply-add with carry c, one wrapping subtraction with borrow, k = c - borrow in
+// {-1,0,1} and a single correction t + k*EPS, which can neither overflow (k = 1: t <= 2^64 - 2^33 - 1)
+// nor underflow (k = -1: t >= 2^64 - 2^32 + 1).
+GL_D uint64_t reduce_prod(uint64_t lo, uint64_t hi) {
+  const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32), w2 = (uint32_t)hi, w3 = (uint32_t)(hi >> 32);
+  uint32_t t0, t1, k;
+  asm("{\n\t"
+      ".reg .u32 u0, u1, c;\n\t"
+      "mad.lo.cc.u32 u0, %5, 0xffffffff, %3;\n\t"
+      "madc.hi.cc.u32 u1, %5, 0xffffffff, %4;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 %0, u0, %6;\n\t"
+      "subc.cc.u32 %1, u1, 0;\n\t"
+      "subc.u32 %2, c, 0;\n\t"
+      "}"
+      : "=r"(t0), "=r"(t1), "=r"(k)
+      : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+  // t + k*EPS = (t1 + k : t0) - sext(k).  The multiplier -1 comes from the constant bank so that ptxas
+  // keeps the 64-bit multiply-add (one FMA-pipe IMAD.WIDE) instead of expanding it into ALU carry chains.
+  const uint64_t t = ((uint64_t)(t1 + k) << 32) | t0;
+  uint64_t r;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(k), "r"(MINUS_ONE), "l"(t));
+  return r;
+}
+GL_D uint64_t mul(uint64_t a, uint64_t b) {
+  const unsigned __int128 p = (unsigned __int128)a * b;
+  return reduce_prod((uint64_t)p, (uint64_t)(p >> 64));
+}
+GL_D uint64_t sqr(uint64_t a) { return mul(a, a); }
+#else
 // a, b: any u64.  Result any u64 == a*b (mod p).  Four IMAD.WIDE.U32 with a zero addend (2 clk each on
 // B200; the accumulating form measures ~5 clk, tools/microbench/pipes.cu) + 32-bit carry chains, then
 // the reduction x0 + 2^32 x1 + (2^32-1) x2 - x3 written out on 32-bit words.
@@ -169,6 +211,7 @@ GL_D uint64_t sqr(uint64_t a) {
       : "r"(a0), "r"(a1));
   return ((uint64_t)r1 << 32) | r0;
 }
+#endif  // ETP_MUL_V
 GL_D uint64_t mul_canon(uint64_t a, uint64_t b) { return canon(mul(a, b)); }
 #else
 // ---- host versions (used by the host-side Challenger / table setup; product code, not the oracle)

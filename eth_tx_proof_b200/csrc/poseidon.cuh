@@ -47,7 +47,14 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
 // permutation (full-round loop + paired partial-round loop) stays below the 32 KB instruction cache:
 // with the eleven S-boxes inlined the kernel stalled on instruction fetch (profiles/, no_instruction).
 // Arguments and results travel in registers (10 instructions of call overhead per pair).
-static __device__ __noinline__ ulonglong2 sbox7_pair(uint64_t a, uint64_t b) {
+#if defined(ETP_COUNT_UNROLL)  // instruction-count builds (tools/sass_count.py): everything inline and unrolled
+#define ETP_ROLL _Pragma("unroll")
+#define ETP_SBOX_PAIR_ATTR __forceinline__
+#else
+#define ETP_ROLL _Pragma("unroll 1")
+#define ETP_SBOX_PAIR_ATTR __noinline__
+#endif
+static __device__ ETP_SBOX_PAIR_ATTR ulonglong2 sbox7_pair(uint64_t a, uint64_t b) {
   ulonglong2 r;
   r.x = sbox7(a);
   r.y = sbox7(b);
@@ -138,9 +145,9 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
   for (int i = 0; i < 12; i++) s[i] = gl::add_c(s[i], RC[i]);
   s[0] = sbox7(s[0]);
   int r = 0;
-#pragma unroll 1
+  ETP_ROLL
   for (int half = 0; half < 2; half++) {
-#pragma unroll 1
+    ETP_ROLL
     for (int i = 0; i < HALF_FULL; i++, r++) {
 #pragma unroll
       for (int k = 1; k < 11; k += 2) {
@@ -160,7 +167,7 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
       s[0] = (r == ROUNDS - 1) ? row0 : next0;  // no S-box after the last round
     }
     if (half == 0) {
-#pragma unroll 1
+      ETP_ROLL
       for (int i = 0; i < PARTIAL / 2; i++, r += 2) {
         double dl[12], dh[12], ol[12], oh[12];
 #pragma unroll
