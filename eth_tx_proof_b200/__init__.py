@@ -9,6 +9,7 @@ There is NO CPU fallback: importing is cheap, but any compute call raises ``EtpE
 is present.  Nothing in this package imports ``oracle/``.
 """
 from .api import (  # noqa: F401
+    BatchShard,
     Context,
     EtpError,
     MerkleTree,

@@ -92,6 +92,24 @@ def load_library():
         "etp_batch_prove": (i32, [vp, sz, _u64p]),
         "etp_batch_lde_dev": (vp, [vp, C.POINTER(sz)]),
         "etp_batch_coeffs_dev": (vp, [vp, C.POINTER(sz)]),
+        "etp_shard_cols_per_rank": (sz, [sz, i32]),
+        "etp_shard_create": (i32, [vp, sz, i32, i32, i32, i32, i32, pp]),
+        "etp_shard_free": (None, [vp]),
+        "etp_shard_first_col": (sz, [vp]),
+        "etp_shard_num_local_cols": (sz, [vp]),
+        "etp_shard_first_row": (sz, [vp]),
+        "etp_shard_num_rows": (sz, [vp]),
+        "etp_shard_lde_dev": (vp, [vp]),
+        "etp_shard_transform_values_host": (i32, [vp, C.POINTER(_u64p)]),
+        "etp_shard_transform_values_dev": (i32, [vp, vp, sz]),
+        "etp_ipc_export": (i32, [vp, vp, C.c_char_p]),
+        "etp_ipc_open": (i32, [vp, C.c_char_p, pp]),
+        "etp_ipc_close": (i32, [vp, vp]),
+        "etp_shard_set_peer": (i32, [vp, i32, vp]),
+        "etp_shard_commit_rows": (i32, [vp, _u64p]),
+        "etp_shard_prove": (i32, [vp, sz, _u64p]),
+        "etp_shard_leaves_at": (i32, [vp, _u64p, sz, _u64p]),
+        "etp_shard_download_coeffs": (i32, [vp, _u64p]),
         "etp_table_num_columns": (i32, [i32]),
         "etp_table_constraint_degree": (i32, [i32]),
         "etp_table_num_public_inputs": (i32, [i32]),
@@ -402,4 +420,88 @@ class PolynomialBatch:
     def __del__(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.L.etp_batch_free(self.h)
+            self.h = None
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class BatchShard:
+    """Rank `rank` of `world`'s share of ONE column-split PolynomialBatch (SURVEY.md 8(e)): the local columns'
+    coefficients + LDE, and the Merkle subtrees of the local leaf rows.  `parallel.commit_column_split` drives
+    the protocol across processes; within one process (several contexts) peers are wired with `set_peer`."""
+
+    def __init__(self, ctx: Context, n_cols_total: int, log_n: int, rate_bits: int, cap_height: int, rank: int, world: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_shard_create(ctx.h, n_cols_total, log_n, rate_bits, cap_height, rank, world, C.byref(h)))
+        self.h = h
+        self.n_cols_total, self.degree_log, self.rate_bits, self.cap_height = n_cols_total, log_n, rate_bits, cap_height
+        self.rank, self.world = rank, world
+        self.first_col = int(ctx.L.etp_shard_first_col(h))
+        self.num_local_cols = int(ctx.L.etp_shard_num_local_cols(h))
+        self.first_row = int(ctx.L.etp_shard_first_row(h))
+        self.num_rows = int(ctx.L.etp_shard_num_rows(h))
+        self._opened = []
+
+    @property
+    def lde_ptr(self) -> int:
+        return int(self.ctx.L.etp_shard_lde_dev(self.h) or 0)
+
+    def transform_values(self, local_values):
+        """iFFT + coset LDE of the local columns (host array, num_local_cols x n)."""
+        a, ptrs = PolynomialBatch._cols(local_values)
+        assert a.shape[0] == self.num_local_cols and (a.size == 0 or a.shape[1] == 1 << self.degree_log)
+        self.ctx.check(self.ctx.L.etp_shard_transform_values_host(self.h, ptrs))
+
+    def transform_values_dev(self, ptr: int, col_stride: int):
+        self.ctx.check(self.ctx.L.etp_shard_transform_values_dev(self.h, C.c_void_p(ptr), col_stride))
+
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self.ctx.check(self.ctx.L.etp_ipc_export(self.ctx.h, C.c_void_p(self.lde_ptr), buf))
+        return buf.raw
+
+    def open_peer(self, peer_rank: int, handle: bytes):
+        p = C.c_void_p()
+        self.ctx.check(self.ctx.L.etp_ipc_open(self.ctx.h, handle, C.byref(p)))
+        self._opened.append(p)
+        self.set_peer(peer_rank, p.value)
+
+    def set_peer(self, peer_rank: int, ptr: int):
+        self.ctx.check(self.ctx.L.etp_shard_set_peer(self.h, peer_rank, C.c_void_p(ptr)))
+
+    def commit_rows(self) -> np.ndarray:
+        """Leaf hashing of the own rows (peers' columns read over NVLink) + own subtrees -> own cap entries."""
+        out = np.zeros(((1 << self.cap_height) // self.world, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_shard_commit_rows(self.h, _p(out)))
+        return out
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        ns = self.degree_log + self.rate_bits - self.cap_height
+        out = np.zeros((max(ns, 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_shard_prove(self.h, leaf_index, _p(out)))
+        return out[:ns]
+
+    def leaves_at(self, idx) -> np.ndarray:
+        idx = _u64(idx).ravel()
+        out = np.zeros((idx.size, self.n_cols_total), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_shard_leaves_at(self.h, _p(idx), idx.size, _p(out)))
+        return out
+
+    @property
+    def polynomials(self) -> np.ndarray:
+        out = np.zeros((max(self.num_local_cols, 1), 1 << self.degree_log), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_shard_download_coeffs(self.h, _p(out)))
+        return out[:self.num_local_cols]
+
+    def close_peers(self):
+        for p in self._opened:
+            self.ctx.L.etp_ipc_close(self.ctx.h, p)
+        self._opened = []
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.close_peers()
+            self.ctx.L.etp_shard_free(self.h)
             self.h = None

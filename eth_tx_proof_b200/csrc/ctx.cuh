@@ -24,6 +24,8 @@ struct DevPowTable {
 struct etp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D of column groups, overlapped with the transforms / hashing on `stream`
+  std::vector<cudaEvent_t> sync_events;  // timing-disabled events reused by the streamed host commits
   std::string err;
   uint64_t launches = 0;
   // (base, bits, scale) -> device tables
@@ -153,5 +155,12 @@ struct etp_batch {
 int batch_create(etp_ctx* ctx, size_t n_cols, int log_n, int rate_bits, int blinding, int cap_height, etp_batch** out);
 // coeffs already in b->coeffs: LDE + leaf hashing + tree
 int batch_commit_from_coeffs(etp_batch* b);
+// host columns -> commit, column group by column group: group k is transformed and absorbed by the leaf
+// sponges while group k+1 crosses PCIe.  is_values: run the iFFT first (from_values) or take the columns as
+// coefficients (from_coeffs).
+int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values);
+int launch_leaf_hash(etp_ctx* ctx, const merkle::LeafSrc& src, int c_begin, int c_end, int n_cols_total, uint32_t row0,
+                     uint32_t n_rows, uint64_t* digests);
+int get_sync_event(etp_ctx* ctx, size_t i, cudaEvent_t* out);
 // values (device, natural order) -> coeffs -> commit
 int batch_commit_from_values(etp_batch* b, const uint64_t* values_dev, size_t col_stride);

@@ -32,7 +32,9 @@ extern "C" int etp_ctx_create(int device, etp_ctx** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  if (cudaMalloc((void**)&ctx->d_pow_result, 16) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void**)&ctx->d_pow_result, 16) != cudaSuccess) {
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ETP_ERR_CUDA;
@@ -48,6 +50,8 @@ extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
   for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
   for (auto& kv : ctx->full_tables) cudaFree(kv.second);
   cudaFree(ctx->d_pow_result);
+  for (auto e : ctx->sync_events) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -443,6 +447,27 @@ int batch_create(etp_ctx* ctx, size_t n_cols, int log_n, int rate_bits, int blin
   return ETP_OK;
 }
 
+int launch_leaf_hash(etp_ctx* ctx, const merkle::LeafSrc& src, int c_begin, int c_end, int n_cols_total, uint32_t row0,
+                     uint32_t n_rows, uint64_t* digests) {
+  if (n_rows == 0) return ETP_OK;
+  merkle::hash_leaves_colmajor<<<(n_rows + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
+      src, c_begin, c_end, n_cols_total, row0, n_rows, digests);
+  ETP_LAUNCH_CHECK(ctx);
+  return ETP_OK;
+}
+
+int get_sync_event(etp_ctx* ctx, size_t i, cudaEvent_t* out) {
+  while (ctx->sync_events.size() <= i) {
+    cudaEvent_t e;
+    ETP_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->sync_events.push_back(e);
+  }
+  *out = ctx->sync_events[i];
+  return ETP_OK;
+}
+
+static int batch_finish_levels(etp_batch* b);
+
 int batch_commit_from_coeffs(etp_batch* b) {
   etp_ctx* ctx = b->ctx;
   if (!b->timed_ifft) cudaEventRecord(b->ev[0], ctx->stream);
@@ -456,13 +481,16 @@ int batch_commit_from_coeffs(etp_batch* b) {
   ETP_TRY(ntt_run(ctx, args));
   cudaEventRecord(b->ev[2], ctx->stream);
   // "build Merkle tree"
-  const uint32_t nl = (uint32_t)b->lde_n();
-  merkle::hash_leaves_colmajor<<<(nl + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
-      b->lde, b->lde_n(), (int)b->n_cols, nl, b->levels);
-  ETP_LAUNCH_CHECK(ctx);
+  ETP_TRY(launch_leaf_hash(ctx, merkle::single_src(b->lde, b->lde_n(), (int)b->n_cols), 0, (int)b->n_cols, (int)b->n_cols, 0,
+                           (uint32_t)b->lde_n(), b->levels));
   cudaEventRecord(b->ev[3], ctx->stream);
   b->timed_ifft = false;
-  // the cap copy inside merkle_build_levels synchronises; record the end marker before it
+  return batch_finish_levels(b);
+}
+
+// inner levels + cap of a batch whose leaf digests are in levels[0]
+static int batch_finish_levels(etp_batch* b) {
+  etp_ctx* ctx = b->ctx;
   size_t n = b->lde_n();
   uint64_t* cur = b->levels;
   while (n > ((size_t)1 << b->cap_height)) {
@@ -492,6 +520,83 @@ int batch_commit_from_values(etp_batch* b, const uint64_t* values_dev, size_t co
   return batch_commit_from_coeffs(b);
 }
 
+// ---- streamed host commit -----------------------------------------------------------------------------
+// Columns are independent until the leaf sponge, and the sponge absorbs them in order, 8 at a time: so the
+// batch is cut into groups of G columns (G a multiple of 8) and group k runs iFFT -> coset LDE -> sponge
+// absorb on the compute stream while group k+1 is copied on the copy stream.  Only 2 G n words of staging
+// are needed (values) or none (coefficients land in b->coeffs directly).
+static size_t stream_group_cols(const etp_batch* b) {
+  const size_t bytes = b->n_cols * b->n() * 8;
+  if (b->n_cols <= 8 || bytes < ((size_t)32 << 20)) return b->n_cols ? b->n_cols : 1;  // too small to pipeline
+  size_t g = (b->n_cols + 7) / 8;   // aim at 8 groups
+  g = (g + 7) / 8 * 8;
+  return g;
+}
+
+__global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* dst, size_t n, size_t n_cols);
+
+int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values) {
+  etp_ctx* ctx = b->ctx;
+  const size_t n = b->n(), C = b->n_cols, G = stream_group_cols(b);
+  // a last group of fewer than 8 columns joins its predecessor: its ragged sponge chunk keeps rate lanes of the
+  // previous permutation, and only the capacity lanes are carried from one launch to the next
+  size_t n_groups = C ? (C + G - 1) / G : 0;
+  if (n_groups > 1 && C - (n_groups - 1) * G < 8) n_groups--;
+  for (size_t c = 0; c < C; c++)
+    if (!cols[c]) return etp_fail(ctx, ETP_ERR_INVALID, "null column %zu", c);
+  DevBuf<uint64_t> stage(ctx);
+  const size_t slot = (G + 8) * n;
+  if (is_values) ETP_TRY(stage.alloc(2 * slot));
+  cudaEvent_t ready;
+  ETP_TRY(get_sync_event(ctx, 0, &ready));
+  cudaEventRecord(b->ev[0], ctx->stream);
+  cudaEventRecord(b->ev[1], ctx->stream);
+  cudaEventRecord(b->ev[2], ctx->stream);
+  ETP_CUDA(ctx, cudaEventRecord(ready, ctx->stream));  // buffers allocated (stream-ordered) before the copies start
+  ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
+  for (size_t k = 0; k < n_groups; k++) {
+    const size_t c0 = k * G, gc = (k + 1 == n_groups ? C - c0 : G);
+    uint64_t* land = is_values ? stage.p + (k & 1) * slot : b->coeffs + c0 * n;
+    cudaEvent_t h2d_done, slot_free;
+    ETP_TRY(get_sync_event(ctx, 1 + 2 * k, &h2d_done));
+    ETP_TRY(get_sync_event(ctx, 2 + 2 * k, &slot_free));
+    if (is_values && k >= 2) {  // the staging slot is free once the iFFT of group k-2 has consumed it
+      cudaEvent_t prev;
+      ETP_TRY(get_sync_event(ctx, 2 + 2 * (k - 2), &prev));
+      ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, prev, 0));
+    }
+    for (size_t c = 0; c < gc; c++)
+      ETP_CUDA(ctx, cudaMemcpyAsync(land + c * n, cols[c0 + c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    ETP_CUDA(ctx, cudaEventRecord(h2d_done, ctx->copy_stream));
+    ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, h2d_done, 0));
+    NttArgs args;
+    if (is_values) {  // "IFFT": natural -> natural; this group's slice of the LDE buffer is the scratch
+      args.in = land; args.in_stride = n; args.n_in = (uint32_t)n;
+      args.out = b->coeffs + c0 * n; args.out_stride = n;
+      args.scratch = b->lde + c0 * b->lde_n(); args.scratch_stride = b->lde_n();
+      args.log_n = b->log_n; args.n_cols = gc; args.inverse = true; args.natural_out = true;
+      ETP_TRY(ntt_run(ctx, args));
+      ETP_CUDA(ctx, cudaEventRecord(slot_free, ctx->stream));
+    } else {
+      k_canon_copy<<<(unsigned)((gc * n + 255) / 256), 256, 0, ctx->stream>>>(land, n, land, n, gc);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+    args = NttArgs();  // "FFT + blinding"
+    args.in = b->coeffs + c0 * n; args.in_stride = n; args.n_in = (uint32_t)n;
+    args.out = b->lde + c0 * b->lde_n(); args.out_stride = b->lde_n();
+    args.log_n = b->log_n + b->rate_bits; args.n_cols = gc;
+    args.coset_shift = gl::GENERATOR;
+    ETP_TRY(ntt_run(ctx, args));
+    ETP_TRY(launch_leaf_hash(ctx, merkle::single_src(b->lde, b->lde_n(), (int)C), (int)c0, (int)(c0 + gc), (int)C, 0,
+                             (uint32_t)b->lde_n(), b->levels));
+  }
+  if (C == 0)
+    ETP_TRY(launch_leaf_hash(ctx, merkle::single_src(b->lde, b->lde_n(), 0), 0, 0, 0, 0, (uint32_t)b->lde_n(), b->levels));
+  cudaEventRecord(b->ev[3], ctx->stream);
+  b->timed_ifft = false;
+  return batch_finish_levels(b);
+}
+
 __global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* dst, size_t n, size_t n_cols) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= n * n_cols) return;
@@ -499,24 +604,12 @@ __global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* d
   dst[t] = gl::canon(src[c * src_stride + i]);
 }
 
-static int upload_columns(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, size_t n, uint64_t* dst) {
-  for (size_t c = 0; c < n_cols; c++) {
-    if (!cols[c]) return etp_fail(ctx, ETP_ERR_INVALID, "null column %zu", c);
-    ETP_CUDA(ctx, cudaMemcpyAsync(dst + c * n, cols[c], n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  return ETP_OK;
-}
-
 extern "C" int etp_batch_from_values_host(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, int log_n, int rate_bits,
                                           int blinding, int cap_height, etp_batch** out) {
   if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
-  DevBuf<uint64_t> stage_buf(ctx);
-  int rc = stage_buf.alloc(n_cols * b->n());
-  uint64_t* stage = stage_buf.p;
-  if (rc == ETP_OK) rc = upload_columns(ctx, cols, n_cols, b->n(), stage);
-  if (rc == ETP_OK) rc = batch_commit_from_values(b, stage, b->n());
+  int rc = batch_commit_from_host_streamed(b, cols, true);
   if (rc != ETP_OK) { etp_batch_free(b); return rc; }
   *out = b;
   return ETP_OK;
@@ -527,13 +620,7 @@ extern "C" int etp_batch_from_coeffs_host(etp_ctx* ctx, const uint64_t* const* c
   if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
-  int rc = upload_columns(ctx, cols, n_cols, b->n(), b->coeffs);
-  const size_t tot = n_cols * b->n();
-  if (rc == ETP_OK && tot) {
-    k_canon_copy<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(b->coeffs, b->n(), b->coeffs, b->n(), n_cols);
-    ctx->launches++;
-  }
-  if (rc == ETP_OK) rc = batch_commit_from_coeffs(b);
+  int rc = batch_commit_from_host_streamed(b, cols, false);
   if (rc != ETP_OK) { etp_batch_free(b); return rc; }
   *out = b;
   return ETP_OK;

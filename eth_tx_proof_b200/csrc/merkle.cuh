@@ -33,31 +33,70 @@ __device__ __forceinline__ void store_digest(uint64_t* dst, const uint64_t (&s)[
   reinterpret_cast<ulonglong2*>(dst)[1] = b;
 }
 
-// leaf i = (cols[0][i], cols[1][i], ...), column c at base + c*col_stride.  hash_or_noop semantics.
-static __global__ void __launch_bounds__(HASH_THREADS, ETP_LEAF_MIN_BLOCKS) hash_leaves_colmajor(const uint64_t* __restrict__ base, size_t col_stride,
-                                                                     int n_cols, uint32_t n_leaves,
+// Where the columns of a leaf live.  Column c is base[c / cols_per_src] + (c % cols_per_src) * col_stride:
+// one source for an ordinary batch; one per GPU for a column-split batch, where the peers' LDE
+// matrices are mapped through CUDA IPC and read over NVLink by the hashing kernel itself (the
+// all-gather of row tiles is fused into the hash: SURVEY.md 8(e)).  cols_per_src is a multiple of 8
+// whenever there is more than one source, so an 8-column sponge chunk never straddles two sources.
+constexpr int MAX_SRC = 8;
+struct LeafSrc {
+  const uint64_t* base[MAX_SRC];
+  size_t col_stride;
+  int cols_per_src;
+};
+
+// leaf row0 + i = (col_0[row0 + i], col_1[row0 + i], ...) -> digests[i].  hash_or_noop semantics.
+// The sponge (overwrite mode, rate 8) absorbs columns [c_begin, c_end) of n_cols_total; a call with
+// c_begin > 0 resumes from the capacity lanes s[8..12) that the previous call left in digests[i]
+// (c_begin is a multiple of 8, so the rate lanes are overwritten anyway), and a call with
+// c_end < n_cols_total leaves them there instead of the digest.  This is what lets a host commit hash
+// column group k while group k+1 is still crossing PCIe (etp_batch_from_values_host).
+static __global__ void __launch_bounds__(HASH_THREADS, ETP_LEAF_MIN_BLOCKS) hash_leaves_colmajor(const __grid_constant__ LeafSrc src, int c_begin, int c_end,
+                                                                     int n_cols_total, uint32_t row0, uint32_t n_rows,
                                                                      uint64_t* __restrict__ digests) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_leaves) return;
+  if (i >= n_rows) return;
+  const size_t row = (size_t)row0 + i;
   uint64_t s[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) s[k] = 0;
-  if (n_cols <= 4) {  // hash_or_noop: copy and zero-pad
+  if (n_cols_total <= 4) {  // hash_or_noop: copy and zero-pad
 #pragma unroll
     for (int c = 0; c < 4; c++)
-      if (c < n_cols) s[c] = base[(size_t)c * col_stride + i];
+      if (c < n_cols_total) s[c] = src.base[0][(size_t)c * src.col_stride + row];
     store_digest(digests + 4 * (size_t)i, s);
     return;
   }
+  if (c_begin > 0) {
+    const ulonglong2* st = reinterpret_cast<const ulonglong2*>(digests + 4 * (size_t)i);
+    const ulonglong2 a = st[0], b = st[1];
+    s[8] = a.x; s[9] = a.y; s[10] = b.x; s[11] = b.y;
+  }
   // one call site for the permutation (instruction-cache footprint); a ragged last chunk overwrites
   // only the first (n_cols - c) rate lanes
-  for (int c = 0; c < n_cols; c += 8) {
+  for (int c = c_begin; c < c_end; c += 8) {
+    const int si = c / src.cols_per_src;
+    const uint64_t* __restrict__ p = src.base[si] + (size_t)(c - si * src.cols_per_src) * src.col_stride + row;
 #pragma unroll
     for (int k = 0; k < 8; k++)
-      if (c + k < n_cols) s[k] = __ldg(base + (size_t)(c + k) * col_stride + i);
+      if (c + k < c_end) s[k] = __ldg(p + (size_t)k * src.col_stride);
     poseidon::permute(s);
   }
+  if (c_end < n_cols_total) {  // park the capacity lanes (kept as they are: any u64 is a valid lane value)
+    ulonglong2 a, b;
+    a.x = s[8]; a.y = s[9]; b.x = s[10]; b.y = s[11];
+    reinterpret_cast<ulonglong2*>(digests + 4 * (size_t)i)[0] = a;
+    reinterpret_cast<ulonglong2*>(digests + 4 * (size_t)i)[1] = b;
+    return;
+  }
   store_digest(digests + 4 * (size_t)i, s);
+}
+inline LeafSrc single_src(const uint64_t* base, size_t col_stride, int n_cols) {
+  LeafSrc s{};
+  s.base[0] = base;
+  s.col_stride = col_stride;
+  s.cols_per_src = n_cols > 0 ? n_cols : 1;
+  return s;
 }
 
 // leaves stored row-major (n_leaves x leaf_len): MerkleTree::new on caller-provided rows, FRI layers.

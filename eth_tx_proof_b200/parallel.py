@@ -11,7 +11,7 @@ through Paladin.
 """
 from __future__ import annotations
 
-from typing import Any, List, Sequence
+from typing import Any, List, Sequence, Tuple
 
 
 def shard_jobs(n_jobs: int, rank: int, world: int) -> List[int]:
@@ -42,3 +42,64 @@ def gather_results(local: Sequence[Any]) -> List[Any]:
     dist.all_gather_object(out, list(local))
     merged = [kv for part in out for kv in part]
     return sorted(merged, key=lambda kv: kv[0])
+
+
+# ---- column-split commit of one oversized table ---------------------------------------
+def cols_per_rank(n_cols: int, world: int) -> int:
+    """Columns per shard: ceil(n_cols / world) rounded up to the sponge rate (8), as etp_shard_cols_per_rank."""
+    cps = -(-n_cols // world)
+    return -(-cps // 8) * 8
+
+
+def column_split_plan(n_cols: int, lde_rows: int, cap_height: int, rank: int, world: int) -> dict:
+    """What rank `rank` owns: a column range (a multiple of 8 wide, so that no 8-column sponge chunk straddles
+    two GPUs), a leaf-row range and the cap entries of those rows (whole cap subtrees)."""
+    if world < 1 or world & (world - 1) or world > 8:
+        raise ValueError("world must be a power of two <= 8")
+    if (1 << cap_height) < world:
+        raise ValueError("2^cap_height must be >= world")
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    cps = cols_per_rank(n_cols, world)
+    c0 = min(cps * rank, n_cols)
+    c1 = min(c0 + cps, n_cols)
+    rows = lde_rows // world
+    caps = (1 << cap_height) // world
+    return {"cols": (c0, c1), "rows": (rows * rank, rows * (rank + 1)), "cap_entries": (caps * rank, caps * (rank + 1))}
+
+
+def assemble_cap(parts: Sequence[Any]):
+    """Cap of the whole table = the ranks' parts in rank order."""
+    import numpy as np
+
+    return np.concatenate([np.asarray(p, dtype=np.uint64).reshape(-1, 4) for p in parts], axis=0)
+
+
+def commit_column_split(shard, local_values=None, values_dev: Tuple[int, int] = None):
+    """Runs the column-split commit protocol on this rank (call on every rank of the default process group):
+    local transforms -> IPC handle exchange -> barrier -> leaf hashing over NVLink peer loads + own subtrees ->
+    all-gather of the cap parts.  Returns the whole cap (2^cap_height x 4).  The peers' mappings stay open
+    (needed for `leaves_at`); call `finish_column_split(shard)` before freeing the shard."""
+    import torch.distributed as dist
+
+    if values_dev is not None:
+        shard.transform_values_dev(*values_dev)
+    else:
+        shard.transform_values(local_values)
+    handles = [None] * shard.world
+    dist.all_gather_object(handles, shard.export_handle())
+    for r, hnd in enumerate(handles):
+        if r != shard.rank and column_split_plan(shard.n_cols_total, 8, shard.cap_height, r, shard.world)["cols"][0] < shard.n_cols_total:
+            shard.open_peer(r, hnd)
+    dist.barrier()  # every LDE matrix complete (the transforms synchronise their stream) and mapped
+    part = shard.commit_rows()
+    parts = [None] * shard.world
+    dist.all_gather_object(parts, part.tolist())
+    return assemble_cap(parts)
+
+
+def finish_column_split(shard):
+    import torch.distributed as dist
+
+    dist.barrier()  # nobody is still reading this rank's LDE
+    shard.close_peers()

@@ -128,6 +128,47 @@ int etp_batch_prove(etp_batch *b, size_t leaf_index, uint64_t *siblings_out);
 const uint64_t *etp_batch_lde_dev(const etp_batch *b, size_t *col_stride);
 const uint64_t *etp_batch_coeffs_dev(const etp_batch *b, size_t *col_stride);
 
+/* ---- column-split commit of one oversized table across the GPUs of a box ------------------------
+ * BASELINE.json north_star / SURVEY.md 8(e): PolynomialBatch::from_values of a table whose LDE does not
+ * fit (or is too slow on) one GPU.  One process per GPU; rank g of `world` (a power of two <= 8 and
+ * <= 2^cap_height) owns columns [g*cps, (g+1)*cps) with cps = etp_shard_cols_per_rank() and the leaf rows
+ * [g*L/world, (g+1)*L/world), i.e. whole cap subtrees.  Protocol (every rank):
+ *   etp_shard_create -> etp_shard_transform_values_{host,dev} (local iFFT + coset LDE)
+ *   -> exchange etp_ipc_export(etp_shard_lde_dev) handles, etp_ipc_open + etp_shard_set_peer for each peer
+ *   -> BARRIER -> etp_shard_commit_rows (leaf hashing reads the peers' columns over NVLink inside the
+ *   kernel; own subtrees; returns the own 2^cap_height/world cap entries) -> all-gather the cap parts
+ *   -> BARRIER before any LDE buffer is freed or overwritten.
+ * The assembled cap, the Merkle paths and the rows equal those of the unsplit from_values. */
+typedef struct etp_shard etp_shard;
+#define ETP_IPC_HANDLE_BYTES 64
+size_t etp_shard_cols_per_rank(size_t n_cols_total, int world);
+int etp_shard_create(etp_ctx *ctx, size_t n_cols_total, int log_n, int rate_bits, int cap_height, int rank, int world,
+                     etp_shard **out);
+void etp_shard_free(etp_shard *s);
+size_t etp_shard_first_col(const etp_shard *s);
+size_t etp_shard_num_local_cols(const etp_shard *s);
+size_t etp_shard_first_row(const etp_shard *s);
+size_t etp_shard_num_rows(const etp_shard *s);
+/* the local LDE matrix (local columns x (n << rate_bits), column-major, bit-reversed rows): what peers map */
+const uint64_t *etp_shard_lde_dev(const etp_shard *s);
+/* local_cols: etp_shard_num_local_cols() host pointers / one device matrix of the LOCAL columns */
+int etp_shard_transform_values_host(etp_shard *s, const uint64_t *const *local_cols);
+int etp_shard_transform_values_dev(etp_shard *s, const uint64_t *values_dev, size_t col_stride);
+/* CUDA IPC plumbing for one-process-per-GPU peers (cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle) */
+int etp_ipc_export(etp_ctx *ctx, const void *dev_ptr, unsigned char handle_out[ETP_IPC_HANDLE_BYTES]);
+int etp_ipc_open(etp_ctx *ctx, const unsigned char handle[ETP_IPC_HANDLE_BYTES], void **dev_ptr_out);
+int etp_ipc_close(etp_ctx *ctx, void *dev_ptr);
+/* peer_lde: rank peer_rank's etp_shard_lde_dev as addressable from this context's device */
+int etp_shard_set_peer(etp_shard *s, int peer_rank, const uint64_t *peer_lde);
+/* cap_part_out: (2^cap_height / world) x 4 — entries [rank * 2^cap_height / world, ...) of merkle_tree.cap */
+int etp_shard_commit_rows(etp_shard *s, uint64_t *cap_part_out);
+/* merkle_tree.prove(leaf_index) for a leaf this rank owns: (log2(L) - cap_height) x 4 */
+int etp_shard_prove(etp_shard *s, size_t leaf_index, uint64_t *siblings_out);
+/* merkle_tree.leaves[idx[q]] (all n_cols_total columns, any owner): rows_out n_idx x n_cols_total */
+int etp_shard_leaves_at(etp_shard *s, const uint64_t *idx, size_t n_idx, uint64_t *rows_out);
+/* polynomials of the local columns (local x n, column-major) */
+int etp_shard_download_coeffs(etp_shard *s, uint64_t *out);
+
 /* ---- starky: tables, compute_quotient_polys, prove ------------------------------------------- */
 #define ETP_TABLE_FIBONACCI 0 /* starky/src/fibonacci_stark.rs                                        */
 #define ETP_TABLE_MEMORY 1    /* evm_arithmetization/src/memory/memory_stark.rs (shape) */

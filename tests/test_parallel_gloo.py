@@ -37,6 +37,15 @@ def _worker(rank, world, port, q):
         local.append((j, oracle.Batch.from_values(vals, 1, 2).cap.tolist()))
     merged = parallel.gather_results(local)
     t = parallel.max_over_ranks(10.0 + rank)
+    # column-split commit, host side: each rank contributes the cap entries of the rows it owns (here cut out of
+    # the oracle's cap of the whole table) and every rank assembles the same whole cap
+    vals = syn.random_columns(20, 6, seed=9)
+    whole = oracle.Batch.from_values(vals, 1, 3).cap
+    plan = parallel.column_split_plan(20, 2 << 6, 3, rank, world)
+    lo, hi = plan["cap_entries"]
+    parts = [None] * world
+    dist.all_gather_object(parts, whole[lo:hi].tolist())
+    assert (parallel.assemble_cap(parts) == whole).all()
     dist.barrier()
     q.put((rank, jobs, merged, t))
     dist.destroy_process_group()
@@ -77,3 +86,26 @@ def test_single_process_fallbacks():
 
     assert parallel.max_over_ranks(3.5) == 3.5
     assert parallel.gather_results([(1, "b"), (0, "a")]) == [(0, "a"), (1, "b")]
+
+
+def test_column_split_plan_covers_columns_rows_and_cap():
+    sys.path.insert(0, ROOT)
+    from eth_tx_proof_b200 import parallel
+
+    for n_cols, world, cap in [(128, 8, 4), (21, 2, 4), (7, 4, 2), (100, 8, 3), (1, 2, 1)]:
+        lde = 1 << 12
+        cols, rows, caps = [], [], []
+        for r in range(world):
+            p = parallel.column_split_plan(n_cols, lde, cap, r, world)
+            assert p["cols"][0] % 8 == 0 or p["cols"][0] == n_cols   # sponge chunks never straddle two GPUs
+            cols += list(range(*p["cols"]))
+            rows.append(p["rows"])
+            caps += list(range(*p["cap_entries"]))
+        assert cols == list(range(n_cols))
+        assert rows[0][0] == 0 and rows[-1][1] == lde and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+        assert caps == list(range(1 << cap))
+    assert parallel.cols_per_rank(128, 8) == 16 and parallel.cols_per_rank(100, 8) == 16 and parallel.cols_per_rank(21, 2) == 16
+    with pytest.raises(ValueError):
+        parallel.column_split_plan(16, 64, 1, 0, 4)   # fewer cap subtrees than ranks
+    with pytest.raises(ValueError):
+        parallel.column_split_plan(16, 64, 4, 0, 3)

@@ -25,3 +25,19 @@ for it in range(5):
 bytes_ = 8 * cols * n * 4 + 32 * (2 * (2 * n - 16) + 16)
 print("phases ms:", {k: round(v, 3) for k, v in b.last_commit_timings().items()})
 print(f"commit 2^{log_n} x {cols}: ms {ts}  best {min(ts):.3f} ms  -> {bytes_ / min(ts) / 1e6:.1f} GB/s algorithmic")
+if "--e2e" in sys.argv:
+    import time
+    import numpy as np
+    del b
+    host = torch.empty((cols, n), dtype=torch.int64).pin_memory()
+    host.copy_(x)
+    harr = host.numpy().view(np.uint64)
+    b2 = etp.PolynomialBatch.from_values(ctx, harr, 1, False, 4); del b2
+    ts = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        b2 = etp.PolynomialBatch.from_values(ctx, harr, 1, False, 4)
+        cap = b2.cap
+        ts.append((time.perf_counter() - t0) * 1e3)
+        del b2
+    print(f"e2e host->commit->cap 2^{log_n} x {cols}: ms {[round(t, 2) for t in ts]}  H2D alone would be {8 * cols * n / 55e6:.1f} ms at 55 GB/s")
