@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--skip-stark", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-split", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,6 +275,35 @@ def main():
                  "timed": "trace resident in HBM -> complete proof bytes on the host (wall clock, max over ranks)"}
         del trace
 
+    # ---- one table column-split across all ranks: strong scaling of a single commit.
+    # Rank g transforms columns [g*C/G, (g+1)*C/G) and hashes leaf rows [g*L/G, (g+1)*L/G), reading the peers'
+    # LDE columns over NVLink inside the hashing kernel; the cap parts are all-gathered over NCCL.
+    split = None
+    if world > 1 and not args.skip_split and (world & (world - 1)) == 0 and world <= 8:
+        from eth_tx_proof_b200 import parallel
+
+        g2 = torch.Generator(device="cuda").manual_seed(0xC0)
+        c0, c1 = parallel.column_split_plan(cols, 2 * n, CAP_HEIGHT, rank, world)["cols"]
+        xs = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g2)[c0:c1].contiguous()
+        shard = etp.BatchShard(ctx, cols, log_n, RATE_BITS, CAP_HEIGHT, rank, world)
+        cap0 = parallel.commit_column_split(shard, values_dev=(xs.data_ptr(), n))
+        for _ in range(2):
+            parallel.recommit_column_split(shard, (xs.data_ptr(), n))
+        barrier()
+        t0 = time.perf_counter()
+        reps = 4
+        for _ in range(reps):
+            cap1 = parallel.recommit_column_split(shard, (xs.data_ptr(), n))
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) / reps)
+        assert (cap0 == cap1).all()
+        split = {"workload": f"ONE 2^{log_n} x {cols} table column-split over {world} GPUs (CUDA IPC + NVLink peer loads fused into the "
+                             "leaf-hash kernel; cap parts all-gathered over NCCL)", "ms_per_commit": dt * 1e3,
+                 "value": nbytes / dt / 1e9, "unit": "GB/s", "scaling": "strong",
+                 "timed": "local columns resident in HBM -> whole cap on every rank (wall clock incl. 2 barriers, max over ranks)"}
+        parallel.finish_column_split(shard)
+        del shard, xs
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,16 +327,20 @@ def main():
     achieved = leaf_bytes / (leaf_ms / 1e3) / 1e9
     perms_leaf = (n << RATE_BITS) * ((cols + 7) // 8)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    # integer-pipe roofline: the Poseidon kernels are bound by the shared ALU/FP64 issue port
-    # (profiles/README.md): 2 clk per warp instruction, ~18.7k such instructions per warp-permutation
-    port_instr_per_perm = 18700
-    perm_peak = 148 * 4 * sm_mhz * 1e6 / (2 * port_instr_per_perm) * 32
+    # issue-slot roofline of the Poseidon kernels (profiles/README.md, tools/microbench/pipes3.cu + poseidon_parts.cu):
+    # on B200 a DFMA/DADD holds the sub-partition's issue port for ~2.2 clk (FP64 and integer work do NOT overlap:
+    # S-boxes alone 15.7k clk + MDS alone 15.2k clk ~= full permutation 29.0k clk per warp), every other
+    # instruction takes one slot.  Static SASS counts per permutation (tools/sass_count.py): 6600 FP64 + 12897 others.
+    fp64_per_perm, other_per_perm = 6600, 12897
+    slots_per_perm = 2.2 * fp64_per_perm + other_per_perm
+    perm_peak = 148 * 4 * sm_mhz * 1e6 / slots_per_perm * 32
     roofline = {"kernel": "merkle::hash_leaves_colmajor", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "dominant kernel is integer/FP64-issue bound (16 Poseidon permutations per 1 KiB row), not HBM bound; see int_pipe"}
     int_pipe = {"kernel": "merkle::hash_leaves_colmajor", "achieved": perms_leaf / (leaf_ms / 1e3), "peak": perm_peak, "unit": "perm/s",
                 "frac": perms_leaf / (leaf_ms / 1e3) / perm_peak,
-                "model": "148 SM x 4 SMSP x f_sm / (2 clk x 18.7k ALU+FP64-port instr per warp-perm) x 32 lanes; f_sm = sampled clock"}
+                "model": "issue slots: 148 SM x 4 SMSP x f_sm x 32 lanes / (2.2 x 6600 FP64 + 12897 other warp-instructions per permutation); "
+                         "f_sm = sampled clock; the bound of this kernel's own instruction stream, not a hardware peak"}
     ntt_bytes_ifft = 16 * cols * n
     ntt_bytes_lde = 8 * cols * n + 8 * cols * (n << RATE_BITS)
     kernels = [
@@ -335,7 +369,7 @@ def main():
                    "l2": f"inputs ({8 * cols * n >> 20} MiB per batch) are larger than the 126 MB L2; no flush needed",
                    "algorithmic_bytes_per_step": nbytes, "poseidon_permutations_per_step": commit_perms(log_n, cols)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark,
+        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "column_split": split,
     }
     print(json.dumps(out))
     if world > 1:

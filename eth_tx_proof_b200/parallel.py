@@ -98,6 +98,23 @@ def commit_column_split(shard, local_values=None, values_dev: Tuple[int, int] = 
     return assemble_cap(parts)
 
 
+def recommit_column_split(shard, values_dev: Tuple[int, int]):
+    """Second and later commits into a shard whose peers are already mapped (the LDE buffers persist, so the IPC
+    handles stay valid): local transforms -> barrier -> leaf hashing over NVLink + own subtrees -> NCCL all-gather
+    of the cap parts.  Returns the whole cap."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    dist.barrier()  # peers have finished reading the previous LDE
+    shard.transform_values_dev(*values_dev)
+    dist.barrier()
+    part = torch.from_numpy(shard.commit_rows().view(np.int64)).cuda()
+    whole = torch.empty((shard.world * part.shape[0], 4), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(whole, part)
+    return whole.cpu().numpy().view(np.uint64)
+
+
 def finish_column_split(shard):
     import torch.distributed as dist
 
