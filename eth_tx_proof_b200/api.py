@@ -110,15 +110,17 @@ def load_library():
         "etp_shard_prove": (i32, [vp, sz, _u64p]),
         "etp_shard_leaves_at": (i32, [vp, _u64p, sz, _u64p]),
         "etp_shard_download_coeffs": (i32, [vp, _u64p]),
-        "etp_table_num_columns": (i32, [i32]),
-        "etp_table_constraint_degree": (i32, [i32]),
-        "etp_table_num_public_inputs": (i32, [i32]),
-        "etp_table_num_aux_columns": (i32, [i32, i32]),
-        "etp_table_quotient_degree_factor": (i32, [i32]),
+        "etp_table_num_columns": (i32, [vp, i32]),
+        "etp_table_constraint_degree": (i32, [vp, i32]),
+        "etp_table_num_public_inputs": (i32, [vp, i32]),
+        "etp_table_num_aux_columns": (i32, [vp, i32, i32]),
+        "etp_table_quotient_degree_factor": (i32, [vp, i32]),
+        "etp_table_register": (i32, [vp, _u64p, sz, C.POINTER(C.c_int32), sz, C.POINTER(i32)]),
+        "etp_cprog_compile_check": (i32, [_u64p, sz, C.POINTER(sz), C.c_char_p, sz]),
         "etp_lookup_helper_columns_dev": (i32, [vp, i32, i32, vp, sz, _u64p, i32, vp]),
         "etp_compute_quotient_polys_dev": (i32, [vp, i32, vp, vp, _u64p, i32, _u64p, _u64p, i32, vp]),
         "etp_pow_grind": (i32, [vp, _u64p, i32, i32, _u64p]),
-        "etp_stark_proof_words": (sz, [i32, i32]),
+        "etp_stark_proof_words": (sz, [vp, i32, i32]),
         "etp_stark_prove_host": (i32, [vp, i32, i32, _u64p, _u64p, _u64p]),
         "etp_stark_prove_dev": (i32, [vp, i32, i32, vp, sz, _u64p, _u64p]),
         "etp_last_prove_timings": (i32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]),
@@ -215,7 +217,23 @@ class Context:
 
     # ---- starky
     def stark_proof_words(self, table, log_n) -> int:
-        return int(self.L.etp_stark_proof_words(table, log_n))
+        return int(self.L.etp_stark_proof_words(self.h, table, log_n))
+
+    def register_table(self, program, lookups=()) -> int:
+        """Registers a table from its constraint program (``cprog.Program.words`` or a u64 array) and its lookups
+        (``[(looking_columns, table_column, frequencies_column), ...]``): NVRTC-compiles the quotient kernel for
+        sm_100a.  Returns the table id accepted by stark_prove / compute_quotient_polys / lookup_helper_columns."""
+        words = _u64(getattr(program, "words", program))
+        flat = [len(lookups)]
+        for looking, table_col, freq_col in lookups:
+            flat += [int(table_col), int(freq_col), len(looking)] + [int(c) for c in looking]
+        arr = (C.c_int32 * len(flat))(*flat)
+        out = C.c_int(0)
+        self.check(self.L.etp_table_register(self.h, _p(words), words.size, arr, len(flat) if lookups else 0, C.byref(out)))
+        return int(out.value)
+
+    def table_num_aux_columns(self, table, num_challenges=2) -> int:
+        return int(self.L.etp_table_num_aux_columns(self.h, table, num_challenges))
 
     def stark_prove(self, table, trace, public_inputs=()) -> np.ndarray:
         """starky::prover::prove(stark, &StarkConfig::standard_fast_config(), trace, public_inputs)."""
@@ -248,7 +266,7 @@ class Context:
         al = _u64(alphas)
         lc = _u64(list(lookup_challenges) + [0])
         pi = _u64(list(public_inputs) + [0])
-        factor = self.L.etp_table_quotient_degree_factor(table)
+        factor = self.L.etp_table_quotient_degree_factor(self.h, table)
         n = 1 << trace_batch.degree_log
         out = np.zeros((factor * al.size, n), dtype=np.uint64)
         d = C.c_void_p()

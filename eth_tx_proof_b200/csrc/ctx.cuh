@@ -21,6 +21,13 @@ struct DevPowTable {
   int lo_bits = 0;
 };
 
+// a kernel compiled at run time from a constraint program (etp_jit.cu)
+struct JitKernel {
+  void* library = nullptr;  // cudaLibrary_t
+  void* kernel = nullptr;   // cudaKernel_t
+};
+struct RegisteredTable;  // etp_stark.cu
+
 struct etp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -35,7 +42,12 @@ struct etp_ctx {
   // last prove timings
   std::vector<std::pair<const char*, float>> timings;
   uint64_t* d_pow_result = nullptr;  // PoW grind result slot
+  std::vector<RegisteredTable*> tables;  // program-defined tables, id = ETP_TABLE_FIRST_REGISTERED + index
 };
+void free_registered_tables(etp_ctx* ctx);  // etp_stark.cu
+int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubin_out, std::string* log_out);
+int jit_load(etp_ctx* ctx, const std::vector<char>& cubin, const char* entry, JitKernel* out);
+void jit_unload(JitKernel* k);
 
 inline int etp_fail(etp_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];

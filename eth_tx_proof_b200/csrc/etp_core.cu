@@ -47,6 +47,7 @@ extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  free_registered_tables(ctx);
   for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
   for (auto& kv : ctx->full_tables) cudaFree(kv.second);
   cudaFree(ctx->d_pow_result);

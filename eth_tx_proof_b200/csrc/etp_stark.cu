@@ -5,6 +5,7 @@
 // See include/etp_b200.h for the upstream item behind each entry point and DESIGN.md for the proof
 // wire format.  Product code: no oracle, no CPU fallback; the only host arithmetic is the transcript
 // (Challenger) and the <= 2^8-coefficient FRI final polynomial.
+#include "cprog.h"
 #include "ctx.cuh"
 #include "host_field.h"
 #include "stark_kernels.cuh"
@@ -16,13 +17,48 @@ constexpr int NUM_CHALLENGES = 2, RATE_BITS = 1, CAP_HEIGHT = 4, POW_BITS = 16, 
               NUM_QUERIES = 84;
 constexpr uint64_t PROOF_MAGIC = 0x4232303053544B31ULL;  // "B200STK1"
 
-struct TableInfo {
-  int cols, degree, n_pi;
-  bool lookup;
+// starky::lookup::Lookup without filters: `looking` columns are looked up in `table_col` with multiplicities
+// `freq_col`.  Helper columns: one per chunk of (constraint_degree - 1) looking columns, then Z.
+struct LookupInfo {
+  std::vector<int> looking;
+  int table_col = 0, freq_col = 0;
 };
-bool table_info(int t, TableInfo* o) {
-  if (t == ETP_TABLE_FIBONACCI) { *o = {2, 2, 3, false}; return true; }
-  if (t == ETP_TABLE_MEMORY) { *o = {21, 3, 0, true}; return true; }
+struct TableInfo {
+  int cols = 0, degree = 0, n_pi = 0;
+  std::vector<LookupInfo> lookups;
+  RegisteredTable* reg = nullptr;  // program-defined table
+  int chunk() const { return degree - 1 < 1 ? 1 : degree - 1; }
+  int helpers(const LookupInfo& l) const { return ((int)l.looking.size() + chunk() - 1) / chunk(); }
+  int aux_per_challenge() const { int a = 0; for (auto& l : lookups) a += helpers(l) + 1; return a; }
+  int n_aux(int n_ch) const { return aux_per_challenge() * n_ch; }
+  bool lookup() const { return !lookups.empty(); }
+};
+}  // namespace
+
+// a table registered at run time: its description + constraint program + the kernel compiled from it
+struct RegisteredTable {
+  TableInfo info;
+  cprog::Program prog;
+  JitKernel kernel;
+};
+void free_registered_tables(etp_ctx* ctx) {
+  for (auto* t : ctx->tables) { jit_unload(&t->kernel); delete t; }
+  ctx->tables.clear();
+}
+
+namespace {
+bool table_info(const etp_ctx* ctx, int t, TableInfo* o) {
+  if (t == ETP_TABLE_FIBONACCI) { *o = TableInfo(); o->cols = 2; o->degree = 2; o->n_pi = 3; return true; }
+  if (t == ETP_TABLE_MEMORY) {
+    *o = TableInfo(); o->cols = 21; o->degree = 3; o->n_pi = 0;
+    LookupInfo l; l.looking = {stark::M_RANGE_CHECK}; l.table_col = stark::M_COUNTER; l.freq_col = stark::M_FREQ;
+    o->lookups.push_back(l);
+    return true;
+  }
+  if (ctx && t >= ETP_TABLE_FIRST_REGISTERED && (size_t)(t - ETP_TABLE_FIRST_REGISTERED) < ctx->tables.size()) {
+    *o = ctx->tables[t - ETP_TABLE_FIRST_REGISTERED]->info;
+    return true;
+  }
   return false;
 }
 int quotient_factor(const TableInfo& ti) { return ti.degree - 1 < 1 ? 1 : ti.degree - 1; }
@@ -82,22 +118,35 @@ int exclusive_scan_dev(etp_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n
 int lookup_helper_columns(etp_ctx* ctx, int table, int log_n, const uint64_t* trace, size_t stride, const uint64_t* ch, int n_ch,
                           uint64_t* aux) {
   TableInfo ti;
-  if (!table_info(table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
-  if (!ti.lookup) return ETP_OK;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (!ti.lookup()) return ETP_OK;
   const size_t n = (size_t)1 << log_n;
+  size_t max_m = 0;
+  for (auto& l : ti.lookups) max_m = l.looking.size() > max_m ? l.looking.size() : max_m;
   DevBuf<uint64_t> den(ctx), term(ctx);
-  ETP_TRY(den.alloc(2 * n));
+  DevBuf<int> d_cols(ctx);
+  ETP_TRY(den.alloc((max_m + 1) * n));
   ETP_TRY(term.alloc(n));
-  for (int k = 0; k < n_ch; k++) {
-    uint64_t* h = aux + (size_t)(2 * k) * n;
-    uint64_t* z = aux + (size_t)(2 * k + 1) * n;
-    stark::lookup_denominators<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(trace + stark::M_RANGE_CHECK * stride,
-                                                                            trace + stark::M_COUNTER * stride, gl::canon(ch[k]), n, den.p);
-    ETP_LAUNCH_CHECK(ctx);
-    ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, 2 * n));
-    stark::lookup_terms<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(den.p, trace + stark::M_FREQ * stride, n, h, term.p);
-    ETP_LAUNCH_CHECK(ctx);
-    ETP_TRY(exclusive_scan_dev(ctx, term.p, z, n));
+  ETP_TRY(d_cols.alloc(max_m + 1));
+  // auxiliary column order (starky prover.rs): for each lookup, for each challenge: helpers..., Z
+  uint64_t* out = aux;
+  for (auto& l : ti.lookups) {
+    const int m = (int)l.looking.size(), nh = ti.helpers(l);
+    std::vector<int> cols(l.looking);
+    cols.push_back(l.table_col);
+    ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `cols` dies at the end of this iteration
+    for (int k = 0; k < n_ch; k++) {
+      stark::lookup_denominators<<<blocks_for((size_t)(m + 1) * n, 256), 256, 0, ctx->stream>>>(trace, stride, d_cols.p, m + 1,
+                                                                                                gl::canon(ch[k]), n, den.p);
+      ETP_LAUNCH_CHECK(ctx);
+      ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, (size_t)(m + 1) * n));
+      stark::lookup_terms<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(den.p, m, ti.chunk(), trace + (size_t)l.freq_col * stride, n, out,
+                                                                      term.p);
+      ETP_LAUNCH_CHECK(ctx);
+      ETP_TRY(exclusive_scan_dev(ctx, term.p, out + (size_t)nh * n, n));
+      out += (size_t)(nh + 1) * n;
+    }
   }
   return ETP_OK;
 }
@@ -152,12 +201,15 @@ int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, c
 int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* lookup_ch, int n_lookup_ch,
                      const uint64_t* pi, const uint64_t* alphas, int n_alphas, uint64_t* out_dev) {
   TableInfo ti;
-  if (!table_info(table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
   if (!trace || (int)trace->n_cols != ti.cols) return etp_fail(ctx, ETP_ERR_INVALID, "trace batch has the wrong number of columns");
   if (n_alphas < 1 || n_alphas > stark::MAX_CHALLENGES) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported number of challenges");
-  const int n_aux = ti.lookup ? 2 * n_lookup_ch : 0;
-  if (ti.lookup && (!aux || (int)aux->n_cols != n_aux || n_lookup_ch > stark::MAX_CHALLENGES))
+  const int n_aux = ti.n_aux(n_lookup_ch);
+  if (ti.lookup() && (!aux || (int)aux->n_cols != n_aux || n_lookup_ch > stark::MAX_CHALLENGES))
     return etp_fail(ctx, ETP_ERR_INVALID, "auxiliary batch does not match the table's lookups");
+  if (ti.reg && ((int)ti.reg->prog.n_aux != n_aux || (int)ti.reg->prog.n_ch > n_lookup_ch))
+    return etp_fail(ctx, ETP_ERR_INVALID, "constraint program expects %u auxiliary columns / %u challenges, got %d / %d",
+                    ti.reg->prog.n_aux, ti.reg->prog.n_ch, n_aux, n_lookup_ch);
   const int log_n = trace->log_n, rate_bits = trace->rate_bits;
   const int factor = quotient_factor(ti), qbits = log2_ceil(factor);
   if (qbits > rate_bits)
@@ -188,7 +240,7 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
   q.n_alphas = n_alphas;
   for (int j = 0; j < n_lookup_ch; j++) q.lookup_ch[j] = gl::canon(lookup_ch[j]);
   q.n_lookup_ch = n_lookup_ch;
-  for (int j = 0; j < ti.n_pi && j < 4; j++) q.pi[j] = gl::canon(pi[j]);
+  for (int j = 0; j < ti.n_pi && j < stark::MAX_PUBLIC_INPUTS; j++) q.pi[j] = gl::canon(pi[j]);
   // Lagrange selectors at every point of the quotient coset
   DevBuf<uint64_t> lag(ctx), qvals(ctx), scratch(ctx);
   ETP_TRY(lag.alloc(2 * size));
@@ -202,8 +254,15 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
   q.lag_first = lag.p; q.lag_last = lag.p + size;
   ETP_TRY(qvals.alloc((size_t)n_alphas * size));
   q.out = qvals.p;
-  if (table == ETP_TABLE_FIBONACCI) stark::quotient_kernel<0><<<gb, 128, 0, ctx->stream>>>(q);
-  else stark::quotient_kernel<1><<<gb, 128, 0, ctx->stream>>>(q);
+  if (ti.reg) {
+    void* args[] = {(void*)&q};
+    ETP_CUDA(ctx, cudaLaunchKernel((const void*)ti.reg->kernel.kernel, dim3(gb), dim3(128), args, 0, ctx->stream));
+    ctx->launches++;
+  } else if (table == ETP_TABLE_FIBONACCI) {
+    stark::quotient_kernel<0><<<gb, 128, 0, ctx->stream>>>(q);
+  } else {
+    stark::quotient_kernel<1><<<gb, 128, 0, ctx->stream>>>(q);
+  }
   ETP_LAUNCH_CHECK(ctx);
   // coset_ifft(7) of each challenge's values, then split into `factor` chunks of n coefficients.
   // size == factor * n whenever factor is a power of two; otherwise the tail must vanish (trim_to_len).
@@ -243,7 +302,7 @@ int pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, int bits, uint64_
 }
 
 size_t proof_words(const TableInfo& ti, int log_n) {
-  const int n_aux = ti.lookup ? 2 * NUM_CHALLENGES : 0, n_quot = quotient_factor(ti) * NUM_CHALLENGES;
+  const int n_aux = ti.n_aux(NUM_CHALLENGES), n_quot = quotient_factor(ti) * NUM_CHALLENGES;
   const int n_layers = fri_num_layers(log_n), log_lde = log_n + RATE_BITS;
   const size_t cap = (size_t)4 << CAP_HEIGHT;
   size_t w = 16 + cap * (2 + (n_aux ? 1 : 0)) + 2 * (size_t)(2 * ti.cols + 2 * n_aux + n_quot) + cap * n_layers;
@@ -266,7 +325,7 @@ struct FriLayer {
 
 int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t stride, const uint64_t* pi_in, uint64_t* proof) {
   TableInfo ti;
-  if (!table_info(table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
   if (log_n < 1 || log_n + RATE_BITS > 30) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported degree_bits %d", log_n);
   const int n_layers = fri_num_layers(log_n);
   if (ARITY_BITS * n_layers > log_n + RATE_BITS - CAP_HEIGHT || log_n + RATE_BITS < CAP_HEIGHT)
@@ -274,8 +333,8 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
   const size_t n = (size_t)1 << log_n;
   const int log_lde = log_n + RATE_BITS;
   const size_t lde_n = (size_t)1 << log_lde, cap_words = (size_t)4 << CAP_HEIGHT;
-  const int n_aux = ti.lookup ? 2 * NUM_CHALLENGES : 0, factor = quotient_factor(ti), n_quot = factor * NUM_CHALLENGES;
-  uint64_t pi[4] = {0, 0, 0, 0};
+  const int n_aux = ti.n_aux(NUM_CHALLENGES), factor = quotient_factor(ti), n_quot = factor * NUM_CHALLENGES;
+  uint64_t pi[stark::MAX_PUBLIC_INPUTS] = {};
   for (int i = 0; i < ti.n_pi; i++) pi[i] = gl::canon(pi_in[i]);
   PhaseTimer timer(ctx);
 
@@ -301,7 +360,7 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
 
   // ---- prove_with_commitment: lookup helper columns + auxiliary commitment
   uint64_t lookup_ch[NUM_CHALLENGES] = {0, 0};
-  if (ti.lookup) {
+  if (ti.lookup()) {
     // get_grand_product_challenge_set: (beta, gamma) per challenge, the lookup argument uses beta
     for (int k = 0; k < NUM_CHALLENGES; k++) { lookup_ch[k] = ch.get(); (void)ch.get(); }
     DevBuf<uint64_t> aux_vals(ctx);
@@ -319,7 +378,7 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
 
   // ---- quotient
   ETP_TRY(batch_create(ctx, n_quot, log_n, RATE_BITS, 0, CAP_HEIGHT, &B.quot));
-  ETP_TRY(compute_quotient(ctx, table, B.trace, B.aux, lookup_ch, ti.lookup ? NUM_CHALLENGES : 0, pi, alphas, NUM_CHALLENGES, B.quot->coeffs));
+  ETP_TRY(compute_quotient(ctx, table, B.trace, B.aux, lookup_ch, ti.lookup() ? NUM_CHALLENGES : 0, pi, alphas, NUM_CHALLENGES, B.quot->coeffs));
   timer.mark("compute quotient polys");
   ETP_TRY(batch_commit_from_coeffs(B.quot));
   timer.mark("quotient polys commit");
@@ -563,11 +622,57 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
 // =================================================================================================
 // C ABI
 // =================================================================================================
-extern "C" int etp_table_num_columns(int t) { TableInfo ti; return table_info(t, &ti) ? ti.cols : -1; }
-extern "C" int etp_table_constraint_degree(int t) { TableInfo ti; return table_info(t, &ti) ? ti.degree : -1; }
-extern "C" int etp_table_num_public_inputs(int t) { TableInfo ti; return table_info(t, &ti) ? ti.n_pi : -1; }
-extern "C" int etp_table_num_aux_columns(int t, int nc) { TableInfo ti; return table_info(t, &ti) ? (ti.lookup ? 2 * nc : 0) : -1; }
-extern "C" int etp_table_quotient_degree_factor(int t) { TableInfo ti; return table_info(t, &ti) ? quotient_factor(ti) : -1; }
+extern "C" int etp_table_num_columns(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.cols : -1; }
+extern "C" int etp_table_constraint_degree(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.degree : -1; }
+extern "C" int etp_table_num_public_inputs(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_pi : -1; }
+extern "C" int etp_table_num_aux_columns(const etp_ctx* c, int t, int nc) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_aux(nc) : -1; }
+extern "C" int etp_table_quotient_degree_factor(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? quotient_factor(ti) : -1; }
+
+extern "C" int etp_table_register(etp_ctx* ctx, const uint64_t* program, size_t n_words, const int32_t* lookups, size_t n_lookup_words,
+                                  int* table_id_out) {
+  if (!ctx || !program || !table_id_out || (!lookups && n_lookup_words)) return ETP_ERR_INVALID;
+  auto t = new RegisteredTable();
+  struct Guard { RegisteredTable* t; ~Guard() { if (t) { jit_unload(&t->kernel); delete t; } } } guard{t};
+  const std::string why = cprog::parse(program, n_words, stark::MAX_PUBLIC_INPUTS, stark::MAX_CHALLENGES, &t->prog);
+  if (!why.empty()) return etp_fail(ctx, ETP_ERR_INVALID, "%s", why.c_str());
+  TableInfo& ti = t->info;
+  ti.cols = (int)t->prog.n_trace; ti.degree = (int)t->prog.degree; ti.n_pi = (int)t->prog.n_pi; ti.reg = t;
+  // lookups: [n_lookups, then per lookup: table_col, freq_col, n_looking, looking columns...]
+  if (n_lookup_words) {
+    size_t pos = 0;
+    const int nl = lookups[pos++];
+    if (nl < 0 || nl > 64) return etp_fail(ctx, ETP_ERR_INVALID, "table: bad number of lookups");
+    for (int i = 0; i < nl; i++) {
+      if (pos + 3 > n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: truncated lookup description");
+      LookupInfo l;
+      l.table_col = lookups[pos++]; l.freq_col = lookups[pos++];
+      const int m = lookups[pos++];
+      if (m < 1 || m > 4096 || pos + m > n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: bad looking-column count");
+      for (int j = 0; j < m; j++) l.looking.push_back(lookups[pos++]);
+      for (int c : l.looking)
+        if (c < 0 || c >= ti.cols) return etp_fail(ctx, ETP_ERR_INVALID, "table: lookup column out of range");
+      if (l.table_col < 0 || l.table_col >= ti.cols || l.freq_col < 0 || l.freq_col >= ti.cols)
+        return etp_fail(ctx, ETP_ERR_INVALID, "table: lookup column out of range");
+      ti.lookups.push_back(l);
+    }
+    if (pos != n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: trailing words in the lookup description");
+  }
+  if ((int)t->prog.n_aux != ti.n_aux(NUM_CHALLENGES))
+    return etp_fail(ctx, ETP_ERR_INVALID, "table: the program reads %u auxiliary columns but the lookups produce %d", t->prog.n_aux,
+                    ti.n_aux(NUM_CHALLENGES));
+  if (log2_ceil(quotient_factor(ti)) > RATE_BITS)
+    return etp_fail(ctx, ETP_ERR_INVALID, "Having constraints of degree higher than the rate is not supported yet.");
+  // same program registered before on this context: share the compiled kernel's source hash -> recompile is cheap
+  // enough to skip a cache; compile now so that errors surface at registration, not in the middle of a proof
+  std::vector<char> cubin;
+  std::string log;
+  ETP_TRY(jit_compile(ctx, cprog::generate_cuda(t->prog), &cubin, &log));
+  ETP_TRY(jit_load(ctx, cubin, "etp_cprog_quotient", &t->kernel));
+  ctx->tables.push_back(t);
+  guard.t = nullptr;
+  *table_id_out = ETP_TABLE_FIRST_REGISTERED + (int)ctx->tables.size() - 1;
+  return ETP_OK;
+}
 
 extern "C" int etp_lookup_helper_columns_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
                                              const uint64_t* challenges, int n_challenges, uint64_t* aux_dev) {
@@ -582,7 +687,7 @@ extern "C" int etp_compute_quotient_polys_dev(etp_ctx* ctx, int table, etp_batch
                                               int n_lookup_challenges, const uint64_t* public_inputs, const uint64_t* alphas, int n_alphas,
                                               uint64_t* out_dev) {
   if (!ctx || !trace || !alphas || !out_dev) return ETP_ERR_INVALID;
-  uint64_t zero[4] = {0, 0, 0, 0};
+  uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
   ETP_TRY(compute_quotient(ctx, table, trace, aux, lookup_challenges ? lookup_challenges : zero, n_lookup_challenges,
                            public_inputs ? public_inputs : zero, alphas, n_alphas, out_dev));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -594,16 +699,16 @@ extern "C" int etp_pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, in
   return pow_grind(ctx, state, pos, bits, witness_out);
 }
 
-extern "C" size_t etp_stark_proof_words(int table, int log_n) {
+extern "C" size_t etp_stark_proof_words(const etp_ctx* ctx, int table, int log_n) {
   TableInfo ti;
-  if (!table_info(table, &ti) || log_n < 1 || log_n > 29) return 0;
+  if (!table_info(ctx, table, &ti) || log_n < 1 || log_n > 29) return 0;
   return proof_words(ti, log_n);
 }
 
 extern "C" int etp_stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
                                    const uint64_t* public_inputs, uint64_t* proof_out) {
   if (!ctx || !trace_dev || !proof_out) return ETP_ERR_INVALID;
-  uint64_t zero[4] = {0, 0, 0, 0};
+  uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
   return stark_prove_dev(ctx, table, log_n, trace_dev, col_stride, public_inputs ? public_inputs : zero, proof_out);
 }
 
@@ -611,13 +716,13 @@ extern "C" int etp_stark_prove_host(etp_ctx* ctx, int table, int log_n, const ui
                                     uint64_t* proof_out) {
   if (!ctx || !trace || !proof_out) return ETP_ERR_INVALID;
   TableInfo ti;
-  if (!table_info(table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
   if (log_n < 1 || log_n > 29) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported degree_bits %d", log_n);
   const size_t n = (size_t)1 << log_n;
   DevBuf<uint64_t> d(ctx);
   ETP_TRY(d.alloc((size_t)ti.cols * n));
   ETP_CUDA(ctx, cudaMemcpyAsync(d.p, trace, (size_t)ti.cols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  uint64_t zero[4] = {0, 0, 0, 0};
+  uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
   return stark_prove_dev(ctx, table, log_n, d.p, n, public_inputs ? public_inputs : zero, proof_out);
 }
 

@@ -12,7 +12,14 @@
 // FMA pipe; the reduction uses 2^64 == 2^32 - 1 and 2^96 == -1 (mod p) with carry-chain adds on the
 // ALU pipe. Tensor cores are deliberately unused.
 #pragma once
+#if defined(__CUDACC_RTC__)  // NVRTC (constraint programs compiled at table registration): no host headers
+typedef unsigned long long uint64_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long size_t;
+#else
 #include <cstdint>
+#endif
 
 #if defined(__CUDACC__)
 #define GL_HD __host__ __device__ __forceinline__
@@ -126,7 +133,13 @@ GL_D uint64_t reduce_prod(uint64_t lo, uint64_t hi) {
   asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(k), "r"(MINUS_ONE), "l"(t));
   return r;
 }
+// ETP_COMPACT_CODE (large NVRTC-compiled constraint programs): one out-of-line copy instead of thousands of
+// inlined ones — the straight-line kernel would otherwise be megabytes of code and minutes of ptxas time.
+#if defined(ETP_COMPACT_CODE)
+static __device__ __noinline__ uint64_t mul(uint64_t a, uint64_t b) {
+#else
 GL_D uint64_t mul(uint64_t a, uint64_t b) {
+#endif
   const unsigned __int128 p = (unsigned __int128)a * b;
   return reduce_prod((uint64_t)p, (uint64_t)(p >> 64));
 }

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include "gl.cuh"
+#include "powtable.cuh"
 
 namespace ntt {
 
@@ -39,17 +40,6 @@ static __device__ __constant__ const uint64_t W16[8] = {0x0000000000000001ULL, 0
                                                  0x0001000000000000ULL, 0x0000000000001000ULL, 0xfffffeff00000101ULL, 0xffffffef00000001ULL};
 static __device__ __constant__ const uint64_t W16I[8] = {0x0000000000000001ULL, 0x0000001000000000ULL, 0x000000ffffffff00ULL, 0xfffffffefffff001ULL,
                                                   0xfffeffff00000001ULL, 0xffefffff00100001ULL, 0x0000000001000000ULL, 0x1000000000000000ULL};
-
-// base^e for e < 2^bits via two tables: hi[e >> lo_bits] * lo[e & mask].  `hi` may carry a scale.
-struct PowTable {
-  const uint64_t* lo;
-  const uint64_t* hi;
-  int lo_bits;
-  uint32_t mask;
-  __device__ __forceinline__ uint64_t get(uint32_t e) const {
-    return gl::mul(__ldg(hi + (e >> lo_bits)), __ldg(lo + (e & mask)));
-  }
-};
 
 struct PassParams {
   const uint64_t* in;   // column 0

@@ -18,28 +18,13 @@
 #include "gl.cuh"
 #include "ntt.cuh"
 #include "poseidon.cuh"
+#include "quotient_rt.cuh"
 
 namespace stark {
 
-constexpr int MAX_CHALLENGES = 2;
 constexpr uint64_t MEM_TRIE_DATA_SEGMENT = 13;
 enum { M_FILTER = 0, M_TIMESTAMP, M_IS_READ, M_CTX, M_SEG, M_VIRT, M_VALUE0, M_CFC = 14, M_SFC, M_VFC, M_INIT_AUX,
        M_RANGE_CHECK, M_COUNTER, M_FREQ };
-
-// ---- ConstraintConsumer ------------------------------------------------------------------------
-struct Consumer {
-  uint64_t alphas[MAX_CHALLENGES], acc[MAX_CHALLENGES];
-  uint64_t z_last, lagrange_first, lagrange_last;
-  int n;
-  __device__ __forceinline__ void constraint(uint64_t c) {
-#pragma unroll
-    for (int j = 0; j < MAX_CHALLENGES; j++)
-      if (j < n) acc[j] = gl::add(gl::mul(acc[j], alphas[j]), c);
-  }
-  __device__ __forceinline__ void transition(uint64_t c) { constraint(gl::mul(c, z_last)); }
-  __device__ __forceinline__ void first_row(uint64_t c) { constraint(gl::mul(c, lagrange_first)); }
-  __device__ __forceinline__ void last_row(uint64_t c) { constraint(gl::mul(c, lagrange_last)); }
-};
 
 template <int TABLE>
 struct Table;
@@ -118,68 +103,30 @@ struct Table<1> {
   }
 };
 
-struct QuotientParams {
-  const uint64_t* trace;  // LDE, bit-reversed rows
-  size_t trace_stride;
-  const uint64_t* aux;
-  size_t aux_stride;
-  int log_lde;      // degree_bits + rate_bits
-  int log_size;     // degree_bits + quotient_degree_bits
-  int step_log;     // rate_bits - quotient_degree_bits
-  int next_step;    // 1 << quotient_degree_bits
-  ntt::PowTable coset;  // 7 * w_size^i
-  const uint64_t* lag_first;  // per position p < size: L_first, L_last at the point of position p
-  const uint64_t* lag_last;
-  uint64_t zh_inv[4];    // 1/Z_H per (i mod 2^qbits)
-  uint64_t last;         // g^-1
-  uint64_t alphas[MAX_CHALLENGES];
-  int n_alphas;
-  uint64_t lookup_ch[MAX_CHALLENGES];
-  int n_lookup_ch;
-  uint64_t pi[4];
-  uint64_t* out;  // n_alphas columns x size, NATURAL order (input of coset_ifft)
-};
-
 // One thread per position p of the quotient coset inside the LDE (p < size): local row = LDE row p,
 // next row = the row of point index k + next_step*step.
 template <int TABLE>
-static __global__ void __launch_bounds__(128) quotient_kernel(QuotientParams q) {
+static __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotientParams q) {
   using T = Table<TABLE>;
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t size = 1u << q.log_size;
-  if (p >= size) return;
-  const uint32_t k = gl::bitrev32(p, q.log_lde);                 // LDE point index, multiple of step
-  const uint32_t i = k >> q.step_log;                              // index on the quotient coset
-  const uint32_t i_next = (i + q.next_step) & (size - 1);
-  const uint32_t p_next = gl::bitrev32(i_next << q.step_log, q.log_lde);
+  RowCtx r;
+  if (!quotient_begin(q, r)) return;
   uint64_t lv[T::COLS], nv[T::COLS];
 #pragma unroll
   for (int c = 0; c < T::COLS; c++) {
-    lv[c] = __ldg(q.trace + (size_t)c * q.trace_stride + p);
-    nv[c] = __ldg(q.trace + (size_t)c * q.trace_stride + p_next);
+    lv[c] = r.lv(q, c);
+    nv[c] = r.nv(q, c);
   }
-  Consumer cs;
-  cs.n = q.n_alphas;
-#pragma unroll
-  for (int j = 0; j < MAX_CHALLENGES; j++) { cs.alphas[j] = q.alphas[j]; cs.acc[j] = 0; }
-  const uint64_t x = q.coset.get(i);
-  cs.z_last = gl::sub(x, q.last);
-  cs.lagrange_first = q.lag_first[p];
-  cs.lagrange_last = q.lag_last[p];
-  T::eval(lv, nv, q.pi, cs);
+  T::eval(lv, nv, q.pi, r.cs);
   if (T::AUX > 0) {
     uint64_t al[T::AUX > 0 ? T::AUX : 1], an[T::AUX > 0 ? T::AUX : 1];
 #pragma unroll
     for (int c = 0; c < T::AUX; c++) {
-      al[c] = __ldg(q.aux + (size_t)c * q.aux_stride + p);
-      an[c] = __ldg(q.aux + (size_t)c * q.aux_stride + p_next);
+      al[c] = r.la(q, c);
+      an[c] = r.na(q, c);
     }
-    T::eval_lookups(lv, al, an, q.lookup_ch, q.n_lookup_ch, cs);
+    T::eval_lookups(lv, al, an, q.lookup_ch, q.n_lookup_ch, r.cs);
   }
-  const uint64_t dinv = q.zh_inv[i & (q.next_step - 1)];
-#pragma unroll
-  for (int j = 0; j < MAX_CHALLENGES; j++)
-    if (j < q.n_alphas) q.out[(size_t)j * size + i] = gl::mul(cs.acc[j], dinv);
+  quotient_end(q, r);
 }
 
 // ---- Lagrange selectors on the coset: L_first(x) = Z_H(x) / (n (x - 1)), L_last(x) = Z_H(x) / (n (g x - 1)) ----
@@ -231,22 +178,30 @@ static __global__ void batch_inverse(const uint64_t* in, uint64_t* out, size_t n
 }
 
 // ---- lookup helper columns -----------------------------------------------------------------------
-// den[0][i] = looking[i] + ch, den[1][i] = table[i] + ch
-static __global__ void lookup_denominators(const uint64_t* __restrict__ looking, const uint64_t* __restrict__ table, uint64_t ch,
-                                           size_t n, uint64_t* __restrict__ den) {
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  den[i] = gl::add(looking[i], ch);
-  den[n + i] = gl::add(table[i], ch);
+// den[j][i] = trace[cols[j]][i] + ch for the m looking columns of a lookup followed by its table column (j = m)
+static __global__ void lookup_denominators(const uint64_t* __restrict__ trace, size_t stride, const int* __restrict__ cols, int n_cols,
+                                           uint64_t ch, size_t n, uint64_t* __restrict__ den) {
+  const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n * n_cols) return;
+  const size_t j = t / n, i = t % n;
+  den[t] = gl::add(trace[(size_t)cols[j] * stride + i], ch);
 }
-// term[i] = h[i] - freq[i] * tinv[i]
-static __global__ void lookup_terms(const uint64_t* __restrict__ inv /* 2 x n */, const uint64_t* __restrict__ freq, size_t n,
-                                    uint64_t* __restrict__ h_out, uint64_t* __restrict__ term) {
+// inv: (m + 1) x n inverted denominators.  helper c = sum of the inverses of chunk c (`chunk` looking columns
+// each); term[i] = sum_c helper_c[i] - freq[i] * inv[m][i]  (the increment of Z)
+static __global__ void lookup_terms(const uint64_t* __restrict__ inv, int m, int chunk, const uint64_t* __restrict__ freq, size_t n,
+                                    uint64_t* __restrict__ h_out /* ceil(m / chunk) columns, stride n */, uint64_t* __restrict__ term) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t h = inv[i];
-  h_out[i] = h;
-  term[i] = gl::canon(gl::sub(h, gl::mul(freq[i], inv[n + i])));
+  uint64_t total = 0;
+  int c = 0;
+  for (int j0 = 0; j0 < m; j0 += chunk, c++) {
+    uint64_t h = 0;
+    for (int j = j0; j < j0 + chunk && j < m; j++) h = gl::add(h, inv[(size_t)j * n + i]);
+    h = gl::canon(h);
+    h_out[(size_t)c * n + i] = h;
+    total = gl::add(total, h);
+  }
+  term[i] = gl::canon(gl::sub(total, gl::mul(freq[i], inv[(size_t)m * n + i])));
 }
 // exclusive prefix sum over the field, 3 phases; SCAN_BLOCK elements per block
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_PER_THREAD;

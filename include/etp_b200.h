@@ -172,11 +172,28 @@ int etp_shard_download_coeffs(etp_shard *s, uint64_t *out);
 /* ---- starky: tables, compute_quotient_polys, prove ------------------------------------------- */
 #define ETP_TABLE_FIBONACCI 0 /* starky/src/fibonacci_stark.rs                                        */
 #define ETP_TABLE_MEMORY 1    /* evm_arithmetization/src/memory/memory_stark.rs (shape) */
-int etp_table_num_columns(int table);
-int etp_table_constraint_degree(int table);
-int etp_table_num_public_inputs(int table);
-int etp_table_num_aux_columns(int table, int num_challenges);
-int etp_table_quotient_degree_factor(int table);
+#define ETP_TABLE_FIRST_REGISTERED 16
+/* ctx may be NULL for the built-in tables; registered tables belong to the context that registered them */
+int etp_table_num_columns(const etp_ctx *ctx, int table);
+int etp_table_constraint_degree(const etp_ctx *ctx, int table);
+int etp_table_num_public_inputs(const etp_ctx *ctx, int table);
+int etp_table_num_aux_columns(const etp_ctx *ctx, int table, int num_challenges);
+int etp_table_quotient_degree_factor(const etp_ctx *ctx, int table);
+
+/* Registers ANY starky table (the arithmetic, byte-packing, CPU, keccak, keccak-sponge, logic, memory STARKs of
+ * evm_arithmetization, or a user's) from its constraint program: the table's `Stark::eval_packed_generic`
+ * followed by `eval_packed_lookups_generic`, recorded once as straight-line code (format: csrc/cprog.h; the
+ * patched starky records it with a symbolic PackedField, rust/etp_b200_sys).  The program is compiled for
+ * sm_100a with NVRTC here, against the same field arithmetic as the built-in kernels, and the returned id
+ * (>= ETP_TABLE_FIRST_REGISTERED, valid on this context) is accepted wherever a table id is.
+ * lookups: starky::lookup::Lookup list without filters, flat int32:
+ *   [n_lookups, then per lookup: table_column, frequencies_column, n_looking, looking columns...];
+ * auxiliary columns are laid out as starky does: per lookup, per challenge: one helper column per chunk of
+ * (constraint_degree - 1) looking columns, then Z. */
+int etp_table_register(etp_ctx *ctx, const uint64_t *program, size_t n_words, const int32_t *lookups, size_t n_lookup_words,
+                       int *table_id_out);
+/* parse + NVRTC-compile a program without a device (CI / the Rust build): cubin size, or an error message */
+int etp_cprog_compile_check(const uint64_t *program, size_t n_words, size_t *cubin_bytes_out, char *err, size_t err_len);
 
 /* starky::lookup::lookup_helper_columns for every lookup of the table and every challenge:
  * aux_dev gets etp_table_num_aux_columns columns of 2^log_n (column-major, stride 2^log_n). */
@@ -198,7 +215,7 @@ int etp_pow_grind(etp_ctx *ctx, const uint64_t state[12], int pos, int bits, uin
  * quotient, openings, FRI (commit phase, PoW, 84 query rounds).  proof_out: etp_stark_proof_words()
  * u64 in the flat wire format of DESIGN.md.  The trace (n_cols x 2^log_n column-major) is a host or a
  * device matrix. */
-size_t etp_stark_proof_words(int table, int log_n);
+size_t etp_stark_proof_words(const etp_ctx *ctx, int table, int log_n);
 int etp_stark_prove_host(etp_ctx *ctx, int table, int log_n, const uint64_t *trace, const uint64_t *public_inputs,
                          uint64_t *proof_out);
 int etp_stark_prove_dev(etp_ctx *ctx, int table, int log_n, const uint64_t *trace_dev, size_t col_stride,

@@ -98,6 +98,8 @@ def lib():
               L.orc_table_uses_lookup):
         f.argtypes = [C.c_int]
         f.restype = C.c_int
+    L.orc_table_register.argtypes = [_u64p, sz, C.POINTER(C.c_int32), sz]
+    L.orc_table_register.restype = C.c_int
     L.orc_table_num_aux_columns.argtypes = [C.c_int, C.c_int]
     L.orc_table_num_aux_columns.restype = C.c_int
     L.orc_table_check_constraints.argtypes = [C.c_int, C.c_int, _u64p, _u64p]
@@ -260,6 +262,20 @@ class Batch:
         if getattr(self, "_h", None) is not None and _lib is not None:
             _lib.orc_batch_free(self._h)
             self._h = None
+
+
+def register_table(program, lookups=()) -> int:
+    """Program-defined table (words of eth_tx_proof_b200.cprog.Program or a u64 array; lookups as
+    [(looking_columns, table_column, frequencies_column)]): interpreted by the oracle.  Returns its table id."""
+    words = _u64(getattr(program, "words", program))
+    flat = [len(lookups)]
+    for looking, table_col, freq_col in lookups:
+        flat += [int(table_col), int(freq_col), len(looking)] + [int(c) for c in looking]
+    arr = (C.c_int32 * len(flat))(*flat)
+    tid = lib().orc_table_register(_ptr(words), words.size, arr, len(flat) if lookups else 0)
+    if tid < 0:
+        raise RuntimeError("oracle: table registration failed")
+    return tid
 
 
 def check_constraints(table, trace, public_inputs=()) -> int:

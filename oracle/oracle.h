@@ -85,6 +85,9 @@ const uint64_t *orc_batch_cap(const orc_batch *b);
 /* ---- stark.c : tables, quotient, FRI, full single-table proof ---- */
 #define ORC_TABLE_FIBONACCI 0
 #define ORC_TABLE_MEMORY 1
+/* program-defined table (constraint program + lookups, formats of the product's csrc/cprog.h / etp_table_register,
+ * restated): interpreted op by op here.  Returns the table id (>= 16) or -1. */
+int orc_table_register(const uint64_t *program, size_t n_words, const int32_t *lookups, size_t n_lookup_words);
 int orc_table_num_columns(int table);
 int orc_table_constraint_degree(int table);
 int orc_table_num_public_inputs(int table);

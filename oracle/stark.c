@@ -52,18 +52,78 @@ static int fri_num_layers(int degree_bits) {
 }
 
 /* ---------------- tables ---------------- */
-int orc_table_num_columns(int t) { return t == ORC_TABLE_FIBONACCI ? 2 : 21; }
-int orc_table_constraint_degree(int t) { return t == ORC_TABLE_FIBONACCI ? 2 : 3; }
-int orc_table_num_public_inputs(int t) { return t == ORC_TABLE_FIBONACCI ? 3 : 0; }
-int orc_table_uses_lookup(int t) { return t == ORC_TABLE_MEMORY; }
+/* Program-defined tables (constraint programs, format of eth_tx_proof_b200/csrc/cprog.h restated here):
+ * the oracle INTERPRETS the program op by op; the product compiles it with NVRTC.  ids >= 16. */
+#define ORC_MAX_TABLES 64
+#define ORC_MAX_LOOKUPS 64
+#define CPROG_MAGIC 0x3147525043505445ULL
+enum { OP_CONST = 0, OP_LV, OP_NV, OP_LA, OP_NA, OP_PI, OP_CH, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_EMIT_TRANSITION, OP_EMIT_FIRST,
+       OP_EMIT_LAST };
+typedef struct {
+  int n_looking, *looking, table_col, freq_col;
+} lookup_t;
+typedef struct {
+  int used, cols, degree, n_pi, n_lookups;
+  lookup_t lookups[ORC_MAX_LOOKUPS];
+  uint32_t n_ops, n_aux, n_ch;
+  uint64_t *ops; /* 2 words per op; NULL for the built-in tables */
+} table_t;
+static table_t g_tables[ORC_MAX_TABLES];
+static int g_mem_looking[1] = {18};
+static const table_t *get_table(int t) {
+  if (!g_tables[ORC_TABLE_MEMORY].used) {
+    table_t *f = &g_tables[ORC_TABLE_FIBONACCI], *m = &g_tables[ORC_TABLE_MEMORY];
+    f->used = 1; f->cols = 2; f->degree = 2; f->n_pi = 3;
+    m->used = 1; m->cols = 21; m->degree = 3; m->n_pi = 0; m->n_lookups = 1;
+    m->lookups[0].n_looking = 1; m->lookups[0].looking = g_mem_looking; m->lookups[0].table_col = 19; m->lookups[0].freq_col = 20;
+  }
+  if (t < 0 || t >= ORC_MAX_TABLES || !g_tables[t].used) { fprintf(stderr, "oracle: unknown table %d\n", t); abort(); }
+  return &g_tables[t];
+}
+/* lookups: [n_lookups, then per lookup: table_col, freq_col, n_looking, looking...]; returns the id or -1 */
+int orc_table_register(const uint64_t *program, size_t n_words, const int32_t *lookups, size_t n_lookup_words) {
+  get_table(0);
+  if (n_words < 8 || program[0] != CPROG_MAGIC || n_words != 8 + 2 * program[1]) return -1;
+  int id = -1;
+  for (int i = 16; i < ORC_MAX_TABLES; i++) if (!g_tables[i].used) { id = i; break; }
+  if (id < 0) return -1;
+  table_t *t = &g_tables[id];
+  memset(t, 0, sizeof *t);
+  t->n_ops = (uint32_t)program[1]; t->cols = (int)program[2]; t->n_aux = (uint32_t)program[3]; t->n_pi = (int)program[4];
+  t->n_ch = (uint32_t)program[5]; t->degree = (int)program[6];
+  t->ops = (uint64_t *)malloc(2 * (size_t)t->n_ops * 8 + 8);
+  memcpy(t->ops, program + 8, 2 * (size_t)t->n_ops * 8);
+  if (n_lookup_words) {
+    size_t pos = 0;
+    t->n_lookups = lookups[pos++];
+    for (int i = 0; i < t->n_lookups; i++) {
+      lookup_t *l = &t->lookups[i];
+      l->table_col = lookups[pos++]; l->freq_col = lookups[pos++]; l->n_looking = lookups[pos++];
+      l->looking = (int *)malloc(sizeof(int) * l->n_looking);
+      for (int j = 0; j < l->n_looking; j++) l->looking[j] = lookups[pos++];
+    }
+  }
+  t->used = 1;
+  return id;
+}
+int orc_table_num_columns(int t) { return get_table(t)->cols; }
+int orc_table_constraint_degree(int t) { return get_table(t)->degree; }
+int orc_table_num_public_inputs(int t) { return get_table(t)->n_pi; }
+int orc_table_uses_lookup(int t) { return get_table(t)->n_lookups > 0; }
+static int lookup_chunk(const table_t *t) { return t->degree - 1 < 1 ? 1 : t->degree - 1; }
+static int lookup_helpers(const table_t *t, const lookup_t *l) { return (l->n_looking + lookup_chunk(t) - 1) / lookup_chunk(t); }
 static int quotient_degree_factor(int t) {
   int d = orc_table_constraint_degree(t) - 1;
   return d < 1 ? 1 : d;
 }
 static int log2_ceil(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
-/* one lookup (RANGE_CHECK in COUNTER, multiplicities FREQUENCIES), 1 looking column:
- * num_helper_columns = ceil(1 / (degree-1)) + 1 = 2 per challenge */
-int orc_table_num_aux_columns(int t, int n_challenges) { return orc_table_uses_lookup(t) ? 2 * n_challenges : 0; }
+/* per lookup and challenge: num_helper_columns = ceil(n_looking / (degree-1)) helpers + Z */
+int orc_table_num_aux_columns(int t, int n_challenges) {
+  const table_t *tb = get_table(t);
+  int a = 0;
+  for (int i = 0; i < tb->n_lookups; i++) a += lookup_helpers(tb, &tb->lookups[i]) + 1;
+  return a * n_challenges;
+}
 
 enum { M_FILTER = 0, M_TIMESTAMP, M_IS_READ, M_CTX, M_SEG, M_VIRT, M_VALUE0, M_CFC = 14, M_SFC, M_VFC,
        M_INIT_AUX, M_RANGE_CHECK, M_COUNTER, M_FREQ };
@@ -127,26 +187,74 @@ static void eval_memory(const uint64_t *lv, const uint64_t *nv, const uint64_t *
   c_transition(c, gl_sub(gl_sub(nv[M_COUNTER], lv[M_COUNTER]), one));
 }
 
+/* constraint program interpreter: own constraints AND lookup checks are in the program */
+static void eval_program(const table_t *tb, const uint64_t *lv, const uint64_t *nv, const uint64_t *al, const uint64_t *an,
+                         const uint64_t *pi, const uint64_t *ch, consumer_t *c) {
+  uint64_t *v = (uint64_t *)malloc((size_t)tb->n_ops * 8 + 8);
+  for (uint32_t k = 0; k < tb->n_ops; k++) {
+    const uint64_t w0 = tb->ops[2 * k], imm = tb->ops[2 * k + 1];
+    const int op = (int)(w0 & 0xFF);
+    const uint32_t a = (uint32_t)((w0 >> 8) & 0xFFFFFFF), b = (uint32_t)((w0 >> 36) & 0xFFFFFFF);
+    switch (op) {
+      case OP_CONST: v[k] = imm; break;
+      case OP_LV: v[k] = lv[a]; break;
+      case OP_NV: v[k] = nv[a]; break;
+      case OP_LA: v[k] = al ? al[a] : 0; break;
+      case OP_NA: v[k] = an ? an[a] : 0; break;
+      case OP_PI: v[k] = pi[a]; break;
+      case OP_CH: v[k] = ch ? ch[a] : 0; break;
+      case OP_ADD: v[k] = gl_add(v[a], v[b]); break;
+      case OP_SUB: v[k] = gl_sub(v[a], v[b]); break;
+      case OP_MUL: v[k] = gl_mul(v[a], v[b]); break;
+      case OP_EMIT: c_constraint(c, v[a]); break;
+      case OP_EMIT_TRANSITION: c_transition(c, v[a]); break;
+      case OP_EMIT_FIRST: c_first_row(c, v[a]); break;
+      case OP_EMIT_LAST: c_last_row(c, v[a]); break;
+      default: break;
+    }
+  }
+  free(v);
+}
+
 static void eval_table(int t, const uint64_t *lv, const uint64_t *nv, const uint64_t *pi, consumer_t *c) {
   if (t == ORC_TABLE_FIBONACCI) eval_fibonacci(lv, nv, pi, c);
   else eval_memory(lv, nv, pi, c);
 }
 
-/* eval_packed_lookups_generic for the single memory lookup */
+/* eval_packed_lookups_generic (no filters): per lookup, per challenge: helpers..., Z */
 static void eval_lookups(int t, const uint64_t *lv, const uint64_t *aux_l, const uint64_t *aux_n,
                          const uint64_t *challenges, int n_ch, consumer_t *c) {
-  if (!orc_table_uses_lookup(t)) return;
+  const table_t *tb = get_table(t);
+  const int chunk = lookup_chunk(tb);
   int start = 0;
-  for (int k = 0; k < n_ch; k++) {
-    uint64_t ch = challenges[k];
-    uint64_t h = aux_l[start], z = aux_l[start + 1], next_z = aux_n[start + 1];
-    /* eval_helper_columns, chunk of length 1, no filter: (f + ch) * h - 1 */
-    c_constraint(c, gl_sub(gl_mul(gl_add(lv[M_RANGE_CHECK], ch), h), 1));
-    uint64_t table_with_challenge = gl_add(lv[M_COUNTER], ch);
-    uint64_t y = gl_sub(gl_mul(h, table_with_challenge), lv[M_FREQ]);
-    c_first_row(c, z);
-    c_constraint(c, gl_sub(gl_mul(gl_sub(next_z, z), table_with_challenge), y));
-    start += 2;
+  for (int li = 0; li < tb->n_lookups; li++) {
+    const lookup_t *l = &tb->lookups[li];
+    const int nh = lookup_helpers(tb, l);
+    for (int k = 0; k < n_ch; k++) {
+      uint64_t ch = challenges[k];
+      uint64_t hsum = 0;
+      for (int hc = 0; hc < nh; hc++) {
+        /* eval_helper_columns: h * prod(col_j + ch) - sum_j prod_{i != j}(col_i + ch) */
+        int j0 = hc * chunk, j1 = j0 + chunk < l->n_looking ? j0 + chunk : l->n_looking;
+        uint64_t h = aux_l[start + hc], prod = 1, rhs = 0;
+        for (int j = j0; j < j1; j++) prod = gl_mul(prod, gl_add(lv[l->looking[j]], ch));
+        if (j1 - j0 == 1) rhs = 1;
+        else
+          for (int j = j0; j < j1; j++) {
+            uint64_t tp = 1;
+            for (int i = j0; i < j1; i++) if (i != j) tp = gl_mul(tp, gl_add(lv[l->looking[i]], ch));
+            rhs = gl_add(rhs, tp);
+          }
+        c_constraint(c, gl_sub(gl_mul(h, prod), rhs));
+        hsum = gl_add(hsum, h);
+      }
+      uint64_t z = aux_l[start + nh], next_z = aux_n[start + nh];
+      uint64_t table_with_challenge = gl_add(lv[l->table_col], ch);
+      uint64_t y = gl_sub(gl_mul(hsum, table_with_challenge), lv[l->freq_col]);
+      c_first_row(c, z);
+      c_constraint(c, gl_sub(gl_mul(gl_sub(next_z, z), table_with_challenge), y));
+      start += nh + 1;
+    }
   }
 }
 
@@ -154,16 +262,20 @@ static void eval_lookups(int t, const uint64_t *lv, const uint64_t *aux_l, const
 long orc_table_check_constraints(int t, int log_n, const uint64_t *trace, const uint64_t *pi) {
   size_t n = (size_t)1 << log_n;
   int nc = orc_table_num_columns(t);
-  uint64_t lv[32], nv[32];
-  for (size_t i = 0; i < n; i++) {
+  const table_t *tb = get_table(t);
+  if (tb->ops) return -2; /* programs: use cprog.Program.check_trace (the lookup checks need the aux columns) */
+  uint64_t *lv = (uint64_t *)malloc(2 * (size_t)nc * 8), *nv = lv + nc;
+  long res = -1;
+  for (size_t i = 0; i < n && res < 0; i++) {
     for (int c = 0; c < nc; c++) { lv[c] = trace[c * n + i]; nv[c] = trace[c * n + (i + 1) % n]; }
     consumer_t cs; memset(&cs, 0, sizeof cs);
     cs.check = 1; cs.first_fail = -1;
     cs.z_last = (i == n - 1) ? 0 : 1; cs.lagrange_first = (i == 0); cs.lagrange_last = (i == n - 1);
     eval_table(t, lv, nv, pi, &cs);
-    if (cs.first_fail >= 0) return (long)i * 1000 + cs.first_fail;
+    if (cs.first_fail >= 0) res = (long)i * 1000 + cs.first_fail;
   }
-  return -1;
+  free(lv);
+  return res;
 }
 
 /* ---------------- lookup helper columns (starky lookup.rs: lookup_helper_columns) ---------------- */
@@ -177,20 +289,42 @@ static void batch_inverse(uint64_t *x, size_t n) {
 }
 void orc_lookup_helper_columns(int t, int log_n, const uint64_t *trace, const uint64_t *challenges,
                                int n_ch, uint64_t *aux) {
-  if (!orc_table_uses_lookup(t)) return;
+  const table_t *tb = get_table(t);
+  if (!tb->n_lookups) return;
   size_t n = (size_t)1 << log_n;
-  const uint64_t *looking = trace + M_RANGE_CHECK * n, *table = trace + M_COUNTER * n, *freq = trace + M_FREQ * n;
-  uint64_t *tinv = (uint64_t *)malloc(n * sizeof(uint64_t));
-  for (int k = 0; k < n_ch; k++) {
-    uint64_t ch = challenges[k];
-    uint64_t *h = aux + (size_t)(2 * k) * n, *z = aux + (size_t)(2 * k + 1) * n;
-    for (size_t i = 0; i < n; i++) { h[i] = gl_add(looking[i], ch); tinv[i] = gl_add(table[i], ch); }
-    batch_inverse(h, n);
-    batch_inverse(tinv, n);
-    z[0] = 0;
-    for (size_t i = 0; i + 1 < n; i++) z[i + 1] = gl_add(z[i], gl_sub(h[i], gl_mul(freq[i], tinv[i])));
+  const int chunk = lookup_chunk(tb);
+  uint64_t *inv = (uint64_t *)malloc(n * sizeof(uint64_t)), *tinv = (uint64_t *)malloc(n * sizeof(uint64_t));
+  uint64_t *out = aux;
+  for (int li = 0; li < tb->n_lookups; li++) {
+    const lookup_t *l = &tb->lookups[li];
+    const int nh = lookup_helpers(tb, l);
+    const uint64_t *table = trace + (size_t)l->table_col * n, *freq = trace + (size_t)l->freq_col * n;
+    for (int k = 0; k < n_ch; k++) {
+      uint64_t ch = challenges[k];
+      uint64_t *z = out + (size_t)nh * n;
+      for (int hc = 0; hc < nh; hc++) {
+        uint64_t *h = out + (size_t)hc * n;
+        memset(h, 0, n * 8);
+        for (int j = hc * chunk; j < (hc + 1) * chunk && j < l->n_looking; j++) {
+          const uint64_t *col = trace + (size_t)l->looking[j] * n;
+          for (size_t i = 0; i < n; i++) inv[i] = gl_add(col[i], ch);
+          batch_inverse(inv, n);
+          for (size_t i = 0; i < n; i++) h[i] = gl_add(h[i], inv[i]);
+        }
+        for (size_t i = 0; i < n; i++) h[i] = gl_canon(h[i]);
+      }
+      for (size_t i = 0; i < n; i++) tinv[i] = gl_add(table[i], ch);
+      batch_inverse(tinv, n);
+      z[0] = 0;
+      for (size_t i = 0; i + 1 < n; i++) {
+        uint64_t tot = 0;
+        for (int hc = 0; hc < nh; hc++) tot = gl_add(tot, out[(size_t)hc * n + i]);
+        z[i + 1] = gl_canon(gl_add(z[i], gl_sub(tot, gl_mul(freq[i], tinv[i]))));
+      }
+      out += (size_t)(nh + 1) * n;
+    }
   }
-  free(tinv);
+  free(inv); free(tinv);
 }
 
 /* ---------------- compute_quotient_polys ---------------- */
@@ -234,11 +368,13 @@ void orc_compute_quotient_polys(int t, int log_n, const orc_batch *trace, const 
     cs.z_last = gl_sub(x, last); cs.lagrange_first = lfirst[i]; cs.lagrange_last = llast[i];
     const uint64_t *lv = trace->leaves + bitrev64(i * step, log_lde) * nc;
     const uint64_t *nv = trace->leaves + bitrev64(i_next * step, log_lde) * nc;
-    eval_table(t, lv, nv, pi, &cs);
-    if (aux) {
-      const uint64_t *al = aux->leaves + bitrev64(i * step, log_lde) * na;
-      const uint64_t *an = aux->leaves + bitrev64(i_next * step, log_lde) * na;
-      eval_lookups(t, lv, al, an, lookup_challenges, NUM_CHALLENGES, &cs);
+    const uint64_t *al = aux ? aux->leaves + bitrev64(i * step, log_lde) * na : NULL;
+    const uint64_t *an = aux ? aux->leaves + bitrev64(i_next * step, log_lde) * na : NULL;
+    if (get_table(t)->ops) {
+      eval_program(get_table(t), lv, nv, al, an, pi, lookup_challenges, &cs);
+    } else {
+      eval_table(t, lv, nv, pi, &cs);
+      if (aux) eval_lookups(t, lv, al, an, lookup_challenges, NUM_CHALLENGES, &cs);
     }
     uint64_t dinv = zh_inv[i % (1 << qbits)];
     for (int j = 0; j < n_alphas; j++) qvals[(size_t)j * size + i] = gl_mul(cs.acc[j], dinv);

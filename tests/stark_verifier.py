@@ -225,16 +225,31 @@ def _interpolate(points, x):
     return total
 
 
-def verify(words, fast=True, max_queries=None):
-    """Raises VerifyError unless the proof is valid. Returns the parsed proof."""
+def _eval_program(program, lv, nv, aux, aux_next, pi, challenges, c):
+    """Program-defined table (eth_tx_proof_b200/cprog.py): the program is interpreted over F_{p^2}."""
+    out = program.evaluate(lv, nv, aux, aux_next, pi, challenges or (), add=R.e_add, sub=R.e_sub, mul=R.e_mul, lift=R.e_from)
+    for kind, val in out:
+        (c.constraint, c.transition, c.first_row, c.last_row)[kind - 10](val)
+
+
+def verify(words, fast=True, max_queries=None, program=None):
+    """Raises VerifyError unless the proof is valid. Returns the parsed proof.  `program`: the cprog.Program of a
+    registered table (table id >= 16 in the header); built-in tables are evaluated by the code above."""
     hash_or_noop, two_to_one, perm = _hashers(fast)
     pr = parse_proof(words)
     h = pr["h"]
     table, db, rate_bits = h["table"], h["degree_bits"], h["rate_bits"]
     n_ch = h["num_challenges"]
     degree = 1 << db
-    factor = {TABLE_FIBONACCI: 1, TABLE_MEMORY: 2}[table]
-    exp_cols = {TABLE_FIBONACCI: (2, 0), TABLE_MEMORY: (21, 2 * n_ch)}[table]
+    if table >= 16:
+        if program is None:
+            raise VerifyError("registered table: pass its program")
+        factor = max(1, program.degree - 1)
+        chunk = max(1, program.degree - 1)
+        exp_cols = (program.n_trace, sum(-(-len(l[0]) // chunk) + 1 for l in program.lookups) * n_ch)
+    else:
+        factor = {TABLE_FIBONACCI: 1, TABLE_MEMORY: 2}[table]
+        exp_cols = {TABLE_FIBONACCI: (2, 0), TABLE_MEMORY: (21, 2 * n_ch)}[table]
     if (h["n_trace"], h["n_aux"]) != exp_cols or h["n_quot"] != factor * n_ch:
         raise VerifyError("shape")
     # ---- transcript (get_challenges)
@@ -279,7 +294,9 @@ def verify(words, fast=True, max_queries=None):
     l_last = R.e_mul(z_x, R.e_inv(R.e_scalar(R.e_sub(R.e_scalar(zeta, g), (1, 0)), degree)))
     z_last = R.e_sub(zeta, R.e_from(pow(g, P - 2, P)))
     cons = _Consumer(alphas, z_last, l_first, l_last)
-    if table == TABLE_FIBONACCI:
+    if table >= 16:
+        _eval_program(program, pr["local"], pr["next"], pr["aux"], pr["aux_next"], pr["public_inputs"], lookup_ch, cons)
+    elif table == TABLE_FIBONACCI:
         _eval_fibonacci(pr["local"], pr["next"], pr["public_inputs"], cons)
     else:
         _eval_memory(pr["local"], pr["next"], pr["public_inputs"], cons)

@@ -1,0 +1,103 @@
+"""CPU tests of the constraint-program path: the Python recorder, the wire format, the oracle's interpreter against
+the oracle's built-in tables and the independent verifier, and — without any GPU — that the product library parses a
+program and NVRTC-compiles its quotient kernel for sm_100a (etp_cprog_compile_check)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+P = 0xFFFFFFFF00000001
+
+
+def test_builder_hash_conses_and_encodes():
+    from eth_tx_proof_b200 import cprog
+
+    b = cprog.ProgramBuilder(3, 1, 3)
+    x, y = b.lv(0), b.nv(1)
+    e1 = x * y + 5
+    e2 = x * y + 5
+    assert e1.id == e2.id                      # shared sub-expressions are evaluated once
+    b.constraint(e1 - b.pi(0))
+    b.constraint(e1 - b.pi(0))                 # ...but every constraint is emitted
+    p = b.build()
+    assert p.n_constraints == 2 and p.words[0] == cprog.MAGIC and p.words[1] == len(p.ops)
+    assert p.words.size == 8 + 2 * len(p.ops)
+    out = p.evaluate([3, 0, 0], [0, 4, 0], pi=[17])
+    assert [v for _, v in out] == [0, 0] and [k for k, _ in out] == [cprog.EMIT, cprog.EMIT]
+
+
+def test_sample_tables_are_satisfied_by_their_traces():
+    from eth_tx_proof_b200 import cprog, synthetic as syn
+
+    assert cprog.logic_program(1).check_trace(cprog.logic_trace(4, 1)) == -1
+    t = cprog.logic_trace(4, 1)
+    t[cprog.logic_layout(1)["RES"], 2] += np.uint64(1)
+    assert cprog.logic_program(1).check_trace(t) // 1000 == 2
+    tr, pi = syn.fibonacci_trace(5)
+    assert cprog.fibonacci_program().check_trace(tr, pi) == -1
+
+
+def test_oracle_interprets_the_memory_program_like_its_builtin_table():
+    import oracle
+    import stark_verifier as V
+    from eth_tx_proof_b200 import cprog, synthetic as syn
+
+    prog = cprog.memory_program()
+    tid = oracle.register_table(prog, prog.lookups)
+    t = syn.memory_trace(6)
+    a = oracle.stark_prove(oracle.TABLE_MEMORY, t)
+    b = oracle.stark_prove(tid, t)
+    assert (a[2:] == b[2:]).all() and int(b[1]) == tid
+    V.verify(b, program=prog, max_queries=3)
+    with pytest.raises(V.VerifyError):
+        V.verify(b)                            # a registered table cannot be verified without its program
+
+
+def test_oracle_multi_column_lookup_and_verifier():
+    import oracle
+    import stark_verifier as V
+    from eth_tx_proof_b200 import cprog
+
+    prog = cprog.rangecheck_program(5)
+    tid = oracle.register_table(prog, prog.lookups)
+    t = cprog.rangecheck_trace(6, 5)
+    assert oracle.lib().orc_table_num_aux_columns(tid, 2) == 8 == prog.n_aux
+    proof = oracle.stark_prove(tid, t)
+    V.verify(proof, program=prog, max_queries=3)
+    aux = oracle.lookup_helper_columns(tid, t, [11, 12])
+    # Z telescopes: Z[n-1] + last term == 0 is what the wrap-around constraint enforces; first Z is 0
+    assert (aux[3] [0] == 0) and (aux[7][0] == 0)
+
+
+def _compile_check(words):
+    import eth_tx_proof_b200 as etp
+
+    L = etp.load_library()
+    n = C.c_size_t()
+    err = C.create_string_buffer(512)
+    rc = L.etp_cprog_compile_check(words.ctypes.data_as(C.POINTER(C.c_uint64)), words.size, C.byref(n), err, 512)
+    return rc, n.value, err.value.decode()
+
+
+def test_product_compiles_programs_for_sm100a_without_a_gpu():
+    from eth_tx_proof_b200 import cprog
+
+    rc, size, err = _compile_check(cprog.memory_program().words)
+    assert rc == 0 and size > 10000, err
+    rc, size, err = _compile_check(cprog.logic_program(2).words)   # > 600 ops: compact-code path
+    assert rc == 0 and size > 10000, err
+
+
+def test_product_rejects_malformed_programs():
+    from eth_tx_proof_b200 import cprog
+
+    w = cprog.fibonacci_program().words.copy()
+    bad = w.copy(); bad[0] = 1
+    assert _compile_check(bad)[0] != 0
+    bad = w[:-1].copy()
+    assert _compile_check(bad)[0] != 0
+    bad = w.copy(); bad[8] = np.uint64(cprog.LV | (7 << 8))        # column 7 of a 2-column table
+    rc, _, err = _compile_check(bad)
+    assert rc != 0 and "malformed" in err
+    bad = w.copy(); bad[7] = 99                                     # n_constraints does not match
+    assert _compile_check(bad)[0] != 0
