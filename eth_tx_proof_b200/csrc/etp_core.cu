@@ -138,16 +138,30 @@ static int plan_digits(int L, int b[8]) {
 }
 int ntt_num_passes(int log_n) { int b[8]; return log_n <= 0 ? 1 : plan_digits(log_n, b); }
 
-template <int B>
+template <int B, int MODE>
 static void launch_strided(const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
-  ntt::pass_strided<B><<<grid, ntt::THREADS, ntt::Geo<B>::SMEM_WORDS_STRIDED * 8, st>>>(p, ul);
+  ntt::pass_strided<B, MODE><<<grid, ntt::THREADS, ntt::Geo<B>::SMEM_WORDS_STRIDED * 8, st>>>(p, ul);
 }
-template <int B>
+template <int B, int MODE>
 static void launch_last(const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
-  ntt::pass_last<B><<<grid, ntt::THREADS, ntt::Geo<B>::SMEM_WORDS_LAST * 8, st>>>(p, ul);
+  ntt::pass_last<B, MODE><<<grid, ntt::THREADS, ntt::Geo<B>::SMEM_WORDS_LAST * 8, st>>>(p, ul);
+}
+// The passes of the big transforms (digits of 5..8 bits with their tables resident) run the instantiations whose
+// switches are compile-time constants; everything else takes the generic kernel of the same digit size.
+template <int B>
+static void dispatch_digit(bool last, const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
+  if (B >= 5) {
+    if (!last && p.tw_full && (!p.in_scale || p.in_full)) {
+      if (p.in_scale) launch_strided<B, 1>(p, ul, grid, st); else launch_strided<B, 0>(p, ul, grid, st);
+      return;
+    }
+    if (last && !p.in_scale && !p.natural_out && p.out_scale == 0) { launch_last<B, 0>(p, ul, grid, st); return; }
+    if (last && !p.in_scale && p.natural_out && p.out_scale == 2) { launch_last<B, 1>(p, ul, grid, st); return; }
+  }
+  if (last) launch_last<B, -1>(p, ul, grid, st); else launch_strided<B, -1>(p, ul, grid, st);
 }
 static void dispatch_pass(bool last, int B, const ntt::PassParams& p, int ul, dim3 grid, cudaStream_t st) {
-#define ETP_CASE(n) case n: if (last) launch_last<n>(p, ul, grid, st); else launch_strided<n>(p, ul, grid, st); break;
+#define ETP_CASE(n) case n: dispatch_digit<n>(last, p, ul, grid, st); break;
   switch (B) { ETP_CASE(1) ETP_CASE(2) ETP_CASE(3) ETP_CASE(4) ETP_CASE(5) ETP_CASE(6) ETP_CASE(7) ETP_CASE(8) default: break; }
 #undef ETP_CASE
 }

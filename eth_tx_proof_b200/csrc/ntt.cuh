@@ -34,6 +34,9 @@ namespace ntt {
 constexpr int THREADS = 256;
 constexpr int TILE_LOG = 12;       // 4096 elements per CTA, 16 per thread
 constexpr int MAX_DIGIT_BITS = 8;
+#ifndef ETP_NTT_MIN_BLOCKS
+#define ETP_NTT_MIN_BLOCKS 4
+#endif
 
 // powers of w16 = primitive_root_of_unity(4) and of its inverse (all of them are powers of two mod p)
 static __device__ __constant__ const uint64_t W16[8] = {0x0000000000000001ULL, 0xefffffff00000001ULL, 0xfffffffeff000001ULL, 0x000ffffffff00000ULL,
@@ -130,9 +133,14 @@ struct Geo {
 };
 
 // ---- strided pass (s >= U_LOG): grid = (columns, tiles) --------------------------------------------
-template <int B>
-static __global__ void __launch_bounds__(THREADS, 3) pass_strided(PassParams p, int units_log) {
+// MODE: compile-time copy of the run-time switches, so that the hot instantiations carry no dead code (the
+// straight-line kernels are executed once per CTA; ncu showed instruction-fetch stalls, profiles/).
+//   strided: -1 read p.in_scale | 0 no input scaling | 1 input scaling from the full table
+//   last   : -1 read the flags  | 0 in place, no scaling (LDE) | 1 natural order, times 1/n (plain iFFT)
+template <int B, int MODE>
+static __global__ void __launch_bounds__(THREADS, ETP_NTT_MIN_BLOCKS) pass_strided(PassParams p, int units_log) {
   using G = Geo<B>;
+  const bool in_scale = MODE < 0 ? (p.in_scale != 0) : (MODE == 1);
   const int U = 1 << units_log;  // <= G::U; smaller only when the transform is smaller than a tile
   extern __shared__ uint64_t smem[];
   uint64_t* tw_r = smem;              // R/2 inner twiddles
@@ -159,7 +167,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_strided(PassParams p, 
       uint64_t x = 0;
       if (u < U && pos < p.n_in) {
         x = in[pos];
-        if (p.in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : slow_pow(p.in_pow.lo, p.in_pow.hi, p.in_pow.lo_bits, p.in_pow.mask, (uint32_t)pos));
+        if (in_scale) x = gl::mul(x, (MODE == 1 || p.in_full) ? __ldg(p.in_full + pos) : slow_pow(p.in_pow.lo, p.in_pow.hi, p.in_pow.lo_bits, p.in_pow.mask, (uint32_t)pos));
       }
       v[gi * (1 << G::Q1) + j] = x;
     }
@@ -196,7 +204,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_strided(PassParams p, 
       const uint32_t low = low0 + u;
       if (u < U) {
         uint64_t w;
-        if (p.tw_full) w = __ldg(p.tw_full + (((size_t)d << s) | low));
+        if (MODE >= 0 || p.tw_full) w = __ldg(p.tw_full + (((size_t)d << s) | low));
         else w = slow_twiddle(p.tw.lo, p.tw.hi, p.tw.lo_bits, p.tw.mask, p.inverse, p.log_n, (uint32_t)(((uint64_t)low * gl::bitrev32(d, B)) << (p.log_n - s - B)));
         out[base | ((size_t)d << s) | u] = gl::mul(v[gi * (1 << QL) + j], w);
       }
@@ -206,9 +214,12 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_strided(PassParams p, 
 
 // ---- last pass (s == 0): a CTA owns U chunks of 2^B contiguous elements; grid = (columns, tiles) ----
 //   in place (bit-reversed order): chunks q0 .. q0+U-1 ; natural_out: chunks bitrev(q0 + u)
-template <int B>
-static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int units_log) {
+template <int B, int MODE>
+static __global__ void __launch_bounds__(THREADS, ETP_NTT_MIN_BLOCKS) pass_last(PassParams p, int units_log) {
   using G = Geo<B>;
+  const bool in_scale = MODE < 0 ? (p.in_scale != 0) : false;
+  const bool natural_out = MODE < 0 ? (p.natural_out != 0) : (MODE == 1);
+  const int out_scale = MODE < 0 ? p.out_scale : (MODE == 1 ? 2 : 0);
   extern __shared__ uint64_t smem[];
   uint64_t* tw_r = smem;
   uint64_t* sm = smem + ((1 << B) >> 1);
@@ -226,7 +237,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
 #pragma unroll
   for (int gi = 0; gi < G::G1; gi++) {
     const int g = t + gi * THREADS, d_lo = g & ((1 << (B - G::Q1)) - 1), u = g >> (B - G::Q1);
-    const uint32_t prefix = p.natural_out ? gl::bitrev32(q0 + u, pb) : (q0 + u);
+    const uint32_t prefix = natural_out ? gl::bitrev32(q0 + u, pb) : (q0 + u);
 #pragma unroll
     for (int j = 0; j < (1 << G::Q1); j++) {
       const int d = (j << (B - G::Q1)) | d_lo;
@@ -234,7 +245,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
       uint64_t x = 0;
       if (u < U && pos < p.n_in) {
         x = in[pos];
-        if (p.in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : slow_pow(p.in_pow.lo, p.in_pow.hi, p.in_pow.lo_bits, p.in_pow.mask, (uint32_t)pos));
+        if (in_scale) x = gl::mul(x, p.in_full ? __ldg(p.in_full + pos) : slow_pow(p.in_pow.lo, p.in_pow.hi, p.in_pow.lo_bits, p.in_pow.mask, (uint32_t)pos));
       }
       v[gi * (1 << G::Q1) + j] = x;
     }
@@ -261,7 +272,7 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
     for (int gi = 0; gi < G::G1; gi++) dft_const<G::Q1>(v + gi * (1 << G::Q1), p.inverse);
   }
   constexpr int QL = (B > 4) ? G::Q2 : G::Q1, GL = (B > 4) ? G::G2 : G::G1;
-  if (p.natural_out) {
+  if (natural_out) {
     // out[(k << pb) | (q0 + u)], k = bitrev_B(d)
 #pragma unroll
     for (int gi = 0; gi < GL; gi++) {
@@ -275,8 +286,8 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
         if (u < U) {
           const uint32_t idx = (gl::bitrev32(d, B) << pb) | (q0 + u);
           uint64_t x = v[gi * (1 << QL) + j];
-          if (p.out_scale == 2) x = gl::mul(x, p.out_const);
-          else if (p.out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, idx));
+          if (out_scale == 2) x = gl::mul(x, p.out_const);
+          else if (out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, idx));
           out[idx] = gl::canon(x);
         }
       }
@@ -298,8 +309,8 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
         if (u < U) {
           const size_t pos = ((size_t)(q0 + u) << B) | d;
           uint64_t x = sm[u * G::PITCH + d + (d >> 4)];
-          if (p.out_scale == 2) x = gl::mul(x, p.out_const);
-          else if (p.out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, gl::bitrev32((uint32_t)pos, p.log_n)));
+          if (out_scale == 2) x = gl::mul(x, p.out_const);
+          else if (out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, gl::bitrev32((uint32_t)pos, p.log_n)));
           out[pos] = gl::canon(x);
         }
       }
@@ -313,8 +324,8 @@ static __global__ void __launch_bounds__(THREADS, 3) pass_last(PassParams p, int
           if (u < U) {
             const size_t pos = ((size_t)(q0 + u) << B) | d;
             uint64_t x = v[gi * (1 << G::Q1) + j];
-            if (p.out_scale == 2) x = gl::mul(x, p.out_const);
-            else if (p.out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, gl::bitrev32((uint32_t)pos, p.log_n)));
+            if (out_scale == 2) x = gl::mul(x, p.out_const);
+            else if (out_scale == 1) x = gl::mul(x, slow_pow(p.out_pow.lo, p.out_pow.hi, p.out_pow.lo_bits, p.out_pow.mask, gl::bitrev32((uint32_t)pos, p.log_n)));
             out[pos] = gl::canon(x);
           }
         }

@@ -8,6 +8,9 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct etp_batch { _p: [u8; 0] }
 #[repr(C)] pub struct etp_tree { _p: [u8; 0] }
 
+#[repr(C)] pub struct etp_shard { _p: [u8; 0] }
+pub mod recorder;
+
 extern "C" {
     pub fn etp_ctx_create(device: c_int, out: *mut *mut etp_ctx) -> c_int;
     pub fn etp_ctx_destroy(ctx: *mut etp_ctx);
@@ -33,7 +36,25 @@ extern "C" {
     pub fn etp_compute_quotient_polys_dev(ctx: *mut etp_ctx, table: c_int, trace: *mut etp_batch, aux: *mut etp_batch,
         lookup_challenges: *const u64, n_lookup_challenges: c_int, public_inputs: *const u64,
         alphas: *const u64, n_alphas: c_int, out_dev: *mut u64) -> c_int;
-    pub fn etp_stark_proof_words(table: c_int, log_n: c_int) -> usize;
+    pub fn etp_stark_proof_words(ctx: *const etp_ctx, table: c_int, log_n: c_int) -> usize;
+    // program-defined tables (csrc/cprog.h): what `recorder::record_table` produces
+    pub fn etp_table_register(ctx: *mut etp_ctx, program: *const u64, n_words: usize, lookups: *const i32,
+        n_lookup_words: usize, table_id_out: *mut c_int) -> c_int;
+    pub fn etp_cprog_compile_check(program: *const u64, n_words: usize, cubin_bytes_out: *mut usize, err: *mut c_char,
+        err_len: usize) -> c_int;
+    // column-split commit of one oversized table across the GPUs of a box (one worker process per GPU)
+    pub fn etp_shard_create(ctx: *mut etp_ctx, n_cols_total: usize, log_n: c_int, rate_bits: c_int, cap_height: c_int,
+        rank: c_int, world: c_int, out: *mut *mut etp_shard) -> c_int;
+    pub fn etp_shard_free(s: *mut etp_shard);
+    pub fn etp_shard_transform_values_host(s: *mut etp_shard, local_cols: *const *const u64) -> c_int;
+    pub fn etp_shard_lde_dev(s: *const etp_shard) -> *const u64;
+    pub fn etp_ipc_export(ctx: *mut etp_ctx, dev_ptr: *const c_void, handle_out: *mut u8) -> c_int;
+    pub fn etp_ipc_open(ctx: *mut etp_ctx, handle: *const u8, dev_ptr_out: *mut *mut c_void) -> c_int;
+    pub fn etp_ipc_close(ctx: *mut etp_ctx, dev_ptr: *mut c_void) -> c_int;
+    pub fn etp_shard_set_peer(s: *mut etp_shard, peer_rank: c_int, peer_lde: *const u64) -> c_int;
+    pub fn etp_shard_commit_rows(s: *mut etp_shard, cap_part_out: *mut u64) -> c_int;
+    pub fn etp_shard_prove(s: *mut etp_shard, leaf_index: usize, siblings_out: *mut u64) -> c_int;
+    pub fn etp_shard_leaves_at(s: *mut etp_shard, idx: *const u64, n_idx: usize, rows_out: *mut u64) -> c_int;
     pub fn etp_stark_prove_host(ctx: *mut etp_ctx, table: c_int, log_n: c_int, trace: *const u64,
         public_inputs: *const u64, proof_out: *mut u64) -> c_int;
     pub fn etp_pow_grind(ctx: *mut etp_ctx, state: *const u64, pos: c_int, bits: c_int, witness_out: *mut u64) -> c_int;
