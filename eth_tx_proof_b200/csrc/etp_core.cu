@@ -553,10 +553,14 @@ __global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* d
 int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values) {
   etp_ctx* ctx = b->ctx;
   const size_t n = b->n(), C = b->n_cols, G = stream_group_cols(b);
-  // a last group of fewer than 8 columns joins its predecessor: its ragged sponge chunk keeps rate lanes of the
-  // previous permutation, and only the capacity lanes are carried from one launch to the next
-  size_t n_groups = C ? (C + G - 1) / G : 0;
-  if (n_groups > 1 && C - (n_groups - 1) * G < 8) n_groups--;
+  // group boundaries (multiples of 8 columns).  The first group is a single sponge chunk: its copy is the only one
+  // nothing can hide.  A last group of fewer than 8 columns joins its predecessor: its ragged sponge chunk keeps
+  // rate lanes of the previous permutation, and only the capacity lanes are carried from one launch to the next.
+  std::vector<size_t> bounds{0};
+  if (G < C && G > 8) bounds.push_back(8);
+  while (bounds.back() < C) bounds.push_back(bounds.back() + G < C ? bounds.back() + G : C);
+  if (bounds.size() > 2 && C - bounds[bounds.size() - 2] < 8) bounds.erase(bounds.end() - 2);
+  const size_t n_groups = bounds.size() - 1;
   for (size_t c = 0; c < C; c++)
     if (!cols[c]) return etp_fail(ctx, ETP_ERR_INVALID, "null column %zu", c);
   DevBuf<uint64_t> stage(ctx);
@@ -570,7 +574,7 @@ int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, b
   ETP_CUDA(ctx, cudaEventRecord(ready, ctx->stream));  // buffers allocated (stream-ordered) before the copies start
   ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
   for (size_t k = 0; k < n_groups; k++) {
-    const size_t c0 = k * G, gc = (k + 1 == n_groups ? C - c0 : G);
+    const size_t c0 = bounds[k], gc = bounds[k + 1] - c0;
     uint64_t* land = is_values ? stage.p + (k & 1) * slot : b->coeffs + c0 * n;
     cudaEvent_t h2d_done, slot_free;
     ETP_TRY(get_sync_event(ctx, 1 + 2 * k, &h2d_done));

@@ -5,6 +5,10 @@
 // See include/etp_b200.h for the upstream item behind each entry point and DESIGN.md for the proof
 // wire format.  Product code: no oracle, no CPU fallback; the only host arithmetic is the transcript
 // (Challenger) and the <= 2^8-coefficient FRI final polynomial.
+#include <time.h>
+
+#include <cstdlib>
+
 #include "cprog.h"
 #include "ctx.cuh"
 #include "host_field.h"
@@ -72,20 +76,26 @@ int fri_num_layers(int degree_bits) {  // FriReductionStrategy::ConstantArityBit
 struct PhaseTimer {
   etp_ctx* ctx;
   std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  std::vector<double> host_ms;  // host clock at each mark (ETP_TRACE=1 prints it: tells a device phase from a host stall)
   explicit PhaseTimer(etp_ctx* c) : ctx(c) { mark("start"); }
   void mark(const char* name) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, ctx->stream);
     marks.emplace_back(name, e);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    host_ms.push_back(ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6);
   }
   void finish() {
     ctx->timings.clear();
     cudaStreamSynchronize(ctx->stream);
+    const bool trace = getenv("ETP_TRACE") != nullptr;
     for (size_t i = 1; i < marks.size(); i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
       ctx->timings.emplace_back(marks[i].first, ms);
+      if (trace) fprintf(stderr, "[etp trace] %-50s device %8.3f ms   host enqueue %8.3f ms\n", marks[i].first, ms, host_ms[i] - host_ms[i - 1]);
     }
   }
   ~PhaseTimer() { for (auto& m : marks) cudaEventDestroy(m.second); }
@@ -288,8 +298,11 @@ int pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, int bits, uint64_
   uint64_t st[12];
   for (int i = 0; i < 12; i++) st[i] = gl::canon(state[i]);
   ETP_CUDA(ctx, cudaMemcpyAsync(d_state.p, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream));
-  const uint64_t batch = (uint64_t)1 << 20;
+  // candidates are scanned in increasing order, one batch per launch; the smallest hit of the first batch that has
+  // one is the smallest witness overall.  2^bits candidates are needed on average: start with 2 x that, then grow.
+  uint64_t batch = (uint64_t)1 << (bits + 1 < 12 ? 12 : (bits + 1 > 22 ? 22 : bits + 1));
   for (uint64_t base = 0;; base += batch) {
+    if (base) batch = batch < ((uint64_t)1 << 22) ? batch << 1 : batch;
     unsigned long long init = ~0ull, found = ~0ull;
     ETP_CUDA(ctx, cudaMemcpyAsync(ctx->d_pow_result, &init, 8, cudaMemcpyHostToDevice, ctx->stream));
     stark::pow_grind<<<(unsigned)(batch / 128), 128, 0, ctx->stream>>>(d_state.p, pos, bits, base, (unsigned long long*)ctx->d_pow_result);
