@@ -6,6 +6,7 @@ import hashlib
 import os
 import re
 import struct
+import sys
 
 import pytest
 
@@ -66,16 +67,18 @@ def test_embedded_round_constants_are_the_pinned_ones():
     with open(os.path.join(ROOT, "tests", "golden", "poseidon_kat.json")) as f:
         kat = json.load(f)
     assert hashlib.sha256(b"".join(struct.pack("<Q", v) for v in vals)).hexdigest() == kat["round_constants_sha256_le_u64"]
-    f64 = src.split("#define ETP_POSEIDON_RC_F64_TABLE")[1].split("}")[0]
-    bits = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ULL", f64)]
-    assert len(bits) == 720
-    as_f64 = lambda b: struct.unpack("<d", struct.pack("<Q", b))[0]
-    for r in range(30):
-        for h in range(2):
-            ks = [((vals[12 * (r + 1) + i] >> (32 * h)) & 0xFFFFFFFF) if r < 29 else 0 for i in range(12)]
-            for i in range(6):
-                assert as_f64(bits[24 * r + 12 * h + i]) == float(2**51 + ks[i])
-                assert as_f64(bits[24 * r + 12 * h + 6 + i]) == float(2**52 + ks[i + 6] - ks[i])
+    # the FP64-pipe start-value tables are the ones tools/gen_poseidon_constants.py derives from those constants
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_poseidon_constants as gen
+
+    _, _, _, _, full, pair = gen.tables()
+    for name, rows in (("ETP_POSEIDON_FULL_F64_TABLE", full), ("ETP_POSEIDON_PAIR_F64_TABLE", pair)):
+        body = src.split("#define " + name)[1].split("}")[0]
+        bits = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ULL", body)]
+        want = [v for layer in rows for plane in layer for v in plane]
+        assert len(bits) == len(want)
+        for b, w in zip(bits, want):
+            assert struct.unpack("<d", struct.pack("<Q", b))[0] == float(w) and abs(w) < 2**53
 
 
 def test_synthetic_traces_are_deterministic_and_valid():
