@@ -341,20 +341,20 @@ def main():
     achieved = leaf_bytes / (leaf_ms / 1e3) / 1e9
     perms_leaf = (n << RATE_BITS) * ((cols + 7) // 8)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    # issue-slot roofline of the Poseidon kernels (profiles/README.md, tools/microbench/pipes3.cu + poseidon_parts.cu):
-    # on B200 a DFMA/DADD holds the sub-partition's issue port for ~2.2 clk (FP64 and integer work do NOT overlap:
-    # S-boxes alone 15.7k clk + MDS alone 15.2k clk ~= full permutation 29.0k clk per warp), every other
-    # instruction takes one slot.  Static SASS counts per permutation (tools/sass_count.py): 6600 FP64 + 12897 others.
-    fp64_per_perm, other_per_perm = 6600, 12897
-    slots_per_perm = 2.2 * fp64_per_perm + other_per_perm
-    perm_peak = 148 * 4 * sm_mhz * 1e6 / slots_per_perm * 32
+    # integer-pipe roofline of the Poseidon kernels (profiles/README.md, tools/microbench/pipes*.cu): on B200 the integer ALU
+    # and the FP64 unit of a sub-partition share one issue port that accepts a warp instruction every 2 clk (16 lanes/clk), and
+    # that port is what saturates (ncu: alu % + fp64 % of the leaf kernel).  Static SASS counts per permutation from
+    # tools/sass_count.py: 4912 ALU + 4280 FP64 port instructions (the IMAD.WIDE multiplier chains run on the FMA pipe beside it).
+    alu_per_perm, fp64_per_perm = 4912, 4280
+    port_clk_per_perm = 2.0 * (alu_per_perm + fp64_per_perm)
+    perm_peak = 148 * 4 * sm_mhz * 1e6 / port_clk_per_perm * 32
     roofline = {"kernel": "merkle::hash_leaves_colmajor", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "dominant kernel is integer/FP64-issue bound (16 Poseidon permutations per 1 KiB row), not HBM bound; see int_pipe"}
     int_pipe = {"kernel": "merkle::hash_leaves_colmajor", "achieved": perms_leaf / (leaf_ms / 1e3), "peak": perm_peak, "unit": "perm/s",
                 "frac": perms_leaf / (leaf_ms / 1e3) / perm_peak,
-                "model": "issue slots: 148 SM x 4 SMSP x f_sm x 32 lanes / (2.2 x 6600 FP64 + 12897 other warp-instructions per permutation); "
-                         "f_sm = sampled clock; the bound of this kernel's own instruction stream, not a hardware peak"}
+                "model": "shared ALU/FP64 issue port: 148 SM x 4 SMSP x f_sm x 32 lanes / (2 clk x (4912 ALU + 4280 FP64) port instructions per "
+                         "permutation, tools/sass_count.py); f_sm = sampled clock; frac is that port's utilisation (cf. ncu alu % + fp64 %)"}
     ntt_bytes_ifft = 16 * cols * n
     ntt_bytes_lde = 8 * cols * n + 8 * cols * (n << RATE_BITS)
     kernels = [

@@ -28,17 +28,30 @@ __global__ void __launch_bounds__(128, 7) k_parts(uint64_t* st, int reps) {
 #pragma unroll 1
       for (int r = 0; r < 22; r++) s[r % 12 == 0 ? 0 : 0] = poseidon::sbox7(s[0] + r);
     } else {
+      // the FP64 part in the same shape as poseidon::permute: 8 full layers + 11 partial-round pairs, no S-boxes
 #pragma unroll 1
-      for (int r = 0; r < 30; r += 2) {
+      for (int f = 0; f < 8; f++) {
         double dl[12], dh[12], ol[12], oh[12];
 #pragma unroll
         for (int k = 0; k < 12; k++) { dl[k] = poseidon::plane_lo(s[k]); dh[k] = poseidon::plane_hi(s[k]); }
-        poseidon::mds_layer(dl, dh, r, ol, oh);
-        const uint64_t m0 = poseidon::combine_planes(ol[0], oh[0]);
-        ol[0] = poseidon::plane_lo(m0); oh[0] = poseidon::plane_hi(m0);
-        poseidon::mds_layer(ol, oh, r + 1, dl, dh);
+        poseidon::mds_plane(dl, poseidon::FULL_F64 + 24 * f, ol);
+        poseidon::mds_plane(dh, poseidon::FULL_F64 + 24 * f + 12, oh);
 #pragma unroll
-        for (int k = 0; k < 12; k++) s[k] = poseidon::combine_planes(dl[k], dh[k]);
+        for (int k = 0; k < 12; k++) s[k] = poseidon::combine_planes(ol[k], oh[k]);
+      }
+#pragma unroll 1
+      for (int i = 0; i < 11; i++) {
+        double dl[12], dh[12], ol[12], oh[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) { dl[k] = poseidon::plane_lo(s[k]); dh[k] = poseidon::plane_hi(s[k]); }
+        poseidon::Chains cl, ch;
+        const double ul = poseidon::pair_phase1(dl, poseidon::PAIR_F64 + 26 * i, cl);
+        const double uh = poseidon::pair_phase1(dh, poseidon::PAIR_F64 + 26 * i + 13, ch);
+        const uint64_t m0 = poseidon::combine_planes(ul, uh);
+        poseidon::pair_phase2(dl[0], ul, poseidon::plane_lo(m0), cl, ol);
+        poseidon::pair_phase2(dh[0], uh, poseidon::plane_hi(m0), ch, oh);
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = poseidon::combine_planes(ol[k], oh[k]);
       }
     }
   }
