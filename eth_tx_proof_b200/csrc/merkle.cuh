@@ -21,7 +21,10 @@
 
 namespace merkle {
 
-constexpr int HASH_THREADS = 128;
+#ifndef ETP_HASH_THREADS
+#define ETP_HASH_THREADS 128
+#endif
+constexpr int HASH_THREADS = ETP_HASH_THREADS;
 #ifndef ETP_LEAF_MIN_BLOCKS
 #define ETP_LEAF_MIN_BLOCKS 7
 #endif

@@ -138,3 +138,27 @@ def test_prove_dev_matches_prove_host(ctx):
     a = ctx.stark_prove(1, t, [])
     b = ctx.stark_prove_dev(1, 12, d.data_ptr(), 1 << 12, [])
     assert (a == b).all()
+
+
+@pytest.mark.gpu
+def test_prover_pool_proofs_are_identical_to_single_context(ctx):
+    """Two prover contexts on one GPU (parallel.ProverPool) produce the same proofs as one context, job by job."""
+    import torch
+
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import parallel, synthetic as syn
+
+    log_n = 10
+    traces = [torch.from_numpy(syn.memory_trace(log_n, seed=s).view(np.int64)).cuda() for s in range(5)]
+    torch.cuda.synchronize()
+    want = [ctx.stark_prove_dev(etp.TABLE_MEMORY, log_n, t.data_ptr(), 1 << log_n) for t in traces]
+    pool = parallel.ProverPool(0, 2)
+    try:
+        got = pool.stark_prove_dev(etp.TABLE_MEMORY, log_n, [(t.data_ptr(), 1 << log_n) for t in traces])
+    finally:
+        pool.close()
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    with pytest.raises(ValueError):
+        parallel.ProverPool(0, 0)
