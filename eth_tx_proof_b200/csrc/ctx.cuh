@@ -132,6 +132,8 @@ inline size_t level_offset(size_t n_leaves, int level) {
 }
 // levels[0] must already hold the leaf digests; hashes up to the cap level and copies the cap to host
 int merkle_build_levels(etp_ctx* ctx, uint64_t* levels, size_t n_leaves, int cap_height, uint64_t* cap_host);
+int launch_hash_level(etp_ctx* ctx, const uint64_t* child, uint32_t parents, uint64_t* parent);
+int launch_leaf_hash_rowmajor(etp_ctx* ctx, const uint64_t* rows, int leaf_len, size_t n_leaves, uint64_t* digests);
 int merkle_prove_from_levels(etp_ctx* ctx, const uint64_t* levels, size_t n_leaves, int cap_height, size_t leaf_index,
                              uint64_t* siblings_out_host);
 int merkle_download_digests(etp_ctx* ctx, const uint64_t* levels, size_t n_leaves, int cap_height, uint64_t* out_host);

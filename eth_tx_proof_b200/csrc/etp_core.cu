@@ -262,6 +262,32 @@ int ntt_run(etp_ctx* ctx, const NttArgs& a) {
   return ETP_OK;
 }
 
+// one Merkle level: wide levels with the register-resident permutation (throughput), narrow ones with the
+// 16-thread cooperative permutation (latency) — merkle.cuh
+int launch_hash_level(etp_ctx* ctx, const uint64_t* child, uint32_t parents, uint64_t* parent) {
+  if (parents <= merkle::COOP_MAX_PARENTS) {
+    const unsigned threads = parents * poseidon::COOP_GROUP;
+    merkle::hash_level_coop<<<(threads + merkle::COOP_THREADS - 1) / merkle::COOP_THREADS, merkle::COOP_THREADS, 0, ctx->stream>>>(child, parents, parent);
+  } else {
+    merkle::hash_level<<<(parents + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(child, parents, parent);
+  }
+  ETP_LAUNCH_CHECK(ctx);
+  return ETP_OK;
+}
+// row-major leaves (MerkleTree::new on caller rows, FRI layers)
+int launch_leaf_hash_rowmajor(etp_ctx* ctx, const uint64_t* rows, int leaf_len, size_t n_leaves, uint64_t* digests) {
+  if (leaf_len > 4 && n_leaves <= merkle::COOP_MAX_PARENTS) {
+    const unsigned threads = (unsigned)n_leaves * poseidon::COOP_GROUP;
+    merkle::hash_leaves_rowmajor_coop<<<(threads + merkle::COOP_THREADS - 1) / merkle::COOP_THREADS, merkle::COOP_THREADS, 0, ctx->stream>>>(
+        rows, leaf_len, (uint32_t)n_leaves, digests);
+  } else {
+    merkle::hash_leaves_rowmajor<<<(unsigned)((n_leaves + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS), merkle::HASH_THREADS, 0, ctx->stream>>>(
+        rows, leaf_len, (uint32_t)n_leaves, digests);
+  }
+  ETP_LAUNCH_CHECK(ctx);
+  return ETP_OK;
+}
+
 // =================================================================================================
 // Merkle driver
 // =================================================================================================
@@ -271,9 +297,7 @@ int merkle_build_levels(etp_ctx* ctx, uint64_t* levels, size_t n_leaves, int cap
   while (n > ((size_t)1 << cap_height)) {
     uint64_t* nxt = cur + 4 * n;
     const uint32_t parents = (uint32_t)(n >> 1);
-    merkle::hash_level<<<(parents + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
-        cur, parents, nxt);
-    ETP_LAUNCH_CHECK(ctx);
+    ETP_TRY(launch_hash_level(ctx, cur, parents, nxt));
     cur = nxt;
     n >>= 1;
   }
@@ -412,9 +436,8 @@ extern "C" int etp_merkle_new_host(etp_ctx* ctx, const uint64_t* leaves, size_t 
   if (rc != ETP_OK) { etp_tree_free(t); return rc; }
   cudaError_t e = cudaMemcpyAsync(d.p, leaves, n_leaves * leaf_len * 8, cudaMemcpyHostToDevice, ctx->stream);
   if (e != cudaSuccess) { etp_tree_free(t); return etp_fail(ctx, ETP_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)); }
-  merkle::hash_leaves_rowmajor<<<(unsigned)((n_leaves + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS), merkle::HASH_THREADS, 0,
-                                 ctx->stream>>>(d.p, (int)leaf_len, (uint32_t)n_leaves, t->levels);
-  ctx->launches++;
+  rc = launch_leaf_hash_rowmajor(ctx, d.p, (int)leaf_len, n_leaves, t->levels);
+  if (rc != ETP_OK) { etp_tree_free(t); return rc; }
   rc = merkle_build_levels(ctx, t->levels, n_leaves, cap_height, t->cap.data());
   if (rc != ETP_OK) { etp_tree_free(t); return rc; }
   *out = t;
@@ -511,8 +534,7 @@ static int batch_finish_levels(etp_batch* b) {
   while (n > ((size_t)1 << b->cap_height)) {
     uint64_t* nxt = cur + 4 * n;
     const uint32_t parents = (uint32_t)(n >> 1);
-    merkle::hash_level<<<(parents + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(cur, parents, nxt);
-    ETP_LAUNCH_CHECK(ctx);
+    ETP_TRY(launch_hash_level(ctx, cur, parents, nxt));
     cur = nxt;
     n >>= 1;
   }

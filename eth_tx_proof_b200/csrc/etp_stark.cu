@@ -491,9 +491,7 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
     L.n_leaves = cur_n >> ARITY_BITS;
     L.cap.resize(cap_words);
     ETP_TRY(dev_alloc(ctx, levels_words(L.n_leaves, CAP_HEIGHT) * 8, (void**)&L.levels));
-    merkle::hash_leaves_rowmajor<<<blocks_for(L.n_leaves, merkle::HASH_THREADS), merkle::HASH_THREADS, 0, ctx->stream>>>(
-        L.values, 2 << ARITY_BITS, (uint32_t)L.n_leaves, L.levels);
-    ETP_LAUNCH_CHECK(ctx);
+    ETP_TRY(launch_leaf_hash_rowmajor(ctx, L.values, 2 << ARITY_BITS, L.n_leaves, L.levels));
     ETP_TRY(merkle_build_levels(ctx, L.levels, L.n_leaves, CAP_HEIGHT, L.cap.data()));
     ch.observe(L.cap.data(), cap_words);
     memcpy(w, L.cap.data(), cap_words * 8); w += cap_words;

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "poseidon.cuh"
+#include "poseidon_coop.cuh"
 
 namespace merkle {
 
@@ -137,6 +138,48 @@ static __global__ void __launch_bounds__(HASH_THREADS) hash_level(const uint64_t
   uint64_t s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
   poseidon::permute(s);
   store_digest(parent + 4 * (size_t)j, s);
+}
+
+// ---- narrow levels: one permutation per 16 threads (poseidon_coop.cuh) -----------------------------------
+// A level that cannot fill the machine costs one permutation LATENCY whatever its width (33 us with the
+// register-resident form); the cooperative form brings that to ~7 us.  Used when n <= COOP_MAX_PARENTS.
+constexpr uint32_t COOP_MAX_PARENTS = 8192;
+constexpr int COOP_THREADS = 128;  // 8 permutations per CTA
+
+__device__ __forceinline__ void coop_load_rc(uint64_t* rc_s) {
+  for (int i = threadIdx.x; i < 360; i += blockDim.x) rc_s[i] = poseidon::RC[i];
+  __syncthreads();
+}
+
+// parent[j] = two_to_one(child[2j], child[2j+1]), group g of the grid computes parent g
+static __global__ void __launch_bounds__(COOP_THREADS) hash_level_coop(const uint64_t* __restrict__ child, uint32_t n_parents,
+                                                                uint64_t* __restrict__ parent) {
+  __shared__ uint64_t rc_s[360];
+  coop_load_rc(rc_s);
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) / poseidon::COOP_GROUP;
+  const int l = threadIdx.x % poseidon::COOP_GROUP;
+  const bool live = j < n_parents;  // whole groups are live or not; dead groups still take part in the warp's shuffles
+  uint64_t x = (live && l < 8) ? child[8 * (size_t)j + l] : 0;
+  x = poseidon::permute_coop(x, l, rc_s);
+  if (live && l < 4) parent[4 * (size_t)j + l] = gl::canon(x);
+}
+
+// leaves stored row-major (n_leaves x leaf_len), leaf_len > 4: one 16-thread group per leaf, the sponge's
+// permutations in sequence (FRI layers: 32 words = 4 permutations)
+static __global__ void __launch_bounds__(COOP_THREADS) hash_leaves_rowmajor_coop(const uint64_t* __restrict__ rows, int leaf_len,
+                                                                          uint32_t n_leaves, uint64_t* __restrict__ digests) {
+  __shared__ uint64_t rc_s[360];
+  coop_load_rc(rc_s);
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / poseidon::COOP_GROUP;
+  const int l = threadIdx.x % poseidon::COOP_GROUP;
+  const bool live = i < n_leaves;
+  const uint64_t* row = rows + (size_t)i * leaf_len;
+  uint64_t x = 0;
+  for (int c0 = 0; c0 < leaf_len; c0 += 8) {
+    if (live && l < 8 && c0 + l < leaf_len) x = row[c0 + l];
+    x = poseidon::permute_coop(x, l, rc_s);
+  }
+  if (live && l < 4) digests[4 * (size_t)i + l] = gl::canon(x);
 }
 
 // level i (n_nodes nodes) -> plonky2 digest layout. num_layers = log2(n_leaves) - cap_height.
