@@ -72,6 +72,7 @@ def lib():
     sz = C.c_size_t
     L.orc_poseidon_constants.argtypes = [_u64p]
     L.orc_poseidon_permute.argtypes = [_u64p]
+    L.orc_poseidon_permute_naive.argtypes = [_u64p]
     L.orc_hash_no_pad.argtypes = [_u64p, sz, _u64p]
     L.orc_hash_or_noop.argtypes = [_u64p, sz, _u64p]
     L.orc_two_to_one.argtypes = [_u64p, _u64p, _u64p]
@@ -134,6 +135,14 @@ def poseidon_permute(state) -> np.ndarray:
     s = _u64(state).copy()
     assert s.shape == (12,)
     lib().orc_poseidon_permute(_ptr(s))
+    return s
+
+
+def poseidon_permute_naive(state) -> np.ndarray:
+    """The round-by-round definition (orc_poseidon_permute is the fast form of the same function)."""
+    s = _u64(state).copy()
+    assert s.shape == (12,)
+    lib().orc_poseidon_permute_naive(_ptr(s))
     return s
 
 

@@ -28,7 +28,8 @@ extern "C" {
 
 /* ---- poseidon.c ---- */
 void orc_poseidon_constants(uint64_t out[360]);
-void orc_poseidon_permute(uint64_t state[12]);
+void orc_poseidon_permute(uint64_t state[12]);       /* fast form (lazy reduction, split MDS) */
+void orc_poseidon_permute_naive(uint64_t state[12]); /* the definition, round by round */
 void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);
 void orc_hash_or_noop(const uint64_t *in, size_t n, uint64_t out[4]);
 void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]);

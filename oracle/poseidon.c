@@ -18,6 +18,9 @@
  */
 #include "oracle.h"
 #include <string.h>
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
 
 static uint64_t RC[360];
 static int rc_ready = 0;
@@ -98,7 +101,7 @@ static inline void mds_layer(uint64_t s[12]) {
   }
   memcpy(s, o, sizeof o);
 }
-void orc_poseidon_permute(uint64_t s[12]) {
+void orc_poseidon_permute_naive(uint64_t s[12]) {
   ensure_rc();
   int rc = 0;
   for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
@@ -115,6 +118,88 @@ void orc_poseidon_permute(uint64_t s[12]) {
     for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], RC[rc++]));
     mds_layer(s);
   }
+}
+
+
+/* ---- the same permutation, written for speed (the timed CPU baseline runs this one; tests check it against the
+ * naive definition above and the upstream known-answer vectors).  Lazy representatives (any u64) between steps,
+ * one conditional fix-up per operation as in goldilocks_field.rs, and the MDS layer on the 32-bit halves of the
+ * lanes with 64-bit accumulators, which is what upstream's vectorised (AVX2 / NEON) mds_layer does: the 12-term
+ * sums stay below 2^42, so no 128-bit arithmetic is needed and the compiler vectorises the dot products. ---- */
+static inline uint64_t f_mul(uint64_t a, uint64_t b) {
+  __uint128_t x = (__uint128_t)a * b;
+  uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64), hh = hi >> 32, hl = hi & GL_EPS;
+  /* the fix-ups are data dependent with probability ~1/2: branch-free on purpose */
+  uint64_t t0 = lo - hh;
+  t0 -= (0 - (uint64_t)(lo < hh)) & GL_EPS;
+  uint64_t t1 = hl * GL_EPS, t2 = t0 + t1;
+  t2 += (0 - (uint64_t)(t2 < t1)) & GL_EPS;
+  return t2;
+}
+static inline uint64_t f_add_canonical(uint64_t a, uint64_t b /* < p */) {
+  uint64_t s = a + b;
+  s += (0 - (uint64_t)(s < a)) & GL_EPS;
+  return s;
+}
+static inline uint64_t f_sbox7(uint64_t x) {
+  uint64_t x2 = f_mul(x, x), x4 = f_mul(x2, x2), x3 = f_mul(x, x2);
+  return f_mul(x3, x4);
+}
+static inline void f_mds_layer(uint64_t s[12]) {
+  static const uint32_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  uint64_t lo[24], hi[24], al[12], ah[12];
+  for (int i = 0; i < 12; i++) {
+    lo[i] = lo[i + 12] = (uint32_t)s[i];
+    hi[i] = hi[i + 12] = s[i] >> 32;
+  }
+#if defined(__AVX2__)
+  /* al[r] = sum_i lo[i + r] * C[i]: twelve broadcast-multiply-adds on three 4-lane vectors per half */
+  __m256i l0 = _mm256_setzero_si256(), l1 = l0, l2 = l0, h0 = l0, h1 = l0, h2 = l0;
+  for (int i = 0; i < 12; i++) {
+    const __m256i c = _mm256_set1_epi64x(C[i]);
+    l0 = _mm256_add_epi64(l0, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(lo + i)), c));
+    l1 = _mm256_add_epi64(l1, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(lo + i + 4)), c));
+    l2 = _mm256_add_epi64(l2, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(lo + i + 8)), c));
+    h0 = _mm256_add_epi64(h0, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(hi + i)), c));
+    h1 = _mm256_add_epi64(h1, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(hi + i + 4)), c));
+    h2 = _mm256_add_epi64(h2, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(hi + i + 8)), c));
+  }
+  _mm256_storeu_si256((__m256i *)al, l0); _mm256_storeu_si256((__m256i *)(al + 4), l1); _mm256_storeu_si256((__m256i *)(al + 8), l2);
+  _mm256_storeu_si256((__m256i *)ah, h0); _mm256_storeu_si256((__m256i *)(ah + 4), h1); _mm256_storeu_si256((__m256i *)(ah + 8), h2);
+#else
+  for (int r = 0; r < 12; r++) {
+    uint64_t a = 0, b = 0;
+    for (int i = 0; i < 12; i++) {
+      a += lo[i + r] * C[i];
+      b += hi[i + r] * C[i];
+    }
+    al[r] = a;
+    ah[r] = b;
+  }
+#endif
+  al[0] += 8 * lo[0]; /* MDS_MATRIX_DIAG[0] */
+  ah[0] += 8 * hi[0];
+  for (int r = 0; r < 12; r++) {
+    /* al + 2^32 ah = low + 2^64 top with top < 2^11: low + top * (2^32 - 1) */
+    uint64_t sh = ah[r] << 32, low = al[r] + sh, top = (ah[r] >> 32) + (low < sh);
+    uint64_t t1 = top * GL_EPS, t2 = low + t1;
+    t2 += (0 - (uint64_t)(t2 < t1)) & GL_EPS;
+    s[r] = t2;
+  }
+}
+void orc_poseidon_permute(uint64_t s[12]) {
+  ensure_rc();
+  const uint64_t *rc = RC;
+  for (int r = 0; r < 30; r++, rc += 12) {
+    for (int i = 0; i < 12; i++) s[i] = f_add_canonical(s[i], rc[i]);
+    if (r < 4 || r >= 26) {
+      for (int i = 0; i < 12; i++) s[i] = f_sbox7(s[i]);
+    } else {
+      s[0] = f_sbox7(s[0]);
+    }
+    f_mds_layer(s);
+  }
+  for (int i = 0; i < 12; i++) s[i] = gl_canon(s[i]);
 }
 
 /* hash_n_to_m_no_pad with m = 4: zero state, overwrite rate lanes chunk by chunk, permute each chunk */

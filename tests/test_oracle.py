@@ -187,3 +187,19 @@ def test_fri_fold_matches_definition():
         for j in range(1 << ab):
             acc = R.e_add(acc, R.e_mul(coeffs[(k << ab) + j], R.e_pow(beta, j)))
         assert (int(got[k][0]), int(got[k][1])) == acc
+
+
+def test_fast_permutation_equals_the_naive_definition():
+    """orc_poseidon_permute (lazy reduction, split MDS: the form the timed CPU baseline runs) against the
+    round-by-round definition, on edge states and random ones."""
+    import random
+
+    import oracle
+
+    rng = random.Random(11)
+    p = 0xFFFFFFFF00000001
+    edge = [[0] * 12, [p - 1] * 12, [2**64 - 1] * 12, [2**32 - 1] * 12, [2**32] * 12, [p] * 12, [0xFFFFFFFF00000000] * 12]
+    for st in edge + [[rng.randrange(2**64) for _ in range(12)] for _ in range(500)]:
+        a = oracle.poseidon_permute(np.array(st, dtype=np.uint64))
+        b = oracle.poseidon_permute_naive(np.array(st, dtype=np.uint64))
+        assert (a == b).all() and (a < np.uint64(p)).all()
