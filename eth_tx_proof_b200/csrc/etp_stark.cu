@@ -188,11 +188,10 @@ int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, c
   out1.assign(np, gl::ext(0, 0));
   if (np == 0) return ETP_OK;
   const unsigned gx = blocks_for(n, stark::OPEN_THREADS * stark::OPEN_CHUNK);
-  const unsigned gy = (np + stark::OPEN_POLYS - 1) / stark::OPEN_POLYS;
+  const unsigned gy = (unsigned)np;
   DevBuf<uint64_t> partial(ctx);
   ETP_TRY(partial.alloc((size_t)gx * np * 4));
-  stark::eval_polys_at_two_points<<<dim3(gx, gy), stark::OPEN_THREADS, 0, ctx->stream>>>(b->coeffs, b->n(), np, n, t0, t1, z0, z1,
-                                                                                         partial.p);
+  stark::eval_polys_at_two_points<<<dim3(gx, gy), stark::OPEN_THREADS, 0, ctx->stream>>>(b->coeffs, b->n(), np, n, t0, t1, partial.p);
   ETP_LAUNCH_CHECK(ctx);
   std::vector<uint64_t> host((size_t)gx * np * 4);
   ETP_CUDA(ctx, cudaMemcpyAsync(host.data(), partial.p, host.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));

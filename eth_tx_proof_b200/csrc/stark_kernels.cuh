@@ -263,47 +263,74 @@ struct ExtPowTable {
     return gl::emul(gl::ext(hi[2 * a], hi[2 * a + 1]), gl::ext(lo[2 * b], lo[2 * b + 1]));
   }
 };
-constexpr int OPEN_THREADS = 256, OPEN_CHUNK = 16, OPEN_POLYS = 8;
-// grid: (n / (OPEN_THREADS*OPEN_CHUNK), ceil(n_polys / OPEN_POLYS)); each thread walks OPEN_CHUNK consecutive
-// coefficients, keeping z^i for both points, for OPEN_POLYS polynomials at once.
+constexpr int OPEN_THREADS = 256, OPEN_CHUNK = 32;
+// 192-bit lazy accumulator for dot products of field elements: sum of <= 2^32 products of two u64, reduced once.
+struct Acc192 {
+  uint64_t w0, w1;
+  uint32_t w2;
+};
+__device__ __forceinline__ void mac192(Acc192& a, uint64_t c, uint64_t u) {
+  const unsigned __int128 p = (unsigned __int128)c * u;
+  const uint64_t pl = (uint64_t)p, ph = (uint64_t)(p >> 64);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(a.w0), "+l"(a.w1), "+r"(a.w2) : "l"(pl), "l"(ph));
+}
+// w0 + 2^64 w1 + 2^128 w2 with 2^128 == -2^32 (mod p); w2 < 2^31
+__device__ __forceinline__ uint64_t reduce192(const Acc192& a) {
+  return gl::sub_c(gl::reduce128(a.w0, a.w1), (uint64_t)a.w2 << 32);
+}
+// grid: (ceil(n / (OPEN_THREADS*OPEN_CHUNK)), n_polys).  Thread t of a block owns the strip of OPEN_CHUNK consecutive
+// coefficients starting at s = (block * OPEN_THREADS + t) * OPEN_CHUNK of ONE polynomial and computes
+//   z^s * sum_b c_{s+b} z^b   for z = z0 and z = z1,
+// the inner sums as four dot products (two extension components x two points) against the shared table z^b, b < OPEN_CHUNK,
+// accumulated WITHOUT modular reduction (192-bit), i.e. 4 wide multiply-adds per coefficient instead of 4 field
+// multiplications + 4 field additions.  The block then adds its strips; the host adds the blocks.
 static __global__ void __launch_bounds__(OPEN_THREADS) eval_polys_at_two_points(const uint64_t* __restrict__ coeffs, size_t col_stride,
                                                                                 int n_polys, uint32_t n, ExtPowTable t0, ExtPowTable t1,
-                                                                                gl::Ext z0, gl::Ext z1, uint64_t* __restrict__ partial) {
+                                                                                uint64_t* __restrict__ partial) {
+  __shared__ uint64_t pw[OPEN_CHUNK * 4];
   __shared__ uint64_t sh[OPEN_THREADS * 4];
-  const int poly0 = blockIdx.y * OPEN_POLYS;
+  const int poly = blockIdx.y;
+  if (threadIdx.x < OPEN_CHUNK) {
+    const gl::Ext a = gl::ecanon(t0.get(threadIdx.x)), b = gl::ecanon(t1.get(threadIdx.x));
+    pw[4 * threadIdx.x + 0] = a.c0; pw[4 * threadIdx.x + 1] = a.c1;
+    pw[4 * threadIdx.x + 2] = b.c0; pw[4 * threadIdx.x + 3] = b.c1;
+  }
+  __syncthreads();
   const uint32_t start = (blockIdx.x * OPEN_THREADS + threadIdx.x) * OPEN_CHUNK;
-  gl::Ext a0[OPEN_POLYS], a1[OPEN_POLYS];
-#pragma unroll
-  for (int q = 0; q < OPEN_POLYS; q++) { a0[q] = gl::ext(0, 0); a1[q] = gl::ext(0, 0); }
+  gl::Ext r0 = gl::ext(0, 0), r1 = gl::ext(0, 0);
   if (start < n) {
-    gl::Ext p0 = t0.get(start), p1 = t1.get(start);
-    for (int k = 0; k < OPEN_CHUNK; k++) {
+    Acc192 a[4] = {};
+    const uint64_t* __restrict__ src = coeffs + (size_t)poly * col_stride + start;
+    const int len = (n - start) < (uint32_t)OPEN_CHUNK ? (int)(n - start) : OPEN_CHUNK;
+    if (len == OPEN_CHUNK) {
+#pragma unroll 4
+      for (int b = 0; b < OPEN_CHUNK; b += 2) {
+        const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(src + b));
 #pragma unroll
-      for (int q = 0; q < OPEN_POLYS; q++) {
-        if (poly0 + q < n_polys) {
-          const uint64_t c = __ldg(coeffs + (size_t)(poly0 + q) * col_stride + start + k);
-          a0[q] = gl::eadd(a0[q], gl::emul_base(p0, c));
-          a1[q] = gl::eadd(a1[q], gl::emul_base(p1, c));
+        for (int w = 0; w < 4; w++) {
+          mac192(a[w], c.x, pw[4 * b + w]);
+          mac192(a[w], c.y, pw[4 * b + 4 + w]);
         }
       }
-      p0 = gl::emul(p0, z0);
-      p1 = gl::emul(p1, z1);
+    } else {
+      for (int b = 0; b < len; b++) {
+        const uint64_t c = __ldg(src + b);
+#pragma unroll
+        for (int w = 0; w < 4; w++) mac192(a[w], c, pw[4 * b + w]);
+      }
     }
+    r0 = gl::emul(gl::ext(reduce192(a[0]), reduce192(a[1])), t0.get(start));
+    r1 = gl::emul(gl::ext(reduce192(a[2]), reduce192(a[3])), t1.get(start));
   }
-  // block reduction, one polynomial at a time
-  for (int q = 0; q < OPEN_POLYS; q++) {
-    if (poly0 + q >= n_polys) break;
-    sh[4 * threadIdx.x + 0] = a0[q].c0; sh[4 * threadIdx.x + 1] = a0[q].c1;
-    sh[4 * threadIdx.x + 2] = a1[q].c0; sh[4 * threadIdx.x + 3] = a1[q].c1;
-    __syncthreads();
-    for (int s = OPEN_THREADS / 2; s > 0; s >>= 1) {
-      if (threadIdx.x < s)
-        for (int w = 0; w < 4; w++) sh[4 * threadIdx.x + w] = gl::add(sh[4 * threadIdx.x + w], sh[4 * (threadIdx.x + s) + w]);
-      __syncthreads();
-    }
-    if (threadIdx.x < 4) partial[((size_t)blockIdx.x * n_polys + poly0 + q) * 4 + threadIdx.x] = gl::canon(sh[threadIdx.x]);
+  sh[4 * threadIdx.x + 0] = r0.c0; sh[4 * threadIdx.x + 1] = r0.c1;
+  sh[4 * threadIdx.x + 2] = r1.c0; sh[4 * threadIdx.x + 3] = r1.c1;
+  __syncthreads();
+  for (int s = OPEN_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s)
+      for (int w = 0; w < 4; w++) sh[4 * threadIdx.x + w] = gl::add(sh[4 * threadIdx.x + w], sh[4 * (threadIdx.x + s) + w]);
     __syncthreads();
   }
+  if (threadIdx.x < 4) partial[((size_t)blockIdx.x * n_polys + poly) * 4 + threadIdx.x] = gl::canon(sh[threadIdx.x]);
 }
 
 // ---- prove_openings in evaluation form -----------------------------------------------------------
@@ -385,16 +412,23 @@ static __global__ void __launch_bounds__(128) fri_fold16(FoldParams f) {
     const ulonglong2 e = reinterpret_cast<const ulonglong2*>(f.in)[16 * (size_t)j + t];
     v[gl::bitrev32(t, 4)] = gl::ext(e.x, e.y);  // natural order m = bitrev4(t)
   }
-  const gl::Ext gamma = gl::emul_base(f.beta, f.x0_inv.get(gl::bitrev32(j, f.log_n - 4)));
-  // result = (1/16) * sum_i gamma^i * sum_m v_m w16^(-i m): Horner over i from 15 down to 0
-  gl::Ext acc = gl::ext(0, 0);
-#pragma unroll 1
-  for (int i = 15; i >= 0; i--) {
-    gl::Ext u = gl::ext(0, 0);
+  gl::Ext gamma = gl::emul_base(f.beta, f.x0_inv.get(gl::bitrev32(j, f.log_n - 4)));
+  // result = (1/16) * sum_i gamma^i * sum_m v_m w16^(-i m), computed as four arity-2 folds with gamma, gamma^2,
+  // gamma^4, gamma^8:  v'[m] = (v[m] + v[m+h]) + gamma_k * (v[m] - v[m+h]) * w_{2h}^(-m)   (15 pair folds instead of
+  // the 16 x 16 matrix; same field elements)
 #pragma unroll
-    for (int m = 0; m < 16; m++) u = gl::eadd(u, gl::emul_base(v[m], f.w16_inv_pows[(i * m) & 15]));
-    acc = gl::eadd(gl::emul(acc, gamma), u);
+  for (int k = 0; k < 4; k++) {
+    const int h = 8 >> k;
+#pragma unroll
+    for (int m = 0; m < h; m++) {
+      const gl::Ext a = v[m], c = v[m + h];
+      gl::Ext d = gl::esub(a, c);
+      if (m) d = gl::emul_base(d, f.w16_inv_pows[m << k]);
+      v[m] = gl::eadd(gl::eadd(a, c), gl::emul(d, gamma));
+    }
+    if (k < 3) gamma = gl::emul(gamma, gamma);
   }
+  gl::Ext acc = v[0];
   acc = gl::ecanon(gl::emul_base(acc, f.inv16));
   reinterpret_cast<ulonglong2*>(f.out)[j] = make_ulonglong2(acc.c0, acc.c1);
 }
