@@ -58,6 +58,8 @@ def load_library():
         "etp_ctx_synchronize": (i32, [vp]),
         "etp_ctx_stream": (vp, [vp]),
         "etp_ctx_launch_count": (C.c_uint64, [vp]),
+        "etp_ctx_trim": (i32, [vp]),
+        "etp_ctx_cached_bytes": (C.c_size_t, [vp]),
         "etp_dev_alloc": (i32, [vp, sz, pp]),
         "etp_dev_free": (i32, [vp, vp]),
         "etp_dev_upload": (i32, [vp, vp, vp, sz]),
@@ -181,6 +183,14 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.L.etp_ctx_launch_count(self.h))
+
+    def trim(self):
+        """Return the context's cached device blocks to the CUDA runtime (etp_ctx_trim)."""
+        self.check(self.L.etp_ctx_trim(self.h))
+
+    @property
+    def cached_bytes(self) -> int:
+        return int(self.L.etp_ctx_cached_bytes(self.h))
 
     # ---- primitives (parity tests)
     def poseidon_permute(self, states) -> np.ndarray:

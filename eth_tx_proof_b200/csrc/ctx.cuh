@@ -8,6 +8,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/etp_b200.h"
@@ -43,7 +44,16 @@ struct etp_ctx {
   std::vector<std::pair<const char*, float>> timings;
   uint64_t* d_pow_result = nullptr;  // PoW grind result slot
   std::vector<RegisteredTable*> tables;  // program-defined tables, id = ETP_TABLE_FIRST_REGISTERED + index
+  // Block cache behind dev_alloc / dev_free.  Everything a context does is ordered on `stream`, so a block released
+  // by dev_free may be handed out again at once: its next use is enqueued behind its last one.  Proofs and commits of
+  // a shape seen before therefore allocate nothing (measured: with cudaMallocAsync pools single proofs at 2^22 rows
+  // jittered between 55 and 900 ms).  Blocks are matched by size (<= 12.5 % slack); on out-of-memory the cache is
+  // emptied and the allocation retried; etp_ctx_trim() empties it on request.
+  std::multimap<size_t, void*> cache_free;
+  std::unordered_map<void*, size_t> cache_live;
+  size_t cache_free_bytes = 0;
 };
+int dev_cache_trim(etp_ctx* ctx);
 void free_registered_tables(etp_ctx* ctx);  // etp_stark.cu
 int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubin_out, std::string* log_out);
 int jit_load(etp_ctx* ctx, const std::vector<char>& cubin, const char* entry, JitKernel* out);
@@ -78,13 +88,40 @@ inline int etp_fail(etp_ctx* ctx, int code, const char* fmt, ...) {
   } while (0)
 
 inline int dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
-  if (bytes == 0) bytes = 8;
+  bytes = (bytes + 511) & ~(size_t)511;
+  if (bytes == 0) bytes = 512;
+  auto it = ctx->cache_free.lower_bound(bytes);
+  if (it != ctx->cache_free.end() && it->first <= bytes + bytes / 8) {
+    *out = it->second;
+    ctx->cache_live[*out] = it->first;
+    ctx->cache_free_bytes -= it->first;
+    ctx->cache_free.erase(it);
+    return ETP_OK;
+  }
   ETP_CUDA(ctx, cudaSetDevice(ctx->device));
-  ETP_CUDA(ctx, cudaMallocAsync(out, bytes, ctx->stream));
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try once more
+    cudaGetLastError();
+    ETP_TRY(dev_cache_trim(ctx));
+    e = cudaMalloc(out, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return etp_fail(ctx, ETP_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+  }
+  ctx->cache_live[*out] = bytes;
   return ETP_OK;
 }
 inline void dev_free(etp_ctx* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->cache_live.find(p);
+  if (it == ctx->cache_live.end()) {  // not ours (never happens for dev_alloc'ed memory): hand it to the runtime
+    cudaFree(p);
+    return;
+  }
+  ctx->cache_free.emplace(it->second, p);
+  ctx->cache_free_bytes += it->second;
+  ctx->cache_live.erase(it);
 }
 template <class T>
 struct DevBuf {  // RAII scratch on the context's stream-ordered pool

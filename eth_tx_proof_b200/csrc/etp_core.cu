@@ -26,12 +26,6 @@ extern "C" int etp_ctx_create(int device, etp_ctx** out) {
     delete ctx;
     return ETP_ERR_CUDA;
   }
-  // keep freed blocks in the stream-ordered pool: repeated commits of the same shape do not re-allocate
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void**)&ctx->d_pow_result, 16) != cudaSuccess) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -43,6 +37,21 @@ extern "C" int etp_ctx_create(int device, etp_ctx** out) {
   return ETP_OK;
 }
 
+// returns every cached (free) block to the runtime; live blocks are untouched
+int dev_cache_trim(etp_ctx* ctx) {
+  ETP_CUDA(ctx, cudaSetDevice(ctx->device));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& kv : ctx->cache_free) cudaFree(kv.second);
+  ctx->cache_free.clear();
+  ctx->cache_free_bytes = 0;
+  return ETP_OK;
+}
+extern "C" int etp_ctx_trim(etp_ctx* ctx) {
+  if (!ctx) return ETP_ERR_INVALID;
+  return dev_cache_trim(ctx);
+}
+extern "C" size_t etp_ctx_cached_bytes(const etp_ctx* ctx) { return ctx ? ctx->cache_free_bytes : 0; }
+
 extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -51,6 +60,8 @@ extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
   for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
   for (auto& kv : ctx->full_tables) cudaFree(kv.second);
   cudaFree(ctx->d_pow_result);
+  dev_cache_trim(ctx);
+  for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // objects the caller never freed
   for (auto e : ctx->sync_events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);

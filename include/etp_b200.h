@@ -53,6 +53,11 @@ int etp_ctx_synchronize(etp_ctx *ctx);
 void *etp_ctx_stream(etp_ctx *ctx);
 /* number of kernel launches issued by this context since creation */
 uint64_t etp_ctx_launch_count(const etp_ctx *ctx);
+/* Device scratch of a context comes from a per-context block cache (a released block is reused by the next
+ * allocation of about the same size, so proofs / commits of a shape seen before allocate nothing).
+ * etp_ctx_trim returns the cached blocks to the CUDA runtime; etp_ctx_cached_bytes reports how much is held. */
+int etp_ctx_trim(etp_ctx *ctx);
+size_t etp_ctx_cached_bytes(const etp_ctx *ctx);
 /* device memory helpers (cudaMalloc / cudaFree / cudaMemcpyAsync on the context's stream + sync) */
 int etp_dev_alloc(etp_ctx *ctx, size_t bytes, void **out);
 int etp_dev_free(etp_ctx *ctx, void *ptr);

@@ -203,3 +203,25 @@ def test_from_values_dev_and_properties_at_baseline_size(ctx):
     o = oracle.Batch.from_values(host, 1, 4)
     assert (ba.polynomials[:3] == o.coeffs).all()
     assert (ba.leaves_at(idx)[:, :3] == o.leaves[idx]).all()
+
+
+def test_block_cache_reuses_and_trims(ctx):
+    """dev_alloc / dev_free go through the context's block cache: a second commit of the same shape allocates nothing new,
+    etp_ctx_trim gives the cached blocks back, and results do not depend on whether a block is fresh or reused."""
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import synthetic as syn
+
+    vals = syn.random_columns(9, 11, seed=5)
+    b1 = etp.PolynomialBatch.from_values(ctx, vals, 1, False, 4)
+    cap1 = b1.cap.copy()
+    del b1
+    held = ctx.cached_bytes
+    assert held >= 9 * (1 << 11) * 8 * 3  # coefficients + LDE of the freed batch are cached
+    b2 = etp.PolynomialBatch.from_values(ctx, vals, 1, False, 4)
+    assert ctx.cached_bytes < held  # served from the cache
+    assert (b2.cap == cap1).all()
+    del b2
+    ctx.trim()
+    assert ctx.cached_bytes == 0
+    b3 = etp.PolynomialBatch.from_values(ctx, vals, 1, False, 4)
+    assert (b3.cap == cap1).all()

@@ -7,7 +7,7 @@ ctx = etp.Context(0)
 log_n = 22
 t = torch.from_numpy(syn.memory_trace(log_n).view(np.int64)).cuda()
 torch.cuda.synchronize()
-for rep in range(8):
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 8):
     t0 = time.perf_counter()
     ctx.stark_prove_dev(etp.TABLE_MEMORY, log_n, t.data_ptr(), 1 << log_n)
     dt = time.perf_counter() - t0
