@@ -190,6 +190,7 @@ def test_from_values_dev_and_properties_at_baseline_size(ctx):
     a = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g)
     b_ = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g)
     s = a + b_  # < 2^63 < p: plain integer sum == field sum
+    torch.cuda.synchronize()  # the library works on its own (non-blocking) stream
     ba = etp.PolynomialBatch.from_values_dev(ctx, a.data_ptr(), n, cols, log_n, 1, False, 4)
     bb = etp.PolynomialBatch.from_values_dev(ctx, b_.data_ptr(), n, cols, log_n, 1, False, 4)
     bs = etp.PolynomialBatch.from_values_dev(ctx, s.data_ptr(), n, cols, log_n, 1, False, 4)
@@ -225,3 +226,47 @@ def test_block_cache_reuses_and_trims(ctx):
     assert ctx.cached_bytes == 0
     b3 = etp.PolynomialBatch.from_values(ctx, vals, 1, False, 4)
     assert (b3.cap == cap1).all()
+
+
+def test_properties_at_the_full_baseline_size(ctx):
+    """BASELINE.json configs[1] at its full size, 2^22 x 128, rate_bits 1, cap_height 4 (the oracle would need minutes for the
+    whole batch): size-independent properties — the commitment is linear on sampled leaf rows, sampled Merkle paths verify
+    to the cap, the cap is reproducible, and three columns agree with the oracle's ifft / coset LDE word for word."""
+    import torch
+
+    import eth_tx_proof_b200 as etp
+    import oracle
+
+    log_n, cols = 22, 128
+    n = 1 << log_n
+    g = torch.Generator(device="cuda").manual_seed(22)
+    a = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g)
+    b_ = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g)
+    idx = [0, 1, 2, 987654, n - 1, n, n + 1, (2 << log_n) - 1]
+    torch.cuda.synchronize()  # the library works on its own (non-blocking) stream
+    ba = etp.PolynomialBatch.from_values_dev(ctx, a.data_ptr(), n, cols, log_n, 1, False, 4)
+    ra, cap_a = ba.leaves_at(idx).astype(object), ba.cap.copy()
+    # three columns against the oracle: coefficients and the whole LDE column in leaf (bit-reversed) order
+    host = a[[0, 63, 127]].cpu().numpy().astype(np.uint64)
+    want_coeffs = np.stack([oracle.ifft(c) for c in host])
+    for k, c in enumerate([0, 63, 127]):
+        lde = oracle.lde(want_coeffs[k], 1)  # natural order: value k = P(7 w^k)
+        for q, i in enumerate(idx):
+            assert int(ra[q][c]) == int(lde[int(format(i, f"0{log_n + 1}b")[::-1], 2)])
+    for i in idx[:4]:
+        assert oracle.merkle_verify(ba.leaves_at([i])[0], i, ba.prove(i), ba.cap)
+    ba.recommit_values_dev(a.data_ptr(), n)
+    assert (ba.cap == cap_a).all()
+    del ba
+    bb = etp.PolynomialBatch.from_values_dev(ctx, b_.data_ptr(), n, cols, log_n, 1, False, 4)
+    rb = bb.leaves_at(idx).astype(object)
+    del bb
+    s = a + b_  # < 2^63 < p: plain integer sum == field sum
+    torch.cuda.synchronize()
+    del a, b_
+    bs = etp.PolynomialBatch.from_values_dev(ctx, s.data_ptr(), n, cols, log_n, 1, False, 4)
+    rs = bs.leaves_at(idx).astype(object)
+    assert ((ra + rb) % P == rs).all()
+    assert oracle.merkle_verify(bs.leaves_at([idx[-1]])[0], idx[-1], bs.prove(idx[-1]), bs.cap)
+    del bs
+    ctx.trim()
