@@ -370,3 +370,81 @@ def rangecheck_trace(log_n: int, n_limbs: int = 7, seed: int = 5) -> np.ndarray:
     t[L["FREQ"]] = freq.astype(np.uint64)
     t[L["PROD"]] = (t[0].astype(object) * t[1].astype(object) % P).astype(np.uint64)
     return t
+
+
+# ---- shape-only stand-ins for the evm_arithmetization tables ---------------------------------------------------
+# The sources of the seven tables the reference proves (/root/reference/ops/src/lib.rs:52 -> evm_arithmetization::
+# {arithmetic, byte_packing, cpu, keccak, keccak_sponge, logic, memory}) are not available offline (hard
+# part 1).  What a prover's cost depends on is their SHAPE: trace width, number and degree of the constraints, logUp
+# lookups.  `shape_program` builds a table of a given width whose constraints have that profile and that a generated
+# trace satisfies:  column 0 is a row counter (first-row + transition constraint); with `n_lookup` > 0, column 1 holds
+# multiplicities and columns 2 .. 2 + n_lookup are limbs range-checked against the counter (logUp, chunked helpers);
+# the remaining columns come in groups (a, b, d, c) with c = a*b + d, every fifth group c = a*b*d (degree 3), and up to
+# three trailing boolean flags.  The widths below are the approximate upstream ones.
+EVM_TABLE_SHAPES = {          # name: (trace columns, range-checked limbs)
+    "arithmetic": (112, 16),
+    "byte_packing": (80, 8),
+    "cpu": (128, 0),
+    "keccak": (2400, 0),
+    "keccak_sponge": (424, 8),
+}
+
+
+def shape_layout(n_cols: int, n_lookup: int = 0):
+    first = 1 + (1 + n_lookup if n_lookup else 0)
+    assert n_cols >= first + 4
+    n_groups = (n_cols - first) // 4
+    return {"COUNTER": 0, "FREQ": 1 if n_lookup else None, "LIMB": 2 if n_lookup else None, "n_lookup": n_lookup,
+            "GROUP": first, "n_groups": n_groups, "FLAG": first + 4 * n_groups, "n_flags": n_cols - first - 4 * n_groups,
+            "cols": n_cols}
+
+
+def shape_program(n_cols: int, n_lookup: int = 0, emit_lookups: bool = True) -> Program:
+    """emit_lookups=False leaves the logUp constraints out (for Program.check_trace, which has no auxiliary columns)."""
+    L = shape_layout(n_cols, n_lookup)
+    b = ProgramBuilder(n_cols, 0, 3)
+    lv, one = b.lv, b.const(1)
+    b.first_row(lv(0))
+    b.transition(b.nv(0) - lv(0) - 1)
+    for g in range(L["n_groups"]):
+        a, bb, d, c = (lv(L["GROUP"] + 4 * g + k) for k in range(4))
+        b.constraint(c - a * bb * d if g % 5 == 4 else c - (a * bb + d))
+    for f in range(L["n_flags"]):
+        fl = lv(L["FLAG"] + f)
+        b.constraint(fl * (fl - one))
+    if n_lookup and emit_lookups:
+        b.add_lookup(list(range(L["LIMB"], L["LIMB"] + n_lookup)), L["COUNTER"], L["FREQ"])
+        b.emit_lookup_constraints()
+    return b.build()
+
+
+def shape_trace(log_n: int, n_cols: int, n_lookup: int = 0, seed: int = 23) -> np.ndarray:
+    """A trace that satisfies shape_program(n_cols, n_lookup): operands below 2^20, so every product fits 64 bits."""
+    from .synthetic import _rand
+
+    L = shape_layout(n_cols, n_lookup)
+    n = 1 << log_n
+    t = np.zeros((n_cols, n), dtype=np.uint64)
+    t[0] = np.arange(n, dtype=np.uint64)
+    if n_lookup:
+        freq = np.zeros(n, dtype=np.int64)
+        for j in range(n_lookup):
+            v = (_rand(seed, 1000 + j, n) % np.uint64(n)).astype(np.int64)
+            t[L["LIMB"] + j] = v.astype(np.uint64)
+            freq += np.bincount(v, minlength=n)
+        t[L["FREQ"]] = freq.astype(np.uint64)
+    m = np.uint64((1 << 20) - 1)
+    for g in range(L["n_groups"]):
+        c0 = L["GROUP"] + 4 * g
+        a, bb, d = (_rand(seed, 3 * g + k, n) & m for k in range(3))
+        t[c0], t[c0 + 1], t[c0 + 2] = a, bb, d
+        t[c0 + 3] = a * bb * d if g % 5 == 4 else a * bb + d
+    for f in range(L["n_flags"]):
+        t[L["FLAG"] + f] = _rand(seed, 5000 + f, n) & np.uint64(1)
+    return t
+
+
+# degree bits of the seven tables in a small transaction: the low end of the reference's circuit ranges
+# (/root/reference/README.md:53-59: arithmetic 15.., byte packing 9.., cpu 12.., keccak 14.., keccak sponge 9..,
+# logic 12.., memory 17..), one notch up for the tables an ETH transfer actually exercises
+TX_TABLE_DEGREE_BITS = {"arithmetic": 16, "byte_packing": 10, "cpu": 14, "keccak": 14, "keccak_sponge": 10, "logic": 12, "memory": 18}

@@ -5,7 +5,8 @@
 // duplex sponge in overwrite mode, rate 8, challenges popped from the END of the output buffer; and
 // `PoseidonPermutation::permute` (plonky2/src/hash/poseidon.rs) — crate pinned at
 // /root/reference/Cargo.lock:3441, reached from /root/reference/ops/src/lib.rs:52.
-// The transcript sequences every phase of the prover but costs microseconds, so it stays on the host;
+// The transcript is strictly sequential, so it stays on a host core (host_poseidon.cpp: ~3 us per permutation;
+// a 2400-column table makes the challenger absorb ~9600 opening words = 1200 permutations);
 // each FRI layer costs one cap download (512 B) and nothing is uploaded but the 16-byte beta.
 // This is NOT the oracle: nothing here includes oracle/.
 #pragma once
@@ -18,34 +19,12 @@
 
 namespace hostf {
 
-inline const uint64_t* round_constants() {
-  static const uint64_t RC[360] = ETP_POSEIDON_RC_TABLE;
-  return RC;
-}
+}  // namespace hostf
+// host_poseidon.cpp (plain C++, AVX2 when the CPU has it): in place, any u64 in, canonical out
+extern "C" void etp_host_poseidon_permute(uint64_t s[12]);
+namespace hostf {
 
-inline uint64_t sbox7(uint64_t x) {
-  uint64_t x2 = gl::mul(x, x), x4 = gl::mul(x2, x2), x3 = gl::mul(x, x2);
-  return gl::mul(x3, x4);
-}
-
-inline void poseidon(uint64_t s[12]) {
-  static const uint64_t C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-  const uint64_t* rc = round_constants();
-  for (int r = 0; r < 30; r++) {
-    for (int i = 0; i < 12; i++) s[i] = gl::add(s[i], rc[12 * r + i]);
-    if (r < 4 || r >= 26) { for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]); }
-    else s[0] = sbox7(s[0]);
-    uint64_t o[12];
-    for (int row = 0; row < 12; row++) {
-      unsigned __int128 acc = 0;
-      for (int i = 0; i < 12; i++) acc += (unsigned __int128)gl::canon(s[(i + row) % 12]) * C[i];
-      if (row == 0) acc += (unsigned __int128)gl::canon(s[0]) * 8;
-      o[row] = gl::reduce128((uint64_t)acc, (uint64_t)(acc >> 64));
-    }
-    memcpy(s, o, sizeof o);
-  }
-  for (int i = 0; i < 12; i++) s[i] = gl::canon(s[i]);
-}
+inline void poseidon(uint64_t s[12]) { etp_host_poseidon_permute(s); }
 
 struct Challenger {
   uint64_t state[12] = {0};

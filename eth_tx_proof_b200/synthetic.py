@@ -132,3 +132,23 @@ def memory_trace(log_n: int, seed: int = 7, dummy_rows: int | None = None) -> np
     t[M_COUNTER] = np.arange(n, dtype=np.uint64)
     t[M_FREQ] = np.bincount(rc, minlength=n).astype(np.uint64)
     return t
+
+
+def tx_job_tables(scale_bits: int = 0):
+    """The seven table proofs of one synthetic transaction: [(name, program or None, degree_bits, trace)] in the order the
+    reference's AllStark lists its tables.  `program` is a cprog.Program to register (shape-only stand-ins of the
+    evm_arithmetization tables, cprog.EVM_TABLE_SHAPES, and the 523-column logic table) or None for the built-in memory
+    table; degree bits = cprog.TX_TABLE_DEGREE_BITS + scale_bits.  Shape only: no cross-table lookups, no recursion."""
+    from . import cprog
+
+    out = []
+    for name in ("arithmetic", "byte_packing", "cpu", "keccak", "keccak_sponge", "logic", "memory"):
+        bits = max(5, cprog.TX_TABLE_DEGREE_BITS[name] + scale_bits)
+        if name == "memory":
+            out.append((name, None, bits, memory_trace(bits, seed=31)))
+        elif name == "logic":
+            out.append((name, cprog.logic_program(8), bits, cprog.logic_trace(bits, 8, seed=37)))
+        else:
+            cols, lk = cprog.EVM_TABLE_SHAPES[name]
+            out.append((name, cprog.shape_program(cols, lk), bits, cprog.shape_trace(bits, cols, lk, seed=41)))
+    return out

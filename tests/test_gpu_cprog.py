@@ -130,3 +130,24 @@ def test_register_misuse(ctx):
         ctx.register_table(prog, [([18], 19, 99)])              # column out of range
     with pytest.raises(etp.EtpError):
         ctx.stark_prove(40, np.zeros((21, 64), dtype=np.uint64))  # unknown table id
+
+
+@pytest.mark.parametrize("n_cols,n_lookup,log_n", [(9, 0, 5), (37, 3, 7), (80, 8, 9), (263, 0, 6)])
+def test_shape_tables_prove_like_the_oracle(ctx, n_cols, n_lookup, log_n):
+    """Shape-only stand-ins of the evm_arithmetization tables (cprog.shape_program): proofs bit-identical to the oracle's
+    interpreter, accepted by the verifier; a trace that breaks one product relation is rejected."""
+    import oracle
+    import stark_verifier as V
+    from eth_tx_proof_b200 import cprog
+
+    prog = cprog.shape_program(n_cols, n_lookup)
+    tid = ctx.register_table(prog, prog.lookups)
+    oid = oracle.register_table(prog, prog.lookups)
+    t = cprog.shape_trace(log_n, n_cols, n_lookup)
+    proof = ctx.stark_prove(tid, t)
+    assert (proof[2:] == oracle.stark_prove(oid, t)[2:]).all()
+    V.verify(proof, program=prog, max_queries=2)
+    bad = t.copy()
+    bad[cprog.shape_layout(n_cols, n_lookup)["GROUP"] + 3, 3] += np.uint64(1)
+    with pytest.raises((Exception,)):
+        V.verify(ctx.stark_prove(tid, bad), program=prog, max_queries=2)

@@ -92,3 +92,35 @@ def test_synthetic_traces_are_deterministic_and_valid():
     assert oracle.check_constraints(oracle.TABLE_MEMORY, a) == -1
     c = syn.random_columns(3, 8)
     assert (c < np.uint64(0xFFFFFFFF00000001)).all()
+
+
+def test_host_transcript_permutation_matches_the_known_answers_and_the_oracle():
+    """The product's host-side Poseidon (csrc/host_poseidon.cpp, used by the Fiat-Shamir Challenger) needs no GPU: check it
+    against the upstream known-answer vectors and against the oracle on edge and random states."""
+    import json
+    import random
+
+    import numpy as np
+
+    import eth_tx_proof_b200 as etp
+    import oracle
+
+    L = etp.load_library()
+    fn = L.etp_host_poseidon_permute
+    fn.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+    fn.restype = None
+
+    def perm(st):
+        a = (ctypes.c_uint64 * 12)(*[int(x) for x in st])
+        fn(a)
+        return [int(x) for x in a]
+
+    p = 0xFFFFFFFF00000001
+    with open(os.path.join(ROOT, "tests", "golden", "poseidon_kat.json")) as f:
+        kat = json.load(f)
+    inputs = {"zeros": [0] * 12, "range12": list(range(12)), "neg_one": [p - 1] * 12}
+    for v in kat["permutation"]:
+        assert perm(inputs[v["input"]]) == [int(x, 16) for x in v["output"]]
+    rng = random.Random(5)
+    for st in [[2**64 - 1] * 12, [p] * 12, [2**32 - 1] * 12, [0xFFFFFFFF00000000] * 12] + [[rng.randrange(2**64) for _ in range(12)] for _ in range(300)]:
+        assert perm(st) == [int(x) for x in oracle.poseidon_permute_naive(np.array(st, dtype=np.uint64))]
