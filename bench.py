@@ -15,7 +15,9 @@ divided by the device time (CUDA events on the library's stream, max over ranks)
   roofline  dominant kernel (leaf hashing), live CUDA-event time; plus per-kernel lines in `kernels`
   cpu_baseline  the oracle (C restatement, OpenMP, all host cores) on a bounded sample of the workload
   stark     BASELINE.json configs[2]: single-table STARK prove (memory-shaped table 2^22 rows): ms and
-            proofs/min (whole job, all ranks)
+            proofs/min (whole job, all ranks; two prover contexts per GPU)
+  tx        synthetic transaction: seven table proofs of the evm_arithmetization shapes (BASELINE configs[3]/[4] shape
+            only: no CTLs, no recursion), ms per transaction and transactions/min (whole job, all ranks)
 
 `--impl reference`: the CPU implementation of the same path on the host cores.  The reference's own
 prover is Rust in un-vendored crates and cannot be built here, so this arm runs the oracle
@@ -180,6 +182,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N)
     ap.add_argument("--skip-stark", action="store_true")
+    ap.add_argument("--skip-tx", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-split", action="store_true")
@@ -321,6 +324,49 @@ def main():
                           "proofs_per_min: all jobs through the pool (wall clock, max over ranks)"}
         del trace
 
+    # ---- BASELINE configs[3] / [4] shape: a synthetic TRANSACTION = seven table proofs of the evm_arithmetization shapes
+    # (arithmetic, byte packing, cpu, keccak 2400 columns, keccak sponge, logic, memory; cprog.EVM_TABLE_SHAPES, degree bits
+    # at the low end of the reference's circuit ranges).  Shape only: no cross-table lookups, no recursion layers.  Tables are
+    # registered (NVRTC) once per context, outside the timed region, like the reference builds its circuits at start-up.
+    tx = None
+    if not args.skip_stark and not args.skip_tx:
+        from eth_tx_proof_b200 import parallel, synthetic as syn
+
+        tables = syn.tx_job_tables()
+        dev = [torch.from_numpy(t.view(np.int64)).cuda() for _, _, _, t in tables]
+        torch.cuda.synchronize()
+        pool = parallel.ProverPool(local_rank, STARK_CONTEXTS_PER_GPU)
+        ids = [[(c.register_table(p, p.lookups) if p is not None else etp.TABLE_MEMORY) for _, p, _, _ in tables] for c in pool.contexts]
+
+        def prove_table(c, k):
+            w = pool.contexts.index(c)
+            return c.stark_prove_dev(ids[w][k], tables[k][2], dev[k].data_ptr(), 1 << tables[k][2])
+
+        n_tx = 8
+        my_tx = parallel.shard_jobs(n_tx, rank, world)
+        flat = [k for _ in my_tx for k in range(len(tables))]
+        pool.map(prove_table, list(range(len(tables))) * STARK_CONTEXTS_PER_GPU)  # warm-up: every table on every context
+        c0 = pool.contexts[0]
+        per_table = {}
+        t0 = time.perf_counter()
+        for k, (name, _, bits, tr) in enumerate(tables):
+            t1 = time.perf_counter()
+            pr = prove_table(c0, k)
+            per_table[f"{name} 2^{bits} x {tr.shape[0]}"] = {"ms": (time.perf_counter() - t1) * 1e3, "proof_bytes": int(pr.size * 8)}
+        tx_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t0 = time.perf_counter()
+        pool.map(prove_table, flat)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        pool.close()
+        del dev
+        tx = {"workload": "synthetic transaction: 7 table STARK proofs of the evm_arithmetization shapes (SURVEY.md App. B), "
+                          f"shape-only constraint programs, no CTLs, no recursion; {n_tx} transactions sharded over {world} GPU(s), "
+                          f"{STARK_CONTEXTS_PER_GPU} prover contexts per GPU",
+              "tx_ms": tx_ms, "tx_per_min": n_tx * 60.0 / dt, "transactions": n_tx, "tables": per_table,
+              "timed": "tx_ms: the seven proofs in sequence on one context, traces resident in HBM -> proof bytes on the host; "
+                       "tx_per_min: all table proofs of all transactions through the pool (wall clock, max over ranks)"}
+
     # ---- one table column-split across all ranks: strong scaling of a single commit.
     # Rank g transforms columns [g*C/G, (g+1)*C/G) and hashes leaf rows [g*L/G, (g+1)*L/G), reading the peers'
     # LDE columns over NVLink inside the hashing kernel; the cap parts are all-gathered over NCCL.
@@ -396,7 +442,7 @@ def main():
                    "l2": f"inputs ({8 * cols * n >> 20} MiB per batch) are larger than the 126 MB L2; no flush needed",
                    "algorithmic_bytes_per_step": nbytes, "poseidon_permutations_per_step": commit_perms(log_n, cols)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "column_split": split,
+        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "column_split": split,
     }
     print(json.dumps(out))
     if world > 1:
