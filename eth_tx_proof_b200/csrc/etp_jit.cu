@@ -4,6 +4,9 @@
 // arithmetic of the built-in kernels.  Product code: if NVRTC or the device is missing the call fails loudly.
 #include <nvrtc.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "cprog.h"
 #include "ctx.cuh"
 
@@ -15,7 +18,23 @@ const char* const kHeaderSources[] = {
 }  // namespace
 
 // Compiles `source` (one extern "C" kernel `entry`) for sm_100a.  cubin_out receives the image.
+// Process-wide cache of compiled programs: the contexts of one process (one per worker thread / parallel.ProverPool)
+// register the same tables, and a wide table takes seconds to compile (keccak shape: 2400 columns, 600 constraints).
+namespace {
+std::mutex g_cubin_mutex;
+std::unordered_map<std::string, std::vector<char>> g_cubin_cache;
+}  // namespace
+
 int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubin_out, std::string* log_out) {
+  {
+    std::lock_guard<std::mutex> lock(g_cubin_mutex);
+    auto it = g_cubin_cache.find(source);
+    if (it != g_cubin_cache.end()) {
+      *cubin_out = it->second;
+      if (log_out) log_out->clear();
+      return ETP_OK;
+    }
+  }
   nvrtcProgram prog;
   if (nvrtcCreateProgram(&prog, source.c_str(), "etp_cprog.cu", 3, kHeaderSources, kHeaderNames) != NVRTC_SUCCESS)
     return etp_fail(ctx, ETP_ERR_CUDA, "nvrtcCreateProgram failed");
@@ -38,6 +57,10 @@ int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubi
   cubin_out->resize(n);
   nvrtcGetCUBIN(prog, cubin_out->data());
   nvrtcDestroyProgram(&prog);
+  {
+    std::lock_guard<std::mutex> lock(g_cubin_mutex);
+    g_cubin_cache.emplace(source, *cubin_out);
+  }
   return ETP_OK;
 }
 

@@ -470,6 +470,16 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
     stark::combine_norms<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(c);
     ETP_LAUNCH_CHECK(ctx);
     ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, 2 * lde_n));
+    // few rows, many columns: one thread per point cannot fill the machine, so the column sums are split into chunks
+    DevBuf<uint64_t> partial(ctx);
+    if (n0 > 256 && lde_n * 4 <= (size_t)1 << 20) {
+      c.col_chunk = 64;
+      c.n_chunks = (n0 + c.col_chunk - 1) / c.col_chunk;
+      ETP_TRY(partial.alloc((size_t)c.n_chunks * lde_n * 4));
+      c.partial = partial.p;
+      stark::combine_accumulate<<<dim3(blocks_for(lde_n, 128), c.n_chunks), 128, 0, ctx->stream>>>(c);
+      ETP_LAUNCH_CHECK(ctx);
+    }
     stark::combine_values<<<blocks_for(lde_n, 128), 128, 0, ctx->stream>>>(c);
     ETP_LAUNCH_CHECK(ctx);
     ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // apow (host) and d_apow stay alive until here

@@ -350,7 +350,40 @@ struct CombineParams {
   uint64_t seven_z0c1_sq, seven_z1c1_sq;
   uint64_t* den;   // 2 x lde_n: norms to invert (phase 1) / inverted norms (phase 2)
   uint64_t* out;   // lde_n ext interleaved, bit-reversed order
+  // wide tables (hundreds of columns on few rows): the column sums are split over blockIdx.y chunks of `col_chunk`
+  // columns by combine_accumulate into partial[chunk][p][acc.c0, acc.c1, acc1.c0, acc1.c1]; n_chunks == 0: inline
+  uint64_t* partial;
+  int col_chunk, n_chunks;
 };
+// (acc, acc1) += sum over the global column indices [k0, k1) of alpha^k * f_k(x_p); acc1 only takes k < n1
+__device__ __forceinline__ void combine_columns(const CombineParams& c, uint32_t p, int k0, int k1, gl::Ext& acc, gl::Ext& acc1) {
+  int base = 0;
+  for (int m = 0; m < 3; m++) {
+    const int lo = k0 > base ? k0 : base, hi = k1 < base + c.n_cols[m] ? k1 : base + c.n_cols[m];
+    for (int k = lo; k < hi; k++) {
+      if (k == c.n1) acc1 = acc;
+      const uint64_t v = __ldg(c.cols[m] + (size_t)(k - base) * c.strides[m] + p);
+      const gl::Ext a = gl::ext(__ldg(c.alpha_pows + 2 * k), __ldg(c.alpha_pows + 2 * k + 1));
+      acc = gl::eadd(acc, gl::emul_base(a, v));
+    }
+    base += c.n_cols[m];
+  }
+}
+static __global__ void __launch_bounds__(128) combine_accumulate(CombineParams c) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = 1u << c.log_lde;
+  if (p >= n) return;
+  const int n0 = c.n_cols[0] + c.n_cols[1] + c.n_cols[2];
+  const int k0 = blockIdx.y * c.col_chunk, k1 = (k0 + c.col_chunk) < n0 ? (k0 + c.col_chunk) : n0;
+  gl::Ext acc = gl::ext(0, 0), acc1 = gl::ext(0, 0);
+  combine_columns(c, p, k0, k1, acc, acc1);
+  // this chunk's contribution to the prefix sum acc1: everything if the chunk ends at or before n1, the part before n1
+  // (captured inside combine_columns) if it straddles n1, nothing if it starts at or after n1
+  if (k1 <= c.n1) acc1 = acc;
+  else if (k0 >= c.n1) acc1 = gl::ext(0, 0);
+  uint64_t* dst = c.partial + ((size_t)blockIdx.y * n + p) * 4;
+  dst[0] = acc.c0; dst[1] = acc.c1; dst[2] = acc1.c0; dst[3] = acc1.c1;
+}
 static __global__ void combine_norms(CombineParams c) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = 1u << c.log_lde;
@@ -366,16 +399,17 @@ static __global__ void __launch_bounds__(128) combine_values(CombineParams c) {
   const uint32_t n = 1u << c.log_lde;
   if (p >= n) return;
   gl::Ext acc = gl::ext(0, 0), acc1 = gl::ext(0, 0);
-  int k = 0;
-  for (int m = 0; m < 3; m++) {
-    for (int col = 0; col < c.n_cols[m]; col++, k++) {
-      if (k == c.n1) acc1 = acc;
-      const uint64_t v = __ldg(c.cols[m] + (size_t)col * c.strides[m] + p);
-      const gl::Ext a = gl::ext(c.alpha_pows[2 * k], c.alpha_pows[2 * k + 1]);
-      acc = gl::eadd(acc, gl::emul_base(a, v));
+  const int n0 = c.n_cols[0] + c.n_cols[1] + c.n_cols[2];
+  if (c.n_chunks == 0) {
+    combine_columns(c, p, 0, n0, acc, acc1);
+    if (n0 <= c.n1) acc1 = acc;
+  } else {
+    for (int j = 0; j < c.n_chunks; j++) {
+      const uint64_t* src = c.partial + ((size_t)j * n + p) * 4;
+      acc = gl::eadd(acc, gl::ext(src[0], src[1]));
+      acc1 = gl::eadd(acc1, gl::ext(src[2], src[3]));
     }
   }
-  if (k == c.n1) acc1 = acc;
   const uint64_t x = c.coset.get(gl::bitrev32(p, c.log_lde));
   // 1/(x - z) = conj(x - z) / norm
   const uint64_t i0 = c.den[p], i1 = c.den[n + p];
