@@ -205,9 +205,14 @@ def main():
     log_n, cols = args.log_n, COLS
     n = 1 << log_n
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) write to file
+    # descriptor 1 directly, so everything but the final line is sent to stderr at the descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (NCCL prints its version banner there)
+        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -444,7 +449,9 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
         "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "column_split": split,
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.destroy_process_group()
 

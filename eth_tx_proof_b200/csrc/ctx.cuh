@@ -59,6 +59,12 @@ int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubi
 int jit_load(etp_ctx* ctx, const std::vector<char>& cubin, const char* entry, JitKernel* out);
 void jit_unload(JitKernel* k);
 
+// Every C-ABI entry point binds the calling thread to its context's device first: callers are arbitrary host threads
+// (tokio workers in the reference, parallel.ProverPool here) whose current device is whatever the runtime defaults to.
+inline void etp_bind(const etp_ctx* ctx) {
+  if (ctx) cudaSetDevice(ctx->device);
+}
+
 inline int etp_fail(etp_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;

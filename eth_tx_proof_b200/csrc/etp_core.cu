@@ -47,12 +47,14 @@ int dev_cache_trim(etp_ctx* ctx) {
   return ETP_OK;
 }
 extern "C" int etp_ctx_trim(etp_ctx* ctx) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   return dev_cache_trim(ctx);
 }
 extern "C" size_t etp_ctx_cached_bytes(const etp_ctx* ctx) { return ctx ? ctx->cache_free_bytes : 0; }
 
 extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
+  etp_bind(ctx);
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -70,6 +72,7 @@ extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
 
 extern "C" const char* etp_last_error(const etp_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 extern "C" int etp_ctx_synchronize(etp_ctx* ctx) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ETP_OK;
@@ -78,24 +81,28 @@ extern "C" void* etp_ctx_stream(etp_ctx* ctx) { return ctx ? (void*)ctx->stream 
 extern "C" uint64_t etp_ctx_launch_count(const etp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int etp_dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
+  etp_bind(ctx);
   if (!ctx || !out) return ETP_ERR_INVALID;
   ETP_CUDA(ctx, cudaSetDevice(ctx->device));
   ETP_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 8));
   return ETP_OK;
 }
 extern "C" int etp_dev_free(etp_ctx* ctx, void* ptr) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ETP_CUDA(ctx, cudaFree(ptr));
   return ETP_OK;
 }
 extern "C" int etp_dev_upload(etp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   ETP_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return ETP_OK;
 }
 extern "C" int etp_dev_download(etp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   ETP_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -362,6 +369,7 @@ __global__ void k_permute_states(uint64_t* st, size_t n) {
 }
 
 extern "C" int etp_poseidon_permute_host(etp_ctx* ctx, uint64_t* states, size_t n) {
+  etp_bind(ctx);
   if (!ctx || (!states && n)) return ETP_ERR_INVALID;
   if (n == 0) return ETP_OK;
   DevBuf<uint64_t> d(ctx);
@@ -394,17 +402,21 @@ static int transform_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n
   return ETP_OK;
 }
 extern "C" int etp_ifft_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n) {
+  etp_bind(ctx);
   return transform_host(ctx, cols, n_cols, log_n, true, 0);
 }
 extern "C" int etp_fft_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n) {
+  etp_bind(ctx);
   return transform_host(ctx, cols, n_cols, log_n, false, 0);
 }
 extern "C" int etp_coset_ifft_host(etp_ctx* ctx, uint64_t* cols, size_t n_cols, int log_n, uint64_t shift) {
+  etp_bind(ctx);
   if (gl::canon(shift) == 0) return etp_fail(ctx, ETP_ERR_INVALID, "coset shift must be non-zero");
   return transform_host(ctx, cols, n_cols, log_n, true, gl::canon(shift));
 }
 extern "C" int etp_coset_lde_host(etp_ctx* ctx, const uint64_t* coeffs, size_t n_cols, int log_n, int rate_bits,
                                   uint64_t shift, uint64_t* out) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   if (log_n < 0 || rate_bits < 0 || log_n + rate_bits > 31 || gl::canon(shift) == 0)
     return etp_fail(ctx, ETP_ERR_INVALID, "coset_lde: bad arguments");
@@ -430,6 +442,7 @@ extern "C" int etp_coset_lde_host(etp_ctx* ctx, const uint64_t* coeffs, size_t n
 // =================================================================================================
 extern "C" int etp_merkle_new_host(etp_ctx* ctx, const uint64_t* leaves, size_t n_leaves, size_t leaf_len, int cap_height,
                                    etp_tree** out) {
+  etp_bind(ctx);
   if (!ctx || !out) return ETP_ERR_INVALID;
   *out = nullptr;
   const int lg = log2_exact(n_leaves);
@@ -455,21 +468,25 @@ extern "C" int etp_merkle_new_host(etp_ctx* ctx, const uint64_t* leaves, size_t 
   return ETP_OK;
 }
 extern "C" void etp_tree_free(etp_tree* t) {
+  etp_bind(t ? t->ctx : nullptr);
   if (!t) return;
   dev_free(t->ctx, t->levels);
   delete t;
 }
 extern "C" size_t etp_tree_num_digests(const etp_tree* t) { return t ? 2 * (t->n_leaves - ((size_t)1 << t->cap_height)) : 0; }
 extern "C" int etp_tree_cap(etp_tree* t, uint64_t* cap_out) {
+  etp_bind(t ? t->ctx : nullptr);
   if (!t || !cap_out) return ETP_ERR_INVALID;
   memcpy(cap_out, t->cap.data(), t->cap.size() * 8);
   return ETP_OK;
 }
 extern "C" int etp_tree_digests(etp_tree* t, uint64_t* out) {
+  etp_bind(t ? t->ctx : nullptr);
   if (!t || (!out && etp_tree_num_digests(t))) return ETP_ERR_INVALID;
   return merkle_download_digests(t->ctx, t->levels, t->n_leaves, t->cap_height, out);
 }
 extern "C" int etp_tree_prove(etp_tree* t, size_t leaf_index, uint64_t* out) {
+  etp_bind(t ? t->ctx : nullptr);
   if (!t) return ETP_ERR_INVALID;
   return merkle_prove_from_levels(t->ctx, t->levels, t->n_leaves, t->cap_height, leaf_index, out);
 }
@@ -658,6 +675,7 @@ __global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* d
 
 extern "C" int etp_batch_from_values_host(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, int log_n, int rate_bits,
                                           int blinding, int cap_height, etp_batch** out) {
+  etp_bind(ctx);
   if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
@@ -669,6 +687,7 @@ extern "C" int etp_batch_from_values_host(etp_ctx* ctx, const uint64_t* const* c
 
 extern "C" int etp_batch_from_coeffs_host(etp_ctx* ctx, const uint64_t* const* cols, size_t n_cols, int log_n, int rate_bits,
                                           int blinding, int cap_height, etp_batch** out) {
+  etp_bind(ctx);
   if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
@@ -680,6 +699,7 @@ extern "C" int etp_batch_from_coeffs_host(etp_ctx* ctx, const uint64_t* const* c
 
 extern "C" int etp_batch_from_values_dev(etp_ctx* ctx, const uint64_t* values_dev, size_t col_stride, size_t n_cols, int log_n,
                                          int rate_bits, int blinding, int cap_height, etp_batch** out) {
+  etp_bind(ctx);
   if (!ctx || !out || (!values_dev && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
@@ -691,6 +711,7 @@ extern "C" int etp_batch_from_values_dev(etp_ctx* ctx, const uint64_t* values_de
 
 extern "C" int etp_batch_from_coeffs_dev(etp_ctx* ctx, const uint64_t* coeffs_dev, size_t col_stride, size_t n_cols, int log_n,
                                          int rate_bits, int blinding, int cap_height, etp_batch** out) {
+  etp_bind(ctx);
   if (!ctx || !out || (!coeffs_dev && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
@@ -707,6 +728,7 @@ extern "C" int etp_batch_from_coeffs_dev(etp_ctx* ctx, const uint64_t* coeffs_de
 }
 
 extern "C" int etp_batch_recommit_values_dev(etp_batch* b, const uint64_t* values_dev, size_t col_stride) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b || !values_dev) return ETP_ERR_INVALID;
   return batch_commit_from_values(b, values_dev, col_stride);
 }
@@ -719,6 +741,7 @@ extern "C" int etp_batch_last_commit_timings(const etp_batch* b, float ms_out[4]
 }
 
 extern "C" void etp_batch_free(etp_batch* b) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b) return;
   for (auto& e : b->ev)
     if (e) cudaEventDestroy(e);
@@ -731,11 +754,13 @@ extern "C" size_t etp_batch_num_cols(const etp_batch* b) { return b ? b->n_cols 
 extern "C" int etp_batch_degree_log(const etp_batch* b) { return b ? b->log_n : -1; }
 extern "C" size_t etp_batch_num_digests(const etp_batch* b) { return b ? 2 * (b->lde_n() - ((size_t)1 << b->cap_height)) : 0; }
 extern "C" int etp_batch_cap(etp_batch* b, uint64_t* cap_out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b || !cap_out) return ETP_ERR_INVALID;
   memcpy(cap_out, b->cap.data(), b->cap.size() * 8);
   return ETP_OK;
 }
 extern "C" int etp_batch_download_coeffs(etp_batch* b, uint64_t* out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b || (!out && b->n_cols)) return ETP_ERR_INVALID;
   if (b->n_cols == 0) return ETP_OK;
   ETP_CUDA(b->ctx, cudaMemcpyAsync(out, b->coeffs, b->n_cols * b->n() * 8, cudaMemcpyDeviceToHost, b->ctx->stream));
@@ -763,6 +788,7 @@ __global__ void k_transpose_to_rows(const uint64_t* __restrict__ lde, size_t col
 }
 
 extern "C" int etp_batch_download_leaves(etp_batch* b, uint64_t* out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b || (!out && b->n_cols)) return ETP_ERR_INVALID;
   if (b->n_cols == 0) return ETP_OK;
   etp_ctx* ctx = b->ctx;
@@ -776,10 +802,12 @@ extern "C" int etp_batch_download_leaves(etp_batch* b, uint64_t* out) {
   return ETP_OK;
 }
 extern "C" int etp_batch_download_digests(etp_batch* b, uint64_t* out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b) return ETP_ERR_INVALID;
   return merkle_download_digests(b->ctx, b->levels, b->lde_n(), b->cap_height, out);
 }
 extern "C" int etp_batch_leaves_at(etp_batch* b, const uint64_t* idx, size_t n_idx, uint64_t* rows_out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b || (!idx && n_idx)) return ETP_ERR_INVALID;
   if (n_idx == 0 || b->n_cols == 0) return ETP_OK;
   etp_ctx* ctx = b->ctx;
@@ -798,6 +826,7 @@ extern "C" int etp_batch_leaves_at(etp_batch* b, const uint64_t* idx, size_t n_i
   return ETP_OK;
 }
 extern "C" int etp_batch_get_lde_values(etp_batch* b, size_t index, size_t step, uint64_t* row_out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b) return ETP_ERR_INVALID;
   const size_t i = index * step;
   if (i >= b->lde_n()) return etp_fail(b->ctx, ETP_ERR_INVALID, "get_lde_values: index out of range");
@@ -805,6 +834,7 @@ extern "C" int etp_batch_get_lde_values(etp_batch* b, size_t index, size_t step,
   return etp_batch_leaves_at(b, &pos, 1, row_out);
 }
 extern "C" int etp_batch_prove(etp_batch* b, size_t leaf_index, uint64_t* out) {
+  etp_bind(b ? b->ctx : nullptr);
   if (!b) return ETP_ERR_INVALID;
   return merkle_prove_from_levels(b->ctx, b->levels, b->lde_n(), b->cap_height, leaf_index, out);
 }

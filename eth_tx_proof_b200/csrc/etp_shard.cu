@@ -38,6 +38,7 @@ extern "C" size_t etp_shard_cols_per_rank(size_t n_cols_total, int world) {
 
 extern "C" int etp_shard_create(etp_ctx* ctx, size_t n_cols_total, int log_n, int rate_bits, int cap_height, int rank, int world,
                                 etp_shard** out) {
+  etp_bind(ctx);
   if (!ctx || !out) return ETP_ERR_INVALID;
   *out = nullptr;
   if (world < 1 || world > merkle::MAX_SRC || (world & (world - 1)) || rank < 0 || rank >= world)
@@ -70,6 +71,7 @@ extern "C" int etp_shard_create(etp_ctx* ctx, size_t n_cols_total, int log_n, in
 }
 
 extern "C" void etp_shard_free(etp_shard* s) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
@@ -105,6 +107,7 @@ static int shard_transform(etp_shard* s, const uint64_t* values_dev, size_t col_
 }
 
 extern "C" int etp_shard_transform_values_dev(etp_shard* s, const uint64_t* values_dev, size_t col_stride) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s || (!values_dev && s->local_cols)) return ETP_ERR_INVALID;
   ETP_TRY(shard_transform(s, values_dev, col_stride, nullptr));
   ETP_CUDA(s->ctx, cudaStreamSynchronize(s->ctx->stream));  // peers may read the LDE once this returns (+ a barrier)
@@ -113,6 +116,7 @@ extern "C" int etp_shard_transform_values_dev(etp_shard* s, const uint64_t* valu
 }
 
 extern "C" int etp_shard_transform_values_host(etp_shard* s, const uint64_t* const* local_cols) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s || (!local_cols && s->local_cols)) return ETP_ERR_INVALID;
   etp_ctx* ctx = s->ctx;
   DevBuf<uint64_t> stage(ctx);
@@ -129,6 +133,7 @@ extern "C" int etp_shard_transform_values_host(etp_shard* s, const uint64_t* con
 
 // ---- peer mapping ---------------------------------------------------------------------------------------
 extern "C" int etp_ipc_export(etp_ctx* ctx, const void* dev_ptr, unsigned char handle_out[ETP_IPC_HANDLE_BYTES]) {
+  etp_bind(ctx);
   if (!ctx || !dev_ptr || !handle_out) return ETP_ERR_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == ETP_IPC_HANDLE_BYTES, "IPC handle size");
   cudaIpcMemHandle_t h;
@@ -138,6 +143,7 @@ extern "C" int etp_ipc_export(etp_ctx* ctx, const void* dev_ptr, unsigned char h
   return ETP_OK;
 }
 extern "C" int etp_ipc_open(etp_ctx* ctx, const unsigned char handle[ETP_IPC_HANDLE_BYTES], void** dev_ptr_out) {
+  etp_bind(ctx);
   if (!ctx || !handle || !dev_ptr_out) return ETP_ERR_INVALID;
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, sizeof h);
@@ -146,6 +152,7 @@ extern "C" int etp_ipc_open(etp_ctx* ctx, const unsigned char handle[ETP_IPC_HAN
   return ETP_OK;
 }
 extern "C" int etp_ipc_close(etp_ctx* ctx, void* dev_ptr) {
+  etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;
   ETP_CUDA(ctx, cudaSetDevice(ctx->device));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -153,6 +160,7 @@ extern "C" int etp_ipc_close(etp_ctx* ctx, void* dev_ptr) {
   return ETP_OK;
 }
 extern "C" int etp_shard_set_peer(etp_shard* s, int peer_rank, const uint64_t* peer_lde) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s) return ETP_ERR_INVALID;
   if (peer_rank < 0 || peer_rank >= s->world || peer_rank == s->rank || !peer_lde)
     return etp_fail(s->ctx, ETP_ERR_INVALID, "shard: bad peer rank %d", peer_rank);
@@ -174,6 +182,7 @@ static int shard_src(etp_shard* s, merkle::LeafSrc* src) {
 
 // ---- phase 2 ------------------------------------------------------------------------------------------------
 extern "C" int etp_shard_commit_rows(etp_shard* s, uint64_t* cap_part_out) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s || !cap_part_out) return ETP_ERR_INVALID;
   etp_ctx* ctx = s->ctx;
   merkle::LeafSrc src;
@@ -186,6 +195,7 @@ extern "C" int etp_shard_commit_rows(etp_shard* s, uint64_t* cap_part_out) {
 }
 
 extern "C" int etp_shard_prove(etp_shard* s, size_t leaf_index, uint64_t* siblings_out) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s) return ETP_ERR_INVALID;
   if (!s->committed) return etp_fail(s->ctx, ETP_ERR_STATE, "shard: not committed");
   if (leaf_index < s->row0() || leaf_index >= s->row0() + s->rows())
@@ -203,6 +213,7 @@ __global__ void k_gather_rows_src(const __grid_constant__ merkle::LeafSrc src, i
 }
 
 extern "C" int etp_shard_leaves_at(etp_shard* s, const uint64_t* idx, size_t n_idx, uint64_t* rows_out) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s || (!idx && n_idx)) return ETP_ERR_INVALID;
   if (n_idx == 0) return ETP_OK;
   etp_ctx* ctx = s->ctx;
@@ -223,6 +234,7 @@ extern "C" int etp_shard_leaves_at(etp_shard* s, const uint64_t* idx, size_t n_i
 }
 
 extern "C" int etp_shard_download_coeffs(etp_shard* s, uint64_t* out) {
+  etp_bind(s ? s->ctx : nullptr);
   if (!s || (!out && s->local_cols)) return ETP_ERR_INVALID;
   if (s->local_cols == 0) return ETP_OK;
   ETP_CUDA(s->ctx, cudaMemcpyAsync(out, s->coeffs, s->local_cols * s->n() * 8, cudaMemcpyDeviceToHost, s->ctx->stream));

@@ -650,6 +650,7 @@ extern "C" int etp_table_quotient_degree_factor(const etp_ctx* c, int t) { Table
 
 extern "C" int etp_table_register(etp_ctx* ctx, const uint64_t* program, size_t n_words, const int32_t* lookups, size_t n_lookup_words,
                                   int* table_id_out) {
+  etp_bind(ctx);
   if (!ctx || !program || !table_id_out || (!lookups && n_lookup_words)) return ETP_ERR_INVALID;
   auto t = new RegisteredTable();
   struct Guard { RegisteredTable* t; ~Guard() { if (t) { jit_unload(&t->kernel); delete t; } } } guard{t};
@@ -696,6 +697,7 @@ extern "C" int etp_table_register(etp_ctx* ctx, const uint64_t* program, size_t 
 
 extern "C" int etp_lookup_helper_columns_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
                                              const uint64_t* challenges, int n_challenges, uint64_t* aux_dev) {
+  etp_bind(ctx);
   if (!ctx || !trace_dev || !challenges || !aux_dev) return ETP_ERR_INVALID;
   if (log_n < 0 || log_n > 30 || n_challenges < 0) return etp_fail(ctx, ETP_ERR_INVALID, "bad arguments");
   ETP_TRY(lookup_helper_columns(ctx, table, log_n, trace_dev, col_stride, challenges, n_challenges, aux_dev));
@@ -706,6 +708,7 @@ extern "C" int etp_lookup_helper_columns_dev(etp_ctx* ctx, int table, int log_n,
 extern "C" int etp_compute_quotient_polys_dev(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* lookup_challenges,
                                               int n_lookup_challenges, const uint64_t* public_inputs, const uint64_t* alphas, int n_alphas,
                                               uint64_t* out_dev) {
+  etp_bind(ctx);
   if (!ctx || !trace || !alphas || !out_dev) return ETP_ERR_INVALID;
   uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
   ETP_TRY(compute_quotient(ctx, table, trace, aux, lookup_challenges ? lookup_challenges : zero, n_lookup_challenges,
@@ -715,6 +718,7 @@ extern "C" int etp_compute_quotient_polys_dev(etp_ctx* ctx, int table, etp_batch
 }
 
 extern "C" int etp_pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, int bits, uint64_t* witness_out) {
+  etp_bind(ctx);
   if (!ctx || !state || !witness_out) return ETP_ERR_INVALID;
   return pow_grind(ctx, state, pos, bits, witness_out);
 }
@@ -727,6 +731,7 @@ extern "C" size_t etp_stark_proof_words(const etp_ctx* ctx, int table, int log_n
 
 extern "C" int etp_stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
                                    const uint64_t* public_inputs, uint64_t* proof_out) {
+  etp_bind(ctx);
   if (!ctx || !trace_dev || !proof_out) return ETP_ERR_INVALID;
   uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
   return stark_prove_dev(ctx, table, log_n, trace_dev, col_stride, public_inputs ? public_inputs : zero, proof_out);
@@ -734,6 +739,7 @@ extern "C" int etp_stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uin
 
 extern "C" int etp_stark_prove_host(etp_ctx* ctx, int table, int log_n, const uint64_t* trace, const uint64_t* public_inputs,
                                     uint64_t* proof_out) {
+  etp_bind(ctx);
   if (!ctx || !trace || !proof_out) return ETP_ERR_INVALID;
   TableInfo ti;
   if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);

@@ -132,3 +132,36 @@ def test_column_split_commit_across_gpus(world):
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("shard ok") == world, r.stdout[-3000:]
+
+
+def test_context_on_another_device_from_a_fresh_thread():
+    """Callers are arbitrary host threads (tokio workers upstream, parallel.ProverPool here): every entry point binds the
+    calling thread to its context's device.  A thread that never touched CUDA drives a context on device 1."""
+    import threading
+
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import synthetic as syn
+
+    if etp.load_library().etp_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    vals = syn.random_columns(11, 10, seed=9)
+    c0 = etp.Context(0)
+    want = etp.PolynomialBatch.from_values(c0, vals, 1, False, 4).cap.copy()
+    out = {}
+
+    def work():
+        try:
+            c1 = etp.Context(1)
+            out["cap"] = etp.PolynomialBatch.from_values(c1, vals, 1, False, 4).cap.copy()
+            out["proof"] = c1.stark_prove(etp.TABLE_MEMORY, syn.memory_trace(8, seed=2))
+            c1.close()
+        except BaseException as e:  # noqa: BLE001
+            out["err"] = e
+
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    assert "err" not in out, out.get("err")
+    assert (out["cap"] == want).all()
+    assert (out["proof"] == c0.stark_prove(etp.TABLE_MEMORY, syn.memory_trace(8, seed=2))).all()
+    c0.close()
