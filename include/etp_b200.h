@@ -53,6 +53,10 @@ int etp_ctx_synchronize(etp_ctx *ctx);
 void *etp_ctx_stream(etp_ctx *ctx);
 /* number of kernel launches issued by this context since creation */
 uint64_t etp_ctx_launch_count(const etp_ctx *ctx);
+/* Host-side Poseidon-12 permutation (plonky2/src/hash/poseidon.rs `Poseidon::poseidon`), in place: any u64 in, canonical
+ * out.  Needs no GPU: it is what the library's Fiat-Shamir Challenger runs on the calling thread (the transcript is
+ * strictly sequential); exported so that a caller-side Challenger can share it. */
+void etp_host_poseidon_permute(uint64_t state[12]);
 /* Device scratch of a context comes from a per-context block cache (a released block is reused by the next
  * allocation of about the same size, so proofs / commits of a shape seen before allocate nothing).
  * etp_ctx_trim returns the cached blocks to the CUDA runtime; etp_ctx_cached_bytes reports how much is held. */

@@ -15,6 +15,7 @@ extern "C" {
     pub fn etp_ctx_create(device: c_int, out: *mut *mut etp_ctx) -> c_int;
     pub fn etp_ctx_destroy(ctx: *mut etp_ctx);
     pub fn etp_ctx_trim(ctx: *mut etp_ctx) -> c_int;
+    pub fn etp_host_poseidon_permute(state: *mut u64);
     pub fn etp_ctx_cached_bytes(ctx: *const etp_ctx) -> usize;
     pub fn etp_last_error(ctx: *const etp_ctx) -> *const c_char;
     pub fn etp_batch_from_values_host(ctx: *mut etp_ctx, cols: *const *const u64, n_cols: usize, log_n: c_int,
