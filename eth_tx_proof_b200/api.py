@@ -60,6 +60,7 @@ def load_library():
         "etp_ctx_launch_count": (C.c_uint64, [vp]),
         "etp_ctx_trim": (i32, [vp]),
         "etp_ctx_cached_bytes": (C.c_size_t, [vp]),
+        "etp_host_poseidon_permute": (None, [C.POINTER(C.c_uint64)]),
         "etp_dev_alloc": (i32, [vp, sz, pp]),
         "etp_dev_free": (i32, [vp, vp]),
         "etp_dev_upload": (i32, [vp, vp, vp, sz]),
