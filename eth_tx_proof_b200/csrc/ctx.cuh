@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -49,6 +50,7 @@ struct etp_ctx {
   // a shape seen before therefore allocate nothing (measured: with cudaMallocAsync pools single proofs at 2^22 rows
   // jittered between 55 and 900 ms).  Blocks are matched by size (<= 12.5 % slack); on out-of-memory the cache is
   // emptied and the allocation retried; etp_ctx_trim() empties it on request.
+  std::mutex cache_mutex;  // objects may be released from another thread (a garbage collector) than the one proving
   std::multimap<size_t, void*> cache_free;
   std::unordered_map<void*, size_t> cache_live;
   size_t cache_free_bytes = 0;
@@ -96,6 +98,7 @@ inline int etp_fail(etp_ctx* ctx, int code, const char* fmt, ...) {
 inline int dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
   bytes = (bytes + 511) & ~(size_t)511;
   if (bytes == 0) bytes = 512;
+  std::unique_lock<std::mutex> lock(ctx->cache_mutex);
   auto it = ctx->cache_free.lower_bound(bytes);
   if (it != ctx->cache_free.end() && it->first <= bytes + bytes / 8) {
     *out = it->second;
@@ -108,7 +111,9 @@ inline int dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
   cudaError_t e = cudaMalloc(out, bytes);
   if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and try once more
     cudaGetLastError();
+    lock.unlock();
     ETP_TRY(dev_cache_trim(ctx));
+    lock.lock();
     e = cudaMalloc(out, bytes);
   }
   if (e != cudaSuccess) {
@@ -120,6 +125,7 @@ inline int dev_alloc(etp_ctx* ctx, size_t bytes, void** out) {
 }
 inline void dev_free(etp_ctx* ctx, void* p) {
   if (!p) return;
+  std::lock_guard<std::mutex> lock(ctx->cache_mutex);
   auto it = ctx->cache_live.find(p);
   if (it == ctx->cache_live.end()) {  // not ours (never happens for dev_alloc'ed memory): hand it to the runtime
     cudaFree(p);

@@ -41,6 +41,7 @@ extern "C" int etp_ctx_create(int device, etp_ctx** out) {
 int dev_cache_trim(etp_ctx* ctx) {
   ETP_CUDA(ctx, cudaSetDevice(ctx->device));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::lock_guard<std::mutex> lock(ctx->cache_mutex);
   for (auto& kv : ctx->cache_free) cudaFree(kv.second);
   ctx->cache_free.clear();
   ctx->cache_free_bytes = 0;

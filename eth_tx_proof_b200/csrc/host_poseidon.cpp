@@ -6,7 +6,7 @@
 // absorb 4 (C + aux + quotient) opening words, i.e. 1200 permutations for a keccak-shaped table (2400 columns), which at
 // the ~10 us of a naive permutation was 12 ms of a 26 ms proof.  Hence: lazy representatives with branch-free fix-ups
 // (the fix-up conditions are ~50/50, branches mispredict), the MDS layer on the 32-bit halves of the lanes with 64-bit
-// accumulators, and an AVX2 version of those dot products chosen at run time.  ~3 us per permutation.
+// accumulators, and an AVX2 version of that layer chosen at run time.  ~2 us per permutation.
 // This is NOT the oracle: nothing here includes oracle/.
 #include <cstdint>
 #include <cstring>
@@ -71,23 +71,34 @@ void mds_scalar(uint64_t s[12]) {
   for (int r = 0; r < 12; r++) s[r] = fold(al[r], ah[r]);
 }
 #if defined(__x86_64__)
+// out = sum_j x_j * column_j of the circulant: twelve broadcasts against constant column vectors (no rotated reloads of
+// freshly stored data, which stall on store forwarding)
+struct Columns {
+  alignas(32) uint64_t c[12][12];
+  Columns() {
+    for (int j = 0; j < 12; j++)
+      for (int r = 0; r < 12; r++) c[j][r] = CIRC[(j - r + 12) % 12];
+  }
+};
 __attribute__((target("avx2"))) void mds_avx2(uint64_t s[12]) {
-  uint64_t lo[24], hi[24], al[12], ah[12];
-  split(s, lo, hi);
+  static const Columns cols;
+  uint64_t al[12], ah[12];
   __m256i l0 = _mm256_setzero_si256(), l1 = l0, l2 = l0, h0 = l0, h1 = l0, h2 = l0;
-  for (int i = 0; i < 12; i++) {
-    const __m256i c = _mm256_set1_epi64x(CIRC[i]);
-    l0 = _mm256_add_epi64(l0, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i*)(lo + i)), c));
-    l1 = _mm256_add_epi64(l1, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i*)(lo + i + 4)), c));
-    l2 = _mm256_add_epi64(l2, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i*)(lo + i + 8)), c));
-    h0 = _mm256_add_epi64(h0, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i*)(hi + i)), c));
-    h1 = _mm256_add_epi64(h1, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i*)(hi + i + 4)), c));
-    h2 = _mm256_add_epi64(h2, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i*)(hi + i + 8)), c));
+  for (int j = 0; j < 12; j++) {
+    const __m256i xl = _mm256_set1_epi64x((long long)(uint32_t)s[j]), xh = _mm256_set1_epi64x((long long)(s[j] >> 32));
+    const __m256i c0 = _mm256_load_si256((const __m256i*)&cols.c[j][0]), c1 = _mm256_load_si256((const __m256i*)&cols.c[j][4]),
+                  c2 = _mm256_load_si256((const __m256i*)&cols.c[j][8]);
+    l0 = _mm256_add_epi64(l0, _mm256_mul_epu32(xl, c0));
+    l1 = _mm256_add_epi64(l1, _mm256_mul_epu32(xl, c1));
+    l2 = _mm256_add_epi64(l2, _mm256_mul_epu32(xl, c2));
+    h0 = _mm256_add_epi64(h0, _mm256_mul_epu32(xh, c0));
+    h1 = _mm256_add_epi64(h1, _mm256_mul_epu32(xh, c1));
+    h2 = _mm256_add_epi64(h2, _mm256_mul_epu32(xh, c2));
   }
   _mm256_storeu_si256((__m256i*)al, l0); _mm256_storeu_si256((__m256i*)(al + 4), l1); _mm256_storeu_si256((__m256i*)(al + 8), l2);
   _mm256_storeu_si256((__m256i*)ah, h0); _mm256_storeu_si256((__m256i*)(ah + 4), h1); _mm256_storeu_si256((__m256i*)(ah + 8), h2);
-  al[0] += 8 * lo[0];
-  ah[0] += 8 * hi[0];
+  al[0] += 8 * (uint64_t)(uint32_t)s[0];
+  ah[0] += 8 * (s[0] >> 32);
   for (int r = 0; r < 12; r++) s[r] = fold(al[r], ah[r]);
 }
 #endif

@@ -153,16 +153,25 @@ static inline void f_mds_layer(uint64_t s[12]) {
     hi[i] = hi[i + 12] = s[i] >> 32;
   }
 #if defined(__AVX2__)
-  /* al[r] = sum_i lo[i + r] * C[i]: twelve broadcast-multiply-adds on three 4-lane vectors per half */
+  /* out = sum_j x_j * column_j of the circulant: twelve broadcasts against constant column vectors */
+  static uint64_t CC[12][12] __attribute__((aligned(32)));
+  static int cc_ready = 0;
+  if (!__atomic_load_n(&cc_ready, __ATOMIC_ACQUIRE)) {
+    for (int j = 0; j < 12; j++)
+      for (int r = 0; r < 12; r++) CC[j][r] = C[(j - r + 12) % 12]; /* idempotent: racing writers store the same values */
+    __atomic_store_n(&cc_ready, 1, __ATOMIC_RELEASE);
+  }
   __m256i l0 = _mm256_setzero_si256(), l1 = l0, l2 = l0, h0 = l0, h1 = l0, h2 = l0;
-  for (int i = 0; i < 12; i++) {
-    const __m256i c = _mm256_set1_epi64x(C[i]);
-    l0 = _mm256_add_epi64(l0, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(lo + i)), c));
-    l1 = _mm256_add_epi64(l1, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(lo + i + 4)), c));
-    l2 = _mm256_add_epi64(l2, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(lo + i + 8)), c));
-    h0 = _mm256_add_epi64(h0, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(hi + i)), c));
-    h1 = _mm256_add_epi64(h1, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(hi + i + 4)), c));
-    h2 = _mm256_add_epi64(h2, _mm256_mul_epu32(_mm256_loadu_si256((const __m256i *)(hi + i + 8)), c));
+  for (int j = 0; j < 12; j++) {
+    const __m256i xl = _mm256_set1_epi64x((long long)lo[j]), xh = _mm256_set1_epi64x((long long)hi[j]);
+    const __m256i c0 = _mm256_load_si256((const __m256i *)&CC[j][0]), c1 = _mm256_load_si256((const __m256i *)&CC[j][4]),
+                  c2 = _mm256_load_si256((const __m256i *)&CC[j][8]);
+    l0 = _mm256_add_epi64(l0, _mm256_mul_epu32(xl, c0));
+    l1 = _mm256_add_epi64(l1, _mm256_mul_epu32(xl, c1));
+    l2 = _mm256_add_epi64(l2, _mm256_mul_epu32(xl, c2));
+    h0 = _mm256_add_epi64(h0, _mm256_mul_epu32(xh, c0));
+    h1 = _mm256_add_epi64(h1, _mm256_mul_epu32(xh, c1));
+    h2 = _mm256_add_epi64(h2, _mm256_mul_epu32(xh, c2));
   }
   _mm256_storeu_si256((__m256i *)al, l0); _mm256_storeu_si256((__m256i *)(al + 4), l1); _mm256_storeu_si256((__m256i *)(al + 8), l2);
   _mm256_storeu_si256((__m256i *)ah, h0); _mm256_storeu_si256((__m256i *)(ah + 4), h1); _mm256_storeu_si256((__m256i *)(ah + 8), h2);
