@@ -594,7 +594,9 @@ int batch_commit_from_values(etp_batch* b, const uint64_t* values_dev, size_t co
 static size_t stream_group_cols(const etp_batch* b) {
   const size_t bytes = b->n_cols * b->n() * 8;
   if (b->n_cols <= 8 || bytes < ((size_t)32 << 20)) return b->n_cols ? b->n_cols : 1;  // too small to pipeline
-  size_t g = (b->n_cols + 7) / 8;   // aim at 8 groups
+  size_t target = 8;                // aim at 8 groups
+  if (const char* e = getenv("ETP_STREAM_GROUPS")) target = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : 8;
+  size_t g = (b->n_cols + target - 1) / target;
   g = (g + 7) / 8 * 8;
   return g;
 }
@@ -607,8 +609,13 @@ int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, b
   // group boundaries (multiples of 8 columns).  The first group is a single sponge chunk: its copy is the only one
   // nothing can hide.  A last group of fewer than 8 columns joins its predecessor: its ragged sponge chunk keeps
   // rate lanes of the previous permutation, and only the capacity lanes are carried from one launch to the next.
+  // The pipeline ramps up: a group's copy (0.6 ms per 2^22-row column) must not outlast the previous group's compute
+  // (1 ms per column), so the first two groups are single sponge chunks and only then come groups of G columns.
   std::vector<size_t> bounds{0};
-  if (G < C && G > 8) bounds.push_back(8);
+  if (G < C && G > 8) {
+    bounds.push_back(8);
+    if (C > 24) bounds.push_back(16);
+  }
   while (bounds.back() < C) bounds.push_back(bounds.back() + G < C ? bounds.back() + G : C);
   if (bounds.size() > 2 && C - bounds[bounds.size() - 2] < 8) bounds.erase(bounds.end() - 2);
   const size_t n_groups = bounds.size() - 1;
@@ -635,28 +642,45 @@ int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, b
       ETP_TRY(get_sync_event(ctx, 2 + 2 * (k - 2), &prev));
       ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, prev, 0));
     }
-    for (size_t c = 0; c < gc; c++)
-      ETP_CUDA(ctx, cudaMemcpyAsync(land + c * n, cols[c0 + c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-    ETP_CUDA(ctx, cudaEventRecord(h2d_done, ctx->copy_stream));
-    ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, h2d_done, 0));
-    NttArgs args;
-    if (is_values) {  // "IFFT": natural -> natural; this group's slice of the LDE buffer is the scratch
-      args.in = land; args.in_stride = n; args.n_in = (uint32_t)n;
-      args.out = b->coeffs + c0 * n; args.out_stride = n;
-      args.scratch = b->lde + c0 * b->lde_n(); args.scratch_stride = b->lde_n();
-      args.log_n = b->log_n; args.n_cols = gc; args.inverse = true; args.natural_out = true;
-      ETP_TRY(ntt_run(ctx, args));
-      ETP_CUDA(ctx, cudaEventRecord(slot_free, ctx->stream));
+    // transforms of columns [t0, t0 + tc) of this group, once `arrived` (recorded on the copy stream) has fired
+    auto transform = [&](size_t t0, size_t tc, cudaEvent_t arrived, bool last_of_group) -> int {
+      ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, arrived, 0));
+      uint64_t* src = land + (t0 - c0) * n;
+      NttArgs args;
+      if (is_values) {  // "IFFT": natural -> natural; this group's slice of the LDE buffer is the scratch
+        args.in = src; args.in_stride = n; args.n_in = (uint32_t)n;
+        args.out = b->coeffs + t0 * n; args.out_stride = n;
+        args.scratch = b->lde + t0 * b->lde_n(); args.scratch_stride = b->lde_n();
+        args.log_n = b->log_n; args.n_cols = tc; args.inverse = true; args.natural_out = true;
+        ETP_TRY(ntt_run(ctx, args));
+        if (last_of_group) ETP_CUDA(ctx, cudaEventRecord(slot_free, ctx->stream));
+      } else {
+        k_canon_copy<<<(unsigned)((tc * n + 255) / 256), 256, 0, ctx->stream>>>(src, n, src, n, tc);
+        ETP_LAUNCH_CHECK(ctx);
+      }
+      args = NttArgs();  // "FFT + blinding"
+      args.in = b->coeffs + t0 * n; args.in_stride = n; args.n_in = (uint32_t)n;
+      args.out = b->lde + t0 * b->lde_n(); args.out_stride = b->lde_n();
+      args.log_n = b->log_n + b->rate_bits; args.n_cols = tc;
+      args.coset_shift = gl::GENERATOR;
+      return ntt_run(ctx, args);
+    };
+    if (k == 0 && n_groups > 1) {
+      // nothing hides the first group's copy, so its columns are transformed one by one as they land: the exposed
+      // time is one column's copy instead of eight
+      for (size_t c = 0; c < gc; c++) {
+        cudaEvent_t col_done;
+        ETP_TRY(get_sync_event(ctx, 1 + 2 * n_groups + c, &col_done));
+        ETP_CUDA(ctx, cudaMemcpyAsync(land + c * n, cols[c0 + c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ETP_CUDA(ctx, cudaEventRecord(col_done, ctx->copy_stream));
+        ETP_TRY(transform(c0 + c, 1, col_done, c + 1 == gc));
+      }
     } else {
-      k_canon_copy<<<(unsigned)((gc * n + 255) / 256), 256, 0, ctx->stream>>>(land, n, land, n, gc);
-      ETP_LAUNCH_CHECK(ctx);
+      for (size_t c = 0; c < gc; c++)
+        ETP_CUDA(ctx, cudaMemcpyAsync(land + c * n, cols[c0 + c], n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      ETP_CUDA(ctx, cudaEventRecord(h2d_done, ctx->copy_stream));
+      ETP_TRY(transform(c0, gc, h2d_done, true));
     }
-    args = NttArgs();  // "FFT + blinding"
-    args.in = b->coeffs + c0 * n; args.in_stride = n; args.n_in = (uint32_t)n;
-    args.out = b->lde + c0 * b->lde_n(); args.out_stride = b->lde_n();
-    args.log_n = b->log_n + b->rate_bits; args.n_cols = gc;
-    args.coset_shift = gl::GENERATOR;
-    ETP_TRY(ntt_run(ctx, args));
     ETP_TRY(launch_leaf_hash(ctx, merkle::single_src(b->lde, b->lde_n(), (int)C), (int)c0, (int)(c0 + gc), (int)C, 0,
                              (uint32_t)b->lde_n(), b->levels));
   }
