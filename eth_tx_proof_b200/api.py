@@ -61,6 +61,8 @@ def load_library():
         "etp_ctx_trim": (i32, [vp]),
         "etp_ctx_cached_bytes": (C.c_size_t, [vp]),
         "etp_host_poseidon_permute": (None, [C.POINTER(C.c_uint64)]),
+        "etp_host_pin": (i32, [vp, vp, sz]),
+        "etp_host_unpin": (i32, [vp, vp]),
         "etp_dev_alloc": (i32, [vp, sz, pp]),
         "etp_dev_free": (i32, [vp, vp]),
         "etp_dev_upload": (i32, [vp, vp, vp, sz]),
@@ -184,6 +186,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.L.etp_ctx_launch_count(self.h))
+
+    def pin(self, array: np.ndarray):
+        """Page-lock a host array in place (etp_host_pin); call unpin(array) before it is freed."""
+        self.check(self.L.etp_host_pin(self.h, C.c_void_p(array.ctypes.data), array.nbytes))
+
+    def unpin(self, array: np.ndarray):
+        self.check(self.L.etp_host_unpin(self.h, C.c_void_p(array.ctypes.data)))
 
     def trim(self):
         """Return the context's cached device blocks to the CUDA runtime (etp_ctx_trim)."""

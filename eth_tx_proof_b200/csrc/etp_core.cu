@@ -95,6 +95,20 @@ extern "C" int etp_dev_free(etp_ctx* ctx, void* ptr) {
   ETP_CUDA(ctx, cudaFree(ptr));
   return ETP_OK;
 }
+// Page-locks caller-owned host memory (cudaHostRegister) so that the *_host entry points copy from it at full PCIe speed
+// and asynchronously; pageable memory works too, but its copies are staged by the driver and block the calling thread.
+extern "C" int etp_host_pin(etp_ctx* ctx, void* ptr, size_t bytes) {
+  etp_bind(ctx);
+  if (!ctx || !ptr || !bytes) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return ETP_OK;
+}
+extern "C" int etp_host_unpin(etp_ctx* ctx, void* ptr) {
+  etp_bind(ctx);
+  if (!ctx || !ptr) return ETP_ERR_INVALID;
+  ETP_CUDA(ctx, cudaHostUnregister(ptr));
+  return ETP_OK;
+}
 extern "C" int etp_dev_upload(etp_ctx* ctx, void* dst, const void* src, size_t bytes) {
   etp_bind(ctx);
   if (!ctx) return ETP_ERR_INVALID;

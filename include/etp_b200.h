@@ -62,6 +62,10 @@ void etp_host_poseidon_permute(uint64_t state[12]);
  * etp_ctx_trim returns the cached blocks to the CUDA runtime; etp_ctx_cached_bytes reports how much is held. */
 int etp_ctx_trim(etp_ctx *ctx);
 size_t etp_ctx_cached_bytes(const etp_ctx *ctx);
+/* Page-lock / release caller-owned host memory (cudaHostRegister): the *_host entry points then copy from it at full PCIe
+ * speed, overlapped with the transforms.  Optional: pageable memory is accepted everywhere, its copies are just slower. */
+int etp_host_pin(etp_ctx *ctx, void *ptr, size_t bytes);
+int etp_host_unpin(etp_ctx *ctx, void *ptr);
 /* device memory helpers (cudaMalloc / cudaFree / cudaMemcpyAsync on the context's stream + sync) */
 int etp_dev_alloc(etp_ctx *ctx, size_t bytes, void **out);
 int etp_dev_free(etp_ctx *ctx, void *ptr);

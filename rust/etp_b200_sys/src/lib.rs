@@ -15,6 +15,8 @@ extern "C" {
     pub fn etp_ctx_create(device: c_int, out: *mut *mut etp_ctx) -> c_int;
     pub fn etp_ctx_destroy(ctx: *mut etp_ctx);
     pub fn etp_ctx_trim(ctx: *mut etp_ctx) -> c_int;
+    pub fn etp_host_pin(ctx: *mut etp_ctx, ptr: *mut c_void, bytes: usize) -> c_int;
+    pub fn etp_host_unpin(ctx: *mut etp_ctx, ptr: *mut c_void) -> c_int;
     pub fn etp_host_poseidon_permute(state: *mut u64);
     pub fn etp_ctx_cached_bytes(ctx: *const etp_ctx) -> usize;
     pub fn etp_last_error(ctx: *const etp_ctx) -> *const c_char;

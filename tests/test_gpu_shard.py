@@ -165,3 +165,21 @@ def test_context_on_another_device_from_a_fresh_thread():
     assert (out["cap"] == want).all()
     assert (out["proof"] == c0.stark_prove(etp.TABLE_MEMORY, syn.memory_trace(8, seed=2))).all()
     c0.close()
+
+
+def test_host_pin_makes_no_difference_to_results(ctx):
+    """etp_host_pin / etp_host_unpin (cudaHostRegister on caller-owned memory): same commitment from pageable and from
+    pinned columns."""
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import synthetic as syn
+
+    vals = syn.random_columns(24, 16, seed=77)  # 12 MiB: below the streaming threshold is fine, the call path is the same
+    cap0 = etp.PolynomialBatch.from_values(ctx, vals, 1, False, 4).cap.copy()
+    ctx.pin(vals)
+    try:
+        cap1 = etp.PolynomialBatch.from_values(ctx, vals, 1, False, 4).cap.copy()
+    finally:
+        ctx.unpin(vals)
+    assert (cap0 == cap1).all()
+    with pytest.raises(etp.EtpError):
+        ctx.unpin(vals)  # not registered any more
