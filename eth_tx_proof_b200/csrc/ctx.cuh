@@ -80,9 +80,11 @@ inline int etp_fail(etp_ctx* ctx, int code, const char* fmt, ...) {
 #define ETP_CUDA(ctx, call)                                                                                  \
   do {                                                                                                       \
     cudaError_t e__ = (call);                                                                                \
-    if (e__ != cudaSuccess)                                                                                  \
+    if (e__ != cudaSuccess) {                                                                                \
+      cudaGetLastError(); /* reported here: must not resurface in a later launch check */                   \
       return etp_fail((ctx), ETP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
                       __LINE__);                                                                             \
+    }                                                                                                        \
   } while (0)
 #define ETP_TRY(expr)            \
   do {                           \
@@ -221,7 +223,7 @@ int batch_commit_from_coeffs(etp_batch* b);
 // host columns -> commit, column group by column group: group k is transformed and absorbed by the leaf
 // sponges while group k+1 crosses PCIe.  is_values: run the iFFT first (from_values) or take the columns as
 // coefficients (from_coeffs).
-int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values);
+int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values, uint64_t* keep_values);
 int launch_leaf_hash(etp_ctx* ctx, const merkle::LeafSrc& src, int c_begin, int c_end, int n_cols_total, uint32_t row0,
                      uint32_t n_rows, uint64_t* digests);
 int get_sync_event(etp_ctx* ctx, size_t i, cudaEvent_t* out);

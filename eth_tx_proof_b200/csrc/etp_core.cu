@@ -617,7 +617,9 @@ static size_t stream_group_cols(const etp_batch* b) {
 
 __global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* dst, size_t n, size_t n_cols);
 
-int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values) {
+// keep_values (device, n_cols x n, values only): the columns land there and stay (a prover needs the trace itself for its
+// helper columns) instead of passing through the two staging slots.
+int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values, uint64_t* keep_values) {
   etp_ctx* ctx = b->ctx;
   const size_t n = b->n(), C = b->n_cols, G = stream_group_cols(b);
   // group boundaries (multiples of 8 columns).  The first group is a single sponge chunk: its copy is the only one
@@ -637,7 +639,8 @@ int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, b
     if (!cols[c]) return etp_fail(ctx, ETP_ERR_INVALID, "null column %zu", c);
   DevBuf<uint64_t> stage(ctx);
   const size_t slot = (G + 8) * n;
-  if (is_values) ETP_TRY(stage.alloc(2 * slot));
+  const bool staged = is_values && !keep_values;
+  if (staged) ETP_TRY(stage.alloc(2 * slot));
   cudaEvent_t ready;
   ETP_TRY(get_sync_event(ctx, 0, &ready));
   cudaEventRecord(b->ev[0], ctx->stream);
@@ -647,11 +650,11 @@ int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, b
   ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ready, 0));
   for (size_t k = 0; k < n_groups; k++) {
     const size_t c0 = bounds[k], gc = bounds[k + 1] - c0;
-    uint64_t* land = is_values ? stage.p + (k & 1) * slot : b->coeffs + c0 * n;
+    uint64_t* land = staged ? stage.p + (k & 1) * slot : (is_values ? keep_values + c0 * n : b->coeffs + c0 * n);
     cudaEvent_t h2d_done, slot_free;
     ETP_TRY(get_sync_event(ctx, 1 + 2 * k, &h2d_done));
     ETP_TRY(get_sync_event(ctx, 2 + 2 * k, &slot_free));
-    if (is_values && k >= 2) {  // the staging slot is free once the iFFT of group k-2 has consumed it
+    if (staged && k >= 2) {  // the staging slot is free once the iFFT of group k-2 has consumed it
       cudaEvent_t prev;
       ETP_TRY(get_sync_event(ctx, 2 + 2 * (k - 2), &prev));
       ETP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, prev, 0));
@@ -718,7 +721,7 @@ extern "C" int etp_batch_from_values_host(etp_ctx* ctx, const uint64_t* const* c
   if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
-  int rc = batch_commit_from_host_streamed(b, cols, true);
+  int rc = batch_commit_from_host_streamed(b, cols, true, nullptr);
   if (rc != ETP_OK) { etp_batch_free(b); return rc; }
   *out = b;
   return ETP_OK;
@@ -730,7 +733,7 @@ extern "C" int etp_batch_from_coeffs_host(etp_ctx* ctx, const uint64_t* const* c
   if (!ctx || !out || (!cols && n_cols)) return ETP_ERR_INVALID;
   etp_batch* b;
   ETP_TRY(batch_create(ctx, n_cols, log_n, rate_bits, blinding, cap_height, &b));
-  int rc = batch_commit_from_host_streamed(b, cols, false);
+  int rc = batch_commit_from_host_streamed(b, cols, false, nullptr);
   if (rc != ETP_OK) { etp_batch_free(b); return rc; }
   *out = b;
   return ETP_OK;

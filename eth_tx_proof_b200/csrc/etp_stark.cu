@@ -335,7 +335,11 @@ struct FriLayer {
   std::vector<uint64_t> cap;
 };
 
-int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t stride, const uint64_t* pi_in, uint64_t* proof) {
+// trace_host != nullptr: the trace (n_cols x n, column-major, stride n) is still on the host; trace_dev is an empty device
+// buffer of the same shape that the streamed trace commit fills column group by column group while it transforms and
+// hashes the groups that have already arrived (etp_stark_prove_host).
+int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t stride, const uint64_t* pi_in, uint64_t* proof,
+                    const uint64_t* trace_host = nullptr) {
   TableInfo ti;
   if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
   if (log_n < 1 || log_n + RATE_BITS > 30) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported degree_bits %d", log_n);
@@ -363,7 +367,13 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
 
   // ---- prove(): trace commitment; the challenger observes the public inputs, then the trace cap
   ETP_TRY(batch_create(ctx, ti.cols, log_n, RATE_BITS, 0, CAP_HEIGHT, &B.trace));
-  ETP_TRY(batch_commit_from_values(B.trace, trace_dev, stride));
+  if (trace_host) {
+    std::vector<const uint64_t*> cols(ti.cols);
+    for (int c = 0; c < ti.cols; c++) cols[c] = trace_host + (size_t)c * n;
+    ETP_TRY(batch_commit_from_host_streamed(B.trace, cols.data(), true, const_cast<uint64_t*>(trace_dev)));
+  } else {
+    ETP_TRY(batch_commit_from_values(B.trace, trace_dev, stride));
+  }
   timer.mark("trace commit (IFFT + FFT + Merkle tree)");
   hostf::Challenger ch;
   ch.observe(pi, ti.n_pi);
@@ -747,9 +757,8 @@ extern "C" int etp_stark_prove_host(etp_ctx* ctx, int table, int log_n, const ui
   const size_t n = (size_t)1 << log_n;
   DevBuf<uint64_t> d(ctx);
   ETP_TRY(d.alloc((size_t)ti.cols * n));
-  ETP_CUDA(ctx, cudaMemcpyAsync(d.p, trace, (size_t)ti.cols * n * 8, cudaMemcpyHostToDevice, ctx->stream));
   uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
-  return stark_prove_dev(ctx, table, log_n, d.p, n, public_inputs ? public_inputs : zero, proof_out);
+  return stark_prove_dev(ctx, table, log_n, d.p, n, public_inputs ? public_inputs : zero, proof_out, trace);
 }
 
 extern "C" int etp_last_prove_timings(const etp_ctx* ctx, const char** names, float* ms, int max) {
