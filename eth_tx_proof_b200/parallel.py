@@ -132,7 +132,13 @@ class ProverPool:
     (tools/prove_concurrent.py): 2 contexts give +8 % proofs/min at 2^22 rows and +45 % at 2^16; a third one
     gains nothing.  The library calls release the GIL (ctypes), so plain threads suffice."""
 
-    def __init__(self, device: int, workers: int = 2):
+    def __init__(self, device: int, workers: int = 2, contexts: Sequence[Any] = None):
+        """`contexts`: ready-made contexts to drive instead of creating `workers` new ones on `device`."""
+        if contexts is not None:
+            self.contexts = list(contexts)
+            if not self.contexts:
+                raise ValueError("contexts must not be empty")
+            return
         import eth_tx_proof_b200 as etp
 
         if workers < 1:

@@ -109,3 +109,44 @@ def test_column_split_plan_covers_columns_rows_and_cap():
         parallel.column_split_plan(16, 64, 1, 0, 4)   # fewer cap subtrees than ranks
     with pytest.raises(ValueError):
         parallel.column_split_plan(16, 64, 4, 0, 3)
+
+
+def test_prover_pool_scheduling_and_error_propagation():
+    """ProverPool.map without a GPU (stand-in contexts): job i runs on context i % workers, in submission order per
+    context, results come back in job order, and a failure on a worker thread is raised on the caller."""
+    import threading
+
+    from eth_tx_proof_b200 import parallel
+
+    class Fake:
+        def __init__(self, name):
+            self.name, self.seen, self.threads = name, [], set()
+
+        def close(self):
+            self.closed = True
+
+    ctxs = [Fake("a"), Fake("b"), Fake("c")]
+    pool = parallel.ProverPool(0, contexts=ctxs)
+
+    def fn(c, job):
+        c.seen.append(job)
+        c.threads.add(threading.get_ident())
+        return (c.name, job * job)
+
+    out = pool.map(fn, list(range(10)))
+    assert out == [("abc"[i % 3], i * i) for i in range(10)]
+    assert ctxs[0].seen == [0, 3, 6, 9] and ctxs[1].seen == [1, 4, 7] and ctxs[2].seen == [2, 5, 8]
+    assert all(len(c.threads) == 1 for c in ctxs) and threading.get_ident() not in ctxs[0].threads
+    assert pool.map(fn, []) == []
+
+    def boom(c, job):
+        if job == 4:
+            raise RuntimeError("job 4 failed")
+        return job
+
+    with pytest.raises(RuntimeError, match="job 4 failed"):
+        pool.map(boom, list(range(6)))
+    pool.close()
+    assert all(getattr(c, "closed", False) for c in ctxs)
+    with pytest.raises(ValueError):
+        parallel.ProverPool(0, contexts=[])
