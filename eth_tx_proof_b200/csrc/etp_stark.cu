@@ -263,6 +263,19 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
   q.lag_first = lag.p; q.lag_last = lag.p + size;
   ETP_TRY(qvals.alloc((size_t)n_alphas * size));
   q.out = qvals.p;
+  // powers of the alphas for the consumer's power-form fold: constraint i of N is weighted by alpha^(N-1-i)
+  if (ti.reg) q.n_constraints = (int)ti.reg->prog.n_constraints;
+  else if (table == ETP_TABLE_FIBONACCI) q.n_constraints = stark::Table<0>::CONSTRAINTS;
+  else q.n_constraints = stark::Table<1>::CONSTRAINTS + stark::Table<1>::LOOKUP_CONSTRAINTS_PER_CHALLENGE * n_lookup_ch;
+  DevBuf<uint64_t> apow(ctx);
+  std::vector<uint64_t> apow_host((size_t)n_alphas * q.n_constraints);
+  for (int j = 0; j < n_alphas; j++) {
+    uint64_t cur = 1;
+    for (int e = 0; e < q.n_constraints; e++) { apow_host[(size_t)j * q.n_constraints + e] = gl::canon(cur); cur = gl::mul(cur, q.alphas[j]); }
+  }
+  ETP_TRY(apow.alloc(apow_host.size() ? apow_host.size() : 1));
+  ETP_CUDA(ctx, cudaMemcpyAsync(apow.p, apow_host.data(), apow_host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  q.alpha_pows = apow.p;
   if (ti.reg) {
     void* args[] = {(void*)&q};
     ETP_CUDA(ctx, cudaLaunchKernel((const void*)ti.reg->kernel.kernel, dim3(gb), dim3(128), args, 0, ctx->stream));

@@ -12,23 +12,52 @@ namespace stark {
 constexpr int MAX_CHALLENGES = 2;
 constexpr int MAX_PUBLIC_INPUTS = 16;
 
+// ---- 192-bit lazy accumulator: a sum of products of two field elements, reduced once -------------------------
+struct Acc192 {
+  uint64_t w0, w1;
+  uint32_t w2;
+};
+__device__ __forceinline__ void mac192(Acc192& a, uint64_t c, uint64_t u) {
+  const unsigned __int128 p = (unsigned __int128)c * u;
+  const uint64_t pl = (uint64_t)p, ph = (uint64_t)(p >> 64);
+  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(a.w0), "+l"(a.w1), "+r"(a.w2) : "l"(pl), "l"(ph));
+}
+// w0 + 2^64 w1 + 2^128 w2 with 2^128 == -2^32 (mod p); w2 < 2^31
+__device__ __forceinline__ uint64_t reduce192(const Acc192& a) {
+  return gl::sub_c(gl::reduce128(a.w0, a.w1), (uint64_t)a.w2 << 32);
+}
+
 // ---- ConstraintConsumer ------------------------------------------------------------------------
+// Upstream folds constraint i into acc_j <- acc_j * alpha_j + c_i * mult_i (mult = 1, x - g^-1, L_first, L_last).  With N
+// constraints in all that is  sum_i c_i mult_i alpha_j^(N-1-i): here the powers come from a table (computed per proof on
+// the host) and the sums are accumulated without modular reduction, one 192-bit accumulator per challenge for the plain
+// constraints and one for the transition constraints (their common factor x - g^-1 is applied once at the end): a wide
+// multiply-add per constraint and challenge instead of a field multiplication and a field addition.
 struct Consumer {
-  uint64_t alphas[MAX_CHALLENGES], acc[MAX_CHALLENGES];
+  Acc192 plain[MAX_CHALLENGES], trans[MAX_CHALLENGES];
+  const uint64_t* apow;  // [n][n_constraints]: alpha_j^e
   uint64_t z_last, lagrange_first, lagrange_last;
-  int n;
+  int n, n_constraints, idx;
 #if defined(ETP_COMPACT_CODE)
-  __device__ __noinline__ void constraint(uint64_t c) {
+  __device__ __noinline__ void emit(uint64_t c, int is_transition) {
 #else
-  __device__ __forceinline__ void constraint(uint64_t c) {
+  __device__ __forceinline__ void emit(uint64_t c, int is_transition) {
 #endif
+    const int e = n_constraints - 1 - idx;
+    idx++;
 #pragma unroll
     for (int j = 0; j < MAX_CHALLENGES; j++)
-      if (j < n) acc[j] = gl::add(gl::mul(acc[j], alphas[j]), c);
+      if (j < n) {
+        const uint64_t a = __ldg(apow + (size_t)j * n_constraints + e);
+        if (is_transition) mac192(trans[j], c, a);
+        else mac192(plain[j], c, a);
+      }
   }
-  __device__ __forceinline__ void transition(uint64_t c) { constraint(gl::mul(c, z_last)); }
-  __device__ __forceinline__ void first_row(uint64_t c) { constraint(gl::mul(c, lagrange_first)); }
-  __device__ __forceinline__ void last_row(uint64_t c) { constraint(gl::mul(c, lagrange_last)); }
+  __device__ __forceinline__ void constraint(uint64_t c) { emit(c, 0); }
+  __device__ __forceinline__ void transition(uint64_t c) { emit(c, 1); }
+  __device__ __forceinline__ void first_row(uint64_t c) { emit(gl::mul(c, lagrange_first), 0); }
+  __device__ __forceinline__ void last_row(uint64_t c) { emit(gl::mul(c, lagrange_last), 0); }
+  __device__ __forceinline__ uint64_t result(int j) const { return gl::add(reduce192(plain[j]), gl::mul(reduce192(trans[j]), z_last)); }
 };
 
 struct QuotientParams {
@@ -47,6 +76,8 @@ struct QuotientParams {
   uint64_t last;         // g^-1
   uint64_t alphas[MAX_CHALLENGES];
   int n_alphas;
+  const uint64_t* alpha_pows;  // device, [n_alphas][n_constraints]: alpha_j^e (Consumer)
+  int n_constraints;           // constraints the table emits per row, lookups included
   uint64_t lookup_ch[MAX_CHALLENGES];
   int n_lookup_ch;
   uint64_t pi[MAX_PUBLIC_INPUTS];
@@ -72,8 +103,11 @@ __device__ __forceinline__ bool quotient_begin(const QuotientParams& q, RowCtx& 
   const uint32_t i_next = (r.i + q.next_step) & (size - 1);
   r.p_next = gl::bitrev32(i_next << q.step_log, q.log_lde);
   r.cs.n = q.n_alphas;
+  r.cs.n_constraints = q.n_constraints;
+  r.cs.idx = 0;
+  r.cs.apow = q.alpha_pows;
 #pragma unroll
-  for (int j = 0; j < MAX_CHALLENGES; j++) { r.cs.alphas[j] = q.alphas[j]; r.cs.acc[j] = 0; }
+  for (int j = 0; j < MAX_CHALLENGES; j++) { r.cs.plain[j] = Acc192{0, 0, 0}; r.cs.trans[j] = Acc192{0, 0, 0}; }
   const uint64_t x = q.coset.get(r.i);
   r.cs.z_last = gl::sub(x, q.last);
   r.cs.lagrange_first = q.lag_first[r.p];
@@ -85,7 +119,7 @@ __device__ __forceinline__ void quotient_end(const QuotientParams& q, const RowC
   const uint64_t dinv = q.zh_inv[r.i & (q.next_step - 1)];
 #pragma unroll
   for (int j = 0; j < MAX_CHALLENGES; j++)
-    if (j < q.n_alphas) q.out[(size_t)j * size + r.i] = gl::mul(r.cs.acc[j], dinv);
+    if (j < q.n_alphas) q.out[(size_t)j * size + r.i] = gl::mul(r.cs.result(j), dinv);
 }
 
 }  // namespace stark

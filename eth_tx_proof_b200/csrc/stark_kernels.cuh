@@ -33,6 +33,7 @@ struct Table;
 template <>
 struct Table<0> {
   static constexpr int COLS = 2, AUX = 0;
+  static constexpr int CONSTRAINTS = 5, LOOKUP_CONSTRAINTS_PER_CHALLENGE = 0;
   __device__ static __forceinline__ void eval(const uint64_t* lv, const uint64_t* nv, const uint64_t* pi, Consumer& c) {
     c.first_row(gl::sub(lv[0], pi[0]));
     c.first_row(gl::sub(lv[1], pi[1]));
@@ -47,6 +48,7 @@ struct Table<0> {
 template <>
 struct Table<1> {
   static constexpr int COLS = 21, AUX = 4;
+  static constexpr int CONSTRAINTS = 40, LOOKUP_CONSTRAINTS_PER_CHALLENGE = 3;
   __device__ static __forceinline__ void eval(const uint64_t* lv, const uint64_t* nv, const uint64_t*, Consumer& c) {
     const uint64_t one = 1;
     const uint64_t filter = lv[M_FILTER];
@@ -264,20 +266,7 @@ struct ExtPowTable {
   }
 };
 constexpr int OPEN_THREADS = 256, OPEN_CHUNK = 32;
-// 192-bit lazy accumulator for dot products of field elements: sum of <= 2^32 products of two u64, reduced once.
-struct Acc192 {
-  uint64_t w0, w1;
-  uint32_t w2;
-};
-__device__ __forceinline__ void mac192(Acc192& a, uint64_t c, uint64_t u) {
-  const unsigned __int128 p = (unsigned __int128)c * u;
-  const uint64_t pl = (uint64_t)p, ph = (uint64_t)(p >> 64);
-  asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(a.w0), "+l"(a.w1), "+r"(a.w2) : "l"(pl), "l"(ph));
-}
-// w0 + 2^64 w1 + 2^128 w2 with 2^128 == -2^32 (mod p); w2 < 2^31
-__device__ __forceinline__ uint64_t reduce192(const Acc192& a) {
-  return gl::sub_c(gl::reduce128(a.w0, a.w1), (uint64_t)a.w2 << 32);
-}
+// (Acc192 / mac192 / reduce192: quotient_rt.cuh)
 // grid: (ceil(n / (OPEN_THREADS*OPEN_CHUNK)), n_polys).  Thread t of a block owns the strip of OPEN_CHUNK consecutive
 // coefficients starting at s = (block * OPEN_THREADS + t) * OPEN_CHUNK of ONE polynomial and computes
 //   z^s * sum_b c_{s+b} z^b   for z = z0 and z = z1,
