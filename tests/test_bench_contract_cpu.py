@@ -1,4 +1,4 @@
-"""The bench line contract, checked on the committed end-of-round line (profiles/r01_bench_2p22x128_v8.json) and on the
+"""The bench line contract, checked on the committed end-of-round line (profiles/r01_bench_2p22x128_v9.json) and on the
 reference-arm line: every key the driver reads is present and of the right kind, the numbers are consistent with each
 other, and bench.py still parses.  No GPU needed."""
 import ast
@@ -16,7 +16,7 @@ def _load(name):
 
 
 def test_bench_line_contract():
-    d = _load("r01_bench_2p22x128_v8.json")
+    d = _load("r01_bench_2p22x128_v9.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
