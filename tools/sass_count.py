@@ -4,7 +4,7 @@
   python tools/sass_count.py file.cubin                    plain per-function counts
   python tools/sass_count.py file.cubin --poseidon KERNEL  dynamic counts of one Poseidon permutation:
       the rolled loops of poseidon::permute are weighted by their trip counts (full-round loop x8,
-      paired partial-round loop x11, half loop x2, out-of-line sbox7_pair x40).
+      paired partial-round loop x11, half loop x2, out-of-line sbox7_quad x24).
 
 Ports (B200, measured in profiles/): "A" = ALU + FP64 (shared issue port, 2 clk per warp instruction),
 "B" = FMA pipe (IMAD 2 clk, IMAD.WIDE with a 64-bit addend ~5.2 clk, IMAD.HI ~4.3 clk).
@@ -88,7 +88,7 @@ def main():
                 k = classify(s)
                 weight = 1
                 if call_target is not None and addr >= call_target:
-                    weight = 40
+                    weight = 24  # three sbox7_quad calls per full round, 8 full rounds
                 else:
                     for rng, ww in w.items():
                         if rng[0] <= addr <= rng[1]:
