@@ -1,4 +1,4 @@
-"""The bench line contract, checked on the committed end-of-round line (profiles/r01_bench_2p22x128_v9.json) and on the
+"""The bench line contract, checked on the committed end-of-round line (profiles/r01_bench_2p22x128_v10.json) and on the
 reference-arm line: every key the driver reads is present and of the right kind, the numbers are consistent with each
 other, and bench.py still parses.  No GPU needed."""
 import ast
@@ -16,7 +16,7 @@ def _load(name):
 
 
 def test_bench_line_contract():
-    d = _load("r01_bench_2p22x128_v9.json")
+    d = _load("r01_bench_2p22x128_v10.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -41,7 +41,7 @@ def test_bench_line_contract():
 
 
 def test_reference_arm_line_contract():
-    d = _load("r01_bench_reference_arm_v7.json")
+    d = _load("r01_bench_reference_arm_v10.json")
     assert d["impl"] == "reference" and d["metric"] == "commit_hbm_gbs" and d["unit"] == "GB/s"
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
