@@ -53,10 +53,11 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
   return gl::mul(x3, x4);
 }
 
-// Two S-boxes behind one call.  The full rounds go through this out-of-line copy so that the whole
+// Several S-boxes behind one call.  The full rounds go through an out-of-line copy so that the whole
 // permutation (full-round loop + paired partial-round loop) stays below the 32 KB instruction cache:
 // with the eleven S-boxes inlined the kernel stalled on instruction fetch (profiles/, no_instruction).
-// Arguments and results travel in registers (10 instructions of call overhead per pair).
+// Arguments and results travel in registers (~10 instructions of call overhead per call); the default is
+// three 4-lane calls per full round (sbox7_quad), -DETP_SBOX_PAIRS selects the older five 2-lane calls.
 #ifndef ETP_SBOX_PAIRS
 #define ETP_SBOX_QUAD 1  // full-round S-boxes through three 4-lane calls (measured 1.3 % faster than five 2-lane calls + 2 inline)
 #endif
