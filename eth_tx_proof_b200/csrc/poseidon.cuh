@@ -59,7 +59,9 @@ __device__ __forceinline__ uint64_t sbox7(uint64_t x) {
 // Arguments and results travel in registers (~10 instructions of call overhead per call); the default is
 // three 4-lane calls per full round (sbox7_quad), -DETP_SBOX_PAIRS selects the older five 2-lane calls.
 #ifndef ETP_SBOX_PAIRS
-#define ETP_SBOX_QUAD 1  // full-round S-boxes through three 4-lane calls (measured 1.3 % faster than five 2-lane calls + 2 inline)
+#define ETP_SBOX_QUAD 1  // full-round S-boxes of all twelve lanes through out-of-line calls (1.3 % faster than five 2-lane calls + 2 inline)
+// (-DETP_SBOX_HEX: two 6-lane calls per round; 0.4 % faster in the microbenchmark, 0.5 % slower in the leaf kernel, where
+// the call needs one more live register than the 72 the occupancy allows)
 #endif
 #if defined(ETP_COUNT_UNROLL)  // instruction-count builds (tools/sass_count.py): everything inline and unrolled
 #define ETP_ROLL _Pragma("unroll")
@@ -82,6 +84,14 @@ static __device__ ETP_SBOX_PAIR_ATTR ulonglong4 sbox7_quad(uint64_t a, uint64_t 
   r.y = sbox7(b);
   r.z = sbox7(c);
   r.w = sbox7(d);
+  return r;
+}
+#endif
+#if defined(ETP_SBOX_HEX)
+struct U64x6 { uint64_t v[6]; };
+static __device__ ETP_SBOX_PAIR_ATTR U64x6 sbox7_hex(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e, uint64_t f) {
+  U64x6 r;
+  r.v[0] = sbox7(a); r.v[1] = sbox7(b); r.v[2] = sbox7(c); r.v[3] = sbox7(d); r.v[4] = sbox7(e); r.v[5] = sbox7(f);
   return r;
 }
 #endif
@@ -244,7 +254,14 @@ __device__ __forceinline__ void permute(uint64_t (&s)[12]) {
   for (int half = 0; half < 2; half++) {
     ETP_ROLL
     for (int i = 0; i < HALF_FULL; i++, f++) {
-#if defined(ETP_SBOX_QUAD)
+#if defined(ETP_SBOX_HEX)
+#pragma unroll
+      for (int k = 0; k < 12; k += 6) {
+        const U64x6 q = sbox7_hex(s[k], s[k + 1], s[k + 2], s[k + 3], s[k + 4], s[k + 5]);
+#pragma unroll
+        for (int j = 0; j < 6; j++) s[k + j] = q.v[j];
+      }
+#elif defined(ETP_SBOX_QUAD)
       // lane 0 arrives here WITHOUT its S-box (see below): all twelve lanes go through three quad calls
 #pragma unroll
       for (int k = 0; k < 12; k += 4) {
