@@ -116,29 +116,61 @@ def cpu_commit_gbs(log_n, cols, repeats=1):
     return commit_bytes(log_n, cols) / best / 1e9, best, oracle.num_threads()
 
 
+def workload_config(log_n, cols):
+    """`config` of both arms (the driver compares them): the workload, not how an arm samples it."""
+    n = 1 << log_n
+    return {"workload": f"PolynomialBatch::from_values commit, 2^{log_n} x {cols} Goldilocks, rate_bits=1, cap_height=4, "
+                        "Poseidon-12 (BASELINE.json configs[1]); one batch per GPU",
+            "l2": f"inputs ({8 * cols * n >> 20} MiB per batch) are larger than the 126 MB L2; no flush needed",
+            "algorithmic_bytes_per_step": commit_bytes(log_n, cols), "poseidon_permutations_per_step": commit_perms(log_n, cols)}
+
+
+def host_mem_available_gib():
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available / 2**30
+    except Exception:
+        return 0.0
+
+
 def run_reference(args, rank, world):
+    """CPU arm.  Exactly --steps timed steps after --warmup warm-up steps; each step is one commit of a bounded SAMPLE of
+    the workload (2^18 of the 2^22 rows: the same columns, rate, cap and hash; GB/s is size-independent to first order and
+    the smaller problem is the cache-friendlier one, i.e. the sample flatters the CPU).  One more commit at the FULL
+    2^22 x 128 size is timed afterwards when the host has the memory for it (17 GiB) and reported as `full_size`, so the
+    like-for-like figure stands beside the sampled one."""
     if rank != 0:
         return
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host cores (set before liboracle loads)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    steps = max(1, args.steps)
-    for _ in range(min(args.warmup, 1)):
-        cpu_commit_gbs(14, COLS)
-    times = []
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    sample_log_n = min(CPU_SAMPLE_LOG_N, args.log_n)
     threads = 1
-    for _ in range(min(steps, 3)):
-        gbs, dt, threads = cpu_commit_gbs(CPU_SAMPLE_LOG_N, COLS)
+    for _ in range(warmup):
+        cpu_commit_gbs(min(14, sample_log_n), COLS)  # warm-up: thread pool, page faults, constant tables
+    times = []
+    for _ in range(steps):
+        _, dt, threads = cpu_commit_gbs(sample_log_n, COLS)
         times.append(dt)
     ms = 1e3 * statistics.mean(times)
-    value = commit_bytes(CPU_SAMPLE_LOG_N, COLS) / (ms / 1e3) / 1e9
-    sample = f"from_values 2^{CPU_SAMPLE_LOG_N} x {COLS} (rows/16 of the 2^{LOG_N} workload), {len(times)} timed commits"
+    value = commit_bytes(sample_log_n, COLS) / (ms / 1e3) / 1e9
+    sample = (f"each step = oracle from_values 2^{sample_log_n} x {COLS} (rows/{1 << (args.log_n - sample_log_n)} of the 2^{args.log_n} "
+              f"workload), {len(times)} timed steps after {warmup} warm-up commits, all {threads} host threads; "
+              "C+OpenMP restatement, NOT plonky2 (the Rust reference cannot be built here)")
+    full = None
+    if not args.skip_full and world == 1 and args.log_n > sample_log_n and host_mem_available_gib() > 48:
+        gbs, dt, _ = cpu_commit_gbs(args.log_n, COLS)
+        full = {"workload": f"from_values 2^{args.log_n} x {COLS}, 1 commit", "seconds": dt, "value": gbs, "unit": "GB/s"}
     print(json.dumps({
         "impl": "reference", "metric": "commit_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": len(times),
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"PolynomialBatch::from_values commit, 2^{LOG_N} x {COLS}, rate_bits=1, cap_height=4, Poseidon-12",
-                   "note": "CPU arm = oracle port (C + OpenMP restatement of plonky2), NOT plonky2 itself: the Rust reference cannot be built here"},
+        "warmup": warmup, "ms_per_step": ms, "ms_per_step_is": f"one SAMPLE step (2^{sample_log_n} rows); a full 2^{args.log_n}-row "
+        f"step is {1 << (args.log_n - sample_log_n)}x that (see full_size)", "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args.log_n, COLS),
+        "note": "CPU arm = oracle port (C + OpenMP restatement of plonky2), NOT plonky2 itself: the Rust reference cannot be built here; "
+                "it runs on ONE host regardless of --gpus (rank 0 only)",
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "full_size": full,
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -150,12 +182,30 @@ def run_column_split(etp, ctx, torch, dist, rank, world, log_n, cols, n, nbytes,
     inside the hashing kernel; the cap parts are all-gathered over NCCL."""
     from eth_tx_proof_b200 import parallel
 
-    g2 = torch.Generator(device="cuda").manual_seed(0xC0)
+    import numpy as np
+
+    g2 = torch.Generator(device="cuda").manual_seed(0xC0)  # same seed on every rank: every rank can build the whole table
     c0, c1 = parallel.column_split_plan(cols, 2 * n, CAP_HEIGHT, rank, world)["cols"]
-    xs = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g2)[c0:c1].contiguous()
+    whole = torch.randint(0, 2**62, (cols, n), dtype=torch.int64, device="cuda", generator=g2)
+    xs = whole[c0:c1].contiguous()
     torch.cuda.synchronize()  # the library works on its own stream
+    # parity: rank 0 commits the SAME table unsplit on its own GPU; the assembled cap of the split commit must equal it
+    unsplit_cap = None
+    if rank == 0:
+        ub = etp.PolynomialBatch.from_values_dev(ctx, whole.data_ptr(), n, cols, log_n, RATE_BITS, False, CAP_HEIGHT)
+        unsplit_cap = ub.cap.copy()
+        probe = [0, 1, n, 2 * n - 1]
+        unsplit_rows = ub.leaves_at(probe)
+        del ub
+        ctx.trim()
+    del whole
     shard = etp.BatchShard(ctx, cols, log_n, RATE_BITS, CAP_HEIGHT, rank, world)
     cap0 = parallel.commit_column_split(shard, values_dev=(xs.data_ptr(), n))
+    parity = None
+    if rank == 0:
+        assert (cap0 == unsplit_cap).all(), "column-split cap differs from the unsplit commit of the same table"
+        assert (shard.leaves_at(probe) == unsplit_rows).all(), "rows gathered across GPUs differ from the unsplit commit"
+        parity = "assembled cap and 4 probe rows (read across NVLink) == unsplit from_values of the same table on rank 0"
     for _ in range(2):
         parallel.recommit_column_split(shard, (xs.data_ptr(), n))
     barrier()
@@ -171,6 +221,7 @@ def run_column_split(etp, ctx, torch, dist, rank, world, log_n, cols, n, nbytes,
     return {"workload": f"ONE 2^{log_n} x {cols} table column-split over {world} GPUs (CUDA IPC + NVLink peer loads fused into the "
                         "leaf-hash kernel; cap parts all-gathered over NCCL)", "ms_per_commit": dt * 1e3,
             "value": nbytes / dt / 1e9, "unit": "GB/s", "scaling": "strong",
+            "parity": parity,
             "timed": "local columns resident in HBM -> whole cap on every rank (wall clock incl. 2 barriers, max over ranks)"}
 
 
@@ -186,6 +237,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-split", action="store_true")
+    ap.add_argument("--skip-full", action="store_true", help="reference arm: skip the extra full-size commit")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -212,7 +264,6 @@ def main():
     os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -266,6 +317,8 @@ def main():
     value = world * nbytes / (ms_per_step / 1e3) / 1e9
     phase = {k: v / steps for k, v in phase.items()}
 
+    pipe_rates = ctx.pipe_rates() if rank == 0 else None
+
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.skip_e2e:
@@ -300,7 +353,7 @@ def main():
         from eth_tx_proof_b200 import parallel, synthetic as syn
 
         sl = min(STARK_LOG_N, log_n)
-        n_jobs = 8
+        n_jobs = 8 * world  # weak scaling: 8 segment jobs per GPU
         my_jobs = parallel.shard_jobs(n_jobs, rank, world)
         trace_pinned = torch.from_numpy(syn.memory_trace(sl, seed=7 + rank).view(np.int64)).pin_memory()
         trace = trace_pinned.cuda()
@@ -331,7 +384,7 @@ def main():
         assert all((p == proof).all() for p in proofs), "pooled proofs differ from the single-context proof"
         pool.close()
         stark = {"workload": f"starky prove, memory-shaped table 2^{sl} x 21 (+4 aux, 4 quotient), standard_fast_config; "
-                             f"{n_jobs} independent segment jobs sharded over {world} GPU(s), {STARK_CONTEXTS_PER_GPU} prover contexts per GPU",
+                             f"{n_jobs} independent segment jobs (8 per GPU) sharded over {world} GPU(s), {STARK_CONTEXTS_PER_GPU} prover contexts per GPU",
                  "prove_ms": prove_ms, "prove_host_ms": prove_host_ms, "h2d_bytes_per_proof": int(trace_host.nbytes),
                  "proofs_per_min": n_jobs * 60.0 / dt, "jobs": n_jobs, "contexts_per_gpu": STARK_CONTEXTS_PER_GPU,
                  "proof_bytes": int(proof.size * 8), "phases_ms": phases,
@@ -358,7 +411,7 @@ def main():
             w = pool.contexts.index(c)
             return c.stark_prove_dev(ids[w][k], tables[k][2], dev[k].data_ptr(), 1 << tables[k][2])
 
-        n_tx = 8
+        n_tx = 8 * world  # weak scaling: 8 transactions per GPU
         my_tx = parallel.shard_jobs(n_tx, rank, world)
         flat = [k for _ in my_tx for k in range(len(tables))]
         pool.map(prove_table, list(range(len(tables))) * STARK_CONTEXTS_PER_GPU)  # warm-up: every table on every context
@@ -377,7 +430,7 @@ def main():
         pool.close()
         del dev
         tx = {"workload": "synthetic transaction: 7 table STARK proofs of the evm_arithmetization shapes (SURVEY.md App. B), "
-                          f"shape-only constraint programs, no CTLs, no recursion; {n_tx} transactions sharded over {world} GPU(s), "
+                          f"shape-only constraint programs, no CTLs, no recursion; {n_tx} transactions (8 per GPU) sharded over {world} GPU(s), "
                           f"{STARK_CONTEXTS_PER_GPU} prover contexts per GPU",
               "tx_ms": tx_ms, "tx_per_min": n_tx * 60.0 / dt, "transactions": n_tx, "tables": per_table,
               "timed": "tx_ms: the seven proofs in sequence on one context, traces resident in HBM -> proof bytes on the host; "
@@ -416,20 +469,24 @@ def main():
     achieved = leaf_bytes / (leaf_ms / 1e3) / 1e9
     perms_leaf = (n << RATE_BITS) * ((cols + 7) // 8)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    # integer-pipe roofline of the Poseidon kernels (profiles/README.md, tools/microbench/pipes*.cu): on B200 the integer ALU
-    # and the FP64 unit of a sub-partition share one issue port that accepts a warp instruction every 2 clk (16 lanes/clk), and
-    # that port is what saturates (ncu: alu % + fp64 % of the leaf kernel).  Static SASS counts per permutation from
-    # tools/sass_count.py: 4840 ALU + 4280 FP64 port instructions (the IMAD.WIDE multiplier chains run on the FMA pipe beside it).
-    alu_per_perm, fp64_per_perm = 4840, 4280
-    port_clk_per_perm = 2.0 * (alu_per_perm + fp64_per_perm)
-    perm_peak = 148 * 4 * sm_mhz * 1e6 / port_clk_per_perm * 32
+    # integer-pipe roofline of the Poseidon kernels: the denominator is MEASURED in this run
+    # (etp_bench_pipe_rates: dependent-chain micro-kernels for IMAD.WIDE.U32, IADD3 and DFMA); the numerator is the
+    # ALGORITHMIC multiply count of a permutation, independent of how the kernel is written: 118 S-boxes x 4 field
+    # multiplications x 4 partial products (32x32->64) = 1888, plus 30 MDS layers x 144 coefficients x 2 32-bit planes =
+    # 8640 small-constant multiply-adds -> 10528 MAC32 per permutation.
+    mac32_per_perm = 118 * 4 * 4 + 30 * 144 * 2
     roofline = {"kernel": "merkle::hash_leaves_colmajor", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "dominant kernel is integer/FP64-issue bound (16 Poseidon permutations per 1 KiB row), not HBM bound; see int_pipe"}
-    int_pipe = {"kernel": "merkle::hash_leaves_colmajor", "achieved": perms_leaf / (leaf_ms / 1e3), "peak": perm_peak, "unit": "perm/s",
-                "frac": perms_leaf / (leaf_ms / 1e3) / perm_peak,
-                "model": "shared ALU/FP64 issue port: 148 SM x 4 SMSP x f_sm x 32 lanes / (2 clk x (4840 ALU + 4280 FP64) port instructions per "
-                         "permutation, tools/sass_count.py); f_sm = sampled clock; frac is that port's utilisation (cf. ncu alu % + fp64 %)"}
+    imad_peak = pipe_rates["imad_wide_u32_zero_addend"]
+    int_pipe = {"kernel": "merkle::hash_leaves_colmajor", "achieved": perms_leaf / (leaf_ms / 1e3) * mac32_per_perm, "peak": imad_peak,
+                "unit": "MAC32/s", "frac": perms_leaf / (leaf_ms / 1e3) * mac32_per_perm / imad_peak,
+                "perm_per_s": perms_leaf / (leaf_ms / 1e3), "mac32_per_permutation": mac32_per_perm, "measured_pipe_rates": pipe_rates,
+                "model": "achieved = permutations/s x 10528 algorithmic 32x32->64 multiply-adds (1888 in the S-boxes + 8640 in the 30 MDS "
+                         "layers on 32-bit planes); peak = IMAD.WIDE.U32 issue rate of the whole GPU measured in this run.  The kernel "
+                         "executes the MDS multiply-adds on the FP64 pipe with an algebraic split (4280 DFMA instead of 8640 IMAD), "
+                         "which is how the fraction of the IMAD-only peak gets this high; ncu's issued-instruction count per permutation "
+                         "is in profiles/"}
     ntt_bytes_ifft = 16 * cols * n
     ntt_bytes_lde = 8 * cols * n + 8 * cols * (n << RATE_BITS)
     kernels = [
@@ -449,14 +506,31 @@ def main():
                "sample": f"oracle from_values 2^{CPU_SAMPLE_LOG_N} x {cols} (rows/16 of the workload), 1 commit, all host threads; "
                          "C+OpenMP restatement, NOT plonky2 (the Rust reference cannot be built here)"}
 
+    if cpu is not None and stark is not None:
+        # BASELINE configs[2] "... 1 B200 vs CPU": the oracle's single-table prover (same table, same config) on a bounded
+        # sample of the rows; prove time is ~linear in the rows (NTT log factor aside), so the scaled figure is a lower bound
+        import numpy as np
+
+        import oracle
+        from eth_tx_proof_b200 import synthetic as syn
+
+        sl_cpu = min(18, STARK_LOG_N, log_n)
+        tr = syn.memory_trace(sl_cpu, seed=7)
+        oracle.stark_prove(oracle.TABLE_MEMORY, syn.memory_trace(10, seed=7))  # warm-up (constant tables, thread pool)
+        t0 = time.perf_counter()
+        oracle.stark_prove(oracle.TABLE_MEMORY, tr)
+        dt = time.perf_counter() - t0
+        sl = min(STARK_LOG_N, log_n)
+        stark["cpu_baseline"] = {"prove_ms_sample": dt * 1e3, "prove_ms_scaled": dt * 1e3 * (1 << (sl - sl_cpu)), "cores": oracle.num_threads(),
+                                 "kind": "port", "sample": f"oracle stark_prove, memory-shaped table 2^{sl_cpu} rows (rows/{1 << (sl - sl_cpu)} of the "
+                                 f"2^{sl} workload), 1 proof, all host threads; scaled linearly in the rows; C+OpenMP restatement, NOT starky",
+                                 "speedup_vs_scaled": dt * 1e3 * (1 << (sl - sl_cpu)) / stark["prove_ms"]}
+
     out = {
         "metric": "commit_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": f"PolynomialBatch::from_values commit, 2^{log_n} x {cols} Goldilocks, rate_bits=1, cap_height=4, "
-                               "Poseidon-12 (BASELINE.json configs[1]); one batch per GPU",
-                   "l2": f"inputs ({8 * cols * n >> 20} MiB per batch) are larger than the 126 MB L2; no flush needed",
-                   "algorithmic_bytes_per_step": nbytes, "poseidon_permutations_per_step": commit_perms(log_n, cols)},
+        "config": workload_config(log_n, cols),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
         "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "column_split": split,
     }

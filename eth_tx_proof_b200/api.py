@@ -61,6 +61,7 @@ def load_library():
         "etp_ctx_trim": (i32, [vp]),
         "etp_ctx_cached_bytes": (C.c_size_t, [vp]),
         "etp_host_poseidon_permute": (None, [C.POINTER(C.c_uint64)]),
+        "etp_bench_pipe_rates": (i32, [vp, C.POINTER(C.c_double)]),
         "etp_host_pin": (i32, [vp, vp, sz]),
         "etp_host_unpin": (i32, [vp, vp]),
         "etp_dev_alloc": (i32, [vp, sz, pp]),
@@ -202,6 +203,12 @@ class Context:
     def cached_bytes(self) -> int:
         return int(self.L.etp_ctx_cached_bytes(self.h))
 
+    def pipe_rates(self) -> dict:
+        """Measured issue rates (thread-instructions/s, whole device) of the integer / FP64 pipes (etp_bench_pipe_rates)."""
+        r = (C.c_double * 4)()
+        self.check(self.L.etp_bench_pipe_rates(self.h, r))
+        return {"imad_wide_u32_zero_addend": r[0], "imad_wide_u32_accumulate": r[1], "iadd3": r[2], "dfma": r[3]}
+
     # ---- primitives (parity tests)
     def poseidon_permute(self, states) -> np.ndarray:
         s = _u64(states).reshape(-1, 12).copy()
@@ -258,13 +265,32 @@ class Context:
     def stark_prove(self, table, trace, public_inputs=()) -> np.ndarray:
         """starky::prover::prove(stark, &StarkConfig::standard_fast_config(), trace, public_inputs)."""
         t = _u64(trace)
-        log_n = int(t.shape[1]).bit_length() - 1
+        log_n = self._check_trace_shape(table, t.shape, public_inputs)
         pi = _u64(list(public_inputs) + [0])
         out = np.zeros(self.stark_proof_words(table, log_n), dtype=np.uint64)
         self.check(self.L.etp_stark_prove_host(self.h, table, log_n, _p(t), _p(pi), _p(out)))
         return out
 
+    def _check_trace_shape(self, table, shape, public_inputs) -> int:
+        """The C side reads n_cols x 2^log_n trace words and n_pi public inputs unconditionally: reject anything else
+        here (upstream: assert! panics in prove / PolynomialBatch::from_values)."""
+        n_cols = int(self.L.etp_table_num_columns(self.h, table))
+        if n_cols < 0:
+            raise EtpError(-1, f"unknown table {table}")
+        if len(shape) != 2 or shape[0] != n_cols:
+            raise EtpError(-1, f"trace must be ({n_cols}, 2^k) column-major for table {table}, got {tuple(shape)}")
+        log_n = int(shape[1]).bit_length() - 1
+        if shape[1] < 2 or shape[1] != 1 << log_n:
+            raise EtpError(-1, f"trace length {shape[1]} is not a power of two >= 2")
+        n_pi = int(self.L.etp_table_num_public_inputs(self.h, table))
+        if len(public_inputs) < n_pi:
+            raise EtpError(-1, f"table {table} takes {n_pi} public inputs, got {len(public_inputs)}")
+        return log_n
+
     def stark_prove_dev(self, table, log_n, trace_ptr, col_stride, public_inputs=()) -> np.ndarray:
+        n_pi = int(self.L.etp_table_num_public_inputs(self.h, table))
+        if n_pi < 0 or len(public_inputs) < n_pi or col_stride < (1 << log_n) or not trace_ptr:
+            raise EtpError(-1, "stark_prove_dev: unknown table, too few public inputs, null trace or stride < 2^log_n")
         pi = _u64(list(public_inputs) + [0])
         out = np.zeros(self.stark_proof_words(table, log_n), dtype=np.uint64)
         self.check(self.L.etp_stark_prove_dev(self.h, table, log_n, C.c_void_p(trace_ptr), col_stride, _p(pi), _p(out)))

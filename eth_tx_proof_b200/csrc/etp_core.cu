@@ -40,11 +40,16 @@ extern "C" int etp_ctx_create(int device, etp_ctx** out) {
 // returns every cached (free) block to the runtime; live blocks are untouched
 int dev_cache_trim(etp_ctx* ctx) {
   ETP_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the streamed host commits also write staging / coefficient blocks from copy_stream
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   std::lock_guard<std::mutex> lock(ctx->cache_mutex);
   for (auto& kv : ctx->cache_free) cudaFree(kv.second);
   ctx->cache_free.clear();
   ctx->cache_free_bytes = 0;
+  // full-size twiddle / coset tables (up to 128 MiB each) are rebuilt on demand
+  for (auto& kv : ctx->full_tables) cudaFree(kv.second);
+  ctx->full_tables.clear();
   return ETP_OK;
 }
 extern "C" int etp_ctx_trim(etp_ctx* ctx) {
@@ -58,12 +63,12 @@ extern "C" void etp_ctx_destroy(etp_ctx* ctx) {
   etp_bind(ctx);
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   free_registered_tables(ctx);
   for (auto& kv : ctx->pow_tables) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
-  for (auto& kv : ctx->full_tables) cudaFree(kv.second);
   cudaFree(ctx->d_pow_result);
-  dev_cache_trim(ctx);
+  dev_cache_trim(ctx);  // also frees the full-size tables
   for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // objects the caller never freed
   for (auto e : ctx->sync_events) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->copy_stream);
@@ -206,9 +211,18 @@ static int get_full_table(etp_ctx* ctx, const std::tuple<int, uint64_t, int, int
   if (it != ctx->full_tables.end()) { *out = it->second; return ETP_OK; }
   uint64_t* d = nullptr;
   ETP_CUDA(ctx, cudaMalloc((void**)&d, n * 8));
-  ctx->full_tables.emplace(key, d);
   *out = d;
-  return 1;  // caller must fill it
+  return 1;  // caller must fill it, then keep_full_table() (or cudaFree it if the fill launch failed)
+}
+static int keep_full_table(etp_ctx* ctx, const std::tuple<int, uint64_t, int, int, int>& key, uint64_t* d) {
+  ctx->launches++;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return etp_fail(ctx, ETP_ERR_CUDA, "table fill kernel failed: %s", cudaGetErrorString(e));
+  }
+  ctx->full_tables.emplace(key, d);
+  return ETP_OK;
 }
 
 int ntt_run(etp_ctx* ctx, const NttArgs& a) {
@@ -235,11 +249,12 @@ int ntt_run(etp_ctx* ctx, const NttArgs& a) {
   if (a.coset_shift && !a.inverse) {
     ETP_TRY(get_pow_table(ctx, a.coset_shift, L, 1, &in_pow));
     if (a.n_in <= kMaxFullTable) {
-      int rc = get_full_table(ctx, std::make_tuple(-1, a.coset_shift, (int)a.n_in, 0, 0), a.n_in, &in_full);
+      const auto key = std::make_tuple(-1, a.coset_shift, (int)a.n_in, 0, 0);
+      int rc = get_full_table(ctx, key, a.n_in, &in_full);
       if (rc < 0) return rc;
       if (rc == 1) {
         ntt::fill_pow_full<<<(unsigned)((a.n_in + 255) / 256), 256, 0, ctx->stream>>>(in_pow, a.n_in, in_full);
-        ETP_LAUNCH_CHECK(ctx);
+        ETP_TRY(keep_full_table(ctx, key, in_full));
       }
     }
   }
@@ -274,11 +289,12 @@ int ntt_run(etp_ctx* ctx, const NttArgs& a) {
       if (ul > s) ul = s;
       if (((size_t)1 << (s + B)) <= kMaxFullTable) {
         uint64_t* tab = nullptr;
-        int rc = get_full_table(ctx, std::make_tuple(L, (uint64_t)0, s, B, p.inverse), (size_t)1 << (s + B), &tab);
+        const auto key = std::make_tuple(L, (uint64_t)0, s, B, p.inverse);
+        int rc = get_full_table(ctx, key, (size_t)1 << (s + B), &tab);
         if (rc < 0) return rc;
         if (rc == 1) {
           ntt::fill_pass_twiddles<<<(unsigned)((((size_t)1 << (s + B)) + 255) / 256), 256, 0, ctx->stream>>>(p, B, tab);
-          ETP_LAUNCH_CHECK(ctx);
+          ETP_TRY(keep_full_table(ctx, key, tab));
         }
         p.tw_full = tab;
       }
@@ -619,7 +635,19 @@ __global__ void k_canon_copy(const uint64_t* src, size_t src_stride, uint64_t* d
 
 // keep_values (device, n_cols x n, values only): the columns land there and stay (a prover needs the trace itself for its
 // helper columns) instead of passing through the two staging slots.
+static int batch_commit_from_host_streamed_impl(etp_batch* b, const uint64_t* const* cols, bool is_values, uint64_t* keep_values);
 int batch_commit_from_host_streamed(etp_batch* b, const uint64_t* const* cols, bool is_values, uint64_t* keep_values) {
+  const int rc = batch_commit_from_host_streamed_impl(b, cols, is_values, keep_values);
+  if (rc != ETP_OK) {
+    // H2D copies of later groups may still be in flight on copy_stream while the caller hands the staging /
+    // coefficient blocks back to the cache: drain both streams first
+    cudaStreamSynchronize(b->ctx->copy_stream);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaGetLastError();
+  }
+  return rc;
+}
+static int batch_commit_from_host_streamed_impl(etp_batch* b, const uint64_t* const* cols, bool is_values, uint64_t* keep_values) {
   etp_ctx* ctx = b->ctx;
   const size_t n = b->n(), C = b->n_cols, G = stream_group_cols(b);
   // group boundaries (multiples of 8 columns).  The first group is a single sponge chunk: its copy is the only one
@@ -889,4 +917,95 @@ extern "C" const uint64_t* etp_batch_coeffs_dev(const etp_batch* b, size_t* col_
   if (!b) return nullptr;
   if (col_stride) *col_stride = b->n();
   return b->coeffs;
+}
+
+// =================================================================================================
+// pipe-rate micro-benchmark (bench.py's integer-pipe roofline denominator)
+// =================================================================================================
+// Each kernel issues PIPE_ITERS x PIPE_CHAINS instructions of one kind per thread on independent dependency chains
+// (8 chains x 8 warps per SM sub-partition hide the pipe latency), so elapsed time / instruction count is the
+// sustained issue rate of that pipe.  Timed with CUDA events on the context's stream.
+namespace pipes {
+constexpr int ITERS = 2048, CHAINS = 8, THREADS = 256, BLOCKS_PER_SM = 4;
+__global__ void __launch_bounds__(THREADS) k_imad_wide_zero(uint64_t* out, uint32_t b) {  // IMAD.WIDE.U32 d = a*b + RZ
+  uint64_t acc[CHAINS];
+  for (int i = 0; i < CHAINS; i++) acc[i] = i + threadIdx.x;
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(acc[i]) : "r"((uint32_t)acc[i]), "r"(b));
+  }
+  uint64_t s = 0;
+  for (int i = 0; i < CHAINS; i++) s += acc[i];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(THREADS) k_imad_wide_acc(uint64_t* out, uint32_t b) {  // IMAD.WIDE.U32 d = a*b + d (64-bit addend)
+  uint64_t acc[CHAINS];
+  for (int i = 0; i < CHAINS; i++) acc[i] = i + threadIdx.x;
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((uint32_t)acc[(i + 1) % CHAINS]), "r"(b));
+  }
+  uint64_t s = 0;
+  for (int i = 0; i < CHAINS; i++) s += acc[i];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(THREADS) k_iadd3(uint64_t* out, uint32_t b) {  // integer ALU port
+  uint32_t acc[CHAINS];
+  for (int i = 0; i < CHAINS; i++) acc[i] = i + threadIdx.x;
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(b));
+  }
+  uint32_t s = 0;
+  for (int i = 0; i < CHAINS; i++) s += acc[i];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(THREADS) k_dfma(uint64_t* out, uint32_t b) {  // FP64 pipe (shares the ALU issue port)
+  double acc[CHAINS];
+  const double m = 1.0 + 1e-9 * b, c = 1e-3;
+  for (int i = 0; i < CHAINS; i++) acc[i] = i + threadIdx.x;
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int i = 0; i < CHAINS; i++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(acc[i]) : "d"(m), "d"(c));
+  }
+  double s = 0;
+  for (int i = 0; i < CHAINS; i++) s += acc[i];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = (uint64_t)s;
+}
+}  // namespace pipes
+
+// rates_out[4]: sustained thread-instructions per second of the whole device for
+// [0] IMAD.WIDE.U32 with a zero addend, [1] IMAD.WIDE.U32 accumulating into a 64-bit addend, [2] IADD3, [3] DFMA.
+extern "C" int etp_bench_pipe_rates(etp_ctx* ctx, double rates_out[4]) {
+  etp_bind(ctx);
+  if (!ctx || !rates_out) return ETP_ERR_INVALID;
+  cudaDeviceProp prop;
+  ETP_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  const unsigned blocks = (unsigned)prop.multiProcessorCount * pipes::BLOCKS_PER_SM;
+  DevBuf<uint64_t> out(ctx);
+  ETP_TRY(out.alloc((size_t)blocks * pipes::THREADS));
+  cudaEvent_t e0, e1;
+  ETP_CUDA(ctx, cudaEventCreate(&e0));
+  ETP_CUDA(ctx, cudaEventCreate(&e1));
+  typedef void (*kern_t)(uint64_t*, uint32_t);
+  const kern_t kerns[4] = {pipes::k_imad_wide_zero, pipes::k_imad_wide_acc, pipes::k_iadd3, pipes::k_dfma};
+  int rc = ETP_OK;
+  for (int k = 0; k < 4 && rc == ETP_OK; k++) {
+    float best = 0;
+    for (int rep = 0; rep < 4; rep++) {  // first repetition warms up
+      cudaEventRecord(e0, ctx->stream);
+      kerns[k]<<<blocks, pipes::THREADS, 0, ctx->stream>>>(out.p, 3u);
+      ctx->launches++;
+      cudaEventRecord(e1, ctx->stream);
+      if (cudaEventSynchronize(e1) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = etp_fail(ctx, ETP_ERR_CUDA, "pipe benchmark kernel failed"); break; }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep && (best == 0 || ms < best)) best = ms;
+    }
+    const double instr = (double)blocks * pipes::THREADS * pipes::ITERS * pipes::CHAINS;
+    rates_out[k] = best > 0 ? instr / (best * 1e-3) : 0;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
