@@ -47,6 +47,114 @@ class Expr:
     __rmul__ = __mul__
 
 
+class Column:
+    """starky::lookup::Column: a linear combination of the local row, of the next row, plus a constant."""
+
+    def __init__(self, local=(), next_row=(), constant=0):
+        self.local = [(int(c), int(f) % P) for c, f in local]
+        self.next_row = [(int(c), int(f) % P) for c, f in next_row]
+        self.constant = int(constant) % P
+
+    @classmethod
+    def single(cls, c):
+        return cls([(c, 1)])
+
+    @classmethod
+    def single_next_row(cls, c):
+        return cls((), [(c, 1)])
+
+    @classmethod
+    def constant_(cls, v):
+        return cls((), (), v)
+
+    @classmethod
+    def le_bits(cls, cols):
+        return cls([(c, 1 << i) for i, c in enumerate(cols)])
+
+    @classmethod
+    def lift(cls, c):
+        return c if isinstance(c, Column) else cls.single(c)
+
+    def is_single(self):
+        return len(self.local) == 1 and self.local[0][1] == 1 and not self.next_row and self.constant == 0
+
+    def words(self):
+        w = [len(self.local)]
+        for c, f in self.local:
+            w += [c, f]
+        w.append(len(self.next_row))
+        for c, f in self.next_row:
+            w += [c, f]
+        w.append(self.constant)
+        return w
+
+    def expr(self, b):
+        """Column::eval_with_next as a program expression."""
+        acc = None
+        for c, f in self.local:
+            t = b.lv(c) if f == 1 else b.lv(c) * f
+            acc = t if acc is None else acc + t
+        for c, f in self.next_row:
+            t = b.nv(c) if f == 1 else b.nv(c) * f
+            acc = t if acc is None else acc + t
+        if acc is None:
+            return b.const(self.constant)
+        return acc + self.constant if self.constant else acc
+
+    def eval_table(self, trace, i):
+        """Column::eval_table: row i of a (cols, n) trace of Python ints / numpy u64, next row cyclic."""
+        n = len(trace[0])
+        acc = self.constant
+        for c, f in self.local:
+            acc += int(trace[c][i]) * f
+        for c, f in self.next_row:
+            acc += int(trace[c][(i + 1) % n]) * f
+        return acc % P
+
+
+class Filter:
+    """starky::lookup::Filter: sum of products of two Columns plus a sum of Columns; Default = the constant 1."""
+
+    def __init__(self, products=(), constants=None):
+        self.products = [(Column.lift(a), Column.lift(b)) for a, b in products]
+        self.constants = [Column.constant_(1)] if constants is None and not self.products else [Column.lift(c) for c in (constants or ())]
+
+    def is_default(self):
+        return not self.products and len(self.constants) == 1 and not self.constants[0].local and \
+            not self.constants[0].next_row and self.constants[0].constant == 1
+
+    def words(self):
+        w = [len(self.products)]
+        for a, b in self.products:
+            w += a.words() + b.words()
+        w.append(len(self.constants))
+        for c in self.constants:
+            w += c.words()
+        return w
+
+    def expr(self, b):
+        acc = None
+        for x, y in self.products:
+            t = x.expr(b) * y.expr(b)
+            acc = t if acc is None else acc + t
+        for c in self.constants:
+            t = c.expr(b)
+            acc = t if acc is None else acc + t
+        return acc if acc is not None else b.const(0)
+
+    def eval_table(self, trace, i):
+        acc = 0
+        for x, y in self.products:
+            acc += x.eval_table(trace, i) * y.eval_table(trace, i)
+        for c in self.constants:
+            acc += c.eval_table(trace, i)
+        return acc % P
+
+
+AUXSPEC_MAGIC = 0x3153585541505445  # "ETPAUXS1"
+CH_CTL_BASE = NUM_CHALLENGES  # challenge scalars: lookup challenges [0, 2), then CTL (beta_k, gamma_k) at 2 + 2k, 3 + 2k
+
+
 class ProgramBuilder:
     def __init__(self, n_trace_cols: int, n_public_inputs: int = 0, constraint_degree: int = 3):
         self.n_trace, self.n_pi, self.degree = n_trace_cols, n_public_inputs, constraint_degree
@@ -55,9 +163,14 @@ class ProgramBuilder:
         self.ops: List[Tuple[int, int, int, int]] = []  # (opcode, a, b, imm)
         self._memo = {}
         self.n_constraints = 0
-        self.lookups: List[Tuple[List[int], int, int]] = []
+        self.lookups: List[Tuple[List[int], int, int]] = []  # (columns, table column, frequencies column[, filters])
+        self.ctl_zs: List[Tuple[int, list]] = []  # (challenge index, [(columns, filter)]) in the table's CtlData order
 
     def _op(self, op, a=0, b=0, imm=0) -> Expr:
+        if op == MUL:  # peephole: x * 1 (default filters) costs nothing
+            for x, y in ((a, b), (b, a)):
+                if self.ops[x][0] == CONST and self.ops[x][3] == 1:
+                    return Expr(self, y)
         key = (op, a, b, imm)
         if key in self._memo:
             return Expr(self, self._memo[key])
@@ -108,53 +221,107 @@ class ProgramBuilder:
     def last_row(self, e: Expr):
         self._emit(EMIT_LAST_ROW, e)
 
-    # ---- starky::lookup::eval_packed_lookups_generic (no filters) ------------------------------------------
-    def add_lookup(self, looking: Sequence[int], table_col: int, freq_col: int):
-        self.lookups.append((list(looking), table_col, freq_col))
+    # ---- starky::lookup::eval_packed_lookups_generic / eval_helper_columns --------------------------------------
+    def add_lookup(self, looking: Sequence, table_col, freq_col, filters: Sequence = None):
+        """Lookup { columns, table_column, frequencies_column, filter_columns }: columns / table / frequencies are
+        trace column indices or `Column`s, filters default to Filter::default() (the constant 1)."""
+        looking = list(looking)
+        if filters is None:
+            self.lookups.append((looking, table_col, freq_col))
+        else:
+            assert len(filters) == len(looking)
+            self.lookups.append((looking, table_col, freq_col, list(filters)))
+
+    def _helper_constraints(self, combos, filts, helpers):
+        """eval_helper_columns: chunks of (degree - 1) = 1 or 2 (combin, filter) pairs against one helper column each."""
+        chunk = max(1, self.degree - 1)
+        assert chunk <= 2, "eval_helper_columns: todo!(\"Allow other constraint degrees\") upstream"
+        for c, h in enumerate(helpers):
+            cs, fs = combos[c * chunk:(c + 1) * chunk], filts[c * chunk:(c + 1) * chunk]
+            if len(cs) == 2:
+                self.constraint(cs[1] * cs[0] * h - fs[0] * cs[1] - fs[1] * cs[0])
+            else:
+                self.constraint(cs[0] * h - fs[0])
 
     def emit_lookup_constraints(self):
         """Call once, after the table's own constraints.  Auxiliary columns: per lookup, per challenge: one helper
         column per chunk of (degree - 1) looking columns, then Z."""
         chunk = max(1, self.degree - 1)
         start = 0
-        for looking, table_col, freq_col in self.lookups:
+        for lk in self.lookups:
+            looking, table_col, freq_col = lk[0], lk[1], lk[2]
+            filters = lk[3] if len(lk) > 3 else [Filter()] * len(looking)
             n_help = -(-len(looking) // chunk)
             for k in range(NUM_CHALLENGES):
                 ch = self.challenge(k)
-                helpers = []
-                for c in range(n_help):
-                    cols = [self.lv(j) + ch for j in looking[c * chunk:(c + 1) * chunk]]
-                    h = self.la(start + c)
-                    helpers.append(h)
-                    # eval_helper_columns: h * prod(col_j + ch) - sum_j prod_{i != j}(col_i + ch)
-                    prod = cols[0]
-                    for x in cols[1:]:
-                        prod = prod * x
-                    if len(cols) == 1:
-                        rhs = self.const(1)
-                    else:
-                        rhs = None
-                        for j in range(len(cols)):
-                            t = None
-                            for i, x in enumerate(cols):
-                                if i != j:
-                                    t = x if t is None else t * x
-                            rhs = t if rhs is None else rhs + t
-                    self.constraint(h * prod - rhs)
+                combos = [Column.lift(j).expr(self) + ch for j in looking]
+                filts = [f.expr(self) for f in filters]
+                helpers = [self.la(start + c) for c in range(n_help)]
+                self._helper_constraints(combos, filts, helpers)
                 z, next_z = self.la(start + n_help), self.na(start + n_help)
-                twc = self.lv(table_col) + ch
+                twc = Column.lift(table_col).expr(self) + ch
                 hs = helpers[0]
                 for h in helpers[1:]:
                     hs = hs + h
-                y = hs * twc - self.lv(freq_col)
+                y = hs * twc - Column.lift(freq_col).expr(self)
                 self.first_row(z)
                 self.constraint((next_z - z) * twc - y)
                 start += n_help + 1
         self.n_aux = max(self.n_aux, start)
+        self._n_lookup_cols = start
 
-    def num_aux_columns(self) -> int:
+    # ---- starky::cross_table_lookup: CtlZData of this table + eval_cross_table_lookup_checks ---------------------
+    def add_ctl_z(self, challenge: int, colsets: Sequence):
+        """One CtlZData of this table, in the order cross_table_lookup_data pushes them: `challenge` = index of the
+        (beta, gamma) pair, `colsets` = [(columns, filter)] — one pair when the table appears once in the CTL (looked
+        table, or a single looking entry), several when it is looking more than once."""
+        assert 0 <= challenge < NUM_CHALLENGES
+        self.ctl_zs.append((challenge, [([Column.lift(c) for c in cols], f if f is not None else Filter()) for cols, f in colsets]))
+
+    def num_ctl_helper_columns(self) -> int:
+        chunk = max(1, self.degree - 1)
+        return sum(-(-len(sets) // chunk) if len(sets) > 1 else 0 for _, sets in self.ctl_zs)
+
+    def emit_ctl_constraints(self):
+        """Call once, after emit_lookup_constraints.  Auxiliary columns after the lookup columns: all CTL helper columns
+        (Z by Z), then all CTL Z columns."""
+        n_lookup = self.num_lookup_columns()
+        n_helpers = self.num_ctl_helper_columns()
+        chunk = max(1, self.degree - 1)
+        h_start = n_lookup
+        for zi, (k, sets) in enumerate(self.ctl_zs):
+            beta, gamma = self.challenge(CH_CTL_BASE + 2 * k), self.challenge(CH_CTL_BASE + 2 * k + 1)
+            combos, filts = [], []
+            for cols, filt in sets:
+                acc = None  # challenges.combine = reduce_with_powers(evals, beta) + gamma
+                for c in reversed(cols):
+                    e = c.expr(self)
+                    acc = e if acc is None else acc * beta + e
+                combos.append(acc + gamma)
+                filts.append(filt.expr(self))
+            z_col = n_lookup + n_helpers + zi
+            local_z, next_z = self.la(z_col), self.na(z_col)
+            if len(sets) > 1:
+                n_h = -(-len(sets) // chunk)
+                helpers = [self.la(h_start + c) for c in range(n_h)]
+                h_start += n_h
+                self._helper_constraints(combos, filts, helpers)
+                h_sum = helpers[0]
+                for h in helpers[1:]:
+                    h_sum = h_sum + h
+                self.last_row(local_z - h_sum)
+                self.transition(local_z - next_z - h_sum)
+            else:
+                self.last_row(combos[0] * local_z - filts[0])
+                self.transition(combos[0] * (local_z - next_z) - filts[0])
+        self.n_aux = max(self.n_aux, n_lookup + n_helpers + len(self.ctl_zs))
+
+    def num_lookup_columns(self) -> int:
         chunk = max(1, self.degree - 1)
         return sum(-(-len(l[0]) // chunk) + 1 for l in self.lookups) * NUM_CHALLENGES
+
+    def num_aux_columns(self) -> int:
+        return self.num_lookup_columns() + self.num_ctl_helper_columns() + len(self.ctl_zs)
 
     def build(self) -> "Program":
         return Program(self)
@@ -164,7 +331,10 @@ class Program:
     def __init__(self, b: ProgramBuilder):
         self.n_trace, self.n_aux, self.n_pi, self.n_ch = b.n_trace, b.n_aux, b.n_pi, b.n_ch
         self.degree, self.n_constraints = b.degree, b.n_constraints
-        self.lookups = [(list(l), t, f) for l, t, f in b.lookups]
+        self.lookups = [tuple(l) for l in b.lookups]
+        self.ctl_zs = list(b.ctl_zs)
+        self.n_lookup_cols = b.num_lookup_columns()
+        self.n_ctl_helper_cols = b.num_ctl_helper_columns()
         self.ops = list(b.ops)
         w = np.zeros(8 + 2 * len(self.ops), dtype=np.uint64)
         w[:8] = [MAGIC, len(self.ops), self.n_trace, self.n_aux, self.n_pi, self.n_ch, self.degree, self.n_constraints]
@@ -172,6 +342,46 @@ class Program:
             w[8 + 2 * k] = op | (a << 8) | (bb << 36)
             w[9 + 2 * k] = imm
         self.words = w
+
+    def simple_lookups(self) -> bool:
+        """True when every lookup uses plain columns and default filters and there is no CTL: the round-1 flat i32 lookup
+        description of etp_table_register is enough."""
+        if self.ctl_zs:
+            return False
+        for lk in self.lookups:
+            if len(lk) > 3 and not all(f.is_default() for f in lk[3]):
+                return False
+            if not all(isinstance(c, int) or c.is_single() for c in list(lk[0]) + [lk[1], lk[2]]):
+                return False
+        return True
+
+    def flat_lookups(self):
+        """[(looking columns, table column, frequencies column)] with plain column indices (simple_lookups() only)."""
+        ix = lambda c: c if isinstance(c, int) else c.local[0][0]
+        return [([ix(c) for c in lk[0]], ix(lk[1]), ix(lk[2])) for lk in self.lookups]
+
+    @property
+    def aux_spec(self) -> np.ndarray:
+        """Auxiliary-column description for etp_table_register_ex (u64 words): every Lookup with its Columns and Filters,
+        then the table's CtlZData descriptors (include/etp_b200.h)."""
+        w = [AUXSPEC_MAGIC, len(self.lookups), len(self.ctl_zs)]
+        for lk in self.lookups:
+            looking = [Column.lift(c) for c in lk[0]]
+            filters = lk[3] if len(lk) > 3 else [Filter()] * len(looking)
+            w.append(len(looking))
+            for c in looking:
+                w += c.words()
+            for f in filters:
+                w += f.words()
+            w += Column.lift(lk[1]).words() + Column.lift(lk[2]).words()
+        for k, sets in self.ctl_zs:
+            w += [k, len(sets)]
+            for cols, filt in sets:
+                w.append(len(cols))
+                for c in cols:
+                    w += c.words()
+                w += filt.words()
+        return np.array(w, dtype=np.uint64)
 
     def evaluate(self, lv, nv, la=(), na=(), pi=(), ch=(), add=None, sub=None, mul=None, lift=None):
         """Interprets the program over any ring (default: Python ints mod p).  Returns [(kind, value)] in emission
@@ -448,3 +658,85 @@ def shape_trace(log_n: int, n_cols: int, n_lookup: int = 0, seed: int = 23) -> n
 # (/root/reference/README.md:53-59: arithmetic 15.., byte packing 9.., cpu 12.., keccak 14.., keccak sponge 9..,
 # logic 12.., memory 17..), one notch up for the tables an ETH transfer actually exercises
 TX_TABLE_DEGREE_BITS = {"arithmetic": 16, "byte_packing": 10, "cpu": 14, "keccak": 14, "keccak_sponge": 10, "logic": 12, "memory": 18}
+
+
+# ---- a small multi-table system linked by a cross-table lookup --------------------------------------------------------
+# The CTL mechanism of starky 0.4.0 / evm_arithmetization (cross_table_lookup.rs: CtlData, partial_sums,
+# eval_cross_table_lookup_checks, verify_cross_table_lookups; reached from /root/reference/ops/src/lib.rs:52 through
+# prove_with_traces) on synthetic tables — the seven EVM tables themselves are not available offline:
+#   table 0 "ops"   looks (key, value) tuples up TWICE per row (two filtered looking entries of the same table -> one CTL
+#                   helper column + Z) and range-checks its keys against its own counter with a filtered logUp Lookup whose
+#                   looked column is a linear combination;
+#   table 1 "rom"   is the looked table: distinct (key, value) rows, filter = multiplicity column;
+#   table 2 "extra" looks up once per row, through linear-combination Columns that also read the NEXT row (Z only).
+def ctl_demo_tables(log_ops: int = 6, log_rom: int = 5, log_extra: int = 5, seed: int = 3):
+    """-> (tables, ctls): tables = [(name, Program, trace)], ctls = [(looking table indices, looked table index)]."""
+    from .synthetic import _rand
+
+    n_ops, n_rom, n_ext = 1 << log_ops, 1 << log_rom, 1 << log_extra
+    value = lambda k: (k.astype(object) * 1000003 + 17) % P  # the ROM contents
+    mult = np.zeros(n_rom, dtype=np.int64)
+
+    # ---- table 0 "ops": columns F1 K1 V1 F2 K2 V2 COUNTER FREQ HALF
+    F1, K1, V1, F2, K2, V2, CNT, FREQ, HALF = range(9)
+    t0 = np.zeros((9, n_ops), dtype=np.uint64)
+    f1 = (_rand(seed, 1, n_ops) % np.uint64(4) != 0).astype(np.int64)
+    f2 = (_rand(seed, 2, n_ops) % np.uint64(3) == 0).astype(np.int64)
+    k1 = (_rand(seed, 3, n_ops) % np.uint64(n_rom)).astype(np.int64)
+    k2 = (_rand(seed, 4, n_ops) % np.uint64(n_rom)).astype(np.int64)
+    t0[F1], t0[K1], t0[F2], t0[K2] = f1, k1, f2, k2
+    t0[V1] = np.array(value(k1), dtype=np.uint64)
+    t0[V2] = np.array(value(k2), dtype=np.uint64)
+    t0[CNT] = np.arange(n_ops, dtype=np.uint64)
+    t0[HALF] = t0[K1] // np.uint64(2)  # K1 = 2*HALF + (K1 & 1): the lookup below range-checks 2*HALF (a linear combination)
+    # filtered logUp: rows with F1 = 1 look 2*HALF up in COUNTER; K2 is looked up on every row
+    freq = np.bincount((2 * (k1 // 2))[f1 == 1], minlength=n_ops) + np.bincount(k2, minlength=n_ops)
+    t0[FREQ] = freq.astype(np.uint64)
+    np.add.at(mult, k1[f1 == 1], 1)
+    np.add.at(mult, k2[f2 == 1], 1)
+    b0 = ProgramBuilder(9, 0, 3)
+    for f in (F1, F2):
+        b0.constraint(b0.lv(f) * (b0.lv(f) - 1))
+    b0.first_row(b0.lv(CNT))
+    b0.transition(b0.nv(CNT) - b0.lv(CNT) - 1)
+    b0.add_lookup([Column([(HALF, 2)]), K2], CNT, FREQ, [Filter(constants=[Column.single(F1)]), Filter()])
+    for k in range(NUM_CHALLENGES):
+        b0.add_ctl_z(k, [([K1, V1], Filter(constants=[Column.single(F1)])), ([K2, V2], Filter(products=[(F2, F2)], constants=[]))])
+    b0.emit_lookup_constraints()
+    b0.emit_ctl_constraints()
+
+    # ---- table 2 "extra": columns A B S with key = A + B (mod n_rom handled by construction), value column = V; the looked
+    # tuple is (A + B, V) and the filter reads the NEXT row: active iff next row's S is 1
+    A, B, V, S = range(4)
+    t2 = np.zeros((4, n_ext), dtype=np.uint64)
+    a = (_rand(seed, 5, n_ext) % np.uint64(n_rom // 2)).astype(np.int64)
+    bb = (_rand(seed, 6, n_ext) % np.uint64(n_rom // 2)).astype(np.int64)
+    s = (_rand(seed, 7, n_ext) % np.uint64(2)).astype(np.int64)
+    t2[A], t2[B], t2[S] = a, bb, s
+    t2[V] = np.array(value(a + bb), dtype=np.uint64)
+    active = np.roll(s, -1)  # row i is active iff S[i + 1] = 1 (cyclic, as Column::eval_table does)
+    np.add.at(mult, (a + bb)[active == 1], 1)
+    b2 = ProgramBuilder(4, 0, 3)
+    b2.constraint(b2.lv(S) * (b2.lv(S) - 1))
+    for k in range(NUM_CHALLENGES):
+        b2.add_ctl_z(k, [([Column([(A, 1), (B, 1)]), V], Filter(constants=[Column.single_next_row(S)]))])
+    b2.emit_lookup_constraints()
+    b2.emit_ctl_constraints()
+
+    # ---- table 1 "rom": columns KEY VAL MULT
+    KEY, VAL, MULT = range(3)
+    t1 = np.zeros((3, n_rom), dtype=np.uint64)
+    keys = np.arange(n_rom, dtype=np.int64)
+    t1[KEY] = keys
+    t1[VAL] = np.array(value(keys), dtype=np.uint64)
+    t1[MULT] = mult.astype(np.uint64)
+    b1 = ProgramBuilder(3, 0, 3)
+    b1.first_row(b1.lv(KEY))
+    b1.transition(b1.nv(KEY) - b1.lv(KEY) - 1)
+    for k in range(NUM_CHALLENGES):
+        b1.add_ctl_z(k, [([KEY, VAL], Filter(constants=[Column.single(MULT)]))])
+    b1.emit_lookup_constraints()
+    b1.emit_ctl_constraints()
+    tables = [("ops", b0.build(), t0), ("rom", b1.build(), t1), ("extra", b2.build(), t2)]
+    ctls = [([0, 0, 2], 1)]
+    return tables, ctls

@@ -54,6 +54,19 @@ class Challenger(C.Structure):
                 ("out", C.c_uint64 * 8), ("n_out", C.c_int)]
 
 
+class FriParams(C.Structure):
+    _fields_ = [("rate_bits", C.c_int), ("cap_height", C.c_int), ("proof_of_work_bits", C.c_int), ("num_query_rounds", C.c_int),
+                ("degree_bits", C.c_int), ("n_reductions", C.c_int), ("reduction_arity_bits", C.c_int * 16)]
+
+
+class FriPoly(C.Structure):
+    _fields_ = [("oracle_index", C.c_uint32), ("polynomial_index", C.c_uint32)]
+
+
+class FriBatch(C.Structure):
+    _fields_ = [("point", C.c_uint64 * 2), ("polynomials", C.POINTER(FriPoly)), ("n_polynomials", C.c_size_t)]
+
+
 class _Batch(C.Structure):
     _fields_ = [("n_cols", C.c_size_t), ("log_n", C.c_int), ("rate_bits", C.c_int), ("cap_height", C.c_int),
                 ("coeffs", _u64p), ("leaves", _u64p), ("digests", _u64p), ("cap", _u64p)]
@@ -101,6 +114,27 @@ def lib():
         f.restype = C.c_int
     L.orc_table_register.argtypes = [_u64p, sz, C.POINTER(C.c_int32), sz]
     L.orc_table_register.restype = C.c_int
+    L.orc_table_register_ex.argtypes = [_u64p, sz, _u64p, sz]
+    L.orc_table_register_ex.restype = C.c_int
+    for f in (L.orc_table_requires_ctls, L.orc_table_num_ctl_helper_columns, L.orc_table_num_ctl_zs):
+        f.argtypes = [C.c_int]
+        f.restype = C.c_int
+    L.orc_table_num_lookup_columns.argtypes = [C.c_int, C.c_int]
+    L.orc_table_num_lookup_columns.restype = C.c_int
+    L.orc_fri_params_make.argtypes = [C.c_int] * 5 + [C.POINTER(FriParams)]
+    L.orc_fri_params_standard_fast.argtypes = [C.c_int, C.POINTER(FriParams)]
+    L.orc_prove_with_commitment.argtypes = [C.c_int, C.c_int, _u64p, C.POINTER(_Batch), _u64p, C.POINTER(Challenger), _u64p, _u64p]
+    L.orc_prove_with_commitment.restype = C.c_int
+    L.orc_challenger_compact.argtypes = [C.POINTER(Challenger), _u64p]
+    L.orc_aux_columns.argtypes = [C.c_int, C.c_int, _u64p, _u64p, C.c_int, _u64p, _u64p]
+    L.orc_aux_columns.restype = C.c_int
+    L.orc_batch_eval_at_ext_point.argtypes = [C.POINTER(_Batch), _u64p, _u64p]
+    L.orc_fri_proof_words.argtypes = [C.POINTER(sz), sz, C.POINTER(FriParams)]
+    L.orc_fri_proof_words.restype = sz
+    L.orc_prove_openings.argtypes = [C.POINTER(FriBatch), sz, C.POINTER(C.POINTER(_Batch)), sz, C.POINTER(Challenger),
+                                     C.POINTER(FriParams), _u64p]
+    L.orc_prove_openings.restype = C.c_int
+    L.orc_challenger_get_n.argtypes = [C.POINTER(Challenger), sz, _u64p]
     L.orc_table_num_aux_columns.argtypes = [C.c_int, C.c_int]
     L.orc_table_num_aux_columns.restype = C.c_int
     L.orc_table_check_constraints.argtypes = [C.c_int, C.c_int, _u64p, _u64p]
@@ -287,6 +321,104 @@ def register_table(program, lookups=()) -> int:
     return tid
 
 
+def register_table_ex(program, aux_spec) -> int:
+    """General registration: `aux_spec` = the u64 words of eth_tx_proof_b200.cprog.AuxSpec (lookups with linear-combination
+    Columns and Filters + the table's CTL Z descriptors)."""
+    words = _u64(getattr(program, "words", program))
+    spec = _u64(getattr(aux_spec, "words", aux_spec))
+    tid = lib().orc_table_register_ex(_ptr(words), words.size, _ptr(spec), spec.size)
+    if tid < 0:
+        raise RuntimeError("oracle: table registration failed")
+    return tid
+
+
+class HostChallenger:
+    """plonky2::iop::challenger::Challenger<GoldilocksField, PoseidonHash> (the oracle's restatement)."""
+
+    def __init__(self):
+        self.c = Challenger()
+        lib().orc_challenger_init(C.byref(self.c))
+
+    def observe(self, elems):
+        e = _u64(elems).ravel()
+        if e.size:
+            lib().orc_challenger_observe(C.byref(self.c), _ptr(e), e.size)
+
+    def get_n(self, n) -> np.ndarray:
+        out = np.zeros(n, dtype=np.uint64)
+        lib().orc_challenger_get_n(C.byref(self.c), n, _ptr(out))
+        return out
+
+    def compact(self) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        lib().orc_challenger_compact(C.byref(self.c), _ptr(out))
+        return out
+
+    def words(self) -> np.ndarray:
+        """[sponge_state 12 | input_buffer 8 | input_len | output_buffer 8 | output_len] — the product's etp_challenger layout."""
+        return np.array(list(self.c.state) + list(self.c.inb) + [self.c.n_in] + list(self.c.out) + [self.c.n_out], dtype=np.uint64)
+
+
+def aux_columns(table, trace, lookup_challenges, ctl_challenges=None) -> np.ndarray:
+    """All auxiliary polynomials of a table (lookup columns ++ CTL helper columns ++ CTL Zs), values on the trace domain."""
+    t = _u64(trace)
+    lc = _u64(lookup_challenges)
+    cc = _u64(list(ctl_challenges if ctl_challenges is not None else []) + [0, 0, 0, 0])
+    na = lib().orc_table_num_aux_columns(table, lc.size)
+    aux = np.zeros((max(na, 1), t.shape[1]), dtype=np.uint64)
+    rc = lib().orc_aux_columns(table, int(t.shape[1]).bit_length() - 1, _ptr(t), _ptr(lc), lc.size, _ptr(cc), _ptr(aux))
+    if rc != 0:
+        raise RuntimeError("oracle: zero denominator in an auxiliary column")
+    return aux[:na]
+
+
+def prove_with_commitment(table, trace, trace_batch: "Batch", challenger: HostChallenger, ctl_challenges=None, public_inputs=()):
+    """starky::prover::prove_with_commitment; the challenger is updated in place."""
+    t = _u64(trace)
+    log_n = int(t.shape[1]).bit_length() - 1
+    pi = _u64(list(public_inputs) + [0])
+    out = np.zeros(lib().orc_stark_proof_words(table, log_n), dtype=np.uint64)
+    cc = _u64(ctl_challenges) if ctl_challenges is not None else None
+    rc = lib().orc_prove_with_commitment(table, log_n, _ptr(t), trace_batch._h, _ptr(cc) if cc is not None else None,
+                                         C.byref(challenger.c), _ptr(pi), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle prove_with_commitment failed rc={rc}")
+    return out
+
+
+def fri_params(degree_bits, rate_bits=1, cap_height=4, pow_bits=16, num_queries=84) -> FriParams:
+    p = FriParams()
+    lib().orc_fri_params_make(degree_bits, rate_bits, cap_height, pow_bits, num_queries, C.byref(p))
+    return p
+
+
+def batch_eval_at_ext_point(batch: "Batch", z) -> np.ndarray:
+    out = np.zeros((max(batch.n_cols, 1), 2), dtype=np.uint64)
+    lib().orc_batch_eval_at_ext_point(batch._h, _ptr(_u64(z)), _ptr(out))
+    return out[:batch.n_cols]
+
+
+def prove_openings(batches, oracles, challenger: HostChallenger, params: FriParams) -> np.ndarray:
+    """PolynomialBatch::prove_openings for a general FriInstanceInfo.  batches: [(point (2,), [(oracle_index, poly_index)])]."""
+    keep = []
+    arr = (FriBatch * len(batches))()
+    for i, (point, polys) in enumerate(batches):
+        pa = (FriPoly * max(len(polys), 1))()
+        for k, (o, c) in enumerate(polys):
+            pa[k].oracle_index, pa[k].polynomial_index = o, c
+        keep.append(pa)
+        arr[i].point[0], arr[i].point[1] = int(point[0]), int(point[1])
+        arr[i].polynomials = C.cast(pa, C.POINTER(FriPoly))
+        arr[i].n_polynomials = len(polys)
+    oc = (C.c_size_t * len(oracles))(*[o.n_cols for o in oracles])
+    out = np.zeros(lib().orc_fri_proof_words(oc, len(oracles), C.byref(params)), dtype=np.uint64)
+    hs = (C.POINTER(_Batch) * len(oracles))(*[o._h for o in oracles])
+    rc = lib().orc_prove_openings(arr, len(batches), hs, len(oracles), C.byref(challenger.c), C.byref(params), _ptr(out))
+    if rc != 0:
+        raise RuntimeError(f"oracle prove_openings failed rc={rc}")
+    return out
+
+
 def check_constraints(table, trace, public_inputs=()) -> int:
     t = _u64(trace)
     pi = _u64(list(public_inputs) + [0])
@@ -319,7 +451,7 @@ def compute_quotient_polys(table, trace_batch: Batch, aux_batch, lookup_challeng
     factor = max(1, deg - 1)
     al = _u64(alphas)
     out = np.zeros((factor * al.size, 1 << trace_batch.log_n), dtype=np.uint64)
-    lc = _u64(list(lookup_challenges) + [0, 0])
+    lc = _u64(list(lookup_challenges) + [0] * 8)
     pi = _u64(list(public_inputs) + [0])
     L.orc_compute_quotient_polys(table, trace_batch.log_n, trace_batch._h, aux_batch._h if aux_batch else None,
                                  _ptr(lc), _ptr(pi), _ptr(al), al.size, _ptr(out))

@@ -83,34 +83,60 @@ const uint64_t *orc_batch_leaves(const orc_batch *b);
 const uint64_t *orc_batch_digests(const orc_batch *b);
 const uint64_t *orc_batch_cap(const orc_batch *b);
 
-/* ---- stark.c : tables, quotient, FRI, full single-table proof ---- */
+/* ---- stark.c : tables, auxiliary columns, quotient, FRI, prove_with_commitment ---- */
 #define ORC_TABLE_FIBONACCI 0
 #define ORC_TABLE_MEMORY 1
+/* FriConfig + FriParams (plonky2/src/fri/mod.rs) */
+typedef struct {
+  int rate_bits, cap_height, proof_of_work_bits, num_query_rounds, degree_bits, n_reductions;
+  int reduction_arity_bits[16];
+} orc_fri_params;
+void orc_fri_params_make(int degree_bits, int rate_bits, int cap_height, int pow_bits, int num_queries, orc_fri_params *p);
+void orc_fri_params_standard_fast(int degree_bits, orc_fri_params *p);
+/* FriPolynomialInfo / FriBatchInfo (plonky2/src/fri/structure.rs) */
+typedef struct { uint32_t oracle_index, polynomial_index; } orc_fri_poly;
+typedef struct { uint64_t point[2]; const orc_fri_poly *polynomials; size_t n_polynomials; } orc_fri_batch;
 /* program-defined table (constraint program + lookups, formats of the product's csrc/cprog.h / etp_table_register,
  * restated): interpreted op by op here.  Returns the table id (>= 16) or -1. */
 int orc_table_register(const uint64_t *program, size_t n_words, const int32_t *lookups, size_t n_lookup_words);
+/* general form (etp_table_register_ex): lookups with linear-combination Columns and Filters + the table's CTL Z descriptors */
+int orc_table_register_ex(const uint64_t *program, size_t n_words, const uint64_t *aux_spec, size_t n_spec_words);
 int orc_table_num_columns(int table);
 int orc_table_constraint_degree(int table);
 int orc_table_num_public_inputs(int table);
 int orc_table_uses_lookup(int table);
+int orc_table_requires_ctls(int table);
+int orc_table_num_lookup_columns(int table, int n_challenges);
+int orc_table_num_ctl_helper_columns(int table);
+int orc_table_num_ctl_zs(int table);
+int orc_table_num_aux_columns(int table, int n_challenges);
 /* check_constraints analogue: -1 if the trace (column-major n_cols x n) satisfies the table's own
  * constraints on every row, else row*1000 + index of the first failing constraint */
 long orc_table_check_constraints(int table, int log_n, const uint64_t *trace, const uint64_t *public_inputs);
 /* number of u64 words of the flat proof for this table / size under standard_fast_config */
 size_t orc_stark_proof_words(int table, int log_n);
-/* StarkConfig::standard_fast_config(); trace is column-major. Returns 0 on success. */
+/* starky::prover::prove, StarkConfig::standard_fast_config(); trace is column-major. Returns 0 on success. */
 int orc_stark_prove(int table, int log_n, const uint64_t *trace, const uint64_t *public_inputs,
                     uint64_t *proof_out);
+/* starky::prover::prove_with_commitment: pre-committed trace, optional CTL challenges, challenger state in/out */
+int orc_prove_with_commitment(int table, int log_n, const uint64_t *trace_vals, const orc_batch *trace, const uint64_t *ctl_challenges,
+                              orc_challenger *challenger, const uint64_t *public_inputs, uint64_t *proof_out);
+void orc_challenger_compact(orc_challenger *c, uint64_t state_out[12]);
 /* pieces exposed for piecewise parity tests */
 void orc_lookup_helper_columns(int table, int log_n, const uint64_t *trace, const uint64_t *challenges,
                                int n_challenges, uint64_t *aux /* col-major */);
-int orc_table_num_aux_columns(int table, int n_challenges);
+int orc_aux_columns(int table, int log_n, const uint64_t *trace, const uint64_t *lookup_challenges, int n_challenges,
+                    const uint64_t *ctl_challenges, uint64_t *aux /* col-major */);
 void orc_compute_quotient_polys(int table, int log_n, const orc_batch *trace, const orc_batch *aux,
-                                const uint64_t *lookup_challenges, const uint64_t *public_inputs,
+                                const uint64_t *challenge_scalars, const uint64_t *public_inputs,
                                 const uint64_t *alphas, int n_alphas, uint64_t *quotient_chunks);
 uint64_t orc_pow_grind(const uint64_t state[12], int pos, int bits);
 /* FRI commit phase on ext values (interleaved c0,c1; natural order) of size 2^log_size */
 void orc_fri_fold_coeffs(const uint64_t *coeffs, size_t n, int arity_bits, const uint64_t beta[2], uint64_t *out);
+void orc_batch_eval_at_ext_point(const orc_batch *b, const uint64_t z[2], uint64_t *out);
+size_t orc_fri_proof_words(const size_t *oracle_cols, size_t n_oracles, const orc_fri_params *p);
+int orc_prove_openings(const orc_fri_batch *batches, size_t n_batches, const orc_batch *const *oracles, size_t n_oracles,
+                       orc_challenger *challenger, const orc_fri_params *params, uint64_t *fri_proof_out);
 
 int orc_num_threads(void);
 #ifdef __cplusplus

@@ -253,6 +253,13 @@ class Challenger:
     def get_n(self, n):
         return [self.get() for _ in range(n)]
 
+    def compact(self):
+        """Challenger::compact: flush pending inputs, drop buffered outputs, return the sponge state."""
+        if self.inb:
+            self._duplex()
+        self.out = []
+        return list(self.state)
+
     def get_ext(self):
         a = self.get_n(2)
         return (a[0], a[1])

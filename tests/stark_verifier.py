@@ -25,7 +25,8 @@ import numpy as np
 from oracle import pyref as R
 
 P = R.P
-MAGIC = 0x4232303053544B31
+MAGIC = 0x4232303053544B32  # "B200STK2"
+HEADER_WORDS = 24
 TABLE_FIBONACCI, TABLE_MEMORY = 0, 1
 MEM_TRIE_DATA_SEGMENT = 13
 
@@ -63,10 +64,12 @@ def parse_proof(words):
         raise VerifyError("bad magic")
     h = dict(table=w[1], degree_bits=w[2], n_trace=w[3], n_aux=w[4], n_quot=w[5], cap_height=w[6], n_layers=w[7],
              arity_bits=w[8], final_len=w[9], num_queries=w[10], n_pi=w[11], rate_bits=w[12], pow_bits=w[13],
-             num_challenges=w[14], total=w[15])
+             num_challenges=w[14], total=w[15], n_ctl_zs=w[16], n_lookup_cols=w[17], n_ctl_helpers=w[18])
     if h["total"] != len(w):
         raise VerifyError("length mismatch")
-    pos = 16
+    if h["n_aux"] != h["n_lookup_cols"] + h["n_ctl_helpers"] + h["n_ctl_zs"]:
+        raise VerifyError("auxiliary column counts are inconsistent")
+    pos = HEADER_WORDS
     capw = 4 << h["cap_height"]
 
     def take(n):
@@ -93,6 +96,7 @@ def parse_proof(words):
     pr["next"] = take_ext(h["n_trace"])
     pr["aux"] = take_ext(h["n_aux"])
     pr["aux_next"] = take_ext(h["n_aux"])
+    pr["ctl_zs_first"] = take(h["n_ctl_zs"])
     pr["quot"] = take_ext(h["n_quot"])
     pr["fri_caps"] = [take_cap() for _ in range(h["n_layers"])]
     log_lde = h["degree_bits"] + h["rate_bits"]
@@ -232,9 +236,35 @@ def _eval_program(program, lv, nv, aux, aux_next, pi, challenges, c):
         (c.constraint, c.transition, c.first_row, c.last_row)[kind - 10](val)
 
 
-def verify(words, fast=True, max_queries=None, program=None):
+def new_challenger(fast=True):
+    return _Challenger(_hashers(fast)[2])
+
+
+def verify_cross_table_lookups(ctls, ctl_zs_first, num_challenges=2):
+    """starky::cross_table_lookup::verify_cross_table_lookups.  ctls: [(looking table indices (with repeats), looked table
+    index)]; ctl_zs_first: per table, the list of openings.  For every CTL and challenge the looking tables' Z(1) must sum
+    to the looked table's."""
+    its = [iter(v) for v in ctl_zs_first]
+    for index, (looking, looked) in enumerate(ctls):
+        uniq = []
+        for t in looking:
+            if t not in uniq:
+                uniq.append(t)
+        for _ in range(num_challenges):
+            total = sum(next(its[t]) for t in uniq) % P
+            if total != next(its[looked]):
+                raise VerifyError(f"Cross-table lookup {index} verification failed.")
+    for it in its:
+        if next(it, None) is not None:
+            raise VerifyError("unused ctl_zs_first openings")
+
+
+def verify(words, fast=True, max_queries=None, program=None, challenger=None, ctl_challenges=None):
     """Raises VerifyError unless the proof is valid. Returns the parsed proof.  `program`: the cprog.Program of a
-    registered table (table id >= 16 in the header); built-in tables are evaluated by the code above."""
+    registered table (table id >= 16 in the header); built-in tables are evaluated by the code above.
+    Multi-table mode (evm_arithmetization verify_proof -> verify_stark_proof_with_challenges): pass the shared
+    `challenger` (it has observed every trace cap and produced `ctl_challenges` = [(beta, gamma)] * num_challenges) —
+    the trace cap and public inputs are then NOT observed again and the lookup challenges are the CTL betas."""
     hash_or_noop, two_to_one, perm = _hashers(fast)
     pr = parse_proof(words)
     h = pr["h"]
@@ -246,30 +276,45 @@ def verify(words, fast=True, max_queries=None, program=None):
             raise VerifyError("registered table: pass its program")
         factor = max(1, program.degree - 1)
         chunk = max(1, program.degree - 1)
-        exp_cols = (program.n_trace, sum(-(-len(l[0]) // chunk) + 1 for l in program.lookups) * n_ch)
+        exp_cols = (program.n_trace, program.n_lookup_cols + program.n_ctl_helper_cols + len(program.ctl_zs))
+        if (h["n_lookup_cols"], h["n_ctl_helpers"], h["n_ctl_zs"]) != (program.n_lookup_cols, program.n_ctl_helper_cols, len(program.ctl_zs)):
+            raise VerifyError("shape (auxiliary columns)")
     else:
         factor = {TABLE_FIBONACCI: 1, TABLE_MEMORY: 2}[table]
         exp_cols = {TABLE_FIBONACCI: (2, 0), TABLE_MEMORY: (21, 2 * n_ch)}[table]
     if (h["n_trace"], h["n_aux"]) != exp_cols or h["n_quot"] != factor * n_ch:
         raise VerifyError("shape")
     # ---- transcript (get_challenges)
-    ch = _Challenger(perm)
-    ch.observe(pr["public_inputs"])
-    for d in pr["trace_cap"]:
-        ch.observe(d)
+    if challenger is None:
+        ch = _Challenger(perm)
+        ch.observe(pr["public_inputs"])
+        for d in pr["trace_cap"]:
+            ch.observe(d)
+    else:
+        ch = challenger
+    if h["n_ctl_zs"] and ctl_challenges is None:
+        raise VerifyError("the proof carries CTL openings but no CTL challenges were given")
     lookup_ch = None
     if pr["aux_cap"] is not None:
-        raw = ch.get_n(2 * n_ch)
-        lookup_ch = raw[0::2]
+        if ctl_challenges is not None:
+            lookup_ch = [int(b) for b, _ in ctl_challenges]
+        else:
+            raw = ch.get_n(2 * n_ch)
+            lookup_ch = raw[0::2]
         for d in pr["aux_cap"]:
             ch.observe(d)
+    scalars = list(lookup_ch or [0] * n_ch)
+    if ctl_challenges is not None:
+        for b, g_ in ctl_challenges:
+            scalars += [int(b), int(g_)]
     alphas = ch.get_n(n_ch)
     for d in pr["quot_cap"]:
         ch.observe(d)
     zeta = ch.get_ext()
     zeta_batch = pr["local"] + pr["aux"] + pr["quot"]
     next_batch = pr["next"] + pr["aux_next"]
-    for batch in (zeta_batch, next_batch):
+    ctl_batch = [(v, 0) for v in pr["ctl_zs_first"]]
+    for batch in (zeta_batch, next_batch, ctl_batch):
         for e in batch:
             ch.observe(e)
     fri_alpha = ch.get_ext()
@@ -295,7 +340,7 @@ def verify(words, fast=True, max_queries=None, program=None):
     z_last = R.e_sub(zeta, R.e_from(pow(g, P - 2, P)))
     cons = _Consumer(alphas, z_last, l_first, l_last)
     if table >= 16:
-        _eval_program(program, pr["local"], pr["next"], pr["aux"], pr["aux_next"], pr["public_inputs"], lookup_ch, cons)
+        _eval_program(program, pr["local"], pr["next"], pr["aux"], pr["aux_next"], pr["public_inputs"], scalars, cons)
     elif table == TABLE_FIBONACCI:
         _eval_fibonacci(pr["local"], pr["next"], pr["public_inputs"], cons)
     else:
@@ -310,7 +355,8 @@ def verify(words, fast=True, max_queries=None, program=None):
     if h["pow_bits"] and (pow_response >> (64 - h["pow_bits"])) != 0:
         raise VerifyError("Invalid proof of work witness")
     zeta_next = R.e_scalar(zeta, g)
-    reduced_openings = [_reduce(fri_alpha, zeta_batch), _reduce(fri_alpha, next_batch)]
+    reduced_openings = [_reduce(fri_alpha, zeta_batch), _reduce(fri_alpha, next_batch), _reduce(fri_alpha, ctl_batch)]
+    z_first_col = h["n_lookup_cols"] + h["n_ctl_helpers"]
     caps = [pr["trace_cap"]] + ([pr["aux_cap"]] if pr["aux_cap"] is not None else []) + [pr["quot_cap"]]
     n_trace, n_aux = h["n_trace"], h["n_aux"]
     w_lde = R.root_of_unity(lde_bits)
@@ -330,8 +376,10 @@ def verify(words, fast=True, max_queries=None, program=None):
         quot_ev = [R.e_from(v) for v in leaves[-1]]
         sx = R.e_from(subgroup_x)
         total = (0, 0)
-        for evals, point, red in ((trace_ev + aux_ev + quot_ev, zeta, reduced_openings[0]),
-                                  (trace_ev + aux_ev, zeta_next, reduced_openings[1])):
+        fri_batches = [(trace_ev + aux_ev + quot_ev, zeta, reduced_openings[0]), (trace_ev + aux_ev, zeta_next, reduced_openings[1])]
+        if h["n_ctl_zs"]:
+            fri_batches.append((aux_ev[z_first_col:], (1, 0), reduced_openings[2]))
+        for evals, point, red in fri_batches:
             numerator = R.e_sub(_reduce(fri_alpha, evals), red)
             denominator = R.e_sub(sx, point)
             total = R.e_mul(total, R.e_pow(fri_alpha, len(evals)))

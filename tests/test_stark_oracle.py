@@ -55,10 +55,10 @@ def test_tampered_proof_is_rejected(field):
     pr = V.parse_proof(proof)
     h = pr["h"]
     capw = 4 << h["cap_height"]
-    off_open = 16 + 3 * capw
+    off_open = V.HEADER_WORDS + 3 * capw
     n_open = 2 * (2 * h["n_trace"] + 2 * h["n_aux"] + h["n_quot"])
     off_fri = off_open + n_open
-    pos = {"trace_cap": 16 + 5, "opening": off_open + 7, "fri_cap": off_fri + 3,
+    pos = {"trace_cap": V.HEADER_WORDS + 5, "opening": off_open + 7, "fri_cap": off_fri + 3,
            "query_leaf": off_fri + capw * h["n_layers"] + 2, "final_poly": len(proof) - 2 - 2 * h["final_len"] + 1,
            "pow": len(proof) - 1}[field]
     bad = proof.copy()
