@@ -10,7 +10,10 @@ is present.  Nothing in this package imports ``oracle/``.
 """
 from .api import (  # noqa: F401
     BatchShard,
+    Challenger,
     Context,
+    FriParams,
+    FriState,
     EtpError,
     MerkleTree,
     PolynomialBatch,

@@ -32,6 +32,70 @@ class EtpError(RuntimeError):
         self.code = code
 
 
+class Challenger(C.Structure):
+    """etp_challenger: plonky2::iop::challenger::Challenger<GoldilocksField, PoseidonHash> as plain data — the transcript
+    state every proving entry point takes in and hands back."""
+    _fields_ = [("sponge_state", C.c_uint64 * 12), ("input_buffer", C.c_uint64 * 8), ("output_buffer", C.c_uint64 * 8),
+                ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
+
+    def observe(self, elements):
+        e = _u64(elements).ravel()
+        if e.size:
+            load_library().etp_challenger_observe(C.byref(self), _p(e), e.size)
+
+    def observe_cap(self, cap):
+        self.observe(cap)
+
+    def get_challenge(self) -> int:
+        return int(load_library().etp_challenger_get_challenge(C.byref(self)))
+
+    def get_n_challenges(self, n) -> np.ndarray:
+        out = np.zeros(n, dtype=np.uint64)
+        load_library().etp_challenger_get_n_challenges(C.byref(self), n, _p(out))
+        return out
+
+    def get_extension_challenge(self) -> np.ndarray:
+        return self.get_n_challenges(2)
+
+    def compact(self) -> np.ndarray:
+        load_library().etp_challenger_compact(C.byref(self))
+        return np.array(list(self.sponge_state), dtype=np.uint64)
+
+    def words(self) -> np.ndarray:
+        """[sponge_state 12 | input_buffer 8 | input_len | output_buffer 8 | output_len]"""
+        return np.array(list(self.sponge_state) + list(self.input_buffer) + [self.input_len] + list(self.output_buffer) + [self.output_len],
+                        dtype=np.uint64)
+
+    def clone(self) -> "Challenger":
+        c = Challenger()
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(Challenger))
+        return c
+
+
+class FriParams(C.Structure):
+    """etp_fri_params: plonky2::fri::FriParams (FriConfig + degree_bits + reduction_arity_bits)."""
+    _fields_ = [("rate_bits", C.c_int), ("cap_height", C.c_int), ("proof_of_work_bits", C.c_int), ("num_query_rounds", C.c_int),
+                ("degree_bits", C.c_int), ("n_reductions", C.c_int), ("reduction_arity_bits", C.c_int * 16)]
+
+    @classmethod
+    def make(cls, degree_bits, rate_bits=1, cap_height=4, proof_of_work_bits=16, num_query_rounds=84) -> "FriParams":
+        """FriConfig::fri_params with ConstantArityBits(4, 5); the defaults are StarkConfig::standard_fast_config(),
+        (3, 4, 16, 28) is CircuitConfig::standard_recursion_config()."""
+        p = cls()
+        rc = load_library().etp_fri_params_make(degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds, C.byref(p))
+        if rc != 0:
+            raise EtpError(rc, "bad FRI parameters")
+        return p
+
+
+class FriPoly(C.Structure):
+    _fields_ = [("oracle_index", C.c_uint32), ("polynomial_index", C.c_uint32)]
+
+
+class FriBatch(C.Structure):
+    _fields_ = [("point", C.c_uint64 * 2), ("polynomials", C.POINTER(FriPoly)), ("n_polynomials", C.c_size_t)]
+
+
 def lib_path() -> str:
     """In-tree library; ETP_B200_LIB selects another build of the same sources (kernel-variant A/B runs)."""
     return os.environ.get("ETP_B200_LIB") or os.path.join(_HERE, "libetp_b200.so")
@@ -130,6 +194,28 @@ def load_library():
         "etp_stark_prove_host": (i32, [vp, i32, i32, _u64p, _u64p, _u64p]),
         "etp_stark_prove_dev": (i32, [vp, i32, i32, vp, sz, _u64p, _u64p]),
         "etp_last_prove_timings": (i32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]),
+        "etp_challenger_init": (None, [C.POINTER(Challenger)]),
+        "etp_challenger_observe": (None, [C.POINTER(Challenger), _u64p, sz]),
+        "etp_challenger_get_challenge": (C.c_uint64, [C.POINTER(Challenger)]),
+        "etp_challenger_get_n_challenges": (None, [C.POINTER(Challenger), sz, _u64p]),
+        "etp_challenger_compact": (None, [C.POINTER(Challenger)]),
+        "etp_fri_params_make": (i32, [i32, i32, i32, i32, i32, C.POINTER(FriParams)]),
+        "etp_batch_eval_at_ext_point": (i32, [vp, _u64p, _u64p]),
+        "etp_table_register_ex": (i32, [vp, _u64p, sz, _u64p, sz, C.POINTER(i32)]),
+        "etp_table_num_lookup_columns": (i32, [vp, i32, i32]),
+        "etp_table_num_ctl_helper_columns": (i32, [vp, i32]),
+        "etp_table_num_ctl_zs": (i32, [vp, i32]),
+        "etp_aux_columns_dev": (i32, [vp, i32, i32, vp, sz, _u64p, i32, _u64p, vp]),
+        "etp_prove_with_commitment": (i32, [vp, i32, vp, vp, sz, _u64p, C.POINTER(Challenger), _u64p, _u64p]),
+        "etp_fri_proof_words": (sz, [C.POINTER(sz), sz, C.POINTER(FriParams)]),
+        "etp_prove_openings": (i32, [vp, C.POINTER(FriBatch), sz, C.POINTER(vp), sz, C.POINTER(Challenger), C.POINTER(FriParams), _u64p]),
+        "etp_fri_begin": (i32, [vp, vp, C.POINTER(FriParams), pp]),
+        "etp_fri_commit_layer": (i32, [vp, _u64p]),
+        "etp_fri_fold": (i32, [vp, _u64p]),
+        "etp_fri_final_poly": (i32, [vp, _u64p]),
+        "etp_fri_commit_phase": (i32, [vp, C.POINTER(Challenger), _u64p, _u64p]),
+        "etp_fri_query_rounds": (i32, [vp, C.POINTER(vp), sz, _u64p, sz, _u64p]),
+        "etp_fri_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
@@ -250,6 +336,8 @@ class Context:
         """Registers a table from its constraint program (``cprog.Program.words`` or a u64 array) and its lookups
         (``[(looking_columns, table_column, frequencies_column), ...]``): NVRTC-compiles the quotient kernel for
         sm_100a.  Returns the table id accepted by stark_prove / compute_quotient_polys / lookup_helper_columns."""
+        if hasattr(program, "simple_lookups") and not program.simple_lookups():
+            return self.register_table_ex(program, program.aux_spec)
         words = _u64(getattr(program, "words", program))
         flat = [len(lookups)]
         for looking, table_col, freq_col in lookups:
@@ -258,6 +346,56 @@ class Context:
         out = C.c_int(0)
         self.check(self.L.etp_table_register(self.h, _p(words), words.size, arr, len(flat) if lookups else 0, C.byref(out)))
         return int(out.value)
+
+    def register_table_ex(self, program, aux_spec) -> int:
+        """General registration (etp_table_register_ex): lookups with linear-combination Columns and Filters and the
+        table's CTL Z descriptors, as the u64 words of ``cprog.Program.aux_spec``."""
+        words = _u64(getattr(program, "words", program))
+        spec = _u64(aux_spec)
+        out = C.c_int(0)
+        self.check(self.L.etp_table_register_ex(self.h, _p(words), words.size, _p(spec) if spec.size else None, spec.size, C.byref(out)))
+        return int(out.value)
+
+    def aux_columns_dev(self, table, log_n, trace_ptr, col_stride, lookup_challenges, ctl_challenges, aux_ptr):
+        """All auxiliary polynomials of a table (lookup columns ++ CTL helper columns ++ CTL Zs) on the device."""
+        lc = _u64(list(lookup_challenges) + [0])
+        cc = _u64(ctl_challenges) if ctl_challenges is not None else None
+        self.check(self.L.etp_aux_columns_dev(self.h, table, log_n, C.c_void_p(trace_ptr), col_stride, _p(lc), len(lookup_challenges),
+                                              _p(cc) if cc is not None else None, C.c_void_p(aux_ptr)))
+
+    def prove_with_commitment(self, table, trace_batch, trace_ptr, col_stride, challenger: Challenger, ctl_challenges=None,
+                              public_inputs=()) -> np.ndarray:
+        """starky::prover::prove_with_commitment: pre-committed trace, CTL challenges (or None), challenger state in/out."""
+        n_pi = int(self.L.etp_table_num_public_inputs(self.h, table))
+        if n_pi < 0 or len(public_inputs) < n_pi:
+            raise EtpError(-1, "unknown table or too few public inputs")
+        pi = _u64(list(public_inputs) + [0])
+        cc = _u64(ctl_challenges) if ctl_challenges is not None else None
+        if cc is not None and cc.size != 4:
+            raise EtpError(-1, "ctl_challenges must be num_challenges (beta, gamma) pairs = 4 words")
+        out = np.zeros(self.stark_proof_words(table, trace_batch.degree_log), dtype=np.uint64)
+        self.check(self.L.etp_prove_with_commitment(self.h, table, trace_batch.h, C.c_void_p(trace_ptr), col_stride,
+                                                    _p(cc) if cc is not None else None, C.byref(challenger), _p(pi), _p(out)))
+        return out
+
+    def prove_openings(self, batches, oracles, challenger: Challenger, params: FriParams) -> np.ndarray:
+        """PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params) -> flat FriProof.
+        batches: [(point (2,), [(oracle_index, polynomial_index)])] — the FriInstanceInfo's FriBatchInfo list."""
+        keep = []
+        arr = (FriBatch * len(batches))()
+        for i, (point, polys) in enumerate(batches):
+            pa = (FriPoly * max(len(polys), 1))()
+            for k, (o, c) in enumerate(polys):
+                pa[k].oracle_index, pa[k].polynomial_index = o, c
+            keep.append(pa)
+            arr[i].point[0], arr[i].point[1] = int(point[0]), int(point[1])
+            arr[i].polynomials = C.cast(pa, C.POINTER(FriPoly))
+            arr[i].n_polynomials = len(polys)
+        oc = (C.c_size_t * len(oracles))(*[o.n_cols for o in oracles])
+        out = np.zeros(int(self.L.etp_fri_proof_words(oc, len(oracles), C.byref(params))), dtype=np.uint64)
+        hs = (C.c_void_p * len(oracles))(*[o.h for o in oracles])
+        self.check(self.L.etp_prove_openings(self.h, arr, len(batches), hs, len(oracles), C.byref(challenger), C.byref(params), _p(out)))
+        return out
 
     def table_num_aux_columns(self, table, num_challenges=2) -> int:
         return int(self.L.etp_table_num_aux_columns(self.h, table, num_challenges))
@@ -481,9 +619,70 @@ class PolynomialBatch:
         self.ctx.check(self.ctx.L.etp_batch_prove(self.h, leaf_index, _p(out)))
         return out[:ns]
 
+    def eval_at_ext_point(self, z) -> np.ndarray:
+        """polynomials[c].to_extension().eval(z) for every polynomial: (n_cols, 2)."""
+        out = np.zeros((max(self.n_cols, 1), 2), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_batch_eval_at_ext_point(self.h, _p(_u64(z)), _p(out)))
+        return out[:self.n_cols]
+
     def __del__(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.L.etp_batch_free(self.h)
+            self.h = None
+
+
+class FriState:
+    """The FRI prover step by step (plonky2::fri::prover::fri_committed_trees / fri_prover_query_rounds): commit a layer, get
+    its cap, fold with the beta the caller's challenger produced, ... — or the fused commit phase with the challenger."""
+
+    def __init__(self, ctx: Context, values_ptr: int, params: FriParams):
+        self.ctx, self.params = ctx, params
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_fri_begin(ctx.h, C.c_void_p(values_ptr), C.byref(params), C.byref(h)))
+        self.h = h
+
+    def commit_layer(self) -> np.ndarray:
+        cap = np.zeros((1 << self.params.cap_height, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_fri_commit_layer(self.h, _p(cap)))
+        return cap
+
+    def fold(self, beta):
+        self.ctx.check(self.ctx.L.etp_fri_fold(self.h, _p(_u64(beta))))
+
+    @property
+    def final_poly_len(self) -> int:
+        p = self.params
+        return 1 << (p.degree_bits - sum(p.reduction_arity_bits[i] for i in range(p.n_reductions)))
+
+    def final_poly(self) -> np.ndarray:
+        out = np.zeros((self.final_poly_len, 2), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_fri_final_poly(self.h, _p(out)))
+        return out
+
+    def commit_phase(self, challenger: Challenger):
+        """-> (caps (n_reductions, 2^cap, 4), final_poly (len, 2)); the challenger is advanced."""
+        caps = np.zeros((max(self.params.n_reductions, 1), 1 << self.params.cap_height, 4), dtype=np.uint64)
+        fin = np.zeros((self.final_poly_len, 2), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_fri_commit_phase(self.h, C.byref(challenger), _p(caps), _p(fin)))
+        return caps[:self.params.n_reductions], fin
+
+    def query_rounds(self, oracles, x_indices) -> np.ndarray:
+        p = self.params
+        log_lde = p.degree_bits + p.rate_bits
+        per = sum(o.n_cols + 4 * (log_lde - p.cap_height) for o in oracles)
+        bits = log_lde
+        for i in range(p.n_reductions):
+            bits -= p.reduction_arity_bits[i]
+            per += 2 * (1 << p.reduction_arity_bits[i]) + 4 * (bits - p.cap_height)
+        idx = _u64(x_indices).ravel()
+        out = np.zeros((max(idx.size, 1), per), dtype=np.uint64)
+        hs = (C.c_void_p * max(len(oracles), 1))(*[o.h for o in oracles])
+        self.ctx.check(self.ctx.L.etp_fri_query_rounds(self.h, hs, len(oracles), _p(idx), idx.size, _p(out)))
+        return out[:idx.size]
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.etp_fri_free(self.h)
             self.h = None
 
 

@@ -88,7 +88,7 @@ void jit_unload(JitKernel* k) {
 // compiled for sm_100a in this process.
 extern "C" int etp_cprog_compile_check(const uint64_t* program, size_t n_words, size_t* cubin_bytes_out, char* err, size_t err_len) {
   cprog::Program p;
-  const std::string why = cprog::parse(program, n_words, 16, 2, &p);
+  const std::string why = cprog::parse(program, n_words, 16, 8, &p);
   auto fail = [&](const std::string& m) { if (err && err_len) snprintf(err, err_len, "%s", m.c_str()); return ETP_ERR_INVALID; };
   if (!why.empty()) return fail(why);
   etp_ctx tmp;  // only its error string is used

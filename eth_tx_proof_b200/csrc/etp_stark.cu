@@ -1,13 +1,16 @@
-// libetp_b200: the starky / FRI half of the C ABI — lookup helper columns, compute_quotient_polys,
-// openings, FRI commit phase (evaluation-domain folding), proof of work, query rounds and the full
-// single-table `starky::prover::prove` under StarkConfig::standard_fast_config()
-// (/root/reference/common/src/prover_state/circuit.rs:204; reached from /root/reference/ops/src/lib.rs:52).
+// libetp_b200: the starky / FRI half of the C ABI — auxiliary columns (logUp helper columns, CTL running sums),
+// compute_quotient_polys, openings, PolynomialBatch::prove_openings for a general FRI instance, the FRI prover step by
+// step (commit phase with evaluation-domain folding, proof of work, query rounds), starky::prover::prove_with_commitment
+// with the challenger state passed in and out, and the stand-alone `starky::prover::prove`, all under
+// StarkConfig::standard_fast_config() (/root/reference/common/src/prover_state/circuit.rs:204; reached from
+// /root/reference/ops/src/lib.rs:52).
 // See include/etp_b200.h for the upstream item behind each entry point and DESIGN.md for the proof
 // wire format.  Product code: no oracle, no CPU fallback; the only host arithmetic is the transcript
 // (Challenger) and the <= 2^8-coefficient FRI final polynomial.
 #include <time.h>
 
 #include <cstdlib>
+#include <memory>
 
 #include "cprog.h"
 #include "ctx.cuh"
@@ -19,23 +22,154 @@ namespace {
 // StarkConfig::standard_fast_config()
 constexpr int NUM_CHALLENGES = 2, RATE_BITS = 1, CAP_HEIGHT = 4, POW_BITS = 16, ARITY_BITS = 4, FINAL_POLY_BITS = 5,
               NUM_QUERIES = 84;
-constexpr uint64_t PROOF_MAGIC = 0x4232303053544B31ULL;  // "B200STK1"
+constexpr uint64_t PROOF_MAGIC = 0x4232303053544B32ULL;  // "B200STK2"
+constexpr int HEADER_WORDS = 24;
+constexpr uint64_t AUXSPEC_MAGIC = 0x3153585541505445ULL;  // "ETPAUXS1"
 
-// starky::lookup::Lookup without filters: `looking` columns are looked up in `table_col` with multiplicities
-// `freq_col`.  Helper columns: one per chunk of (constraint_degree - 1) looking columns, then Z.
-struct LookupInfo {
-  std::vector<int> looking;
-  int table_col = 0, freq_col = 0;
+// ---- auxiliary-column descriptors (starky/src/lookup.rs Lookup / Column / Filter, cross_table_lookup.rs CtlZData) ----
+// The descriptors stay in their wire form (include/etp_b200.h, etp_table_register_ex); parsing validates them and records
+// where each Column / Filter starts, which is all the device kernels need.
+struct LookupE {
+  std::vector<size_t> col_off, filt_off;  // per looking column
+  size_t table_off = 0, freq_off = 0;
+  // every column a plain trace column with coefficient 1 and every filter the default: the dedicated fast kernels apply
+  bool simple = false;
+  std::vector<int> simple_cols;
+  int simple_table = 0, simple_freq = 0;
+  int n() const { return (int)col_off.size(); }
 };
+struct ColsetE {
+  size_t cols_off = 0, filt_off = 0;
+  int n_cols = 0;
+};
+struct CtlZE {
+  int challenge = 0;
+  std::vector<ColsetE> sets;
+};
+struct AuxSpec {
+  std::vector<uint64_t> words;
+  std::vector<LookupE> lookups;
+  std::vector<CtlZE> zs;
+};
+struct SpecReader {
+  const std::vector<uint64_t>& w;
+  size_t pos = 0;
+  int n_trace;
+  bool bad = false;
+  uint64_t rd() { if (pos >= w.size()) { bad = true; return 0; } return w[pos++]; }
+  // advances over one Column; *single = trace column index if it is Column::single(c), else -1
+  void column(int* single) {
+    const uint64_t nl = rd();
+    if (nl > 65536) { bad = true; return; }
+    int one_col = -1;
+    bool plain = nl == 1;
+    for (uint64_t i = 0; i < nl && !bad; i++) {
+      const uint64_t c = rd(), f = rd();
+      if (c >= (uint64_t)n_trace) bad = true;
+      if (gl::canon(f) != 1) plain = false;
+      one_col = (int)c;
+    }
+    const uint64_t nn = rd();
+    if (nn > 65536) { bad = true; return; }
+    for (uint64_t i = 0; i < nn && !bad; i++) { if (rd() >= (uint64_t)n_trace) bad = true; rd(); }
+    const uint64_t k = rd();
+    if (single) *single = (plain && nn == 0 && gl::canon(k) == 0) ? one_col : -1;
+  }
+  // advances over one Filter; *is_default = it is Filter::default() (the constant 1)
+  void filter(bool* is_default) {
+    const size_t start = pos;
+    const uint64_t np = rd();
+    if (np > 4096) { bad = true; return; }
+    for (uint64_t i = 0; i < np && !bad; i++) { column(nullptr); column(nullptr); }
+    const uint64_t nc = rd();
+    if (nc > 4096) { bad = true; return; }
+    for (uint64_t i = 0; i < nc && !bad; i++) column(nullptr);
+    // default filter words: 0 products, 1 constant: Column{0 local, 0 next, constant 1} = [0, 1, 0, 0, 1]
+    if (is_default) *is_default = !bad && pos - start == 5 && w[start] == 0 && w[start + 1] == 1 && w[start + 2] == 0 && w[start + 3] == 0 &&
+                                  gl::canon(w[start + 4]) == 1;
+  }
+};
+std::string parse_aux_spec(const uint64_t* words, size_t n, int n_trace, int num_challenges, AuxSpec* out) {
+  AuxSpec a;
+  a.words.assign(words, words + n);
+  SpecReader r{a.words, 0, n_trace};
+  if (r.rd() != AUXSPEC_MAGIC) return "auxiliary-column spec: bad magic";
+  const uint64_t nl = r.rd(), nz = r.rd();
+  if (r.bad || nl > 256 || nz > 256) return "auxiliary-column spec: bad lookup / CTL counts";
+  for (uint64_t i = 0; i < nl; i++) {
+    LookupE l;
+    const uint64_t m = r.rd();
+    if (r.bad || m < 1 || m > 65536) return "auxiliary-column spec: bad number of looking columns";
+    l.simple = true;
+    for (uint64_t j = 0; j < m; j++) {
+      int single = -1;
+      l.col_off.push_back(r.pos);
+      r.column(&single);
+      if (single < 0) l.simple = false;
+      l.simple_cols.push_back(single);
+    }
+    for (uint64_t j = 0; j < m; j++) {
+      bool def = false;
+      l.filt_off.push_back(r.pos);
+      r.filter(&def);
+      if (!def) l.simple = false;
+    }
+    l.table_off = r.pos; r.column(&l.simple_table);
+    l.freq_off = r.pos; r.column(&l.simple_freq);
+    if (l.simple_table < 0 || l.simple_freq < 0) l.simple = false;
+    if (r.bad) return "auxiliary-column spec: malformed lookup";
+    a.lookups.push_back(std::move(l));
+  }
+  for (uint64_t i = 0; i < nz; i++) {
+    CtlZE z;
+    z.challenge = (int)r.rd();
+    const uint64_t ns = r.rd();
+    if (r.bad || z.challenge < 0 || z.challenge >= num_challenges || ns < 1 || ns > 4096) return "auxiliary-column spec: bad CTL Z header";
+    for (uint64_t s = 0; s < ns; s++) {
+      ColsetE cs;
+      const uint64_t nc = r.rd();
+      if (r.bad || nc < 1 || nc > 65536) return "auxiliary-column spec: bad CTL column count";
+      cs.n_cols = (int)nc;
+      cs.cols_off = r.pos;
+      for (uint64_t j = 0; j < nc; j++) r.column(nullptr);
+      cs.filt_off = r.pos;
+      r.filter(nullptr);
+      z.sets.push_back(cs);
+    }
+    if (r.bad) return "auxiliary-column spec: malformed CTL Z";
+    a.zs.push_back(std::move(z));
+  }
+  if (r.bad || r.pos != n) return "auxiliary-column spec: trailing or missing words";
+  *out = std::move(a);
+  return "";
+}
+// spec words of plain lookups: [(looking columns, table column, frequencies column)], default filters
+void push_single(std::vector<uint64_t>& w, int c) { w.insert(w.end(), {1, (uint64_t)c, 1, 0, 0}); }
+std::vector<uint64_t> simple_spec_words(const std::vector<std::tuple<std::vector<int>, int, int>>& lookups) {
+  std::vector<uint64_t> w{AUXSPEC_MAGIC, lookups.size(), 0};
+  for (auto& l : lookups) {
+    w.push_back(std::get<0>(l).size());
+    for (int c : std::get<0>(l)) push_single(w, c);
+    for (size_t j = 0; j < std::get<0>(l).size(); j++) w.insert(w.end(), {0, 1, 0, 0, 1});
+    push_single(w, std::get<1>(l));
+    push_single(w, std::get<2>(l));
+  }
+  return w;
+}
+
 struct TableInfo {
   int cols = 0, degree = 0, n_pi = 0;
-  std::vector<LookupInfo> lookups;
+  std::shared_ptr<AuxSpec> aux;    // never null after table_info()
   RegisteredTable* reg = nullptr;  // program-defined table
   int chunk() const { return degree - 1 < 1 ? 1 : degree - 1; }
-  int helpers(const LookupInfo& l) const { return ((int)l.looking.size() + chunk() - 1) / chunk(); }
-  int aux_per_challenge() const { int a = 0; for (auto& l : lookups) a += helpers(l) + 1; return a; }
-  int n_aux(int n_ch) const { return aux_per_challenge() * n_ch; }
-  bool lookup() const { return !lookups.empty(); }
+  int helpers(const LookupE& l) const { return (l.n() + chunk() - 1) / chunk(); }
+  int ctl_helpers(const CtlZE& z) const { return z.sets.size() > 1 ? ((int)z.sets.size() + chunk() - 1) / chunk() : 0; }
+  int n_lookup_cols(int n_ch) const { int a = 0; for (auto& l : aux->lookups) a += helpers(l) + 1; return a * n_ch; }
+  int n_ctl_helpers() const { int a = 0; for (auto& z : aux->zs) a += ctl_helpers(z); return a; }
+  int n_ctl_zs() const { return (int)aux->zs.size(); }
+  int n_aux(int n_ch) const { return n_lookup_cols(n_ch) + n_ctl_helpers() + n_ctl_zs(); }
+  bool lookup() const { return !aux->lookups.empty(); }
+  bool ctl() const { return !aux->zs.empty(); }
 };
 }  // namespace
 
@@ -44,21 +178,27 @@ struct RegisteredTable {
   TableInfo info;
   cprog::Program prog;
   JitKernel kernel;
+  uint64_t* d_spec = nullptr;  // the aux spec words on the device (general lookups / CTL), uploaded on first use
 };
 void free_registered_tables(etp_ctx* ctx) {
-  for (auto* t : ctx->tables) { jit_unload(&t->kernel); delete t; }
+  for (auto* t : ctx->tables) { jit_unload(&t->kernel); cudaFree(t->d_spec); delete t; }
   ctx->tables.clear();
 }
 
 namespace {
+std::shared_ptr<AuxSpec> empty_spec() { static auto s = std::make_shared<AuxSpec>(); return s; }
+std::shared_ptr<AuxSpec> memory_spec() {
+  static std::shared_ptr<AuxSpec> s = [] {
+    auto a = std::make_shared<AuxSpec>();
+    const auto w = simple_spec_words({std::make_tuple(std::vector<int>{stark::M_RANGE_CHECK}, (int)stark::M_COUNTER, (int)stark::M_FREQ)});
+    parse_aux_spec(w.data(), w.size(), 21, NUM_CHALLENGES, a.get());
+    return a;
+  }();
+  return s;
+}
 bool table_info(const etp_ctx* ctx, int t, TableInfo* o) {
-  if (t == ETP_TABLE_FIBONACCI) { *o = TableInfo(); o->cols = 2; o->degree = 2; o->n_pi = 3; return true; }
-  if (t == ETP_TABLE_MEMORY) {
-    *o = TableInfo(); o->cols = 21; o->degree = 3; o->n_pi = 0;
-    LookupInfo l; l.looking = {stark::M_RANGE_CHECK}; l.table_col = stark::M_COUNTER; l.freq_col = stark::M_FREQ;
-    o->lookups.push_back(l);
-    return true;
-  }
+  if (t == ETP_TABLE_FIBONACCI) { *o = TableInfo(); o->cols = 2; o->degree = 2; o->n_pi = 3; o->aux = empty_spec(); return true; }
+  if (t == ETP_TABLE_MEMORY) { *o = TableInfo(); o->cols = 21; o->degree = 3; o->n_pi = 0; o->aux = memory_spec(); return true; }
   if (ctx && t >= ETP_TABLE_FIRST_REGISTERED && (size_t)(t - ETP_TABLE_FIRST_REGISTERED) < ctx->tables.size()) {
     *o = ctx->tables[t - ETP_TABLE_FIRST_REGISTERED]->info;
     return true;
@@ -67,10 +207,22 @@ bool table_info(const etp_ctx* ctx, int t, TableInfo* o) {
 }
 int quotient_factor(const TableInfo& ti) { return ti.degree - 1 < 1 ? 1 : ti.degree - 1; }
 int log2_ceil(int x) { int l = 0; while ((1 << l) < x) l++; return l; }
-int fri_num_layers(int degree_bits) {  // FriReductionStrategy::ConstantArityBits(4, 5)
-  int layers = 0;
-  while (degree_bits > FINAL_POLY_BITS && degree_bits + RATE_BITS - ARITY_BITS >= CAP_HEIGHT) { layers++; degree_bits -= ARITY_BITS; }
-  return layers;
+int fri_total_arities(const etp_fri_params& p) { int t = 0; for (int i = 0; i < p.n_reductions; i++) t += p.reduction_arity_bits[i]; return t; }
+// FriConfig::fri_params with FriReductionStrategy::ConstantArityBits(4, 5)
+void fri_params_make(int degree_bits, int rate_bits, int cap_height, int pow_bits, int num_queries, etp_fri_params* p) {
+  memset(p, 0, sizeof *p);
+  p->degree_bits = degree_bits; p->rate_bits = rate_bits; p->cap_height = cap_height; p->proof_of_work_bits = pow_bits;
+  p->num_query_rounds = num_queries;
+  int db = degree_bits;
+  while (db > FINAL_POLY_BITS && db + rate_bits - ARITY_BITS >= cap_height && p->n_reductions < 16) {
+    p->reduction_arity_bits[p->n_reductions++] = ARITY_BITS;
+    db -= ARITY_BITS;
+  }
+}
+etp_fri_params standard_fast_params(int degree_bits) {
+  etp_fri_params p;
+  fri_params_make(degree_bits, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES, &p);
+  return p;
 }
 
 struct PhaseTimer {
@@ -103,10 +255,24 @@ struct PhaseTimer {
 
 unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// ctx->d_pow_result[1] doubles as the "a batch inverse met a zero" flag of the call in flight
+unsigned long long* zero_flag(etp_ctx* ctx) { return (unsigned long long*)(ctx->d_pow_result + 1); }
+int reset_zero_flag(etp_ctx* ctx) {
+  ETP_CUDA(ctx, cudaMemsetAsync(zero_flag(ctx), 0, 8, ctx->stream));
+  return ETP_OK;
+}
+// call after a synchronisation point of the stream
+int check_zero_flag(etp_ctx* ctx, const char* what) {
+  unsigned long long f = 0;
+  ETP_CUDA(ctx, cudaMemcpyAsync(&f, zero_flag(ctx), 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (f) return etp_fail(ctx, ETP_ERR_PROOF, "Tried to invert zero (%s)", what);
+  return ETP_OK;
+}
 int batch_inverse_dev(etp_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n) {
   const int threads = 128;
   const size_t per_block = (size_t)threads * stark::INV_K;
-  stark::batch_inverse<<<blocks_for(n, (int)per_block), threads, 0, ctx->stream>>>(in, out, n);
+  stark::batch_inverse<<<blocks_for(n, (int)per_block), threads, 0, ctx->stream>>>(in, out, n, zero_flag(ctx));
   ETP_LAUNCH_CHECK(ctx);
   return ETP_OK;
 }
@@ -125,38 +291,101 @@ int exclusive_scan_dev(etp_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n
   return ETP_OK;
 }
 
-int lookup_helper_columns(etp_ctx* ctx, int table, int log_n, const uint64_t* trace, size_t stride, const uint64_t* ch, int n_ch,
-                          uint64_t* aux) {
-  TableInfo ti;
-  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
-  if (!ti.lookup()) return ETP_OK;
+int spec_on_device(etp_ctx* ctx, const TableInfo& ti, const uint64_t** out) {
+  if (!ti.reg) return etp_fail(ctx, ETP_ERR_STATE, "internal error: general auxiliary columns on a built-in table");
+  if (!ti.reg->d_spec) {
+    const auto& w = ti.aux->words;
+    ETP_CUDA(ctx, cudaMalloc((void**)&ti.reg->d_spec, w.size() * 8));
+    ETP_CUDA(ctx, cudaMemcpyAsync(ti.reg->d_spec, w.data(), w.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  *out = ti.reg->d_spec;
+  return ETP_OK;
+}
+
+// All auxiliary polynomials of a table (values on the trace domain): lookup_helper_columns for every lookup and challenge,
+// then the CTL helper columns, then the CTL Z columns (starky prover.rs: auxiliary_polys = lookup columns ++
+// get_ctl_auxiliary_polys(ctl_data); cross_table_lookup.rs: ctl_helper_polys() ++ ctl_z_polys()).
+int aux_columns(etp_ctx* ctx, const TableInfo& ti, int log_n, const uint64_t* trace, size_t stride, const uint64_t* lookup_ch, int n_ch,
+                const uint64_t* ctl_ch, uint64_t* aux) {
+  if (!ti.lookup() && !ti.ctl()) return ETP_OK;
   const size_t n = (size_t)1 << log_n;
-  size_t max_m = 0;
-  for (auto& l : ti.lookups) max_m = l.looking.size() > max_m ? l.looking.size() : max_m;
-  DevBuf<uint64_t> den(ctx), term(ctx);
+  size_t max_m = 1;
+  for (auto& l : ti.aux->lookups) max_m = (size_t)l.n() > max_m ? (size_t)l.n() : max_m;
+  for (auto& z : ti.aux->zs) max_m = z.sets.size() > max_m ? z.sets.size() : max_m;
+  DevBuf<uint64_t> den(ctx), filt(ctx), term(ctx), freq(ctx), prefix(ctx);
   DevBuf<int> d_cols(ctx);
   ETP_TRY(den.alloc((max_m + 1) * n));
   ETP_TRY(term.alloc(n));
   ETP_TRY(d_cols.alloc(max_m + 1));
+  bool general = ti.ctl();
+  for (auto& l : ti.aux->lookups) general = general || !l.simple;
+  const uint64_t* spec = nullptr;
+  if (general) {
+    ETP_TRY(spec_on_device(ctx, ti, &spec));
+    ETP_TRY(filt.alloc(max_m * n));
+    ETP_TRY(freq.alloc(n));
+    ETP_TRY(prefix.alloc(n));
+  }
+  const unsigned gb = blocks_for(n, 256);
   // auxiliary column order (starky prover.rs): for each lookup, for each challenge: helpers..., Z
   uint64_t* out = aux;
-  for (auto& l : ti.lookups) {
-    const int m = (int)l.looking.size(), nh = ti.helpers(l);
-    std::vector<int> cols(l.looking);
-    cols.push_back(l.table_col);
-    ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `cols` dies at the end of this iteration
+  for (auto& l : ti.aux->lookups) {
+    const int m = l.n(), nh = ti.helpers(l);
+    if (l.simple) {
+      std::vector<int> cols(l.simple_cols);
+      cols.push_back(l.simple_table);
+      ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `cols` dies at the end of this iteration
+    }
     for (int k = 0; k < n_ch; k++) {
-      stark::lookup_denominators<<<blocks_for((size_t)(m + 1) * n, 256), 256, 0, ctx->stream>>>(trace, stride, d_cols.p, m + 1,
-                                                                                                gl::canon(ch[k]), n, den.p);
-      ETP_LAUNCH_CHECK(ctx);
-      ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, (size_t)(m + 1) * n));
-      stark::lookup_terms<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(den.p, m, ti.chunk(), trace + (size_t)l.freq_col * stride, n, out,
-                                                                      term.p);
-      ETP_LAUNCH_CHECK(ctx);
+      const uint64_t ch = gl::canon(lookup_ch[k]);
+      if (l.simple) {
+        stark::lookup_denominators<<<blocks_for((size_t)(m + 1) * n, 256), 256, 0, ctx->stream>>>(trace, stride, d_cols.p, m + 1, ch, n, den.p);
+        ETP_LAUNCH_CHECK(ctx);
+        ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, (size_t)(m + 1) * n));
+        stark::lookup_terms<<<gb, 256, 0, ctx->stream>>>(den.p, m, ti.chunk(), trace + (size_t)l.simple_freq * stride, n, out, term.p);
+        ETP_LAUNCH_CHECK(ctx);
+      } else {
+        // GrandProductChallenge { beta: 1, gamma: challenge } on one-column sets, each with its filter
+        for (int j = 0; j < m; j++) {
+          stark::aux_colset_eval<<<gb, 256, 0, ctx->stream>>>(trace, stride, (uint32_t)n, spec + l.col_off[j], 1, spec + l.filt_off[j], 1, ch,
+                                                             den.p + (size_t)j * n, filt.p + (size_t)j * n);
+          ETP_LAUNCH_CHECK(ctx);
+        }
+        stark::aux_column_eval<<<gb, 256, 0, ctx->stream>>>(trace, stride, (uint32_t)n, spec + l.table_off, ch, den.p + (size_t)m * n);
+        ETP_LAUNCH_CHECK(ctx);
+        stark::aux_column_eval<<<gb, 256, 0, ctx->stream>>>(trace, stride, (uint32_t)n, spec + l.freq_off, 0, freq.p);
+        ETP_LAUNCH_CHECK(ctx);
+        ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, (size_t)(m + 1) * n));
+        stark::aux_helper_terms<<<gb, 256, 0, ctx->stream>>>(den.p, filt.p, m, ti.chunk(), n, freq.p, den.p + (size_t)m * n, out, term.p);
+        ETP_LAUNCH_CHECK(ctx);
+      }
       ETP_TRY(exclusive_scan_dev(ctx, term.p, out + (size_t)nh * n, n));
       out += (size_t)(nh + 1) * n;
     }
+  }
+  // CTL: helper columns of every CtlZData, then every Z
+  uint64_t* helpers = out;
+  uint64_t* zs = out + (size_t)ti.n_ctl_helpers() * n;
+  for (size_t zi = 0; zi < ti.aux->zs.size(); zi++) {
+    const CtlZE& z = ti.aux->zs[zi];
+    if (!ctl_ch) return etp_fail(ctx, ETP_ERR_INVALID, "the table requires CTLs but no CTL challenges were given");
+    const uint64_t beta = gl::canon(ctl_ch[2 * z.challenge]), gamma = gl::canon(ctl_ch[2 * z.challenge + 1]);
+    const int S = (int)z.sets.size(), nh = ti.ctl_helpers(z);
+    for (int s = 0; s < S; s++) {
+      stark::aux_colset_eval<<<gb, 256, 0, ctx->stream>>>(trace, stride, (uint32_t)n, spec + z.sets[s].cols_off, z.sets[s].n_cols,
+                                                         spec + z.sets[s].filt_off, beta, gamma, den.p + (size_t)s * n, filt.p + (size_t)s * n);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+    ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, (size_t)S * n));
+    stark::aux_helper_terms<<<gb, 256, 0, ctx->stream>>>(den.p, filt.p, S, ti.chunk(), n, nullptr, nullptr, nh ? helpers : nullptr, term.p);
+    ETP_LAUNCH_CHECK(ctx);
+    helpers += (size_t)nh * n;
+    // partial_sums: Z[i] = sum_{j >= i} term[j]
+    ETP_TRY(exclusive_scan_dev(ctx, term.p, prefix.p, n));
+    stark::suffix_from_prefix<<<gb, 256, 0, ctx->stream>>>(prefix.p, term.p, n, zs + zi * n);
+    ETP_LAUNCH_CHECK(ctx);
   }
   return ETP_OK;
 }
@@ -180,7 +409,7 @@ int ext_pow_table(etp_ctx* ctx, gl::Ext z, int bits, DevBuf<uint64_t>& lo, DevBu
 }
 
 // evaluate all polynomials of a batch at z0 and z1: out0/out1 get n_cols ext values
-int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, const stark::ExtPowTable& t1, gl::Ext z0, gl::Ext z1,
+int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, const stark::ExtPowTable& t1,
                std::vector<gl::Ext>& out0, std::vector<gl::Ext>& out1) {
   const uint32_t n = (uint32_t)b->n();
   const int np = (int)b->n_cols;
@@ -207,18 +436,21 @@ int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, c
   return ETP_OK;
 }
 
-int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* lookup_ch, int n_lookup_ch,
+// n_scalars challenge scalars: lookup challenges [0, NUM_CHALLENGES), then the CTL (beta, gamma) pairs
+int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* scalars, int n_scalars,
                      const uint64_t* pi, const uint64_t* alphas, int n_alphas, uint64_t* out_dev) {
   TableInfo ti;
   if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
   if (!trace || (int)trace->n_cols != ti.cols) return etp_fail(ctx, ETP_ERR_INVALID, "trace batch has the wrong number of columns");
   if (n_alphas < 1 || n_alphas > stark::MAX_CHALLENGES) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported number of challenges");
+  if (n_scalars < 0 || n_scalars > stark::MAX_CH_SCALARS) return etp_fail(ctx, ETP_ERR_INVALID, "too many challenge scalars");
+  const int n_lookup_ch = n_scalars < NUM_CHALLENGES ? n_scalars : NUM_CHALLENGES;
   const int n_aux = ti.n_aux(n_lookup_ch);
-  if (ti.lookup() && (!aux || (int)aux->n_cols != n_aux || n_lookup_ch > stark::MAX_CHALLENGES))
-    return etp_fail(ctx, ETP_ERR_INVALID, "auxiliary batch does not match the table's lookups");
-  if (ti.reg && ((int)ti.reg->prog.n_aux != n_aux || (int)ti.reg->prog.n_ch > n_lookup_ch))
-    return etp_fail(ctx, ETP_ERR_INVALID, "constraint program expects %u auxiliary columns / %u challenges, got %d / %d",
-                    ti.reg->prog.n_aux, ti.reg->prog.n_ch, n_aux, n_lookup_ch);
+  if ((ti.lookup() || ti.ctl()) && (!aux || (int)aux->n_cols != n_aux))
+    return etp_fail(ctx, ETP_ERR_INVALID, "auxiliary batch does not match the table's lookups / CTLs");
+  if (ti.reg && ((int)ti.reg->prog.n_aux != n_aux || (int)ti.reg->prog.n_ch > n_scalars))
+    return etp_fail(ctx, ETP_ERR_INVALID, "constraint program expects %u auxiliary columns / %u challenge scalars, got %d / %d",
+                    ti.reg->prog.n_aux, ti.reg->prog.n_ch, n_aux, n_scalars);
   const int log_n = trace->log_n, rate_bits = trace->rate_bits;
   const int factor = quotient_factor(ti), qbits = log2_ceil(factor);
   if (qbits > rate_bits)
@@ -247,7 +479,7 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
   q.last = gl::canon(gl::inv(g));
   for (int j = 0; j < n_alphas; j++) q.alphas[j] = gl::canon(alphas[j]);
   q.n_alphas = n_alphas;
-  for (int j = 0; j < n_lookup_ch; j++) q.lookup_ch[j] = gl::canon(lookup_ch[j]);
+  for (int j = 0; j < n_scalars; j++) q.lookup_ch[j] = gl::canon(scalars[j]);
   q.n_lookup_ch = n_lookup_ch;
   for (int j = 0; j < ti.n_pi && j < stark::MAX_PUBLIC_INPUTS; j++) q.pi[j] = gl::canon(pi[j]);
   // Lagrange selectors at every point of the quotient coset
@@ -326,20 +558,49 @@ int pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, int bits, uint64_
   }
 }
 
-size_t proof_words(const TableInfo& ti, int log_n) {
-  const int n_aux = ti.n_aux(NUM_CHALLENGES), n_quot = quotient_factor(ti) * NUM_CHALLENGES;
-  const int n_layers = fri_num_layers(log_n), log_lde = log_n + RATE_BITS;
-  const size_t cap = (size_t)4 << CAP_HEIGHT;
-  size_t w = 16 + cap * (2 + (n_aux ? 1 : 0)) + 2 * (size_t)(2 * ti.cols + 2 * n_aux + n_quot) + cap * n_layers;
-  const int init_path = log_lde - CAP_HEIGHT;
-  size_t per_query = ti.cols + 4 * init_path + (n_aux ? n_aux + 4 * init_path : 0) + n_quot + 4 * init_path;
+size_t fri_proof_words(const size_t* oracle_cols, size_t n_oracles, const etp_fri_params& p) {
+  const size_t cap = (size_t)4 << p.cap_height;
+  const int log_lde = p.degree_bits + p.rate_bits;
+  size_t per_query = 0;
+  for (size_t o = 0; o < n_oracles; o++) per_query += oracle_cols[o] + 4 * (size_t)(log_lde - p.cap_height);
   int bits = log_lde;
-  for (int l = 0; l < n_layers; l++) { bits -= ARITY_BITS; per_query += 2 * (1 << ARITY_BITS) + 4 * (bits - CAP_HEIGHT); }
-  w += NUM_QUERIES * per_query;
-  w += 2 * ((size_t)1 << (log_n - ARITY_BITS * n_layers)) + 1 + ti.n_pi;
-  return w;
+  for (int l = 0; l < p.n_reductions; l++) {
+    bits -= p.reduction_arity_bits[l];
+    per_query += 2 * ((size_t)1 << p.reduction_arity_bits[l]) + 4 * (size_t)(bits - p.cap_height);
+  }
+  const size_t final_len = (size_t)1 << (p.degree_bits - fri_total_arities(p));
+  return cap * p.n_reductions + (size_t)p.num_query_rounds * per_query + 2 * final_len + 1;
 }
 
+size_t proof_words(const TableInfo& ti, int log_n) {
+  const etp_fri_params fp = standard_fast_params(log_n);
+  const int n_aux = ti.n_aux(NUM_CHALLENGES), n_quot = quotient_factor(ti) * NUM_CHALLENGES;
+  const size_t cap = (size_t)4 << CAP_HEIGHT;
+  size_t w = HEADER_WORDS + cap * (2 + (n_aux ? 1 : 0)) + 2 * (size_t)(2 * ti.cols + 2 * n_aux + n_quot) + ti.n_ctl_zs();
+  size_t oc[3];
+  size_t no = 0;
+  oc[no++] = ti.cols;
+  if (n_aux) oc[no++] = n_aux;
+  oc[no++] = n_quot;
+  return w + fri_proof_words(oc, no, fp) + ti.n_pi;
+}
+
+int check_fri_params(etp_ctx* ctx, const etp_fri_params& p) {
+  if (p.degree_bits < 0 || p.rate_bits < 0 || p.degree_bits + p.rate_bits > 30 || p.cap_height < 0 || p.n_reductions < 0 || p.n_reductions > 16 ||
+      p.proof_of_work_bits < 0 || p.proof_of_work_bits > 40 || p.num_query_rounds < 0 || p.num_query_rounds > 4096)
+    return etp_fail(ctx, ETP_ERR_INVALID, "bad FRI parameters");
+  for (int i = 0; i < p.n_reductions; i++)
+    if (p.reduction_arity_bits[i] != ARITY_BITS) return etp_fail(ctx, ETP_ERR_INVALID, "only arity-16 FRI reductions are supported (ConstantArityBits(4, 5))");
+  if (fri_total_arities(p) > p.degree_bits + p.rate_bits - p.cap_height || p.degree_bits + p.rate_bits < p.cap_height)
+    return etp_fail(ctx, ETP_ERR_INVALID, "FRI total reduction arity is too large.");
+  if (fri_total_arities(p) > p.degree_bits) return etp_fail(ctx, ETP_ERR_INVALID, "FRI reductions exceed the degree");
+  return ETP_OK;
+}
+}  // namespace
+
+// =================================================================================================
+// the FRI prover, step by step (plonky2/src/fri/prover.rs)
+// =================================================================================================
 struct FriLayer {
   uint64_t* values = nullptr;  // n ext, bit-reversed order (== leaves, 2^arity ext per row)
   uint64_t* levels = nullptr;
@@ -347,63 +608,412 @@ struct FriLayer {
   int log_n = 0;
   std::vector<uint64_t> cap;
 };
+struct etp_fri_state {
+  etp_ctx* ctx = nullptr;
+  etp_fri_params p{};
+  std::vector<FriLayer> layers;  // n_reductions + 1 entries; layers[l].values exists once layer l has been produced
+  int committed = 0, folded = 0;  // layers with a tree / layers folded away
+  uint64_t shift = gl::GENERATOR;  // coset shift of the current layer: 7^(16^l)
+  ~etp_fri_state() {
+    for (auto& x : layers) { dev_free(ctx, x.values); dev_free(ctx, x.levels); }
+  }
+};
+namespace {
+// takes ownership of `values` (a dev_alloc'ed block of 2 * 2^(degree_bits + rate_bits) words)
+int fri_begin_owned(etp_ctx* ctx, uint64_t* values, const etp_fri_params& p, etp_fri_state** out) {
+  auto* s = new etp_fri_state();
+  s->ctx = ctx; s->p = p;
+  s->layers.resize(p.n_reductions + 1);
+  s->layers[0].values = values;
+  s->layers[0].log_n = p.degree_bits + p.rate_bits;
+  *out = s;
+  return ETP_OK;
+}
+int fri_commit_layer(etp_fri_state* s, uint64_t* cap_out) {
+  etp_ctx* ctx = s->ctx;
+  if (s->committed >= s->p.n_reductions || s->committed != s->folded) return etp_fail(ctx, ETP_ERR_STATE, "fri_commit_layer: no layer to commit");
+  FriLayer& L = s->layers[s->committed];
+  const size_t cap_words = (size_t)4 << s->p.cap_height;
+  L.n_leaves = ((size_t)1 << L.log_n) >> ARITY_BITS;
+  L.cap.resize(cap_words);
+  ETP_TRY(dev_alloc(ctx, levels_words(L.n_leaves, s->p.cap_height) * 8, (void**)&L.levels));
+  ETP_TRY(launch_leaf_hash_rowmajor(ctx, L.values, 2 << ARITY_BITS, L.n_leaves, L.levels));
+  ETP_TRY(merkle_build_levels(ctx, L.levels, L.n_leaves, s->p.cap_height, L.cap.data()));
+  if (cap_out) memcpy(cap_out, L.cap.data(), cap_words * 8);
+  s->committed++;
+  return ETP_OK;
+}
+int fri_fold(etp_fri_state* s, gl::Ext beta) {
+  etp_ctx* ctx = s->ctx;
+  if (s->folded >= s->p.n_reductions || s->committed != s->folded + 1) return etp_fail(ctx, ETP_ERR_STATE, "fri_fold: commit the layer first");
+  FriLayer& L = s->layers[s->folded];
+  FriLayer& Nx = s->layers[s->folded + 1];
+  const size_t cur_n = (size_t)1 << L.log_n;
+  Nx.log_n = L.log_n - ARITY_BITS;
+  ETP_TRY(dev_alloc(ctx, (2 * cur_n >> ARITY_BITS) * 8, (void**)&Nx.values));
+  stark::FoldParams f{};
+  f.in = L.values; f.out = Nx.values; f.log_n = L.log_n; f.beta = gl::ecanon(beta);
+  ETP_TRY(get_pow_table(ctx, gl::canon(gl::inv(gl::root_of_unity(L.log_n))), L.log_n, gl::canon(gl::inv(s->shift)), &f.x0_inv));
+  {
+    const uint64_t wi = gl::canon(gl::inv(gl::root_of_unity(ARITY_BITS)));
+    uint64_t cur = 1;
+    for (int i = 0; i < 16; i++) { f.w16_inv_pows[i] = gl::canon(cur); cur = gl::mul(cur, wi); }
+  }
+  f.inv16 = gl::canon(gl::inv(16));
+  stark::fri_fold16<<<blocks_for(L.n_leaves, 128), 128, 0, ctx->stream>>>(f);
+  ETP_LAUNCH_CHECK(ctx);
+  s->shift = gl::canon(gl::pow(s->shift, 16));
+  s->folded++;
+  return ETP_OK;
+}
+// final polynomial: coset iDFT of the last layer's values on the host (<= 2^8 points)
+int fri_final_poly(etp_fri_state* s, std::vector<uint64_t>* final_coeffs) {
+  etp_ctx* ctx = s->ctx;
+  if (s->folded != s->p.n_reductions) return etp_fail(ctx, ETP_ERR_STATE, "fri_final_poly: layers remain to be folded");
+  const FriLayer& F = s->layers[s->p.n_reductions];
+  if (F.log_n > 16) return etp_fail(ctx, ETP_ERR_INVALID, "FRI final layer too large (2^%d values)", F.log_n);
+  const size_t fin_n = (size_t)1 << F.log_n, final_len = fin_n >> s->p.rate_bits;
+  std::vector<uint64_t> fin_host(2 * fin_n);
+  ETP_CUDA(ctx, cudaMemcpyAsync(fin_host.data(), F.values, fin_host.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<gl::Ext> fin(fin_n);
+  for (size_t p = 0; p < fin_n; p++) {
+    const size_t k = gl::bitrev32((uint32_t)p, F.log_n);
+    fin[k] = gl::ext(fin_host[2 * p], fin_host[2 * p + 1]);
+  }
+  hostf::ext_fft(fin, F.log_n, true);
+  {
+    const uint64_t si = gl::canon(gl::inv(s->shift));
+    uint64_t cur = 1;
+    for (size_t k = 0; k < fin_n; k++) { fin[k] = gl::ecanon(gl::emul_base(fin[k], cur)); cur = gl::mul(cur, si); }
+  }
+  for (size_t k = final_len; k < fin_n; k++)
+    if (fin[k].c0 || fin[k].c1)
+      return etp_fail(ctx, ETP_ERR_PROOF, "FRI final polynomial has degree >= %zu: the committed function is not a low-degree polynomial (trace violates the constraints)", final_len);
+  final_coeffs->resize(2 * final_len);
+  for (size_t k = 0; k < final_len; k++) { (*final_coeffs)[2 * k] = fin[k].c0; (*final_coeffs)[2 * k + 1] = fin[k].c1; }
+  return ETP_OK;
+}
+// fri_committed_trees: all layers through the challenger, then observe the final polynomial
+int fri_commit_phase(etp_fri_state* s, hostf::Challenger& ch, uint64_t* caps_out, std::vector<uint64_t>* final_coeffs) {
+  const size_t cap_words = (size_t)4 << s->p.cap_height;
+  for (int l = 0; l < s->p.n_reductions; l++) {
+    ETP_TRY(fri_commit_layer(s, nullptr));
+    const FriLayer& L = s->layers[l];
+    ch.observe(L.cap.data(), cap_words);
+    if (caps_out) memcpy(caps_out + (size_t)l * cap_words, L.cap.data(), cap_words * 8);
+    ETP_TRY(fri_fold(s, ch.get_ext()));
+  }
+  ETP_TRY(fri_final_poly(s, final_coeffs));
+  ch.observe(final_coeffs->data(), final_coeffs->size());
+  return ETP_OK;
+}
+// fri_prover_query_rounds for the given x indices: out receives, per index, the initial-tree rows + paths and the per-layer
+// evaluations + paths
+int fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracles, const uint64_t* x_idx, size_t nq, uint64_t* out) {
+  etp_ctx* ctx = s->ctx;
+  const etp_fri_params& p = s->p;
+  const int log_lde = p.degree_bits + p.rate_bits, n_layers = p.n_reductions;
+  const size_t lde_n = (size_t)1 << log_lde;
+  if (s->committed != n_layers) return etp_fail(ctx, ETP_ERR_STATE, "fri_query_rounds: the commit phase is not finished");
+  if (nq == 0) return ETP_OK;
+  const int init_path = log_lde - p.cap_height;
+  for (size_t o = 0; o < n_oracles; o++)
+    if (!oracles[o] || oracles[o]->ctx != ctx || oracles[o]->log_n != p.degree_bits || oracles[o]->rate_bits != p.rate_bits || oracles[o]->cap_height != p.cap_height)
+      return etp_fail(ctx, ETP_ERR_INVALID, "FRI oracle %zu does not match the FRI parameters", o);
+  // device staging: per oracle rows + paths, per layer rows + paths
+  size_t stage_words = 0;
+  for (size_t o = 0; o < n_oracles; o++) stage_words += nq * (oracles[o]->n_cols + 4 * (size_t)init_path);
+  {
+    int bits = log_lde;
+    for (int l = 0; l < n_layers; l++) { bits -= ARITY_BITS; stage_words += nq * (32 + 4 * (size_t)(bits - p.cap_height)); }
+  }
+  DevBuf<uint64_t> stage(ctx), d_idx(ctx);
+  ETP_TRY(stage.alloc(stage_words));
+  ETP_TRY(d_idx.alloc(nq * (n_layers + 1)));
+  std::vector<uint64_t> idx_all(nq * (n_layers + 1));
+  for (size_t qn = 0; qn < nq; qn++) {
+    uint64_t x = x_idx[qn];
+    if (x >= lde_n) return etp_fail(ctx, ETP_ERR_INVALID, "FRI query index out of range");
+    idx_all[qn] = x;
+    for (int l = 0; l < n_layers; l++) { x >>= ARITY_BITS; idx_all[(size_t)(l + 1) * nq + qn] = x; }
+  }
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_idx.p, idx_all.data(), idx_all.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<size_t> off_rows(n_oracles), off_paths(n_oracles);
+  size_t off = 0;
+  for (size_t o = 0; o < n_oracles; o++) {
+    const int nc = (int)oracles[o]->n_cols;
+    off_rows[o] = off;
+    if (nc) {
+      merkle::gather_rows_colmajor<<<blocks_for(nq * nc, 256), 256, 0, ctx->stream>>>(oracles[o]->lde, lde_n, nc, d_idx.p, (int)nq, stage.p + off);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+    off += nq * nc;
+    off_paths[o] = off;
+    if (init_path > 0) {
+      stark::gather_paths<<<blocks_for(nq * init_path, 256), 256, 0, ctx->stream>>>(oracles[o]->levels, (uint32_t)lde_n, init_path, d_idx.p, (int)nq,
+                                                                                   stage.p + off);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+    off += nq * 4 * init_path;
+  }
+  std::vector<size_t> loff_rows(n_layers), loff_paths(n_layers);
+  for (int l = 0; l < n_layers; l++) {
+    const FriLayer& L = s->layers[l];
+    const int path = L.log_n - ARITY_BITS - p.cap_height;
+    loff_rows[l] = off;
+    stark::gather_rows_rowmajor<<<blocks_for(nq * 32, 256), 256, 0, ctx->stream>>>(L.values, 32, d_idx.p + (size_t)(l + 1) * nq, (int)nq, stage.p + off);
+    ETP_LAUNCH_CHECK(ctx);
+    off += nq * 32;
+    loff_paths[l] = off;
+    if (path > 0) {
+      stark::gather_paths<<<blocks_for(nq * path, 256), 256, 0, ctx->stream>>>(L.levels, (uint32_t)L.n_leaves, path, d_idx.p + (size_t)(l + 1) * nq,
+                                                                              (int)nq, stage.p + off);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+    off += nq * 4 * path;
+  }
+  std::vector<uint64_t> sh(stage_words ? stage_words : 1);
+  ETP_CUDA(ctx, cudaMemcpyAsync(sh.data(), stage.p, stage_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint64_t* w = out;
+  for (size_t qn = 0; qn < nq; qn++) {
+    for (size_t o = 0; o < n_oracles; o++) {
+      const size_t nc = oracles[o]->n_cols;
+      memcpy(w, &sh[off_rows[o] + qn * nc], nc * 8); w += nc;
+      memcpy(w, &sh[off_paths[o] + qn * 4 * init_path], (size_t)4 * init_path * 8); w += 4 * init_path;
+    }
+    for (int l = 0; l < n_layers; l++) {
+      const int path = s->layers[l].log_n - ARITY_BITS - p.cap_height;
+      memcpy(w, &sh[loff_rows[l] + qn * 32], 32 * 8); w += 32;
+      memcpy(w, &sh[loff_paths[l] + qn * 4 * path], (size_t)4 * path * 8); w += 4 * path;
+    }
+  }
+  return ETP_OK;
+}
 
-// trace_host != nullptr: the trace (n_cols x n, column-major, stride n) is still on the host; trace_dev is an empty device
-// buffer of the same shape that the streamed trace commit fills column group by column group while it transforms and
-// hashes the groups that have already arrived (etp_stark_prove_host).
-int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t stride, const uint64_t* pi_in, uint64_t* proof,
-                    const uint64_t* trace_host = nullptr) {
-  TableInfo ti;
-  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
-  if (log_n < 1 || log_n + RATE_BITS > 30) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported degree_bits %d", log_n);
-  const int n_layers = fri_num_layers(log_n);
-  if (ARITY_BITS * n_layers > log_n + RATE_BITS - CAP_HEIGHT || log_n + RATE_BITS < CAP_HEIGHT)
-    return etp_fail(ctx, ETP_ERR_INVALID, "FRI total reduction arity is too large.");
+// fri_proof: commit phase, proof of work, query rounds.  out: flat FriProof (fri_proof_words)
+int fri_proof(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracles, hostf::Challenger& ch, uint64_t* out, PhaseTimer* timer) {
+  etp_ctx* ctx = s->ctx;
+  const etp_fri_params& p = s->p;
+  const size_t cap_words = (size_t)4 << p.cap_height;
+  const size_t lde_n = (size_t)1 << (p.degree_bits + p.rate_bits);
+  uint64_t* w = out;
+  std::vector<uint64_t> final_coeffs;
+  ETP_TRY(fri_commit_phase(s, ch, w, &final_coeffs));
+  w += cap_words * p.n_reductions;
+  if (timer) timer->mark("fold codewords in the commitment phase");
+  // fri_proof_of_work
+  uint64_t st[12];
+  memcpy(st, ch.sponge_state, sizeof st);
+  for (uint32_t i = 0; i < ch.input_len; i++) st[i] = ch.input_buffer[i];
+  uint64_t pow_witness = 0;
+  ETP_TRY(pow_grind(ctx, st, (int)ch.input_len, p.proof_of_work_bits, &pow_witness));
+  ch.observe(pow_witness);
+  const uint64_t pow_response = ch.get();
+  if (p.proof_of_work_bits && (pow_response >> (64 - p.proof_of_work_bits)) != 0) return etp_fail(ctx, ETP_ERR_PROOF, "proof of work response mismatch");
+  if (timer) timer->mark("find proof-of-work witness");
+  // fri_prover_query_rounds
+  std::vector<uint64_t> qidx(p.num_query_rounds);
+  for (int qn = 0; qn < p.num_query_rounds; qn++) qidx[qn] = ch.get() % lde_n;
+  ETP_TRY(fri_query_rounds(s, oracles, n_oracles, qidx.data(), qidx.size(), w));
+  std::vector<size_t> oc(n_oracles);
+  for (size_t o = 0; o < n_oracles; o++) oc[o] = oracles[o]->n_cols;
+  w = out + fri_proof_words(oc.data(), n_oracles, p) - final_coeffs.size() - 1;
+  if (timer) timer->mark("build FRI query rounds");
+  memcpy(w, final_coeffs.data(), final_coeffs.size() * 8); w += final_coeffs.size();
+  *w++ = pow_witness;
+  return ETP_OK;
+}
+
+template <int B>
+void launch_combine(etp_ctx* ctx, const stark::CombineParams& c, size_t lde_n, bool chunked) {
+  if (chunked) stark::combine_accumulate<B><<<dim3(blocks_for(lde_n, 128), c.n_chunks), 128, 0, ctx->stream>>>(c);
+  else stark::combine_values<B><<<blocks_for(lde_n, 128), 128, 0, ctx->stream>>>(c);
+}
+
+// PolynomialBatch::prove_openings in evaluation form over the LDE coset, then fri_proof.  `ys`: the claimed value of every
+// batch polynomial at the batch point when the caller already has them (the openings of a STARK), else nullptr (they are
+// then evaluated here from the coefficients).
+int prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches, etp_batch* const* oracles, size_t n_oracles,
+                   hostf::Challenger& ch, const etp_fri_params& fp, const std::vector<std::vector<gl::Ext>>* ys, uint64_t* out, PhaseTimer* timer) {
+  ETP_TRY(check_fri_params(ctx, fp));
+  if (n_batches < 1 || n_batches > (size_t)stark::MAX_FRI_BATCHES) return etp_fail(ctx, ETP_ERR_INVALID, "between 1 and %d FRI batches are supported", stark::MAX_FRI_BATCHES);
+  const int log_n = fp.degree_bits, log_lde = log_n + fp.rate_bits;
+  const size_t lde_n = (size_t)1 << log_lde;
+  for (size_t o = 0; o < n_oracles; o++)
+    if (!oracles[o] || oracles[o]->ctx != ctx || oracles[o]->log_n != log_n || oracles[o]->rate_bits != fp.rate_bits || oracles[o]->cap_height != fp.cap_height)
+      return etp_fail(ctx, ETP_ERR_INVALID, "FRI oracle %zu does not match the FRI parameters", o);
+  const gl::Ext alpha = ch.get_ext();
+  // unique columns in order of first appearance, with their alpha power per batch
+  std::vector<stark::CombineCol> cols;
+  std::map<std::pair<uint32_t, uint32_t>, int> where;
+  size_t max_count = 0;
+  for (size_t b = 0; b < n_batches; b++) {
+    max_count = batches[b].n_polynomials > max_count ? batches[b].n_polynomials : max_count;
+    for (size_t k = 0; k < batches[b].n_polynomials; k++) {
+      const etp_fri_poly fpi = batches[b].polynomials[k];
+      if (fpi.oracle_index >= n_oracles || fpi.polynomial_index >= oracles[fpi.oracle_index]->n_cols)
+        return etp_fail(ctx, ETP_ERR_INVALID, "FRI batch %zu: polynomial (%u, %u) does not exist", b, fpi.oracle_index, fpi.polynomial_index);
+      auto key = std::make_pair(fpi.oracle_index, fpi.polynomial_index);
+      auto it = where.find(key);
+      int u;
+      if (it == where.end()) {
+        stark::CombineCol cc{};
+        cc.ptr = oracles[fpi.oracle_index]->lde + (size_t)fpi.polynomial_index * lde_n;
+        for (int j = 0; j < stark::MAX_FRI_BATCHES; j++) cc.idx[j] = stark::COMBINE_NONE;
+        cols.push_back(cc);
+        u = (int)cols.size() - 1;
+        where.emplace(key, u);
+      } else {
+        u = it->second;
+      }
+      if (cols[u].idx[b] != stark::COMBINE_NONE) return etp_fail(ctx, ETP_ERR_INVALID, "FRI batch %zu lists a polynomial twice", b);
+      cols[u].idx[b] = (uint32_t)k;
+    }
+  }
+  stark::CombineParams c{};
+  c.n_cols = (int)cols.size(); c.n_batches = (int)n_batches; c.log_lde = log_lde;
+  for (size_t b = 1; b < n_batches; b++) {  // prefix batches: unique column u carries power u in batch 0 and in batch b, for u < n_b
+    bool prefix = batches[b].n_polynomials > 0 && batches[b].n_polynomials <= batches[0].n_polynomials;
+    for (size_t u = 0; prefix && u < cols.size(); u++)
+      prefix = u < batches[b].n_polynomials ? (cols[u].idx[b] == u && cols[u].idx[0] == u) : cols[u].idx[b] == stark::COMBINE_NONE;
+    c.prefix_len[b] = prefix ? (int)batches[b].n_polynomials : 0;
+  }
+  // alpha powers, the reduced openings y_b = sum_k alpha^k f_k(z_b) and the batch shifts
+  std::vector<uint64_t> apow(2 * (max_count + 1));
+  std::vector<gl::Ext> apow_e(max_count + 1);
+  {
+    gl::Ext cur = gl::ext(1, 0);
+    for (size_t k = 0; k <= max_count; k++) { cur = gl::ecanon(cur); apow_e[k] = cur; apow[2 * k] = cur.c0; apow[2 * k + 1] = cur.c1; cur = gl::emul(cur, alpha); }
+  }
+  std::vector<std::vector<gl::Ext>> ys_local;
+  if (!ys) {  // evaluate f_k(z_b) from the coefficients: one kernel per (oracle, pair of points)
+    ys_local.resize(n_batches);
+    for (size_t b = 0; b < n_batches; b += 2) {
+      const gl::Ext z0 = gl::ecanon(gl::ext(batches[b].point[0], batches[b].point[1]));
+      const gl::Ext z1 = b + 1 < n_batches ? gl::ecanon(gl::ext(batches[b + 1].point[0], batches[b + 1].point[1])) : z0;
+      DevBuf<uint64_t> l0(ctx), h0(ctx), l1(ctx), h1(ctx);
+      stark::ExtPowTable t0, t1;
+      ETP_TRY(ext_pow_table(ctx, z0, log_n, l0, h0, &t0));
+      ETP_TRY(ext_pow_table(ctx, z1, log_n, l1, h1, &t1));
+      std::vector<std::vector<gl::Ext>> e0(n_oracles), e1(n_oracles);
+      std::vector<bool> done(n_oracles, false);
+      for (size_t bb = b; bb < b + 2 && bb < n_batches; bb++) {
+        ys_local[bb].resize(batches[bb].n_polynomials);
+        for (size_t k = 0; k < batches[bb].n_polynomials; k++) {
+          const etp_fri_poly fpi = batches[bb].polynomials[k];
+          if (!done[fpi.oracle_index]) { ETP_TRY(eval_batch(ctx, oracles[fpi.oracle_index], t0, t1, e0[fpi.oracle_index], e1[fpi.oracle_index])); done[fpi.oracle_index] = true; }
+          ys_local[bb][k] = (bb == b ? e0 : e1)[fpi.oracle_index][fpi.polynomial_index];
+        }
+      }
+    }
+    ys = &ys_local;
+  }
+  {
+    size_t later = 0;
+    for (size_t b = n_batches; b-- > 0;) {
+      c.z[b] = gl::ecanon(gl::ext(batches[b].point[0], batches[b].point[1]));
+      c.seven_zc1_sq[b] = gl::canon(gl::mul(7, gl::mul(c.z[b].c1, c.z[b].c1)));
+      gl::Ext y = gl::ext(0, 0);
+      if ((*ys)[b].size() != batches[b].n_polynomials) return etp_fail(ctx, ETP_ERR_STATE, "internal error: opening count mismatch");
+      for (size_t k = 0; k < batches[b].n_polynomials; k++) y = gl::eadd(y, gl::emul(apow_e[k], (*ys)[b][k]));
+      c.y[b] = gl::ecanon(y);
+      c.shift[b] = gl::ecanon(gl::epow(alpha, later));
+      later += batches[b].n_polynomials;
+    }
+  }
+  uint64_t* values = nullptr;
+  ETP_TRY(dev_alloc(ctx, 2 * lde_n * 8, (void**)&values));
+  etp_fri_state* st = nullptr;
+  ETP_TRY(fri_begin_owned(ctx, values, fp, &st));
+  std::unique_ptr<etp_fri_state> guard(st);
+  {
+    DevBuf<uint64_t> d_apow(ctx), den(ctx), partial(ctx);
+    DevBuf<stark::CombineCol> d_cols(ctx);
+    ETP_TRY(d_apow.alloc(apow.size()));
+    ETP_TRY(den.alloc(n_batches * lde_n));
+    ETP_TRY(d_cols.alloc(cols.size() ? cols.size() : 1));
+    ETP_CUDA(ctx, cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(stark::CombineCol), cudaMemcpyHostToDevice, ctx->stream));
+    ETP_TRY(get_pow_table(ctx, gl::root_of_unity(log_lde), log_lde, gl::GENERATOR, &c.coset));
+    c.cols = d_cols.p; c.alpha_pows = d_apow.p; c.den = den.p; c.out = values;
+    ETP_TRY(reset_zero_flag(ctx));
+    stark::combine_norms<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(c);
+    ETP_LAUNCH_CHECK(ctx);
+    ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, n_batches * lde_n));
+    // few rows, many columns: one thread per point cannot fill the machine, so the column sums are split into chunks
+    const int B = n_batches <= 2 ? 2 : (n_batches == 3 ? 3 : 4);
+    if (c.n_cols > 256 && lde_n * 4 <= (size_t)1 << 20) {
+      c.col_chunk = 64;
+      c.n_chunks = (c.n_cols + c.col_chunk - 1) / c.col_chunk;
+      ETP_TRY(partial.alloc((size_t)c.n_chunks * lde_n * 2 * B));
+      c.partial = partial.p;
+      if (B == 2) launch_combine<2>(ctx, c, lde_n, true); else if (B == 3) launch_combine<3>(ctx, c, lde_n, true); else launch_combine<4>(ctx, c, lde_n, true);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+    if (B == 2) launch_combine<2>(ctx, c, lde_n, false); else if (B == 3) launch_combine<3>(ctx, c, lde_n, false); else launch_combine<4>(ctx, c, lde_n, false);
+    ETP_LAUNCH_CHECK(ctx);
+    ETP_TRY(check_zero_flag(ctx, "an opening point lies on the LDE coset"));  // also: apow / cols (host) stay alive until here
+  }
+  if (timer) timer->mark("compute openings proof: combine on the LDE domain");
+  return fri_proof(st, oracles, n_oracles, ch, out, timer);
+}
+
+// starky::prover::prove_with_commitment.  trace_dev: the trace values (needed for the auxiliary columns).
+int prove_with_commitment(etp_ctx* ctx, int table, const TableInfo& ti, etp_batch* trace, const uint64_t* trace_dev, size_t stride,
+                          const uint64_t* ctl_ch, hostf::Challenger& ch, const uint64_t* pi_in, uint64_t* proof, PhaseTimer& timer) {
+  const int log_n = trace->log_n;
+  const etp_fri_params fp = standard_fast_params(log_n);
+  ETP_TRY(check_fri_params(ctx, fp));
+  if ((int)trace->n_cols != ti.cols || trace->rate_bits != RATE_BITS || trace->cap_height != CAP_HEIGHT || trace->ctx != ctx)
+    return etp_fail(ctx, ETP_ERR_INVALID, "trace commitment does not match the table / standard_fast_config");
+  if (ti.ctl() && !ctl_ch) return etp_fail(ctx, ETP_ERR_INVALID, "the table requires CTLs but no CTL challenges were given");
   const size_t n = (size_t)1 << log_n;
-  const int log_lde = log_n + RATE_BITS;
-  const size_t lde_n = (size_t)1 << log_lde, cap_words = (size_t)4 << CAP_HEIGHT;
-  const int n_aux = ti.n_aux(NUM_CHALLENGES), factor = quotient_factor(ti), n_quot = factor * NUM_CHALLENGES;
+  const size_t cap_words = (size_t)4 << CAP_HEIGHT;
+  const int n_lookup = ti.n_lookup_cols(NUM_CHALLENGES), n_helpers = ti.n_ctl_helpers(), n_zs = ti.n_ctl_zs();
+  const int n_aux = n_lookup + n_helpers + n_zs, factor = quotient_factor(ti), n_quot = factor * NUM_CHALLENGES;
   uint64_t pi[stark::MAX_PUBLIC_INPUTS] = {};
   for (int i = 0; i < ti.n_pi; i++) pi[i] = gl::canon(pi_in[i]);
-  PhaseTimer timer(ctx);
 
   uint64_t* w = proof;
-  uint64_t* hdr = w; w += 16;
+  uint64_t* hdr = w; w += HEADER_WORDS;
+  memset(hdr, 0, HEADER_WORDS * 8);
   hdr[0] = PROOF_MAGIC; hdr[1] = table; hdr[2] = log_n; hdr[3] = ti.cols; hdr[4] = n_aux; hdr[5] = n_quot; hdr[6] = CAP_HEIGHT;
-  hdr[7] = n_layers; hdr[8] = ARITY_BITS; hdr[9] = (uint64_t)1 << (log_n - ARITY_BITS * n_layers); hdr[10] = NUM_QUERIES; hdr[11] = ti.n_pi;
+  hdr[7] = fp.n_reductions; hdr[8] = ARITY_BITS; hdr[9] = (uint64_t)1 << (log_n - fri_total_arities(fp)); hdr[10] = NUM_QUERIES; hdr[11] = ti.n_pi;
   hdr[12] = RATE_BITS; hdr[13] = POW_BITS; hdr[14] = NUM_CHALLENGES; hdr[15] = proof_words(ti, log_n);
+  hdr[16] = n_zs; hdr[17] = n_lookup; hdr[18] = n_helpers;
+  memcpy(w, trace->cap.data(), cap_words * 8); w += cap_words;
 
   struct Batches {
-    etp_batch *trace = nullptr, *aux = nullptr, *quot = nullptr;
-    ~Batches() { etp_batch_free(trace); etp_batch_free(aux); etp_batch_free(quot); }
+    etp_batch *aux = nullptr, *quot = nullptr;
+    ~Batches() { etp_batch_free(aux); etp_batch_free(quot); }
   } B;
 
-  // ---- prove(): trace commitment; the challenger observes the public inputs, then the trace cap
-  ETP_TRY(batch_create(ctx, ti.cols, log_n, RATE_BITS, 0, CAP_HEIGHT, &B.trace));
-  if (trace_host) {
-    std::vector<const uint64_t*> cols(ti.cols);
-    for (int c = 0; c < ti.cols; c++) cols[c] = trace_host + (size_t)c * n;
-    ETP_TRY(batch_commit_from_host_streamed(B.trace, cols.data(), true, const_cast<uint64_t*>(trace_dev)));
-  } else {
-    ETP_TRY(batch_commit_from_values(B.trace, trace_dev, stride));
-  }
-  timer.mark("trace commit (IFFT + FFT + Merkle tree)");
-  hostf::Challenger ch;
-  ch.observe(pi, ti.n_pi);
-  ch.observe(B.trace->cap.data(), cap_words);
-  memcpy(w, B.trace->cap.data(), cap_words * 8); w += cap_words;
-
-  // ---- prove_with_commitment: lookup helper columns + auxiliary commitment
-  uint64_t lookup_ch[NUM_CHALLENGES] = {0, 0};
+  // ---- lookup challenges: the CTL betas when CTL challenges are given, else get_grand_product_challenge_set's betas
+  uint64_t scalars[stark::MAX_CH_SCALARS] = {};
   if (ti.lookup()) {
-    // get_grand_product_challenge_set: (beta, gamma) per challenge, the lookup argument uses beta
-    for (int k = 0; k < NUM_CHALLENGES; k++) { lookup_ch[k] = ch.get(); (void)ch.get(); }
+    for (int k = 0; k < NUM_CHALLENGES; k++) {
+      if (ctl_ch) scalars[k] = gl::canon(ctl_ch[2 * k]);
+      else { scalars[k] = ch.get(); (void)ch.get(); }
+    }
+  }
+  if (ctl_ch) for (int k = 0; k < 2 * NUM_CHALLENGES; k++) scalars[NUM_CHALLENGES + k] = gl::canon(ctl_ch[k]);
+  const int n_scalars = ctl_ch ? 3 * NUM_CHALLENGES : (ti.lookup() ? NUM_CHALLENGES : 0);
+  std::vector<uint64_t> zs_first(n_zs);
+  if (n_aux) {
     DevBuf<uint64_t> aux_vals(ctx);
     ETP_TRY(aux_vals.alloc((size_t)n_aux * n));
-    ETP_TRY(lookup_helper_columns(ctx, table, log_n, trace_dev, stride, lookup_ch, NUM_CHALLENGES, aux_vals.p));
+    ETP_TRY(reset_zero_flag(ctx));
+    ETP_TRY(aux_columns(ctx, ti, log_n, trace_dev, stride, scalars, NUM_CHALLENGES, ctl_ch ? scalars + NUM_CHALLENGES : nullptr, aux_vals.p));
+    // ctl_zs_first: Z(1) = the first trace-domain value of every CTL Z
+    if (n_zs)
+      ETP_CUDA(ctx, cudaMemcpy2DAsync(zs_first.data(), 8, aux_vals.p + (size_t)(n_lookup + n_helpers) * n, n * 8, 8, n_zs, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
     timer.mark("compute lookup helper columns");
     ETP_TRY(batch_create(ctx, n_aux, log_n, RATE_BITS, 0, CAP_HEIGHT, &B.aux));
-    ETP_TRY(batch_commit_from_values(B.aux, aux_vals.p, n));
+    ETP_TRY(batch_commit_from_values(B.aux, aux_vals.p, n));  // synchronises the stream
+    ETP_TRY(check_zero_flag(ctx, "a lookup / CTL denominator vanishes on the trace"));
     timer.mark("auxiliary polys commit");
     ch.observe(B.aux->cap.data(), cap_words);
     memcpy(w, B.aux->cap.data(), cap_words * 8); w += cap_words;
@@ -413,7 +1023,7 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
 
   // ---- quotient
   ETP_TRY(batch_create(ctx, n_quot, log_n, RATE_BITS, 0, CAP_HEIGHT, &B.quot));
-  ETP_TRY(compute_quotient(ctx, table, B.trace, B.aux, lookup_ch, ti.lookup() ? NUM_CHALLENGES : 0, pi, alphas, NUM_CHALLENGES, B.quot->coeffs));
+  ETP_TRY(compute_quotient(ctx, table, trace, B.aux, scalars, n_scalars, pi, alphas, NUM_CHALLENGES, B.quot->coeffs));
   timer.mark("compute quotient polys");
   ETP_TRY(batch_commit_from_coeffs(B.quot));
   timer.mark("quotient polys commit");
@@ -436,226 +1046,80 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
     stark::ExtPowTable t0, t1;
     ETP_TRY(ext_pow_table(ctx, zeta, log_n, l0, h0, &t0));
     ETP_TRY(ext_pow_table(ctx, zeta_next, log_n, l1, h1, &t1));
-    ETP_TRY(eval_batch(ctx, B.trace, t0, t1, zeta, zeta_next, tr0, tr1));
-    if (B.aux) ETP_TRY(eval_batch(ctx, B.aux, t0, t1, zeta, zeta_next, ax0, ax1));
-    ETP_TRY(eval_batch(ctx, B.quot, t0, t1, zeta, zeta_next, qu0, qu1));
+    ETP_TRY(eval_batch(ctx, trace, t0, t1, tr0, tr1));
+    if (B.aux) ETP_TRY(eval_batch(ctx, B.aux, t0, t1, ax0, ax1));
+    ETP_TRY(eval_batch(ctx, B.quot, t0, t1, qu0, qu1));
   }
   timer.mark("compute openings proof: evaluate at zeta, g*zeta");
+  // StarkOpeningSet order: local_values, next_values, auxiliary_polys, auxiliary_polys_next, ctl_zs_first, quotient_polys
   auto put = [&](const std::vector<gl::Ext>& v) { for (auto& e : v) { *w++ = e.c0; *w++ = e.c1; } };
-  put(tr0); put(tr1); put(ax0); put(ax1); put(qu0);
-  // observe_openings(to_fri_openings): zeta batch = local ++ aux ++ quotient ; next batch = next ++ aux_next
+  put(tr0); put(tr1); put(ax0); put(ax1);
+  for (int k = 0; k < n_zs; k++) *w++ = gl::canon(zs_first[k]);
+  put(qu0);
+  // observe_openings(to_fri_openings): zeta batch = local ++ aux ++ quotient ; next batch = next ++ aux_next ; ctl_zs_first
   auto obs = [&](const std::vector<gl::Ext>& v) { for (auto& e : v) { ch.observe(e.c0); ch.observe(e.c1); } };
   obs(tr0); obs(ax0); obs(qu0); obs(tr1); obs(ax1);
+  for (int k = 0; k < n_zs; k++) { ch.observe(zs_first[k]); ch.observe(0); }
 
-  // ---- PolynomialBatch::prove_openings, in evaluation form over the LDE coset
-  const gl::Ext alpha = ch.get_ext();
-  const int n0 = ti.cols + n_aux + n_quot, n1 = ti.cols + n_aux;
-  std::vector<uint64_t> apow(2 * (size_t)(n0 + 1));
-  gl::Ext y0 = gl::ext(0, 0), y1 = gl::ext(0, 0), shift0;
-  {
-    gl::Ext cur = gl::ext(1, 0);
-    std::vector<gl::Ext> all0 = tr0, all1 = tr1;
-    all0.insert(all0.end(), ax0.begin(), ax0.end());
-    all0.insert(all0.end(), qu0.begin(), qu0.end());
-    all1.insert(all1.end(), ax1.begin(), ax1.end());
-    for (int k = 0; k <= n0; k++) {
-      cur = gl::ecanon(cur);
-      apow[2 * k] = cur.c0; apow[2 * k + 1] = cur.c1;
-      if (k < n0) y0 = gl::eadd(y0, gl::emul(cur, all0[k]));
-      if (k < n1) y1 = gl::eadd(y1, gl::emul(cur, all1[k]));
-      if (k == n1) shift0 = cur;
-      cur = gl::emul(cur, alpha);
-    }
-  }
-  std::vector<FriLayer> layers(n_layers + 1);
-  struct LayerGuard {
-    etp_ctx* ctx; std::vector<FriLayer>* l;
-    ~LayerGuard() { for (auto& x : *l) { dev_free(ctx, x.values); dev_free(ctx, x.levels); } }
-  } guard{ctx, &layers};
-  layers[0].log_n = log_lde;
-  ETP_TRY(dev_alloc(ctx, 2 * lde_n * 8, (void**)&layers[0].values));
-  {
-    DevBuf<uint64_t> d_apow(ctx), den(ctx);
-    ETP_TRY(d_apow.alloc(apow.size()));
-    ETP_TRY(den.alloc(2 * lde_n));
-    ETP_CUDA(ctx, cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    stark::CombineParams c{};
-    c.cols[0] = B.trace->lde; c.strides[0] = lde_n; c.n_cols[0] = ti.cols;
-    c.cols[1] = B.aux ? B.aux->lde : nullptr; c.strides[1] = lde_n; c.n_cols[1] = n_aux;
-    c.cols[2] = B.quot->lde; c.strides[2] = lde_n; c.n_cols[2] = n_quot;
-    c.n1 = n1; c.log_lde = log_lde;
-    ETP_TRY(get_pow_table(ctx, gl::root_of_unity(log_lde), log_lde, gl::GENERATOR, &c.coset));
-    c.alpha_pows = d_apow.p;
-    c.y0 = gl::ecanon(y0); c.y1 = gl::ecanon(y1); c.z0 = zeta; c.z1 = zeta_next; c.shift0 = shift0;
-    c.seven_z0c1_sq = gl::canon(gl::mul(7, gl::mul(zeta.c1, zeta.c1)));
-    c.seven_z1c1_sq = gl::canon(gl::mul(7, gl::mul(zeta_next.c1, zeta_next.c1)));
-    c.den = den.p; c.out = layers[0].values;
-    stark::combine_norms<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(c);
-    ETP_LAUNCH_CHECK(ctx);
-    ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, 2 * lde_n));
-    // few rows, many columns: one thread per point cannot fill the machine, so the column sums are split into chunks
-    DevBuf<uint64_t> partial(ctx);
-    if (n0 > 256 && lde_n * 4 <= (size_t)1 << 20) {
-      c.col_chunk = 64;
-      c.n_chunks = (n0 + c.col_chunk - 1) / c.col_chunk;
-      ETP_TRY(partial.alloc((size_t)c.n_chunks * lde_n * 4));
-      c.partial = partial.p;
-      stark::combine_accumulate<<<dim3(blocks_for(lde_n, 128), c.n_chunks), 128, 0, ctx->stream>>>(c);
-      ETP_LAUNCH_CHECK(ctx);
-    }
-    stark::combine_values<<<blocks_for(lde_n, 128), 128, 0, ctx->stream>>>(c);
-    ETP_LAUNCH_CHECK(ctx);
-    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // apow (host) and d_apow stay alive until here
-  }
-  timer.mark("compute openings proof: combine on the LDE domain");
-
-  // ---- fri_committed_trees: evaluation-domain folding, shift_l = 7^(16^l)
-  uint64_t shift = gl::GENERATOR;
-  uint64_t w16_inv_pows[16];
-  {
-    const uint64_t wi = gl::canon(gl::inv(gl::root_of_unity(ARITY_BITS)));
-    uint64_t cur = 1;
-    for (int i = 0; i < 16; i++) { w16_inv_pows[i] = gl::canon(cur); cur = gl::mul(cur, wi); }
-  }
-  for (int l = 0; l < n_layers; l++) {
-    FriLayer& L = layers[l];
-    const size_t cur_n = (size_t)1 << L.log_n;
-    L.n_leaves = cur_n >> ARITY_BITS;
-    L.cap.resize(cap_words);
-    ETP_TRY(dev_alloc(ctx, levels_words(L.n_leaves, CAP_HEIGHT) * 8, (void**)&L.levels));
-    ETP_TRY(launch_leaf_hash_rowmajor(ctx, L.values, 2 << ARITY_BITS, L.n_leaves, L.levels));
-    ETP_TRY(merkle_build_levels(ctx, L.levels, L.n_leaves, CAP_HEIGHT, L.cap.data()));
-    ch.observe(L.cap.data(), cap_words);
-    memcpy(w, L.cap.data(), cap_words * 8); w += cap_words;
-    const gl::Ext beta = ch.get_ext();
-    FriLayer& Nx = layers[l + 1];
-    Nx.log_n = L.log_n - ARITY_BITS;
-    ETP_TRY(dev_alloc(ctx, (2 * cur_n >> ARITY_BITS) * 8, (void**)&Nx.values));
-    stark::FoldParams f{};
-    f.in = L.values; f.out = Nx.values; f.log_n = L.log_n; f.beta = beta;
-    ETP_TRY(get_pow_table(ctx, gl::canon(gl::inv(gl::root_of_unity(L.log_n))), L.log_n, gl::canon(gl::inv(shift)), &f.x0_inv));
-    memcpy(f.w16_inv_pows, w16_inv_pows, sizeof w16_inv_pows);
-    f.inv16 = gl::canon(gl::inv(16));
-    stark::fri_fold16<<<blocks_for(L.n_leaves, 128), 128, 0, ctx->stream>>>(f);
-    ETP_LAUNCH_CHECK(ctx);
-    shift = gl::canon(gl::pow(shift, 16));
-  }
-  timer.mark("fold codewords in the commitment phase");
-
-  // ---- final polynomial: coset iDFT of the last layer's values on the host (<= 2^8 points)
-  const FriLayer& F = layers[n_layers];
-  const size_t fin_n = (size_t)1 << F.log_n, final_len = fin_n >> RATE_BITS;
-  std::vector<uint64_t> fin_host(2 * fin_n);
-  ETP_CUDA(ctx, cudaMemcpyAsync(fin_host.data(), F.values, fin_host.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  std::vector<gl::Ext> fin(fin_n);
-  for (size_t p = 0; p < fin_n; p++) {
-    const size_t k = gl::bitrev32((uint32_t)p, F.log_n);
-    fin[k] = gl::ext(fin_host[2 * p], fin_host[2 * p + 1]);
-  }
-  hostf::ext_fft(fin, F.log_n, true);
-  {
-    const uint64_t si = gl::canon(gl::inv(shift));
-    uint64_t cur = 1;
-    for (size_t k = 0; k < fin_n; k++) { fin[k] = gl::ecanon(gl::emul_base(fin[k], cur)); cur = gl::mul(cur, si); }
-  }
-  for (size_t k = final_len; k < fin_n; k++)
-    if (fin[k].c0 || fin[k].c1)
-      return etp_fail(ctx, ETP_ERR_PROOF, "FRI final polynomial has degree >= %zu: the quotient is not a polynomial (trace violates the constraints)", final_len);
-  std::vector<uint64_t> final_coeffs(2 * final_len);
-  for (size_t k = 0; k < final_len; k++) { final_coeffs[2 * k] = fin[k].c0; final_coeffs[2 * k + 1] = fin[k].c1; }
-  ch.observe(final_coeffs.data(), final_coeffs.size());
-
-  // ---- fri_proof_of_work
-  uint64_t st[12];
-  memcpy(st, ch.state, sizeof st);
-  for (int i = 0; i < ch.n_in; i++) st[i] = ch.in[i];
-  uint64_t pow_witness = 0;
-  ETP_TRY(pow_grind(ctx, st, ch.n_in, POW_BITS, &pow_witness));
-  ch.observe(pow_witness);
-  const uint64_t pow_response = ch.get();
-  if (POW_BITS && (pow_response >> (64 - POW_BITS)) != 0) return etp_fail(ctx, ETP_ERR_PROOF, "proof of work response mismatch");
-  timer.mark("find proof-of-work witness");
-
-  // ---- fri_prover_query_rounds
-  std::vector<uint64_t> qidx(NUM_QUERIES);
-  for (int qn = 0; qn < NUM_QUERIES; qn++) qidx[qn] = ch.get() % lde_n;
-  const int init_path = log_lde - CAP_HEIGHT;
-  const etp_batch* init[3] = {B.trace, B.aux, B.quot};
-  // device staging: per oracle rows + paths, per layer rows + paths
-  size_t stage_words = 0;
-  for (int o = 0; o < 3; o++)
-    if (init[o]) stage_words += (size_t)NUM_QUERIES * (init[o]->n_cols + 4 * init_path);
-  {
-    int bits = log_lde;
-    for (int l = 0; l < n_layers; l++) { bits -= ARITY_BITS; stage_words += (size_t)NUM_QUERIES * (32 + 4 * (bits - CAP_HEIGHT)); }
-  }
-  DevBuf<uint64_t> stage(ctx), d_idx(ctx);
-  ETP_TRY(stage.alloc(stage_words));
-  ETP_TRY(d_idx.alloc((size_t)NUM_QUERIES * (n_layers + 1)));
-  std::vector<uint64_t> idx_all((size_t)NUM_QUERIES * (n_layers + 1));
-  for (int qn = 0; qn < NUM_QUERIES; qn++) {
-    uint64_t x = qidx[qn];
-    idx_all[qn] = x;
-    for (int l = 0; l < n_layers; l++) { x >>= ARITY_BITS; idx_all[(size_t)(l + 1) * NUM_QUERIES + qn] = x; }
-  }
-  ETP_CUDA(ctx, cudaMemcpyAsync(d_idx.p, idx_all.data(), idx_all.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  std::vector<size_t> off_rows, off_paths;
-  size_t off = 0;
-  for (int o = 0; o < 3; o++) {
-    if (!init[o]) { off_rows.push_back(0); off_paths.push_back(0); continue; }
-    const int nc = (int)init[o]->n_cols;
-    off_rows.push_back(off);
-    merkle::gather_rows_colmajor<<<blocks_for((size_t)NUM_QUERIES * nc, 256), 256, 0, ctx->stream>>>(init[o]->lde, lde_n, nc, d_idx.p,
-                                                                                                    NUM_QUERIES, stage.p + off);
-    ETP_LAUNCH_CHECK(ctx);
-    off += (size_t)NUM_QUERIES * nc;
-    off_paths.push_back(off);
-    if (init_path > 0) {
-      stark::gather_paths<<<blocks_for((size_t)NUM_QUERIES * init_path, 256), 256, 0, ctx->stream>>>(init[o]->levels, (uint32_t)lde_n, init_path,
-                                                                                                   d_idx.p, NUM_QUERIES, stage.p + off);
-      ETP_LAUNCH_CHECK(ctx);
-    }
-    off += (size_t)NUM_QUERIES * 4 * init_path;
-  }
-  std::vector<size_t> loff_rows(n_layers), loff_paths(n_layers);
-  for (int l = 0; l < n_layers; l++) {
-    const FriLayer& L = layers[l];
-    const int path = L.log_n - ARITY_BITS - CAP_HEIGHT;
-    loff_rows[l] = off;
-    stark::gather_rows_rowmajor<<<blocks_for((size_t)NUM_QUERIES * 32, 256), 256, 0, ctx->stream>>>(
-        L.values, 32, d_idx.p + (size_t)(l + 1) * NUM_QUERIES, NUM_QUERIES, stage.p + off);
-    ETP_LAUNCH_CHECK(ctx);
-    off += (size_t)NUM_QUERIES * 32;
-    loff_paths[l] = off;
-    if (path > 0) {
-      stark::gather_paths<<<blocks_for((size_t)NUM_QUERIES * path, 256), 256, 0, ctx->stream>>>(
-          L.levels, (uint32_t)L.n_leaves, path, d_idx.p + (size_t)(l + 1) * NUM_QUERIES, NUM_QUERIES, stage.p + off);
-      ETP_LAUNCH_CHECK(ctx);
-    }
-    off += (size_t)NUM_QUERIES * 4 * path;
-  }
-  std::vector<uint64_t> sh(stage_words ? stage_words : 1);
-  ETP_CUDA(ctx, cudaMemcpyAsync(sh.data(), stage.p, stage_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  for (int qn = 0; qn < NUM_QUERIES; qn++) {
-    for (int o = 0; o < 3; o++) {
-      if (!init[o]) continue;
-      const size_t nc = init[o]->n_cols;
-      memcpy(w, &sh[off_rows[o] + qn * nc], nc * 8); w += nc;
-      memcpy(w, &sh[off_paths[o] + (size_t)qn * 4 * init_path], (size_t)4 * init_path * 8); w += 4 * init_path;
-    }
-    for (int l = 0; l < n_layers; l++) {
-      const int path = layers[l].log_n - ARITY_BITS - CAP_HEIGHT;
-      memcpy(w, &sh[loff_rows[l] + (size_t)qn * 32], 32 * 8); w += 32;
-      memcpy(w, &sh[loff_paths[l] + (size_t)qn * 4 * path], (size_t)4 * path * 8); w += 4 * path;
-    }
-  }
-  timer.mark("build FRI query rounds");
-  memcpy(w, final_coeffs.data(), final_coeffs.size() * 8); w += final_coeffs.size();
-  *w++ = pow_witness;
+  // ---- stark.fri_instance(zeta, g, num_ctl_helpers, num_ctl_zs, config) + prove_openings
+  etp_batch* oracles[3];
+  size_t n_oracles = 0;
+  const uint32_t o_trace = (uint32_t)n_oracles; oracles[n_oracles++] = trace;
+  const uint32_t o_aux = (uint32_t)n_oracles; if (B.aux) oracles[n_oracles++] = B.aux;
+  const uint32_t o_quot = (uint32_t)n_oracles; oracles[n_oracles++] = B.quot;
+  std::vector<etp_fri_poly> p0, p1, p2;
+  std::vector<std::vector<gl::Ext>> ys(3);
+  for (int cidx = 0; cidx < ti.cols; cidx++) { p0.push_back({o_trace, (uint32_t)cidx}); p1.push_back({o_trace, (uint32_t)cidx}); }
+  for (int cidx = 0; cidx < n_aux; cidx++) { p0.push_back({o_aux, (uint32_t)cidx}); p1.push_back({o_aux, (uint32_t)cidx}); }
+  for (int cidx = 0; cidx < n_quot; cidx++) p0.push_back({o_quot, (uint32_t)cidx});
+  for (int k = 0; k < n_zs; k++) p2.push_back({o_aux, (uint32_t)(n_lookup + n_helpers + k)});
+  ys[0] = tr0; ys[0].insert(ys[0].end(), ax0.begin(), ax0.end()); ys[0].insert(ys[0].end(), qu0.begin(), qu0.end());
+  ys[1] = tr1; ys[1].insert(ys[1].end(), ax1.begin(), ax1.end());
+  for (int k = 0; k < n_zs; k++) ys[2].push_back(gl::ext(gl::canon(zs_first[k]), 0));
+  etp_fri_batch batches[3];
+  batches[0] = {{zeta.c0, zeta.c1}, p0.data(), p0.size()};
+  batches[1] = {{zeta_next.c0, zeta_next.c1}, p1.data(), p1.size()};
+  batches[2] = {{1, 0}, p2.data(), p2.size()};
+  const size_t n_batches = n_zs ? 3 : 2;
+  ys.resize(n_batches);
+  ETP_TRY(prove_openings(ctx, batches, n_batches, oracles, n_oracles, ch, fp, &ys, w, &timer));
+  size_t oc[3];
+  for (size_t o = 0; o < n_oracles; o++) oc[o] = oracles[o]->n_cols;
+  w += fri_proof_words(oc, n_oracles, fp);
   for (int i = 0; i < ti.n_pi; i++) *w++ = pi[i];
   if ((size_t)(w - proof) != hdr[15]) return etp_fail(ctx, ETP_ERR_STATE, "internal error: proof size mismatch");
+  return ETP_OK;
+}
+
+// starky::prover::prove.  trace_host != nullptr: the trace (n_cols x n, column-major, stride n) is still on the host;
+// trace_dev is an empty device buffer of the same shape that the streamed trace commit fills column group by column group
+// while it transforms and hashes the groups that have already arrived (etp_stark_prove_host).
+int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t stride, const uint64_t* pi_in, uint64_t* proof,
+                    const uint64_t* trace_host = nullptr) {
+  TableInfo ti;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (log_n < 1 || log_n + RATE_BITS > 30) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported degree_bits %d", log_n);
+  if (ti.ctl()) return etp_fail(ctx, ETP_ERR_INVALID, "the table requires CTLs: use etp_prove_with_commitment with the CTL challenges");
+  ETP_TRY(check_fri_params(ctx, standard_fast_params(log_n)));
+  const size_t n = (size_t)1 << log_n;
+  PhaseTimer timer(ctx);
+  struct Guard { etp_batch* b = nullptr; ~Guard() { etp_batch_free(b); } } T;
+  // ---- prove(): trace commitment; the challenger observes the public inputs, then the trace cap
+  ETP_TRY(batch_create(ctx, ti.cols, log_n, RATE_BITS, 0, CAP_HEIGHT, &T.b));
+  if (trace_host) {
+    std::vector<const uint64_t*> cols(ti.cols);
+    for (int c = 0; c < ti.cols; c++) cols[c] = trace_host + (size_t)c * n;
+    ETP_TRY(batch_commit_from_host_streamed(T.b, cols.data(), true, const_cast<uint64_t*>(trace_dev)));
+  } else {
+    ETP_TRY(batch_commit_from_values(T.b, trace_dev, stride));
+  }
+  timer.mark("trace commit (IFFT + FFT + Merkle tree)");
+  hostf::Challenger ch;
+  uint64_t pi[stark::MAX_PUBLIC_INPUTS] = {};
+  for (int i = 0; i < ti.n_pi; i++) pi[i] = gl::canon(pi_in[i]);
+  ch.observe(pi, ti.n_pi);
+  ch.observe(T.b->cap.data(), (size_t)4 << CAP_HEIGHT);
+  ETP_TRY(prove_with_commitment(ctx, table, ti, T.b, trace_dev, stride, nullptr, ch, pi, proof, timer));
   timer.finish();
   return ETP_OK;
 }
@@ -665,49 +1129,72 @@ int stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_de
 // =================================================================================================
 // C ABI
 // =================================================================================================
+extern "C" void etp_challenger_init(etp_challenger* c) { if (c) memset(c, 0, sizeof *c); }
+extern "C" void etp_challenger_observe(etp_challenger* c, const uint64_t* e, size_t n) {
+  if (!c || (!e && n)) return;
+  hostf::Challenger ch(*c);
+  ch.observe(e, n);
+  *c = ch;
+}
+extern "C" uint64_t etp_challenger_get_challenge(etp_challenger* c) {
+  if (!c) return 0;
+  hostf::Challenger ch(*c);
+  const uint64_t v = ch.get();
+  *c = ch;
+  return v;
+}
+extern "C" void etp_challenger_get_n_challenges(etp_challenger* c, size_t n, uint64_t* out) {
+  if (!c || (!out && n)) return;
+  hostf::Challenger ch(*c);
+  for (size_t i = 0; i < n; i++) out[i] = ch.get();
+  *c = ch;
+}
+extern "C" void etp_challenger_compact(etp_challenger* c) {
+  if (!c) return;
+  hostf::Challenger ch(*c);
+  ch.compact();
+  *c = ch;
+}
+static bool challenger_ok(const etp_challenger* c) { return c && c->input_len < 8 && c->output_len <= 8; }
+
+extern "C" int etp_fri_params_make(int degree_bits, int rate_bits, int cap_height, int pow_bits, int num_queries, etp_fri_params* out) {
+  if (!out || degree_bits < 0 || rate_bits < 0 || degree_bits + rate_bits > 30 || cap_height < 0) return ETP_ERR_INVALID;
+  fri_params_make(degree_bits, rate_bits, cap_height, pow_bits, num_queries, out);
+  return ETP_OK;
+}
+
 extern "C" int etp_table_num_columns(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.cols : -1; }
 extern "C" int etp_table_constraint_degree(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.degree : -1; }
 extern "C" int etp_table_num_public_inputs(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_pi : -1; }
 extern "C" int etp_table_num_aux_columns(const etp_ctx* c, int t, int nc) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_aux(nc) : -1; }
+extern "C" int etp_table_num_lookup_columns(const etp_ctx* c, int t, int nc) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_lookup_cols(nc) : -1; }
+extern "C" int etp_table_num_ctl_helper_columns(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_ctl_helpers() : -1; }
+extern "C" int etp_table_num_ctl_zs(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_ctl_zs() : -1; }
 extern "C" int etp_table_quotient_degree_factor(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? quotient_factor(ti) : -1; }
 
-extern "C" int etp_table_register(etp_ctx* ctx, const uint64_t* program, size_t n_words, const int32_t* lookups, size_t n_lookup_words,
-                                  int* table_id_out) {
-  etp_bind(ctx);
-  if (!ctx || !program || !table_id_out || (!lookups && n_lookup_words)) return ETP_ERR_INVALID;
+static int register_table(etp_ctx* ctx, const uint64_t* program, size_t n_words, const std::vector<uint64_t>& spec_words, int* table_id_out) {
   auto t = new RegisteredTable();
   struct Guard { RegisteredTable* t; ~Guard() { if (t) { jit_unload(&t->kernel); delete t; } } } guard{t};
-  const std::string why = cprog::parse(program, n_words, stark::MAX_PUBLIC_INPUTS, stark::MAX_CHALLENGES, &t->prog);
+  const std::string why = cprog::parse(program, n_words, stark::MAX_PUBLIC_INPUTS, stark::MAX_CH_SCALARS, &t->prog);
   if (!why.empty()) return etp_fail(ctx, ETP_ERR_INVALID, "%s", why.c_str());
   TableInfo& ti = t->info;
   ti.cols = (int)t->prog.n_trace; ti.degree = (int)t->prog.degree; ti.n_pi = (int)t->prog.n_pi; ti.reg = t;
-  // lookups: [n_lookups, then per lookup: table_col, freq_col, n_looking, looking columns...]
-  if (n_lookup_words) {
-    size_t pos = 0;
-    const int nl = lookups[pos++];
-    if (nl < 0 || nl > 64) return etp_fail(ctx, ETP_ERR_INVALID, "table: bad number of lookups");
-    for (int i = 0; i < nl; i++) {
-      if (pos + 3 > n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: truncated lookup description");
-      LookupInfo l;
-      l.table_col = lookups[pos++]; l.freq_col = lookups[pos++];
-      const int m = lookups[pos++];
-      if (m < 1 || m > 4096 || pos + m > n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: bad looking-column count");
-      for (int j = 0; j < m; j++) l.looking.push_back(lookups[pos++]);
-      for (int c : l.looking)
-        if (c < 0 || c >= ti.cols) return etp_fail(ctx, ETP_ERR_INVALID, "table: lookup column out of range");
-      if (l.table_col < 0 || l.table_col >= ti.cols || l.freq_col < 0 || l.freq_col >= ti.cols)
-        return etp_fail(ctx, ETP_ERR_INVALID, "table: lookup column out of range");
-      ti.lookups.push_back(l);
-    }
-    if (pos != n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: trailing words in the lookup description");
+  ti.aux = std::make_shared<AuxSpec>();
+  if (!spec_words.empty()) {
+    const std::string bad = parse_aux_spec(spec_words.data(), spec_words.size(), ti.cols, NUM_CHALLENGES, ti.aux.get());
+    if (!bad.empty()) return etp_fail(ctx, ETP_ERR_INVALID, "%s", bad.c_str());
   }
+  if ((ti.lookup() || ti.ctl()) && ti.chunk() > 2)
+    return etp_fail(ctx, ETP_ERR_INVALID, "lookups / CTLs need constraint degree 2 or 3 (eval_helper_columns: \"Allow other constraint degrees\")");
   if ((int)t->prog.n_aux != ti.n_aux(NUM_CHALLENGES))
-    return etp_fail(ctx, ETP_ERR_INVALID, "table: the program reads %u auxiliary columns but the lookups produce %d", t->prog.n_aux,
+    return etp_fail(ctx, ETP_ERR_INVALID, "table: the program reads %u auxiliary columns but the lookups / CTLs produce %d", t->prog.n_aux,
                     ti.n_aux(NUM_CHALLENGES));
+  if ((int)t->prog.n_ch > (ti.ctl() ? 3 * NUM_CHALLENGES : (ti.lookup() ? NUM_CHALLENGES : 0)))
+    return etp_fail(ctx, ETP_ERR_INVALID, "table: the program reads %u challenge scalars, more than its lookups / CTLs provide", t->prog.n_ch);
   if (log2_ceil(quotient_factor(ti)) > RATE_BITS)
     return etp_fail(ctx, ETP_ERR_INVALID, "Having constraints of degree higher than the rate is not supported yet.");
-  // same program registered before on this context: share the compiled kernel's source hash -> recompile is cheap
-  // enough to skip a cache; compile now so that errors surface at registration, not in the middle of a proof
+  // compile now so that errors surface at registration, not in the middle of a proof (compiled programs are cached
+  // per process: etp_jit.cu)
   std::vector<char> cubin;
   std::string log;
   ETP_TRY(jit_compile(ctx, cprog::generate_cuda(t->prog), &cubin, &log));
@@ -718,14 +1205,61 @@ extern "C" int etp_table_register(etp_ctx* ctx, const uint64_t* program, size_t 
   return ETP_OK;
 }
 
+extern "C" int etp_table_register(etp_ctx* ctx, const uint64_t* program, size_t n_words, const int32_t* lookups, size_t n_lookup_words,
+                                  int* table_id_out) {
+  etp_bind(ctx);
+  if (!ctx || !program || !table_id_out || (!lookups && n_lookup_words)) return ETP_ERR_INVALID;
+  // lookups: [n_lookups, then per lookup: table_col, freq_col, n_looking, looking columns...] -> general spec words
+  std::vector<uint64_t> spec;
+  if (n_lookup_words) {
+    const int n_trace = n_words > 2 ? (int)program[2] : 0;
+    std::vector<std::tuple<std::vector<int>, int, int>> ls;
+    size_t pos = 0;
+    const int nl = lookups[pos++];
+    if (nl < 0 || nl > 64) return etp_fail(ctx, ETP_ERR_INVALID, "table: bad number of lookups");
+    for (int i = 0; i < nl; i++) {
+      if (pos + 3 > n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: truncated lookup description");
+      const int table_col = lookups[pos++], freq_col = lookups[pos++], m = lookups[pos++];
+      if (m < 1 || m > 4096 || pos + m > n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: bad looking-column count");
+      std::vector<int> looking(lookups + pos, lookups + pos + m);
+      pos += m;
+      for (int c : looking)
+        if (c < 0 || c >= n_trace) return etp_fail(ctx, ETP_ERR_INVALID, "table: lookup column out of range");
+      if (table_col < 0 || table_col >= n_trace || freq_col < 0 || freq_col >= n_trace)
+        return etp_fail(ctx, ETP_ERR_INVALID, "table: lookup column out of range");
+      ls.emplace_back(looking, table_col, freq_col);
+    }
+    if (pos != n_lookup_words) return etp_fail(ctx, ETP_ERR_INVALID, "table: trailing words in the lookup description");
+    spec = simple_spec_words(ls);
+  }
+  return register_table(ctx, program, n_words, spec, table_id_out);
+}
+
+extern "C" int etp_table_register_ex(etp_ctx* ctx, const uint64_t* program, size_t n_words, const uint64_t* aux_spec, size_t n_spec_words,
+                                     int* table_id_out) {
+  etp_bind(ctx);
+  if (!ctx || !program || !table_id_out || (!aux_spec && n_spec_words)) return ETP_ERR_INVALID;
+  return register_table(ctx, program, n_words, std::vector<uint64_t>(aux_spec, aux_spec + n_spec_words), table_id_out);
+}
+
+extern "C" int etp_aux_columns_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
+                                   const uint64_t* lookup_challenges, int n_challenges, const uint64_t* ctl_challenges, uint64_t* aux_dev) {
+  etp_bind(ctx);
+  if (!ctx || !trace_dev || !aux_dev) return ETP_ERR_INVALID;
+  TableInfo ti;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (log_n < 0 || log_n > 30 || n_challenges < 0 || n_challenges > NUM_CHALLENGES || col_stride < ((size_t)1 << log_n) ||
+      (ti.lookup() && (!lookup_challenges || n_challenges == 0)))
+    return etp_fail(ctx, ETP_ERR_INVALID, "bad arguments");
+  if (ti.ctl() && n_challenges != NUM_CHALLENGES) return etp_fail(ctx, ETP_ERR_INVALID, "CTL tables take %d challenges", NUM_CHALLENGES);
+  ETP_TRY(reset_zero_flag(ctx));
+  ETP_TRY(aux_columns(ctx, ti, log_n, trace_dev, col_stride, lookup_challenges, n_challenges, ctl_challenges, aux_dev));
+  return check_zero_flag(ctx, "a lookup / CTL denominator vanishes on the trace");
+}
 extern "C" int etp_lookup_helper_columns_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
                                              const uint64_t* challenges, int n_challenges, uint64_t* aux_dev) {
-  etp_bind(ctx);
-  if (!ctx || !trace_dev || !challenges || !aux_dev) return ETP_ERR_INVALID;
-  if (log_n < 0 || log_n > 30 || n_challenges < 0) return etp_fail(ctx, ETP_ERR_INVALID, "bad arguments");
-  ETP_TRY(lookup_helper_columns(ctx, table, log_n, trace_dev, col_stride, challenges, n_challenges, aux_dev));
-  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return ETP_OK;
+  if (!challenges) return ETP_ERR_INVALID;
+  return etp_aux_columns_dev(ctx, table, log_n, trace_dev, col_stride, challenges, n_challenges, nullptr, aux_dev);
 }
 
 extern "C" int etp_compute_quotient_polys_dev(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* lookup_challenges,
@@ -734,6 +1268,7 @@ extern "C" int etp_compute_quotient_polys_dev(etp_ctx* ctx, int table, etp_batch
   etp_bind(ctx);
   if (!ctx || !trace || !alphas || !out_dev) return ETP_ERR_INVALID;
   uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
+  ETP_TRY(reset_zero_flag(ctx));
   ETP_TRY(compute_quotient(ctx, table, trace, aux, lookup_challenges ? lookup_challenges : zero, n_lookup_challenges,
                            public_inputs ? public_inputs : zero, alphas, n_alphas, out_dev));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -746,10 +1281,115 @@ extern "C" int etp_pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, in
   return pow_grind(ctx, state, pos, bits, witness_out);
 }
 
+extern "C" int etp_batch_eval_at_ext_point(etp_batch* b, const uint64_t z[2], uint64_t* out) {
+  etp_bind(b ? b->ctx : nullptr);
+  if (!b || !z || (!out && b->n_cols)) return ETP_ERR_INVALID;
+  etp_ctx* ctx = b->ctx;
+  const gl::Ext ze = gl::ecanon(gl::ext(z[0], z[1]));
+  DevBuf<uint64_t> l0(ctx), h0(ctx);
+  stark::ExtPowTable t0;
+  ETP_TRY(ext_pow_table(ctx, ze, b->log_n, l0, h0, &t0));
+  std::vector<gl::Ext> e0, e1;
+  ETP_TRY(eval_batch(ctx, b, t0, t0, e0, e1));
+  for (size_t c = 0; c < b->n_cols; c++) { out[2 * c] = e0[c].c0; out[2 * c + 1] = e0[c].c1; }
+  return ETP_OK;
+}
+
+extern "C" size_t etp_fri_proof_words(const size_t* oracle_num_cols, size_t n_oracles, const etp_fri_params* params) {
+  if (!params || (!oracle_num_cols && n_oracles) || params->n_reductions < 0 || params->n_reductions > 16) return 0;
+  return fri_proof_words(oracle_num_cols, n_oracles, *params);
+}
+extern "C" int etp_prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches, etp_batch* const* oracles, size_t n_oracles,
+                                  etp_challenger* challenger, const etp_fri_params* params, uint64_t* fri_proof_out) {
+  etp_bind(ctx);
+  if (!ctx || !batches || !oracles || !n_oracles || !params || !fri_proof_out) return ETP_ERR_INVALID;
+  if (!challenger_ok(challenger)) return etp_fail(ctx, ETP_ERR_INVALID, "bad challenger state");
+  for (size_t b = 0; b < n_batches; b++)
+    if (!batches[b].polynomials && batches[b].n_polynomials) return etp_fail(ctx, ETP_ERR_INVALID, "FRI batch %zu has no polynomial list", b);
+  hostf::Challenger ch(*challenger);
+  PhaseTimer timer(ctx);
+  ETP_TRY(prove_openings(ctx, batches, n_batches, oracles, n_oracles, ch, *params, nullptr, fri_proof_out, &timer));
+  timer.finish();
+  *challenger = ch;
+  return ETP_OK;
+}
+
+extern "C" int etp_fri_begin(etp_ctx* ctx, const uint64_t* values_dev, const etp_fri_params* params, etp_fri_state** out) {
+  etp_bind(ctx);
+  if (!ctx || !values_dev || !params || !out) return ETP_ERR_INVALID;
+  *out = nullptr;
+  ETP_TRY(check_fri_params(ctx, *params));
+  const size_t words = (size_t)2 << (params->degree_bits + params->rate_bits);
+  uint64_t* v = nullptr;
+  ETP_TRY(dev_alloc(ctx, words * 8, (void**)&v));
+  stark::canon_copy<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(values_dev, v, words);
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) { dev_free(ctx, v); return etp_fail(ctx, ETP_ERR_CUDA, "copy kernel failed"); }
+  return fri_begin_owned(ctx, v, *params, out);
+}
+extern "C" int etp_fri_commit_layer(etp_fri_state* s, uint64_t* cap_out) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !cap_out) return ETP_ERR_INVALID;
+  return fri_commit_layer(s, cap_out);
+}
+extern "C" int etp_fri_fold(etp_fri_state* s, const uint64_t beta[2]) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !beta) return ETP_ERR_INVALID;
+  return fri_fold(s, gl::ext(beta[0], beta[1]));
+}
+extern "C" int etp_fri_final_poly(etp_fri_state* s, uint64_t* coeffs_out) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !coeffs_out) return ETP_ERR_INVALID;
+  std::vector<uint64_t> fc;
+  ETP_TRY(fri_final_poly(s, &fc));
+  memcpy(coeffs_out, fc.data(), fc.size() * 8);
+  return ETP_OK;
+}
+extern "C" int etp_fri_commit_phase(etp_fri_state* s, etp_challenger* challenger, uint64_t* caps_out, uint64_t* final_poly_out) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !caps_out || !final_poly_out) return ETP_ERR_INVALID;
+  if (!challenger_ok(challenger)) return etp_fail(s->ctx, ETP_ERR_INVALID, "bad challenger state");
+  hostf::Challenger ch(*challenger);
+  std::vector<uint64_t> fc;
+  ETP_TRY(fri_commit_phase(s, ch, caps_out, &fc));
+  memcpy(final_poly_out, fc.data(), fc.size() * 8);
+  *challenger = ch;
+  return ETP_OK;
+}
+extern "C" int etp_fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracles, const uint64_t* x_indices, size_t n_indices,
+                                    uint64_t* out) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || (!oracles && n_oracles) || (!x_indices && n_indices) || (!out && n_indices)) return ETP_ERR_INVALID;
+  return fri_query_rounds(s, oracles, n_oracles, x_indices, n_indices, out);
+}
+extern "C" void etp_fri_free(etp_fri_state* s) {
+  etp_bind(s ? s->ctx : nullptr);
+  delete s;
+}
+
 extern "C" size_t etp_stark_proof_words(const etp_ctx* ctx, int table, int log_n) {
   TableInfo ti;
   if (!table_info(ctx, table, &ti) || log_n < 1 || log_n > 29) return 0;
   return proof_words(ti, log_n);
+}
+
+extern "C" int etp_prove_with_commitment(etp_ctx* ctx, int table, etp_batch* trace_commitment, const uint64_t* trace_dev, size_t col_stride,
+                                         const uint64_t* ctl_challenges, etp_challenger* challenger, const uint64_t* public_inputs,
+                                         uint64_t* proof_out) {
+  etp_bind(ctx);
+  if (!ctx || !trace_commitment || !trace_dev || !proof_out) return ETP_ERR_INVALID;
+  if (!challenger_ok(challenger)) return etp_fail(ctx, ETP_ERR_INVALID, "bad challenger state");
+  TableInfo ti;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (col_stride < trace_commitment->n()) return etp_fail(ctx, ETP_ERR_INVALID, "trace column stride is smaller than the trace length");
+  uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
+  hostf::Challenger ch(*challenger);
+  PhaseTimer timer(ctx);
+  ETP_TRY(prove_with_commitment(ctx, table, ti, trace_commitment, trace_dev, col_stride, ctl_challenges, ch, public_inputs ? public_inputs : zero,
+                                proof_out, timer));
+  timer.finish();
+  *challenger = ch;
+  return ETP_OK;
 }
 
 extern "C" int etp_stark_prove_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,

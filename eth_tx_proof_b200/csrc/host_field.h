@@ -14,6 +14,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../include/etp_b200.h"
 #include "gl.cuh"
 #include "poseidon_constants.h"
 
@@ -26,30 +27,34 @@ namespace hostf {
 
 inline void poseidon(uint64_t s[12]) { etp_host_poseidon_permute(s); }
 
-struct Challenger {
-  uint64_t state[12] = {0};
-  uint64_t in[8];
-  int n_in = 0;
-  uint64_t out[8];
-  int n_out = 0;
+// The transcript state IS the public plain-data struct etp_challenger (include/etp_b200.h): callers hand it in and get
+// it back (challenger state in / out), exactly the fields of plonky2's Challenger.
+struct Challenger : etp_challenger {
+  Challenger() { memset(static_cast<etp_challenger*>(this), 0, sizeof(etp_challenger)); }
+  explicit Challenger(const etp_challenger& c) : etp_challenger(c) {}
   void duplexing() {
-    for (int i = 0; i < n_in; i++) state[i] = in[i];
-    n_in = 0;
-    poseidon(state);
-    memcpy(out, state, sizeof out);
-    n_out = 8;
+    for (uint32_t i = 0; i < input_len; i++) sponge_state[i] = input_buffer[i];
+    input_len = 0;
+    poseidon(sponge_state);
+    memcpy(output_buffer, sponge_state, sizeof output_buffer);
+    output_len = 8;
   }
   void observe(uint64_t e) {
-    n_out = 0;
-    in[n_in++] = gl::canon(e);
-    if (n_in == 8) duplexing();
+    output_len = 0;
+    input_buffer[input_len++] = gl::canon(e);
+    if (input_len == 8) duplexing();
   }
   void observe(const uint64_t* e, size_t n) { for (size_t i = 0; i < n; i++) observe(e[i]); }
   uint64_t get() {
-    if (n_in != 0 || n_out == 0) duplexing();
-    return out[--n_out];
+    if (input_len != 0 || output_len == 0) duplexing();
+    return output_buffer[--output_len];
   }
   gl::Ext get_ext() { uint64_t a = get(); uint64_t b = get(); return gl::ext(a, b); }
+  // Challenger::compact: flush pending inputs, drop buffered outputs; the sponge state is what a recursion circuit resumes from
+  void compact() {
+    if (input_len != 0) duplexing();
+    output_len = 0;
+  }
 };
 
 // in-place radix-2 DFT on ext values (natural order in/out), root = w or w^-1

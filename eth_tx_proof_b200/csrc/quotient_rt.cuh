@@ -9,7 +9,8 @@
 
 namespace stark {
 
-constexpr int MAX_CHALLENGES = 2;
+constexpr int MAX_CHALLENGES = 2;   // StarkConfig::num_challenges: alphas, lookup challenges, CTL (beta, gamma) pairs
+constexpr int MAX_CH_SCALARS = 8;   // challenge scalars a program may read: lookup challenges [0, 2), then CTL beta_k, gamma_k
 constexpr int MAX_PUBLIC_INPUTS = 16;
 
 // ---- 192-bit lazy accumulator: a sum of products of two field elements, reduced once -------------------------
@@ -78,7 +79,7 @@ struct QuotientParams {
   int n_alphas;
   const uint64_t* alpha_pows;  // device, [n_alphas][n_constraints]: alpha_j^e (Consumer)
   int n_constraints;           // constraints the table emits per row, lookups included
-  uint64_t lookup_ch[MAX_CHALLENGES];
+  uint64_t lookup_ch[MAX_CH_SCALARS];  // lookup challenges, then the CTL challenges (programs index all of them)
   int n_lookup_ch;
   uint64_t pi[MAX_PUBLIC_INPUTS];
   uint64_t* out;  // n_alphas columns x size, NATURAL order (input of coset_ifft)

@@ -156,9 +156,10 @@ static __global__ void lagrange_finish(int log_lde, int log_size, int step_log, 
 }
 
 // ---- batch inverse (Montgomery's trick inside each thread, K strided elements per thread) ----------
-// All inputs must be non-zero (callers guarantee it or report ETP_ERR_PROOF).
+// A zero input (upstream: batch_multiplicative_inverse panics, "Tried to invert zero") raises *zero_flag; the strip's
+// outputs are then meaningless and the caller reports ETP_ERR_PROOF at its next synchronisation point.
 constexpr int INV_K = 8;
-static __global__ void batch_inverse(const uint64_t* in, uint64_t* out, size_t n) {
+static __global__ void batch_inverse(const uint64_t* in, uint64_t* out, size_t n, unsigned long long* zero_flag) {
   const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   uint64_t v[INV_K], pre[INV_K];
@@ -170,6 +171,7 @@ static __global__ void batch_inverse(const uint64_t* in, uint64_t* out, size_t n
     pre[k] = acc;
     acc = gl::mul(acc, v[k]);
   }
+  if (gl::canon(acc) == 0) atomicOr(zero_flag, 1ull);
   uint64_t inv = gl::inv(acc);
 #pragma unroll
   for (int k = INV_K - 1; k >= 0; k--) {
@@ -204,6 +206,96 @@ static __global__ void lookup_terms(const uint64_t* __restrict__ inv, int m, int
     total = gl::add(total, h);
   }
   term[i] = gl::canon(gl::sub(total, gl::mul(freq[i], inv[(size_t)m * n + i])));
+}
+// ---- general auxiliary columns: Lookups with linear-combination Columns / Filters, CTL Z data -----------------------
+// (starky/src/lookup.rs Column::eval_table, Filter::eval_table, get_helper_cols; cross_table_lookup.rs partial_sums)
+// The descriptors are the aux-spec words of include/etp_b200.h, interpreted per row; every thread walks the same words
+// (uniform, cached loads), the trace reads are coalesced along the rows.
+//   Column: n_local, (col, coeff)*, n_next, (col, coeff)*, constant       Filter: n_prod, (Column, Column)*, n_const, Column*
+__device__ __forceinline__ uint64_t aux_eval_column(const uint64_t* __restrict__& w, const uint64_t* __restrict__ trace, size_t stride,
+                                                    uint32_t i, uint32_t i_next) {
+  uint64_t acc = 0;
+  const uint32_t nl = (uint32_t)__ldg(w++);
+  for (uint32_t k = 0; k < nl; k++) {
+    const uint64_t col = __ldg(w++), coeff = __ldg(w++);
+    const uint64_t v = __ldg(trace + col * stride + i);
+    acc = gl::add(acc, coeff == 1 ? v : gl::mul(v, coeff));
+  }
+  const uint32_t nn = (uint32_t)__ldg(w++);
+  for (uint32_t k = 0; k < nn; k++) {
+    const uint64_t col = __ldg(w++), coeff = __ldg(w++);
+    const uint64_t v = __ldg(trace + col * stride + i_next);
+    acc = gl::add(acc, coeff == 1 ? v : gl::mul(v, coeff));
+  }
+  return gl::add(acc, __ldg(w++));
+}
+__device__ __forceinline__ uint64_t aux_eval_filter(const uint64_t* __restrict__& w, const uint64_t* __restrict__ trace, size_t stride,
+                                                    uint32_t i, uint32_t i_next) {
+  uint64_t acc = 0;
+  const uint32_t np = (uint32_t)__ldg(w++);
+  for (uint32_t k = 0; k < np; k++) {
+    const uint64_t a = aux_eval_column(w, trace, stride, i, i_next);
+    const uint64_t b = aux_eval_column(w, trace, stride, i, i_next);
+    acc = gl::add(acc, gl::mul(a, b));
+  }
+  const uint32_t nc = (uint32_t)__ldg(w++);
+  for (uint32_t k = 0; k < nc; k++) acc = gl::add(acc, aux_eval_column(w, trace, stride, i, i_next));
+  return acc;
+}
+// One (columns, filter) pair on every row: den[i] = reduce_with_powers(column evals, beta) + gamma, filt[i] = filter(i).
+// cols: n_cols Column descriptors back to back; filter: one Filter descriptor.
+static __global__ void aux_colset_eval(const uint64_t* __restrict__ trace, size_t stride, uint32_t n, const uint64_t* __restrict__ cols,
+                                       int n_cols, const uint64_t* __restrict__ filter, uint64_t beta, uint64_t gamma,
+                                       uint64_t* __restrict__ den, uint64_t* __restrict__ filt) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t i_next = (i + 1 == n) ? 0 : i + 1;
+  // sum_j col_j * beta^j, ascending with a running power (the descriptors can only be walked forwards)
+  const uint64_t* w = cols;
+  uint64_t acc = 0, bp = 1;
+  for (int j = 0; j < n_cols; j++) {
+    const uint64_t v = aux_eval_column(w, trace, stride, i, i_next);
+    acc = gl::add(acc, j == 0 ? v : gl::mul(v, bp));
+    if (j + 1 < n_cols) bp = j == 0 ? beta : gl::mul(bp, beta);
+  }
+  den[i] = gl::add(acc, gamma);
+  const uint64_t* f = filter;
+  filt[i] = aux_eval_filter(f, trace, stride, i, i_next);
+}
+// a single Column on every row
+static __global__ void aux_column_eval(const uint64_t* __restrict__ trace, size_t stride, uint32_t n, const uint64_t* __restrict__ col,
+                                       uint64_t add_const, uint64_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* w = col;
+  out[i] = gl::add(aux_eval_column(w, trace, stride, i, (i + 1 == n) ? 0 : i + 1), add_const);
+}
+// helper columns of one Lookup / CtlZData from the inverted denominators: helper c = sum over its chunk of filt_s * inv_s;
+// term[i] = sum_c helper_c[i] (- freq[i] * table_inv[i] for a Lookup).  h_out == nullptr: helpers are not kept (single colset).
+static __global__ void aux_helper_terms(const uint64_t* __restrict__ inv, const uint64_t* __restrict__ filt, int n_sets, int chunk, size_t n,
+                                        const uint64_t* __restrict__ freq, const uint64_t* __restrict__ table_inv,
+                                        uint64_t* __restrict__ h_out, uint64_t* __restrict__ term) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t total = 0;
+  int c = 0;
+  for (int s0 = 0; s0 < n_sets; s0 += chunk, c++) {
+    uint64_t h = 0;
+    for (int s = s0; s < s0 + chunk && s < n_sets; s++) h = gl::add(h, gl::mul(inv[(size_t)s * n + i], filt[(size_t)s * n + i]));
+    h = gl::canon(h);
+    if (h_out) h_out[(size_t)c * n + i] = h;
+    total = gl::add(total, h);
+  }
+  if (freq) total = gl::sub(total, gl::mul(freq[i], table_inv[i]));
+  term[i] = gl::canon(total);
+}
+// partial_sums: z[i] = sum_{j >= i} term[j] = total - exclusive_prefix[i], total = prefix[n-1] + term[n-1]
+static __global__ void suffix_from_prefix(const uint64_t* __restrict__ prefix, const uint64_t* __restrict__ term, size_t n,
+                                          uint64_t* __restrict__ z) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t total = gl::add(prefix[n - 1], term[n - 1]);
+  z[i] = gl::canon(gl::sub(total, prefix[i]));
 }
 // exclusive prefix sum over the field, 3 phases; SCAN_BLOCK elements per block
 constexpr int SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_PER_THREAD;
@@ -323,61 +415,83 @@ static __global__ void __launch_bounds__(OPEN_THREADS) eval_polys_at_two_points(
 }
 
 // ---- prove_openings in evaluation form -----------------------------------------------------------
-// final(x) = alpha^shift0 * (sum_{k<n0} alpha^k f_k(x) - y0) / (x - z0) + (sum_{k<n1} alpha^k f_k(x) - y1) / (x - z1)
-// over the LDE coset, where the n1 polynomials of the second batch are a PREFIX of the n0 of the first
-// (trace ++ aux ++ quotient at zeta; trace ++ aux at g*zeta).  This equals coset_fft(final_poly.lde())
-// of upstream's coefficient-form computation point by point.
+// PolynomialBatch::prove_openings for a general FriInstanceInfo (plonky2/src/fri/oracle.rs), point by point on the LDE coset:
+//   final(x) = sum_b alpha^(shift_b) * (sum_{k < n_b} alpha^k f_{b,k}(x) - y_b) / (x - z_b),   shift_b = sum_{b' > b} n_b'
+// which equals coset_fft(final_poly.lde()) of upstream's coefficient-form computation (reduce_polys_base, divide_by_linear,
+// shift_poly).  Every committed column that occurs in some batch is read ONCE: `cols` lists the unique columns in order of
+// first appearance with, per batch, the alpha power it carries there (or NONE).  A batch whose polynomial list is a prefix
+// of batch 0's (starky: the g*zeta batch = trace ++ aux, a prefix of trace ++ aux ++ quotient) costs nothing extra: its sum
+// is a snapshot of batch 0's accumulator.
+constexpr int MAX_FRI_BATCHES = 4;
+constexpr uint32_t COMBINE_NONE = 0xFFFFFFFFu;
+struct CombineCol {
+  const uint64_t* ptr;             // LDE column (bit-reversed rows)
+  uint32_t idx[MAX_FRI_BATCHES];   // alpha power of this column in batch b, or COMBINE_NONE
+};
 struct CombineParams {
-  const uint64_t* cols[3];   // LDE matrices (trace, aux, quotient), bit-reversed rows
-  size_t strides[3];
-  int n_cols[3];
-  int n1;                    // columns in the second batch (prefix)
+  const CombineCol* cols;  // device
+  int n_cols, n_batches;
+  int prefix_len[MAX_FRI_BATCHES];  // > 0: batch b (>= 1) == the first prefix_len[b] unique columns with batch 0's powers
   int log_lde;
-  ntt::PowTable coset;       // 7 * w^k
-  const uint64_t* alpha_pows;  // device: (n0 + 1) ext, interleaved; alpha^k
-  gl::Ext y0, y1, z0, z1, shift0;  // shift0 = alpha^n1
-  uint64_t seven_z0c1_sq, seven_z1c1_sq;
-  uint64_t* den;   // 2 x lde_n: norms to invert (phase 1) / inverted norms (phase 2)
+  ntt::PowTable coset;         // 7 * w^k
+  const uint64_t* alpha_pows;  // device: ext interleaved, alpha^k
+  gl::Ext y[MAX_FRI_BATCHES], z[MAX_FRI_BATCHES], shift[MAX_FRI_BATCHES];
+  uint64_t seven_zc1_sq[MAX_FRI_BATCHES];
+  uint64_t* den;   // n_batches x lde_n: norms to invert (phase 1) / inverted norms (phase 2)
   uint64_t* out;   // lde_n ext interleaved, bit-reversed order
   // wide tables (hundreds of columns on few rows): the column sums are split over blockIdx.y chunks of `col_chunk`
-  // columns by combine_accumulate into partial[chunk][p][acc.c0, acc.c1, acc1.c0, acc1.c1]; n_chunks == 0: inline
+  // columns by combine_accumulate into partial[chunk][p][batch][c0, c1]; n_chunks == 0: inline
   uint64_t* partial;
   int col_chunk, n_chunks;
 };
-// (acc, acc1) += sum over the global column indices [k0, k1) of alpha^k * f_k(x_p); acc1 only takes k < n1.  The two
-// components of alpha^k * v are accumulated without modular reduction (192-bit, reduced once at the end): two wide
-// multiply-adds per column instead of two field multiplications and two field additions.
-__device__ __forceinline__ void combine_columns(const CombineParams& c, uint32_t p, int k0, int k1, gl::Ext& acc, gl::Ext& acc1) {
-  Acc192 s0{}, s1{}, t0{}, t1{};
-  bool snap = false;
-  int base = 0;
-  for (int m = 0; m < 3; m++) {
-    const int lo = k0 > base ? k0 : base, hi = k1 < base + c.n_cols[m] ? k1 : base + c.n_cols[m];
-    for (int k = lo; k < hi; k++) {
-      if (k == c.n1) { t0 = s0; t1 = s1; snap = true; }
-      const uint64_t v = __ldg(c.cols[m] + (size_t)(k - base) * c.strides[m] + p);
-      mac192(s0, v, __ldg(c.alpha_pows + 2 * k));
-      mac192(s1, v, __ldg(c.alpha_pows + 2 * k + 1));
+// acc[b] += sum over the unique columns [u0, u1) of alpha^idx * f(x_p).  The two components of alpha^k * v are accumulated
+// without modular reduction (192-bit, reduced once at the end): two wide multiply-adds per column and batch.
+template <int B>
+__device__ __forceinline__ void combine_columns(const CombineParams& c, uint32_t p, int u0, int u1, gl::Ext (&acc)[B]) {
+  Acc192 s[B][2] = {};
+  Acc192 snap[B][2] = {};
+  for (int u = u0; u < u1; u++) {
+#pragma unroll
+    for (int b = 1; b < B; b++)
+      if (c.prefix_len[b] == u) { snap[b][0] = s[0][0]; snap[b][1] = s[0][1]; }
+    const uint64_t* ptr = reinterpret_cast<const uint64_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&c.cols[u].ptr)));
+    const uint64_t v = __ldg(ptr + p);
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      if (b >= c.n_batches || (b > 0 && c.prefix_len[b] > 0)) continue;
+      const uint32_t k = __ldg(&c.cols[u].idx[b]);
+      if (k == COMBINE_NONE) continue;
+      mac192(s[b][0], v, __ldg(c.alpha_pows + 2 * (size_t)k));
+      mac192(s[b][1], v, __ldg(c.alpha_pows + 2 * (size_t)k + 1));
     }
-    base += c.n_cols[m];
   }
-  if (snap) acc1 = gl::eadd(acc1, gl::ext(reduce192(t0), reduce192(t1)));
-  acc = gl::eadd(acc, gl::ext(reduce192(s0), reduce192(s1)));
+#pragma unroll
+  for (int b = 0; b < B; b++) {
+    if (b >= c.n_batches) continue;
+    if (b > 0 && c.prefix_len[b] > 0) {
+      // this range's share of the prefix sum: everything if it ends inside the prefix, the snapshot if it straddles the
+      // end of the prefix, nothing if it starts after it
+      const int L = c.prefix_len[b];
+      if (L >= u1) acc[b] = gl::eadd(acc[b], gl::ext(reduce192(s[0][0]), reduce192(s[0][1])));
+      else if (L > u0) acc[b] = gl::eadd(acc[b], gl::ext(reduce192(snap[b][0]), reduce192(snap[b][1])));
+    } else {
+      acc[b] = gl::eadd(acc[b], gl::ext(reduce192(s[b][0]), reduce192(s[b][1])));
+    }
+  }
 }
+template <int B>
 static __global__ void __launch_bounds__(128) combine_accumulate(CombineParams c) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = 1u << c.log_lde;
   if (p >= n) return;
-  const int n0 = c.n_cols[0] + c.n_cols[1] + c.n_cols[2];
-  const int k0 = blockIdx.y * c.col_chunk, k1 = (k0 + c.col_chunk) < n0 ? (k0 + c.col_chunk) : n0;
-  gl::Ext acc = gl::ext(0, 0), acc1 = gl::ext(0, 0);
-  combine_columns(c, p, k0, k1, acc, acc1);
-  // this chunk's contribution to the prefix sum acc1: everything if the chunk ends at or before n1, the part before n1
-  // (captured inside combine_columns) if it straddles n1, nothing if it starts at or after n1
-  if (k1 <= c.n1) acc1 = acc;
-  else if (k0 >= c.n1) acc1 = gl::ext(0, 0);
-  uint64_t* dst = c.partial + ((size_t)blockIdx.y * n + p) * 4;
-  dst[0] = acc.c0; dst[1] = acc.c1; dst[2] = acc1.c0; dst[3] = acc1.c1;
+  const int u0 = blockIdx.y * c.col_chunk, u1 = (u0 + c.col_chunk) < c.n_cols ? (u0 + c.col_chunk) : c.n_cols;
+  gl::Ext acc[B];
+#pragma unroll
+  for (int b = 0; b < B; b++) acc[b] = gl::ext(0, 0);
+  combine_columns<B>(c, p, u0, u1, acc);
+  uint64_t* dst = c.partial + ((size_t)blockIdx.y * n + p) * (2 * B);
+#pragma unroll
+  for (int b = 0; b < B; b++) { dst[2 * b] = acc[b].c0; dst[2 * b + 1] = acc[b].c1; }
 }
 static __global__ void combine_norms(CombineParams c) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,34 +499,41 @@ static __global__ void combine_norms(CombineParams c) {
   if (p >= n) return;
   const uint64_t x = c.coset.get(gl::bitrev32(p, c.log_lde));
   // norm of (x - z) = (x - z.c0)^2 - 7 z.c1^2   (7 z.c1^2 is precomputed on the host)
-  const uint64_t a0 = gl::sub(x, c.z0.c0), a1 = gl::sub(x, c.z1.c0);
-  c.den[p] = gl::canon(gl::sub(gl::mul(a0, a0), c.seven_z0c1_sq));
-  c.den[n + p] = gl::canon(gl::sub(gl::mul(a1, a1), c.seven_z1c1_sq));
+  for (int b = 0; b < c.n_batches; b++) {
+    const uint64_t a = gl::sub(x, c.z[b].c0);
+    c.den[(size_t)b * n + p] = gl::canon(gl::sub(gl::mul(a, a), c.seven_zc1_sq[b]));
+  }
 }
+template <int B>
 static __global__ void __launch_bounds__(128) combine_values(CombineParams c) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n = 1u << c.log_lde;
   if (p >= n) return;
-  gl::Ext acc = gl::ext(0, 0), acc1 = gl::ext(0, 0);
-  const int n0 = c.n_cols[0] + c.n_cols[1] + c.n_cols[2];
+  gl::Ext acc[B];
+#pragma unroll
+  for (int b = 0; b < B; b++) acc[b] = gl::ext(0, 0);
   if (c.n_chunks == 0) {
-    combine_columns(c, p, 0, n0, acc, acc1);
-    if (n0 <= c.n1) acc1 = acc;
+    combine_columns<B>(c, p, 0, c.n_cols, acc);
   } else {
     for (int j = 0; j < c.n_chunks; j++) {
-      const uint64_t* src = c.partial + ((size_t)j * n + p) * 4;
-      acc = gl::eadd(acc, gl::ext(src[0], src[1]));
-      acc1 = gl::eadd(acc1, gl::ext(src[2], src[3]));
+      const uint64_t* src = c.partial + ((size_t)j * n + p) * (2 * B);
+#pragma unroll
+      for (int b = 0; b < B; b++) acc[b] = gl::eadd(acc[b], gl::ext(src[2 * b], src[2 * b + 1]));
     }
   }
   const uint64_t x = c.coset.get(gl::bitrev32(p, c.log_lde));
-  // 1/(x - z) = conj(x - z) / norm
-  const uint64_t i0 = c.den[p], i1 = c.den[n + p];
-  const gl::Ext inv0 = gl::ext(gl::mul(gl::sub(x, c.z0.c0), i0), gl::mul(c.z0.c1, i0));   // (x - z0.c0, -(-z0.c1)) / norm
-  const gl::Ext inv1 = gl::ext(gl::mul(gl::sub(x, c.z1.c0), i1), gl::mul(c.z1.c1, i1));
-  const gl::Ext q0 = gl::emul(gl::esub(acc, c.y0), inv0);
-  const gl::Ext q1 = gl::emul(gl::esub(acc1, c.y1), inv1);
-  const gl::Ext f = gl::ecanon(gl::eadd(gl::emul(q0, c.shift0), q1));
+  gl::Ext f = gl::ext(0, 0);
+#pragma unroll
+  for (int b = 0; b < B; b++) {
+    if (b >= c.n_batches) continue;
+    // 1/(x - z) = conj(x - z) / norm
+    const uint64_t i = c.den[(size_t)b * n + p];
+    const gl::Ext inv = gl::ext(gl::mul(gl::sub(x, c.z[b].c0), i), gl::mul(c.z[b].c1, i));
+    gl::Ext q = gl::emul(gl::esub(acc[b], c.y[b]), inv);
+    if (b + 1 < c.n_batches) q = gl::emul(q, c.shift[b]);
+    f = gl::eadd(f, q);
+  }
+  f = gl::ecanon(f);
   c.out[2 * (size_t)p] = f.c0;
   c.out[2 * (size_t)p + 1] = f.c1;
 }
@@ -473,6 +594,11 @@ static __global__ void __launch_bounds__(128) pow_grind(const uint64_t* __restri
   poseidon::permute(s);
   const uint64_t resp = gl::canon(s[7]);
   if (bits == 0 || (resp >> (64 - bits)) == 0) atomicMin(result, (unsigned long long)cand);
+}
+
+static __global__ void canon_copy(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = gl::canon(src[i]);
 }
 
 // ---- gathers for the query phase --------------------------------------------------------------------

@@ -78,6 +78,32 @@ int etp_dev_download(etp_ctx *ctx, void *dst_host, const void *src_dev, size_t b
  * of the Poseidon kernels ("an IMAD.WIDE.U32 micro-benchmark peak measured in the same run"). */
 int etp_bench_pipe_rates(etp_ctx *ctx, double rates_out[4]);
 
+/* ---- Fiat-Shamir transcript: plonky2/src/iop/challenger.rs Challenger<GoldilocksField, PoseidonHash> --------------
+ * Plain data, owned by the caller: the "challenger state in / out" of every proving entry point below.  The fields are
+ * upstream's: sponge_state, input_buffer (pending observations, < 8), output_buffer (challenges popped from the END).
+ * Host-only functions (no GPU): duplex sponge in overwrite mode, rate 8. */
+typedef struct etp_challenger {
+  uint64_t sponge_state[12];
+  uint64_t input_buffer[8];
+  uint64_t output_buffer[8];
+  uint32_t input_len, output_len;
+} etp_challenger;
+void etp_challenger_init(etp_challenger *c);                                        /* Challenger::new            */
+void etp_challenger_observe(etp_challenger *c, const uint64_t *elements, size_t n); /* observe_elements / _cap    */
+uint64_t etp_challenger_get_challenge(etp_challenger *c);                           /* get_challenge              */
+void etp_challenger_get_n_challenges(etp_challenger *c, size_t n, uint64_t *out);   /* get_n_challenges           */
+void etp_challenger_compact(etp_challenger *c);                                     /* compact (state = sponge_state) */
+
+/* ---- FRI parameters: plonky2/src/fri/mod.rs FriConfig + FriParams (hiding = false) -------------------------------- */
+typedef struct etp_fri_params {
+  int rate_bits, cap_height, proof_of_work_bits, num_query_rounds, degree_bits, n_reductions;
+  int reduction_arity_bits[16]; /* every entry must be 4 (FriReductionStrategy::ConstantArityBits(4, 5), the strategy of both
+                                   StarkConfig::standard_fast_config and CircuitConfig::standard_recursion_config) */
+} etp_fri_params;
+/* FriConfig::fri_params(degree_bits, false) with ConstantArityBits(4, 5) */
+int etp_fri_params_make(int degree_bits, int rate_bits, int cap_height, int proof_of_work_bits, int num_query_rounds,
+                        etp_fri_params *out);
+
 /* ---- hashing primitives: plonky2/src/hash/poseidon.rs, hashing.rs ---------------------------- */
 /* PoseidonPermutation::permute on n independent 12-lane states (host pointers, n x 12) */
 int etp_poseidon_permute_host(etp_ctx *ctx, uint64_t *states, size_t n);
@@ -147,6 +173,10 @@ int etp_batch_prove(etp_batch *b, size_t leaf_index, uint64_t *siblings_out);
 const uint64_t *etp_batch_lde_dev(const etp_batch *b, size_t *col_stride);
 const uint64_t *etp_batch_coeffs_dev(const etp_batch *b, size_t *col_stride);
 
+/* polynomials[c].to_extension().eval(z) for every polynomial of the batch (StarkOpeningSet::new's eval_commitment):
+ * out has num_cols extension values (c0, c1 interleaved), canonical. */
+int etp_batch_eval_at_ext_point(etp_batch *b, const uint64_t z[2], uint64_t *out);
+
 /* ---- column-split commit of one oversized table across the GPUs of a box ------------------------
  * BASELINE.json north_star / SURVEY.md 8(e): PolynomialBatch::from_values of a table whose LDE does not
  * fit (or is too slow on) one GPU.  One process per GPU; rank g of `world` (a power of two <= 8 and
@@ -214,6 +244,31 @@ int etp_table_register(etp_ctx *ctx, const uint64_t *program, size_t n_words, co
 /* parse + NVRTC-compile a program without a device (CI / the Rust build): cubin size, or an error message */
 int etp_cprog_compile_check(const uint64_t *program, size_t n_words, size_t *cubin_bytes_out, char *err, size_t err_len);
 
+/* General registration.  `aux_spec` describes every auxiliary polynomial the prover must generate for this table
+ * (starky/src/lookup.rs Lookup / Column / Filter, starky/src/cross_table_lookup.rs CtlZData) as u64 words:
+ *   [0] magic "ETPAUXS1"  [1] n_lookups  [2] n_ctl_zs
+ *   per lookup : n_columns, n_columns x Column, n_columns x Filter, table Column, frequencies Column
+ *   per CTL Z  : challenge_index (< num_challenges), n_colsets, per colset: n_columns, Columns..., Filter
+ *   Column     : n_local, (trace column, coefficient)*, n_next_row, (trace column, coefficient)*, constant
+ *   Filter     : n_products, (Column, Column)*, n_constants, Column*          (Filter::default() = 0 products, [constant 1])
+ * The CTL Z list is this table's `CtlData.zs_columns` in upstream's order (per cross-table lookup, per challenge; a table
+ * that is looking k > 1 times in one CTL has k colsets in its entry, the looked table one).  Auxiliary polynomial order
+ * (starky prover.rs): lookup columns [per lookup, per challenge: helpers, Z] ++ CTL helper columns ++ CTL Z columns.
+ * The program must contain the table's constraints, its lookup checks and its CTL checks (eval_vanishing_poly order);
+ * challenge scalars: CH 0..1 = lookup challenges, CH 2+2k / 3+2k = CTL (beta_k, gamma_k). */
+int etp_table_register_ex(etp_ctx *ctx, const uint64_t *program, size_t n_words, const uint64_t *aux_spec, size_t n_spec_words,
+                          int *table_id_out);
+int etp_table_num_lookup_columns(const etp_ctx *ctx, int table, int num_challenges);
+int etp_table_num_ctl_helper_columns(const etp_ctx *ctx, int table);
+int etp_table_num_ctl_zs(const etp_ctx *ctx, int table);
+/* All auxiliary polynomials of a table on the trace domain, on the device: lookup_helper_columns for every lookup and
+ * challenge, then cross_table_lookup_data's helper columns and Z columns (partial_sums) for this table.
+ * lookup_challenges: num_challenges scalars; ctl_challenges: num_challenges (beta, gamma) pairs or NULL (table without CTL).
+ * aux_dev: etp_table_num_aux_columns columns of 2^log_n (column-major, stride 2^log_n).  A zero denominator
+ * (upstream: "Tried to invert zero" panic) gives ETP_ERR_PROOF. */
+int etp_aux_columns_dev(etp_ctx *ctx, int table, int log_n, const uint64_t *trace_dev, size_t col_stride,
+                        const uint64_t *lookup_challenges, int num_challenges, const uint64_t *ctl_challenges, uint64_t *aux_dev);
+
 /* starky::lookup::lookup_helper_columns for every lookup of the table and every challenge:
  * aux_dev gets etp_table_num_aux_columns columns of 2^log_n (column-major, stride 2^log_n). */
 int etp_lookup_helper_columns_dev(etp_ctx *ctx, int table, int log_n, const uint64_t *trace_dev, size_t col_stride,
@@ -221,7 +276,8 @@ int etp_lookup_helper_columns_dev(etp_ctx *ctx, int table, int log_n, const uint
 /* starky::prover::compute_quotient_polys: returns the quotient chunks
  * (quotient_degree_factor * n_alphas polynomials of 2^log_n coefficients, column-major) in out_dev. */
 int etp_compute_quotient_polys_dev(etp_ctx *ctx, int table, etp_batch *trace, etp_batch *aux /* may be NULL */,
-                                   const uint64_t *lookup_challenges, int n_lookup_challenges,
+                                   const uint64_t *lookup_challenges /* challenge scalars: lookup challenges, then CTL (beta, gamma) pairs */,
+                                   int n_lookup_challenges,
                                    const uint64_t *public_inputs, const uint64_t *alphas, int n_alphas,
                                    uint64_t *out_dev);
 
@@ -230,9 +286,9 @@ int etp_compute_quotient_polys_dev(etp_ctx *ctx, int table, etp_batch *trace, et
  * pos = index the candidate is written to. */
 int etp_pow_grind(etp_ctx *ctx, const uint64_t state[12], int pos, int bits, uint64_t *witness_out);
 
-/* starky::prover::prove under StarkConfig::standard_fast_config(): trace commit, auxiliary columns,
- * quotient, openings, FRI (commit phase, PoW, 84 query rounds).  proof_out: etp_stark_proof_words()
- * u64 in the flat wire format of DESIGN.md.  The trace (n_cols x 2^log_n column-major) is a host or a
+/* starky::prover::prove under StarkConfig::standard_fast_config(): trace commit, challenger observes the public inputs
+ * and the trace cap, then prove_with_commitment (auxiliary columns, quotient, openings, FRI: commit phase, PoW, 84 query
+ * rounds).  proof_out: etp_stark_proof_words() u64 in the flat wire format of DESIGN.md.  The trace (n_cols x 2^log_n column-major) is a host or a
  * device matrix. */
 size_t etp_stark_proof_words(const etp_ctx *ctx, int table, int log_n);
 int etp_stark_prove_host(etp_ctx *ctx, int table, int log_n, const uint64_t *trace, const uint64_t *public_inputs,
@@ -242,6 +298,55 @@ int etp_stark_prove_dev(etp_ctx *ctx, int table, int log_n, const uint64_t *trac
 /* per-phase device times (ms) of the last etp_stark_prove_* on this context, named after plonky2's
  * TimingTree scopes; returns the number of entries written (<= max). */
 int etp_last_prove_timings(const etp_ctx *ctx, const char **names, float *ms, int max);
+
+/* starky::prover::prove_with_commitment(stark, config, trace_poly_values, trace_commitment, ctl_data, ctl_challenges,
+ * challenger, public_inputs, timing) under standard_fast_config — the call evm_arithmetization's prove_single_table makes
+ * for each of the seven tables (/root/reference/ops/src/lib.rs:52 -> prove_with_traces).
+ *   trace_commitment : PolynomialBatch::from_values(trace, rate_bits 1, blinding false, cap_height 4), already observed
+ *                      by the caller's challenger (with every other table's cap);
+ *   trace_dev        : the trace values (device, column-major), needed for the auxiliary columns;
+ *   ctl_challenges   : num_challenges (beta, gamma) pairs from get_grand_product_challenge_set, or NULL for a table
+ *                      outside any CTL (stand-alone prove: the lookup challenges are then drawn from the challenger).
+ *                      The table's ctl_data (Z and helper columns) is computed here, on the device, from its registered
+ *                      CtlZData descriptors;
+ *   challenger       : transcript state, updated in place (state in -> state out).
+ * proof_out: etp_stark_proof_words() u64, layout "B200STK2" (DESIGN.md): StarkProofWithPublicInputs field by field. */
+int etp_prove_with_commitment(etp_ctx *ctx, int table, etp_batch *trace_commitment, const uint64_t *trace_dev, size_t col_stride,
+                              const uint64_t *ctl_challenges, etp_challenger *challenger, const uint64_t *public_inputs,
+                              uint64_t *proof_out);
+
+/* ---- PolynomialBatch::prove_openings / plonky2::fri::prover::fri_proof for a general FriInstanceInfo -------------------
+ * (plonky2/src/fri/oracle.rs, fri/prover.rs, fri/structure.rs).  This is what starky's prove_with_commitment and
+ * plonky2's circuit prover (plonk/prover.rs, the recursion layers of /root/reference/ops/src/lib.rs:72,95) both end in. */
+typedef struct etp_fri_poly { uint32_t oracle_index, polynomial_index; } etp_fri_poly;                 /* FriPolynomialInfo */
+typedef struct etp_fri_batch { uint64_t point[2]; const etp_fri_poly *polynomials; size_t n_polynomials; } etp_fri_batch; /* FriBatchInfo */
+/* words of a flat FriProof: commit_phase_merkle_caps (n_reductions x 2^cap x 4), query_round_proofs (num_query_rounds x
+ * { per oracle: leaf row (n_cols), MerkleProof siblings x 4 ; per reduction: FriQueryStep.evals (2^arity ext — the
+ * uncompressed FriProof carries all of them; only CompressedFriProof drops the queried one), siblings x 4 }),
+ * final_poly (ext coefficients), pow_witness */
+size_t etp_fri_proof_words(const size_t *oracle_num_cols, size_t n_oracles, const etp_fri_params *params);
+int etp_prove_openings(etp_ctx *ctx, const etp_fri_batch *batches, size_t n_batches, etp_batch *const *oracles, size_t n_oracles,
+                       etp_challenger *challenger, const etp_fri_params *params, uint64_t *fri_proof_out);
+
+/* ---- the FRI prover, step by step (fri_committed_trees is sequential through the challenger: beta_l depends on cap_l) --
+ * values_dev: 2^(degree_bits + rate_bits) extension values (c0, c1 interleaved) of the polynomial on the coset 7*H in
+ * BIT-REVERSED order (what reverse_index_bits_in_place gives upstream); the state takes a private copy. */
+typedef struct etp_fri_state etp_fri_state;
+int etp_fri_begin(etp_ctx *ctx, const uint64_t *values_dev, const etp_fri_params *params, etp_fri_state **out);
+/* MerkleTree::new(chunked values of the current layer, cap_height) -> its cap (2^cap_height x 4) */
+int etp_fri_commit_layer(etp_fri_state *s, uint64_t *cap_out);
+/* fold the current layer with beta (arity 16) into the next one */
+int etp_fri_fold(etp_fri_state *s, const uint64_t beta[2]);
+/* after the last fold: the final polynomial's 2^(degree_bits - total arity bits) extension coefficients */
+int etp_fri_final_poly(etp_fri_state *s, uint64_t *coeffs_out);
+/* fused fri_committed_trees: every layer with the challenger (observe cap, draw beta), then observes the final polynomial.
+ * caps_out: n_reductions caps; final_poly_out as above. */
+int etp_fri_commit_phase(etp_fri_state *s, etp_challenger *challenger, uint64_t *caps_out, uint64_t *final_poly_out);
+/* fri_prover_query_rounds for the given x indices (< 2^(degree_bits + rate_bits)): out gets n_indices query rounds in the
+ * layout of etp_fri_proof_words */
+int etp_fri_query_rounds(etp_fri_state *s, etp_batch *const *oracles, size_t n_oracles, const uint64_t *x_indices, size_t n_indices,
+                         uint64_t *out);
+void etp_fri_free(etp_fri_state *s);
 
 #ifdef __cplusplus
 }

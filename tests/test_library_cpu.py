@@ -124,3 +124,37 @@ def test_host_transcript_permutation_matches_the_known_answers_and_the_oracle():
     rng = random.Random(5)
     for st in [[2**64 - 1] * 12, [p] * 12, [2**32 - 1] * 12, [0xFFFFFFFF00000000] * 12] + [[rng.randrange(2**64) for _ in range(12)] for _ in range(300)]:
         assert perm(st) == [int(x) for x in oracle.poseidon_permute_naive(np.array(st, dtype=np.uint64))]
+
+
+def test_challenger_c_abi_matches_the_oracle_and_compacts():
+    """etp_challenger (plain data, host only): observe / get_challenge / compact == plonky2's Challenger as restated by the oracle."""
+    import numpy as np
+
+    import eth_tx_proof_b200 as etp
+    import oracle
+
+    g, o = etp.Challenger(), oracle.HostChallenger()
+    rng = np.random.default_rng(5)
+    for step in range(40):
+        k = int(rng.integers(0, 20))
+        vals = rng.integers(0, 2**63, size=k, dtype=np.uint64)
+        g.observe(vals)
+        o.observe(vals)
+        m = int(rng.integers(0, 11))
+        assert (g.get_n_challenges(m) == o.get_n(m)).all()
+        if step % 7 == 3:
+            assert (g.compact() == o.compact()).all()
+        assert (g.words() == o.words()).all()
+    c = g.clone()
+    assert c.get_challenge() == g.get_challenge()
+
+
+def test_fri_params_standard_configs():
+    import eth_tx_proof_b200 as etp
+
+    fp = etp.FriParams.make(22)  # StarkConfig::standard_fast_config
+    assert (fp.rate_bits, fp.cap_height, fp.proof_of_work_bits, fp.num_query_rounds, fp.n_reductions) == (1, 4, 16, 84, 4)
+    assert [fp.reduction_arity_bits[i] for i in range(4)] == [4, 4, 4, 4]
+    fr = etp.FriParams.make(12, 3, 4, 16, 28)  # CircuitConfig::standard_recursion_config
+    assert fr.n_reductions == 2
+    assert etp.FriParams.make(5).n_reductions == 0 and etp.FriParams.make(6).n_reductions == 0 and etp.FriParams.make(8).n_reductions == 1
