@@ -954,7 +954,10 @@ __global__ void __launch_bounds__(THREADS) k_iadd3(uint64_t* out, uint32_t b) { 
   for (int i = 0; i < CHAINS; i++) acc[i] = i + threadIdx.x;
   for (int it = 0; it < ITERS; it++) {
 #pragma unroll
-    for (int i = 0; i < CHAINS; i++) asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(b));
+    for (int i = 0; i < CHAINS; i += 2) {  // add / xor alternate so that ptxas cannot fuse two adds into one IADD3
+      asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(b));
+      asm volatile("xor.b32 %0, %0, %1;" : "+r"(acc[i + 1]) : "r"(b));
+    }
   }
   uint32_t s = 0;
   for (int i = 0; i < CHAINS; i++) s += acc[i];
@@ -975,7 +978,7 @@ __global__ void __launch_bounds__(THREADS) k_dfma(uint64_t* out, uint32_t b) {  
 }  // namespace pipes
 
 // rates_out[4]: sustained thread-instructions per second of the whole device for
-// [0] IMAD.WIDE.U32 with a zero addend, [1] IMAD.WIDE.U32 accumulating into a 64-bit addend, [2] IADD3, [3] DFMA.
+// [0] IMAD.WIDE.U32 with a zero addend, [1] IMAD.WIDE.U32 accumulating into a 64-bit addend, [2] integer ALU (IADD3 / LOP3), [3] DFMA.
 extern "C" int etp_bench_pipe_rates(etp_ctx* ctx, double rates_out[4]) {
   etp_bind(ctx);
   if (!ctx || !rates_out) return ETP_ERR_INVALID;

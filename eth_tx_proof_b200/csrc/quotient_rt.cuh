@@ -95,8 +95,21 @@ struct RowCtx {
   __device__ __forceinline__ uint64_t la(const QuotientParams& q, int c) const { return __ldg(q.aux + (size_t)c * q.aux_stride + p); }
   __device__ __forceinline__ uint64_t na(const QuotientParams& q, int c) const { return __ldg(q.aux + (size_t)c * q.aux_stride + p_next); }
 };
+// Block order.  Position p = (H << 7) | t (t = thread) holds point index i = (bitrev_7(t) << m) | bitrev_m(H), m = log_size - 7,
+// so the "next" row i + next_step of EVERY thread of a block lies in the block whose low index bits are I + next_step,
+// I = bitrev_m(H).  Blocks are therefore issued along the chains I, I + next_step, I + 2 next_step, ...: the rows block b
+// reads as `next` are the rows block b + 1 reads as `local`, the two run side by side and the second read is served by L2
+// instead of DRAM (ncu, round 1: 3.35 GB read for 1.68 GB of LDE rows with the natural block order).
+__device__ __forceinline__ uint32_t quotient_block_position(const QuotientParams& q) {
+  const uint32_t b = blockIdx.x;
+  const int m = q.log_size - 7;
+  const int qb = 31 - __clz(q.next_step);  // next_step is a power of two
+  if (blockDim.x != 128 || m < qb + 1) return b * blockDim.x + threadIdx.x;
+  const uint32_t I = ((b << qb) & ((1u << m) - 1)) | (b >> (m - qb));
+  return (gl::bitrev32(I, m) << 7) | threadIdx.x;
+}
 __device__ __forceinline__ bool quotient_begin(const QuotientParams& q, RowCtx& r) {
-  r.p = blockIdx.x * blockDim.x + threadIdx.x;
+  r.p = quotient_block_position(q);
   const uint32_t size = 1u << q.log_size;
   if (r.p >= size) return false;
   const uint32_t k = gl::bitrev32(r.p, q.log_lde);                 // LDE point index, multiple of step

@@ -450,19 +450,31 @@ template <int B>
 __device__ __forceinline__ void combine_columns(const CombineParams& c, uint32_t p, int u0, int u1, gl::Ext (&acc)[B]) {
   Acc192 s[B][2] = {};
   Acc192 snap[B][2] = {};
-  for (int u = u0; u < u1; u++) {
+  constexpr int G = 4;  // columns in flight per thread: the loads of a group are issued before its multiply-adds
+  for (int ug = u0; ug < u1; ug += G) {
+    const uint64_t* ptr[G];
+    uint64_t v[G];
 #pragma unroll
-    for (int b = 1; b < B; b++)
-      if (c.prefix_len[b] == u) { snap[b][0] = s[0][0]; snap[b][1] = s[0][1]; }
-    const uint64_t* ptr = reinterpret_cast<const uint64_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&c.cols[u].ptr)));
-    const uint64_t v = __ldg(ptr + p);
+    for (int j = 0; j < G; j++)
+      if (ug + j < u1) ptr[j] = reinterpret_cast<const uint64_t*>(__ldg(reinterpret_cast<const unsigned long long*>(&c.cols[ug + j].ptr)));
 #pragma unroll
-    for (int b = 0; b < B; b++) {
-      if (b >= c.n_batches || (b > 0 && c.prefix_len[b] > 0)) continue;
-      const uint32_t k = __ldg(&c.cols[u].idx[b]);
-      if (k == COMBINE_NONE) continue;
-      mac192(s[b][0], v, __ldg(c.alpha_pows + 2 * (size_t)k));
-      mac192(s[b][1], v, __ldg(c.alpha_pows + 2 * (size_t)k + 1));
+    for (int j = 0; j < G; j++)
+      if (ug + j < u1) v[j] = __ldg(ptr[j] + p);
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+      const int u = ug + j;
+      if (u >= u1) break;
+#pragma unroll
+      for (int b = 1; b < B; b++)
+        if (c.prefix_len[b] == u) { snap[b][0] = s[0][0]; snap[b][1] = s[0][1]; }
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        if (b >= c.n_batches || (b > 0 && c.prefix_len[b] > 0)) continue;
+        const uint32_t k = __ldg(&c.cols[u].idx[b]);
+        if (k == COMBINE_NONE) continue;
+        mac192(s[b][0], v[j], __ldg(c.alpha_pows + 2 * (size_t)k));
+        mac192(s[b][1], v[j], __ldg(c.alpha_pows + 2 * (size_t)k + 1));
+      }
     }
   }
 #pragma unroll
@@ -552,6 +564,9 @@ struct FoldParams {
   uint64_t w16_inv_pows[16];  // (w16^-1)^e
   uint64_t inv16;
 };
+// (Measured, profiles/r02_ncu_stark_kernels_2p22.csv: staging the leaves through padded shared memory for fully coalesced
+// loads does not help — layer 0 is bound by the integer ALU (66 %), not by its 134 MB of reads; the L1 absorbs the
+// per-thread 256-byte leaf reads.)
 static __global__ void __launch_bounds__(128) fri_fold16(FoldParams f) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_out = 1u << (f.log_n - 4);
