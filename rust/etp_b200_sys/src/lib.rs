@@ -1,124 +1,187 @@
-//! Raw bindings of `include/etp_b200.h` + the safe wrappers a patched `plonky2` / `starky` would call.
-//! SOURCE ONLY — not compiled here (no Rust toolchain in the build image). See INTEGRATION.md.
+//! `etp_b200_sys` — Rust side of libetp_b200: the generated raw bindings (`sys`, every function of `include/etp_b200.h`),
+//! safe wrappers shaped like the plonky2 / starky items they stand behind, and the constraint-program recorder.
+//! SOURCE ONLY — not compiled in this repository (no Rust toolchain in the build image); see INTEGRATION.md for how a
+//! plonky2 0.2.2 / starky 0.4.0 fork uses it (/root/reference/Cargo.toml `[patch.crates-io]`).
 #![allow(non_camel_case_types)]
-use std::ffi::CStr;
-use std::os::raw::{c_char, c_int, c_void};
-
-#[repr(C)] pub struct etp_ctx { _p: [u8; 0] }
-#[repr(C)] pub struct etp_batch { _p: [u8; 0] }
-#[repr(C)] pub struct etp_tree { _p: [u8; 0] }
-
-#[repr(C)] pub struct etp_shard { _p: [u8; 0] }
 pub mod recorder;
+pub mod sys;
+pub use sys::*;
 
-extern "C" {
-    pub fn etp_ctx_create(device: c_int, out: *mut *mut etp_ctx) -> c_int;
-    pub fn etp_ctx_destroy(ctx: *mut etp_ctx);
-    pub fn etp_ctx_trim(ctx: *mut etp_ctx) -> c_int;
-    pub fn etp_host_pin(ctx: *mut etp_ctx, ptr: *mut c_void, bytes: usize) -> c_int;
-    pub fn etp_host_unpin(ctx: *mut etp_ctx, ptr: *mut c_void) -> c_int;
-    pub fn etp_host_poseidon_permute(state: *mut u64);
-    pub fn etp_ctx_cached_bytes(ctx: *const etp_ctx) -> usize;
-    pub fn etp_last_error(ctx: *const etp_ctx) -> *const c_char;
-    pub fn etp_batch_from_values_host(ctx: *mut etp_ctx, cols: *const *const u64, n_cols: usize, log_n: c_int,
-        rate_bits: c_int, blinding: c_int, cap_height: c_int, out: *mut *mut etp_batch) -> c_int;
-    pub fn etp_batch_from_coeffs_host(ctx: *mut etp_ctx, cols: *const *const u64, n_cols: usize, log_n: c_int,
-        rate_bits: c_int, blinding: c_int, cap_height: c_int, out: *mut *mut etp_batch) -> c_int;
-    pub fn etp_batch_free(b: *mut etp_batch);
-    pub fn etp_batch_cap(b: *mut etp_batch, cap_out: *mut u64) -> c_int;
-    pub fn etp_batch_download_coeffs(b: *mut etp_batch, out: *mut u64) -> c_int;
-    pub fn etp_batch_download_leaves(b: *mut etp_batch, out: *mut u64) -> c_int;
-    pub fn etp_batch_download_digests(b: *mut etp_batch, out: *mut u64) -> c_int;
-    pub fn etp_batch_num_digests(b: *const etp_batch) -> usize;
-    pub fn etp_batch_leaves_at(b: *mut etp_batch, idx: *const u64, n_idx: usize, rows_out: *mut u64) -> c_int;
-    pub fn etp_batch_prove(b: *mut etp_batch, leaf_index: usize, siblings_out: *mut u64) -> c_int;
-    pub fn etp_merkle_new_host(ctx: *mut etp_ctx, leaves: *const u64, n_leaves: usize, leaf_len: usize,
-        cap_height: c_int, out: *mut *mut etp_tree) -> c_int;
-    pub fn etp_tree_cap(t: *mut etp_tree, cap_out: *mut u64) -> c_int;
-    pub fn etp_tree_digests(t: *mut etp_tree, digests_out: *mut u64) -> c_int;
-    pub fn etp_tree_num_digests(t: *const etp_tree) -> usize;
-    pub fn etp_tree_free(t: *mut etp_tree);
-    pub fn etp_compute_quotient_polys_dev(ctx: *mut etp_ctx, table: c_int, trace: *mut etp_batch, aux: *mut etp_batch,
-        lookup_challenges: *const u64, n_lookup_challenges: c_int, public_inputs: *const u64,
-        alphas: *const u64, n_alphas: c_int, out_dev: *mut u64) -> c_int;
-    pub fn etp_stark_proof_words(ctx: *const etp_ctx, table: c_int, log_n: c_int) -> usize;
-    // program-defined tables (csrc/cprog.h): what `recorder::record_table` produces
-    pub fn etp_table_register(ctx: *mut etp_ctx, program: *const u64, n_words: usize, lookups: *const i32,
-        n_lookup_words: usize, table_id_out: *mut c_int) -> c_int;
-    pub fn etp_cprog_compile_check(program: *const u64, n_words: usize, cubin_bytes_out: *mut usize, err: *mut c_char,
-        err_len: usize) -> c_int;
-    // column-split commit of one oversized table across the GPUs of a box (one worker process per GPU)
-    pub fn etp_shard_create(ctx: *mut etp_ctx, n_cols_total: usize, log_n: c_int, rate_bits: c_int, cap_height: c_int,
-        rank: c_int, world: c_int, out: *mut *mut etp_shard) -> c_int;
-    pub fn etp_shard_free(s: *mut etp_shard);
-    pub fn etp_shard_transform_values_host(s: *mut etp_shard, local_cols: *const *const u64) -> c_int;
-    pub fn etp_shard_lde_dev(s: *const etp_shard) -> *const u64;
-    pub fn etp_ipc_export(ctx: *mut etp_ctx, dev_ptr: *const c_void, handle_out: *mut u8) -> c_int;
-    pub fn etp_ipc_open(ctx: *mut etp_ctx, handle: *const u8, dev_ptr_out: *mut *mut c_void) -> c_int;
-    pub fn etp_ipc_close(ctx: *mut etp_ctx, dev_ptr: *mut c_void) -> c_int;
-    pub fn etp_shard_set_peer(s: *mut etp_shard, peer_rank: c_int, peer_lde: *const u64) -> c_int;
-    pub fn etp_shard_commit_rows(s: *mut etp_shard, cap_part_out: *mut u64) -> c_int;
-    pub fn etp_shard_prove(s: *mut etp_shard, leaf_index: usize, siblings_out: *mut u64) -> c_int;
-    pub fn etp_shard_leaves_at(s: *mut etp_shard, idx: *const u64, n_idx: usize, rows_out: *mut u64) -> c_int;
-    pub fn etp_stark_prove_host(ctx: *mut etp_ctx, table: c_int, log_n: c_int, trace: *const u64,
-        public_inputs: *const u64, proof_out: *mut u64) -> c_int;
-    pub fn etp_pow_grind(ctx: *mut etp_ctx, state: *const u64, pos: c_int, bits: c_int, witness_out: *mut u64) -> c_int;
-    pub fn etp_dev_alloc(ctx: *mut etp_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
-    pub fn etp_dev_free(ctx: *mut etp_ctx, ptr: *mut c_void) -> c_int;
-}
+use std::ffi::CStr;
+use std::os::raw::c_int;
+use std::ptr;
 
-/// One context per worker thread (one Paladin worker <-> one GPU: CUDA_VISIBLE_DEVICES=%i).
+/// One CUDA device + stream + scratch cache.  One per worker thread (`thread_local!`), like upstream's one tokio task per op
+/// (/root/reference/ops/src/lib.rs:29-61).
 pub struct Ctx(pub *mut etp_ctx);
 unsafe impl Send for Ctx {}
+
 impl Ctx {
+    /// `device`: index inside CUDA_VISIBLE_DEVICES (a Paladin worker pinned to one GPU passes 0).
     pub fn new(device: i32) -> Self {
-        let mut p = std::ptr::null_mut();
-        let rc = unsafe { etp_ctx_create(device, &mut p) };
-        assert_eq!(rc, 0, "etp_b200: no usable CUDA device {device} (there is no CPU fallback)");
+        let mut p = ptr::null_mut();
+        let rc = unsafe { etp_ctx_create(device as c_int, &mut p) };
+        assert!(rc == ETP_OK, "etp_ctx_create({device}) failed ({rc}): no usable CUDA device; there is no CPU fallback");
         Ctx(p)
     }
-    /// Upstream's functions are infallible by signature and panic on misuse; keep that contract.
+    /// Upstream's functions are infallible by signature and panic on misuse; so does the glue.
     pub fn check(&self, rc: c_int) {
-        if rc != 0 {
+        if rc != ETP_OK {
             let msg = unsafe { CStr::from_ptr(etp_last_error(self.0)) }.to_string_lossy().into_owned();
             panic!("etp_b200 error {rc}: {msg}");
         }
     }
 }
-impl Drop for Ctx { fn drop(&mut self) { unsafe { etp_ctx_destroy(self.0) } } }
+impl Drop for Ctx {
+    fn drop(&mut self) { unsafe { etp_ctx_destroy(self.0) } }
+}
 
-/// Device-resident `PolynomialBatch<GoldilocksField, PoseidonGoldilocksConfig, 2>`.
+/// Device-resident `PolynomialBatch<GoldilocksField, PoseidonGoldilocksConfig, 2>` (plonky2/src/fri/oracle.rs).
 pub struct DeviceBatch { pub raw: *mut etp_batch, pub n_cols: usize, pub degree_log: usize, pub rate_bits: usize, pub cap_height: usize }
-impl Drop for DeviceBatch { fn drop(&mut self) { unsafe { etp_batch_free(self.raw) } } }
+unsafe impl Send for DeviceBatch {}
 
 impl DeviceBatch {
-    /// `PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height, ..)`; `values[c]` is the
-    /// `Vec<u64>` behind `PolynomialValues<GoldilocksField>` (GoldilocksField is `repr(transparent)` over u64).
-    pub fn from_values(ctx: &Ctx, values: &[&[u64]], rate_bits: usize, blinding: bool, cap_height: usize) -> Self {
-        let n = values.first().map_or(1, |v| v.len());
-        assert!(values.iter().all(|v| v.len() == n), "Polynomial degrees inconsistent");
-        let ptrs: Vec<*const u64> = values.iter().map(|v| v.as_ptr()).collect();
-        let mut raw = std::ptr::null_mut();
-        ctx.check(unsafe { etp_batch_from_values_host(ctx.0, ptrs.as_ptr(), ptrs.len(), n.trailing_zeros() as c_int,
-            rate_bits as c_int, blinding as c_int, cap_height as c_int, &mut raw) });
-        DeviceBatch { raw, n_cols: values.len(), degree_log: n.trailing_zeros() as usize, rate_bits, cap_height }
+    /// `PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, ..)`; `cols[c]` = the u64 view of column c
+    /// (`GoldilocksField` is `repr(transparent)` over u64).
+    pub fn from_values(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, blinding: bool, cap_height: usize) -> Self {
+        Self::build(ctx, cols, rate_bits, blinding, cap_height, true)
     }
-    /// `merkle_tree.cap` as 2^cap_height digests of 4 u64.
-    pub fn cap(&self, ctx: &Ctx) -> Vec<[u64; 4]> {
+    /// `PolynomialBatch::from_coeffs`
+    pub fn from_coeffs(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, blinding: bool, cap_height: usize) -> Self {
+        Self::build(ctx, cols, rate_bits, blinding, cap_height, false)
+    }
+    fn build(ctx: &Ctx, cols: &[&[u64]], rate_bits: usize, blinding: bool, cap_height: usize, values: bool) -> Self {
+        let n = cols.first().map_or(1, |c| c.len());
+        assert!(n.is_power_of_two() && cols.iter().all(|c| c.len() == n), "all polynomials must have the same power-of-two length");
+        let ptrs: Vec<*const u64> = cols.iter().map(|c| c.as_ptr()).collect();
+        let mut raw = ptr::null_mut();
+        let log_n = n.trailing_zeros() as c_int;
+        let rc = unsafe {
+            if values {
+                etp_batch_from_values_host(ctx.0, ptrs.as_ptr(), cols.len(), log_n, rate_bits as c_int, blinding as c_int, cap_height as c_int, &mut raw)
+            } else {
+                etp_batch_from_coeffs_host(ctx.0, ptrs.as_ptr(), cols.len(), log_n, rate_bits as c_int, blinding as c_int, cap_height as c_int, &mut raw)
+            }
+        };
+        ctx.check(rc);
+        DeviceBatch { raw, n_cols: cols.len(), degree_log: log_n as usize, rate_bits, cap_height }
+    }
+    /// `merkle_tree.cap` as 2^cap_height x 4 words
+    pub fn cap(&self) -> Vec<[u64; 4]> {
         let mut out = vec![[0u64; 4]; 1 << self.cap_height];
-        ctx.check(unsafe { etp_batch_cap(self.raw, out.as_mut_ptr() as *mut u64) });
+        let rc = unsafe { etp_batch_cap(self.raw, out.as_mut_ptr() as *mut u64) };
+        assert!(rc == ETP_OK);
         out
     }
-    /// `merkle_tree.leaves[i]` for the query rounds (only queried rows ever cross PCIe).
-    pub fn leaves_at(&self, ctx: &Ctx, idx: &[u64]) -> Vec<Vec<u64>> {
-        let mut flat = vec![0u64; idx.len() * self.n_cols];
-        ctx.check(unsafe { etp_batch_leaves_at(self.raw, idx.as_ptr(), idx.len(), flat.as_mut_ptr()) });
-        flat.chunks(self.n_cols.max(1)).map(|r| r.to_vec()).collect()
+    /// `polynomials` (lazy public field): n_cols x 2^degree_log, column-major
+    pub fn polynomials(&self) -> Vec<u64> {
+        let mut out = vec![0u64; self.n_cols << self.degree_log];
+        let rc = unsafe { etp_batch_download_coeffs(self.raw, out.as_mut_ptr()) };
+        assert!(rc == ETP_OK);
+        out
     }
-    /// `merkle_tree.prove(leaf_index).siblings`
-    pub fn prove(&self, ctx: &Ctx, leaf_index: usize) -> Vec<[u64; 4]> {
+    /// `merkle_tree.leaves` (lazy public field): (2^degree_log << rate_bits) rows x n_cols
+    pub fn leaves(&self) -> Vec<u64> {
+        let mut out = vec![0u64; (self.n_cols << self.degree_log) << self.rate_bits];
+        let rc = unsafe { etp_batch_download_leaves(self.raw, out.as_mut_ptr()) };
+        assert!(rc == ETP_OK);
+        out
+    }
+    /// `merkle_tree.digests` in plonky2's layout, 4 words per digest
+    pub fn digests(&self) -> Vec<u64> {
+        let nd = unsafe { etp_batch_num_digests(self.raw) };
+        let mut out = vec![0u64; 4 * nd];
+        let rc = unsafe { etp_batch_download_digests(self.raw, out.as_mut_ptr()) };
+        assert!(rc == ETP_OK);
+        out
+    }
+    /// `merkle_tree.prove(leaf_index)`
+    pub fn prove(&self, leaf_index: usize) -> Vec<[u64; 4]> {
         let mut out = vec![[0u64; 4]; self.degree_log + self.rate_bits - self.cap_height];
-        ctx.check(unsafe { etp_batch_prove(self.raw, leaf_index, out.as_mut_ptr() as *mut u64) });
+        let rc = unsafe { etp_batch_prove(self.raw, leaf_index, out.as_mut_ptr() as *mut u64) };
+        assert!(rc == ETP_OK);
         out
     }
+    /// `StarkOpeningSet::new`'s eval_commitment: every polynomial at the extension point z = (c0, c1)
+    pub fn eval_at_ext_point(&self, z: [u64; 2]) -> Vec<[u64; 2]> {
+        let mut out = vec![[0u64; 2]; self.n_cols];
+        let rc = unsafe { etp_batch_eval_at_ext_point(self.raw, z.as_ptr(), out.as_mut_ptr() as *mut u64) };
+        assert!(rc == ETP_OK);
+        out
+    }
+}
+impl Drop for DeviceBatch {
+    fn drop(&mut self) { unsafe { etp_batch_free(self.raw) } }
+}
+
+/// The transcript as the C ABI sees it; convert from / to plonky2's `Challenger` field by field
+/// (`sponge_state`, `input_buffer`, `output_buffer` are public in the fork).
+impl etp_challenger {
+    pub fn new() -> Self {
+        let mut c = etp_challenger { sponge_state: [0; 12], input_buffer: [0; 8], output_buffer: [0; 8], input_len: 0, output_len: 0 };
+        unsafe { etp_challenger_init(&mut c) };
+        c
+    }
+    pub fn from_parts(sponge_state: [u64; 12], input_buffer: &[u64], output_buffer: &[u64]) -> Self {
+        assert!(input_buffer.len() < 8 && output_buffer.len() <= 8);
+        let mut c = Self::new();
+        c.sponge_state = sponge_state;
+        c.input_buffer[..input_buffer.len()].copy_from_slice(input_buffer);
+        c.output_buffer[..output_buffer.len()].copy_from_slice(output_buffer);
+        c.input_len = input_buffer.len() as u32;
+        c.output_len = output_buffer.len() as u32;
+        c
+    }
+    pub fn observe_elements(&mut self, e: &[u64]) { unsafe { etp_challenger_observe(self, e.as_ptr(), e.len()) } }
+    pub fn get_challenge(&mut self) -> u64 { unsafe { etp_challenger_get_challenge(self) } }
+    pub fn get_n_challenges(&mut self, n: usize) -> Vec<u64> {
+        let mut out = vec![0u64; n];
+        unsafe { etp_challenger_get_n_challenges(self, n, out.as_mut_ptr()) };
+        out
+    }
+    pub fn compact(&mut self) -> [u64; 12] {
+        unsafe { etp_challenger_compact(self) };
+        self.sponge_state
+    }
+}
+
+/// `starky::prover::prove_with_commitment` for a registered table: returns the flat "B200STK2" proof words that
+/// `StarkProof::from_flat` in the fork re-shapes into `StarkProofWithPublicInputs`; the challenger is advanced in place.
+pub fn prove_with_commitment(ctx: &Ctx, table: i32, trace_commitment: &DeviceBatch, trace_dev: *const u64, col_stride: usize,
+                             ctl_challenges: Option<&[u64; 4]>, challenger: &mut etp_challenger, public_inputs: &[u64]) -> Vec<u64> {
+    let words = unsafe { etp_stark_proof_words(ctx.0, table as c_int, trace_commitment.degree_log as c_int) };
+    assert!(words > 0, "unknown table {table}");
+    let mut proof = vec![0u64; words];
+    let mut pi = public_inputs.to_vec();
+    pi.push(0);
+    let rc = unsafe {
+        etp_prove_with_commitment(ctx.0, table as c_int, trace_commitment.raw, trace_dev, col_stride,
+                                  ctl_challenges.map_or(ptr::null(), |c| c.as_ptr()), challenger, pi.as_ptr(), proof.as_mut_ptr())
+    };
+    ctx.check(rc);
+    proof
+}
+
+/// `PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing)` -> flat FriProof words.
+pub fn prove_openings(ctx: &Ctx, batches: &[([u64; 2], Vec<etp_fri_poly>)], oracles: &[&DeviceBatch], challenger: &mut etp_challenger,
+                      params: &etp_fri_params) -> Vec<u64> {
+    let raw_batches: Vec<etp_fri_batch> =
+        batches.iter().map(|(point, polys)| etp_fri_batch { point: *point, polynomials: polys.as_ptr(), n_polynomials: polys.len() }).collect();
+    let handles: Vec<*mut etp_batch> = oracles.iter().map(|o| o.raw).collect();
+    let n_cols: Vec<usize> = oracles.iter().map(|o| o.n_cols).collect();
+    let words = unsafe { etp_fri_proof_words(n_cols.as_ptr(), n_cols.len(), params) };
+    let mut out = vec![0u64; words];
+    let rc = unsafe {
+        etp_prove_openings(ctx.0, raw_batches.as_ptr(), raw_batches.len(), handles.as_ptr(), handles.len(), challenger, params, out.as_mut_ptr())
+    };
+    ctx.check(rc);
+    out
+}
+
+/// Registers a table from a recorded program + auxiliary-column spec (`recorder::finish`, `recorder::AuxSpecBuilder`).
+pub fn register_table(ctx: &Ctx, program: &[u64], aux_spec: &[u64]) -> i32 {
+    let mut id: c_int = 0;
+    let rc = unsafe { etp_table_register_ex(ctx.0, program.as_ptr(), program.len(), aux_spec.as_ptr(), aux_spec.len(), &mut id) };
+    ctx.check(rc);
+    id as i32
 }
