@@ -393,48 +393,67 @@ def main():
                           "proofs_per_min: all jobs through the pool (wall clock, max over ranks)"}
         del trace
 
-    # ---- BASELINE configs[3] / [4] shape: a synthetic TRANSACTION = seven table proofs of the evm_arithmetization shapes
-    # (arithmetic, byte packing, cpu, keccak 2400 columns, keccak sponge, logic, memory; cprog.EVM_TABLE_SHAPES, degree bits
-    # at the low end of the reference's circuit ranges).  Shape only: no cross-table lookups, no recursion layers.  Tables are
-    # registered (NVRTC) once per context, outside the timed region, like the reference builds its circuits at start-up.
+    # ---- BASELINE configs[3] / [4] shape: a synthetic TRANSACTION = seven tables of the evm_arithmetization shapes (arithmetic,
+    # byte packing, cpu, keccak 2400 columns, keccak sponge, logic 523 bit-decomposed columns, memory) linked by cross-table
+    # lookups in upstream's topology and proven like evm_arithmetization::prover::prove_with_traces does: all trace caps into ONE
+    # challenger, CTL challenges, then prove_with_commitment per table on that challenger (eth_tx_proof_b200/prover.py).
+    # The constraint sets are shape stand-ins (the real ones are not available offline) and there are no recursion layers.
+    # Tables are registered (NVRTC) once per context, outside the timed region, like the reference builds its circuits at start-up.
     tx = None
     if not args.skip_stark and not args.skip_tx:
-        from eth_tx_proof_b200 import parallel, synthetic as syn
+        from eth_tx_proof_b200 import cprog, parallel, prover
 
-        tables = syn.tx_job_tables()
-        dev = [torch.from_numpy(t.view(np.int64)).cuda() for _, _, _, t in tables]
+        tables, ctls = cprog.evm_shaped_system()
+        dev = [torch.from_numpy(t.view(np.int64)).cuda() for _, _, t in tables]
+        traces_dev = [(d.data_ptr(), t.shape[1], t.shape[0], int(t.shape[1]).bit_length() - 1) for d, (_, _, t) in zip(dev, tables)]
         torch.cuda.synchronize()
         pool = parallel.ProverPool(local_rank, STARK_CONTEXTS_PER_GPU)
-        ids = [[(c.register_table(p, p.lookups) if p is not None else etp.TABLE_MEMORY) for _, p, _, _ in tables] for c in pool.contexts]
+        ids = [[c.register_table(p) for _, p, _ in tables] for c in pool.contexts]
 
-        def prove_table(c, k):
-            w = pool.contexts.index(c)
-            return c.stark_prove_dev(ids[w][k], tables[k][2], dev[k].data_ptr(), 1 << tables[k][2])
+        def prove_tx(c, _job):
+            return prover.prove_with_traces(c, ids[pool.contexts.index(c)], traces_dev)
 
         n_tx = 8 * world  # weak scaling: 8 transactions per GPU
         my_tx = parallel.shard_jobs(n_tx, rank, world)
-        flat = [k for _ in my_tx for k in range(len(tables))]
-        pool.map(prove_table, list(range(len(tables))) * STARK_CONTEXTS_PER_GPU)  # warm-up: every table on every context
+        warm = pool.map(prove_tx, list(range(STARK_CONTEXTS_PER_GPU)))  # warm-up: every table on every context
         c0 = pool.contexts[0]
-        per_table = {}
         t0 = time.perf_counter()
-        for k, (name, _, bits, tr) in enumerate(tables):
-            t1 = time.perf_counter()
-            pr = prove_table(c0, k)
-            per_table[f"{name} 2^{bits} x {tr.shape[0]}"] = {"ms": (time.perf_counter() - t1) * 1e3, "proof_bytes": int(pr.size * 8)}
+        one = prove_tx(c0, 0)
         tx_ms = (time.perf_counter() - t0) * 1e3
+        assert all((a == b).all() for a, b in zip(one.stark_proofs, warm[0].stark_proofs)), "transaction proofs are not reproducible"
+        per_table = {f"{name} 2^{int(t.shape[1]).bit_length() - 1} x {t.shape[0]} (+{p.n_aux} aux)": int(pr.size * 8)
+                     for (name, p, t), pr in zip(tables, one.stark_proofs)}
         barrier()
         t0 = time.perf_counter()
-        pool.map(prove_table, flat)
+        pool.map(prove_tx, list(my_tx))
         dt = max_over_ranks(time.perf_counter() - t0)
         pool.close()
         del dev
-        tx = {"workload": "synthetic transaction: 7 table STARK proofs of the evm_arithmetization shapes (SURVEY.md App. B), "
-                          f"shape-only constraint programs, no CTLs, no recursion; {n_tx} transactions (8 per GPU) sharded over {world} GPU(s), "
+        tx = {"workload": "synthetic transaction: 7 table STARK proofs of the evm_arithmetization shapes (SURVEY.md App. B) linked by 7 "
+                          "cross-table lookups (upstream topology), one shared transcript + CTL challenges (prove_with_traces shape); "
+                          f"shape-only constraint programs, no recursion; {n_tx} transactions (8 per GPU) sharded over {world} GPU(s), "
                           f"{STARK_CONTEXTS_PER_GPU} prover contexts per GPU",
-              "tx_ms": tx_ms, "tx_per_min": n_tx * 60.0 / dt, "transactions": n_tx, "tables": per_table,
-              "timed": "tx_ms: the seven proofs in sequence on one context, traces resident in HBM -> proof bytes on the host; "
-                       "tx_per_min: all table proofs of all transactions through the pool (wall clock, max over ranks)"}
+              "tx_ms": tx_ms, "tx_per_min": n_tx * 60.0 / dt, "transactions": n_tx, "proof_bytes_per_table": per_table,
+              "ctl": {"cross_table_lookups": len(ctls), "ctl_z_columns_per_table": [len(p.ctl_zs) for _, p, _ in tables]},
+              "timed": "tx_ms: the seven table proofs (trace commits, CTL data, quotients, openings, FRI) in sequence on one context, traces "
+                       "resident in HBM -> proof bytes on the host; tx_per_min: all transactions through the pool (wall clock, max over ranks)"}
+
+    # ---- SURVEY.md 8(f3), first slice: the device skeleton of one recursion-layer proof (plonky2's circuit prover under
+    # standard_recursion_config: wires / Z / quotient commits at rate_bits 3, openings, four-oracle FRI with 28 queries) on
+    # stand-in polynomials of the shrink-circuit shapes; gate evaluation and witness generation are NOT included
+    recursion = None
+    if not args.skip_stark and world == 1:
+        from eth_tx_proof_b200 import recursion as rec
+
+        recursion = {"workload": "plonky2 circuit-prover skeleton, standard_recursion_config, 135 wires + 20 Z/partial products + 16 quotient "
+                                 "chunks + 84 constants/sigmas (pre-committed): commits + openings + FRI on stand-in polynomials; NOT a "
+                                 "recursion proof (no witness generation, no gate-constraint quotient)", "degree_bits": {}}
+        for db in (12, 13):
+            polys = rec.stand_in_polys(db)
+            cs = etp.PolynomialBatch.from_values(ctx, polys["constants_sigmas"], rec.RATE_BITS, False, rec.CAP_HEIGHT)
+            rec.prove_skeleton(ctx, db, polys, cs)  # warm-up
+            runs = [rec.prove_skeleton(ctx, db, polys, cs)["ms"] for _ in range(5)]
+            recursion["degree_bits"][str(db)] = {k: min(r[k] for r in runs) for k in runs[0]}
 
     # ---- one table column-split across all ranks: strong scaling of a single commit.
     # Rank g transforms columns [g*C/G, (g+1)*C/G) and hashes leaf rows [g*L/G, (g+1)*L/G), reading the peers'
@@ -532,7 +551,7 @@ def main():
         "data": "synthetic",
         "config": workload_config(log_n, cols),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "column_split": split,
+        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "recursion_skeleton": recursion, "column_split": split,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())

@@ -443,10 +443,18 @@ def memory_program() -> Program:
     """The memory-shaped table (built in as ETP_TABLE_MEMORY) as a constraint program, in
     the same constraint order: proofs of the registered table must equal the built-in table's word for word
     (only the table id in the header differs)."""
+    b = memory_builder()
+    b.emit_lookup_constraints()
+    return b.build()
+
+
+def memory_builder(extra_cols: int = 0) -> ProgramBuilder:
+    """The memory-shaped table's own constraints + its range-check Lookup on a builder with `extra_cols` more trace columns
+    (CTL ports); the caller emits the lookup / CTL checks."""
     from .synthetic import (M_CFC, M_COUNTER, M_CTX, M_FILTER, M_FREQ, M_INIT_AUX, M_IS_READ, M_RANGE_CHECK, M_SEG, M_SFC,
                             M_TIMESTAMP, M_VALUE0, M_VFC, M_VIRT, MEMORY_COLUMNS)
 
-    b = ProgramBuilder(MEMORY_COLUMNS, 0, 3)
+    b = ProgramBuilder(MEMORY_COLUMNS + extra_cols, 0, 3)
     lv, nv, one = b.lv, b.nv, b.const(1)
     f = lv(M_FILTER)
     b.constraint(f * (f - one))
@@ -474,8 +482,7 @@ def memory_program() -> Program:
     b.first_row(lv(M_COUNTER))
     b.transition(nv(M_COUNTER) - lv(M_COUNTER) - one)
     b.add_lookup([M_RANGE_CHECK], M_COUNTER, M_FREQ)
-    b.emit_lookup_constraints()
-    return b.build()
+    return b
 
 
 def fibonacci_program() -> Program:
@@ -499,8 +506,12 @@ def logic_layout(limbs: int = 8):
 
 
 def logic_program(limbs: int = 8) -> Program:
+    return logic_builder(limbs).build()
+
+
+def logic_builder(limbs: int = 8, extra_cols: int = 0) -> ProgramBuilder:
     L = logic_layout(limbs)
-    b = ProgramBuilder(L["cols"], 0, 3)
+    b = ProgramBuilder(L["cols"] + extra_cols, 0, 3)
     lv, one = b.lv, b.const(1)
     is_and, is_or, is_xor = lv(L["IS_AND"]), lv(L["IS_OR"]), lv(L["IS_XOR"])
     for fl in (is_and, is_or, is_xor):
@@ -523,7 +534,7 @@ def logic_program(limbs: int = 8) -> Program:
             y_lin = ty if y_lin is None else y_lin + ty
             xy = txy if xy is None else xy + txy
         b.constraint(lv(L["RES"] + limb) - (sum_coeff * (x_lin + y_lin) + and_coeff * xy))
-    return b.build()
+    return b
 
 
 def logic_trace(log_n: int, limbs: int = 8, seed: int = 11) -> np.ndarray:
@@ -611,8 +622,15 @@ def shape_layout(n_cols: int, n_lookup: int = 0):
 
 def shape_program(n_cols: int, n_lookup: int = 0, emit_lookups: bool = True) -> Program:
     """emit_lookups=False leaves the logUp constraints out (for Program.check_trace, which has no auxiliary columns)."""
+    b = shape_builder(n_cols, n_lookup, with_lookup=emit_lookups)
+    if n_lookup and emit_lookups:
+        b.emit_lookup_constraints()
+    return b.build()
+
+
+def shape_builder(n_cols: int, n_lookup: int = 0, extra_cols: int = 0, with_lookup: bool = True) -> ProgramBuilder:
     L = shape_layout(n_cols, n_lookup)
-    b = ProgramBuilder(n_cols, 0, 3)
+    b = ProgramBuilder(n_cols + extra_cols, 0, 3)
     lv, one = b.lv, b.const(1)
     b.first_row(lv(0))
     b.transition(b.nv(0) - lv(0) - 1)
@@ -622,10 +640,9 @@ def shape_program(n_cols: int, n_lookup: int = 0, emit_lookups: bool = True) -> 
     for f in range(L["n_flags"]):
         fl = lv(L["FLAG"] + f)
         b.constraint(fl * (fl - one))
-    if n_lookup and emit_lookups:
+    if n_lookup and with_lookup:
         b.add_lookup(list(range(L["LIMB"], L["LIMB"] + n_lookup)), L["COUNTER"], L["FREQ"])
-        b.emit_lookup_constraints()
-    return b.build()
+    return b
 
 
 def shape_trace(log_n: int, n_cols: int, n_lookup: int = 0, seed: int = 23) -> np.ndarray:
@@ -740,3 +757,103 @@ def ctl_demo_tables(log_ops: int = 6, log_rom: int = 5, log_extra: int = 5, seed
     tables = [("ops", b0.build(), t0), ("rom", b1.build(), t1), ("extra", b2.build(), t2)]
     ctls = [([0, 0, 2], 1)]
     return tables, ctls
+
+
+# ---- a synthetic TRANSACTION: seven tables of the evm_arithmetization shapes linked by cross-table lookups ------------------
+# Table order and CTL topology follow evm_arithmetization 0.1.3 (src/all_stark.rs: Table::all(), all_cross_table_lookups;
+# /root/reference/Cargo.lock:1675, reached from /root/reference/ops/src/lib.rs:52): cpu looks into arithmetic, byte packing,
+# keccak sponge, logic and (three memory channels here) memory; keccak sponge looks into keccak (inputs and outputs), logic
+# and memory; byte packing looks into memory.  The tables themselves are the shape stand-ins above (the real constraint
+# sets are not available offline) with CTL "ports" appended: a looking port is (filter, key, value) columns with
+# value = A_c * key + B_c, a looked port opens the tuple (row counter, A_c * counter + B_c) — the value as a
+# linear-combination Column — filtered by a multiplicity column.  Proven through prover.prove_with_traces, i.e. with
+# upstream's transcript threading and CTL challenges.
+EVM_TABLE_ORDER = ("arithmetic", "byte_packing", "cpu", "keccak", "keccak_sponge", "logic", "memory")
+EVM_CTLS = [  # (looking tables, looked table), indices into EVM_TABLE_ORDER
+    ([2], 0), ([2], 1), ([2], 4), ([4], 3), ([4], 3), ([2, 4], 5), ([2, 2, 2, 4, 1], 6),
+]
+
+
+def evm_shaped_system(scale_bits: int = 0, seed: int = 1, degree_bits: dict = None):
+    """-> (tables, ctls): tables = [(name, Program, trace)] in EVM_TABLE_ORDER, ctls = EVM_CTLS."""
+    from .synthetic import _rand, memory_trace, MEMORY_COLUMNS
+    from .synthetic import M_COUNTER as MEM_COUNTER
+
+    bits = {k: max(5, v + scale_bits) for k, v in (degree_bits or TX_TABLE_DEGREE_BITS).items()}
+    n_rows = {k: 1 << v for k, v in bits.items()}
+    names = EVM_TABLE_ORDER
+    # ports per table, in CtlData order: for each CTL (list order): looking entries grouped per table, then the looked one
+    looking = {t: [] for t in range(7)}   # table -> [(ctl index, [port ordinals within that CTL for this table])]
+    looked = {t: [] for t in range(7)}    # table -> [ctl index]
+    for c, (lk, ld) in enumerate(EVM_CTLS):
+        for t in dict.fromkeys(lk):
+            looking[t].append((c, lk.count(t)))
+        looked[ld].append(c)
+    n_extra = {t: sum(3 * k for _, k in looking[t]) + len(looked[t]) for t in range(7)}
+    A = lambda c: 1000003 + 7919 * c
+    B = lambda c: 17 + c
+    logic_limbs = 8
+    base_cols, builders, traces, counter_col = {}, {}, {}, {}
+    for t, name in enumerate(names):
+        if name == "memory":
+            base_cols[t] = MEMORY_COLUMNS
+            builders[t] = memory_builder(n_extra[t])
+            base = memory_trace(bits[name], seed=31 + seed)
+            counter_col[t] = MEM_COUNTER
+        elif name == "logic":
+            L = logic_layout(logic_limbs)
+            base_cols[t] = L["cols"] + 1  # + a row counter for the looked port's key
+            builders[t] = logic_builder(logic_limbs, 1 + n_extra[t])
+            base = np.concatenate([logic_trace(bits[name], logic_limbs, seed=37 + seed), np.arange(n_rows[name], dtype=np.uint64)[None, :]])
+            counter_col[t] = L["cols"]
+            bb = builders[t]
+            bb.first_row(bb.lv(counter_col[t]))
+            bb.transition(bb.nv(counter_col[t]) - bb.lv(counter_col[t]) - 1)
+        else:
+            cols, lk = EVM_TABLE_SHAPES[name]
+            base_cols[t] = cols
+            builders[t] = shape_builder(cols, lk, n_extra[t])
+            base = shape_trace(bits[name], cols, lk, seed=41 + seed + t)
+            counter_col[t] = 0
+        traces[t] = np.concatenate([base, np.zeros((n_extra[t], n_rows[name]), dtype=np.uint64)])
+    # fill the looking ports, count multiplicities
+    mult = {c: np.zeros(n_rows[names[ld]], dtype=np.int64) for c, (_, ld) in enumerate(EVM_CTLS)}
+    port_cols = {t: {} for t in range(7)}  # table -> {(ctl, j): (F, K, V)}; looked: {("m", ctl): MULT}
+    for t, name in enumerate(names):
+        col = base_cols[t]
+        n = n_rows[name]
+        for c, k in looking[t]:
+            n_looked = n_rows[names[EVM_CTLS[c][1]]]
+            for j in range(k):
+                f = (_rand(seed, 100 * c + 10 * j + 1, n) % np.uint64(3) != 0).astype(np.int64)
+                key = (_rand(seed, 100 * c + 10 * j + 2, n) % np.uint64(n_looked)).astype(np.int64)
+                traces[t][col], traces[t][col + 1] = f, key
+                traces[t][col + 2] = np.array((key.astype(object) * A(c) + B(c)) % P, dtype=np.uint64)
+                np.add.at(mult[c], key[f == 1], 1)
+                port_cols[t][(c, j)] = (col, col + 1, col + 2)
+                col += 3
+        for c in looked[t]:
+            port_cols[t][("m", c)] = col
+            col += 1
+    for t in range(7):
+        for c in looked[t]:
+            traces[t][port_cols[t][("m", c)]] = mult[c].astype(np.uint64)
+    # CtlZData per table in cross_table_lookup_data's order: per CTL, per challenge: looking tables (grouped), then looked
+    for c, (lk, ld) in enumerate(EVM_CTLS):
+        for k in range(NUM_CHALLENGES):
+            for t in dict.fromkeys(lk):
+                sets = []
+                for j in range(lk.count(t)):
+                    F, K, V = port_cols[t][(c, j)]
+                    builders[t].constraint(builders[t].lv(F) * (builders[t].lv(F) - 1)) if k == 0 else None
+                    sets.append(([K, V], Filter(constants=[Column.single(F)])))
+                builders[t].add_ctl_z(k, sets)
+            cc = counter_col[ld]
+            builders[ld].add_ctl_z(k, [([cc, Column([(cc, A(c))], constant=B(c))], Filter(constants=[Column.single(port_cols[ld][("m", c)])]))])
+    tables = []
+    for t, name in enumerate(names):
+        b = builders[t]
+        b.emit_lookup_constraints()
+        b.emit_ctl_constraints()
+        tables.append((name, b.build(), traces[t]))
+    return tables, [(list(lk), ld) for lk, ld in EVM_CTLS]

@@ -116,3 +116,15 @@ def test_tampered_ctl_opening_is_rejected():
     bad[0][off] = np.uint64((int(bad[0][off]) + 1) % P)
     with pytest.raises(V.VerifyError):
         verify_all(tables, ctls, bad, caps, max_queries=2)
+
+
+def test_evm_shaped_transaction_proves_and_verifies():
+    """Seven tables of the evm_arithmetization shapes linked by the upstream CTL topology (cprog.evm_shaped_system): cpu ->
+    arithmetic / byte packing / keccak sponge / logic / memory x3, keccak sponge -> keccak x2 / logic / memory, byte packing ->
+    memory.  One shared transcript, CTL challenges, per-table prove_with_commitment, then verify_cross_table_lookups."""
+    bits = {"arithmetic": 6, "byte_packing": 5, "cpu": 6, "keccak": 5, "keccak_sponge": 5, "logic": 5, "memory": 7}
+    tables, ctls = cprog.evm_shaped_system(degree_bits=bits)
+    assert [n for n, _, _ in tables] == list(cprog.EVM_TABLE_ORDER)
+    proofs, caps = prove_all(tables)
+    zs = verify_all(tables, ctls, proofs, caps, max_queries=1)
+    assert [len(z) for z in zs] == [2, 4, 10, 4, 10, 2, 2]

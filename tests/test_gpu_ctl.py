@@ -248,3 +248,58 @@ def test_stepwise_fri_equals_fused_and_oracle(ctx):
     assert (coeffs[: fin.shape[0]] == fin).all() and not coeffs[fin.shape[0]:].any()
     with pytest.raises(etp.EtpError):
         s1.fold([1, 2])  # nothing left to fold
+
+
+@pytest.mark.parametrize("degree_bits", [6, 9, 12])
+def test_recursion_proof_skeleton_matches_oracle(ctx, degree_bits):
+    """plonky2's circuit-prover skeleton under standard_recursion_config (eth_tx_proof_b200/recursion.py): the four caps, the
+    openings, the FriProof and the final transcript state equal the oracle's on the same stand-in polynomials."""
+    import oracle
+    from eth_tx_proof_b200 import recursion as rec
+
+    polys = rec.stand_in_polys(degree_bits, seed=degree_bits)
+    got = rec.prove_skeleton(ctx, degree_bits, polys)
+    ob = [oracle.Batch.from_values(polys["constants_sigmas"], 3, 4), oracle.Batch.from_values(polys["wires"], 3, 4),
+          oracle.Batch.from_values(polys["zs_partial_products"], 3, 4), oracle.Batch.from_coeffs(polys["quotient"], 3, 4)]
+    och = oracle.HostChallenger()
+    och.observe(ob[0].cap)
+    och.observe(ob[1].cap)
+    assert (och.get_n(2) == got["betas"]).all() and (och.get_n(2) == got["gammas"]).all()
+    och.observe(ob[2].cap)
+    assert (och.get_n(2) == got["alphas"]).all()
+    och.observe(ob[3].cap)
+    zeta = och.get_n(2)
+    assert (zeta == got["zeta"]).all()
+    for o, cap, op in zip(ob, got["caps"], got["openings"]):
+        assert (o.cap == cap).all()
+        want = oracle.batch_eval_at_ext_point(o, zeta)
+        assert (want == op).all()
+        och.observe(want)
+    g = rec.root_of_unity(degree_bits)
+    zn = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
+    och.observe(oracle.batch_eval_at_ext_point(ob[2], zn)[:2])
+    want = oracle.prove_openings(rec.fri_instance(zeta, degree_bits), ob, och, oracle.fri_params(degree_bits, 3, 4, 16, 28))
+    assert (got["fri_proof"] == want).all()
+    assert (got["challenger"].words() == och.words()).all()
+
+
+def test_evm_shaped_transaction_matches_oracle(ctx):
+    """The seven-table transaction with upstream's CTL topology (2400-column keccak shape, bit-decomposed logic, memory with its
+    range-check lookup): every proof equals the oracle's and the CTL sums close."""
+    import torch
+
+    import oracle
+    from eth_tx_proof_b200 import cprog, prover
+    from test_ctl_oracle import prove_all, verify_all
+
+    bits = {"arithmetic": 7, "byte_packing": 5, "cpu": 6, "keccak": 6, "keccak_sponge": 5, "logic": 6, "memory": 8}
+    tables, ctls = cprog.evm_shaped_system(degree_bits=bits, seed=5)
+    tids = [ctx.register_table(p) for _, p, _ in tables]
+    devs = [dev(t) for _, _, t in tables]
+    torch.cuda.synchronize()
+    traces_dev = [(d.data_ptr(), t.shape[1], t.shape[0], int(t.shape[1]).bit_length() - 1) for d, (_, _, t) in zip(devs, tables)]
+    got = prover.prove_with_traces(ctx, tids, traces_dev)
+    want, caps = prove_all(tables)
+    for k in range(7):
+        assert (np.delete(got.stark_proofs[k], 1) == np.delete(want[k], 1)).all(), tables[k][0]
+    verify_all(tables, ctls, got.stark_proofs, got.trace_caps, max_queries=1)
