@@ -341,6 +341,7 @@ def main():
         dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         assert (cap == cap_ref).all()
         e2e = {"value": world * nbytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": 8 * cols * n,
+               "h2d_gbs_aggregate": world * 8 * cols * n / dt / 1e9,  # all ranks pull from the same host: this is what caps e2e at large N
                "d2h_bytes_per_step": 32 << CAP_HEIGHT, "call": "etp_batch_from_values_host (pinned host columns) + etp_batch_cap"}
         del host, harr
     else:
