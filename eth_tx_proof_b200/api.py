@@ -216,6 +216,7 @@ def load_library():
         "etp_fri_commit_phase": (i32, [vp, C.POINTER(Challenger), _u64p, _u64p]),
         "etp_fri_query_rounds": (i32, [vp, C.POINTER(vp), sz, _u64p, sz, _u64p]),
         "etp_fri_free": (None, [vp]),
+        "etp_plonk_partial_products_and_zs_dev": (i32, [vp, vp, sz, vp, sz, _u64p, i32, i32, i32, _u64p, _u64p, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here == header/library mismatch
@@ -396,6 +397,15 @@ class Context:
         hs = (C.c_void_p * len(oracles))(*[o.h for o in oracles])
         self.check(self.L.etp_prove_openings(self.h, arr, len(batches), hs, len(oracles), C.byref(challenger), C.byref(params), _p(out)))
         return out
+
+    def plonk_partial_products_and_zs_dev(self, wires_ptr, wires_stride, sigmas_ptr, sigmas_stride, k_is, degree_bits,
+                                          quotient_degree_factor, betas, gammas, out_ptr):
+        """plonky2::plonk::prover::all_wires_permutation_partial_products on the device (routed wires + sigma values in,
+        [Z per challenge] ++ [partial products per challenge] out, column-major with stride 2^degree_bits)."""
+        k, b, g = _u64(k_is), _u64(betas), _u64(gammas)
+        self.check(self.L.etp_plonk_partial_products_and_zs_dev(self.h, C.c_void_p(wires_ptr), wires_stride, C.c_void_p(sigmas_ptr),
+                                                                sigmas_stride, _p(k), k.size, degree_bits, quotient_degree_factor,
+                                                                _p(b), _p(g), b.size, C.c_void_p(out_ptr)))
 
     def table_num_aux_columns(self, table, num_challenges=2) -> int:
         return int(self.L.etp_table_num_aux_columns(self.h, table, num_challenges))

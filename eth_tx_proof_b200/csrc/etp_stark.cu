@@ -15,6 +15,7 @@
 #include "cprog.h"
 #include "ctx.cuh"
 #include "host_field.h"
+#include "plonk_kernels.cuh"
 #include "stark_kernels.cuh"
 
 namespace {
@@ -1293,6 +1294,58 @@ extern "C" int etp_batch_eval_at_ext_point(etp_batch* b, const uint64_t z[2], ui
   ETP_TRY(eval_batch(ctx, b, t0, t0, e0, e1));
   for (size_t c = 0; c < b->n_cols; c++) { out[2 * c] = e0[c].c0; out[2 * c + 1] = e0[c].c1; }
   return ETP_OK;
+}
+
+// plonky2::plonk::prover::all_wires_permutation_partial_products, laid out as the prover commits it: out = [Z per challenge]
+// ++ [partial products of challenge 0] ++ [partial products of challenge 1] ...
+extern "C" int etp_plonk_partial_products_and_zs_dev(etp_ctx* ctx, const uint64_t* wires_dev, size_t wires_stride, const uint64_t* sigmas_dev,
+                                                     size_t sigmas_stride, const uint64_t* k_is, int num_routed_wires, int degree_bits,
+                                                     int quotient_degree_factor, const uint64_t* betas, const uint64_t* gammas, int num_challenges,
+                                                     uint64_t* out_dev) {
+  etp_bind(ctx);
+  if (!ctx || !wires_dev || !sigmas_dev || !k_is || !betas || !gammas || !out_dev) return ETP_ERR_INVALID;
+  if (num_routed_wires < 1 || num_routed_wires > 4096 || degree_bits < 0 || degree_bits > 28 || quotient_degree_factor < 1 || num_challenges < 1 ||
+      num_challenges > 8 || wires_stride < ((size_t)1 << degree_bits) || sigmas_stride < ((size_t)1 << degree_bits))
+    return etp_fail(ctx, ETP_ERR_INVALID, "partial_products_and_zs: bad arguments");
+  const size_t n = (size_t)1 << degree_bits;
+  const int n_chunks = (num_routed_wires + quotient_degree_factor - 1) / quotient_degree_factor, n_pp = n_chunks - 1;
+  DevBuf<uint64_t> den(ctx), chunk(ctx), rowprod(ctx), totals(ctx), d_k(ctx);
+  ETP_TRY(den.alloc((size_t)num_routed_wires * n));
+  ETP_TRY(chunk.alloc((size_t)n_chunks * n));
+  ETP_TRY(rowprod.alloc(n));
+  const size_t nb = (n + plonk::PSCAN_BLOCK - 1) / plonk::PSCAN_BLOCK;
+  ETP_TRY(totals.alloc(nb));
+  ETP_TRY(d_k.alloc(num_routed_wires));
+  std::vector<uint64_t> kc(k_is, k_is + num_routed_wires);
+  for (auto& k : kc) k = gl::canon(k);
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_k.p, kc.data(), kc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ntt::PowTable subgroup;
+  ETP_TRY(get_pow_table(ctx, gl::root_of_unity(degree_bits), degree_bits, 1, &subgroup));
+  ETP_TRY(reset_zero_flag(ctx));
+  for (int c = 0; c < num_challenges; c++) {
+    const uint64_t beta = gl::canon(betas[c]), gamma = gl::canon(gammas[c]);
+    plonk::permutation_denominators<<<blocks_for((size_t)num_routed_wires * n, 256), 256, 0, ctx->stream>>>(
+        wires_dev, wires_stride, sigmas_dev, sigmas_stride, num_routed_wires, (uint32_t)n, beta, gamma, den.p);
+    ETP_LAUNCH_CHECK(ctx);
+    ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, (size_t)num_routed_wires * n));
+    plonk::permutation_chunk_products<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(wires_dev, wires_stride, den.p, d_k.p, num_routed_wires,
+                                                                                 quotient_degree_factor, (uint32_t)n, subgroup, beta, gamma,
+                                                                                 chunk.p, rowprod.p);
+    ETP_LAUNCH_CHECK(ctx);
+    uint64_t* z = out_dev + (size_t)c * n;
+    plonk::prod_block_totals<<<(unsigned)nb, plonk::PSCAN_THREADS, 0, ctx->stream>>>(rowprod.p, n, totals.p);
+    ETP_LAUNCH_CHECK(ctx);
+    plonk::prod_totals_serial<<<1, 1, 0, ctx->stream>>>(totals.p, nb);
+    ETP_LAUNCH_CHECK(ctx);
+    plonk::prod_finish<<<(unsigned)nb, plonk::PSCAN_THREADS, 0, ctx->stream>>>(rowprod.p, n, totals.p, z);
+    ETP_LAUNCH_CHECK(ctx);
+    if (n_pp > 0) {
+      plonk::permutation_partial_products<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(
+          z, chunk.p, n_chunks, (uint32_t)n, out_dev + ((size_t)num_challenges + (size_t)c * n_pp) * n);
+      ETP_LAUNCH_CHECK(ctx);
+    }
+  }
+  return check_zero_flag(ctx, "a permutation-argument denominator vanishes");  // also keeps kc alive until the copy is done
 }
 
 extern "C" size_t etp_fri_proof_words(const size_t* oracle_num_cols, size_t n_oracles, const etp_fri_params* params) {

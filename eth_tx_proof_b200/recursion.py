@@ -7,14 +7,15 @@ What is on the device here, under `CircuitConfig::standard_recursion_config()` (
 16 PoW bits, ConstantArityBits(4, 5), 135 wires of which 80 routed, 2 challenges, quotient degree factor 8):
 
     wires_commitment          = PolynomialBatch::from_values(wires, rate_bits, blinding=false, cap_height)        135 polys
+    all_wires_permutation_partial_products(witness, betas, gammas, ..)       Z and partial products of the permutation argument
     partial_products_and_zs   = PolynomialBatch::from_values(...)                          2 x (1 Z + 9 partial products) = 20 polys
     quotient_polys_commitment = PolynomialBatch::from_coeffs(quotient chunks)                                  2 x 8 = 16 polys
     openings at zeta (all four oracles) and g*zeta (the Zs), observe, PolynomialBatch::prove_openings over the
     four-oracle FriInstanceInfo (constants_sigmas is the circuit's pre-committed batch: 4 constants + 80 sigmas)
 
 through the same C-ABI calls the starky path uses (`etp_batch_from_*`, `etp_batch_eval_at_ext_point`, `etp_prove_openings`)
-with a caller-side `Challenger`.  What is NOT: witness generation, the wire / Z values themselves and the gate-constraint
-quotient — they stay on the CPU side of the fork for now (gate evaluation is the next slice); this module feeds seeded
+and `etp_plonk_partial_products_and_zs_dev`, with a caller-side `Challenger`.  What is NOT: witness generation and the
+gate-constraint quotient — they stay on the CPU side of the fork for now (gate evaluation is the next slice); this module feeds seeded
 stand-in polynomials of the right SHAPES, so the numbers it produces time the device skeleton of a recursion proof, not a
 recursion proof.  The transcript order follows plonk/prover.rs: circuit digest, public-input hash, wires cap -> betas,
 gammas; Z cap -> alphas; quotient cap -> zeta; openings -> FRI.
@@ -51,8 +52,49 @@ def fri_instance(zeta, degree_bits: int):
     return [([int(zeta[0]), int(zeta[1])], all_polys), (zeta_next, zs)]
 
 
+def coset_shifts(num_shifts: int):
+    """plonky2::field::cosets::get_unique_coset_shifts: k_j = g^j for the multiplicative generator g = 7 (k_0 = 1)."""
+    return [pow(7, j, P) for j in range(num_shifts)]
+
+
+def permutation_witness(degree_bits: int, num_routed: int = NUM_ROUTED, seed: int = 1):
+    """A wire assignment that satisfies a random copy-constraint permutation, with the sigma values that encode it.
+    Positions (row i, routed column j) are paired at random; both wires of a pair hold the same value and sigma maps each
+    to the other's identity value k_j * g^i (plonky2::plonk::permutation_argument / CircuitBuilder::sigma_vecs).
+    -> (wires (num_routed, n), sigmas (num_routed, n), k_is)"""
+    n = 1 << degree_bits
+    rng = np.random.default_rng(seed)
+    g = root_of_unity(degree_bits)
+    k_is = coset_shifts(num_routed)
+    xs = [1]
+    for _ in range(n - 1):
+        xs.append(xs[-1] * g % P)
+    k_obj, x_obj = np.array(k_is, dtype=object), np.array(xs, dtype=object)
+    total = n * num_routed  # position = column * n + row
+    order = rng.permutation(total)
+    a, b = order[0:total - total % 2:2], order[1::2]
+    ident = lambda pos: np.array(k_obj[pos // n] * x_obj[pos % n] % P, dtype=np.uint64)
+    vals = rng.integers(0, 2**63, size=a.size, dtype=np.uint64)
+    wires, sig = np.zeros(total, dtype=np.uint64), np.zeros(total, dtype=np.uint64)
+    wires[a] = wires[b] = vals
+    sig[a], sig[b] = ident(b), ident(a)
+    if total % 2:
+        last = order[-1:]
+        wires[last] = 7
+        sig[last] = ident(last)
+    return wires.reshape(num_routed, n), sig.reshape(num_routed, n), np.array(k_is, dtype=np.uint64)
+
+
 def stand_in_polys(degree_bits: int, seed: int = 0xC1C) -> Dict[str, np.ndarray]:
-    return {name: syn.random_columns(n, degree_bits, seed=seed + 1000 * i) for i, (name, n) in enumerate(ORACLE_SHAPES.items())}
+    """Seeded inputs of one skeleton proof: the routed wires satisfy a random permutation argument (so Z closes), the
+    advice wires, constants and quotient chunks are random stand-ins; `sigmas` are the sigma VALUES on the subgroup (the
+    constants_sigmas oracle commits to them), `k_is` the coset shifts."""
+    wires_routed, sigmas, k_is = permutation_witness(degree_bits, NUM_ROUTED, seed)
+    polys = {name: syn.random_columns(n, degree_bits, seed=seed + 1000 * i) for i, (name, n) in enumerate(ORACLE_SHAPES.items())}
+    polys["wires"][:NUM_ROUTED] = wires_routed
+    polys["constants_sigmas"][NUM_CONSTANTS:] = sigmas
+    polys["k_is"] = k_is
+    return polys
 
 
 def prove_skeleton(ctx: Context, degree_bits: int, polys: Dict[str, np.ndarray] = None, constants_sigmas: PolynomialBatch = None) -> dict:
@@ -69,9 +111,24 @@ def prove_skeleton(ctx: Context, degree_bits: int, polys: Dict[str, np.ndarray] 
     t["wires commit"] = (time.perf_counter() - t0) * 1e3
     ch.observe_cap(wires.cap)
     betas, gammas = ch.get_n_challenges(NUM_CHALLENGES), ch.get_n_challenges(NUM_CHALLENGES)
+    # all_wires_permutation_partial_products on the device: routed wires + sigma values -> Z and partial products
+    import torch
+
+    n = 1 << degree_bits
     t0 = time.perf_counter()
-    zs = PolynomialBatch.from_values(ctx, polys["zs_partial_products"], RATE_BITS, False, CAP_HEIGHT)
+    d_w = torch.from_numpy(np.ascontiguousarray(polys["wires"][:NUM_ROUTED]).view(np.int64)).cuda()
+    d_s = torch.from_numpy(np.ascontiguousarray(polys["constants_sigmas"][NUM_CONSTANTS:]).view(np.int64)).cuda()
+    d_z = torch.empty((ORACLE_SHAPES["zs_partial_products"], n), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    t["upload routed wires + sigmas"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    ctx.plonk_partial_products_and_zs_dev(d_w.data_ptr(), n, d_s.data_ptr(), n, polys["k_is"], degree_bits, QUOTIENT_DEGREE_FACTOR,
+                                          betas, gammas, d_z.data_ptr())
+    t["partial products and Zs"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    zs = PolynomialBatch.from_values_dev(ctx, d_z.data_ptr(), n, ORACLE_SHAPES["zs_partial_products"], degree_bits, RATE_BITS, False, CAP_HEIGHT)
     t["partial products and Zs commit"] = (time.perf_counter() - t0) * 1e3
+    zs_values = d_z.cpu().numpy().view(np.uint64)
     ch.observe_cap(zs.cap)
     alphas = ch.get_n_challenges(NUM_CHALLENGES)
     t0 = time.perf_counter()
@@ -94,5 +151,5 @@ def prove_skeleton(ctx: Context, degree_bits: int, polys: Dict[str, np.ndarray] 
     fri = ctx.prove_openings(fri_instance(zeta, degree_bits), oracles, ch, fp)
     t["prove_openings (FRI)"] = (time.perf_counter() - t0) * 1e3
     t["total"] = sum(t.values())
-    return {"caps": [o.cap for o in oracles], "betas": betas, "gammas": gammas, "alphas": alphas, "zeta": zeta, "openings": openings,
+    return {"zs_partial_products": zs_values, "caps": [o.cap for o in oracles], "betas": betas, "gammas": gammas, "alphas": alphas, "zeta": zeta, "openings": openings,
             "openings_next": openings_next, "fri_proof": fri, "challenger": ch, "ms": t, "fri_params": fp}

@@ -328,6 +328,21 @@ size_t etp_fri_proof_words(const size_t *oracle_num_cols, size_t n_oracles, cons
 int etp_prove_openings(etp_ctx *ctx, const etp_fri_batch *batches, size_t n_batches, etp_batch *const *oracles, size_t n_oracles,
                        etp_challenger *challenger, const etp_fri_params *params, uint64_t *fri_proof_out);
 
+/* ---- plonky2's circuit prover, first slice (the recursion layers: /root/reference/ops/src/lib.rs:52,72,95) -----------------
+ * plonky2::plonk::prover::all_wires_permutation_partial_products (wires_permutation_partial_products_and_zs per challenge,
+ * util/partial_products.rs): the permutation argument's Z and partial-product polynomials, values on the subgroup (row i =
+ * point g^i), computed on the device from the routed wires and the sigma values:
+ *   quotient_j(i) = (wire_j(i) + beta k_j g^i + gamma) / (wire_j(i) + beta sigma_j(i) + gamma),
+ *   chunk products over quotient_degree_factor wires, Z(g x) = Z(x) * (product of the row's chunks), Z(1) = 1.
+ * wires_dev / sigmas_dev: num_routed_wires columns of 2^degree_bits (column-major, given strides); k_is: the coset shifts.
+ * out_dev: num_challenges * (1 + num_partial_products) columns of 2^degree_bits, stride 2^degree_bits, in the order the
+ * prover commits them: [Z of every challenge] ++ [partial products of challenge 0] ++ [of challenge 1] ...;
+ * num_partial_products = ceil(num_routed_wires / quotient_degree_factor) - 1.  A zero denominator gives ETP_ERR_PROOF. */
+int etp_plonk_partial_products_and_zs_dev(etp_ctx *ctx, const uint64_t *wires_dev, size_t wires_stride, const uint64_t *sigmas_dev,
+                                          size_t sigmas_stride, const uint64_t *k_is, int num_routed_wires, int degree_bits,
+                                          int quotient_degree_factor, const uint64_t *betas, const uint64_t *gammas, int num_challenges,
+                                          uint64_t *out_dev);
+
 /* ---- the FRI prover, step by step (fri_committed_trees is sequential through the challenger: beta_l depends on cap_l) --
  * values_dev: 2^(degree_bits + rate_bits) extension values (c0, c1 interleaved) of the polynomial on the coset 7*H in
  * BIT-REVERSED order (what reverse_index_bits_in_place gives upstream); the state takes a private copy. */

@@ -149,6 +149,8 @@ def lib():
     L.orc_pow_grind.argtypes = [_u64p, C.c_int, C.c_int]
     L.orc_pow_grind.restype = C.c_uint64
     L.orc_fri_fold_coeffs.argtypes = [_u64p, sz, C.c_int, _u64p, _u64p]
+    L.orc_plonk_partial_products_and_zs.argtypes = [_u64p, _u64p, _u64p, C.c_int, C.c_int, C.c_int, _u64p, _u64p, C.c_int, _u64p]
+    L.orc_plonk_partial_products_and_zs.restype = C.c_int
     L.orc_num_threads.restype = C.c_int
     _lib = L
     return L
@@ -466,6 +468,20 @@ def fri_fold_coeffs(coeffs, arity_bits, beta) -> np.ndarray:
     c = _u64(coeffs).reshape(-1, 2)
     out = np.zeros((c.shape[0] >> arity_bits, 2), dtype=np.uint64)
     lib().orc_fri_fold_coeffs(_ptr(c), c.shape[0], arity_bits, _ptr(_u64(beta)), _ptr(out))
+    return out
+
+
+def plonk_partial_products_and_zs(wires, sigmas, k_is, quotient_degree_factor, betas, gammas) -> np.ndarray:
+    """plonky2 all_wires_permutation_partial_products: [Z per challenge] ++ [partial products per challenge], values on the subgroup."""
+    w, s_ = _u64(wires), _u64(sigmas)
+    k, b, g = _u64(k_is), _u64(betas), _u64(gammas)
+    n_routed, n = w.shape
+    n_pp = -(-n_routed // quotient_degree_factor) - 1
+    out = np.zeros((b.size * (1 + n_pp), n), dtype=np.uint64)
+    rc = lib().orc_plonk_partial_products_and_zs(_ptr(w), _ptr(s_), _ptr(k), n_routed, int(n).bit_length() - 1, quotient_degree_factor,
+                                                 _ptr(b), _ptr(g), b.size, _ptr(out))
+    if rc != 0:
+        raise RuntimeError("oracle: zero denominator in the permutation argument")
     return out
 
 

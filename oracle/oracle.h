@@ -138,6 +138,11 @@ size_t orc_fri_proof_words(const size_t *oracle_cols, size_t n_oracles, const or
 int orc_prove_openings(const orc_fri_batch *batches, size_t n_batches, const orc_batch *const *oracles, size_t n_oracles,
                        orc_challenger *challenger, const orc_fri_params *params, uint64_t *fri_proof_out);
 
+/* ---- plonk.c : first slice of plonky2's circuit prover ---- */
+int orc_plonk_partial_products_and_zs(const uint64_t *wires, const uint64_t *sigmas, const uint64_t *k_is, int num_routed,
+                                      int degree_bits, int quotient_degree_factor, const uint64_t *betas, const uint64_t *gammas,
+                                      int num_challenges, uint64_t *out);
+
 int orc_num_threads(void);
 #ifdef __cplusplus
 }

@@ -167,7 +167,9 @@ def test_prove_openings_general_instance_matches_oracle(ctx, degree_bits, rate_b
     gb = [etp.PolynomialBatch.from_values(ctx, v, rate_bits, False, 4) for v in cols]
     ob = [oracle.Batch.from_values(v, rate_bits, 4) for v in cols]
     zeta = [123456789123456789 % P, 987654321987654321 % P]
-    g = oracle.pyref.root_of_unity(degree_bits)
+    from oracle import pyref
+
+    g = pyref.root_of_unity(degree_bits)
     zeta_next = [zeta[0] * g % P, zeta[1] * g % P]
     all_polys = [(o, c) for o, n in enumerate(shapes) for c in range(n)]
     zs = [(2, 0), (2, 1)]
@@ -259,12 +261,20 @@ def test_recursion_proof_skeleton_matches_oracle(ctx, degree_bits):
 
     polys = rec.stand_in_polys(degree_bits, seed=degree_bits)
     got = rec.prove_skeleton(ctx, degree_bits, polys)
-    ob = [oracle.Batch.from_values(polys["constants_sigmas"], 3, 4), oracle.Batch.from_values(polys["wires"], 3, 4),
-          oracle.Batch.from_values(polys["zs_partial_products"], 3, 4), oracle.Batch.from_coeffs(polys["quotient"], 3, 4)]
+    ob = [oracle.Batch.from_values(polys["constants_sigmas"], 3, 4), oracle.Batch.from_values(polys["wires"], 3, 4), None,
+          oracle.Batch.from_coeffs(polys["quotient"], 3, 4)]
     och = oracle.HostChallenger()
     och.observe(ob[0].cap)
     och.observe(ob[1].cap)
-    assert (och.get_n(2) == got["betas"]).all() and (och.get_n(2) == got["gammas"]).all()
+    betas, gammas = och.get_n(2), och.get_n(2)
+    assert (betas == got["betas"]).all() and (gammas == got["gammas"]).all()
+    # Z and partial products from the device == plonky2's all_wires_permutation_partial_products as restated by the oracle,
+    # and the permutation argument closes: Z(x_{n-1}) times the last row's quotient product is 1
+    want_z = oracle.plonk_partial_products_and_zs(polys["wires"][:rec.NUM_ROUTED], polys["constants_sigmas"][rec.NUM_CONSTANTS:], polys["k_is"],
+                                                  rec.QUOTIENT_DEGREE_FACTOR, betas, gammas)
+    assert (got["zs_partial_products"] == want_z).all()
+    assert (want_z[:2, 0] == 1).all()
+    ob[2] = oracle.Batch.from_values(want_z, 3, 4)
     och.observe(ob[2].cap)
     assert (och.get_n(2) == got["alphas"]).all()
     och.observe(ob[3].cap)
@@ -303,3 +313,96 @@ def test_evm_shaped_transaction_matches_oracle(ctx):
     for k in range(7):
         assert (np.delete(got.stark_proofs[k], 1) == np.delete(want[k], 1)).all(), tables[k][0]
     verify_all(tables, ctls, got.stark_proofs, got.trace_caps, max_queries=1)
+
+
+def test_prove_openings_edge_instances(ctx):
+    """One batch, four batches, a batch over a single polynomial, degree too small for any FRI reduction — against the oracle;
+    and the misuse the C ABI must reject (upstream: panics)."""
+    import eth_tx_proof_b200 as etp
+    import oracle
+    from eth_tx_proof_b200 import synthetic as syn
+
+    for degree_bits, rate_bits in ((4, 1), (7, 2), (9, 1)):
+        cols = [syn.random_columns(c, degree_bits, seed=40 + i) for i, c in enumerate((3, 5))]
+        gb = [etp.PolynomialBatch.from_values(ctx, v, rate_bits, False, 2) for v in cols]
+        ob = [oracle.Batch.from_values(v, rate_bits, 2) for v in cols]
+        pts = [[5, 6], [7, 0], [P - 3, 11], [1, 0]]
+        instances = [
+            [(pts[0], [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4)])],
+            [(pts[0], [(1, 4)]), (pts[1], [(0, 2)])],
+            [(pts[0], [(0, 0), (1, 0)]), (pts[1], [(0, 0)]), (pts[2], [(1, 0), (0, 0)]), (pts[3], [(1, 3), (1, 2), (0, 1)])],
+        ]
+        fp = etp.FriParams.make(degree_bits, rate_bits, 2, 3, 5)
+        ofp = oracle.fri_params(degree_bits, rate_bits, 2, 3, 5)
+        for inst in instances:
+            gch, och = etp.Challenger(), oracle.HostChallenger()
+            gch.observe([degree_bits])
+            och.observe([degree_bits])
+            got = ctx.prove_openings(inst, gb, gch, fp)
+            want = oracle.prove_openings(inst, ob, och, ofp)
+            assert (got == want).all() and (gch.words() == och.words()).all(), (degree_bits, len(inst))
+    b = etp.PolynomialBatch.from_values(ctx, syn.random_columns(2, 6, seed=1), 1, False, 4)
+    fp = etp.FriParams.make(6, 1, 4, 16, 84)
+    with pytest.raises(etp.EtpError):  # polynomial index out of range
+        ctx.prove_openings([([1, 2], [(0, 2)])], [b], etp.Challenger(), fp)
+    with pytest.raises(etp.EtpError):  # oracle committed with another rate
+        ctx.prove_openings([([1, 2], [(0, 0)])], [b], etp.Challenger(), etp.FriParams.make(6, 2, 4, 16, 84))
+    with pytest.raises(etp.EtpError):  # five batches
+        ctx.prove_openings([([k, 2], [(0, 0)]) for k in range(5)], [b], etp.Challenger(), fp)
+    with pytest.raises(etp.EtpError):  # the same polynomial twice in one batch
+        ctx.prove_openings([([1, 2], [(0, 0), (0, 0)])], [b], etp.Challenger(), fp)
+    bad = etp.Challenger()
+    bad.input_len = 9
+    with pytest.raises(etp.EtpError):  # corrupt transcript state
+        ctx.prove_openings([([1, 2], [(0, 0)])], [b], bad, fp)
+
+
+def test_opening_point_on_the_lde_coset_is_reported(ctx):
+    """(x - z) vanishes at an LDE point: upstream's divide_by_linear is fine in coefficient form, the evaluation-form path
+    must say so instead of returning garbage."""
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import synthetic as syn
+
+    b = etp.PolynomialBatch.from_values(ctx, syn.random_columns(2, 5, seed=2), 1, False, 4)
+    with pytest.raises(etp.EtpError) as e:
+        ctx.prove_openings([([7, 0], [(0, 0), (0, 1)])], [b], etp.Challenger(), etp.FriParams.make(5, 1, 4, 4, 3))  # 7 = the coset shift
+    assert e.value.code == -4
+
+
+def test_register_ex_rejects_malformed_specs(ctx):
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import cprog
+
+    tables, _ = cprog.ctl_demo_tables(5, 4, 4)
+    _, prog, _ = tables[0]
+    spec = prog.aux_spec.copy()
+    ok = ctx.register_table_ex(prog, spec)
+    assert ok >= 16
+    for mutate in (lambda s: s[:-1], lambda s: np.concatenate([s, [0]]).astype(np.uint64),
+                   lambda s: np.concatenate([[1], s[1:]]).astype(np.uint64),                    # bad magic
+                   lambda s: np.concatenate([s[:1], [s[1] + 1], s[2:]]).astype(np.uint64)):     # one more lookup than described
+        with pytest.raises(etp.EtpError):
+            ctx.register_table_ex(prog, mutate(spec))
+    col = spec.copy()
+    col[5] = 1000  # first looking column reads trace column 1000
+    with pytest.raises(etp.EtpError):
+        ctx.register_table_ex(prog, col)
+    with pytest.raises(etp.EtpError):  # program reads CTL aux columns but the spec has none
+        ctx.register_table_ex(prog, np.array([cprog.AUXSPEC_MAGIC, 0, 0], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 5])
+def test_tiny_tables_through_prove_with_commitment(ctx, log_n):
+    """Degrees below every FRI reduction and below the cap height's comfort zone (2^log_n << rate_bits vs 2^cap_height)."""
+    import torch
+
+    import eth_tx_proof_b200 as etp
+    import oracle
+    from eth_tx_proof_b200 import synthetic as syn
+
+    if log_n + 1 < 4:
+        with pytest.raises(etp.EtpError):  # cap_height 4 > log2(leaves): upstream asserts in MerkleTree::new
+            ctx.stark_prove(etp.TABLE_FIBONACCI, *syn.fibonacci_trace(log_n))
+        return
+    t, pi = syn.fibonacci_trace(log_n, seed=log_n)
+    assert (ctx.stark_prove(etp.TABLE_FIBONACCI, t, pi) == oracle.stark_prove(oracle.TABLE_FIBONACCI, t, pi)).all()
