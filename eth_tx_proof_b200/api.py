@@ -333,6 +333,13 @@ class Context:
     def stark_proof_words(self, table, log_n) -> int:
         return int(self.L.etp_stark_proof_words(self.h, table, log_n))
 
+    def _proof_buffer(self, table, log_n) -> np.ndarray:
+        words = self.stark_proof_words(table, log_n)
+        if words == 0:
+            raise EtpError(-1, f"no proof shape for table {table} at degree_bits {log_n}: unknown table, or cap_height=4 should be at "
+                               f"most log2(leaves.len())={log_n + 1}")
+        return np.zeros(words, dtype=np.uint64)
+
     def register_table(self, program, lookups=()) -> int:
         """Registers a table from its constraint program (``cprog.Program.words`` or a u64 array) and its lookups
         (``[(looking_columns, table_column, frequencies_column), ...]``): NVRTC-compiles the quotient kernel for
@@ -374,7 +381,7 @@ class Context:
         cc = _u64(ctl_challenges) if ctl_challenges is not None else None
         if cc is not None and cc.size != 4:
             raise EtpError(-1, "ctl_challenges must be num_challenges (beta, gamma) pairs = 4 words")
-        out = np.zeros(self.stark_proof_words(table, trace_batch.degree_log), dtype=np.uint64)
+        out = self._proof_buffer(table, trace_batch.degree_log)
         self.check(self.L.etp_prove_with_commitment(self.h, table, trace_batch.h, C.c_void_p(trace_ptr), col_stride,
                                                     _p(cc) if cc is not None else None, C.byref(challenger), _p(pi), _p(out)))
         return out
@@ -415,7 +422,7 @@ class Context:
         t = _u64(trace)
         log_n = self._check_trace_shape(table, t.shape, public_inputs)
         pi = _u64(list(public_inputs) + [0])
-        out = np.zeros(self.stark_proof_words(table, log_n), dtype=np.uint64)
+        out = self._proof_buffer(table, log_n)
         self.check(self.L.etp_stark_prove_host(self.h, table, log_n, _p(t), _p(pi), _p(out)))
         return out
 
@@ -440,7 +447,7 @@ class Context:
         if n_pi < 0 or len(public_inputs) < n_pi or col_stride < (1 << log_n) or not trace_ptr:
             raise EtpError(-1, "stark_prove_dev: unknown table, too few public inputs, null trace or stride < 2^log_n")
         pi = _u64(list(public_inputs) + [0])
-        out = np.zeros(self.stark_proof_words(table, log_n), dtype=np.uint64)
+        out = self._proof_buffer(table, log_n)
         self.check(self.L.etp_stark_prove_dev(self.h, table, log_n, C.c_void_p(trace_ptr), col_stride, _p(pi), _p(out)))
         return out
 

@@ -723,8 +723,9 @@ int fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracl
     if (!oracles[o] || oracles[o]->ctx != ctx || oracles[o]->log_n != p.degree_bits || oracles[o]->rate_bits != p.rate_bits || oracles[o]->cap_height != p.cap_height)
       return etp_fail(ctx, ETP_ERR_INVALID, "FRI oracle %zu does not match the FRI parameters", o);
   // device staging: per oracle rows + paths, per layer rows + paths
+  // (gather_paths stores digests as two 16-byte words: every path section starts on an even word)
   size_t stage_words = 0;
-  for (size_t o = 0; o < n_oracles; o++) stage_words += nq * (oracles[o]->n_cols + 4 * (size_t)init_path);
+  for (size_t o = 0; o < n_oracles; o++) stage_words += nq * (oracles[o]->n_cols + 4 * (size_t)init_path) + 1;
   {
     int bits = log_lde;
     for (int l = 0; l < n_layers; l++) { bits -= ARITY_BITS; stage_words += nq * (32 + 4 * (size_t)(bits - p.cap_height)); }
@@ -750,6 +751,7 @@ int fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracl
       ETP_LAUNCH_CHECK(ctx);
     }
     off += nq * nc;
+    off += off & 1;
     off_paths[o] = off;
     if (init_path > 0) {
       stark::gather_paths<<<blocks_for(nq * init_path, 256), 256, 0, ctx->stream>>>(oracles[o]->levels, (uint32_t)lde_n, init_path, d_idx.p, (int)nq,
@@ -1422,7 +1424,8 @@ extern "C" void etp_fri_free(etp_fri_state* s) {
 
 extern "C" size_t etp_stark_proof_words(const etp_ctx* ctx, int table, int log_n) {
   TableInfo ti;
-  if (!table_info(ctx, table, &ti) || log_n < 1 || log_n > 29) return 0;
+  // 0 = no such proof: unknown table, or a degree for which cap_height > log2(LDE size) (upstream: MerkleTree::new asserts)
+  if (!table_info(ctx, table, &ti) || log_n < 1 || log_n > 29 || log_n + RATE_BITS < CAP_HEIGHT) return 0;
   return proof_words(ti, log_n);
 }
 

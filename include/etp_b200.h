@@ -324,6 +324,8 @@ typedef struct etp_fri_batch { uint64_t point[2]; const etp_fri_poly *polynomial
  * { per oracle: leaf row (n_cols), MerkleProof siblings x 4 ; per reduction: FriQueryStep.evals (2^arity ext — the
  * uncompressed FriProof carries all of them; only CompressedFriProof drops the queried one), siblings x 4 }),
  * final_poly (ext coefficients), pow_witness */
+/* The quotients (F_b(x) - y_b) / (x - z_b) are formed point-wise on the LDE coset 7*H: an opening point that lies ON that coset
+ * (never the case for a Fiat-Shamir zeta; upstream's coefficient-form division would accept it) gives ETP_ERR_PROOF. */
 size_t etp_fri_proof_words(const size_t *oracle_num_cols, size_t n_oracles, const etp_fri_params *params);
 int etp_prove_openings(etp_ctx *ctx, const etp_fri_batch *batches, size_t n_batches, etp_batch *const *oracles, size_t n_oracles,
                        etp_challenger *challenger, const etp_fri_params *params, uint64_t *fri_proof_out);

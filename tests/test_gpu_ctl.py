@@ -326,7 +326,7 @@ def test_prove_openings_edge_instances(ctx):
         cols = [syn.random_columns(c, degree_bits, seed=40 + i) for i, c in enumerate((3, 5))]
         gb = [etp.PolynomialBatch.from_values(ctx, v, rate_bits, False, 2) for v in cols]
         ob = [oracle.Batch.from_values(v, rate_bits, 2) for v in cols]
-        pts = [[5, 6], [7, 0], [P - 3, 11], [1, 0]]
+        pts = [[5, 6], [8, 0], [P - 3, 11], [1, 0]]  # ([7, 0] would be a point OF the LDE coset: see the next test)
         instances = [
             [(pts[0], [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4)])],
             [(pts[0], [(1, 4)]), (pts[1], [(0, 2)])],
