@@ -69,6 +69,30 @@ GL_D uint64_t sub(uint64_t a, uint64_t b) {
   asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u32 %1, 0, 0;" : "+l"(d), "=r"(br) : "l"((uint64_t)br));
   return d - (uint64_t)br;
 }
+// add / sub with the second fix-up out of line.  The second wrap happens only when BOTH operands are >= p (add) or the
+// subtrahend exceeds p + minuend (sub): never for canonical data, probability ~2^-64 for random representatives.  Keeping it
+// behind a predicated call takes its two ALU instructions off the integer pipe that bounds the NTT (ptxas would if-convert
+// an inline branch back into predicated instructions, which still occupy the pipe).
+#if !defined(__CUDACC_RTC__)
+static __device__ __noinline__ uint64_t add_eps_slow(uint64_t s) { return s + EPS; }
+static __device__ __noinline__ uint64_t sub_eps_slow(uint64_t s) { return s - EPS; }
+GL_D uint64_t add_r(uint64_t a, uint64_t b) {
+  uint64_t s;
+  uint32_t c, c2;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(s), "=r"(c) : "l"(a), "l"(b));
+  asm("add.cc.u64 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+l"(s), "=r"(c2) : "l"((uint64_t)(0u - c)));
+  if (__builtin_expect(c2 != 0, 0)) s = add_eps_slow(s);
+  return s;
+}
+GL_D uint64_t sub_r(uint64_t a, uint64_t b) {
+  uint64_t d;
+  uint32_t br, br2;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(d), "=r"(br) : "l"(a), "l"(b));
+  asm("sub.cc.u64 %0, %0, %2;\n\tsubc.u32 %1, 0, 0;" : "+l"(d), "=r"(br2) : "l"((uint64_t)br));
+  if (__builtin_expect(br2 != 0, 0)) d = sub_eps_slow(d);
+  return d;
+}
+#endif
 // a: any u64, b: CANONICAL (< p).
 GL_D uint64_t sub_c(uint64_t a, uint64_t b) {
   uint64_t d;
@@ -255,6 +279,8 @@ GL_HD uint64_t sub(uint64_t a, uint64_t b) {
   return d;
 }
 GL_HD uint64_t sub_c(uint64_t a, uint64_t b) { return sub(a, b); }
+GL_HD uint64_t add_r(uint64_t a, uint64_t b) { return add(a, b); }
+GL_HD uint64_t sub_r(uint64_t a, uint64_t b) { return sub(a, b); }
 #endif
 
 #if !defined(__CUDA_ARCH__)

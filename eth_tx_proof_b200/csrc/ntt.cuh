@@ -31,6 +31,18 @@
 
 namespace ntt {
 
+// butterfly add / sub: -DETP_NTT_RARE_FIX=0 selects the fully inline double fix-up
+#ifndef ETP_NTT_RARE_FIX
+#define ETP_NTT_RARE_FIX 1
+#endif
+#if ETP_NTT_RARE_FIX
+__device__ __forceinline__ uint64_t badd(uint64_t a, uint64_t b) { return gl::add_r(a, b); }
+__device__ __forceinline__ uint64_t bsub(uint64_t a, uint64_t b) { return gl::sub_r(a, b); }
+#else
+__device__ __forceinline__ uint64_t badd(uint64_t a, uint64_t b) { return gl::add(a, b); }
+__device__ __forceinline__ uint64_t bsub(uint64_t a, uint64_t b) { return gl::sub(a, b); }
+#endif
+
 constexpr int THREADS = 256;
 constexpr int TILE_LOG = 12;       // 4096 elements per CTA, 16 per thread
 constexpr int MAX_DIGIT_BITS = 8;
@@ -91,8 +103,8 @@ __device__ __forceinline__ void dft_const(uint64_t* v, bool inverse) {
       if ((j & half) == 0) {
         const int e = ((j & (half - 1)) << q) << (4 - Q);  // exponent in units of w16
         const uint64_t a = v[j], c = v[j + half];
-        v[j] = gl::add(a, c);
-        const uint64_t d = gl::sub(a, c);
+        v[j] = badd(a, c);
+        const uint64_t d = bsub(a, c);
         v[j + half] = (e == 0) ? d : gl::mul(d, inverse ? W16I[e] : W16[e]);
       }
     }
@@ -112,8 +124,8 @@ __device__ __forceinline__ void dif_top(uint64_t* v, const uint64_t* tw_r, int d
         const int dm = ((j & (half - 1)) << (B - Q)) | d_lo;
         const uint64_t w = tw_r[dm << q];
         const uint64_t a = v[j], c = v[j + half];
-        v[j] = gl::add(a, c);
-        v[j + half] = gl::mul(gl::sub(a, c), w);
+        v[j] = badd(a, c);
+        v[j + half] = gl::mul(bsub(a, c), w);
       }
     }
   }
