@@ -490,7 +490,7 @@ def main():
     perms_leaf = (n << RATE_BITS) * ((cols + 7) // 8)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     # integer-pipe roofline of the Poseidon kernels: the denominator is MEASURED in this run
-    # (etp_bench_pipe_rates: dependent-chain micro-kernels for IMAD.WIDE.U32, IADD3 and DFMA); the numerator is the
+    # (etp_bench_pipe_rates: dependent-chain micro-kernels for IMAD.WIDE.U32 and DFMA); the numerator is the
     # ALGORITHMIC multiply count of a permutation, independent of how the kernel is written: 118 S-boxes x 4 field
     # multiplications x 4 partial products (32x32->64) = 1888, plus 30 MDS layers x 144 coefficients x 2 32-bit planes =
     # 8640 small-constant multiply-adds -> 10528 MAC32 per permutation.

@@ -292,9 +292,9 @@ class Context:
 
     def pipe_rates(self) -> dict:
         """Measured issue rates (thread-instructions/s, whole device) of the integer / FP64 pipes (etp_bench_pipe_rates)."""
-        r = (C.c_double * 4)()
+        r = (C.c_double * 3)()
         self.check(self.L.etp_bench_pipe_rates(self.h, r))
-        return {"imad_wide_u32_zero_addend": r[0], "imad_wide_u32_accumulate": r[1], "iadd3": r[2], "dfma": r[3]}
+        return {"imad_wide_u32_zero_addend": r[0], "mad_wide_u32_accumulate": r[1], "dfma": r[2]}
 
     # ---- primitives (parity tests)
     def poseidon_permute(self, states) -> np.ndarray:

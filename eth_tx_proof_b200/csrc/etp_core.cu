@@ -949,20 +949,6 @@ __global__ void __launch_bounds__(THREADS) k_imad_wide_acc(uint64_t* out, uint32
   for (int i = 0; i < CHAINS; i++) s += acc[i];
   out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
 }
-__global__ void __launch_bounds__(THREADS) k_iadd3(uint64_t* out, uint32_t b) {  // integer ALU port
-  uint32_t acc[CHAINS];
-  for (int i = 0; i < CHAINS; i++) acc[i] = i + threadIdx.x;
-  for (int it = 0; it < ITERS; it++) {
-#pragma unroll
-    for (int i = 0; i < CHAINS; i += 2) {  // add / xor alternate so that ptxas cannot fuse two adds into one IADD3
-      asm volatile("add.u32 %0, %0, %1;" : "+r"(acc[i]) : "r"(b));
-      asm volatile("xor.b32 %0, %0, %1;" : "+r"(acc[i + 1]) : "r"(b));
-    }
-  }
-  uint32_t s = 0;
-  for (int i = 0; i < CHAINS; i++) s += acc[i];
-  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
-}
 __global__ void __launch_bounds__(THREADS) k_dfma(uint64_t* out, uint32_t b) {  // FP64 pipe (shares the ALU issue port)
   double acc[CHAINS];
   const double m = 1.0 + 1e-9 * b, c = 1e-3;
@@ -977,9 +963,11 @@ __global__ void __launch_bounds__(THREADS) k_dfma(uint64_t* out, uint32_t b) {  
 }
 }  // namespace pipes
 
-// rates_out[4]: sustained thread-instructions per second of the whole device for
-// [0] IMAD.WIDE.U32 with a zero addend, [1] IMAD.WIDE.U32 accumulating into a 64-bit addend, [2] integer ALU (IADD3 / LOP3), [3] DFMA.
-extern "C" int etp_bench_pipe_rates(etp_ctx* ctx, double rates_out[4]) {
+// rates_out[3]: sustained thread-instructions per second of the whole device for
+// [0] IMAD.WIDE.U32 with a zero addend, [1] mad.wide.u32 accumulating into a 64-bit addend (ptxas emits IMAD.WIDE + a 64-bit
+// IADD3 pair for it), [2] DFMA.  (A plain integer-add chain is not reported: ptxas rewrites it — IADD3 fusion, IMAD moves —
+// so its "rate" says nothing about the ALU port.)
+extern "C" int etp_bench_pipe_rates(etp_ctx* ctx, double rates_out[3]) {
   etp_bind(ctx);
   if (!ctx || !rates_out) return ETP_ERR_INVALID;
   cudaDeviceProp prop;
@@ -991,9 +979,9 @@ extern "C" int etp_bench_pipe_rates(etp_ctx* ctx, double rates_out[4]) {
   ETP_CUDA(ctx, cudaEventCreate(&e0));
   ETP_CUDA(ctx, cudaEventCreate(&e1));
   typedef void (*kern_t)(uint64_t*, uint32_t);
-  const kern_t kerns[4] = {pipes::k_imad_wide_zero, pipes::k_imad_wide_acc, pipes::k_iadd3, pipes::k_dfma};
+  const kern_t kerns[3] = {pipes::k_imad_wide_zero, pipes::k_imad_wide_acc, pipes::k_dfma};
   int rc = ETP_OK;
-  for (int k = 0; k < 4 && rc == ETP_OK; k++) {
+  for (int k = 0; k < 3 && rc == ETP_OK; k++) {
     float best = 0;
     for (int rep = 0; rep < 4; rep++) {  // first repetition warms up
       cudaEventRecord(e0, ctx->stream);

@@ -73,10 +73,10 @@ int etp_dev_upload(etp_ctx *ctx, void *dst_dev, const void *src_host, size_t byt
 int etp_dev_download(etp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
 /* Sustained issue rates of the integer / FP64 pipes of this device (thread-instructions per second, whole GPU), measured
- * with dependent-chain micro-kernels on the context's stream: [0] IMAD.WIDE.U32 with a zero addend, [1] IMAD.WIDE.U32
- * accumulating into a 64-bit addend, [2] IADD3, [3] DFMA.  bench.py uses them as the integer-pipe roofline denominator
+ * with dependent-chain micro-kernels on the context's stream: [0] IMAD.WIDE.U32 with a zero addend, [1] mad.wide.u32
+ * accumulating into a 64-bit addend (IMAD.WIDE + a 64-bit add), [2] DFMA.  bench.py uses them as the integer-pipe roofline denominator
  * of the Poseidon kernels ("an IMAD.WIDE.U32 micro-benchmark peak measured in the same run"). */
-int etp_bench_pipe_rates(etp_ctx *ctx, double rates_out[4]);
+int etp_bench_pipe_rates(etp_ctx *ctx, double rates_out[3]);
 
 /* ---- Fiat-Shamir transcript: plonky2/src/iop/challenger.rs Challenger<GoldilocksField, PoseidonHash> --------------
  * Plain data, owned by the caller: the "challenger state in / out" of every proving entry point below.  The fields are
