@@ -216,6 +216,10 @@ def load_library():
         "etp_fri_commit_phase": (i32, [vp, C.POINTER(Challenger), _u64p, _u64p]),
         "etp_fri_query_rounds": (i32, [vp, C.POINTER(vp), sz, _u64p, sz, _u64p]),
         "etp_fri_free": (None, [vp]),
+        "etp_fri_proof_of_work": (i32, [vp, C.POINTER(Challenger), i32, _u64p]),
+        "etp_shard_compute_quotient_polys_dev": (i32, [vp, i32, _u64p, _u64p, i32, vp]),
+        "etp_shard_eval_at_ext_points": (i32, [vp, _u64p, _u64p, _u64p, _u64p]),
+        "etp_shard_fri_begin": (i32, [vp, C.POINTER(vp), sz, C.POINTER(FriBatch), sz, _u64p, _u64p, C.POINTER(FriParams), pp]),
         "etp_plonk_partial_products_and_zs_dev": (i32, [vp, vp, sz, vp, sz, _u64p, i32, i32, i32, _u64p, _u64p, i32, vp]),
     }
     for name, (res, args) in sig.items():
@@ -225,6 +229,21 @@ def load_library():
     _LIB = L
     L._etp_signatures = sig
     return L
+
+
+def _fri_batches(batches):
+    """[(point (2,), [(oracle_index, polynomial_index)])] -> (etp_fri_batch array, objects to keep alive)."""
+    keep = []
+    arr = (FriBatch * len(batches))()
+    for i, (point, polys) in enumerate(batches):
+        pa = (FriPoly * max(len(polys), 1))()
+        for k, (o, c) in enumerate(polys):
+            pa[k].oracle_index, pa[k].polynomial_index = o, c
+        keep.append(pa)
+        arr[i].point[0], arr[i].point[1] = int(point[0]), int(point[1])
+        arr[i].polynomials = C.cast(pa, C.POINTER(FriPoly))
+        arr[i].n_polynomials = len(polys)
+    return arr, keep
 
 
 def _p(a: np.ndarray):
@@ -330,6 +349,12 @@ class Context:
         return int(out.value)
 
     # ---- starky
+    def fri_proof_of_work(self, challenger: Challenger, proof_of_work_bits: int) -> int:
+        """fri_proof_of_work: grind, observe the witness, draw (and check) the response; returns the witness."""
+        out = np.zeros(1, dtype=np.uint64)
+        self.check(self.L.etp_fri_proof_of_work(self.h, C.byref(challenger), proof_of_work_bits, _p(out)))
+        return int(out[0])
+
     def stark_proof_words(self, table, log_n) -> int:
         return int(self.L.etp_stark_proof_words(self.h, table, log_n))
 
@@ -389,16 +414,7 @@ class Context:
     def prove_openings(self, batches, oracles, challenger: Challenger, params: FriParams) -> np.ndarray:
         """PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params) -> flat FriProof.
         batches: [(point (2,), [(oracle_index, polynomial_index)])] — the FriInstanceInfo's FriBatchInfo list."""
-        keep = []
-        arr = (FriBatch * len(batches))()
-        for i, (point, polys) in enumerate(batches):
-            pa = (FriPoly * max(len(polys), 1))()
-            for k, (o, c) in enumerate(polys):
-                pa[k].oracle_index, pa[k].polynomial_index = o, c
-            keep.append(pa)
-            arr[i].point[0], arr[i].point[1] = int(point[0]), int(point[1])
-            arr[i].polynomials = C.cast(pa, C.POINTER(FriPoly))
-            arr[i].n_polynomials = len(polys)
+        arr, keep = _fri_batches(batches)
         oc = (C.c_size_t * len(oracles))(*[o.n_cols for o in oracles])
         out = np.zeros(int(self.L.etp_fri_proof_words(oc, len(oracles), C.byref(params))), dtype=np.uint64)
         hs = (C.c_void_p * len(oracles))(*[o.h for o in oracles])
@@ -652,11 +668,12 @@ class FriState:
     """The FRI prover step by step (plonky2::fri::prover::fri_committed_trees / fri_prover_query_rounds): commit a layer, get
     its cap, fold with the beta the caller's challenger produced, ... — or the fused commit phase with the challenger."""
 
-    def __init__(self, ctx: Context, values_ptr: int, params: FriParams):
+    def __init__(self, ctx: Context, values_ptr: int, params: FriParams, handle=None):
         self.ctx, self.params = ctx, params
-        h = C.c_void_p()
-        ctx.check(ctx.L.etp_fri_begin(ctx.h, C.c_void_p(values_ptr), C.byref(params), C.byref(h)))
-        self.h = h
+        if handle is None:
+            handle = C.c_void_p()
+            ctx.check(ctx.L.etp_fri_begin(ctx.h, C.c_void_p(values_ptr), C.byref(params), C.byref(handle)))
+        self.h = handle
 
     def commit_layer(self) -> np.ndarray:
         cap = np.zeros((1 << self.params.cap_height, 4), dtype=np.uint64)
@@ -774,6 +791,32 @@ class BatchShard:
         out = np.zeros((max(self.num_local_cols, 1), 1 << self.degree_log), dtype=np.uint64)
         self.ctx.check(self.ctx.L.etp_shard_download_coeffs(self.h, _p(out)))
         return out[:self.num_local_cols]
+
+    def compute_quotient_polys_dev(self, table, public_inputs, alphas, out_ptr: int):
+        """compute_quotient_polys over the split trace on THIS rank (peers' columns over NVLink); out: device matrix of
+        num_challenges * quotient_degree_factor polynomials x n."""
+        pi = _u64(list(public_inputs) + [0])
+        a = _u64(alphas)
+        self.ctx.check(self.ctx.L.etp_shard_compute_quotient_polys_dev(self.h, table, _p(pi), _p(a), a.size, C.c_void_p(out_ptr)))
+
+    def eval_at_ext_points(self, z0, z1):
+        """The local columns' polynomials at z0 and z1 -> two (num_local_cols, 2) arrays."""
+        o0 = np.zeros((max(self.num_local_cols, 1), 2), dtype=np.uint64)
+        o1 = np.zeros_like(o0)
+        self.ctx.check(self.ctx.L.etp_shard_eval_at_ext_points(self.h, _p(_u64(z0)), _p(_u64(z1)), _p(o0), _p(o1)))
+        return o0[:self.num_local_cols], o1[:self.num_local_cols]
+
+    def fri_begin(self, extra_oracles, batches, ys, alpha, params: FriParams) -> "FriState":
+        """The combination step of prove_openings with oracle 0 = this split table, oracles 1.. = `extra_oracles`
+        (PolynomialBatches of this rank).  ys: per batch, the (n_polynomials, 2) claimed openings."""
+        arr, keep = _fri_batches(batches)
+        flat = _u64(np.concatenate([_u64(y).reshape(-1) for y in ys]) if ys else [])
+        hs = (C.c_void_p * max(len(extra_oracles), 1))(*[o.h for o in extra_oracles])
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.L.etp_shard_fri_begin(self.h, hs, len(extra_oracles), arr, len(batches), _p(flat), _p(_u64(alpha)),
+                                                      C.byref(params), C.byref(h)))
+        del keep
+        return FriState(self.ctx, 0, params, handle=h)
 
     def close_peers(self):
         for p in self._opened:

@@ -87,12 +87,13 @@ inline uint64_t hash(const Program& p) {
 
 // CUDA source of the quotient kernel of this program (body between quotient_begin and quotient_end of
 // quotient_rt.cuh).  Straight-line SSA: register allocation and scheduling are ptxas's job.
-inline std::string generate_cuda(const Program& p) {
+inline std::string generate_cuda(const Program& p, bool split_columns = false) {
   std::string s;
   s.reserve(64 * (size_t)p.n_ops + 1024);
   // small programs are fully inlined (as fast as a built-in table); large ones share one copy of the field
   // multiplication and of the consumer so that code size and ptxas time stay bounded
   if (p.n_ops > COMPACT_THRESHOLD_OPS) s += "#define ETP_COMPACT_CODE 1\n";
+  if (split_columns) s += "#define ETP_SPLIT_COLUMNS 1\n";  // trace columns through QuotientParams::trace_cols (etp_shard)
   s += "#include \"quotient_rt.cuh\"\n"
        "extern \"C\" __global__ void __launch_bounds__(128) etp_cprog_quotient(const __grid_constant__ stark::QuotientParams q) {\n"
        "  stark::RowCtx r;\n"

@@ -12,23 +12,8 @@
 //   of the G parts (a 2^h*32-byte all-gather done by the caller over torch.distributed).
 // Same field elements as PolynomialBatch::from_values on the whole table (plonky2/src/fri/oracle.rs):
 // tests compare the assembled cap and the Merkle paths with the unsplit commit.
-#include "ctx.cuh"
+#include "shard.cuh"
 
-struct etp_shard {
-  etp_ctx* ctx;
-  size_t n_cols_total, cps, c0, local_cols;
-  int log_n, rate_bits, cap_height, rank, world;
-  uint64_t* coeffs = nullptr;   // local_cols x n      (cudaMalloc: exportable)
-  uint64_t* lde = nullptr;      // local_cols x L      (cudaMalloc: exportable)
-  uint64_t* levels = nullptr;   // digests of the own rows, level by level, down to the own cap entries
-  const uint64_t* peer[merkle::MAX_SRC] = {};
-  bool committed = false;
-  size_t n() const { return (size_t)1 << log_n; }
-  size_t lde_n() const { return (size_t)1 << (log_n + rate_bits); }
-  size_t rows() const { return lde_n() / world; }
-  size_t row0() const { return rows() * rank; }
-  int local_cap_height() const { int lw = 0; while ((1 << lw) < world) lw++; return cap_height - lw; }
-};
 
 extern "C" size_t etp_shard_cols_per_rank(size_t n_cols_total, int world) {
   if (world <= 0) return 0;

@@ -10,12 +10,14 @@
 #include <time.h>
 
 #include <cstdlib>
+#include <functional>
 #include <memory>
 
 #include "cprog.h"
 #include "ctx.cuh"
 #include "host_field.h"
 #include "plonk_kernels.cuh"
+#include "shard.cuh"
 #include "stark_kernels.cuh"
 
 namespace {
@@ -179,10 +181,11 @@ struct RegisteredTable {
   TableInfo info;
   cprog::Program prog;
   JitKernel kernel;
+  JitKernel kernel_split;  // the same program reading its trace columns through a pointer table (etp_shard), compiled on first use
   uint64_t* d_spec = nullptr;  // the aux spec words on the device (general lookups / CTL), uploaded on first use
 };
 void free_registered_tables(etp_ctx* ctx) {
-  for (auto* t : ctx->tables) { jit_unload(&t->kernel); cudaFree(t->d_spec); delete t; }
+  for (auto* t : ctx->tables) { jit_unload(&t->kernel); jit_unload(&t->kernel_split); cudaFree(t->d_spec); delete t; }
   ctx->tables.clear();
 }
 
@@ -410,10 +413,10 @@ int ext_pow_table(etp_ctx* ctx, gl::Ext z, int bits, DevBuf<uint64_t>& lo, DevBu
 }
 
 // evaluate all polynomials of a batch at z0 and z1: out0/out1 get n_cols ext values
-int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, const stark::ExtPowTable& t1,
-               std::vector<gl::Ext>& out0, std::vector<gl::Ext>& out1) {
-  const uint32_t n = (uint32_t)b->n();
-  const int np = (int)b->n_cols;
+int eval_coeffs(etp_ctx* ctx, const uint64_t* coeffs, size_t n_len, size_t n_cols, const stark::ExtPowTable& t0, const stark::ExtPowTable& t1,
+                std::vector<gl::Ext>& out0, std::vector<gl::Ext>& out1) {
+  const uint32_t n = (uint32_t)n_len;
+  const int np = (int)n_cols;
   out0.assign(np, gl::ext(0, 0));
   out1.assign(np, gl::ext(0, 0));
   if (np == 0) return ETP_OK;
@@ -421,7 +424,7 @@ int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, c
   const unsigned gy = (unsigned)np;
   DevBuf<uint64_t> partial(ctx);
   ETP_TRY(partial.alloc((size_t)gx * np * 4));
-  stark::eval_polys_at_two_points<<<dim3(gx, gy), stark::OPEN_THREADS, 0, ctx->stream>>>(b->coeffs, b->n(), np, n, t0, t1, partial.p);
+  stark::eval_polys_at_two_points<<<dim3(gx, gy), stark::OPEN_THREADS, 0, ctx->stream>>>(coeffs, n_len, np, n, t0, t1, partial.p);
   ETP_LAUNCH_CHECK(ctx);
   std::vector<uint64_t> host((size_t)gx * np * 4);
   ETP_CUDA(ctx, cudaMemcpyAsync(host.data(), partial.p, host.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -437,12 +440,27 @@ int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, c
   return ETP_OK;
 }
 
+int eval_batch(etp_ctx* ctx, const etp_batch* b, const stark::ExtPowTable& t0, const stark::ExtPowTable& t1,
+               std::vector<gl::Ext>& out0, std::vector<gl::Ext>& out1) {
+  return eval_coeffs(ctx, b->coeffs, b->n(), b->n_cols, t0, t1, out0, out1);
+}
+
+// The trace LDE a quotient is computed over: one matrix of this context (a PolynomialBatch), or one device pointer per
+// column (a column-split table: own columns and the peers', read over NVLink).
+struct TraceView {
+  const uint64_t* lde = nullptr;
+  size_t stride = 0;
+  const uint64_t* const* cols_dev = nullptr;  // device array of n_cols column bases, or nullptr
+  size_t n_cols = 0;
+  int log_n = 0, rate_bits = 0;
+};
+
 // n_scalars challenge scalars: lookup challenges [0, NUM_CHALLENGES), then the CTL (beta, gamma) pairs
-int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* scalars, int n_scalars,
+int compute_quotient(etp_ctx* ctx, int table, const TraceView& trace, etp_batch* aux, const uint64_t* scalars, int n_scalars,
                      const uint64_t* pi, const uint64_t* alphas, int n_alphas, uint64_t* out_dev) {
   TableInfo ti;
   if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
-  if (!trace || (int)trace->n_cols != ti.cols) return etp_fail(ctx, ETP_ERR_INVALID, "trace batch has the wrong number of columns");
+  if ((int)trace.n_cols != ti.cols) return etp_fail(ctx, ETP_ERR_INVALID, "trace batch has the wrong number of columns");
   if (n_alphas < 1 || n_alphas > stark::MAX_CHALLENGES) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported number of challenges");
   if (n_scalars < 0 || n_scalars > stark::MAX_CH_SCALARS) return etp_fail(ctx, ETP_ERR_INVALID, "too many challenge scalars");
   const int n_lookup_ch = n_scalars < NUM_CHALLENGES ? n_scalars : NUM_CHALLENGES;
@@ -452,14 +470,15 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
   if (ti.reg && ((int)ti.reg->prog.n_aux != n_aux || (int)ti.reg->prog.n_ch > n_scalars))
     return etp_fail(ctx, ETP_ERR_INVALID, "constraint program expects %u auxiliary columns / %u challenge scalars, got %d / %d",
                     ti.reg->prog.n_aux, ti.reg->prog.n_ch, n_aux, n_scalars);
-  const int log_n = trace->log_n, rate_bits = trace->rate_bits;
+  const int log_n = trace.log_n, rate_bits = trace.rate_bits;
+  const bool split = trace.cols_dev != nullptr;
   const int factor = quotient_factor(ti), qbits = log2_ceil(factor);
   if (qbits > rate_bits)
     return etp_fail(ctx, ETP_ERR_INVALID, "Having constraints of degree higher than the rate is not supported yet.");
   const int log_size = log_n + qbits, log_lde = log_n + rate_bits;
   const size_t size = (size_t)1 << log_size;
   stark::QuotientParams q{};
-  q.trace = trace->lde; q.trace_stride = trace->lde_n();
+  q.trace = trace.lde; q.trace_stride = trace.stride; q.trace_cols = trace.cols_dev;
   q.aux = aux ? aux->lde : nullptr; q.aux_stride = aux ? aux->lde_n() : 0;
   q.log_lde = log_lde; q.log_size = log_size; q.step_log = rate_bits - qbits; q.next_step = 1 << qbits;
   ETP_TRY(get_pow_table(ctx, gl::root_of_unity(log_size), log_size, gl::GENERATOR, &q.coset));
@@ -510,13 +529,21 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
   ETP_CUDA(ctx, cudaMemcpyAsync(apow.p, apow_host.data(), apow_host.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   q.alpha_pows = apow.p;
   if (ti.reg) {
+    if (split && !ti.reg->kernel_split.kernel) {
+      std::vector<char> cubin;
+      std::string log;
+      ETP_TRY(jit_compile(ctx, cprog::generate_cuda(ti.reg->prog, true), &cubin, &log));
+      ETP_TRY(jit_load(ctx, cubin, "etp_cprog_quotient", &ti.reg->kernel_split));
+    }
     void* args[] = {(void*)&q};
-    ETP_CUDA(ctx, cudaLaunchKernel((const void*)ti.reg->kernel.kernel, dim3(gb), dim3(128), args, 0, ctx->stream));
+    ETP_CUDA(ctx, cudaLaunchKernel((const void*)(split ? ti.reg->kernel_split : ti.reg->kernel).kernel, dim3(gb), dim3(128), args, 0, ctx->stream));
     ctx->launches++;
   } else if (table == ETP_TABLE_FIBONACCI) {
-    stark::quotient_kernel<0><<<gb, 128, 0, ctx->stream>>>(q);
+    if (split) stark::quotient_kernel<0, true><<<gb, 128, 0, ctx->stream>>>(q);
+    else stark::quotient_kernel<0><<<gb, 128, 0, ctx->stream>>>(q);
   } else {
-    stark::quotient_kernel<1><<<gb, 128, 0, ctx->stream>>>(q);
+    if (split) stark::quotient_kernel<1, true><<<gb, 128, 0, ctx->stream>>>(q);
+    else stark::quotient_kernel<1><<<gb, 128, 0, ctx->stream>>>(q);
   }
   ETP_LAUNCH_CHECK(ctx);
   // coset_ifft(7) of each challenge's values, then split into `factor` chunks of n coefficients.
@@ -534,6 +561,14 @@ int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, 
     ETP_CUDA(ctx, cudaMemcpyAsync(out_dev + (size_t)j * factor * n, coeffs.p + (size_t)j * size, (size_t)factor * n * 8,
                                   cudaMemcpyDeviceToDevice, ctx->stream));
   return ETP_OK;
+}
+
+int compute_quotient(etp_ctx* ctx, int table, etp_batch* trace, etp_batch* aux, const uint64_t* scalars, int n_scalars,
+                     const uint64_t* pi, const uint64_t* alphas, int n_alphas, uint64_t* out_dev) {
+  if (!trace) return etp_fail(ctx, ETP_ERR_INVALID, "trace batch has the wrong number of columns");
+  TraceView tv;
+  tv.lde = trace->lde; tv.stride = trace->lde_n(); tv.n_cols = trace->n_cols; tv.log_n = trace->log_n; tv.rate_bits = trace->rate_bits;
+  return compute_quotient(ctx, table, tv, aux, scalars, n_scalars, pi, alphas, n_alphas, out_dev);
 }
 
 int pow_grind(etp_ctx* ctx, const uint64_t state[12], int pos, int bits, uint64_t* witness) {
@@ -795,6 +830,19 @@ int fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracl
   return ETP_OK;
 }
 
+// fri_proof_of_work: the smallest witness whose response has `bits` leading zeros; the challenger observes the witness
+// and the response is drawn from it (what the verifier's challenger does).
+int fri_proof_of_work(etp_ctx* ctx, hostf::Challenger& ch, int bits, uint64_t* witness) {
+  uint64_t st[12];
+  memcpy(st, ch.sponge_state, sizeof st);
+  for (uint32_t i = 0; i < ch.input_len; i++) st[i] = ch.input_buffer[i];
+  ETP_TRY(pow_grind(ctx, st, (int)ch.input_len, bits, witness));
+  ch.observe(*witness);
+  const uint64_t pow_response = ch.get();
+  if (bits && (pow_response >> (64 - bits)) != 0) return etp_fail(ctx, ETP_ERR_PROOF, "proof of work response mismatch");
+  return ETP_OK;
+}
+
 // fri_proof: commit phase, proof of work, query rounds.  out: flat FriProof (fri_proof_words)
 int fri_proof(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracles, hostf::Challenger& ch, uint64_t* out, PhaseTimer* timer) {
   etp_ctx* ctx = s->ctx;
@@ -806,15 +854,8 @@ int fri_proof(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracles, hos
   ETP_TRY(fri_commit_phase(s, ch, w, &final_coeffs));
   w += cap_words * p.n_reductions;
   if (timer) timer->mark("fold codewords in the commitment phase");
-  // fri_proof_of_work
-  uint64_t st[12];
-  memcpy(st, ch.sponge_state, sizeof st);
-  for (uint32_t i = 0; i < ch.input_len; i++) st[i] = ch.input_buffer[i];
   uint64_t pow_witness = 0;
-  ETP_TRY(pow_grind(ctx, st, (int)ch.input_len, p.proof_of_work_bits, &pow_witness));
-  ch.observe(pow_witness);
-  const uint64_t pow_response = ch.get();
-  if (p.proof_of_work_bits && (pow_response >> (64 - p.proof_of_work_bits)) != 0) return etp_fail(ctx, ETP_ERR_PROOF, "proof of work response mismatch");
+  ETP_TRY(fri_proof_of_work(ctx, ch, p.proof_of_work_bits, &pow_witness));
   if (timer) timer->mark("find proof-of-work witness");
   // fri_prover_query_rounds
   std::vector<uint64_t> qidx(p.num_query_rounds);
@@ -835,19 +876,16 @@ void launch_combine(etp_ctx* ctx, const stark::CombineParams& c, size_t lde_n, b
   else stark::combine_values<B><<<blocks_for(lde_n, 128), 128, 0, ctx->stream>>>(c);
 }
 
-// PolynomialBatch::prove_openings in evaluation form over the LDE coset, then fri_proof.  `ys`: the claimed value of every
-// batch polynomial at the batch point when the caller already has them (the openings of a STARK), else nullptr (they are
-// then evaluated here from the coefficients).
-int prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches, etp_batch* const* oracles, size_t n_oracles,
-                   hostf::Challenger& ch, const etp_fri_params& fp, const std::vector<std::vector<gl::Ext>>* ys, uint64_t* out, PhaseTimer* timer) {
-  ETP_TRY(check_fri_params(ctx, fp));
+// The combination step of prove_openings on the LDE coset: values[p] = sum_b alpha^(shift_b) (sum_k alpha^k f_{b,k}(x_p) - y_b) / (x_p - z_b)
+// (ext, interleaved, bit-reversed order).  `col(oracle, poly)` resolves a FriPolynomialInfo to the device pointer of that
+// polynomial's LDE column (bit-reversed rows, 2^(log_n + rate_bits) words) or nullptr — a PolynomialBatch of this context,
+// or a column of a peer GPU's shard mapped over NVLink (column-split tables).
+typedef std::function<const uint64_t*(uint32_t, uint32_t)> ColResolver;
+int combine_on_lde(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches, const ColResolver& col, int log_n, int rate_bits, gl::Ext alpha,
+                   const std::vector<std::vector<gl::Ext>>& ys, uint64_t* values) {
   if (n_batches < 1 || n_batches > (size_t)stark::MAX_FRI_BATCHES) return etp_fail(ctx, ETP_ERR_INVALID, "between 1 and %d FRI batches are supported", stark::MAX_FRI_BATCHES);
-  const int log_n = fp.degree_bits, log_lde = log_n + fp.rate_bits;
+  const int log_lde = log_n + rate_bits;
   const size_t lde_n = (size_t)1 << log_lde;
-  for (size_t o = 0; o < n_oracles; o++)
-    if (!oracles[o] || oracles[o]->ctx != ctx || oracles[o]->log_n != log_n || oracles[o]->rate_bits != fp.rate_bits || oracles[o]->cap_height != fp.cap_height)
-      return etp_fail(ctx, ETP_ERR_INVALID, "FRI oracle %zu does not match the FRI parameters", o);
-  const gl::Ext alpha = ch.get_ext();
   // unique columns in order of first appearance, with their alpha power per batch
   std::vector<stark::CombineCol> cols;
   std::map<std::pair<uint32_t, uint32_t>, int> where;
@@ -856,14 +894,13 @@ int prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
     max_count = batches[b].n_polynomials > max_count ? batches[b].n_polynomials : max_count;
     for (size_t k = 0; k < batches[b].n_polynomials; k++) {
       const etp_fri_poly fpi = batches[b].polynomials[k];
-      if (fpi.oracle_index >= n_oracles || fpi.polynomial_index >= oracles[fpi.oracle_index]->n_cols)
-        return etp_fail(ctx, ETP_ERR_INVALID, "FRI batch %zu: polynomial (%u, %u) does not exist", b, fpi.oracle_index, fpi.polynomial_index);
       auto key = std::make_pair(fpi.oracle_index, fpi.polynomial_index);
       auto it = where.find(key);
       int u;
       if (it == where.end()) {
         stark::CombineCol cc{};
-        cc.ptr = oracles[fpi.oracle_index]->lde + (size_t)fpi.polynomial_index * lde_n;
+        cc.ptr = col(fpi.oracle_index, fpi.polynomial_index);
+        if (!cc.ptr) return etp_fail(ctx, ETP_ERR_INVALID, "FRI batch %zu: polynomial (%u, %u) does not exist", b, fpi.oracle_index, fpi.polynomial_index);
         for (int j = 0; j < stark::MAX_FRI_BATCHES; j++) cc.idx[j] = stark::COMBINE_NONE;
         cols.push_back(cc);
         u = (int)cols.size() - 1;
@@ -890,6 +927,66 @@ int prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
     gl::Ext cur = gl::ext(1, 0);
     for (size_t k = 0; k <= max_count; k++) { cur = gl::ecanon(cur); apow_e[k] = cur; apow[2 * k] = cur.c0; apow[2 * k + 1] = cur.c1; cur = gl::emul(cur, alpha); }
   }
+  {
+    size_t later = 0;
+    for (size_t b = n_batches; b-- > 0;) {
+      c.z[b] = gl::ecanon(gl::ext(batches[b].point[0], batches[b].point[1]));
+      c.seven_zc1_sq[b] = gl::canon(gl::mul(7, gl::mul(c.z[b].c1, c.z[b].c1)));
+      gl::Ext y = gl::ext(0, 0);
+      if (ys[b].size() != batches[b].n_polynomials) return etp_fail(ctx, ETP_ERR_INVALID, "opening count of batch %zu does not match its polynomial list", b);
+      for (size_t k = 0; k < batches[b].n_polynomials; k++) y = gl::eadd(y, gl::emul(apow_e[k], ys[b][k]));
+      c.y[b] = gl::ecanon(y);
+      c.shift[b] = gl::ecanon(gl::epow(alpha, later));
+      later += batches[b].n_polynomials;
+    }
+  }
+  DevBuf<uint64_t> d_apow(ctx), den(ctx), partial(ctx);
+  DevBuf<stark::CombineCol> d_cols(ctx);
+  ETP_TRY(d_apow.alloc(apow.size()));
+  ETP_TRY(den.alloc(n_batches * lde_n));
+  ETP_TRY(d_cols.alloc(cols.size() ? cols.size() : 1));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(stark::CombineCol), cudaMemcpyHostToDevice, ctx->stream));
+  ETP_TRY(get_pow_table(ctx, gl::root_of_unity(log_lde), log_lde, gl::GENERATOR, &c.coset));
+  c.cols = d_cols.p; c.alpha_pows = d_apow.p; c.den = den.p; c.out = values;
+  ETP_TRY(reset_zero_flag(ctx));
+  stark::combine_norms<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(c);
+  ETP_LAUNCH_CHECK(ctx);
+  ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, n_batches * lde_n));
+  // few rows, many columns: one thread per point cannot fill the machine, so the column sums are split into chunks
+  const int B = n_batches <= 2 ? 2 : (n_batches == 3 ? 3 : 4);
+  if (c.n_cols > 256 && lde_n * 4 <= (size_t)1 << 20) {
+    c.col_chunk = 64;
+    c.n_chunks = (c.n_cols + c.col_chunk - 1) / c.col_chunk;
+    ETP_TRY(partial.alloc((size_t)c.n_chunks * lde_n * 2 * B));
+    c.partial = partial.p;
+    if (B == 2) launch_combine<2>(ctx, c, lde_n, true); else if (B == 3) launch_combine<3>(ctx, c, lde_n, true); else launch_combine<4>(ctx, c, lde_n, true);
+    ETP_LAUNCH_CHECK(ctx);
+  }
+  if (B == 2) launch_combine<2>(ctx, c, lde_n, false); else if (B == 3) launch_combine<3>(ctx, c, lde_n, false); else launch_combine<4>(ctx, c, lde_n, false);
+  ETP_LAUNCH_CHECK(ctx);
+  return check_zero_flag(ctx, "an opening point lies on the LDE coset");  // also: apow / cols (host) stay alive until here
+}
+
+// PolynomialBatch::prove_openings in evaluation form over the LDE coset, then fri_proof.  `ys`: the claimed value of every
+// batch polynomial at the batch point when the caller already has them (the openings of a STARK), else nullptr (they are
+// then evaluated here from the coefficients).
+int prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches, etp_batch* const* oracles, size_t n_oracles,
+                   hostf::Challenger& ch, const etp_fri_params& fp, const std::vector<std::vector<gl::Ext>>* ys, uint64_t* out, PhaseTimer* timer) {
+  ETP_TRY(check_fri_params(ctx, fp));
+  if (n_batches < 1 || n_batches > (size_t)stark::MAX_FRI_BATCHES) return etp_fail(ctx, ETP_ERR_INVALID, "between 1 and %d FRI batches are supported", stark::MAX_FRI_BATCHES);
+  const int log_n = fp.degree_bits, log_lde = log_n + fp.rate_bits;
+  const size_t lde_n = (size_t)1 << log_lde;
+  for (size_t o = 0; o < n_oracles; o++)
+    if (!oracles[o] || oracles[o]->ctx != ctx || oracles[o]->log_n != log_n || oracles[o]->rate_bits != fp.rate_bits || oracles[o]->cap_height != fp.cap_height)
+      return etp_fail(ctx, ETP_ERR_INVALID, "FRI oracle %zu does not match the FRI parameters", o);
+  for (size_t b = 0; b < n_batches; b++)
+    for (size_t k = 0; k < batches[b].n_polynomials; k++) {
+      const etp_fri_poly fpi = batches[b].polynomials[k];
+      if (fpi.oracle_index >= n_oracles || fpi.polynomial_index >= oracles[fpi.oracle_index]->n_cols)
+        return etp_fail(ctx, ETP_ERR_INVALID, "FRI batch %zu: polynomial (%u, %u) does not exist", b, fpi.oracle_index, fpi.polynomial_index);
+    }
+  const gl::Ext alpha = ch.get_ext();
   std::vector<std::vector<gl::Ext>> ys_local;
   if (!ys) {  // evaluate f_k(z_b) from the coefficients: one kernel per (oracle, pair of points)
     ys_local.resize(n_batches);
@@ -913,52 +1010,13 @@ int prove_openings(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
     }
     ys = &ys_local;
   }
-  {
-    size_t later = 0;
-    for (size_t b = n_batches; b-- > 0;) {
-      c.z[b] = gl::ecanon(gl::ext(batches[b].point[0], batches[b].point[1]));
-      c.seven_zc1_sq[b] = gl::canon(gl::mul(7, gl::mul(c.z[b].c1, c.z[b].c1)));
-      gl::Ext y = gl::ext(0, 0);
-      if ((*ys)[b].size() != batches[b].n_polynomials) return etp_fail(ctx, ETP_ERR_STATE, "internal error: opening count mismatch");
-      for (size_t k = 0; k < batches[b].n_polynomials; k++) y = gl::eadd(y, gl::emul(apow_e[k], (*ys)[b][k]));
-      c.y[b] = gl::ecanon(y);
-      c.shift[b] = gl::ecanon(gl::epow(alpha, later));
-      later += batches[b].n_polynomials;
-    }
-  }
   uint64_t* values = nullptr;
   ETP_TRY(dev_alloc(ctx, 2 * lde_n * 8, (void**)&values));
   etp_fri_state* st = nullptr;
   ETP_TRY(fri_begin_owned(ctx, values, fp, &st));
   std::unique_ptr<etp_fri_state> guard(st);
-  {
-    DevBuf<uint64_t> d_apow(ctx), den(ctx), partial(ctx);
-    DevBuf<stark::CombineCol> d_cols(ctx);
-    ETP_TRY(d_apow.alloc(apow.size()));
-    ETP_TRY(den.alloc(n_batches * lde_n));
-    ETP_TRY(d_cols.alloc(cols.size() ? cols.size() : 1));
-    ETP_CUDA(ctx, cudaMemcpyAsync(d_apow.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(stark::CombineCol), cudaMemcpyHostToDevice, ctx->stream));
-    ETP_TRY(get_pow_table(ctx, gl::root_of_unity(log_lde), log_lde, gl::GENERATOR, &c.coset));
-    c.cols = d_cols.p; c.alpha_pows = d_apow.p; c.den = den.p; c.out = values;
-    ETP_TRY(reset_zero_flag(ctx));
-    stark::combine_norms<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(c);
-    ETP_LAUNCH_CHECK(ctx);
-    ETP_TRY(batch_inverse_dev(ctx, den.p, den.p, n_batches * lde_n));
-    // few rows, many columns: one thread per point cannot fill the machine, so the column sums are split into chunks
-    const int B = n_batches <= 2 ? 2 : (n_batches == 3 ? 3 : 4);
-    if (c.n_cols > 256 && lde_n * 4 <= (size_t)1 << 20) {
-      c.col_chunk = 64;
-      c.n_chunks = (c.n_cols + c.col_chunk - 1) / c.col_chunk;
-      ETP_TRY(partial.alloc((size_t)c.n_chunks * lde_n * 2 * B));
-      c.partial = partial.p;
-      if (B == 2) launch_combine<2>(ctx, c, lde_n, true); else if (B == 3) launch_combine<3>(ctx, c, lde_n, true); else launch_combine<4>(ctx, c, lde_n, true);
-      ETP_LAUNCH_CHECK(ctx);
-    }
-    if (B == 2) launch_combine<2>(ctx, c, lde_n, false); else if (B == 3) launch_combine<3>(ctx, c, lde_n, false); else launch_combine<4>(ctx, c, lde_n, false);
-    ETP_LAUNCH_CHECK(ctx);
-    ETP_TRY(check_zero_flag(ctx, "an opening point lies on the LDE coset"));  // also: apow / cols (host) stay alive until here
-  }
+  const ColResolver col = [&](uint32_t o, uint32_t k) -> const uint64_t* { return oracles[o]->lde + (size_t)k * lde_n; };
+  ETP_TRY(combine_on_lde(ctx, batches, n_batches, col, log_n, fp.rate_bits, alpha, *ys, values));
   if (timer) timer->mark("compute openings proof: combine on the LDE domain");
   return fri_proof(st, oracles, n_oracles, ch, out, timer);
 }
@@ -1411,6 +1469,16 @@ extern "C" int etp_fri_commit_phase(etp_fri_state* s, etp_challenger* challenger
   *challenger = ch;
   return ETP_OK;
 }
+extern "C" int etp_fri_proof_of_work(etp_ctx* ctx, etp_challenger* challenger, int proof_of_work_bits, uint64_t* witness_out) {
+  etp_bind(ctx);
+  if (!ctx || !witness_out) return ETP_ERR_INVALID;
+  if (!challenger_ok(challenger)) return etp_fail(ctx, ETP_ERR_INVALID, "bad challenger state");
+  if (proof_of_work_bits < 0 || proof_of_work_bits > 40) return etp_fail(ctx, ETP_ERR_INVALID, "unsupported proof_of_work_bits");
+  hostf::Challenger ch(*challenger);
+  ETP_TRY(fri_proof_of_work(ctx, ch, proof_of_work_bits, witness_out));
+  *challenger = ch;
+  return ETP_OK;
+}
 extern "C" int etp_fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles, size_t n_oracles, const uint64_t* x_indices, size_t n_indices,
                                     uint64_t* out) {
   etp_bind(s ? s->ctx : nullptr);
@@ -1420,6 +1488,99 @@ extern "C" int etp_fri_query_rounds(etp_fri_state* s, etp_batch* const* oracles,
 extern "C" void etp_fri_free(etp_fri_state* s) {
   etp_bind(s ? s->ctx : nullptr);
   delete s;
+}
+
+// ---- quotient / openings / FRI over a column-split table (etp_shard) ------------------------------------------
+// The rank that calls these (the "leader" of a column-split proof) reads the trace columns where they live: its own HBM
+// or, through the mappings of etp_shard_set_peer, a peer's over NVLink — the same fused access as the leaf hashing.
+static int shard_column_table(etp_shard* s, DevBuf<uint64_t>& d_cols) {
+  etp_ctx* ctx = s->ctx;
+  std::vector<uint64_t> cols(s->n_cols_total);
+  for (size_t c = 0; c < s->n_cols_total; c++) {
+    const uint64_t* p = s->column(c);
+    if (!p) return etp_fail(ctx, ETP_ERR_STATE, "shard: LDE of rank %zu not mapped (etp_shard_set_peer)", c / s->cps);
+    cols[c] = (uint64_t)(uintptr_t)p;
+  }
+  ETP_TRY(d_cols.alloc(cols.size()));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+extern "C" int etp_shard_compute_quotient_polys_dev(etp_shard* s, int table, const uint64_t* public_inputs, const uint64_t* alphas, int n_alphas,
+                                                    uint64_t* out_dev) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !alphas || !out_dev) return ETP_ERR_INVALID;
+  etp_ctx* ctx = s->ctx;
+  TableInfo ti;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (ti.lookup() || ti.ctl()) return etp_fail(ctx, ETP_ERR_INVALID, "column-split proofs of tables with lookups / CTLs are not supported yet");
+  if (ti.n_pi && !public_inputs) return ETP_ERR_INVALID;
+  DevBuf<uint64_t> d_cols(ctx);
+  ETP_TRY(shard_column_table(s, d_cols));
+  TraceView tv;
+  tv.cols_dev = (const uint64_t* const*)d_cols.p; tv.n_cols = s->n_cols_total; tv.log_n = s->log_n; tv.rate_bits = s->rate_bits;
+  uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
+  ETP_TRY(compute_quotient(ctx, table, tv, nullptr, zero, 0, public_inputs ? public_inputs : zero, alphas, n_alphas, out_dev));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // d_cols is read by the kernel
+  return ETP_OK;
+}
+
+extern "C" int etp_shard_eval_at_ext_points(etp_shard* s, const uint64_t z0[2], const uint64_t z1[2], uint64_t* out0, uint64_t* out1) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !z0 || !z1 || ((!out0 || !out1) && s->local_cols)) return ETP_ERR_INVALID;
+  if (s->local_cols == 0) return ETP_OK;
+  etp_ctx* ctx = s->ctx;
+  DevBuf<uint64_t> l0(ctx), h0(ctx), l1(ctx), h1(ctx);
+  stark::ExtPowTable t0, t1;
+  ETP_TRY(ext_pow_table(ctx, gl::ecanon(gl::ext(z0[0], z0[1])), s->log_n, l0, h0, &t0));
+  ETP_TRY(ext_pow_table(ctx, gl::ecanon(gl::ext(z1[0], z1[1])), s->log_n, l1, h1, &t1));
+  std::vector<gl::Ext> e0, e1;
+  ETP_TRY(eval_coeffs(ctx, s->coeffs, s->n(), s->local_cols, t0, t1, e0, e1));
+  for (size_t c = 0; c < s->local_cols; c++) {
+    out0[2 * c] = e0[c].c0; out0[2 * c + 1] = e0[c].c1;
+    out1[2 * c] = e1[c].c0; out1[2 * c + 1] = e1[c].c1;
+  }
+  return ETP_OK;
+}
+
+extern "C" int etp_shard_fri_begin(etp_shard* s, etp_batch* const* extra_oracles, size_t n_extra, const etp_fri_batch* batches, size_t n_batches,
+                                   const uint64_t* ys, const uint64_t alpha[2], const etp_fri_params* params, etp_fri_state** out) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || (!extra_oracles && n_extra) || !batches || !ys || !alpha || !params || !out) return ETP_ERR_INVALID;
+  etp_ctx* ctx = s->ctx;
+  *out = nullptr;
+  ETP_TRY(check_fri_params(ctx, *params));
+  if (params->degree_bits != s->log_n || params->rate_bits != s->rate_bits || params->cap_height != s->cap_height)
+    return etp_fail(ctx, ETP_ERR_INVALID, "the FRI parameters do not match the shard");
+  for (size_t o = 0; o < n_extra; o++)
+    if (!extra_oracles[o] || extra_oracles[o]->ctx != ctx || extra_oracles[o]->log_n != s->log_n || extra_oracles[o]->rate_bits != s->rate_bits ||
+        extra_oracles[o]->cap_height != s->cap_height)
+      return etp_fail(ctx, ETP_ERR_INVALID, "FRI oracle %zu does not match the FRI parameters", o + 1);
+  if (n_batches < 1 || n_batches > (size_t)stark::MAX_FRI_BATCHES) return etp_fail(ctx, ETP_ERR_INVALID, "between 1 and %d FRI batches are supported", stark::MAX_FRI_BATCHES);
+  std::vector<std::vector<gl::Ext>> yv(n_batches);
+  {
+    const uint64_t* y = ys;
+    for (size_t b = 0; b < n_batches; b++) {
+      if (!batches[b].polynomials && batches[b].n_polynomials) return ETP_ERR_INVALID;
+      yv[b].resize(batches[b].n_polynomials);
+      for (size_t k = 0; k < batches[b].n_polynomials; k++, y += 2) yv[b][k] = gl::ecanon(gl::ext(y[0], y[1]));
+    }
+  }
+  const size_t lde_n = s->lde_n();
+  const ColResolver col = [&](uint32_t o, uint32_t k) -> const uint64_t* {
+    if (o == 0) return s->column(k);
+    if (o - 1 >= n_extra || k >= extra_oracles[o - 1]->n_cols) return nullptr;
+    return extra_oracles[o - 1]->lde + (size_t)k * lde_n;
+  };
+  uint64_t* values = nullptr;
+  ETP_TRY(dev_alloc(ctx, 2 * lde_n * 8, (void**)&values));
+  etp_fri_state* st = nullptr;
+  ETP_TRY(fri_begin_owned(ctx, values, *params, &st));
+  std::unique_ptr<etp_fri_state> guard(st);
+  ETP_TRY(combine_on_lde(ctx, batches, n_batches, col, s->log_n, s->rate_bits, gl::ecanon(gl::ext(alpha[0], alpha[1])), yv, values));
+  *out = guard.release();
+  return ETP_OK;
 }
 
 extern "C" size_t etp_stark_proof_words(const etp_ctx* ctx, int table, int log_n) {

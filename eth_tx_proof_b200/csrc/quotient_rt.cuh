@@ -64,6 +64,9 @@ struct Consumer {
 struct QuotientParams {
   const uint64_t* trace;  // LDE, bit-reversed rows
   size_t trace_stride;
+  // column-split tables (etp_shard): the LDE base of every trace column, in this GPU's HBM or in a peer's (read over
+  // NVLink); used instead of trace / trace_stride by the kernels compiled with SPLIT
+  const uint64_t* const* trace_cols;
   const uint64_t* aux;
   size_t aux_stride;
   int log_lde;      // degree_bits + rate_bits
@@ -87,14 +90,24 @@ struct QuotientParams {
 
 
 // per-thread row context: position p of the quotient coset inside the LDE, its "next" row, and the consumer
-struct RowCtx {
+template <bool SPLIT>
+struct RowCtxT {
   uint32_t p, p_next, i;
   Consumer cs;
-  __device__ __forceinline__ uint64_t lv(const QuotientParams& q, int c) const { return __ldg(q.trace + (size_t)c * q.trace_stride + p); }
-  __device__ __forceinline__ uint64_t nv(const QuotientParams& q, int c) const { return __ldg(q.trace + (size_t)c * q.trace_stride + p_next); }
+  __device__ __forceinline__ const uint64_t* col(const QuotientParams& q, int c) const {
+    if (SPLIT) return (const uint64_t*)__ldg((const unsigned long long*)q.trace_cols + c);
+    return q.trace + (size_t)c * q.trace_stride;
+  }
+  __device__ __forceinline__ uint64_t lv(const QuotientParams& q, int c) const { return __ldg(col(q, c) + p); }
+  __device__ __forceinline__ uint64_t nv(const QuotientParams& q, int c) const { return __ldg(col(q, c) + p_next); }
   __device__ __forceinline__ uint64_t la(const QuotientParams& q, int c) const { return __ldg(q.aux + (size_t)c * q.aux_stride + p); }
   __device__ __forceinline__ uint64_t na(const QuotientParams& q, int c) const { return __ldg(q.aux + (size_t)c * q.aux_stride + p_next); }
 };
+#if defined(ETP_SPLIT_COLUMNS)
+typedef RowCtxT<true> RowCtx;
+#else
+typedef RowCtxT<false> RowCtx;
+#endif
 // Block order.  Position p = (H << 7) | t (t = thread) holds point index i = (bitrev_7(t) << m) | bitrev_m(H), m = log_size - 7,
 // so the "next" row i + next_step of EVERY thread of a block lies in the block whose low index bits are I + next_step,
 // I = bitrev_m(H).  Blocks are therefore issued along the chains I, I + next_step, I + 2 next_step, ...: the rows block b
@@ -108,7 +121,8 @@ __device__ __forceinline__ uint32_t quotient_block_position(const QuotientParams
   const uint32_t I = ((b << qb) & ((1u << m) - 1)) | (b >> (m - qb));
   return (gl::bitrev32(I, m) << 7) | threadIdx.x;
 }
-__device__ __forceinline__ bool quotient_begin(const QuotientParams& q, RowCtx& r) {
+template <bool SPLIT>
+__device__ __forceinline__ bool quotient_begin(const QuotientParams& q, RowCtxT<SPLIT>& r) {
   r.p = quotient_block_position(q);
   const uint32_t size = 1u << q.log_size;
   if (r.p >= size) return false;
@@ -128,7 +142,8 @@ __device__ __forceinline__ bool quotient_begin(const QuotientParams& q, RowCtx& 
   r.cs.lagrange_last = q.lag_last[r.p];
   return true;
 }
-__device__ __forceinline__ void quotient_end(const QuotientParams& q, const RowCtx& r) {
+template <bool SPLIT>
+__device__ __forceinline__ void quotient_end(const QuotientParams& q, const RowCtxT<SPLIT>& r) {
   const uint32_t size = 1u << q.log_size;
   const uint64_t dinv = q.zh_inv[r.i & (q.next_step - 1)];
 #pragma unroll

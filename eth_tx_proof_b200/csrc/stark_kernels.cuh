@@ -107,10 +107,10 @@ struct Table<1> {
 
 // One thread per position p of the quotient coset inside the LDE (p < size): local row = LDE row p,
 // next row = the row of point index k + next_step*step.
-template <int TABLE>
+template <int TABLE, bool SPLIT = false>
 static __global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotientParams q) {
   using T = Table<TABLE>;
-  RowCtx r;
+  RowCtxT<SPLIT> r;
   if (!quotient_begin(q, r)) return;
   uint64_t lv[T::COLS], nv[T::COLS];
 #pragma unroll

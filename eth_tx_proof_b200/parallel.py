@@ -122,6 +122,190 @@ def finish_column_split(shard):
     shard.close_peers()
 
 
+# ---- proof of ONE column-split table (starky prove() for a table without lookups / CTLs) --------------------------
+P = 0xFFFFFFFF00000001
+STARK_RATE_BITS, STARK_CAP_HEIGHT, STARK_POW_BITS, STARK_NUM_QUERIES, STARK_NUM_CHALLENGES = 1, 4, 16, 84, 2
+
+
+def _ext_mul(a, b):
+    """GoldilocksField quadratic extension, X^2 = 7."""
+    return [(a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P]
+
+
+class ThreadComm:
+    """all_gather between the threads of ONE process, each driving one shard (a context per GPU, or several contexts on
+    one GPU in the tests): `comm = ThreadComm(world)`, rank r calls `comm.rank(r).all_gather(obj)`."""
+
+    def __init__(self, world: int):
+        import threading
+
+        self.world = world
+        self._slots = [None] * world
+        self._barrier = threading.Barrier(world)
+
+    def rank(self, r: int):
+        outer = self
+
+        class _Rank:
+            def all_gather(self, obj):
+                outer._slots[r] = obj
+                outer._barrier.wait()
+                out = list(outer._slots)
+                outer._barrier.wait()
+                return out
+
+        return _Rank()
+
+
+def _all_gather(obj, comm=None):
+    if comm is not None:
+        return comm.all_gather(obj)
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = (), leader: int = None, timings: dict = None, comm=None):
+    """starky::prover::prove for ONE table whose trace is column-split over the ranks (call on every rank, after
+    `commit_column_split(shard, ...)` returned the trace `cap`).  Returns the proof words ("B200STK2", the layout of
+    `Context.stark_prove`) on the leader rank and None on the others; for the same trace it is word for word the proof
+    one GPU produces.
+
+    Who does what.  Every rank keeps only its columns (coefficients + LDE) and its leaf rows' Merkle subtrees.  The
+    leader (default: the last rank, which owns the fewest columns) runs the transcript and every step that needs whole
+    rows — the quotient, the FRI combination — reading the peers' LDE columns in place over NVLink (the mappings of the
+    commit); the openings at zeta and g*zeta are evaluated where the coefficients live and gathered (2 x 16 bytes per
+    column); the Merkle paths of the queried trace rows come from the ranks that own those rows.  Nothing of the trace is
+    ever copied between GPUs as a whole.  Tables with lookups / CTLs are refused by the library (their auxiliary columns
+    need whole trace rows on one GPU).  `comm`: an object with all_gather(obj) -> list (ThreadComm.rank(r)) when the ranks
+    are threads of one process; default: the torch.distributed default group."""
+    import time
+
+    import numpy as np
+
+    from .api import Challenger, EtpError, FriParams, PolynomialBatch
+    from . import wire
+
+    ctx, rank, world = shard.ctx, shard.rank, shard.world
+    leader = world - 1 if leader is None else leader
+    log_n, n_cols = shard.degree_log, shard.n_cols_total
+    if shard.rate_bits != STARK_RATE_BITS or shard.cap_height != STARK_CAP_HEIGHT:
+        raise ValueError("a STARK proof needs the shard committed with rate_bits 1 and cap_height 4 (StarkConfig::standard_fast_config)")
+    n, lde_n = 1 << log_n, 1 << (log_n + STARK_RATE_BITS)
+    L = ctx.L
+    if L.etp_table_num_columns(ctx.h, table) != n_cols:
+        raise ValueError("the table does not have the shard's number of columns")
+    n_pi = int(L.etp_table_num_public_inputs(ctx.h, table))
+    if len(public_inputs) < n_pi:
+        raise ValueError("too few public inputs")
+    pi = [int(x) % P for x in public_inputs[:n_pi]]
+    n_quot = int(L.etp_table_quotient_degree_factor(ctx.h, table)) * STARK_NUM_CHALLENGES
+    fp = FriParams.make(log_n, STARK_RATE_BITS, STARK_CAP_HEIGHT, STARK_POW_BITS, STARK_NUM_QUERIES)
+    cap = np.asarray(cap, dtype=np.uint64).reshape(-1, 4)
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            ctx.synchronize()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
+
+    # ---- leader: transcript up to zeta; quotient over the split trace; quotient commitment
+    ch = quot = None
+    msg = None
+    if rank == leader:
+        import ctypes as C
+
+        ch = Challenger()
+        ch.observe(pi)
+        ch.observe_cap(cap)
+        alphas = ch.get_n_challenges(STARK_NUM_CHALLENGES)
+        d = C.c_void_p()
+        ctx.check(L.etp_dev_alloc(ctx.h, n_quot * n * 8, C.byref(d)))
+        try:
+            shard.compute_quotient_polys_dev(table, pi, alphas, d.value)
+            mark("compute quotient polys (trace columns over NVLink)")
+            quot = PolynomialBatch.from_coeffs_dev(ctx, d.value, n, n_quot, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
+        finally:
+            L.etp_dev_free(ctx.h, d)
+        mark("quotient polys commit")
+        ch.observe_cap(quot.cap)
+        zeta = [int(x) for x in ch.get_extension_challenge()]
+        zp = zeta
+        for _ in range(log_n):
+            zp = _ext_mul(zp, zp)
+        g = pow(1753635133440165772, 1 << (32 - log_n), P)
+        msg = {"zeta": zeta, "zeta_next": [zeta[0] * g % P, zeta[1] * g % P], "in_subgroup": zp == [1, 0]}
+    msg = _all_gather(msg, comm)[leader]
+    if msg["in_subgroup"]:
+        raise EtpError(-4, "Opening point is in the subgroup.")
+    zeta, zeta_next = msg["zeta"], msg["zeta_next"]
+
+    # ---- every rank: openings of its own columns, gathered
+    e0, e1 = shard.eval_at_ext_points(zeta, zeta_next)
+    parts = _all_gather((e0.tolist(), e1.tolist()), comm)
+    mark("evaluate the local columns at zeta, g*zeta")
+
+    idx = None
+    if rank == leader:
+        tr0 = np.array([v for part in parts for v in part[0]], dtype=np.uint64).reshape(-1, 2)
+        tr1 = np.array([v for part in parts for v in part[1]], dtype=np.uint64).reshape(-1, 2)
+        assert tr0.shape[0] == n_cols and tr1.shape[0] == n_cols
+        qu0 = quot.eval_at_ext_point(zeta).reshape(-1, 2)
+        for v in (tr0, qu0, tr1):  # observe_openings(to_fri_openings): zeta batch = local ++ quotient, then the next batch
+            ch.observe(v)
+        # stark.fri_instance + prove_openings: oracle 0 = trace (split), oracle 1 = quotient
+        alpha = ch.get_extension_challenge()
+        trace_polys = [(0, c) for c in range(n_cols)]
+        batches = [(zeta, trace_polys + [(1, c) for c in range(n_quot)]), (zeta_next, trace_polys)]
+        fri = shard.fri_begin([quot], batches, [np.concatenate([tr0, qu0]), tr1], alpha, fp)
+        mark("combine on the LDE domain (trace columns over NVLink)")
+        fri_caps, final_poly = fri.commit_phase(ch)
+        mark("fold codewords in the commitment phase")
+        pow_witness = ctx.fri_proof_of_work(ch, STARK_POW_BITS)
+        mark("find proof-of-work witness")
+        idx = [ch.get_challenge() % lde_n for _ in range(STARK_NUM_QUERIES)]
+    idx = _all_gather(idx, comm)[leader]
+
+    # ---- Merkle paths of the queried trace rows, from their owners
+    mine = {}
+    for i in sorted(set(idx)):
+        if shard.first_row <= i < shard.first_row + shard.num_rows:
+            mine[i] = shard.prove(i).reshape(-1).tolist()
+    rows = shard.leaves_at(idx) if rank == leader else None  # whole rows, the peers' columns over NVLink
+    paths = {}
+    for part in _all_gather(mine, comm):  # also the barrier after which no rank reads a peer's LDE any more
+        paths.update(part)
+    if rank != leader:
+        return None
+    rest = fri.query_rounds([quot], idx)  # per query: quotient row + path, then the FRI layers
+    mark("build FRI query rounds")
+
+    # ---- the flat proof (wire.py / DESIGN.md "B200STK2")
+    total = ctx.stark_proof_words(table, log_n)
+    hdr = np.zeros(wire.HEADER_WORDS, dtype=np.uint64)
+    vals = {"magic": wire.MAGIC, "table": table, "degree_bits": log_n, "n_trace": n_cols, "n_aux": 0, "n_quot": n_quot,
+            "cap_height": STARK_CAP_HEIGHT, "n_fri_layers": fp.n_reductions, "arity_bits": 4, "final_poly_len": final_poly.shape[0],
+            "num_queries": STARK_NUM_QUERIES, "n_public_inputs": n_pi, "rate_bits": STARK_RATE_BITS, "pow_bits": STARK_POW_BITS,
+            "num_challenges": STARK_NUM_CHALLENGES, "total_words": total, "n_ctl_zs": 0, "n_lookup_cols": 0, "n_ctl_helper_cols": 0}
+    for k, name in enumerate(wire.HEADER_FIELDS):
+        hdr[k] = vals[name]
+    out = [hdr, cap.reshape(-1), np.asarray(quot.cap, dtype=np.uint64).reshape(-1), tr0.reshape(-1), tr1.reshape(-1), qu0.reshape(-1),
+           np.asarray(fri_caps, dtype=np.uint64).reshape(-1)]
+    for q, i in enumerate(idx):
+        out += [rows[q], np.array(paths[i], dtype=np.uint64), rest[q]]
+    out += [np.asarray(final_poly, dtype=np.uint64).reshape(-1), np.array([pow_witness], dtype=np.uint64), np.array(pi, dtype=np.uint64)]
+    proof = np.concatenate([np.asarray(x, dtype=np.uint64).reshape(-1) for x in out])
+    if proof.size != total:
+        raise EtpError(-3, f"internal error: proof size mismatch ({proof.size} != {total})")
+    return proof
+
+
 # ---- several prover contexts on one GPU ----------------------------------------------------------------
 class ProverPool:
     """`workers` independent contexts (own stream, own scratch) on one device, each driven by a host thread.

@@ -359,11 +359,37 @@ int etp_fri_final_poly(etp_fri_state *s, uint64_t *coeffs_out);
 /* fused fri_committed_trees: every layer with the challenger (observe cap, draw beta), then observes the final polynomial.
  * caps_out: n_reductions caps; final_poly_out as above. */
 int etp_fri_commit_phase(etp_fri_state *s, etp_challenger *challenger, uint64_t *caps_out, uint64_t *final_poly_out);
+/* fri_proof_of_work: grinds the smallest witness for the challenger's current state, lets the challenger observe it and
+ * draws the response (checked to have proof_of_work_bits leading zeros); the FRI query indices are the next
+ * num_query_rounds challenges mod the LDE size. */
+int etp_fri_proof_of_work(etp_ctx *ctx, etp_challenger *challenger, int proof_of_work_bits, uint64_t *witness_out);
 /* fri_prover_query_rounds for the given x indices (< 2^(degree_bits + rate_bits)): out gets n_indices query rounds in the
  * layout of etp_fri_proof_words */
 int etp_fri_query_rounds(etp_fri_state *s, etp_batch *const *oracles, size_t n_oracles, const uint64_t *x_indices, size_t n_indices,
                          uint64_t *out);
 void etp_fri_free(etp_fri_state *s);
+
+/* ---- proving a column-split table: quotient, openings and FRI on one rank (the "leader"), trace columns read
+ * where they live (own HBM or a peer's over NVLink, through the etp_shard_set_peer mappings).  Protocol
+ * (eth_tx_proof_b200/parallel.py prove_column_split; starky prover.rs prove_with_commitment for a table without
+ * lookups / CTLs): every rank commits the shard -> leader: challenger, alphas, etp_shard_compute_quotient_polys_dev,
+ * commits the quotient batch (a PolynomialBatch of its own), zeta -> every rank: etp_shard_eval_at_ext_points of its
+ * columns at zeta and g*zeta, gathered -> leader: etp_shard_fri_begin (the combination step of prove_openings over
+ * oracle 0 = the split table and oracles 1.. = its own batches), then the FRI prover step by step (etp_fri_*);
+ * rows of the split table at the query indices: etp_shard_leaves_at; their Merkle paths: etp_shard_prove on the
+ * ranks that own the leaves. */
+/* compute_quotient_polys over the split trace; out_dev: num_challenges * quotient_degree_factor polynomials x n.
+ * Tables with auxiliary polynomials (lookups / CTLs) are refused (ETP_ERR_INVALID). */
+int etp_shard_compute_quotient_polys_dev(etp_shard *s, int table, const uint64_t *public_inputs, const uint64_t *alphas,
+                                         int n_alphas, uint64_t *out_dev);
+/* polynomials of the LOCAL columns at z0 and z1 (eval_commitment): out0 / out1 get num_local_cols extension values */
+int etp_shard_eval_at_ext_points(etp_shard *s, const uint64_t z0[2], const uint64_t z1[2], uint64_t *out0, uint64_t *out1);
+/* FriPolynomialInfo.oracle_index 0 = the split table (polynomial_index = column of the whole table), k >= 1 =
+ * extra_oracles[k - 1]; ys: the claimed openings, per batch and polynomial, extension values concatenated;
+ * alpha: the challenge prove_openings draws.  Returns the FRI state holding the combined LDE values. */
+int etp_shard_fri_begin(etp_shard *s, etp_batch *const *extra_oracles, size_t n_extra, const struct etp_fri_batch *batches,
+                        size_t n_batches, const uint64_t *ys, const uint64_t alpha[2], const struct etp_fri_params *params,
+                        etp_fri_state **out);
 
 #ifdef __cplusplus
 }
