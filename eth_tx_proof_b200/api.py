@@ -217,7 +217,8 @@ def load_library():
         "etp_fri_query_rounds": (i32, [vp, C.POINTER(vp), sz, _u64p, sz, _u64p]),
         "etp_fri_free": (None, [vp]),
         "etp_fri_proof_of_work": (i32, [vp, C.POINTER(Challenger), i32, _u64p]),
-        "etp_shard_compute_quotient_polys_dev": (i32, [vp, i32, _u64p, _u64p, i32, vp]),
+        "etp_shard_aux_columns_dev": (i32, [vp, i32, _u64p, i32, _u64p, vp, _u64p]),
+        "etp_shard_compute_quotient_polys_dev": (i32, [vp, i32, vp, _u64p, i32, _u64p, _u64p, i32, vp]),
         "etp_shard_eval_at_ext_points": (i32, [vp, _u64p, _u64p, _u64p, _u64p]),
         "etp_shard_fri_begin": (i32, [vp, C.POINTER(vp), sz, C.POINTER(FriBatch), sz, _u64p, _u64p, C.POINTER(FriParams), pp]),
         "etp_plonk_partial_products_and_zs_dev": (i32, [vp, vp, sz, vp, sz, _u64p, i32, i32, i32, _u64p, _u64p, i32, vp]),
@@ -365,12 +366,14 @@ class Context:
                                f"most log2(leaves.len())={log_n + 1}")
         return np.zeros(words, dtype=np.uint64)
 
-    def register_table(self, program, lookups=()) -> int:
+    def register_table(self, program, lookups=None) -> int:
         """Registers a table from its constraint program (``cprog.Program.words`` or a u64 array) and its lookups
         (``[(looking_columns, table_column, frequencies_column), ...]``): NVRTC-compiles the quotient kernel for
         sm_100a.  Returns the table id accepted by stark_prove / compute_quotient_polys / lookup_helper_columns."""
         if hasattr(program, "simple_lookups") and not program.simple_lookups():
             return self.register_table_ex(program, program.aux_spec)
+        if lookups is None:  # a cprog.Program carries its own lookups
+            lookups = getattr(program, "lookups", ())
         words = _u64(getattr(program, "words", program))
         flat = [len(lookups)]
         for looking, table_col, freq_col in lookups:
@@ -792,12 +795,25 @@ class BatchShard:
         self.ctx.check(self.ctx.L.etp_shard_download_coeffs(self.h, _p(out)))
         return out[:self.num_local_cols]
 
-    def compute_quotient_polys_dev(self, table, public_inputs, alphas, out_ptr: int):
+    def aux_columns_dev(self, table, lookup_challenges, ctl_challenges, aux_ptr: int) -> np.ndarray:
+        """Every auxiliary polynomial of the table (values on the trace domain) into the device matrix `aux_ptr`
+        (num_aux_columns x n), computed on THIS rank from the mapped LDE; returns ctl_zs_first."""
+        lc = _u64(list(lookup_challenges) + [0])
+        cc = _u64(ctl_challenges) if ctl_challenges is not None else None
+        n_zs = max(int(self.ctx.L.etp_table_num_ctl_zs(self.ctx.h, table)), 0)
+        zs = np.zeros(max(n_zs, 1), dtype=np.uint64)
+        self.ctx.check(self.ctx.L.etp_shard_aux_columns_dev(self.h, table, _p(lc), len(lookup_challenges), _p(cc) if cc is not None else None,
+                                                            C.c_void_p(aux_ptr), _p(zs)))
+        return zs[:n_zs]
+
+    def compute_quotient_polys_dev(self, table, aux_batch, challenge_scalars, public_inputs, alphas, out_ptr: int):
         """compute_quotient_polys over the split trace on THIS rank (peers' columns over NVLink); out: device matrix of
         num_challenges * quotient_degree_factor polynomials x n."""
         pi = _u64(list(public_inputs) + [0])
+        sc = _u64(list(challenge_scalars) + [0])
         a = _u64(alphas)
-        self.ctx.check(self.ctx.L.etp_shard_compute_quotient_polys_dev(self.h, table, _p(pi), _p(a), a.size, C.c_void_p(out_ptr)))
+        self.ctx.check(self.ctx.L.etp_shard_compute_quotient_polys_dev(self.h, table, aux_batch.h if aux_batch is not None else None, _p(sc),
+                                                                       len(challenge_scalars), _p(pi), _p(a), a.size, C.c_void_p(out_ptr)))
 
     def eval_at_ext_points(self, z0, z1):
         """The local columns' polynomials at z0 and z1 -> two (num_local_cols, 2) arrays."""

@@ -9,6 +9,7 @@
 // (Challenger) and the <= 2^8-coefficient FRI final polynomial.
 #include <time.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <functional>
 #include <memory>
@@ -59,6 +60,7 @@ struct SpecReader {
   size_t pos = 0;
   int n_trace;
   bool bad = false;
+  std::vector<size_t>* col_pos = nullptr;  // if set: the position of every trace-column index word
   uint64_t rd() { if (pos >= w.size()) { bad = true; return 0; } return w[pos++]; }
   // advances over one Column; *single = trace column index if it is Column::single(c), else -1
   void column(int* single) {
@@ -67,6 +69,7 @@ struct SpecReader {
     int one_col = -1;
     bool plain = nl == 1;
     for (uint64_t i = 0; i < nl && !bad; i++) {
+      if (col_pos) col_pos->push_back(pos);
       const uint64_t c = rd(), f = rd();
       if (c >= (uint64_t)n_trace) bad = true;
       if (gl::canon(f) != 1) plain = false;
@@ -74,7 +77,7 @@ struct SpecReader {
     }
     const uint64_t nn = rd();
     if (nn > 65536) { bad = true; return; }
-    for (uint64_t i = 0; i < nn && !bad; i++) { if (rd() >= (uint64_t)n_trace) bad = true; rd(); }
+    for (uint64_t i = 0; i < nn && !bad; i++) { if (col_pos) col_pos->push_back(pos); if (rd() >= (uint64_t)n_trace) bad = true; rd(); }
     const uint64_t k = rd();
     if (single) *single = (plain && nn == 0 && gl::canon(k) == 0) ? one_col : -1;
   }
@@ -92,10 +95,11 @@ struct SpecReader {
                                   gl::canon(w[start + 4]) == 1;
   }
 };
-std::string parse_aux_spec(const uint64_t* words, size_t n, int n_trace, int num_challenges, AuxSpec* out) {
+std::string parse_aux_spec(const uint64_t* words, size_t n, int n_trace, int num_challenges, AuxSpec* out, std::vector<size_t>* col_pos = nullptr) {
   AuxSpec a;
   a.words.assign(words, words + n);
   SpecReader r{a.words, 0, n_trace};
+  r.col_pos = col_pos;
   if (r.rd() != AUXSPEC_MAGIC) return "auxiliary-column spec: bad magic";
   const uint64_t nl = r.rd(), nz = r.rd();
   if (r.bad || nl > 256 || nz > 256) return "auxiliary-column spec: bad lookup / CTL counts";
@@ -158,6 +162,25 @@ std::vector<uint64_t> simple_spec_words(const std::vector<std::tuple<std::vector
     push_single(w, std::get<2>(l));
   }
   return w;
+}
+
+// The trace columns the auxiliary polynomials of a table are computed from (sorted), and the same spec over a matrix that
+// holds only those columns, in that order (column-split tables: the leader recovers just these columns).
+std::string compact_aux_spec(const AuxSpec& a, int n_trace, int num_challenges, std::vector<int>* used, AuxSpec* compact) {
+  std::vector<size_t> pos;
+  AuxSpec tmp;
+  if (a.words.empty()) { used->clear(); *compact = a; return ""; }
+  std::string why = parse_aux_spec(a.words.data(), a.words.size(), n_trace, num_challenges, &tmp, &pos);
+  if (!why.empty()) return why;
+  std::vector<int> cols;
+  for (size_t p : pos) cols.push_back((int)a.words[p]);
+  std::sort(cols.begin(), cols.end());
+  cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+  std::vector<uint64_t> w = a.words;
+  for (size_t p : pos) w[p] = (uint64_t)(std::lower_bound(cols.begin(), cols.end(), (int)a.words[p]) - cols.begin());
+  why = parse_aux_spec(w.data(), w.size(), (int)cols.size(), num_challenges, compact);
+  *used = cols;
+  return why;
 }
 
 struct TableInfo {
@@ -311,7 +334,7 @@ int spec_on_device(etp_ctx* ctx, const TableInfo& ti, const uint64_t** out) {
 // then the CTL helper columns, then the CTL Z columns (starky prover.rs: auxiliary_polys = lookup columns ++
 // get_ctl_auxiliary_polys(ctl_data); cross_table_lookup.rs: ctl_helper_polys() ++ ctl_z_polys()).
 int aux_columns(etp_ctx* ctx, const TableInfo& ti, int log_n, const uint64_t* trace, size_t stride, const uint64_t* lookup_ch, int n_ch,
-                const uint64_t* ctl_ch, uint64_t* aux) {
+                const uint64_t* ctl_ch, uint64_t* aux, const uint64_t* d_spec_override = nullptr) {
   if (!ti.lookup() && !ti.ctl()) return ETP_OK;
   const size_t n = (size_t)1 << log_n;
   size_t max_m = 1;
@@ -326,7 +349,8 @@ int aux_columns(etp_ctx* ctx, const TableInfo& ti, int log_n, const uint64_t* tr
   for (auto& l : ti.aux->lookups) general = general || !l.simple;
   const uint64_t* spec = nullptr;
   if (general) {
-    ETP_TRY(spec_on_device(ctx, ti, &spec));
+    if (d_spec_override) spec = d_spec_override;
+    else ETP_TRY(spec_on_device(ctx, ti, &spec));
     ETP_TRY(filt.alloc(max_m * n));
     ETP_TRY(freq.alloc(n));
     ETP_TRY(prefix.alloc(n));
@@ -1507,21 +1531,88 @@ static int shard_column_table(etp_shard* s, DevBuf<uint64_t>& d_cols) {
   return ETP_OK;
 }
 
-extern "C" int etp_shard_compute_quotient_polys_dev(etp_shard* s, int table, const uint64_t* public_inputs, const uint64_t* alphas, int n_alphas,
-                                                    uint64_t* out_dev) {
+// out[k] = in[bitrev(k)]: an LDE column (bit-reversed rows, possibly in a peer's HBM) -> natural order, local
+static __global__ void k_bitrev_gather(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int bits) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >> bits) return;
+  out[k] = in[gl::bitrev32((uint32_t)k, bits)];
+}
+
+// All auxiliary polynomials (values on the trace domain) of a column-split table, on the calling rank.  Only the few trace
+// columns the lookups / CTLs read are needed as VALUES; they are recovered from the LDE the peers already map: bit-reversed
+// gather over NVLink -> coset iFFT (size 2^(log_n + rate_bits)) -> FFT (size n).  ctl_zs_first_out: Z(1) of every CTL Z.
+extern "C" int etp_shard_aux_columns_dev(etp_shard* s, int table, const uint64_t* lookup_challenges, int n_challenges, const uint64_t* ctl_challenges,
+                                         uint64_t* aux_out_dev, uint64_t* ctl_zs_first_out) {
   etp_bind(s ? s->ctx : nullptr);
-  if (!s || !alphas || !out_dev) return ETP_ERR_INVALID;
+  if (!s || !aux_out_dev) return ETP_ERR_INVALID;
   etp_ctx* ctx = s->ctx;
   TableInfo ti;
   if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
-  if (ti.lookup() || ti.ctl()) return etp_fail(ctx, ETP_ERR_INVALID, "column-split proofs of tables with lookups / CTLs are not supported yet");
+  if ((size_t)ti.cols != s->n_cols_total) return etp_fail(ctx, ETP_ERR_INVALID, "the table does not have the shard's number of columns");
+  if (n_challenges < 0 || n_challenges > NUM_CHALLENGES || (n_challenges && !lookup_challenges)) return etp_fail(ctx, ETP_ERR_INVALID, "bad lookup challenges");
+  if (!ti.lookup() && !ti.ctl()) return ETP_OK;
+  std::vector<int> used;
+  auto compact = std::make_shared<AuxSpec>();
+  const std::string why = compact_aux_spec(*ti.aux, ti.cols, NUM_CHALLENGES, &used, compact.get());
+  if (!why.empty()) return etp_fail(ctx, ETP_ERR_STATE, "internal error: %s", why.c_str());
+  const int log_n = s->log_n, log_lde = s->log_n + s->rate_bits;
+  const size_t n = s->n(), lde_n = s->lde_n();
+  DevBuf<uint64_t> vals(ctx), nat(ctx), co(ctx), scratch(ctx), d_spec(ctx);
+  ETP_TRY(vals.alloc((used.empty() ? 1 : used.size()) * n));
+  ETP_TRY(nat.alloc(lde_n));
+  ETP_TRY(co.alloc(lde_n));
+  ETP_TRY(scratch.alloc(lde_n));
+  for (size_t j = 0; j < used.size(); j++) {
+    const uint64_t* col = s->column((size_t)used[j]);
+    if (!col) return etp_fail(ctx, ETP_ERR_STATE, "shard: LDE of rank %zu not mapped (etp_shard_set_peer)", (size_t)used[j] / s->cps);
+    k_bitrev_gather<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(col, nat.p, log_lde);
+    ETP_LAUNCH_CHECK(ctx);
+    NttArgs a;
+    a.in = nat.p; a.in_stride = lde_n; a.n_in = (uint32_t)lde_n; a.out = co.p; a.out_stride = lde_n; a.scratch = scratch.p; a.scratch_stride = lde_n;
+    a.log_n = log_lde; a.n_cols = 1; a.inverse = true; a.natural_out = true; a.coset_shift = gl::GENERATOR;
+    ETP_TRY(ntt_run(ctx, a));
+    a = NttArgs();
+    a.in = co.p; a.in_stride = lde_n; a.n_in = (uint32_t)n; a.out = vals.p + j * n; a.out_stride = n; a.scratch = scratch.p; a.scratch_stride = n;
+    a.log_n = log_n; a.n_cols = 1; a.natural_out = true;
+    ETP_TRY(ntt_run(ctx, a));
+  }
+  TableInfo tc = ti;
+  tc.aux = compact;
+  if (!compact->words.empty()) {
+    ETP_TRY(d_spec.alloc(compact->words.size()));
+    ETP_CUDA(ctx, cudaMemcpyAsync(d_spec.p, compact->words.data(), compact->words.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ETP_TRY(reset_zero_flag(ctx));
+  ETP_TRY(aux_columns(ctx, tc, log_n, vals.p, n, lookup_challenges, n_challenges, ctl_challenges, aux_out_dev, d_spec.p));
+  const int n_zs = ti.n_ctl_zs();
+  if (n_zs && ctl_zs_first_out) {
+    const size_t first = (size_t)(ti.n_lookup_cols(n_challenges) + ti.n_ctl_helpers()) * n;
+    ETP_CUDA(ctx, cudaMemcpy2DAsync(ctl_zs_first_out, 8, aux_out_dev + first, n * 8, 8, n_zs, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  ETP_TRY(check_zero_flag(ctx, "a lookup / CTL denominator vanishes on the trace"));  // synchronises the stream
+  for (int k = 0; k < n_zs && ctl_zs_first_out; k++) ctl_zs_first_out[k] = gl::canon(ctl_zs_first_out[k]);
+  return ETP_OK;
+}
+
+// compute_quotient_polys over the split trace.  aux: the committed auxiliary polynomials (a batch of this rank) or NULL;
+// challenge_scalars: what the constraint program reads (lookup challenges, then the CTL (beta, gamma) pairs).
+extern "C" int etp_shard_compute_quotient_polys_dev(etp_shard* s, int table, etp_batch* aux, const uint64_t* challenge_scalars, int n_scalars,
+                                                    const uint64_t* public_inputs, const uint64_t* alphas, int n_alphas, uint64_t* out_dev) {
+  etp_bind(s ? s->ctx : nullptr);
+  if (!s || !alphas || !out_dev || (n_scalars && !challenge_scalars)) return ETP_ERR_INVALID;
+  etp_ctx* ctx = s->ctx;
+  TableInfo ti;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
   if (ti.n_pi && !public_inputs) return ETP_ERR_INVALID;
+  if (aux && (aux->ctx != ctx || aux->log_n != s->log_n || aux->rate_bits != s->rate_bits))
+    return etp_fail(ctx, ETP_ERR_INVALID, "auxiliary batch does not match the shard");
   DevBuf<uint64_t> d_cols(ctx);
   ETP_TRY(shard_column_table(s, d_cols));
   TraceView tv;
   tv.cols_dev = (const uint64_t* const*)d_cols.p; tv.n_cols = s->n_cols_total; tv.log_n = s->log_n; tv.rate_bits = s->rate_bits;
   uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
-  ETP_TRY(compute_quotient(ctx, table, tv, nullptr, zero, 0, public_inputs ? public_inputs : zero, alphas, n_alphas, out_dev));
+  ETP_TRY(compute_quotient(ctx, table, tv, aux, n_scalars ? challenge_scalars : zero, n_scalars, public_inputs ? public_inputs : zero, alphas, n_alphas,
+                           out_dev));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // d_cols is read by the kernel
   return ETP_OK;
 }

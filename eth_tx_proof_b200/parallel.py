@@ -169,20 +169,26 @@ def _all_gather(obj, comm=None):
     return out
 
 
-def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = (), leader: int = None, timings: dict = None, comm=None):
-    """starky::prover::prove for ONE table whose trace is column-split over the ranks (call on every rank, after
-    `commit_column_split(shard, ...)` returned the trace `cap`).  Returns the proof words ("B200STK2", the layout of
-    `Context.stark_prove`) on the leader rank and None on the others; for the same trace it is word for word the proof
-    one GPU produces.
+def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = (), leader: int = None, timings: dict = None, comm=None,
+                       challenger=None, ctl_challenges=None):
+    """starky::prover::prove (or, with `challenger`, prove_with_commitment) for ONE table whose trace is column-split over
+    the ranks (call on every rank, after `commit_column_split(shard, ...)` returned the trace `cap`).  Returns the proof
+    words ("B200STK2", the layout of `Context.stark_prove` / `Context.prove_with_commitment`) on the leader rank and None
+    on the others; for the same trace it is word for word the proof one GPU produces.
 
     Who does what.  Every rank keeps only its columns (coefficients + LDE) and its leaf rows' Merkle subtrees.  The
     leader (default: the last rank, which owns the fewest columns) runs the transcript and every step that needs whole
     rows — the quotient, the FRI combination — reading the peers' LDE columns in place over NVLink (the mappings of the
     commit); the openings at zeta and g*zeta are evaluated where the coefficients live and gathered (2 x 16 bytes per
     column); the Merkle paths of the queried trace rows come from the ranks that own those rows.  Nothing of the trace is
-    ever copied between GPUs as a whole.  Tables with lookups / CTLs are refused by the library (their auxiliary columns
-    need whole trace rows on one GPU).  `comm`: an object with all_gather(obj) -> list (ThreadComm.rank(r)) when the ranks
-    are threads of one process; default: the torch.distributed default group."""
+    ever copied between GPUs as a whole.  Lookups / CTLs: the auxiliary polynomials are few; the leader computes them from
+    the handful of trace columns they read (recovered from the mapped LDE), commits them as a batch of its own.
+
+    `challenger` (leader only; an api.Challenger that has already observed what upstream's caller observed, e.g. every
+    table's trace cap in prove_with_traces) is advanced in place; without it the transcript starts as prove() does
+    (public inputs, trace cap).  `ctl_challenges`: the 4 words (beta, gamma) x num_challenges of a multi-table proof.
+    `comm`: an object with all_gather(obj) -> list (ThreadComm.rank(r)) when the ranks are threads of one process;
+    default: the torch.distributed default group."""
     import time
 
     import numpy as np
@@ -203,7 +209,18 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
     if len(public_inputs) < n_pi:
         raise ValueError("too few public inputs")
     pi = [int(x) % P for x in public_inputs[:n_pi]]
-    n_quot = int(L.etp_table_quotient_degree_factor(ctx.h, table)) * STARK_NUM_CHALLENGES
+    K = STARK_NUM_CHALLENGES
+    n_quot = int(L.etp_table_quotient_degree_factor(ctx.h, table)) * K
+    n_aux = int(L.etp_table_num_aux_columns(ctx.h, table, K))
+    n_lookup = int(L.etp_table_num_lookup_columns(ctx.h, table, K))
+    n_helpers = int(L.etp_table_num_ctl_helper_columns(ctx.h, table))
+    n_zs = int(L.etp_table_num_ctl_zs(ctx.h, table))
+    if n_zs and ctl_challenges is None:
+        raise EtpError(-1, "the table requires CTLs: pass the CTL challenges (and the shared challenger)")
+    if ctl_challenges is not None:
+        ctl_challenges = [int(x) % P for x in np.asarray(ctl_challenges, dtype=np.uint64).ravel()]
+        if len(ctl_challenges) != 2 * K:
+            raise EtpError(-1, "ctl_challenges must be num_challenges (beta, gamma) pairs = 4 words")
     fp = FriParams.make(log_n, STARK_RATE_BITS, STARK_CAP_HEIGHT, STARK_POW_BITS, STARK_NUM_QUERIES)
     cap = np.asarray(cap, dtype=np.uint64).reshape(-1, 4)
     t_last = [time.perf_counter()]
@@ -215,20 +232,50 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
             timings[name] = timings.get(name, 0.0) + (now - t_last[0]) * 1e3
             t_last[0] = now
 
-    # ---- leader: transcript up to zeta; quotient over the split trace; quotient commitment
-    ch = quot = None
+    # ---- leader: transcript up to zeta; auxiliary polynomials; quotient over the split trace; their commitments
+    ch = aux = quot = None
+    zs_first = np.zeros(0, dtype=np.uint64)
     msg = None
     if rank == leader:
         import ctypes as C
 
-        ch = Challenger()
-        ch.observe(pi)
-        ch.observe_cap(cap)
-        alphas = ch.get_n_challenges(STARK_NUM_CHALLENGES)
-        d = C.c_void_p()
-        ctx.check(L.etp_dev_alloc(ctx.h, n_quot * n * 8, C.byref(d)))
+        def dev_matrix(words):
+            d = C.c_void_p()
+            ctx.check(L.etp_dev_alloc(ctx.h, max(words, 1) * 8, C.byref(d)))
+            return d
+
+        if challenger is None:
+            ch = Challenger()
+            ch.observe(pi)
+            ch.observe_cap(cap)
+        else:
+            ch = challenger
+        # lookup challenges: the CTL betas when CTL challenges are given, else get_grand_product_challenge_set's betas
+        scalars = []
+        if n_lookup:
+            for k in range(K):
+                if ctl_challenges is not None:
+                    scalars.append(ctl_challenges[2 * k])
+                else:
+                    scalars.append(ch.get_challenge())
+                    ch.get_challenge()
+        lookup_ch = list(scalars)
+        if ctl_challenges is not None:
+            scalars = (scalars + [0] * K)[:K] + ctl_challenges
+        if n_aux:
+            d = dev_matrix(n_aux * n)
+            try:
+                zs_first = shard.aux_columns_dev(table, lookup_ch if n_lookup else [0] * K, ctl_challenges, d.value)
+                mark("compute auxiliary columns (their trace columns recovered from the LDE over NVLink)")
+                aux = PolynomialBatch.from_values_dev(ctx, d.value, n, n_aux, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
+            finally:
+                L.etp_dev_free(ctx.h, d)
+            mark("auxiliary polys commit")
+            ch.observe_cap(aux.cap)
+        alphas = ch.get_n_challenges(K)
+        d = dev_matrix(n_quot * n)
         try:
-            shard.compute_quotient_polys_dev(table, pi, alphas, d.value)
+            shard.compute_quotient_polys_dev(table, aux, scalars, pi, alphas, d.value)
             mark("compute quotient polys (trace columns over NVLink)")
             quot = PolynomialBatch.from_coeffs_dev(ctx, d.value, n, n_quot, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
         finally:
@@ -253,17 +300,30 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
 
     idx = None
     if rank == leader:
+        ext0 = np.zeros((0, 2), dtype=np.uint64)
         tr0 = np.array([v for part in parts for v in part[0]], dtype=np.uint64).reshape(-1, 2)
         tr1 = np.array([v for part in parts for v in part[1]], dtype=np.uint64).reshape(-1, 2)
         assert tr0.shape[0] == n_cols and tr1.shape[0] == n_cols
+        ax0 = aux.eval_at_ext_point(zeta).reshape(-1, 2) if aux is not None else ext0
+        ax1 = aux.eval_at_ext_point(zeta_next).reshape(-1, 2) if aux is not None else ext0
         qu0 = quot.eval_at_ext_point(zeta).reshape(-1, 2)
-        for v in (tr0, qu0, tr1):  # observe_openings(to_fri_openings): zeta batch = local ++ quotient, then the next batch
+        # observe_openings(to_fri_openings): zeta batch = local ++ aux ++ quotient, next batch = next ++ aux_next, ctl_zs_first
+        for v in (tr0, ax0, qu0, tr1, ax1):
             ch.observe(v)
-        # stark.fri_instance + prove_openings: oracle 0 = trace (split), oracle 1 = quotient
+        for z in zs_first:
+            ch.observe([int(z), 0])
+        # stark.fri_instance + prove_openings: oracle 0 = trace (split), then the auxiliary batch (if any), then the quotient
         alpha = ch.get_extension_challenge()
+        extra = [aux, quot] if aux is not None else [quot]
+        o_aux, o_quot = 1, len(extra)
         trace_polys = [(0, c) for c in range(n_cols)]
-        batches = [(zeta, trace_polys + [(1, c) for c in range(n_quot)]), (zeta_next, trace_polys)]
-        fri = shard.fri_begin([quot], batches, [np.concatenate([tr0, qu0]), tr1], alpha, fp)
+        aux_polys = [(o_aux, c) for c in range(n_aux)]
+        batches = [(zeta, trace_polys + aux_polys + [(o_quot, c) for c in range(n_quot)]), (zeta_next, trace_polys + aux_polys)]
+        ys = [np.concatenate([tr0, ax0, qu0]), np.concatenate([tr1, ax1])]
+        if n_zs:
+            batches.append(([1, 0], [(o_aux, n_lookup + n_helpers + k) for k in range(n_zs)]))
+            ys.append(np.array([[int(z), 0] for z in zs_first], dtype=np.uint64))
+        fri = shard.fri_begin(extra, batches, ys, alpha, fp)
         mark("combine on the LDE domain (trace columns over NVLink)")
         fri_caps, final_poly = fri.commit_phase(ch)
         mark("fold codewords in the commitment phase")
@@ -283,20 +343,23 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
         paths.update(part)
     if rank != leader:
         return None
-    rest = fri.query_rounds([quot], idx)  # per query: quotient row + path, then the FRI layers
+    rest = fri.query_rounds(extra, idx)  # per query: auxiliary / quotient rows + paths, then the FRI layers
     mark("build FRI query rounds")
 
     # ---- the flat proof (wire.py / DESIGN.md "B200STK2")
     total = ctx.stark_proof_words(table, log_n)
     hdr = np.zeros(wire.HEADER_WORDS, dtype=np.uint64)
-    vals = {"magic": wire.MAGIC, "table": table, "degree_bits": log_n, "n_trace": n_cols, "n_aux": 0, "n_quot": n_quot,
+    vals = {"magic": wire.MAGIC, "table": table, "degree_bits": log_n, "n_trace": n_cols, "n_aux": n_aux, "n_quot": n_quot,
             "cap_height": STARK_CAP_HEIGHT, "n_fri_layers": fp.n_reductions, "arity_bits": 4, "final_poly_len": final_poly.shape[0],
             "num_queries": STARK_NUM_QUERIES, "n_public_inputs": n_pi, "rate_bits": STARK_RATE_BITS, "pow_bits": STARK_POW_BITS,
-            "num_challenges": STARK_NUM_CHALLENGES, "total_words": total, "n_ctl_zs": 0, "n_lookup_cols": 0, "n_ctl_helper_cols": 0}
+            "num_challenges": K, "total_words": total, "n_ctl_zs": n_zs, "n_lookup_cols": n_lookup, "n_ctl_helper_cols": n_helpers}
     for k, name in enumerate(wire.HEADER_FIELDS):
         hdr[k] = vals[name]
-    out = [hdr, cap.reshape(-1), np.asarray(quot.cap, dtype=np.uint64).reshape(-1), tr0.reshape(-1), tr1.reshape(-1), qu0.reshape(-1),
-           np.asarray(fri_caps, dtype=np.uint64).reshape(-1)]
+    out = [hdr, cap.reshape(-1)]
+    if aux is not None:
+        out.append(np.asarray(aux.cap, dtype=np.uint64).reshape(-1))
+    out += [np.asarray(quot.cap, dtype=np.uint64).reshape(-1), tr0.reshape(-1), tr1.reshape(-1), ax0.reshape(-1), ax1.reshape(-1),
+            np.asarray(zs_first, dtype=np.uint64), qu0.reshape(-1), np.asarray(fri_caps, dtype=np.uint64).reshape(-1)]
     for q, i in enumerate(idx):
         out += [rows[q], np.array(paths[i], dtype=np.uint64), rest[q]]
     out += [np.asarray(final_poly, dtype=np.uint64).reshape(-1), np.array([pow_witness], dtype=np.uint64), np.array(pi, dtype=np.uint64)]

@@ -371,17 +371,25 @@ void etp_fri_free(etp_fri_state *s);
 
 /* ---- proving a column-split table: quotient, openings and FRI on one rank (the "leader"), trace columns read
  * where they live (own HBM or a peer's over NVLink, through the etp_shard_set_peer mappings).  Protocol
- * (eth_tx_proof_b200/parallel.py prove_column_split; starky prover.rs prove_with_commitment for a table without
- * lookups / CTLs): every rank commits the shard -> leader: challenger, alphas, etp_shard_compute_quotient_polys_dev,
+ * (eth_tx_proof_b200/parallel.py prove_column_split; starky prover.rs prove_with_commitment): every rank commits the
+ * shard -> leader: challenger, [etp_shard_aux_columns_dev, commits the auxiliary batch,] alphas, etp_shard_compute_quotient_polys_dev,
  * commits the quotient batch (a PolynomialBatch of its own), zeta -> every rank: etp_shard_eval_at_ext_points of its
  * columns at zeta and g*zeta, gathered -> leader: etp_shard_fri_begin (the combination step of prove_openings over
  * oracle 0 = the split table and oracles 1.. = its own batches), then the FRI prover step by step (etp_fri_*);
  * rows of the split table at the query indices: etp_shard_leaves_at; their Merkle paths: etp_shard_prove on the
  * ranks that own the leaves. */
-/* compute_quotient_polys over the split trace; out_dev: num_challenges * quotient_degree_factor polynomials x n.
- * Tables with auxiliary polynomials (lookups / CTLs) are refused (ETP_ERR_INVALID). */
-int etp_shard_compute_quotient_polys_dev(etp_shard *s, int table, const uint64_t *public_inputs, const uint64_t *alphas,
-                                         int n_alphas, uint64_t *out_dev);
+/* All auxiliary polynomials of the table (values on the trace domain, order of etp_aux_columns_dev) computed on the
+ * calling rank: the few trace columns the lookups / CTLs read are recovered from the mapped LDE (bit-reversed gather over
+ * NVLink, coset iFFT, FFT).  aux_out_dev: num_aux_columns x n; ctl_zs_first_out: Z(1) per CTL Z (may be NULL).
+ * A vanishing lookup / CTL denominator -> ETP_ERR_PROOF. */
+int etp_shard_aux_columns_dev(etp_shard *s, int table, const uint64_t *lookup_challenges, int n_challenges,
+                              const uint64_t *ctl_challenges, uint64_t *aux_out_dev, uint64_t *ctl_zs_first_out);
+/* compute_quotient_polys over the split trace; aux: the committed auxiliary batch (NULL if the table has none);
+ * challenge_scalars: lookup challenges, then the CTL (beta, gamma) pairs, as etp_compute_quotient_polys_dev;
+ * out_dev: num_challenges * quotient_degree_factor polynomials x n. */
+int etp_shard_compute_quotient_polys_dev(etp_shard *s, int table, etp_batch *aux, const uint64_t *challenge_scalars,
+                                         int n_scalars, const uint64_t *public_inputs, const uint64_t *alphas, int n_alphas,
+                                         uint64_t *out_dev);
 /* polynomials of the LOCAL columns at z0 and z1 (eval_commitment): out0 / out1 get num_local_cols extension values */
 int etp_shard_eval_at_ext_points(etp_shard *s, const uint64_t z0[2], const uint64_t z1[2], uint64_t *out0, uint64_t *out1);
 /* FriPolynomialInfo.oracle_index 0 = the split table (polynomial_index = column of the whole table), k >= 1 =

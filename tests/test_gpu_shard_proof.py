@@ -17,8 +17,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _split_proof(world, make_table, trace, pi, leader=None):
-    """Runs the protocol with `world` threads; returns (proof of the leader, the contexts' launch counts)."""
+def _split_proof(world, make_table, trace, pi, leader=None, challenger=None, ctl_challenges=None, want_cap=None):
+    """Runs the protocol with `world` threads (one context + one shard each); returns the leader's proof.  `challenger`
+    (advanced in place) and `ctl_challenges`: the prove_with_commitment form."""
     import eth_tx_proof_b200 as etp
     from eth_tx_proof_b200 import parallel
 
@@ -34,12 +35,16 @@ def _split_proof(world, make_table, trace, pi, leader=None):
             if r != s.rank and t.num_local_cols:
                 s.set_peer(r, t.lde_ptr)
     cap = parallel.assemble_cap([s.commit_rows() for s in shards])
+    if want_cap is not None:
+        assert (cap == want_cap).all()
+    lead = world - 1 if leader is None else leader
     comm = parallel.ThreadComm(world)
     out, err = [None] * world, [None] * world
 
     def work(r):
         try:
-            out[r] = parallel.prove_column_split(shards[r], tables[r], cap, pi, leader=leader, comm=comm.rank(r))
+            out[r] = parallel.prove_column_split(shards[r], tables[r], cap, pi, leader=leader, comm=comm.rank(r),
+                                                 challenger=challenger if r == lead else None, ctl_challenges=ctl_challenges)
         except BaseException as e:  # noqa: BLE001
             err[r] = e
             comm._barrier.abort()
@@ -52,7 +57,6 @@ def _split_proof(world, make_table, trace, pi, leader=None):
     first = next((e for e in err if e is not None and not isinstance(e, threading.BrokenBarrierError)), None)
     if first is not None:
         raise first
-    lead = world - 1 if leader is None else leader
     assert all(out[r] is None for r in range(world) if r != lead)
     proof = out[lead]
     del shards
@@ -114,12 +118,94 @@ def test_split_proof_is_accepted_by_the_verifier(ctx):
     stark_verifier.verify(got, program=prog)
 
 
-def test_split_proof_refuses_tables_with_lookups(ctx):
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("log_n", [7, 10])
+def test_split_memory_table_with_lookups_equals_single_gpu_and_oracle(ctx, world, log_n):
+    """The memory-shaped table (21 columns, range-check logUp: 2 x (helper, Z) auxiliary polynomials) — the table that
+    outgrows one GPU upstream.  The leader recovers the three trace columns the lookup reads from the mapped LDE."""
     import eth_tx_proof_b200 as etp
+    import oracle
     from eth_tx_proof_b200 import synthetic as syn
 
-    with pytest.raises(etp.EtpError, match="lookups"):
-        _split_proof(2, lambda c: etp.TABLE_MEMORY, syn.memory_trace(8, seed=2), [])
+    trace = syn.memory_trace(log_n, seed=4)
+    want = ctx.stark_prove(etp.TABLE_MEMORY, trace)
+    got = _split_proof(world, lambda c: etp.TABLE_MEMORY, trace, [])
+    assert got.shape == want.shape and (got == want).all()
+    if log_n <= 7:
+        assert (got == oracle.stark_prove(oracle.TABLE_MEMORY, trace)).all()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_split_registered_tables_with_general_lookups(ctx, world):
+    """Program-defined tables with lookups: the memory program (plain columns) and a shape table with 8 range-checked limbs
+    (chunked helpers); the compacted spec renumbers the columns the leader recovered."""
+    from eth_tx_proof_b200 import cprog, synthetic as syn
+
+    for prog, trace in ((cprog.memory_program(), syn.memory_trace(8, seed=5)),
+                        (cprog.shape_program(40, 8), cprog.shape_trace(8, 40, 8, seed=6))):
+        want = ctx.stark_prove(ctx.register_table(prog), trace)
+        got = _split_proof(world, lambda c: c.register_table(prog), trace, [])
+        assert got.shape == want.shape and (got[2:] == want[2:]).all()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_split_ctl_system_equals_single_gpu_table_by_table(ctx, world):
+    """prove_with_traces on the three-table CTL system (filtered lookups, linear-combination and next-row Columns, CTL
+    helper columns + Z, ctl_zs_first and the third FRI batch): every table column-split, one challenger threaded through
+    all of them — proofs and challenger states equal the single-GPU prover's, and the verifier accepts the CTL sums."""
+    import torch
+
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import cprog, prover
+    from test_ctl_oracle import verify_all
+
+    tables, ctls = cprog.ctl_demo_tables(7, 6, 5)
+    tids = [ctx.register_table(p) for _, p, _ in tables]
+    devs = [torch.from_numpy(np.ascontiguousarray(t).view(np.int64)).cuda() for _, _, t in tables]
+    torch.cuda.synchronize()
+    traces_dev = [(d.data_ptr(), t.shape[1], t.shape[0], int(t.shape[1]).bit_length() - 1) for d, (_, _, t) in zip(devs, tables)]
+    want = prover.prove_with_traces(ctx, tids, traces_dev)
+    ch = etp.Challenger()
+    for cap in want.trace_caps:
+        ch.observe_cap(cap)
+    ctl_ch = ch.get_n_challenges(4)
+    assert (ctl_ch == want.ctl_challenges).all()
+    proofs = []
+    for k, (_, prog, trace) in enumerate(tables):
+        assert (ch.compact() == want.init_challenger_states[k]).all()
+        got = _split_proof(world, lambda c: c.register_table(prog), trace, [], challenger=ch, ctl_challenges=ctl_ch,
+                           want_cap=want.trace_caps[k])
+        assert got.shape == want.stark_proofs[k].shape and (got[2:] == want.stark_proofs[k][2:]).all(), f"table {k}"
+        proofs.append(got)
+    zs = verify_all(tables, ctls, proofs, want.trace_caps, max_queries=2)
+    assert [len(z) for z in zs] == [2, 2, 2]
+
+
+def test_split_ctl_table_needs_ctl_challenges(ctx):
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import cprog
+
+    tables, _ = cprog.ctl_demo_tables(5, 4, 4)
+    _, prog, trace = tables[1]
+    with pytest.raises(etp.EtpError, match="CTL"):
+        _split_proof(2, lambda c: c.register_table(prog), trace, [])
+
+
+def test_split_lookup_with_vanishing_denominator_fails_loudly(ctx):
+    """challenge + table value = 0 on some row: upstream panics in batch_multiplicative_inverse; here ETP_ERR_PROOF, on the
+    split path too (the zero flag is checked after the auxiliary columns)."""
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import cprog
+
+    tables, _ = cprog.ctl_demo_tables(5, 4, 4)
+    _, prog, trace = tables[1]
+    # rom: combine = KEY + beta * VAL + gamma; gamma = -(KEY + beta * VAL) at row 3 makes that row's denominator vanish
+    P = 0xFFFFFFFF00000001
+    beta = 5
+    gamma = (-(int(trace[0, 3]) + beta * int(trace[1, 3]))) % P
+    ch = etp.Challenger()
+    with pytest.raises(etp.EtpError, match="denominator"):
+        _split_proof(2, lambda c: c.register_table(prog), trace, [], challenger=ch, ctl_challenges=[beta, gamma, beta, gamma])
 
 
 def test_split_proof_of_an_invalid_trace_fails_like_the_single_gpu_prover(ctx):
