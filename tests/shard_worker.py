@@ -63,7 +63,9 @@ def prove(ctx, rank, world, args):
     cases = [("fibonacci", etp.TABLE_FIBONACCI, fib, list(fib_pi)),
              ("shape21", ctx.register_table(cprog.shape_program(21, 0)), cprog.shape_trace(log_n, 21, 0, seed=5), []),
              ("logic68", ctx.register_table(cprog.logic_program(1)), cprog.logic_trace(log_n, 1, seed=6), []),
-             ("shape%d" % args.cols, ctx.register_table(cprog.shape_program(args.cols, 0)), cprog.shape_trace(log_n, args.cols, 0, seed=7), [])]
+             ("shape%d" % args.cols, ctx.register_table(cprog.shape_program(args.cols, 0)), cprog.shape_trace(log_n, args.cols, 0, seed=7), []),
+             ("memory", etp.TABLE_MEMORY, syn.memory_trace(log_n, seed=8), []),
+             ("shape40+8 lookups", ctx.register_table(cprog.shape_program(40, 8)), cprog.shape_trace(log_n, 40, 8, seed=9), [])]
     for name, table, trace, pi in cases:
         cols = trace.shape[0]
         shard = etp.BatchShard(ctx, cols, log_n, 1, 4, rank, world)

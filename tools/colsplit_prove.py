@@ -1,5 +1,6 @@
 """Proof of ONE oversized table column-split over all ranks (torchrun, one process per GPU): a shape_program(cols) table
-(cprog.py: counter column, groups c = a*b + d / a*b*d, boolean flags; no lookups) whose trace columns are generated on
+(cprog.py: counter column, groups c = a*b + d / a*b*d, boolean flags; --lookups K adds K limbs range-checked against the
+counter with a logUp lookup: chunked helper columns + Z per challenge) whose trace columns are generated on
 the GPUs that own them, committed with the column-split commit and proved with parallel.prove_column_split.
   --verify          the leader runs the Python verifier (tests/stark_verifier.py) on the proof
   --compare-single  the leader also proves the whole table alone (must fit one GPU) and compares word for word
@@ -22,6 +23,7 @@ from eth_tx_proof_b200 import cprog, parallel
 ap = argparse.ArgumentParser()
 ap.add_argument("--log-n", type=int, default=20)
 ap.add_argument("--cols", type=int, default=21)
+ap.add_argument("--lookups", type=int, default=0)
 ap.add_argument("--verify", action="store_true")
 ap.add_argument("--compare-single", action="store_true")
 ap.add_argument("--reps", type=int, default=1, help="prove this many times (same committed shard); the last run is reported")
@@ -33,9 +35,14 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = etp.Context(local)
 log_n, cols = args.log_n, args.cols
 n = 1 << log_n
-lay = cprog.shape_layout(cols, 0)
-prog = cprog.shape_program(cols, 0)
+lay = cprog.shape_layout(cols, args.lookups)
+prog = cprog.shape_program(cols, args.lookups)
 table = ctx.register_table(prog)
+
+
+def limb(j):
+    gen = torch.Generator(device="cuda").manual_seed(55000 + j)
+    return torch.randint(0, n, (n,), dtype=torch.int64, device="cuda", generator=gen)
 
 
 def columns(c0, c1):
@@ -45,6 +52,13 @@ def columns(c0, c1):
     for c in range(c0, c1):
         if c == 0:
             out[c - c0] = torch.arange(n, dtype=torch.int64, device="cuda")
+        elif args.lookups and c == lay["FREQ"]:  # multiplicities of the counter values among all limbs
+            freq = torch.zeros(n, dtype=torch.int64, device="cuda")
+            for j in range(args.lookups):
+                freq += torch.bincount(limb(j), minlength=n)
+            out[c - c0] = freq
+        elif args.lookups and c < lay["GROUP"]:
+            out[c - c0] = limb(c - lay["LIMB"])
         elif c < lay["FLAG"]:
             g, k = divmod(c - lay["GROUP"], 4)
             if g not in groups:
@@ -80,7 +94,7 @@ for _ in range(max(args.reps, 1)):
 leader = world - 1
 res = None
 if rank == leader:
-    res = {"workload": f"shape_program({cols}) 2^{log_n} rows column-split over {world} GPUs", "log_n": log_n, "cols": cols, "world": world,
+    res = {"workload": f"shape_program({cols}, {args.lookups} range-checked limbs) 2^{log_n} rows column-split over {world} GPUs", "log_n": log_n, "cols": cols, "world": world,
            "trace_commit_ms": round(t_commit * 1e3, 1), "prove_after_commit_ms": round(t_prove * 1e3, 1),
            "total_ms": round((t_commit + t_prove) * 1e3, 1), "proof_words": int(proof.size), "reps": args.reps,
            "phases_ms": {k: round(v, 1) for k, v in timings.items()},
