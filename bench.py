@@ -225,6 +225,54 @@ def run_column_split(etp, ctx, torch, dist, rank, world, log_n, cols, n, nbytes,
             "timed": "local columns resident in HBM -> whole cap on every rank (wall clock incl. 2 barriers, max over ranks)"}
 
 
+def run_column_split_proof(etp, ctx, torch, dist, rank, world, barrier, max_over_ranks, log_n=22, cols=40, lookups=8):
+    """ONE table column-split across all ranks, proved (parallel.prove_column_split): trace commit + auxiliary polynomials +
+    quotient + openings + FRI with the trace columns read in place over NVLink.  Parity inside the bench: the leader also
+    proves the same table alone on its GPU and the two proofs must be equal word for word."""
+    from eth_tx_proof_b200 import cprog, parallel, synthetic as syn
+
+    n = 1 << log_n
+    prog = cprog.shape_program(cols, lookups)
+    table = ctx.register_table(prog)
+    c0, c1 = parallel.column_split_plan(cols, 2 * n, CAP_HEIGHT, rank, world)["cols"]
+    xs = syn.shape_trace_columns_dev(log_n, cols, lookups, c0, c1)
+    torch.cuda.synchronize()
+    shard = etp.BatchShard(ctx, cols, log_n, RATE_BITS, CAP_HEIGHT, rank, world)
+    cap = parallel.commit_column_split(shard, values_dev=(xs.data_ptr(), n))
+    leader = world - 1
+    proof = parallel.prove_column_split(shard, table, cap)  # warm-up (compiles the column-split variant of the quotient kernel)
+    times = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        cap = parallel.recommit_column_split(shard, (xs.data_ptr(), n))
+        proof = parallel.prove_column_split(shard, table, cap)
+        torch.cuda.synchronize()
+        times.append(max_over_ranks(time.perf_counter() - t0))
+    parallel.finish_column_split(shard)
+    del shard, xs
+    ctx.trim()
+    res = None
+    if rank == leader:
+        whole = syn.shape_trace_columns_dev(log_n, cols, lookups, 0, cols)
+        torch.cuda.synchronize()
+        ctx.stark_prove_dev(table, log_n, whole.data_ptr(), n)  # warm-up
+        single = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            want = ctx.stark_prove_dev(table, log_n, whole.data_ptr(), n)
+            single.append(time.perf_counter() - t0)
+        assert want.shape == proof.shape and (want == proof).all(), "column-split proof differs from the single-GPU proof of the same trace"
+        res = {"workload": f"ONE table shape_program({cols}, {lookups} range-checked limbs) 2^{log_n} rows column-split over {world} GPUs, "
+                           "proved (trace commit + auxiliary columns + quotient + openings + FRI; trace columns read over NVLink)",
+               "ms_per_proof": min(times) * 1e3, "single_gpu_ms_per_proof": min(single) * 1e3, "scaling": "strong",
+               "parity": "proof words == the single-GPU proof of the same trace (leader rank)",
+               "timed": "local trace columns resident in HBM -> proof words on the leader (wall clock, max over ranks, best of 3)"}
+    out = [None] * world
+    dist.all_gather_object(out, res)
+    return out[leader]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -459,12 +507,16 @@ def main():
     # ---- one table column-split across all ranks: strong scaling of a single commit.
     # Rank g transforms columns [g*C/G, (g+1)*C/G) and hashes leaf rows [g*L/G, (g+1)*L/G), reading the peers'
     # LDE columns over NVLink inside the hashing kernel; the cap parts are all-gathered over NCCL.
-    split = None
+    split = split_proof = None
     if world > 1 and not args.skip_split and (world & (world - 1)) == 0 and world <= 8:
         try:
             split = run_column_split(etp, ctx, torch, dist, rank, world, log_n, cols, n, nbytes, barrier, max_over_ranks)
         except Exception as e:  # the weak-scaling line above must survive a box without CUDA IPC between its GPUs
             split = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            split_proof = run_column_split_proof(etp, ctx, torch, dist, rank, world, barrier, max_over_ranks)
+        except Exception as e:
+            split_proof = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -552,7 +604,7 @@ def main():
         "data": "synthetic",
         "config": workload_config(log_n, cols),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "recursion_skeleton": recursion, "column_split": split,
+        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "recursion_skeleton": recursion, "column_split": split, "column_split_proof": split_proof,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())

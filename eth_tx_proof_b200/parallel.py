@@ -169,6 +169,22 @@ def _all_gather(obj, comm=None):
     return out
 
 
+def _collective(fn, comm):
+    """Runs fn() on this rank and all-gathers the results.  A failure on ANY rank is raised on EVERY rank (as EtpError with
+    the first failing rank's code and message) instead of leaving the others blocked in the next collective."""
+    from .api import EtpError
+
+    try:
+        val, err = fn(), None
+    except Exception as e:  # noqa: BLE001
+        val, err = None, (getattr(e, "code", -3), f"{type(e).__name__}: {e}")
+    out = _all_gather((err, val), comm)
+    for r, (e, _) in enumerate(out):
+        if e:
+            raise EtpError(e[0], f"column-split proof, rank {r}: {e[1]}")
+    return [v for _, v in out]
+
+
 def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = (), leader: int = None, timings: dict = None, comm=None,
                        challenger=None, ctl_challenges=None):
     """starky::prover::prove (or, with `challenger`, prove_with_commitment) for ONE table whose trace is column-split over
@@ -233,10 +249,11 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
             t_last[0] = now
 
     # ---- leader: transcript up to zeta; auxiliary polynomials; quotient over the split trace; their commitments
-    ch = aux = quot = None
-    zs_first = np.zeros(0, dtype=np.uint64)
-    msg = None
-    if rank == leader:
+    st = {"zs_first": np.zeros(0, dtype=np.uint64), "aux": None}
+
+    def leader_until_zeta():
+        if rank != leader:
+            return None
         import ctypes as C
 
         def dev_matrix(words):
@@ -250,6 +267,7 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
             ch.observe_cap(cap)
         else:
             ch = challenger
+        st["ch"] = ch
         # lookup challenges: the CTL betas when CTL challenges are given, else get_grand_product_challenge_set's betas
         scalars = []
         if n_lookup:
@@ -265,41 +283,47 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
         if n_aux:
             d = dev_matrix(n_aux * n)
             try:
-                zs_first = shard.aux_columns_dev(table, lookup_ch if n_lookup else [0] * K, ctl_challenges, d.value)
+                st["zs_first"] = shard.aux_columns_dev(table, lookup_ch if n_lookup else [0] * K, ctl_challenges, d.value)
                 mark("compute auxiliary columns (their trace columns recovered from the LDE over NVLink)")
-                aux = PolynomialBatch.from_values_dev(ctx, d.value, n, n_aux, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
+                st["aux"] = PolynomialBatch.from_values_dev(ctx, d.value, n, n_aux, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
             finally:
                 L.etp_dev_free(ctx.h, d)
             mark("auxiliary polys commit")
-            ch.observe_cap(aux.cap)
+            ch.observe_cap(st["aux"].cap)
         alphas = ch.get_n_challenges(K)
         d = dev_matrix(n_quot * n)
         try:
-            shard.compute_quotient_polys_dev(table, aux, scalars, pi, alphas, d.value)
+            shard.compute_quotient_polys_dev(table, st["aux"], scalars, pi, alphas, d.value)
             mark("compute quotient polys (trace columns over NVLink)")
-            quot = PolynomialBatch.from_coeffs_dev(ctx, d.value, n, n_quot, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
+            st["quot"] = PolynomialBatch.from_coeffs_dev(ctx, d.value, n, n_quot, log_n, STARK_RATE_BITS, False, STARK_CAP_HEIGHT)
         finally:
             L.etp_dev_free(ctx.h, d)
         mark("quotient polys commit")
-        ch.observe_cap(quot.cap)
+        ch.observe_cap(st["quot"].cap)
         zeta = [int(x) for x in ch.get_extension_challenge()]
         zp = zeta
         for _ in range(log_n):
             zp = _ext_mul(zp, zp)
+        if zp == [1, 0]:
+            raise EtpError(-4, "Opening point is in the subgroup.")
         g = pow(1753635133440165772, 1 << (32 - log_n), P)
-        msg = {"zeta": zeta, "zeta_next": [zeta[0] * g % P, zeta[1] * g % P], "in_subgroup": zp == [1, 0]}
-    msg = _all_gather(msg, comm)[leader]
-    if msg["in_subgroup"]:
-        raise EtpError(-4, "Opening point is in the subgroup.")
+        return {"zeta": zeta, "zeta_next": [zeta[0] * g % P, zeta[1] * g % P]}
+
+    msg = _collective(leader_until_zeta, comm)[leader]
     zeta, zeta_next = msg["zeta"], msg["zeta_next"]
 
     # ---- every rank: openings of its own columns, gathered
-    e0, e1 = shard.eval_at_ext_points(zeta, zeta_next)
-    parts = _all_gather((e0.tolist(), e1.tolist()), comm)
+    def local_openings():
+        e0, e1 = shard.eval_at_ext_points(zeta, zeta_next)
+        return e0.tolist(), e1.tolist()
+
+    parts = _collective(local_openings, comm)
     mark("evaluate the local columns at zeta, g*zeta")
 
-    idx = None
-    if rank == leader:
+    def leader_until_queries():
+        if rank != leader:
+            return None
+        ch, aux, quot, zs_first = st["ch"], st["aux"], st["quot"], st["zs_first"]
         ext0 = np.zeros((0, 2), dtype=np.uint64)
         tr0 = np.array([v for part in parts for v in part[0]], dtype=np.uint64).reshape(-1, 2)
         tr1 = np.array([v for part in parts for v in part[1]], dtype=np.uint64).reshape(-1, 2)
@@ -307,6 +331,7 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
         ax0 = aux.eval_at_ext_point(zeta).reshape(-1, 2) if aux is not None else ext0
         ax1 = aux.eval_at_ext_point(zeta_next).reshape(-1, 2) if aux is not None else ext0
         qu0 = quot.eval_at_ext_point(zeta).reshape(-1, 2)
+        st["openings"] = (tr0, tr1, ax0, ax1, qu0)
         # observe_openings(to_fri_openings): zeta batch = local ++ aux ++ quotient, next batch = next ++ aux_next, ctl_zs_first
         for v in (tr0, ax0, qu0, tr1, ax1):
             ch.observe(v)
@@ -325,24 +350,33 @@ def prove_column_split(shard, table: int, cap, public_inputs: Sequence[int] = ()
             ys.append(np.array([[int(z), 0] for z in zs_first], dtype=np.uint64))
         fri = shard.fri_begin(extra, batches, ys, alpha, fp)
         mark("combine on the LDE domain (trace columns over NVLink)")
-        fri_caps, final_poly = fri.commit_phase(ch)
+        st["fri"], st["extra"] = fri, extra
+        st["fri_caps"], st["final_poly"] = fri.commit_phase(ch)
         mark("fold codewords in the commitment phase")
-        pow_witness = ctx.fri_proof_of_work(ch, STARK_POW_BITS)
+        st["pow_witness"] = ctx.fri_proof_of_work(ch, STARK_POW_BITS)
         mark("find proof-of-work witness")
-        idx = [ch.get_challenge() % lde_n for _ in range(STARK_NUM_QUERIES)]
-    idx = _all_gather(idx, comm)[leader]
+        return [ch.get_challenge() % lde_n for _ in range(STARK_NUM_QUERIES)]
 
-    # ---- Merkle paths of the queried trace rows, from their owners
-    mine = {}
-    for i in sorted(set(idx)):
-        if shard.first_row <= i < shard.first_row + shard.num_rows:
-            mine[i] = shard.prove(i).reshape(-1).tolist()
-    rows = shard.leaves_at(idx) if rank == leader else None  # whole rows, the peers' columns over NVLink
+    idx = _collective(leader_until_queries, comm)[leader]
+
+    # ---- Merkle paths of the queried trace rows, from their owners; whole rows on the leader (peers' columns over NVLink)
+    def local_paths():
+        mine = {}
+        for i in sorted(set(idx)):
+            if shard.first_row <= i < shard.first_row + shard.num_rows:
+                mine[i] = shard.prove(i).reshape(-1).tolist()
+        if rank == leader:
+            st["rows"] = shard.leaves_at(idx)
+        return mine
+
     paths = {}
-    for part in _all_gather(mine, comm):  # also the barrier after which no rank reads a peer's LDE any more
+    for part in _collective(local_paths, comm):  # also the barrier after which no rank reads a peer's LDE any more
         paths.update(part)
     if rank != leader:
         return None
+    aux, quot, zs_first, fri, extra, rows = st["aux"], st["quot"], st["zs_first"], st["fri"], st["extra"], st["rows"]
+    tr0, tr1, ax0, ax1, qu0 = st["openings"]
+    fri_caps, final_poly, pow_witness = st["fri_caps"], st["final_poly"], st["pow_witness"]
     rest = fri.query_rounds(extra, idx)  # per query: auxiliary / quotient rows + paths, then the FRI layers
     mark("build FRI query rounds")
 

@@ -152,3 +152,42 @@ def tx_job_tables(scale_bits: int = 0):
             cols, lk = cprog.EVM_TABLE_SHAPES[name]
             out.append((name, cprog.shape_program(cols, lk), bits, cprog.shape_trace(bits, cols, lk, seed=41)))
     return out
+
+
+def shape_trace_columns_dev(log_n: int, n_cols: int, n_lookup: int, c0: int, c1: int, seed: int = 77):
+    """Columns [c0, c1) of a trace that satisfies cprog.shape_program(n_cols, n_lookup), generated on the current CUDA device
+    (torch int64 tensor (c1 - c0, n)): every column is a function of (seed, column) only, so each rank of a column-split
+    table builds just the columns it owns and any rank can rebuild any column.  Not the numpy trace of cprog.shape_trace
+    (different random stream): a valid trace of the same shape for sizes no host generates in reasonable time."""
+    import torch
+
+    from . import cprog
+
+    lay = cprog.shape_layout(n_cols, n_lookup)
+    n = 1 << log_n
+
+    def rnd(stream, hi, shape):
+        gen = torch.Generator(device="cuda").manual_seed(seed * 100003 + stream)
+        return torch.randint(0, hi, shape, dtype=torch.int64, device="cuda", generator=gen)
+
+    out = torch.empty((max(c1 - c0, 0), n), dtype=torch.int64, device="cuda")
+    group = (None, None)
+    for c in range(c0, c1):
+        if c == 0:
+            out[c - c0] = torch.arange(n, dtype=torch.int64, device="cuda")
+        elif n_lookup and c == lay["FREQ"]:  # multiplicities of the counter values among all limbs
+            freq = torch.zeros(n, dtype=torch.int64, device="cuda")
+            for j in range(n_lookup):
+                freq += torch.bincount(rnd(50000 + j, n, (n,)), minlength=n)
+            out[c - c0] = freq
+        elif n_lookup and c < lay["GROUP"]:
+            out[c - c0] = rnd(50000 + c - lay["LIMB"], n, (n,))
+        elif c < lay["FLAG"]:
+            g, k = divmod(c - lay["GROUP"], 4)
+            if group[0] != g:
+                group = (g, rnd(g, 1 << 20, (3, n)))
+            a, b, d = group[1]
+            out[c - c0] = (a, b, d, a * b * d if g % 5 == 4 else a * b + d)[k]
+        else:
+            out[c - c0] = rnd(90000 + c, 2, (n,))
+    return out

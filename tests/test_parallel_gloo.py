@@ -150,3 +150,83 @@ def test_prover_pool_scheduling_and_error_propagation():
     assert all(getattr(c, "closed", False) for c in ctxs)
     with pytest.raises(ValueError):
         parallel.ProverPool(0, contexts=[])
+
+
+def test_thread_comm_all_gather_and_collective_errors():
+    """Host logic of the column-split proof (parallel.prove_column_split): ThreadComm gathers in rank order, repeatedly;
+    a failure on one rank is raised on every rank — nobody stays blocked in the next collective."""
+    import threading
+
+    sys.path.insert(0, ROOT)
+    from eth_tx_proof_b200 import EtpError, parallel
+
+    world = 4
+    comm = parallel.ThreadComm(world)
+    got, errs = [None] * world, [None] * world
+
+    def work(r):
+        c = comm.rank(r)
+        a = parallel._all_gather({"r": r}, c)
+        b = parallel._collective(lambda: r * r, c)
+        try:
+            def step():
+                if r == 2:
+                    raise EtpError(-4, "boom")
+                return r
+            parallel._collective(step, c)
+        except EtpError as e:
+            errs[r] = e
+        got[r] = (a, b, parallel._collective(lambda: "after", c))  # the communicator is still usable
+
+    ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=30)
+    assert all(not t.is_alive() for t in ths)
+    for r in range(world):
+        a, b, c = got[r]
+        assert a == [{"r": k} for k in range(world)] and b == [0, 1, 4, 9] and c == ["after"] * world
+        assert errs[r] is not None and errs[r].code == -4 and "rank 2" in str(errs[r]) and "boom" in str(errs[r])
+
+
+def _collective_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from eth_tx_proof_b200 import EtpError, parallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = parallel._collective(lambda: rank + 10, None)
+    try:
+        def step():
+            if rank == 1:
+                raise ValueError("bad shard")
+            return rank
+        parallel._collective(step, None)
+        err = None
+    except EtpError as e:
+        err = (e.code, str(e))
+    q.put((rank, ok, err))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_collective_errors_across_processes():
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    ps = [ctxm.Process(target=_collective_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, err in res:
+        assert ok == [10, 11]
+        assert err is not None and err[0] == -3 and "rank 1" in err[1] and "bad shard" in err[1]

@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 import eth_tx_proof_b200 as etp
-from eth_tx_proof_b200 import cprog, parallel
+from eth_tx_proof_b200 import cprog, parallel, synthetic as syn
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--log-n", type=int, default=20)
@@ -35,41 +35,12 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = etp.Context(local)
 log_n, cols = args.log_n, args.cols
 n = 1 << log_n
-lay = cprog.shape_layout(cols, args.lookups)
 prog = cprog.shape_program(cols, args.lookups)
 table = ctx.register_table(prog)
 
 
-def limb(j):
-    gen = torch.Generator(device="cuda").manual_seed(55000 + j)
-    return torch.randint(0, n, (n,), dtype=torch.int64, device="cuda", generator=gen)
-
-
 def columns(c0, c1):
-    """Columns [c0, c1) of a trace that satisfies shape_program(cols): any rank can rebuild any column."""
-    out = torch.empty((max(c1 - c0, 0), n), dtype=torch.int64, device="cuda")
-    groups = {}
-    for c in range(c0, c1):
-        if c == 0:
-            out[c - c0] = torch.arange(n, dtype=torch.int64, device="cuda")
-        elif args.lookups and c == lay["FREQ"]:  # multiplicities of the counter values among all limbs
-            freq = torch.zeros(n, dtype=torch.int64, device="cuda")
-            for j in range(args.lookups):
-                freq += torch.bincount(limb(j), minlength=n)
-            out[c - c0] = freq
-        elif args.lookups and c < lay["GROUP"]:
-            out[c - c0] = limb(c - lay["LIMB"])
-        elif c < lay["FLAG"]:
-            g, k = divmod(c - lay["GROUP"], 4)
-            if g not in groups:
-                gen = torch.Generator(device="cuda").manual_seed(77000 + g)
-                groups = {g: torch.randint(0, 1 << 20, (3, n), dtype=torch.int64, device="cuda", generator=gen)}
-            a, b, d = groups[g]
-            out[c - c0] = (a, b, d, a * b * d if g % 5 == 4 else a * b + d)[k]
-        else:
-            gen = torch.Generator(device="cuda").manual_seed(99000 + c)
-            out[c - c0] = torch.randint(0, 2, (n,), dtype=torch.int64, device="cuda", generator=gen)
-    return out
+    return syn.shape_trace_columns_dev(log_n, cols, args.lookups, c0, c1)
 
 
 c0, c1 = parallel.column_split_plan(cols, 2 * n, 4, rank, world)["cols"]
