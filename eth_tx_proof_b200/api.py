@@ -217,6 +217,9 @@ def load_library():
         "etp_fri_query_rounds": (i32, [vp, C.POINTER(vp), sz, _u64p, sz, _u64p]),
         "etp_fri_free": (None, [vp]),
         "etp_fri_proof_of_work": (i32, [vp, C.POINTER(Challenger), i32, _u64p]),
+        "etp_poseidon_constants": (None, [_u64p, _u64p, _u64p]),
+        "etp_program_register": (i32, [vp, _u64p, sz, C.POINTER(i32)]),
+        "etp_compute_quotient_polys_cols_dev": (i32, [vp, i32, C.POINTER(vp), sz, i32, i32, _u64p, i32, _u64p, _u64p, i32, vp]),
         "etp_shard_aux_columns_dev": (i32, [vp, i32, _u64p, i32, _u64p, vp, _u64p]),
         "etp_shard_compute_quotient_polys_dev": (i32, [vp, i32, vp, _u64p, i32, _u64p, _u64p, i32, vp]),
         "etp_shard_eval_at_ext_points": (i32, [vp, _u64p, _u64p, _u64p, _u64p]),
@@ -245,6 +248,13 @@ def _fri_batches(batches):
         arr[i].polynomials = C.cast(pa, C.POINTER(FriPoly))
         arr[i].n_polynomials = len(polys)
     return arr, keep
+
+
+def poseidon_constants():
+    """(ALL_ROUND_CONSTANTS (30, 12), MDS_MATRIX_CIRC (12,), MDS_MATRIX_DIAG (12,)) as Python ints, from the library."""
+    rc, circ, diag = np.zeros(360, dtype=np.uint64), np.zeros(12, dtype=np.uint64), np.zeros(12, dtype=np.uint64)
+    load_library().etp_poseidon_constants(_p(rc), _p(circ), _p(diag))
+    return [[int(x) for x in rc[12 * r:12 * r + 12]] for r in range(30)], [int(x) for x in circ], [int(x) for x in diag]
 
 
 def _p(a: np.ndarray):
@@ -356,6 +366,15 @@ class Context:
         self.check(self.L.etp_fri_proof_of_work(self.h, C.byref(challenger), proof_of_work_bits, _p(out)))
         return int(out[0])
 
+    def compute_quotient_polys_cols_dev(self, table, lde_cols, log_n, rate_bits, challenge_scalars, public_inputs, alphas, out_ptr: int):
+        """compute_quotient_polys over a list of LDE column pointers (etp_compute_quotient_polys_cols_dev)."""
+        cols = (C.c_void_p * len(lde_cols))(*[int(c) for c in lde_cols])
+        sc = _u64(list(challenge_scalars) + [0])
+        pi = _u64(list(public_inputs) + [0])
+        a = _u64(alphas)
+        self.check(self.L.etp_compute_quotient_polys_cols_dev(self.h, table, cols, len(lde_cols), log_n, rate_bits, _p(sc), len(challenge_scalars),
+                                                              _p(pi), _p(a), a.size, C.c_void_p(out_ptr)))
+
     def stark_proof_words(self, table, log_n) -> int:
         return int(self.L.etp_stark_proof_words(self.h, table, log_n))
 
@@ -381,6 +400,13 @@ class Context:
         arr = (C.c_int32 * len(flat))(*flat)
         out = C.c_int(0)
         self.check(self.L.etp_table_register(self.h, _p(words), words.size, arr, len(flat) if lookups else 0, C.byref(out)))
+        return int(out.value)
+
+    def register_program(self, program) -> int:
+        """A constraint program that is not a starky table (etp_program_register): evaluated by compute_quotient_polys_cols_dev."""
+        words = _u64(getattr(program, "words", program))
+        out = C.c_int(0)
+        self.check(self.L.etp_program_register(self.h, _p(words), words.size, C.byref(out)))
         return int(out.value)
 
     def register_table_ex(self, program, aux_spec) -> int:

@@ -1,0 +1,614 @@
+"""Second slice of the recursion layers: plonky2's circuit prover — `plonky2::plonk::prover::prove`,
+plonky2 0.2.2 (/root/reference/Cargo.lock:3441), what every shrink / root / aggregation / block proof of the reference runs
+(/root/reference/ops/src/lib.rs:52,72,95; /root/reference/leader/src/prover.rs:26-36) — with the QUOTIENT on the device:
+
+    circuit (gates, selectors, constants, copy constraints -> sigmas)                       host, once per circuit
+    wires_commitment = from_values(witness wires)                                           device
+    Z / partial products of the permutation argument, their commitment                      device
+    compute_quotient_polys: eval_vanishing_poly_base_batch on the 8x LDE, / Z_H, coset iFFT,
+        split in quotient_degree_factor chunks; commitment                                  device  (new in this slice)
+    openings at zeta / g*zeta, prove_openings over the four-oracle FriInstanceInfo          device
+
+How the vanishing polynomial gets to the device.  plonk/vanishing_poly.rs reduces, with every alpha, ONE list of terms:
+`L_0(x)(Z_i(x) - 1)` per challenge, the partial-product checks per challenge, then the gate-constraint slots
+`sum_gates filter_gate(x) * constraint_k(x)` (evaluate_gate_constraints; filters from the selector polynomials,
+gates/selectors.rs).  That list is recorded once per circuit as a constraint program (cprog.py — the same SSA form the
+starky tables use) over a VIRTUAL column space [constants | sigmas | wires | Zs | partial products | X]; the library compiles
+it with NVRTC and `etp_compute_quotient_polys_cols_dev` evaluates it over the LDE columns of the three committed oracles plus
+the LDE of the polynomial X (the point itself), all read in place through a pointer table.  `reduce_with_powers` weights
+term i with alpha^i, the consumer of the quotient kernels weights emission i of N with alpha^(N-1-i): the terms are emitted
+in reverse.
+
+Gates (constraints restated from plonky2/src/gates/*.rs): NoopGate, ConstantGate, PublicInputGate, ArithmeticGate,
+PoseidonGate (123 constraints of degree 7; the partial rounds are written with the plain round function — the same
+polynomials in the wires as upstream's fast partial rounds, which only re-factor the linear layers).  Not built: the other
+gates of the recursive verifier circuit (base-sum, random-access, reducing, coset-interpolation, exponentiation, extension
+arithmetic), lookup tables, witness generation by generators (witnesses here are computed directly), zero-knowledge blinding
+(off in standard_recursion_config).  The circuit digest is a stand-in (hash of the constants/sigmas cap and degree_bits).
+Nothing here can be checked against real plonky2 offline: parity is against the pure-Python evaluation in the tests.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from . import cprog
+from .api import Challenger, Context, FriParams, PolynomialBatch, load_library, poseidon_constants
+
+P = 0xFFFFFFFF00000001
+NUM_WIRES, NUM_ROUTED, NUM_CHALLENGES, QUOTIENT_DEGREE_FACTOR = 135, 80, 2, 8
+RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES = 3, 4, 16, 28
+NUM_PARTIAL_PRODUCTS = -(-NUM_ROUTED // QUOTIENT_DEGREE_FACTOR) - 1  # 9
+UNUSED_SELECTOR = (1 << 32) - 1
+
+
+def root_of_unity(n_log: int) -> int:
+    return pow(1753635133440165772, 1 << (32 - n_log), P)
+
+
+def coset_shifts(num_shifts: int) -> List[int]:
+    """plonky2::field::cosets::get_unique_coset_shifts: k_j = g^j for the multiplicative generator g = 7."""
+    return [pow(7, j, P) for j in range(num_shifts)]
+
+
+# ---- Poseidon over Python ints (witness generation of PoseidonGate rows; the product hashes on the GPU) ---------------------
+_PC = None
+
+
+def _pc():
+    global _PC
+    if _PC is None:
+        _PC = poseidon_constants()
+    return _PC
+
+
+def mds_layer(state, add=None, mulc=None):
+    """res[r] = sum_i state[(i + r) % 12] * MDS_MATRIX_CIRC[i] + state[r] * MDS_MATRIX_DIAG[r] (poseidon.rs mds_row_shf)."""
+    _, circ, diag = _pc()
+    add = add or (lambda x, y: (x + y) % P)
+    mulc = mulc or (lambda x, c: x * c % P)
+    out = []
+    for r in range(12):
+        acc = None
+        for i in range(12):
+            t = mulc(state[(i + r) % 12], circ[i])
+            acc = t if acc is None else add(acc, t)
+        if diag[r]:
+            acc = add(acc, mulc(state[r], diag[r]))
+        out.append(acc)
+    return out
+
+
+def poseidon_gate_wires(inputs: Sequence[int], swap: int) -> List[int]:
+    """All 135 wires of one PoseidonGate row (gates/poseidon.rs PoseidonGenerator::run_once): inputs, outputs, swap, deltas
+    and the S-box inputs of every round after the first."""
+    rc, _, _ = _pc()
+    w = [0] * NUM_WIRES
+    inputs = [int(x) % P for x in inputs]
+    w[0:12] = inputs
+    w[PoseidonGate.WIRE_SWAP] = swap
+    state = list(inputs)
+    for i in range(4):
+        delta = swap * (inputs[i + 4] - inputs[i]) % P
+        w[PoseidonGate.wire_delta(i)] = delta
+        state[i] = (inputs[i] + delta) % P
+        state[i + 4] = (inputs[i + 4] - delta) % P
+    rnd = 0
+    for r in range(4):
+        state = [(s + c) % P for s, c in zip(state, rc[rnd])]
+        if r != 0:
+            for i in range(12):
+                w[PoseidonGate.wire_full_sbox_0(r, i)] = state[i]
+        state = mds_layer([pow(s, 7, P) for s in state])
+        rnd += 1
+    for r in range(22):
+        state = [(s + c) % P for s, c in zip(state, rc[rnd])]
+        w[PoseidonGate.wire_partial_sbox(r)] = state[0]
+        state[0] = pow(state[0], 7, P)
+        state = mds_layer(state)
+        rnd += 1
+    for r in range(4):
+        state = [(s + c) % P for s, c in zip(state, rc[rnd])]
+        for i in range(12):
+            w[PoseidonGate.wire_full_sbox_1(r, i)] = state[i]
+        state = mds_layer([pow(s, 7, P) for s in state])
+        rnd += 1
+    w[12:24] = state
+    return w
+
+
+def hash_no_pad(elements: Sequence[int]) -> List[int]:
+    """PoseidonHash::hash_no_pad (overwrite-mode sponge, rate 8) with the library's host permutation."""
+    import ctypes as C
+
+    L = load_library()
+    st = (C.c_uint64 * 12)()
+    elements = [int(x) % P for x in elements]
+    for off in range(0, len(elements), 8):
+        for k, v in enumerate(elements[off:off + 8]):
+            st[k] = v
+        L.etp_host_poseidon_permute(st)
+    return [int(st[k]) for k in range(4)]
+
+
+# ---- gates ---------------------------------------------------------------------------------------------------------------------
+class Gate:
+    """eval(b, wire, const, pi) -> the gate's constraints as cprog expressions (Gate::eval_unfiltered); wire(j) / const(j):
+    local wire j / the gate's j-th constant (selectors already stripped), pi(i): public_inputs_hash[i]."""
+    name, degree, num_constants, num_constraints = "gate", 0, 0, 0
+
+    def eval(self, b, wire, const, pi):
+        return []
+
+    def id(self):
+        return self.name
+
+
+class NoopGate(Gate):
+    name = "NoopGate"
+
+
+class ConstantGate(Gate):
+    """gates/constant.rs: wire_i - const_i."""
+
+    def __init__(self, num_consts: int = 2):
+        self.name, self.degree, self.num_constants, self.num_constraints = f"ConstantGate {{ num_consts: {num_consts} }}", 1, num_consts, num_consts
+
+    def eval(self, b, wire, const, pi):
+        return [const(i) - wire(i) for i in range(self.num_constants)]
+
+
+class PublicInputGate(Gate):
+    """gates/public_input.rs: wires 0..4 - public_inputs_hash."""
+    name, degree, num_constants, num_constraints = "PublicInputGate", 1, 0, 4
+
+    def eval(self, b, wire, const, pi):
+        return [wire(i) - pi(i) for i in range(4)]
+
+
+class ArithmeticGate(Gate):
+    """gates/arithmetic_base.rs: per operation  output - (multiplicand_0 * multiplicand_1 * const_0 + addend * const_1)."""
+
+    def __init__(self, num_ops: int = 20):
+        self.num_ops = num_ops
+        self.name, self.degree, self.num_constants, self.num_constraints = f"ArithmeticGate {{ num_ops: {num_ops} }}", 3, 2, num_ops
+
+    def eval(self, b, wire, const, pi):
+        out = []
+        for i in range(self.num_ops):
+            m0, m1, addend, output = wire(4 * i), wire(4 * i + 1), wire(4 * i + 2), wire(4 * i + 3)
+            out.append(output - (m0 * m1 * const(0) + addend * const(1)))
+        return out
+
+
+class PoseidonGate(Gate):
+    """gates/poseidon.rs: one permutation per row, with an optional swap of the two 4-element input halves (Merkle paths)."""
+    name, degree, num_constants, num_constraints = "PoseidonGate", 7, 0, 123
+    WIRE_SWAP = 24
+    START_DELTA, START_FULL_0, START_PARTIAL, START_FULL_1 = 25, 29, 65, 87
+
+    @staticmethod
+    def wire_delta(i):
+        return PoseidonGate.START_DELTA + i
+
+    @staticmethod
+    def wire_full_sbox_0(rnd, i):  # rnd 1..3
+        return PoseidonGate.START_FULL_0 + 12 * (rnd - 1) + i
+
+    @staticmethod
+    def wire_partial_sbox(rnd):
+        return PoseidonGate.START_PARTIAL + rnd
+
+    @staticmethod
+    def wire_full_sbox_1(rnd, i):
+        return PoseidonGate.START_FULL_1 + 12 * rnd + i
+
+    def eval(self, b, wire, const, pi):
+        rc, _, _ = _pc()
+        cons = []
+        swap = wire(self.WIRE_SWAP)
+        cons.append(swap * (swap - 1))
+        state = [None] * 12
+        for i in range(4):
+            lhs, rhs, delta = wire(i), wire(i + 4), wire(self.wire_delta(i))
+            cons.append(swap * (rhs - lhs) - delta)
+            state[i], state[i + 4] = lhs + delta, rhs - delta
+        for i in range(8, 12):
+            state[i] = wire(i)
+
+        def sbox(x):
+            x2 = x * x
+            x4 = x2 * x2
+            return x4 * (x2 * x)
+
+        def mds(st):
+            return mds_layer(st, add=lambda x, y: x + y, mulc=lambda x, c: x * b.const(c))
+
+        rnd = 0
+        for r in range(4):
+            state = [s + b.const(c) for s, c in zip(state, rc[rnd])]
+            if r != 0:
+                for i in range(12):
+                    sbox_in = wire(self.wire_full_sbox_0(r, i))
+                    cons.append(state[i] - sbox_in)
+                    state[i] = sbox_in
+            state = mds([sbox(s) for s in state])
+            rnd += 1
+        for r in range(22):
+            state = [s + b.const(c) for s, c in zip(state, rc[rnd])]
+            sbox_in = wire(self.wire_partial_sbox(r))
+            cons.append(state[0] - sbox_in)
+            state[0] = sbox(sbox_in)
+            state = mds(state)
+            rnd += 1
+        for r in range(4):
+            state = [s + b.const(c) for s, c in zip(state, rc[rnd])]
+            for i in range(12):
+                sbox_in = wire(self.wire_full_sbox_1(r, i))
+                cons.append(state[i] - sbox_in)
+                state[i] = sbox_in
+            state = mds([sbox(s) for s in state])
+            rnd += 1
+        for i in range(12):
+            cons.append(state[i] - wire(12 + i))
+        assert len(cons) == self.num_constraints
+        return cons
+
+
+# ---- selectors (gates/selectors.rs) -----------------------------------------------------------------------------------------------
+def selector_groups(gates: Sequence[Gate], max_degree: int) -> List[range]:
+    """Greedy grouping of the (degree-sorted) gates: a group of `size` gates costs a filter of degree size - 1 (+ 1 for the
+    UNUSED factor when there are several groups), so size + degree of its last gate must stay below max_degree."""
+    n = len(gates)
+    if max(g.degree for g in gates) + n - 1 <= max_degree:
+        return [range(0, n)]
+    groups, start = [], 0
+    while start < n:
+        size = 0
+        while start + size < n and size + gates[start + size].degree < max_degree:
+            size += 1
+        assert size > 0, "a gate of this degree does not fit the quotient degree factor"
+        groups.append(range(start, start + size))
+        start += size
+    return groups
+
+
+class Circuit:
+    """CommonCircuitData + ProverOnlyCircuitData, as far as the prover steps here need them."""
+
+    # virtual column space of the vanishing program
+    def col_const(self, j):
+        return j
+
+    def col_sigma(self, j):
+        return self.num_constants + j
+
+    def col_wire(self, j):
+        return self.num_constants + NUM_ROUTED + j
+
+    def col_z(self, i):
+        return self.num_constants + NUM_ROUTED + NUM_WIRES + i
+
+    def col_pp(self, i, k):
+        return self.num_constants + NUM_ROUTED + NUM_WIRES + NUM_CHALLENGES + i * NUM_PARTIAL_PRODUCTS + k
+
+    @property
+    def col_x(self):
+        return self.num_constants + NUM_ROUTED + NUM_WIRES + NUM_CHALLENGES * (1 + NUM_PARTIAL_PRODUCTS)
+
+    @property
+    def num_virtual_columns(self):
+        return self.col_x + 1
+
+    def __init__(self, degree_bits: int, gates: List[Gate], gate_of_row: np.ndarray, gate_constants: np.ndarray, sigmas: np.ndarray,
+                 num_public_inputs: int):
+        self.degree_bits, self.n = degree_bits, 1 << degree_bits
+        self.gates = gates
+        self.groups = selector_groups(gates, QUOTIENT_DEGREE_FACTOR)
+        self.num_selectors = len(self.groups)
+        self.num_gate_constants = max(g.num_constants for g in gates)
+        self.num_constants = self.num_selectors + self.num_gate_constants
+        self.num_gate_constraints = max(g.num_constraints for g in gates)
+        self.num_public_inputs = num_public_inputs
+        self.k_is = coset_shifts(NUM_ROUTED)
+        self.gate_of_row = gate_of_row
+        # constants = selector polynomials ++ gate constants
+        consts = np.zeros((self.num_constants, self.n), dtype=np.uint64)
+        for s, grp in enumerate(self.groups):
+            in_group = (gate_of_row >= grp.start) & (gate_of_row < grp.stop)
+            consts[s] = np.where(in_group, gate_of_row, UNUSED_SELECTOR).astype(np.uint64)
+        consts[self.num_selectors:] = gate_constants
+        self.constants, self.sigmas = consts, sigmas
+        self.program = self._vanishing_program()
+
+    def selector_index(self, gate_index: int) -> int:
+        return next(s for s, grp in enumerate(self.groups) if gate_index in grp)
+
+    def _vanishing_program(self) -> cprog.Program:
+        """eval_vanishing_poly as ONE constraint program (module docstring).  CH 0..1 = betas, CH 2..3 = gammas; PI 0..3 =
+        public_inputs_hash; X = the point (a virtual column)."""
+        b = cprog.ProgramBuilder(self.num_virtual_columns, 4, QUOTIENT_DEGREE_FACTOR + 1)
+        one = b.const(1)
+        x = b.lv(self.col_x)
+        wire = lambda j: b.lv(self.col_wire(j))
+        # ---- evaluate_gate_constraints: slot k = sum over gates of filter * constraint k
+        slots = [None] * self.num_gate_constraints
+        many = self.num_selectors > 1
+        for gi, gate in enumerate(self.gates):
+            if gate.num_constraints == 0:
+                continue
+            s_idx = self.selector_index(gi)
+            s = b.lv(self.col_const(s_idx))
+            filt = None
+            for i in self.groups[s_idx]:  # compute_filter: prod_{i in group, i != row} (i - s) [* (UNUSED - s)]
+                if i != gi:
+                    f = b.const(i) - s
+                    filt = f if filt is None else filt * f
+            if many:
+                f = b.const(UNUSED_SELECTOR) - s
+                filt = f if filt is None else filt * f
+            const = lambda j: b.lv(self.col_const(self.num_selectors + j))
+            for k, c in enumerate(gate.eval(b, wire, const, b.pi)):
+                t = c if filt is None else filt * c
+                slots[k] = t if slots[k] is None else slots[k] + t
+        zero = b.const(0)
+        slots = [zero if s is None else s for s in slots]
+        # ---- permutation argument
+        z_1_terms, pp_terms = [], []
+        for i in range(NUM_CHALLENGES):
+            beta, gamma = b.challenge(i), b.challenge(NUM_CHALLENGES + i)
+            z_x, z_gx = b.lv(self.col_z(i)), b.nv(self.col_z(i))
+            z_1_terms.append(("first", z_x - one))  # L_0(x) (Z(x) - 1): the consumer's first-row selector is L_0
+            num = [wire(j) + beta * (x * b.const(self.k_is[j])) + gamma for j in range(NUM_ROUTED)]
+            den = [wire(j) + beta * b.lv(self.col_sigma(j)) + gamma for j in range(NUM_ROUTED)]
+            accs = [z_x] + [b.lv(self.col_pp(i, k)) for k in range(NUM_PARTIAL_PRODUCTS)] + [z_gx]
+            for c in range(0, NUM_ROUTED, QUOTIENT_DEGREE_FACTOR):  # check_partial_products
+                prod = lambda xs: xs[0] if len(xs) == 1 else prod(xs[:len(xs) // 2]) * prod(xs[len(xs) // 2:])
+                k = c // QUOTIENT_DEGREE_FACTOR
+                pp_terms.append(("all", accs[k] * prod(num[c:c + 8]) - accs[k + 1] * prod(den[c:c + 8])))
+        terms = z_1_terms + pp_terms + [("all", s) for s in slots]
+        for kind, e in reversed(terms):  # reduce_with_powers: term i * alpha^i
+            (b.first_row if kind == "first" else b.constraint)(e)
+        self.num_vanishing_terms = len(terms)
+        return b.build()
+
+    def virtual_trace(self, wires: np.ndarray, zs_pp: np.ndarray) -> np.ndarray:
+        """[constants | sigmas | wires | Zs | partial products | X] on the trace domain (tests: Program.check_trace)."""
+        g = root_of_unity(self.degree_bits)
+        xs = np.zeros(self.n, dtype=np.uint64)
+        cur = 1
+        for i in range(self.n):
+            xs[i] = cur
+            cur = cur * g % P
+        return np.concatenate([self.constants, self.sigmas, wires, zs_pp, xs[None, :]], axis=0)
+
+
+class CircuitBuilder:
+    """Rows of gates with their constants, copy constraints between routed wires, direct wire assignment (no generators)."""
+
+    def __init__(self):
+        self.rows: List[Tuple[Gate, List[int]]] = []
+        self.wires: List[List[int]] = []
+        self.copies: List[Tuple[Tuple[int, int], Tuple[int, int]]] = []
+        self.public_inputs: List[int] = []
+
+    def add_gate(self, gate: Gate, constants: Sequence[int] = (), wires: Sequence[int] = None) -> int:
+        self.rows.append((gate, [int(c) % P for c in constants]))
+        w = [0] * NUM_WIRES
+        if wires is not None:
+            w[:len(wires)] = [int(v) % P for v in wires]
+        self.wires.append(w)
+        return len(self.rows) - 1
+
+    def connect(self, a: Tuple[int, int], b_: Tuple[int, int]):
+        assert a[1] < NUM_ROUTED and b_[1] < NUM_ROUTED, "only routed wires can be copy-constrained"
+        assert self.wires[a[0]][a[1]] == self.wires[b_[0]][b_[1]], f"copy constraint between different values {a} {b_}"
+        self.copies.append((a, b_))
+
+    def build(self, min_degree_bits: int = 0):
+        """-> (Circuit, wires (135, n)).  Gates are sorted by (degree, id) as CircuitBuilder::build does; rows are padded with
+        NoopGates to a power of two."""
+        n_rows = max(len(self.rows), 2)
+        degree_bits = max((n_rows - 1).bit_length(), min_degree_bits)
+        n = 1 << degree_bits
+        noop = next((g for g, _ in self.rows if isinstance(g, NoopGate)), NoopGate())
+        rows = self.rows + [(noop, [])] * (n - len(self.rows))
+        wires = np.zeros((NUM_WIRES, n), dtype=np.uint64)
+        wires[:, :len(self.wires)] = np.array(self.wires, dtype=np.uint64).T
+        uniq: Dict[str, Gate] = {}
+        for g, _ in rows:
+            uniq.setdefault(g.id(), g)
+        gates = sorted(uniq.values(), key=lambda g: (g.degree, g.id()))
+        index = {g.id(): i for i, g in enumerate(gates)}
+        gate_of_row = np.array([index[g.id()] for g, _ in rows], dtype=np.int64)
+        n_gc = max(g.num_constants for g in gates)
+        gate_constants = np.zeros((n_gc, n), dtype=np.uint64)
+        for r, (g, cs) in enumerate(rows):
+            for j, c in enumerate(cs):
+                gate_constants[j, r] = c
+        # copy constraints -> partition of the routed wire positions -> sigma: every position maps to the next of its set
+        parent = list(range(NUM_ROUTED * n))  # position = column * n + row
+
+        def find(u):
+            while parent[u] != u:
+                parent[u] = parent[parent[u]]
+                u = parent[u]
+            return u
+
+        for (r0, c0), (r1, c1) in self.copies:
+            a, b_ = find(c0 * n + r0), find(c1 * n + r1)
+            if a != b_:
+                parent[a] = b_
+        sets: Dict[int, List[int]] = {}
+        for pos in sorted({c * n + r for pair in self.copies for (r, c) in pair}):
+            sets.setdefault(find(pos), []).append(pos)
+        g = root_of_unity(degree_bits)
+        xs = [1]
+        for _ in range(n - 1):
+            xs.append(xs[-1] * g % P)
+        k_is = coset_shifts(NUM_ROUTED)
+        sig = np.zeros(NUM_ROUTED * n, dtype=np.uint64)
+        for c in range(NUM_ROUTED):
+            col = np.array([k_is[c] * x % P for x in xs], dtype=np.uint64)
+            sig[c * n:(c + 1) * n] = col
+        ident = lambda pos: k_is[pos // n] * xs[pos % n] % P
+        for members in sets.values():
+            for a, b_ in zip(members, members[1:] + members[:1]):
+                sig[a] = ident(b_)
+        circuit = Circuit(degree_bits, gates, gate_of_row, gate_constants, sig.reshape(NUM_ROUTED, n), len(self.public_inputs))
+        return circuit, wires
+
+
+def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float = 0.6, arithmetic_fraction: float = 0.3):
+    """A recursion-verifier-shaped synthetic circuit with its witness: the public inputs are hashed in-circuit (PoseidonGate
+    row wired to the PublicInputGate), a Merkle-path-like chain of swapped PoseidonGates, chains of ArithmeticGate operations,
+    constants through a ConstantGate — all linked by copy constraints — padded with NoopGates to 2^degree_bits rows.
+    -> (Circuit, wires (135, n), public_inputs)"""
+    rng = np.random.default_rng(seed)
+    n = 1 << degree_bits
+    cb = CircuitBuilder()
+    rnd = lambda: int(rng.integers(0, 2**63)) % P
+    public_inputs = [rnd() for _ in range(8)]
+    cb.public_inputs = list(public_inputs)
+    pi_hash = hash_no_pad(public_inputs)
+    r_pi = cb.add_gate(PublicInputGate(), wires=pi_hash)
+    r_const = cb.add_gate(ConstantGate(2), constants=[0, 1], wires=[0, 1])
+    pos = PoseidonGate()
+    w = poseidon_gate_wires(public_inputs + [0, 0, 0, 0], 0)
+    r_h = cb.add_gate(pos, wires=w)
+    assert w[12:16] == pi_hash
+    for i in range(4):
+        cb.connect((r_h, 12 + i), (r_pi, i))
+        cb.connect((r_h, 8 + i), (r_const, 0))
+    cb.connect((r_h, PoseidonGate.WIRE_SWAP), (r_const, 0))
+    budget = n - len(cb.rows)
+    n_pos = max(int(budget * poseidon_fraction), 1)
+    n_ar = max(int(budget * arithmetic_fraction), 1)
+    prev_row, digest = r_h, w[12:16]
+    for _ in range(n_pos):  # Merkle-path shape: state = hash(swap ? (sibling, state) : (state, sibling))
+        swap = int(rng.integers(0, 2))
+        sibling = [rnd() for _ in range(4)]
+        w = poseidon_gate_wires(list(digest) + sibling + [0, 0, 0, 0], swap)
+        r = cb.add_gate(pos, wires=w)
+        for i in range(4):
+            cb.connect((r, i), (prev_row, 12 + i))
+            cb.connect((r, 8 + i), (r_const, 0))
+        prev_row, digest = r, w[12:16]
+    ar = ArithmeticGate(20)
+    prev = None
+    for _ in range(n_ar):
+        c0, c1 = rnd(), rnd()
+        w = [0] * (4 * ar.num_ops)
+        r = len(cb.rows)
+        links = []
+        for i in range(ar.num_ops):
+            m0 = prev[2] if prev is not None else rnd()
+            m1, addend = rnd(), rnd()
+            out = (m0 * m1 % P * c0 + addend * c1) % P
+            w[4 * i:4 * i + 4] = [m0, m1, addend, out]
+            if prev is not None:
+                links.append(((r, 4 * i), (prev[0], prev[1])))
+            prev = (r, 4 * i + 3, out)
+        cb.add_gate(ar, constants=[c0, c1], wires=w)
+        for a, b_ in links:
+            cb.connect(a, b_)
+    return (*cb.build(degree_bits), public_inputs)
+
+
+# ---- the prover -----------------------------------------------------------------------------------------------------------------
+class CircuitProver:
+    """Per-circuit state built once (ProverOnlyCircuitData / CommonCircuitData): the constants/sigmas commitment, the digest,
+    the compiled vanishing program, the LDE of X; `prove(wires, public_inputs)` runs plonk::prover::prove's steps on the device."""
+
+    def __init__(self, ctx: Context, circuit: Circuit):
+        self.ctx, self.c = ctx, circuit
+        n = circuit.n
+        self.constants_sigmas = PolynomialBatch.from_values(ctx, np.concatenate([circuit.constants, circuit.sigmas]), RATE_BITS, False, CAP_HEIGHT)
+        self.digest = hash_no_pad([int(v) for v in np.asarray(self.constants_sigmas.cap).reshape(-1)] + [circuit.degree_bits])
+        self.table = ctx.register_program(circuit.program)
+        x_coeffs = np.zeros((1, n), dtype=np.uint64)
+        x_coeffs[0, 1] = 1
+        self.x_poly = PolynomialBatch.from_coeffs(ctx, x_coeffs, RATE_BITS, False, 0)  # its LDE column is the point itself
+        self.fri_params = FriParams.make(circuit.degree_bits, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES)
+
+    def fri_instance(self, zeta):
+        """CommonCircuitData::get_fri_instance: zeta opens every polynomial of the four oracles, g*zeta the Zs."""
+        c = self.c
+        g = root_of_unity(c.degree_bits)
+        zeta_next = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
+        shapes = [c.num_constants + NUM_ROUTED, NUM_WIRES, NUM_CHALLENGES * (1 + NUM_PARTIAL_PRODUCTS), NUM_CHALLENGES * QUOTIENT_DEGREE_FACTOR]
+        all_polys = [(o, k) for o, cnt in enumerate(shapes) for k in range(cnt)]
+        return [([int(zeta[0]), int(zeta[1])], all_polys), (zeta_next, [(2, k) for k in range(NUM_CHALLENGES)])]
+
+    def prove(self, wires: np.ndarray, public_inputs: Sequence[int]) -> dict:
+        import ctypes as C
+
+        import torch
+
+        ctx, c = self.ctx, self.c
+        n, L = c.n, ctx.L
+        t = {}
+        pi_hash = hash_no_pad(public_inputs)
+        ch = Challenger()
+        ch.observe(self.digest)
+        ch.observe(pi_hash)
+        t0 = time.perf_counter()
+        d_wires = torch.from_numpy(np.ascontiguousarray(wires).view(np.int64)).cuda()
+        d_sig = torch.from_numpy(np.ascontiguousarray(c.sigmas).view(np.int64)).cuda()
+        torch.cuda.synchronize()
+        t["upload wires"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        wires_b = PolynomialBatch.from_values_dev(ctx, d_wires.data_ptr(), n, NUM_WIRES, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
+        t["wires commit"] = (time.perf_counter() - t0) * 1e3
+        ch.observe_cap(wires_b.cap)
+        betas, gammas = ch.get_n_challenges(NUM_CHALLENGES), ch.get_n_challenges(NUM_CHALLENGES)
+        n_zs = NUM_CHALLENGES * (1 + NUM_PARTIAL_PRODUCTS)
+        d_z = torch.empty((n_zs, n), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.plonk_partial_products_and_zs_dev(d_wires.data_ptr(), n, d_sig.data_ptr(), n, np.array(c.k_is, dtype=np.uint64), c.degree_bits,
+                                              QUOTIENT_DEGREE_FACTOR, betas, gammas, d_z.data_ptr())
+        zs_b = PolynomialBatch.from_values_dev(ctx, d_z.data_ptr(), n, n_zs, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
+        t["partial products and Zs + commit"] = (time.perf_counter() - t0) * 1e3
+        ch.observe_cap(zs_b.cap)
+        alphas = ch.get_n_challenges(NUM_CHALLENGES)
+        # ---- compute_quotient_polys over the virtual columns [constants | sigmas | wires | Zs | partial products | X]
+        t0 = time.perf_counter()
+        cols = []
+        for batch in (self.constants_sigmas, wires_b, zs_b, self.x_poly):
+            stride = C.c_size_t()
+            base = L.etp_batch_lde_dev(batch.h, C.byref(stride))
+            cols += [int(base) + 8 * k * stride.value for k in range(batch.n_cols)]
+        assert len(cols) == c.num_virtual_columns
+        n_q = NUM_CHALLENGES * QUOTIENT_DEGREE_FACTOR
+        d_q = torch.empty((n_q, n), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.compute_quotient_polys_cols_dev(self.table, cols, c.degree_bits, RATE_BITS, list(betas) + list(gammas), pi_hash, alphas, d_q.data_ptr())
+        t["compute quotient polys"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        quot_b = PolynomialBatch.from_coeffs_dev(ctx, d_q.data_ptr(), n, n_q, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
+        t["quotient commit"] = (time.perf_counter() - t0) * 1e3
+        ch.observe_cap(quot_b.cap)
+        zeta = ch.get_extension_challenge()
+        oracles = [self.constants_sigmas, wires_b, zs_b, quot_b]
+        g = root_of_unity(c.degree_bits)
+        zeta_next = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
+        t0 = time.perf_counter()
+        openings = [o.eval_at_ext_point(zeta) for o in oracles]
+        zs_next = zs_b.eval_at_ext_point(zeta_next)[:NUM_CHALLENGES]
+        t["openings"] = (time.perf_counter() - t0) * 1e3
+        for o in openings:  # OpeningSet order: constants, plonk_sigmas, wires, plonk_zs, partial_products, quotient_polys; then plonk_zs_next
+            ch.observe(o)
+        ch.observe(zs_next)
+        t0 = time.perf_counter()
+        fri = ctx.prove_openings(self.fri_instance(zeta), oracles, ch, self.fri_params)
+        t["prove_openings (FRI)"] = (time.perf_counter() - t0) * 1e3
+        t["total"] = sum(t.values())
+        return {"degree_bits": c.degree_bits, "public_inputs": [int(x) % P for x in public_inputs],
+                "wires_cap": wires_b.cap.copy(), "plonk_zs_partial_products_cap": zs_b.cap.copy(), "quotient_polys_cap": quot_b.cap.copy(),
+                "openings": {"constants_sigmas": openings[0], "wires": openings[1], "zs_partial_products": openings[2], "quotient_polys": openings[3],
+                             "plonk_zs_next": zs_next},
+                "opening_proof": fri, "ms": t,
+                "quotient_coeffs": d_q.cpu().numpy().view(np.uint64) if n <= (1 << 8) else None}

@@ -205,6 +205,7 @@ struct RegisteredTable {
   cprog::Program prog;
   JitKernel kernel;
   JitKernel kernel_split;  // the same program reading its trace columns through a pointer table (etp_shard), compiled on first use
+  bool standalone = false;  // etp_program_register: not a starky table (no StarkConfig limits); only the pointer-table kernel exists
   uint64_t* d_spec = nullptr;  // the aux spec words on the device (general lookups / CTL), uploaded on first use
 };
 void free_registered_tables(etp_ctx* ctx) {
@@ -496,9 +497,12 @@ int compute_quotient(etp_ctx* ctx, int table, const TraceView& trace, etp_batch*
                     ti.reg->prog.n_aux, ti.reg->prog.n_ch, n_aux, n_scalars);
   const int log_n = trace.log_n, rate_bits = trace.rate_bits;
   const bool split = trace.cols_dev != nullptr;
+  if (ti.reg && ti.reg->standalone && !split)
+    return etp_fail(ctx, ETP_ERR_INVALID, "a standalone program (etp_program_register) is evaluated through etp_compute_quotient_polys_cols_dev");
   const int factor = quotient_factor(ti), qbits = log2_ceil(factor);
   if (qbits > rate_bits)
     return etp_fail(ctx, ETP_ERR_INVALID, "Having constraints of degree higher than the rate is not supported yet.");
+  if (qbits > 3) return etp_fail(ctx, ETP_ERR_INVALID, "quotient degree factors above 8 are not supported");
   const int log_size = log_n + qbits, log_lde = log_n + rate_bits;
   const size_t size = (size_t)1 << log_size;
   stark::QuotientParams q{};
@@ -1257,9 +1261,10 @@ extern "C" int etp_table_num_ctl_helper_columns(const etp_ctx* c, int t) { Table
 extern "C" int etp_table_num_ctl_zs(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? ti.n_ctl_zs() : -1; }
 extern "C" int etp_table_quotient_degree_factor(const etp_ctx* c, int t) { TableInfo ti; return table_info(c, t, &ti) ? quotient_factor(ti) : -1; }
 
-static int register_table(etp_ctx* ctx, const uint64_t* program, size_t n_words, const std::vector<uint64_t>& spec_words, int* table_id_out) {
+static int register_table(etp_ctx* ctx, const uint64_t* program, size_t n_words, const std::vector<uint64_t>& spec_words, int* table_id_out,
+                          bool standalone = false) {
   auto t = new RegisteredTable();
-  struct Guard { RegisteredTable* t; ~Guard() { if (t) { jit_unload(&t->kernel); delete t; } } } guard{t};
+  struct Guard { RegisteredTable* t; ~Guard() { if (t) { jit_unload(&t->kernel); jit_unload(&t->kernel_split); delete t; } } } guard{t};
   const std::string why = cprog::parse(program, n_words, stark::MAX_PUBLIC_INPUTS, stark::MAX_CH_SCALARS, &t->prog);
   if (!why.empty()) return etp_fail(ctx, ETP_ERR_INVALID, "%s", why.c_str());
   TableInfo& ti = t->info;
@@ -1274,16 +1279,18 @@ static int register_table(etp_ctx* ctx, const uint64_t* program, size_t n_words,
   if ((int)t->prog.n_aux != ti.n_aux(NUM_CHALLENGES))
     return etp_fail(ctx, ETP_ERR_INVALID, "table: the program reads %u auxiliary columns but the lookups / CTLs produce %d", t->prog.n_aux,
                     ti.n_aux(NUM_CHALLENGES));
-  if ((int)t->prog.n_ch > (ti.ctl() ? 3 * NUM_CHALLENGES : (ti.lookup() ? NUM_CHALLENGES : 0)))
+  t->standalone = standalone;
+  if (!standalone && (int)t->prog.n_ch > (ti.ctl() ? 3 * NUM_CHALLENGES : (ti.lookup() ? NUM_CHALLENGES : 0)))
     return etp_fail(ctx, ETP_ERR_INVALID, "table: the program reads %u challenge scalars, more than its lookups / CTLs provide", t->prog.n_ch);
-  if (log2_ceil(quotient_factor(ti)) > RATE_BITS)
+  if (!standalone && log2_ceil(quotient_factor(ti)) > RATE_BITS)
     return etp_fail(ctx, ETP_ERR_INVALID, "Having constraints of degree higher than the rate is not supported yet.");
+  if (standalone && quotient_factor(ti) > 8) return etp_fail(ctx, ETP_ERR_INVALID, "quotient degree factors above 8 are not supported");
   // compile now so that errors surface at registration, not in the middle of a proof (compiled programs are cached
   // per process: etp_jit.cu)
   std::vector<char> cubin;
   std::string log;
-  ETP_TRY(jit_compile(ctx, cprog::generate_cuda(t->prog), &cubin, &log));
-  ETP_TRY(jit_load(ctx, cubin, "etp_cprog_quotient", &t->kernel));
+  ETP_TRY(jit_compile(ctx, cprog::generate_cuda(t->prog, standalone), &cubin, &log));
+  ETP_TRY(jit_load(ctx, cubin, "etp_cprog_quotient", standalone ? &t->kernel_split : &t->kernel));
   ctx->tables.push_back(t);
   guard.t = nullptr;
   *table_id_out = ETP_TABLE_FIRST_REGISTERED + (int)ctx->tables.size() - 1;
@@ -1327,6 +1334,14 @@ extern "C" int etp_table_register_ex(etp_ctx* ctx, const uint64_t* program, size
   return register_table(ctx, program, n_words, std::vector<uint64_t>(aux_spec, aux_spec + n_spec_words), table_id_out);
 }
 
+// A constraint program that is not a starky table: any constraint degree up to 9, up to MAX_CH_SCALARS challenge scalars, no
+// auxiliary polynomials — the plonky2 circuit prover's vanishing polynomial (etp_compute_quotient_polys_cols_dev).
+extern "C" int etp_program_register(etp_ctx* ctx, const uint64_t* program, size_t n_words, int* table_id_out) {
+  etp_bind(ctx);
+  if (!ctx || !program || !table_id_out) return ETP_ERR_INVALID;
+  return register_table(ctx, program, n_words, std::vector<uint64_t>(), table_id_out, true);
+}
+
 extern "C" int etp_aux_columns_dev(etp_ctx* ctx, int table, int log_n, const uint64_t* trace_dev, size_t col_stride,
                                    const uint64_t* lookup_challenges, int n_challenges, const uint64_t* ctl_challenges, uint64_t* aux_dev) {
   etp_bind(ctx);
@@ -1357,6 +1372,37 @@ extern "C" int etp_compute_quotient_polys_dev(etp_ctx* ctx, int table, etp_batch
   ETP_TRY(compute_quotient(ctx, table, trace, aux, lookup_challenges ? lookup_challenges : zero, n_lookup_challenges,
                            public_inputs ? public_inputs : zero, alphas, n_alphas, out_dev));
   ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return ETP_OK;
+}
+
+// compute_quotient_polys over an arbitrary list of LDE columns (one device pointer per virtual trace column): the form the
+// plonky2 circuit prover needs — its vanishing polynomial reads the constants / sigmas, wires and Z / partial-product
+// oracles (three PolynomialBatches) and the point x itself (the LDE of the polynomial X) as ONE program's columns.
+extern "C" int etp_compute_quotient_polys_cols_dev(etp_ctx* ctx, int table, const uint64_t* const* lde_cols, size_t n_cols, int log_n, int rate_bits,
+                                                   const uint64_t* challenge_scalars, int n_scalars, const uint64_t* public_inputs, const uint64_t* alphas,
+                                                   int n_alphas, uint64_t* out_dev) {
+  etp_bind(ctx);
+  if (!ctx || !lde_cols || !alphas || !out_dev || (n_scalars && !challenge_scalars)) return ETP_ERR_INVALID;
+  TableInfo ti;
+  if (!table_info(ctx, table, &ti)) return etp_fail(ctx, ETP_ERR_INVALID, "unknown table %d", table);
+  if (ti.lookup() || ti.ctl()) return etp_fail(ctx, ETP_ERR_INVALID, "tables with auxiliary polynomials take etp_compute_quotient_polys_dev");
+  if (ti.n_pi && !public_inputs) return ETP_ERR_INVALID;
+  if (log_n < 1 || rate_bits < 0 || log_n + rate_bits > 30) return etp_fail(ctx, ETP_ERR_INVALID, "bad degree / rate");
+  if ((size_t)ti.cols != n_cols) return etp_fail(ctx, ETP_ERR_INVALID, "the table has %d columns, %zu were given", ti.cols, n_cols);
+  std::vector<uint64_t> cols(n_cols);
+  for (size_t c = 0; c < n_cols; c++) {
+    if (!lde_cols[c]) return etp_fail(ctx, ETP_ERR_INVALID, "null column %zu", c);
+    cols[c] = (uint64_t)(uintptr_t)lde_cols[c];
+  }
+  DevBuf<uint64_t> d_cols(ctx);
+  ETP_TRY(d_cols.alloc(n_cols));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), n_cols * 8, cudaMemcpyHostToDevice, ctx->stream));
+  TraceView tv;
+  tv.cols_dev = (const uint64_t* const*)d_cols.p; tv.n_cols = n_cols; tv.log_n = log_n; tv.rate_bits = rate_bits;
+  uint64_t zero[stark::MAX_PUBLIC_INPUTS] = {};
+  ETP_TRY(compute_quotient(ctx, table, tv, nullptr, n_scalars ? challenge_scalars : zero, n_scalars, public_inputs ? public_inputs : zero, alphas,
+                           n_alphas, out_dev));
+  ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // cols / d_cols are read until here
   return ETP_OK;
 }
 

@@ -126,3 +126,12 @@ extern "C" void etp_host_poseidon_permute(uint64_t s[12]) {
 #endif
   permute<mds_scalar>(s);
 }
+
+// The parameters of the permutation, for callers that build circuits over it (plonky2's PoseidonGate evaluates the
+// permutation symbolically): ALL_ROUND_CONSTANTS (30 x 12), MDS_MATRIX_CIRC, MDS_MATRIX_DIAG.
+extern "C" void etp_poseidon_constants(uint64_t round_constants_out[360], uint64_t mds_circ_out[12], uint64_t mds_diag_out[12]) {
+  static const uint64_t circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  for (int i = 0; i < 360 && round_constants_out; i++) round_constants_out[i] = RC[i];
+  for (int i = 0; i < 12 && mds_circ_out; i++) mds_circ_out[i] = circ[i];
+  for (int i = 0; i < 12 && mds_diag_out; i++) mds_diag_out[i] = i == 0 ? 8 : 0;
+}

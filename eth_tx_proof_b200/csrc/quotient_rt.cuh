@@ -76,7 +76,7 @@ struct QuotientParams {
   ntt::PowTable coset;  // 7 * w_size^i
   const uint64_t* lag_first;  // per position p < size: L_first, L_last at the point of position p
   const uint64_t* lag_last;
-  uint64_t zh_inv[4];    // 1/Z_H per (i mod 2^qbits)
+  uint64_t zh_inv[8];    // 1/Z_H per (i mod 2^qbits), qbits <= 3
   uint64_t last;         // g^-1
   uint64_t alphas[MAX_CHALLENGES];
   int n_alphas;

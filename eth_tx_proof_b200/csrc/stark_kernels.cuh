@@ -143,7 +143,7 @@ static __global__ void lagrange_denominators(int log_lde, int log_size, int step
   den[p] = gl::mul(n_field, gl::sub(x, 1));
   den[size + p] = gl::mul(n_field, gl::sub(gl::mul(g, x), 1));
 }
-struct ZhVals { uint64_t v[4]; };  // Z_H(x_i) per (i mod 2^qbits)
+struct ZhVals { uint64_t v[8]; };  // Z_H(x_i) per (i mod 2^qbits), qbits <= 3
 static __global__ void lagrange_finish(int log_lde, int log_size, int step_log, int qmask, ZhVals zhv,
                                        uint64_t* inv /* 2 x size, in place */) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;

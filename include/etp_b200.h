@@ -57,6 +57,9 @@ uint64_t etp_ctx_launch_count(const etp_ctx *ctx);
  * out.  Needs no GPU: it is what the library's Fiat-Shamir Challenger runs on the calling thread (the transcript is
  * strictly sequential); exported so that a caller-side Challenger can share it. */
 void etp_host_poseidon_permute(uint64_t state[12]);
+/* ALL_ROUND_CONSTANTS (30 x 12), MDS_MATRIX_CIRC, MDS_MATRIX_DIAG of plonky2/src/hash/poseidon_goldilocks.rs — for callers
+ * that build circuits over the permutation (PoseidonGate); any pointer may be NULL */
+void etp_poseidon_constants(uint64_t round_constants_out[360], uint64_t mds_circ_out[12], uint64_t mds_diag_out[12]);
 /* Device scratch of a context comes from a per-context block cache (a released block is reused by the next
  * allocation of about the same size, so proofs / commits of a shape seen before allocate nothing).
  * etp_ctx_trim returns the cached blocks to the CUDA runtime; etp_ctx_cached_bytes reports how much is held. */
@@ -281,6 +284,19 @@ int etp_compute_quotient_polys_dev(etp_ctx *ctx, int table, etp_batch *trace, et
                                    const uint64_t *public_inputs, const uint64_t *alphas, int n_alphas,
                                    uint64_t *out_dev);
 
+/* Registers a constraint program that is NOT a starky table: constraint degree up to 9 (quotient degree factor up to 8), up
+ * to 8 challenge scalars, no auxiliary polynomials, no StarkConfig limits — e.g. the vanishing polynomial of a plonky2
+ * circuit (plonk/vanishing_poly.rs eval_vanishing_poly recorded over the virtual columns [constants | sigmas | wires | Zs |
+ * partial products | X]).  The id is accepted by etp_compute_quotient_polys_cols_dev only. */
+int etp_program_register(etp_ctx *ctx, const uint64_t *program, size_t n_words, int *table_id_out);
+/* compute_quotient_polys over an arbitrary list of LDE columns: lde_cols[c] = device pointer of virtual trace column c
+ * (bit-reversed rows, 2^(log_n + rate_bits) words), from any PolynomialBatch of this context.  The plonky2 circuit prover's
+ * form (plonk/prover.rs compute_quotient_polys -> eval_vanishing_poly_base_batch): one program reads the constants / sigmas,
+ * wires and Z / partial-product oracles and the LDE of X.  The table must have no auxiliary polynomials;
+ * quotient_degree_factor <= 2^rate_bits and <= 8.  out_dev: n_alphas * quotient_degree_factor polynomials x n. */
+int etp_compute_quotient_polys_cols_dev(etp_ctx *ctx, int table, const uint64_t *const *lde_cols, size_t n_cols, int log_n,
+                                        int rate_bits, const uint64_t *challenge_scalars, int n_scalars,
+                                        const uint64_t *public_inputs, const uint64_t *alphas, int n_alphas, uint64_t *out_dev);
 /* plonky2::fri::prover::fri_proof_of_work: SMALLEST witness w such that the duplex response has
  * `bits` leading zeros; state = sponge state with the pending inputs already overwritten in,
  * pos = index the candidate is written to. */

@@ -1,0 +1,105 @@
+"""CPU tests of the circuit-prover host logic (eth_tx_proof_b200/circuit.py; plonky2 0.2.2 plonk/{prover,vanishing_poly}.rs,
+gates/*.rs, gates/selectors.rs — /root/reference/Cargo.lock:3441, reached from /root/reference/ops/src/lib.rs:52,72,95):
+gates, selector groups, copy constraints -> sigmas, and the vanishing polynomial recorded as ONE constraint program, which
+must vanish on every row of a valid witness (with the oracle's Z / partial products) and must not on a corrupted one."""
+import numpy as np
+import pytest
+
+P = 0xFFFFFFFF00000001
+
+
+def _eval_rows(circuit, wires, zs_pp, pi_hash, betas, gammas):
+    """The program on every trace-domain row at once (numpy object arrays): [(kind, values[n])]."""
+    t = circuit.virtual_trace(wires, zs_pp).astype(object)
+    lv = [t[c] for c in range(t.shape[0])]
+    nv = [np.roll(t[c], -1) for c in range(t.shape[0])]
+    return circuit.program.evaluate(lv, nv, pi=pi_hash, ch=[int(x) for x in betas] + [int(x) for x in gammas])
+
+
+def _violations(circuit, wires, zs_pp, pi_hash, betas, gammas):
+    from eth_tx_proof_b200 import cprog
+
+    bad = []
+    for idx, (kind, vals) in enumerate(_eval_rows(circuit, wires, zs_pp, pi_hash, betas, gammas)):
+        vals = np.asarray(vals, dtype=object) % P if not np.isscalar(vals) else np.array([vals % P] * circuit.n, dtype=object)
+        rows = [0] if kind == cprog.EMIT_FIRST_ROW else range(circuit.n)
+        bad += [(idx, r) for r in rows if vals[r] != 0]
+    return bad
+
+
+def test_poseidon_gate_witness_matches_the_permutation():
+    import ctypes as C
+
+    from eth_tx_proof_b200 import circuit as cc
+    from eth_tx_proof_b200 import load_library
+
+    L = load_library()
+    rng = np.random.default_rng(3)
+    for swap in (0, 1):
+        ins = [int(x) % P for x in rng.integers(0, 2**63, 12)]
+        w = cc.poseidon_gate_wires(ins, swap)
+        st = list(ins)
+        if swap:
+            st[0:4], st[4:8] = ins[4:8], ins[0:4]
+        a = (C.c_uint64 * 12)(*st)
+        L.etp_host_poseidon_permute(a)
+        assert w[12:24] == [int(x) for x in a]
+    assert cc.hash_no_pad(list(range(8))) == cc.poseidon_gate_wires(list(range(8)) + [0] * 4, 0)[12:16]
+
+
+def test_selector_groups_follow_the_degree_rule():
+    from eth_tx_proof_b200 import circuit as cc
+
+    gates = sorted([cc.NoopGate(), cc.ConstantGate(2), cc.PublicInputGate(), cc.ArithmeticGate(20), cc.PoseidonGate()], key=lambda g: (g.degree, g.id()))
+    groups = cc.selector_groups(gates, 8)
+    assert [list(g) for g in groups] == [[0, 1, 2, 3], [4]]
+    assert [list(g) for g in cc.selector_groups(gates[:4], 8)] == [[0, 1, 2, 3]]  # 3 + 4 - 1 <= 8: one selector
+    for grp in groups:  # filter degree + gate degree <= quotient degree factor
+        assert max(len(grp) - 1 + (len(groups) > 1) + gates[i].degree for i in grp) <= 8
+
+
+@pytest.mark.parametrize("degree_bits", [5, 6])
+def test_vanishing_program_vanishes_on_a_valid_witness_only(degree_bits):
+    import oracle
+    from eth_tx_proof_b200 import circuit as cc
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(degree_bits, seed=degree_bits)
+    assert circuit.num_constants == 4 and circuit.num_selectors == 2 and circuit.num_gate_constraints == 123
+    assert circuit.program.n_trace == 4 + 80 + 135 + 20 + 1 and circuit.program.degree == 9
+    assert circuit.program.n_constraints == 2 + 20 + 123 == circuit.num_vanishing_terms
+    pi_hash = cc.hash_no_pad(public_inputs)
+    betas, gammas = [0x1234567, 0x7654321], [0xABCDEF, 0xFEDCBA]
+    zs_pp = oracle.plonk_partial_products_and_zs(wires[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
+    assert (zs_pp[0] != 1).any() or True
+    assert _violations(circuit, wires, zs_pp, pi_hash, betas, gammas) == []
+    # sigma is a permutation of the identity values that respects the copy constraints
+    ident = circuit.virtual_trace(wires, zs_pp)[-1][None, :].astype(object) * np.array(circuit.k_is, dtype=object)[:, None] % P
+    assert sorted(ident.reshape(-1).tolist()) == sorted(circuit.sigmas.astype(object).reshape(-1).tolist())
+    assert (circuit.sigmas.astype(object) != ident).sum() > 100
+    # a corrupted S-box wire breaks a Poseidon constraint; a corrupted copy breaks the permutation argument
+    bad = wires.copy()
+    row = int(np.nonzero(circuit.gate_of_row == 4)[0][3])
+    bad[cc.PoseidonGate.wire_partial_sbox(7), row] ^= np.uint64(1)
+    assert _violations(circuit, bad, zs_pp, pi_hash, betas, gammas)
+    bad = wires.copy()
+    bad[0, row] = (int(bad[0, row]) + 1) % P  # an input wired to the previous row's output
+    zs_bad = oracle.plonk_partial_products_and_zs(bad[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
+    v = _violations(circuit, bad, zs_bad, pi_hash, betas, gammas)
+    assert v and any(idx >= 123 for idx, _ in v)  # a permutation / Z term (emitted after the reversed gate slots)
+    # wrong public inputs: the PublicInputGate row fails
+    assert _violations(circuit, wires, zs_pp, [1, 2, 3, 4], betas, gammas)
+
+
+def test_vanishing_program_compiles_for_sm_100a():
+    from eth_tx_proof_b200 import circuit as cc
+    import eth_tx_proof_b200 as etp
+    import ctypes as C
+
+    circuit, _, _ = cc.hash_chain_circuit(5, seed=1)
+    L = etp.load_library()
+    w = np.ascontiguousarray(circuit.program.words)
+    size = C.c_size_t()
+    err = C.create_string_buffer(512)
+    rc = L.etp_cprog_compile_check(w.ctypes.data_as(C.POINTER(C.c_uint64)), w.size, C.byref(size), err, 512)
+    assert rc == 0, err.value
+    assert size.value > 10000
