@@ -504,6 +504,42 @@ def main():
             runs = [rec.prove_skeleton(ctx, db, polys, cs)["ms"] for _ in range(5)]
             recursion["degree_bits"][str(db)] = {k: min(r[k] for r in runs) for k in runs[0]}
 
+    # ---- SURVEY.md 8(f3), second slice: a circuit proof with the QUOTIENT on the device (eth_tx_proof_b200/circuit.py): a
+    # recursion-verifier-shaped synthetic circuit (PoseidonGate chain + ArithmeticGates + public-input hashing, copy constraints)
+    # proved as plonk::prover::prove does; CPU arm: the oracle's restatement of the same steps on the host cores; the two proofs
+    # must be equal word for word.
+    circuit_leg = None
+    if not args.skip_stark and world == 1:
+        from eth_tx_proof_b200 import circuit as cc
+
+        circuit_leg = {"workload": "plonky2-style circuit proof under standard_recursion_config (135 wires, 80 routed, rate_bits 3, 28 queries): "
+                                   "wires commit, permutation Z / partial products, vanishing-polynomial quotient (gate constraints with "
+                                   "selector filters: PoseidonGate 60 % of the rows, ArithmeticGate 30 %, + permutation argument), openings, "
+                                   "four-oracle FRI — all on the device; the witness is given (no generators); synthetic circuit, not the "
+                                   "reference's recursive verifier circuit", "degree_bits": {}}
+        for db in (12, 13):
+            circ, wires_w, pis = cc.hash_chain_circuit(db, seed=db)
+            prover = cc.CircuitProver(ctx, circ)
+            proof = prover.prove(wires_w, pis)  # warm-up (also compiles nothing: the program was compiled at registration)
+            runs = [prover.prove(wires_w, pis)["ms"] for _ in range(5)]
+            entry = {"gpu_ms": {k: min(r[k] for r in runs) for k in runs[0]}, "program_ops": len(circ.program.ops),
+                     "vanishing_terms": circ.num_vanishing_terms}
+            if not args.skip_cpu:
+                import oracle
+
+                tms = {}
+                t0 = time.perf_counter()
+                want = oracle.circuit_prove(circ, wires_w, pis, prover.digest, timings=tms)
+                cpu_total = (time.perf_counter() - t0) * 1e3
+                same = bool((want["opening_proof"] == proof["opening_proof"]).all() and (np.asarray(want["quotient_polys_cap"]) == np.asarray(proof["quotient_polys_cap"])).all())
+                assert same, "circuit proof differs from the oracle's"
+                entry["cpu_ms"] = dict(tms, total=cpu_total)
+                entry["cpu_cores"] = oracle.num_threads()
+                entry["parity"] = "caps and FRI proof == oracle.circuit_prove (C + OpenMP restatement, NOT plonky2)"
+                entry["speedup_total"] = (cpu_total - tms.get("constants_sigmas commit (per circuit)", 0.0)) / entry["gpu_ms"]["total"]
+            circuit_leg["degree_bits"][str(db)] = entry
+            del prover
+
     # ---- one table column-split across all ranks: strong scaling of a single commit.
     # Rank g transforms columns [g*C/G, (g+1)*C/G) and hashes leaf rows [g*L/G, (g+1)*L/G), reading the peers'
     # LDE columns over NVLink inside the hashing kernel; the cap parts are all-gathered over NCCL.
@@ -604,7 +640,7 @@ def main():
         "data": "synthetic",
         "config": workload_config(log_n, cols),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "recursion_skeleton": recursion, "column_split": split, "column_split_proof": split_proof,
+        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "recursion_skeleton": recursion, "circuit_prover": circuit_leg, "column_split": split, "column_split_proof": split_proof,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())

@@ -487,3 +487,68 @@ def plonk_partial_products_and_zs(wires, sigmas, k_is, quotient_degree_factor, b
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def circuit_prove(circuit, wires, public_inputs, circuit_digest, table_id=None, timings=None) -> dict:
+    """plonky2::plonk::prover::prove over the oracle's CPU primitives (test infrastructure; the checker of
+    eth_tx_proof_b200/circuit.py CircuitProver.prove): wires commitment, all_wires_permutation_partial_products, the quotient
+    of the circuit's vanishing program (compute_quotient_polys over ONE batch that holds every virtual column
+    [constants | sigmas | wires | Zs | partial products | X] at rate_bits 3), openings, prove_openings over the four oracles.
+    `circuit`: eth_tx_proof_b200.circuit.Circuit.  Same dict layout as the product's."""
+    import time
+
+    from eth_tx_proof_b200 import circuit as cc
+
+    t = {} if timings is None else timings
+    n, db = circuit.n, circuit.degree_bits
+    t0 = time.perf_counter()
+    cs_b = Batch.from_values(np.concatenate([circuit.constants, circuit.sigmas]), cc.RATE_BITS, cc.CAP_HEIGHT)
+    t["constants_sigmas commit (per circuit)"] = (time.perf_counter() - t0) * 1e3
+    pi_hash = [int(x) for x in hash_no_pad(np.array(public_inputs, dtype=np.uint64))]
+    ch = HostChallenger()
+    ch.observe(circuit_digest)
+    ch.observe(pi_hash)
+    t0 = time.perf_counter()
+    wires_b = Batch.from_values(wires, cc.RATE_BITS, cc.CAP_HEIGHT)
+    t["wires commit"] = (time.perf_counter() - t0) * 1e3
+    ch.observe(wires_b.cap)
+    betas, gammas = ch.get_n(cc.NUM_CHALLENGES), ch.get_n(cc.NUM_CHALLENGES)
+    t0 = time.perf_counter()
+    zs_pp = plonk_partial_products_and_zs(wires[:cc.NUM_ROUTED], circuit.sigmas, circuit.k_is, cc.QUOTIENT_DEGREE_FACTOR, betas, gammas)
+    zs_b = Batch.from_values(zs_pp, cc.RATE_BITS, cc.CAP_HEIGHT)
+    t["partial products and Zs + commit"] = (time.perf_counter() - t0) * 1e3
+    ch.observe(zs_b.cap)
+    alphas = ch.get_n(cc.NUM_CHALLENGES)
+    t0 = time.perf_counter()
+    if table_id is None:
+        table_id = register_table(circuit.program)
+    virt = Batch.from_values(circuit.virtual_trace(wires, zs_pp), cc.RATE_BITS, 0)
+    quot = compute_quotient_polys(table_id, virt, None, list(betas) + list(gammas), pi_hash, alphas)
+    del virt
+    t["compute quotient polys"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    quot_b = Batch.from_coeffs(quot, cc.RATE_BITS, cc.CAP_HEIGHT)
+    t["quotient commit"] = (time.perf_counter() - t0) * 1e3
+    ch.observe(quot_b.cap)
+    zeta = ch.get_n(2)
+    g = pow(1753635133440165772, 1 << (32 - db), 0xFFFFFFFF00000001)
+    zeta_next = [int(zeta[0]) * g % 0xFFFFFFFF00000001, int(zeta[1]) * g % 0xFFFFFFFF00000001]
+    oracles = [cs_b, wires_b, zs_b, quot_b]
+    t0 = time.perf_counter()
+    openings = [batch_eval_at_ext_point(o, zeta) for o in oracles]
+    zs_next = batch_eval_at_ext_point(zs_b, zeta_next)[:cc.NUM_CHALLENGES]
+    t["openings"] = (time.perf_counter() - t0) * 1e3
+    for o in openings:
+        ch.observe(o)
+    ch.observe(zs_next)
+    shapes = [o.n_cols for o in oracles]
+    all_polys = [(o, k) for o, cnt in enumerate(shapes) for k in range(cnt)]
+    batches = [([int(zeta[0]), int(zeta[1])], all_polys), (zeta_next, [(2, k) for k in range(cc.NUM_CHALLENGES)])]
+    t0 = time.perf_counter()
+    fri = prove_openings(batches, oracles, ch, fri_params(db, cc.RATE_BITS, cc.CAP_HEIGHT, cc.POW_BITS, cc.NUM_QUERIES))
+    t["prove_openings (FRI)"] = (time.perf_counter() - t0) * 1e3
+    return {"degree_bits": db, "public_inputs": [int(x) for x in public_inputs], "constants_sigmas_cap": cs_b.cap,
+            "wires_cap": wires_b.cap, "plonk_zs_partial_products_cap": zs_b.cap, "quotient_polys_cap": quot_b.cap,
+            "openings": {"constants_sigmas": openings[0], "wires": openings[1], "zs_partial_products": openings[2], "quotient_polys": openings[3],
+                         "plonk_zs_next": zs_next},
+            "opening_proof": fri, "quotient_coeffs": quot, "ms": t}

@@ -103,3 +103,35 @@ def test_vanishing_program_compiles_for_sm_100a():
     rc = L.etp_cprog_compile_check(w.ctypes.data_as(C.POINTER(C.c_uint64)), w.size, C.byref(size), err, 512)
     assert rc == 0, err.value
     assert size.value > 10000
+
+
+@pytest.mark.parametrize("degree_bits", [5, 7])
+def test_oracle_circuit_proof_is_accepted_and_tampering_is_not(degree_bits):
+    """The CPU restatement of plonk::prover::prove (oracle.circuit_prove) against the independent Python verifier
+    (tests/plonk_verifier.py): transcript, vanishing identity at zeta, FRI."""
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(degree_bits, seed=2 + degree_bits)
+    digest = [11, 22, 33, 44]
+    proof = oracle.circuit_prove(circuit, wires, public_inputs, digest)
+    plonk_verifier.verify(proof, circuit, proof["constants_sigmas_cap"], digest, max_queries=3)
+    bad = dict(proof, public_inputs=[(public_inputs[0] + 1) % P] + list(public_inputs[1:]))
+    with pytest.raises(plonk_verifier.VerifyError):
+        plonk_verifier.verify(bad, circuit, proof["constants_sigmas_cap"], digest, max_queries=1)
+    op = dict(proof["openings"])
+    op["wires"] = op["wires"].copy()
+    op["wires"][3, 0] ^= np.uint64(1)
+    with pytest.raises(plonk_verifier.VerifyError):
+        plonk_verifier.verify(dict(proof, openings=op), circuit, proof["constants_sigmas_cap"], digest, max_queries=1)
+    fri = proof["opening_proof"].copy()
+    fri[-3] ^= np.uint64(1)  # a final-polynomial coefficient
+    with pytest.raises(plonk_verifier.VerifyError):
+        plonk_verifier.verify(dict(proof, opening_proof=fri), circuit, proof["constants_sigmas_cap"], digest, max_queries=1)
+    # a witness that violates a gate: the oracle's quotient is not a polynomial and the proof is rejected
+    w = wires.copy()
+    row = int(np.nonzero(circuit.gate_of_row == 3)[0][0])  # an ArithmeticGate row
+    w[3, row] = (int(w[3, row]) + 1) % P
+    with pytest.raises(plonk_verifier.VerifyError):
+        plonk_verifier.verify(oracle.circuit_prove(circuit, w, public_inputs, digest), circuit, proof["constants_sigmas_cap"], digest, max_queries=1)

@@ -120,6 +120,26 @@ def test_circuit_proof_is_accepted_by_the_verifier(ctx, degree_bits):
     assert (proof2["opening_proof"] == proof["opening_proof"]).all()
 
 
+@pytest.mark.parametrize("degree_bits", [6, 9, 12])
+def test_circuit_proof_equals_the_oracles_bit_for_bit(ctx, degree_bits):
+    """Every cap, opening, quotient coefficient and FRI word of the device proof == the CPU restatement's (oracle.circuit_prove)."""
+    import oracle
+    from eth_tx_proof_b200 import circuit as cc
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(degree_bits, seed=40 + degree_bits)
+    prover = cc.CircuitProver(ctx, circuit)
+    got = prover.prove(wires, public_inputs)
+    want = oracle.circuit_prove(circuit, wires, public_inputs, prover.digest)
+    assert (np.asarray(prover.constants_sigmas.cap) == want["constants_sigmas_cap"]).all()
+    for k in ("wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap"):
+        assert (np.asarray(got[k]) == want[k]).all(), k
+    for k, v in want["openings"].items():
+        assert (np.asarray(got["openings"][k]).reshape(-1) == np.asarray(v).reshape(-1)).all(), k
+    if got["quotient_coeffs"] is not None:
+        assert (got["quotient_coeffs"] == want["quotient_coeffs"]).all()
+    assert got["opening_proof"].shape == want["opening_proof"].shape and (got["opening_proof"] == want["opening_proof"]).all()
+
+
 def test_invalid_witness_is_rejected(ctx):
     """A wrong S-box wire / a broken copy constraint / wrong public inputs: the quotient is no longer a polynomial of the
     right degree — the verifier's identity at zeta fails."""
