@@ -487,6 +487,52 @@ def main():
               "timed": "tx_ms: the seven table proofs (trace commits, CTL data, quotients, openings, FRI) in sequence on one context, traces "
                        "resident in HBM -> proof bytes on the host; tx_per_min: all transactions through the pool (wall clock, max over ranks)"}
 
+    # ---- BASELINE "tx proofs/min", shape of the WHOLE transaction job of the reference (ops/src/lib.rs:52 generate_txn_proof ->
+    # prove_root): the seven table STARKs above, then per table a chain of recursive wrapper / shrinking circuit proofs down to
+    # the threshold degree, then one root circuit proof.  The circuit proofs are eth_tx_proof_b200/circuit.py proofs of the
+    # recursion-verifier-SHAPED synthetic circuit at placeholder sizes (per table 2^13, 2^13, 2^12; root 2^13): the reference's
+    # recursive verifier circuits (and their exact sizes) are not available offline, witness generation is not included.
+    tx_rec = None
+    if not args.skip_stark and not args.skip_tx:
+        from eth_tx_proof_b200 import circuit as cc
+
+        chain_bits, root_bits = (13, 13, 12), 13
+        circuits = {db: cc.hash_chain_circuit(db, seed=db) for db in sorted(set(chain_bits) | {root_bits})}
+        pool = parallel.ProverPool(local_rank, STARK_CONTEXTS_PER_GPU)
+        ids = [[c.register_table(p) for _, p, _ in tables] for c in pool.contexts]
+        cprovers = [{db: cc.CircuitProver(c, circuits[db][0]) for db in circuits} for c in pool.contexts]
+        dev = [torch.from_numpy(t.view(np.int64)).cuda() for _, _, t in tables]
+        traces_dev = [(d.data_ptr(), t.shape[1], t.shape[0], int(t.shape[1]).bit_length() - 1) for d, (_, _, t) in zip(dev, tables)]
+        torch.cuda.synchronize()
+
+        def prove_tx_full(c, _job):
+            k = pool.contexts.index(c)
+            out = [prover.prove_with_traces(c, ids[k], traces_dev)]
+            for _table in range(len(tables)):
+                for db in chain_bits:
+                    out.append(cprovers[k][db].prove(circuits[db][1], circuits[db][2])["opening_proof"])
+            out.append(cprovers[k][root_bits].prove(circuits[root_bits][1], circuits[root_bits][2])["opening_proof"])
+            return out
+
+        n_txr = 8 * world
+        pool.map(prove_tx_full, list(range(STARK_CONTEXTS_PER_GPU)))  # warm-up
+        t0 = time.perf_counter()
+        prove_tx_full(pool.contexts[0], 0)
+        txr_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t0 = time.perf_counter()
+        pool.map(prove_tx_full, list(parallel.shard_jobs(n_txr, rank, world)))
+        dt = max_over_ranks(time.perf_counter() - t0)
+        pool.close()
+        del dev, cprovers
+        tx_rec = {"workload": "synthetic transaction WITH recursion layers: 7 table STARKs + CTLs (as `tx`) + per table a chain of circuit "
+                              f"proofs at 2^{chain_bits} rows + one root circuit proof at 2^{root_bits} rows = {len(tables) * len(chain_bits) + 1} "
+                              "circuit proofs (standard_recursion_config; synthetic recursion-verifier-shaped circuit, placeholder sizes; "
+                              f"witnesses given); {n_txr} transactions (8 per GPU) over {world} GPU(s), {STARK_CONTEXTS_PER_GPU} contexts per GPU",
+                  "tx_ms": txr_ms, "tx_per_min": n_txr * 60.0 / dt, "transactions": n_txr,
+                  "timed": "tx_ms: one whole job on one context (table traces resident in HBM, circuit witnesses uploaded from the host inside) "
+                           "-> all proofs on the host; tx_per_min: all jobs through the pool (wall clock, max over ranks)"}
+
     # ---- SURVEY.md 8(f3), first slice: the device skeleton of one recursion-layer proof (plonky2's circuit prover under
     # standard_recursion_config: wires / Z / quotient commits at rate_bits 3, openings, four-oracle FRI with 28 queries) on
     # stand-in polynomials of the shrink-circuit shapes; gate evaluation and witness generation are NOT included
@@ -640,7 +686,7 @@ def main():
         "data": "synthetic",
         "config": workload_config(log_n, cols),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "recursion_skeleton": recursion, "circuit_prover": circuit_leg, "column_split": split, "column_split_proof": split_proof,
+        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "tx_with_recursion": tx_rec, "recursion_skeleton": recursion, "circuit_prover": circuit_leg, "column_split": split, "column_split_proof": split_proof,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())

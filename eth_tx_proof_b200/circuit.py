@@ -533,6 +533,14 @@ class CircuitProver:
         self.x_poly = PolynomialBatch.from_coeffs(ctx, x_coeffs, RATE_BITS, False, 0)  # its LDE column is the point itself
         self.fri_params = FriParams.make(circuit.degree_bits, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES)
 
+    def _sigmas_dev(self, dev):
+        """The sigma values on the device (circuit data: uploaded once)."""
+        if getattr(self, "_d_sig", None) is None:
+            import torch
+
+            self._d_sig = torch.from_numpy(np.ascontiguousarray(self.c.sigmas).view(np.int64)).to(dev)
+        return self._d_sig
+
     def fri_instance(self, zeta):
         """CommonCircuitData::get_fri_instance: zeta opens every polynomial of the four oracles, g*zeta the Zs."""
         c = self.c
@@ -555,9 +563,10 @@ class CircuitProver:
         ch.observe(self.digest)
         ch.observe(pi_hash)
         t0 = time.perf_counter()
-        d_wires = torch.from_numpy(np.ascontiguousarray(wires).view(np.int64)).cuda()
-        d_sig = torch.from_numpy(np.ascontiguousarray(c.sigmas).view(np.int64)).cuda()
-        torch.cuda.synchronize()
+        dev = torch.device("cuda", ctx.device)  # explicit: worker threads do not inherit the caller's current device
+        d_wires = torch.from_numpy(np.ascontiguousarray(wires).view(np.int64)).to(dev)
+        d_sig = self._sigmas_dev(dev)
+        torch.cuda.synchronize(dev)
         t["upload wires"] = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter()
         wires_b = PolynomialBatch.from_values_dev(ctx, d_wires.data_ptr(), n, NUM_WIRES, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
@@ -565,8 +574,8 @@ class CircuitProver:
         ch.observe_cap(wires_b.cap)
         betas, gammas = ch.get_n_challenges(NUM_CHALLENGES), ch.get_n_challenges(NUM_CHALLENGES)
         n_zs = NUM_CHALLENGES * (1 + NUM_PARTIAL_PRODUCTS)
-        d_z = torch.empty((n_zs, n), dtype=torch.int64, device="cuda")
-        torch.cuda.synchronize()
+        d_z = torch.empty((n_zs, n), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         ctx.plonk_partial_products_and_zs_dev(d_wires.data_ptr(), n, d_sig.data_ptr(), n, np.array(c.k_is, dtype=np.uint64), c.degree_bits,
                                               QUOTIENT_DEGREE_FACTOR, betas, gammas, d_z.data_ptr())
@@ -583,8 +592,8 @@ class CircuitProver:
             cols += [int(base) + 8 * k * stride.value for k in range(batch.n_cols)]
         assert len(cols) == c.num_virtual_columns
         n_q = NUM_CHALLENGES * QUOTIENT_DEGREE_FACTOR
-        d_q = torch.empty((n_q, n), dtype=torch.int64, device="cuda")
-        torch.cuda.synchronize()
+        d_q = torch.empty((n_q, n), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
         ctx.compute_quotient_polys_cols_dev(self.table, cols, c.degree_bits, RATE_BITS, list(betas) + list(gammas), pi_hash, alphas, d_q.data_ptr())
         t["compute quotient polys"] = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter()
