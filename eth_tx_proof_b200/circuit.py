@@ -21,9 +21,9 @@ in reverse.
 
 Gates (constraints restated from plonky2/src/gates/*.rs): NoopGate, ConstantGate, PublicInputGate, ArithmeticGate,
 PoseidonGate (123 constraints of degree 7; the partial rounds are written with the plain round function — the same
-polynomials in the wires as upstream's fast partial rounds, which only re-factor the linear layers).  Not built: the other
-gates of the recursive verifier circuit (base-sum, random-access, reducing, coset-interpolation, exponentiation, extension
-arithmetic), lookup tables, witness generation by generators (witnesses here are computed directly), zero-knowledge blinding
+polynomials in the wires as upstream's fast partial rounds, which only re-factor the linear layers), ArithmeticExtensionGate,
+MulExtensionGate, BaseSumGate<2>, ReducingGate, ReducingExtensionGate, RandomAccessGate, ExponentiationGate, PoseidonMdsGate.
+Not built: CosetInterpolationGate, lookup tables / lookup gates, witness generation by generators (witnesses here are computed directly), zero-knowledge blinding
 (off in standard_recursion_config).  The circuit digest is a stand-in (hash of the constants/sigmas cap and degree_bits).
 Nothing here can be checked against real plonky2 offline: parity is against the pure-Python evaluation in the tests.
 """
@@ -257,6 +257,260 @@ class PoseidonGate(Gate):
         return cons
 
 
+# quadratic extension (X^2 = 7) over pairs — Python ints or cprog expressions alike
+def _e_mul(a, b, seven=7):
+    return (a[0] * b[0] + a[1] * b[1] * seven, a[0] * b[1] + a[1] * b[0])
+
+
+def _e_add(a, b):
+    return (a[0] + b[0], a[1] + b[1])
+
+
+def _e_sub(a, b):
+    return (a[0] - b[0], a[1] - b[1])
+
+
+def _e_mod(a):
+    return (a[0] % P, a[1] % P)
+
+
+class ArithmeticExtensionGate(Gate):
+    """gates/arithmetic_extension.rs: per operation, over the quadratic extension: output - (m0 * m1 * c0 + addend * c1)."""
+
+    def __init__(self, num_ops: int = 10):
+        self.num_ops = num_ops
+        self.name, self.degree, self.num_constants, self.num_constraints = f"ArithmeticExtensionGate {{ num_ops: {num_ops} }}", 3, 2, 2 * num_ops
+
+    def eval(self, b, wire, const, pi):
+        out = []
+        pair = lambda k: (wire(k), wire(k + 1))
+        for i in range(self.num_ops):
+            m0, m1, addend, output = (pair(8 * i + 2 * j) for j in range(4))
+            prod = _e_mul(m0, m1, b.const(7))
+            out += list(_e_sub(output, _e_add((prod[0] * const(0), prod[1] * const(0)), (addend[0] * const(1), addend[1] * const(1)))))
+        return out
+
+    def witness(self, rnd, c0, c1):
+        w = []
+        for _ in range(self.num_ops):
+            m0, m1, ad = (rnd(), rnd()), (rnd(), rnd()), (rnd(), rnd())
+            pr = _e_mod(_e_mul(m0, m1))
+            w += [*m0, *m1, *ad, (pr[0] * c0 + ad[0] * c1) % P, (pr[1] * c0 + ad[1] * c1) % P]
+        return w
+
+
+class MulExtensionGate(Gate):
+    """gates/multiplication_extension.rs: output - m0 * m1 * c0 over the extension."""
+
+    def __init__(self, num_ops: int = 13):
+        self.num_ops = num_ops
+        self.name, self.degree, self.num_constants, self.num_constraints = f"MulExtensionGate {{ num_ops: {num_ops} }}", 3, 1, 2 * num_ops
+
+    def eval(self, b, wire, const, pi):
+        out = []
+        pair = lambda k: (wire(k), wire(k + 1))
+        for i in range(self.num_ops):
+            m0, m1, output = (pair(6 * i + 2 * j) for j in range(3))
+            prod = _e_mul(m0, m1, b.const(7))
+            out += list(_e_sub(output, (prod[0] * const(0), prod[1] * const(0))))
+        return out
+
+    def witness(self, rnd, c0):
+        w = []
+        for _ in range(self.num_ops):
+            m0, m1 = (rnd(), rnd()), (rnd(), rnd())
+            pr = _e_mod(_e_mul(m0, m1))
+            w += [*m0, *m1, pr[0] * c0 % P, pr[1] * c0 % P]
+        return w
+
+
+class BaseSumGate(Gate):
+    """gates/base_sum.rs with B = 2: wire 0 = sum_i limb_i 2^i, every limb boolean."""
+
+    def __init__(self, num_limbs: int = 63):
+        self.num_limbs = num_limbs
+        self.name, self.degree, self.num_constants, self.num_constraints = f"BaseSumGate {{ num_limbs: {num_limbs} }} + Base: 2", 2, 0, 1 + num_limbs
+
+    def eval(self, b, wire, const, pi):
+        limbs = [wire(1 + i) for i in range(self.num_limbs)]
+        acc = None
+        for l in reversed(limbs):  # reduce_with_powers(limbs, 2)
+            acc = l if acc is None else acc * b.const(2) + l
+        return [acc - wire(0)] + [l * (l - 1) for l in limbs]
+
+    def witness(self, value):
+        assert 0 <= value < 1 << self.num_limbs
+        return [value] + [(value >> i) & 1 for i in range(self.num_limbs)]
+
+
+class ReducingGate(Gate):
+    """gates/reducing.rs: Horner over base-field coefficients with an extension alpha: acc_i = acc_{i-1} * alpha + coeff_i."""
+
+    def __init__(self, num_coeffs: int = 43):
+        self.num_coeffs = num_coeffs
+        self.name, self.degree, self.num_constants, self.num_constraints = f"ReducingGate {{ num_coeffs: {num_coeffs} }}", 2, 0, 2 * num_coeffs
+        self.start_coeffs, self.start_accs = 6, 6 + num_coeffs
+
+    def _acc(self, i):  # wires of accumulator i; the last one is the output
+        return (0, 1) if i == self.num_coeffs - 1 else (self.start_accs + 2 * i, self.start_accs + 2 * i + 1)
+
+    def eval(self, b, wire, const, pi):
+        alpha, acc = (wire(2), wire(3)), (wire(4), wire(5))
+        out = []
+        for i in range(self.num_coeffs):
+            nxt = tuple(wire(k) for k in self._acc(i))
+            t = _e_mul(acc, alpha, b.const(7))
+            out += [t[0] + wire(self.start_coeffs + i) - nxt[0], t[1] - nxt[1]]
+            acc = nxt
+        return out
+
+    def witness(self, rnd):
+        w = [0] * NUM_WIRES
+        alpha, acc = (rnd(), rnd()), (rnd(), rnd())
+        w[2:6] = [*alpha, *acc]
+        for i in range(self.num_coeffs):
+            c = rnd()
+            w[self.start_coeffs + i] = c
+            t = _e_mod(_e_mul(acc, alpha))
+            acc = ((t[0] + c) % P, t[1])
+            a0, a1 = self._acc(i)
+            w[a0], w[a1] = acc
+        return w
+
+
+class ReducingExtensionGate(Gate):
+    """gates/reducing_extension.rs: the same with extension coefficients."""
+
+    def __init__(self, num_coeffs: int = 32):
+        self.num_coeffs = num_coeffs
+        self.name, self.degree, self.num_constants, self.num_constraints = f"ReducingExtensionGate {{ num_coeffs: {num_coeffs} }}", 2, 0, 2 * num_coeffs
+        self.start_coeffs, self.start_accs = 6, 6 + 2 * num_coeffs
+
+    def _acc(self, i):
+        return (0, 1) if i == self.num_coeffs - 1 else (self.start_accs + 2 * i, self.start_accs + 2 * i + 1)
+
+    def eval(self, b, wire, const, pi):
+        alpha, acc = (wire(2), wire(3)), (wire(4), wire(5))
+        out = []
+        for i in range(self.num_coeffs):
+            nxt = tuple(wire(k) for k in self._acc(i))
+            coeff = (wire(self.start_coeffs + 2 * i), wire(self.start_coeffs + 2 * i + 1))
+            t = _e_add(_e_mul(acc, alpha, b.const(7)), coeff)
+            out += [t[0] - nxt[0], t[1] - nxt[1]]
+            acc = nxt
+        return out
+
+    def witness(self, rnd):
+        w = [0] * NUM_WIRES
+        alpha, acc = (rnd(), rnd()), (rnd(), rnd())
+        w[2:6] = [*alpha, *acc]
+        for i in range(self.num_coeffs):
+            c = (rnd(), rnd())
+            w[self.start_coeffs + 2 * i], w[self.start_coeffs + 2 * i + 1] = c
+            acc = _e_mod(_e_add(_e_mul(acc, alpha), c))
+            a0, a1 = self._acc(i)
+            w[a0], w[a1] = acc
+        return w
+
+
+class RandomAccessGate(Gate):
+    """gates/random_access.rs: num_copies look-ups claimed_element = list[access_index] in lists of 2^bits items (index bits
+    as advice wires, the list folded bit by bit), plus num_extra_constants constant wires."""
+
+    def __init__(self, bits: int = 4, num_copies: int = 4, num_extra_constants: int = 2):
+        self.bits, self.num_copies, self.num_extra = bits, num_copies, num_extra_constants
+        self.vec = 1 << bits
+        self.name = f"RandomAccessGate {{ bits: {bits}, num_copies: {num_copies}, num_extra_constants: {num_extra_constants} }}"
+        self.degree, self.num_constants = bits + 1, num_extra_constants
+        self.num_constraints = num_copies * (bits + 2) + num_extra_constants
+        self.start_extra = (2 + self.vec) * num_copies
+        self.num_routed = self.start_extra + num_extra_constants
+
+    def eval(self, b, wire, const, pi):
+        out = []
+        for c in range(self.num_copies):
+            base = (2 + self.vec) * c
+            index, claimed = wire(base), wire(base + 1)
+            items = [wire(base + 2 + j) for j in range(self.vec)]
+            bits = [wire(self.num_routed + c * self.bits + j) for j in range(self.bits)]
+            out += [x * (x - 1) for x in bits]
+            acc = None
+            for x in reversed(bits):
+                acc = x if acc is None else acc * b.const(2) + x
+            out.append(acc - index)
+            for x in bits:  # fold pairs: x + b (y - x)
+                items = [items[k] + x * (items[k + 1] - items[k]) for k in range(0, len(items), 2)]
+            out.append(items[0] - claimed)
+        out += [const(i) - wire(self.start_extra + i) for i in range(self.num_extra)]
+        return out
+
+    def witness(self, rnd, rng, extra):
+        w = [0] * NUM_WIRES
+        for c in range(self.num_copies):
+            base = (2 + self.vec) * c
+            items = [rnd() for _ in range(self.vec)]
+            idx = int(rng.integers(0, self.vec))
+            w[base], w[base + 1] = idx, items[idx]
+            w[base + 2:base + 2 + self.vec] = items
+            for j in range(self.bits):
+                w[self.num_routed + c * self.bits + j] = (idx >> j) & 1
+        for i, v in enumerate(extra):
+            w[self.start_extra + i] = v
+        return w
+
+
+class ExponentiationGate(Gate):
+    """gates/exponentiation.rs: output = base^power by square-and-multiply over the power's bits (most significant first)."""
+
+    def __init__(self, num_power_bits: int = 66):
+        self.n_bits = num_power_bits
+        self.name, self.degree, self.num_constants, self.num_constraints = f"ExponentiationGate {{ num_power_bits: {num_power_bits} }}", 4, 0, num_power_bits + 1
+
+    def eval(self, b, wire, const, pi):
+        base, output = wire(0), wire(1 + self.n_bits)
+        inter = [wire(2 + self.n_bits + i) for i in range(self.n_bits)]
+        one = b.const(1)
+        out = []
+        for i in range(self.n_bits):
+            prev = one if i == 0 else inter[i - 1] * inter[i - 1]
+            bit = wire(1 + self.n_bits - 1 - i)
+            out.append(prev * (bit * base + one - bit) - inter[i])
+        out.append(output - inter[-1])
+        return out
+
+    def witness(self, base, power):
+        w = [0] * NUM_WIRES
+        w[0] = base
+        bits = [(power >> i) & 1 for i in range(self.n_bits)]
+        w[1:1 + self.n_bits] = bits
+        cur = 1
+        for i in range(self.n_bits):
+            prev = 1 if i == 0 else cur * cur % P
+            cur = prev * (base if bits[self.n_bits - 1 - i] else 1) % P
+            w[2 + self.n_bits + i] = cur
+        w[1 + self.n_bits] = cur
+        assert cur == pow(base, power, P)
+        return w
+
+
+class PoseidonMdsGate(Gate):
+    """gates/poseidon_mds.rs: the MDS layer on 12 extension elements."""
+    name, degree, num_constants, num_constraints = "PoseidonMdsGate", 1, 0, 24
+
+    def eval(self, b, wire, const, pi):
+        out = []
+        for comp in range(2):
+            ins = [wire(2 * i + comp) for i in range(12)]
+            res = mds_layer(ins, add=lambda x, y: x + y, mulc=lambda x, c: x * b.const(c))
+            out += [(i, comp, res[i] - wire(24 + 2 * i + comp)) for i in range(12)]
+        return [e for _, _, e in sorted(out, key=lambda t: (t[0], t[1]))]
+
+    def witness(self, rnd):
+        ins = [(rnd(), rnd()) for _ in range(12)]
+        outs = list(zip(mds_layer([x[0] for x in ins]), mds_layer([x[1] for x in ins])))
+        return [v for x in ins for v in x] + [v for x in outs for v in x]
+
+
 # ---- selectors (gates/selectors.rs) -----------------------------------------------------------------------------------------------
 def selector_groups(gates: Sequence[Gate], max_degree: int) -> List[range]:
     """Greedy grouping of the (degree-sorted) gates: a group of `size` gates costs a filter of degree size - 1 (+ 1 for the
@@ -461,10 +715,13 @@ class CircuitBuilder:
         return circuit, wires
 
 
-def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float = 0.6, arithmetic_fraction: float = 0.3):
+def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float = 0.6, arithmetic_fraction: float = 0.3, all_gates: bool = False,
+                       extra_rows: int = 1):
     """A recursion-verifier-shaped synthetic circuit with its witness: the public inputs are hashed in-circuit (PoseidonGate
     row wired to the PublicInputGate), a Merkle-path-like chain of swapped PoseidonGates, chains of ArithmeticGate operations,
     constants through a ConstantGate — all linked by copy constraints — padded with NoopGates to 2^degree_bits rows.
+    all_gates: also `extra_rows` rows of each of ArithmeticExtension, MulExtension, BaseSum, Exponentiation (its exponent bits wired
+    to the base-sum limbs), Reducing, ReducingExtension, RandomAccess and PoseidonMds gates (four selector groups instead of two).
     -> (Circuit, wires (135, n), public_inputs)"""
     rng = np.random.default_rng(seed)
     n = 1 << degree_bits
@@ -483,7 +740,7 @@ def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float
         cb.connect((r_h, 12 + i), (r_pi, i))
         cb.connect((r_h, 8 + i), (r_const, 0))
     cb.connect((r_h, PoseidonGate.WIRE_SWAP), (r_const, 0))
-    budget = n - len(cb.rows)
+    budget = n - len(cb.rows) - (8 * extra_rows if all_gates else 0)
     n_pos = max(int(budget * poseidon_fraction), 1)
     n_ar = max(int(budget * arithmetic_fraction), 1)
     prev_row, digest = r_h, w[12:16]
@@ -514,6 +771,33 @@ def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float
         cb.add_gate(ar, constants=[c0, c1], wires=w)
         for a, b_ in links:
             cb.connect(a, b_)
+    if all_gates:  # a few rows of every other gate of the recursive verifier's gate set (CosetInterpolationGate excepted)
+        for _ in range(extra_rows):
+            c0, c1 = rnd(), rnd()
+            g = ArithmeticExtensionGate(10)
+            r_ae = cb.add_gate(g, constants=[c0, c1], wires=g.witness(rnd, c0, c1))
+            g = MulExtensionGate(13)
+            w = g.witness(rnd, c0)
+            w[0:2] = cb.wires[r_ae][6:8]  # first product's m0 = the extension output of the row above
+            pr = _e_mod(_e_mul((w[0], w[1]), (w[2], w[3])))
+            w[4:6] = [pr[0] * c0 % P, pr[1] * c0 % P]
+            r_me = cb.add_gate(g, constants=[c0], wires=w)
+            cb.connect((r_me, 0), (r_ae, 6))
+            cb.connect((r_me, 1), (r_ae, 7))
+            g = BaseSumGate(63)
+            value = int(rng.integers(0, 2**62))
+            r_bs = cb.add_gate(g, wires=g.witness(value))
+            g = ExponentiationGate(66)
+            w = g.witness(rnd(), value)
+            r_ex = cb.add_gate(g, wires=w)
+            for i in range(62):  # the exponent's bits are the base-sum limbs
+                cb.connect((r_ex, 1 + i), (r_bs, 1 + i))
+            cb.add_gate(ReducingGate(43), wires=ReducingGate(43).witness(rnd))
+            cb.add_gate(ReducingExtensionGate(32), wires=ReducingExtensionGate(32).witness(rnd))
+            g = RandomAccessGate(4, 4, 2)
+            e0, e1 = rnd(), rnd()
+            cb.add_gate(g, constants=[e0, e1], wires=g.witness(rnd, rng, [e0, e1]))
+            cb.add_gate(PoseidonMdsGate(), wires=PoseidonMdsGate().witness(rnd))
     return (*cb.build(degree_bits), public_inputs)
 
 

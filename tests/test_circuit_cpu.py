@@ -135,3 +135,42 @@ def test_oracle_circuit_proof_is_accepted_and_tampering_is_not(degree_bits):
     w[3, row] = (int(w[3, row]) + 1) % P
     with pytest.raises(plonk_verifier.VerifyError):
         plonk_verifier.verify(oracle.circuit_prove(circuit, w, public_inputs, digest), circuit, proof["constants_sigmas_cap"], digest, max_queries=1)
+
+
+def test_full_gate_set_constraints_hold_and_every_gate_bites():
+    """All thirteen gates (four selector groups): the vanishing program vanishes on the witness; corrupting one wire of a row of
+    each gate type makes that gate's filtered constraints non-zero on that row."""
+    import oracle
+    from eth_tx_proof_b200 import circuit as cc
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(6, seed=5, all_gates=True)
+    assert [list(g) for g in circuit.groups] == [[0, 1, 2, 3, 4, 5], [6, 7, 8, 9], [10, 11], [12]]
+    assert circuit.num_constants == 6 and len(circuit.gates) == 13
+    pi_hash = cc.hash_no_pad(public_inputs)
+    betas, gammas = [3, 5], [7, 11]
+    zs_pp = oracle.plonk_partial_products_and_zs(wires[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
+    assert _violations(circuit, wires, zs_pp, pi_hash, betas, gammas) == []
+    # advice (non-routed or unconnected) wires: changing them cannot be absorbed by the permutation argument
+    victims = {"ArithmeticExtensionGate": 15, "MulExtensionGate": 10, "BaseSumGate": 63, "ReducingExtensionGate": 80, "ReducingGate": 60,
+               "ExponentiationGate": 100, "RandomAccessGate": 75, "PoseidonMdsGate": 30, "ConstantGate": 1, "ArithmeticGate": 7}
+    for gi, gate in enumerate(circuit.gates):
+        key = gate.name.split(" ")[0]
+        if key not in victims:
+            continue
+        row = int(np.nonzero(circuit.gate_of_row == gi)[0][0])
+        bad = wires.copy()
+        bad[victims[key], row] = (int(bad[victims[key], row]) + 1) % P
+        zs_bad = oracle.plonk_partial_products_and_zs(bad[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
+        v = _violations(circuit, bad, zs_bad, pi_hash, betas, gammas)
+        assert v and all(r == row or idx >= 123 for idx, r in v), key
+
+
+def test_oracle_proof_of_the_full_gate_set_verifies():
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(6, seed=8, all_gates=True)
+    digest = [5, 6, 7, 8]
+    proof = oracle.circuit_prove(circuit, wires, public_inputs, digest)
+    plonk_verifier.verify(proof, circuit, proof["constants_sigmas_cap"], digest, max_queries=2)

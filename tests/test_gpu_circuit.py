@@ -140,6 +140,24 @@ def test_circuit_proof_equals_the_oracles_bit_for_bit(ctx, degree_bits):
     assert got["opening_proof"].shape == want["opening_proof"].shape and (got["opening_proof"] == want["opening_proof"]).all()
 
 
+@pytest.mark.parametrize("degree_bits", [6, 10])
+def test_full_gate_set_proof_equals_oracle_and_verifies(ctx, degree_bits):
+    """Thirteen gates in four selector groups (extension arithmetic, base sum, reducing, random access, exponentiation, MDS,
+    ...): same parity and acceptance as the Poseidon / arithmetic circuit."""
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(degree_bits, seed=70 + degree_bits, all_gates=True, extra_rows=1 if degree_bits < 8 else 12)
+    prover = cc.CircuitProver(ctx, circuit)
+    got = prover.prove(wires, public_inputs)
+    want = oracle.circuit_prove(circuit, wires, public_inputs, prover.digest)
+    for k in ("wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap"):
+        assert (np.asarray(got[k]) == want[k]).all(), k
+    assert (got["opening_proof"] == want["opening_proof"]).all()
+    plonk_verifier.verify(got, circuit, prover.constants_sigmas.cap, prover.digest, max_queries=3)
+
+
 def test_invalid_witness_is_rejected(ctx):
     """A wrong S-box wire / a broken copy constraint / wrong public inputs: the quotient is no longer a polynomial of the
     right degree — the verifier's identity at zeta fails."""
