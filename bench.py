@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 LOG_N, COLS, RATE_BITS, CAP_HEIGHT = 22, 128, 1, 4
 STARK_LOG_N = 22
 STARK_CONTEXTS_PER_GPU = 2  # parallel.ProverPool: the tail of one proof overlaps the commits of the next (tools/prove_concurrent.py)
+REC_CONTEXTS_PER_GPU = 4    # the recursion layers are latency-bound small proofs (2^12-2^13 rows): more host threads in flight per GPU
 CPU_SAMPLE_LOG_N = 18  # bounded CPU sample: 2^18 x 128 (1/16 of the rows; ~10-30 s of CPU work)
 
 
@@ -498,7 +499,8 @@ def main():
 
         chain_bits, root_bits = (13, 13, 12), 13
         circuits = {db: cc.hash_chain_circuit(db, seed=db) for db in sorted(set(chain_bits) | {root_bits})}
-        pool = parallel.ProverPool(local_rank, STARK_CONTEXTS_PER_GPU)
+        rec_contexts = int(os.environ.get("ETP_BENCH_REC_CONTEXTS", REC_CONTEXTS_PER_GPU))
+        pool = parallel.ProverPool(local_rank, rec_contexts)
         ids = [[c.register_table(p) for _, p, _ in tables] for c in pool.contexts]
         cprovers = [{db: cc.CircuitProver(c, circuits[db][0]) for db in circuits} for c in pool.contexts]
         dev = [torch.from_numpy(t.view(np.int64)).cuda() for _, _, t in tables]
@@ -510,12 +512,12 @@ def main():
             out = [prover.prove_with_traces(c, ids[k], traces_dev)]
             for _table in range(len(tables)):
                 for db in chain_bits:
-                    out.append(cprovers[k][db].prove(circuits[db][1], circuits[db][2])["opening_proof"])
-            out.append(cprovers[k][root_bits].prove(circuits[root_bits][1], circuits[root_bits][2])["opening_proof"])
+                    out.append(cprovers[k][db].prove_words(circuits[db][1], circuits[db][2]))
+            out.append(cprovers[k][root_bits].prove_words(circuits[root_bits][1], circuits[root_bits][2]))
             return out
 
         n_txr = 8 * world
-        pool.map(prove_tx_full, list(range(STARK_CONTEXTS_PER_GPU)))  # warm-up
+        pool.map(prove_tx_full, list(range(rec_contexts)))  # warm-up
         t0 = time.perf_counter()
         prove_tx_full(pool.contexts[0], 0)
         txr_ms = (time.perf_counter() - t0) * 1e3
@@ -533,7 +535,7 @@ def main():
             dist.barrier()  # the KB-sized segment proofs travel to the aggregator (here: only their completion)
         if rank == 0:
             for _ in range(8):
-                cprovers[0][root_bits].prove(circuits[root_bits][1], circuits[root_bits][2])
+                cprovers[0][root_bits].prove_words(circuits[root_bits][1], circuits[root_bits][2])
         block_ms = max_over_ranks(time.perf_counter() - t0) * 1e3
         pool.close()
         del dev, cprovers
@@ -542,7 +544,7 @@ def main():
                   "workload": "synthetic transaction WITH recursion layers: 7 table STARKs + CTLs (as `tx`) + per table a chain of circuit "
                               f"proofs at 2^{chain_bits} rows + one root circuit proof at 2^{root_bits} rows = {len(tables) * len(chain_bits) + 1} "
                               "circuit proofs (standard_recursion_config; synthetic recursion-verifier-shaped circuit, placeholder sizes; "
-                              f"witnesses given); {n_txr} transactions (8 per GPU) over {world} GPU(s), {STARK_CONTEXTS_PER_GPU} contexts per GPU",
+                              f"witnesses given); {n_txr} transactions (8 per GPU) over {world} GPU(s), {rec_contexts} contexts per GPU",
                   "tx_ms": txr_ms, "tx_per_min": n_txr * 60.0 / dt, "transactions": n_txr,
                   "timed": "tx_ms: one whole job on one context (table traces resident in HBM, circuit witnesses uploaded from the host inside) "
                            "-> all proofs on the host; tx_per_min: all jobs through the pool (wall clock, max over ranks)"}
@@ -580,9 +582,11 @@ def main():
         for db in (12, 13):
             circ, wires_w, pis = cc.hash_chain_circuit(db, seed=db)
             prover = cc.CircuitProver(ctx, circ)
-            proof = prover.prove(wires_w, pis)  # warm-up (also compiles nothing: the program was compiled at registration)
+            proof = prover.prove(wires_w, pis)  # warm-up (the program was compiled at etp_circuit_create)
             runs = [prover.prove(wires_w, pis)["ms"] for _ in range(5)]
-            entry = {"gpu_ms": {k: min(r[k] for r in runs) for k in runs[0]}, "program_ops": len(circ.program.ops),
+            entry = {"gpu_ms": {k: min(r[k] for r in runs) for k in runs[0]},
+                     "timed": "total: one etp_circuit_prove_host call, witness in pageable host memory -> proof words on the host (wall clock); "
+                              "the other keys: device time per phase (CUDA events)", "program_ops": len(circ.program.ops),
                      "vanishing_terms": circ.num_vanishing_terms}
             if not args.skip_cpu:
                 import oracle

@@ -219,6 +219,13 @@ def load_library():
         "etp_fri_proof_of_work": (i32, [vp, C.POINTER(Challenger), i32, _u64p]),
         "etp_poseidon_constants": (None, [_u64p, _u64p, _u64p]),
         "etp_program_register": (i32, [vp, _u64p, sz, C.POINTER(i32)]),
+        "etp_circuit_create": (i32, [vp, _u64p, sz, _u64p, i32, _u64p, _u64p, i32, i32, i32, i32, i32, C.POINTER(FriParams), _u64p, pp]),
+        "etp_circuit_free": (None, [vp]),
+        "etp_circuit_digest": (i32, [vp, _u64p]),
+        "etp_circuit_constants_sigmas_cap": (i32, [vp, _u64p]),
+        "etp_circuit_proof_words": (sz, [vp]),
+        "etp_circuit_prove_host": (i32, [vp, _u64p, _u64p, _u64p]),
+        "etp_circuit_prove_dev": (i32, [vp, vp, sz, _u64p, _u64p]),
         "etp_compute_quotient_polys_cols_dev": (i32, [vp, i32, C.POINTER(vp), sz, i32, i32, _u64p, i32, _u64p, _u64p, i32, vp]),
         "etp_shard_aux_columns_dev": (i32, [vp, i32, _u64p, i32, _u64p, vp, _u64p]),
         "etp_shard_compute_quotient_polys_dev": (i32, [vp, i32, vp, _u64p, i32, _u64p, _u64p, i32, vp]),

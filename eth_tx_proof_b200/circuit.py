@@ -803,105 +803,64 @@ def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float
 
 # ---- the prover -----------------------------------------------------------------------------------------------------------------
 class CircuitProver:
-    """Per-circuit state built once (ProverOnlyCircuitData / CommonCircuitData): the constants/sigmas commitment, the digest,
-    the compiled vanishing program, the LDE of X; `prove(wires, public_inputs)` runs plonk::prover::prove's steps on the device."""
+    """etp_circuit (include/etp_b200.h): per-circuit state built once (ProverOnlyCircuitData / CommonCircuitData — the
+    constants/sigmas commitment, the digest, the compiled vanishing program, the LDE of X); `prove(wires, public_inputs)` is ONE
+    C-ABI call that runs plonk::prover::prove's steps on the device and returns the proof."""
 
-    def __init__(self, ctx: Context, circuit: Circuit):
-        self.ctx, self.c = ctx, circuit
-        n = circuit.n
-        self.constants_sigmas = PolynomialBatch.from_values(ctx, np.concatenate([circuit.constants, circuit.sigmas]), RATE_BITS, False, CAP_HEIGHT)
-        self.digest = hash_no_pad([int(v) for v in np.asarray(self.constants_sigmas.cap).reshape(-1)] + [circuit.degree_bits])
-        self.table = ctx.register_program(circuit.program)
-        x_coeffs = np.zeros((1, n), dtype=np.uint64)
-        x_coeffs[0, 1] = 1
-        self.x_poly = PolynomialBatch.from_coeffs(ctx, x_coeffs, RATE_BITS, False, 0)  # its LDE column is the point itself
-        self.fri_params = FriParams.make(circuit.degree_bits, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES)
-
-    def _sigmas_dev(self, dev):
-        """The sigma values on the device (circuit data: uploaded once)."""
-        if getattr(self, "_d_sig", None) is None:
-            import torch
-
-            self._d_sig = torch.from_numpy(np.ascontiguousarray(self.c.sigmas).view(np.int64)).to(dev)
-        return self._d_sig
-
-    def fri_instance(self, zeta):
-        """CommonCircuitData::get_fri_instance: zeta opens every polynomial of the four oracles, g*zeta the Zs."""
-        c = self.c
-        g = root_of_unity(c.degree_bits)
-        zeta_next = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
-        shapes = [c.num_constants + NUM_ROUTED, NUM_WIRES, NUM_CHALLENGES * (1 + NUM_PARTIAL_PRODUCTS), NUM_CHALLENGES * QUOTIENT_DEGREE_FACTOR]
-        all_polys = [(o, k) for o, cnt in enumerate(shapes) for k in range(cnt)]
-        return [([int(zeta[0]), int(zeta[1])], all_polys), (zeta_next, [(2, k) for k in range(NUM_CHALLENGES)])]
-
-    def prove(self, wires: np.ndarray, public_inputs: Sequence[int]) -> dict:
+    def __init__(self, ctx: Context, circuit: Circuit, circuit_digest: Sequence[int] = None):
         import ctypes as C
 
-        import torch
+        self.ctx, self.c = ctx, circuit
+        self.fri_params = FriParams.make(circuit.degree_bits, RATE_BITS, CAP_HEIGHT, POW_BITS, NUM_QUERIES)
+        u64 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+        ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+        prog, consts, sig, k_is = u64(circuit.program.words), u64(circuit.constants), u64(circuit.sigmas), u64(circuit.k_is)
+        dig = u64(circuit_digest) if circuit_digest is not None else None
+        h = C.c_void_p()
+        ctx.check(ctx.L.etp_circuit_create(ctx.h, ptr(prog), prog.size, ptr(consts), circuit.num_constants, ptr(sig), ptr(k_is), NUM_ROUTED, NUM_WIRES,
+                                           circuit.degree_bits, QUOTIENT_DEGREE_FACTOR, NUM_CHALLENGES, C.byref(self.fri_params),
+                                           ptr(dig) if dig is not None else None, C.byref(h)))
+        self.h = h
+        d = np.zeros(4, dtype=np.uint64)
+        ctx.check(ctx.L.etp_circuit_digest(h, ptr(d)))
+        self.digest = [int(x) for x in d]
+        cap = np.zeros((1 << CAP_HEIGHT, 4), dtype=np.uint64)
+        ctx.check(ctx.L.etp_circuit_constants_sigmas_cap(h, ptr(cap)))
+        self.constants_sigmas_cap = cap
+        self.proof_words = int(ctx.L.etp_circuit_proof_words(h))
 
-        ctx, c = self.ctx, self.c
-        n, L = c.n, ctx.L
-        t = {}
-        pi_hash = hash_no_pad(public_inputs)
-        ch = Challenger()
-        ch.observe(self.digest)
-        ch.observe(pi_hash)
+    def prove_words(self, wires: np.ndarray, public_inputs: Sequence[int]) -> np.ndarray:
+        """-> the flat "B200PLK1" proof (wire.parse_circuit_proof)."""
+        import ctypes as C
+
+        w = np.ascontiguousarray(np.asarray(wires, dtype=np.uint64))
+        assert w.shape == (NUM_WIRES, self.c.n)
+        pi_hash = np.array(hash_no_pad(public_inputs), dtype=np.uint64)
+        out = np.zeros(self.proof_words, dtype=np.uint64)
+        ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+        self.ctx.check(self.ctx.L.etp_circuit_prove_host(self.h, ptr(w), ptr(pi_hash), ptr(out)))
+        return out
+
+    def prove(self, wires: np.ndarray, public_inputs: Sequence[int]) -> dict:
+        """-> the proof as a dict (the layout oracle.circuit_prove and tests/plonk_verifier.py use) + per-phase device times."""
+        from . import wire
+
         t0 = time.perf_counter()
-        dev = torch.device("cuda", ctx.device)  # explicit: worker threads do not inherit the caller's current device
-        d_wires = torch.from_numpy(np.ascontiguousarray(wires).view(np.int64)).to(dev)
-        d_sig = self._sigmas_dev(dev)
-        torch.cuda.synchronize(dev)
-        t["upload wires"] = (time.perf_counter() - t0) * 1e3
-        t0 = time.perf_counter()
-        wires_b = PolynomialBatch.from_values_dev(ctx, d_wires.data_ptr(), n, NUM_WIRES, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
-        t["wires commit"] = (time.perf_counter() - t0) * 1e3
-        ch.observe_cap(wires_b.cap)
-        betas, gammas = ch.get_n_challenges(NUM_CHALLENGES), ch.get_n_challenges(NUM_CHALLENGES)
-        n_zs = NUM_CHALLENGES * (1 + NUM_PARTIAL_PRODUCTS)
-        d_z = torch.empty((n_zs, n), dtype=torch.int64, device=dev)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        ctx.plonk_partial_products_and_zs_dev(d_wires.data_ptr(), n, d_sig.data_ptr(), n, np.array(c.k_is, dtype=np.uint64), c.degree_bits,
-                                              QUOTIENT_DEGREE_FACTOR, betas, gammas, d_z.data_ptr())
-        zs_b = PolynomialBatch.from_values_dev(ctx, d_z.data_ptr(), n, n_zs, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
-        t["partial products and Zs + commit"] = (time.perf_counter() - t0) * 1e3
-        ch.observe_cap(zs_b.cap)
-        alphas = ch.get_n_challenges(NUM_CHALLENGES)
-        # ---- compute_quotient_polys over the virtual columns [constants | sigmas | wires | Zs | partial products | X]
-        t0 = time.perf_counter()
-        cols = []
-        for batch in (self.constants_sigmas, wires_b, zs_b, self.x_poly):
-            stride = C.c_size_t()
-            base = L.etp_batch_lde_dev(batch.h, C.byref(stride))
-            cols += [int(base) + 8 * k * stride.value for k in range(batch.n_cols)]
-        assert len(cols) == c.num_virtual_columns
-        n_q = NUM_CHALLENGES * QUOTIENT_DEGREE_FACTOR
-        d_q = torch.empty((n_q, n), dtype=torch.int64, device=dev)
-        torch.cuda.synchronize(dev)
-        ctx.compute_quotient_polys_cols_dev(self.table, cols, c.degree_bits, RATE_BITS, list(betas) + list(gammas), pi_hash, alphas, d_q.data_ptr())
-        t["compute quotient polys"] = (time.perf_counter() - t0) * 1e3
-        t0 = time.perf_counter()
-        quot_b = PolynomialBatch.from_coeffs_dev(ctx, d_q.data_ptr(), n, n_q, c.degree_bits, RATE_BITS, False, CAP_HEIGHT)
-        t["quotient commit"] = (time.perf_counter() - t0) * 1e3
-        ch.observe_cap(quot_b.cap)
-        zeta = ch.get_extension_challenge()
-        oracles = [self.constants_sigmas, wires_b, zs_b, quot_b]
-        g = root_of_unity(c.degree_bits)
-        zeta_next = [int(zeta[0]) * g % P, int(zeta[1]) * g % P]
-        t0 = time.perf_counter()
-        openings = [o.eval_at_ext_point(zeta) for o in oracles]
-        zs_next = zs_b.eval_at_ext_point(zeta_next)[:NUM_CHALLENGES]
-        t["openings"] = (time.perf_counter() - t0) * 1e3
-        for o in openings:  # OpeningSet order: constants, plonk_sigmas, wires, plonk_zs, partial_products, quotient_polys; then plonk_zs_next
-            ch.observe(o)
-        ch.observe(zs_next)
-        t0 = time.perf_counter()
-        fri = ctx.prove_openings(self.fri_instance(zeta), oracles, ch, self.fri_params)
-        t["prove_openings (FRI)"] = (time.perf_counter() - t0) * 1e3
-        t["total"] = sum(t.values())
-        return {"degree_bits": c.degree_bits, "public_inputs": [int(x) % P for x in public_inputs],
-                "wires_cap": wires_b.cap.copy(), "plonk_zs_partial_products_cap": zs_b.cap.copy(), "quotient_polys_cap": quot_b.cap.copy(),
-                "openings": {"constants_sigmas": openings[0], "wires": openings[1], "zs_partial_products": openings[2], "quotient_polys": openings[3],
-                             "plonk_zs_next": zs_next},
-                "opening_proof": fri, "ms": t,
-                "quotient_coeffs": d_q.cpu().numpy().view(np.uint64) if n <= (1 << 8) else None}
+        words = self.prove_words(wires, public_inputs)
+        total = (time.perf_counter() - t0) * 1e3
+        p = wire.parse_circuit_proof(words)
+        op = p["openings"]
+        ms = dict(self.ctx.last_prove_timings())
+        ms["total"] = total
+        return {"degree_bits": self.c.degree_bits, "public_inputs": [int(x) % P for x in public_inputs], "words": words,
+                "wires_cap": p["wires_cap"], "plonk_zs_partial_products_cap": p["plonk_zs_partial_products_cap"],
+                "quotient_polys_cap": p["quotient_polys_cap"],
+                "openings": {"constants_sigmas": np.concatenate([op["constants"], op["plonk_sigmas"]]), "wires": op["wires"],
+                             "zs_partial_products": np.concatenate([op["plonk_zs"], op["partial_products"]]),
+                             "quotient_polys": op["quotient_polys"], "plonk_zs_next": op["plonk_zs_next"]},
+                "opening_proof": p["opening_proof"], "ms": ms}
+
+    def __del__(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.etp_circuit_free(self.h)
+            self.h = None

@@ -1428,11 +1428,20 @@ extern "C" int etp_batch_eval_at_ext_point(etp_batch* b, const uint64_t z[2], ui
 
 // plonky2::plonk::prover::all_wires_permutation_partial_products, laid out as the prover commits it: out = [Z per challenge]
 // ++ [partial products of challenge 0] ++ [partial products of challenge 1] ...
+static int plonk_partial_products_and_zs(etp_ctx* ctx, const uint64_t* wires_dev, size_t wires_stride, const uint64_t* sigmas_dev,
+                                        size_t sigmas_stride, const uint64_t* k_is, int num_routed_wires, int degree_bits, int quotient_degree_factor,
+                                        const uint64_t* betas, const uint64_t* gammas, int num_challenges, uint64_t* out_dev);
 extern "C" int etp_plonk_partial_products_and_zs_dev(etp_ctx* ctx, const uint64_t* wires_dev, size_t wires_stride, const uint64_t* sigmas_dev,
                                                      size_t sigmas_stride, const uint64_t* k_is, int num_routed_wires, int degree_bits,
                                                      int quotient_degree_factor, const uint64_t* betas, const uint64_t* gammas, int num_challenges,
                                                      uint64_t* out_dev) {
   etp_bind(ctx);
+  return plonk_partial_products_and_zs(ctx, wires_dev, wires_stride, sigmas_dev, sigmas_stride, k_is, num_routed_wires, degree_bits,
+                                       quotient_degree_factor, betas, gammas, num_challenges, out_dev);
+}
+static int plonk_partial_products_and_zs(etp_ctx* ctx, const uint64_t* wires_dev, size_t wires_stride, const uint64_t* sigmas_dev,
+                                        size_t sigmas_stride, const uint64_t* k_is, int num_routed_wires, int degree_bits, int quotient_degree_factor,
+                                        const uint64_t* betas, const uint64_t* gammas, int num_challenges, uint64_t* out_dev) {
   if (!ctx || !wires_dev || !sigmas_dev || !k_is || !betas || !gammas || !out_dev) return ETP_ERR_INVALID;
   if (num_routed_wires < 1 || num_routed_wires > 4096 || degree_bits < 0 || degree_bits > 28 || quotient_degree_factor < 1 || num_challenges < 1 ||
       num_challenges > 8 || wires_stride < ((size_t)1 << degree_bits) || sigmas_stride < ((size_t)1 << degree_bits))
@@ -1476,6 +1485,247 @@ extern "C" int etp_plonk_partial_products_and_zs_dev(etp_ctx* ctx, const uint64_
     }
   }
   return check_zero_flag(ctx, "a permutation-argument denominator vanishes");  // also keeps kc alive until the copy is done
+}
+
+// ---- plonky2 circuit prover (plonk/prover.rs prove) ------------------------------------------------------------------
+// CommonCircuitData + ProverOnlyCircuitData as far as the device steps need them.  The vanishing polynomial of the circuit
+// (plonk/vanishing_poly.rs eval_vanishing_poly) arrives as a constraint program over the virtual columns
+// [constants | sigmas | wires | Zs | partial products | X] (include/etp_b200.h, etp_circuit_create).
+constexpr uint64_t CIRCUIT_PROOF_MAGIC = 0x42323030504C4B31ULL;  // "B200PLK1"
+struct etp_circuit {
+  etp_ctx* ctx = nullptr;
+  int degree_bits = 0, num_constants = 0, num_routed = 0, num_wires = 0, num_challenges = 0, qdf = 0, n_pp = 0, table = -1;
+  etp_fri_params fp{};
+  etp_batch* constants_sigmas = nullptr;
+  etp_batch* x_poly = nullptr;     // the polynomial X: its LDE column is the evaluation point of every row
+  uint64_t* d_sigmas = nullptr;    // sigma values on the subgroup (num_routed x n), for the permutation argument
+  std::vector<uint64_t> k_is;
+  uint64_t digest[4] = {};
+  size_t n() const { return (size_t)1 << degree_bits; }
+  int n_zs() const { return num_challenges * (1 + n_pp); }
+  int n_quot() const { return num_challenges * qdf; }
+  ~etp_circuit() {
+    etp_batch_free(constants_sigmas);
+    etp_batch_free(x_poly);
+    if (d_sigmas) dev_free(ctx, d_sigmas);
+  }
+};
+static void host_hash_no_pad(const std::vector<uint64_t>& in, uint64_t out[4]) {
+  uint64_t st[12] = {};
+  for (size_t off = 0; off < in.size(); off += 8) {
+    for (size_t k = 0; k < 8 && off + k < in.size(); k++) st[k] = gl::canon(in[off + k]);
+    etp_host_poseidon_permute(st);
+  }
+  memcpy(out, st, 32);
+}
+static size_t circuit_proof_words(const etp_circuit* c) {
+  const size_t cap_words = (size_t)4 << c->fp.cap_height;
+  const size_t oc[4] = {(size_t)(c->num_constants + c->num_routed), (size_t)c->num_wires, (size_t)c->n_zs(), (size_t)c->n_quot()};
+  const size_t n_open = oc[0] + oc[1] + oc[2] + c->num_challenges + oc[3];
+  return HEADER_WORDS + 3 * cap_words + 2 * n_open + fri_proof_words(oc, 4, c->fp) + 4;
+}
+
+extern "C" int etp_circuit_create(etp_ctx* ctx, const uint64_t* vanishing_program, size_t n_words, const uint64_t* constants, int num_constants,
+                                  const uint64_t* sigmas, const uint64_t* k_is, int num_routed_wires, int num_wires, int degree_bits,
+                                  int quotient_degree_factor, int num_challenges, const etp_fri_params* fri_params, const uint64_t* circuit_digest,
+                                  etp_circuit** out) {
+  etp_bind(ctx);
+  if (!ctx || !vanishing_program || !constants || !sigmas || !k_is || !fri_params || !out) return ETP_ERR_INVALID;
+  *out = nullptr;
+  ETP_TRY(check_fri_params(ctx, *fri_params));
+  if (fri_params->degree_bits != degree_bits || degree_bits < 1 || num_constants < 1 || num_routed_wires < 1 || num_wires < num_routed_wires ||
+      num_challenges < 1 || num_challenges > NUM_CHALLENGES || quotient_degree_factor < 1 || quotient_degree_factor > 8 ||
+      (1 << fri_params->rate_bits) < quotient_degree_factor)
+    return etp_fail(ctx, ETP_ERR_INVALID, "circuit: bad shape (quotient_degree_factor must be <= min(8, 2^rate_bits), num_challenges <= %d)", NUM_CHALLENGES);
+  std::unique_ptr<etp_circuit> c(new etp_circuit());
+  c->ctx = ctx; c->degree_bits = degree_bits; c->num_constants = num_constants; c->num_routed = num_routed_wires; c->num_wires = num_wires;
+  c->num_challenges = num_challenges; c->qdf = quotient_degree_factor; c->fp = *fri_params;
+  c->n_pp = (num_routed_wires + quotient_degree_factor - 1) / quotient_degree_factor - 1;
+  c->k_is.assign(k_is, k_is + num_routed_wires);
+  ETP_TRY(register_table(ctx, vanishing_program, n_words, std::vector<uint64_t>(), &c->table, true));
+  {
+    TableInfo ti;
+    table_info(ctx, c->table, &ti);
+    const int want_cols = num_constants + num_routed_wires + num_wires + c->n_zs() + 1;
+    if (ti.cols != want_cols || quotient_factor(ti) != quotient_degree_factor || ti.n_pi > 4)
+      return etp_fail(ctx, ETP_ERR_INVALID, "circuit: the vanishing program must read %d virtual columns (has %d), have constraint degree %d and at most "
+                      "4 public inputs (the public-input hash)", want_cols, ti.cols, quotient_degree_factor + 1);
+    if ((int)ti.reg->prog.n_ch > 2 * num_challenges) return etp_fail(ctx, ETP_ERR_INVALID, "circuit: the vanishing program reads more than the betas and gammas");
+  }
+  const size_t n = c->n();
+  const int ncs = num_constants + num_routed_wires;
+  {
+    DevBuf<uint64_t> vals(ctx);
+    ETP_TRY(vals.alloc((size_t)ncs * n));
+    ETP_CUDA(ctx, cudaMemcpyAsync(vals.p, constants, (size_t)num_constants * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaMemcpyAsync(vals.p + (size_t)num_constants * n, sigmas, (size_t)num_routed_wires * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_TRY(batch_create(ctx, ncs, degree_bits, c->fp.rate_bits, 0, c->fp.cap_height, &c->constants_sigmas));
+    ETP_TRY(batch_commit_from_values(c->constants_sigmas, vals.p, n));
+    ETP_TRY(dev_alloc(ctx, (size_t)num_routed_wires * n * 8, (void**)&c->d_sigmas));
+    ETP_CUDA(ctx, cudaMemcpyAsync(c->d_sigmas, vals.p + (size_t)num_constants * n, (size_t)num_routed_wires * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  {
+    ETP_TRY(batch_create(ctx, 1, degree_bits, c->fp.rate_bits, 0, 0, &c->x_poly));
+    ETP_CUDA(ctx, cudaMemsetAsync(c->x_poly->coeffs, 0, n * 8, ctx->stream));
+    const uint64_t one = 1;
+    ETP_CUDA(ctx, cudaMemcpyAsync(c->x_poly->coeffs + 1, &one, 8, cudaMemcpyHostToDevice, ctx->stream));
+    ETP_TRY(batch_commit_from_coeffs(c->x_poly));
+  }
+  if (circuit_digest) {
+    for (int i = 0; i < 4; i++) c->digest[i] = gl::canon(circuit_digest[i]);
+  } else {  // stand-in for CircuitData::circuit_digest: hash_no_pad(constants_sigmas cap ++ degree_bits)
+    std::vector<uint64_t> in(c->constants_sigmas->cap);
+    in.push_back((uint64_t)degree_bits);
+    host_hash_no_pad(in, c->digest);
+  }
+  *out = c.release();
+  return ETP_OK;
+}
+extern "C" void etp_circuit_free(etp_circuit* c) {
+  etp_bind(c ? c->ctx : nullptr);
+  delete c;
+}
+extern "C" int etp_circuit_digest(const etp_circuit* c, uint64_t digest_out[4]) {
+  if (!c || !digest_out) return ETP_ERR_INVALID;
+  memcpy(digest_out, c->digest, 32);
+  return ETP_OK;
+}
+extern "C" int etp_circuit_constants_sigmas_cap(const etp_circuit* c, uint64_t* cap_out) {
+  if (!c || !cap_out) return ETP_ERR_INVALID;
+  memcpy(cap_out, c->constants_sigmas->cap.data(), c->constants_sigmas->cap.size() * 8);
+  return ETP_OK;
+}
+extern "C" size_t etp_circuit_proof_words(const etp_circuit* c) { return c ? circuit_proof_words(c) : 0; }
+
+// plonk::prover::prove after witness generation.  wires_dev: num_wires x n values (column-major).
+static int circuit_prove_dev(etp_circuit* c, const uint64_t* wires_dev, size_t stride, const uint64_t* pi_hash_in, uint64_t* proof) {
+  etp_ctx* ctx = c->ctx;
+  const size_t n = c->n(), cap_words = (size_t)4 << c->fp.cap_height;
+  const int log_n = c->degree_bits, rate_bits = c->fp.rate_bits, K = c->num_challenges;
+  PhaseTimer timer(ctx);
+  uint64_t pi_hash[4];
+  for (int i = 0; i < 4; i++) pi_hash[i] = gl::canon(pi_hash_in[i]);
+  struct Batches {
+    etp_batch *wires = nullptr, *zs = nullptr, *quot = nullptr;
+    ~Batches() { etp_batch_free(wires); etp_batch_free(zs); etp_batch_free(quot); }
+  } B;
+  uint64_t* w = proof;
+  uint64_t* hdr = w; w += HEADER_WORDS;
+  memset(hdr, 0, HEADER_WORDS * 8);
+  hdr[0] = CIRCUIT_PROOF_MAGIC; hdr[1] = log_n; hdr[2] = c->num_constants; hdr[3] = c->num_routed; hdr[4] = c->num_wires; hdr[5] = K;
+  hdr[6] = c->n_pp; hdr[7] = c->qdf; hdr[8] = rate_bits; hdr[9] = c->fp.cap_height; hdr[10] = c->fp.n_reductions; hdr[11] = ARITY_BITS;
+  hdr[12] = (uint64_t)1 << (log_n - fri_total_arities(c->fp)); hdr[13] = c->fp.num_query_rounds; hdr[14] = c->fp.proof_of_work_bits;
+  hdr[15] = circuit_proof_words(c);
+  hostf::Challenger ch;
+  ch.observe(c->digest, 4);
+  ch.observe(pi_hash, 4);
+  // ---- wires commitment
+  ETP_TRY(batch_create(ctx, c->num_wires, log_n, rate_bits, 0, c->fp.cap_height, &B.wires));
+  ETP_TRY(batch_commit_from_values(B.wires, wires_dev, stride));
+  timer.mark("wires commit");
+  ch.observe(B.wires->cap.data(), cap_words);
+  memcpy(w, B.wires->cap.data(), cap_words * 8); w += cap_words;
+  uint64_t betas[NUM_CHALLENGES], gammas[NUM_CHALLENGES], alphas[NUM_CHALLENGES];
+  for (int i = 0; i < K; i++) betas[i] = ch.get();
+  for (int i = 0; i < K; i++) gammas[i] = ch.get();
+  // ---- all_wires_permutation_partial_products + commitment
+  {
+    DevBuf<uint64_t> zs_vals(ctx);
+    ETP_TRY(zs_vals.alloc((size_t)c->n_zs() * n));
+    ETP_TRY(plonk_partial_products_and_zs(ctx, wires_dev, stride, c->d_sigmas, n, c->k_is.data(), c->num_routed, log_n, c->qdf, betas, gammas, K, zs_vals.p));
+    timer.mark("partial products and Zs");
+    ETP_TRY(batch_create(ctx, c->n_zs(), log_n, rate_bits, 0, c->fp.cap_height, &B.zs));
+    ETP_TRY(batch_commit_from_values(B.zs, zs_vals.p, n));
+    timer.mark("partial products and Zs commit");
+  }
+  ch.observe(B.zs->cap.data(), cap_words);
+  memcpy(w, B.zs->cap.data(), cap_words * 8); w += cap_words;
+  for (int i = 0; i < K; i++) alphas[i] = ch.get();
+  // ---- compute_quotient_polys: the vanishing program over [constants | sigmas | wires | Zs | partial products | X]
+  ETP_TRY(batch_create(ctx, c->n_quot(), log_n, rate_bits, 0, c->fp.cap_height, &B.quot));
+  {
+    const etp_batch* src[4] = {c->constants_sigmas, B.wires, B.zs, c->x_poly};
+    std::vector<uint64_t> cols;
+    for (const etp_batch* b : src)
+      for (size_t k = 0; k < b->n_cols; k++) cols.push_back((uint64_t)(uintptr_t)(b->lde + k * b->lde_n()));
+    DevBuf<uint64_t> d_cols(ctx);
+    ETP_TRY(d_cols.alloc(cols.size()));
+    ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TraceView tv;
+    tv.cols_dev = (const uint64_t* const*)d_cols.p; tv.n_cols = cols.size(); tv.log_n = log_n; tv.rate_bits = rate_bits;
+    uint64_t scalars[stark::MAX_CH_SCALARS] = {};
+    for (int i = 0; i < K; i++) { scalars[i] = betas[i]; scalars[K + i] = gammas[i]; }
+    ETP_TRY(compute_quotient(ctx, c->table, tv, nullptr, scalars, 2 * K, pi_hash, alphas, K, B.quot->coeffs));
+    ETP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // cols / d_cols are read until here
+  }
+  timer.mark("compute quotient polys");
+  ETP_TRY(batch_commit_from_coeffs(B.quot));
+  timer.mark("quotient polys commit");
+  ch.observe(B.quot->cap.data(), cap_words);
+  memcpy(w, B.quot->cap.data(), cap_words * 8); w += cap_words;
+  // ---- openings
+  const gl::Ext zeta = ch.get_ext();
+  const uint64_t g = gl::root_of_unity(log_n);
+  {
+    gl::Ext zp = zeta;
+    for (int i = 0; i < log_n; i++) zp = gl::emul(zp, zp);
+    zp = gl::ecanon(zp);
+    if (zp.c0 == 1 && zp.c1 == 0) return etp_fail(ctx, ETP_ERR_PROOF, "Opening point is in the subgroup.");
+  }
+  const gl::Ext zeta_next = gl::ecanon(gl::emul_base(zeta, g));
+  etp_batch* oracles[4] = {c->constants_sigmas, B.wires, B.zs, B.quot};
+  std::vector<gl::Ext> at[4], zs_next_all, unused;
+  {
+    DevBuf<uint64_t> l0(ctx), h0(ctx), l1(ctx), h1(ctx);
+    stark::ExtPowTable t0, t1;
+    ETP_TRY(ext_pow_table(ctx, zeta, log_n, l0, h0, &t0));
+    ETP_TRY(ext_pow_table(ctx, zeta_next, log_n, l1, h1, &t1));
+    for (int o = 0; o < 4; o++) ETP_TRY(eval_batch(ctx, oracles[o], t0, t1, at[o], o == 2 ? zs_next_all : unused));
+  }
+  timer.mark("compute openings proof: evaluate at zeta, g*zeta");
+  std::vector<gl::Ext> zs_next(zs_next_all.begin(), zs_next_all.begin() + K);
+  // OpeningSet: constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys
+  auto put = [&](const gl::Ext* v, size_t cnt) { for (size_t i = 0; i < cnt; i++) { *w++ = v[i].c0; *w++ = v[i].c1; } };
+  put(at[0].data(), at[0].size()); put(at[1].data(), at[1].size()); put(at[2].data(), K); put(zs_next.data(), K);
+  put(at[2].data() + K, at[2].size() - K); put(at[3].data(), at[3].size());
+  // observe_openings(to_fri_openings): the zeta batch (constants, sigmas, wires, zs, partial products, quotient), then zs_next
+  auto obs = [&](const std::vector<gl::Ext>& v) { for (auto& e : v) { ch.observe(e.c0); ch.observe(e.c1); } };
+  for (int o = 0; o < 4; o++) obs(at[o]);
+  obs(zs_next);
+  // ---- get_fri_instance + prove_openings
+  std::vector<etp_fri_poly> p0, p1;
+  std::vector<std::vector<gl::Ext>> ys(2);
+  for (uint32_t o = 0; o < 4; o++)
+    for (uint32_t k = 0; k < oracles[o]->n_cols; k++) { p0.push_back({o, k}); ys[0].push_back(at[o][k]); }
+  for (uint32_t k = 0; k < (uint32_t)K; k++) { p1.push_back({2, k}); ys[1].push_back(zs_next[k]); }
+  etp_fri_batch batches[2];
+  batches[0] = {{zeta.c0, zeta.c1}, p0.data(), p0.size()};
+  batches[1] = {{zeta_next.c0, zeta_next.c1}, p1.data(), p1.size()};
+  ETP_TRY(prove_openings(ctx, batches, 2, oracles, 4, ch, c->fp, &ys, w, &timer));
+  const size_t oc[4] = {oracles[0]->n_cols, oracles[1]->n_cols, oracles[2]->n_cols, oracles[3]->n_cols};
+  w += fri_proof_words(oc, 4, c->fp);
+  for (int i = 0; i < 4; i++) *w++ = pi_hash[i];
+  if ((size_t)(w - proof) != hdr[15]) return etp_fail(ctx, ETP_ERR_STATE, "internal error: circuit proof size mismatch");
+  timer.finish();
+  return ETP_OK;
+}
+
+extern "C" int etp_circuit_prove_dev(etp_circuit* c, const uint64_t* wires_dev, size_t col_stride, const uint64_t public_inputs_hash[4],
+                                     uint64_t* proof_out) {
+  etp_bind(c ? c->ctx : nullptr);
+  if (!c || !wires_dev || !public_inputs_hash || !proof_out) return ETP_ERR_INVALID;
+  if (col_stride < c->n()) return etp_fail(c->ctx, ETP_ERR_INVALID, "circuit: wires stride below n");
+  return circuit_prove_dev(c, wires_dev, col_stride, public_inputs_hash, proof_out);
+}
+extern "C" int etp_circuit_prove_host(etp_circuit* c, const uint64_t* wires, const uint64_t public_inputs_hash[4], uint64_t* proof_out) {
+  etp_bind(c ? c->ctx : nullptr);
+  if (!c || !wires || !public_inputs_hash || !proof_out) return ETP_ERR_INVALID;
+  etp_ctx* ctx = c->ctx;
+  DevBuf<uint64_t> d(ctx);
+  ETP_TRY(d.alloc((size_t)c->num_wires * c->n()));
+  ETP_CUDA(ctx, cudaMemcpyAsync(d.p, wires, (size_t)c->num_wires * c->n() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return circuit_prove_dev(c, d.p, c->n(), public_inputs_hash, proof_out);
 }
 
 extern "C" size_t etp_fri_proof_words(const size_t* oracle_num_cols, size_t n_oracles, const etp_fri_params* params) {

@@ -133,3 +133,44 @@ def from_serde_json(text: str, table: int, degree_bits: int, rate_bits: int = 1,
                 len(fri["final_poly"]["coeffs"]), len(fri["query_round_proofs"]), len(pi), rate_bits, pow_bits, num_challenges,
                 HEADER_WORDS + len(body), n_zs, n_lookup_cols, n_ctl_helper_cols]
     return np.array(hdr + body, dtype=np.uint64)
+
+
+# ---- circuit proofs ("B200PLK1", include/etp_b200.h etp_circuit_prove_*) ------------------------------------------------------
+CIRCUIT_MAGIC = 0x42323030504C4B31  # "B200PLK1"
+CIRCUIT_HEADER_FIELDS = ("magic", "degree_bits", "num_constants", "num_routed_wires", "num_wires", "num_challenges", "num_partial_products",
+                         "quotient_degree_factor", "rate_bits", "cap_height", "n_fri_layers", "arity_bits", "final_poly_len", "num_queries",
+                         "pow_bits", "total_words")
+
+
+def parse_circuit_proof(words) -> Dict[str, Any]:
+    """Flat circuit proof -> the field structure of plonky2's ProofWithPublicInputs as numpy arrays:
+    {"header", "wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap" ((2^cap, 4)),
+     "openings": {"constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys"} ((k, 2)),
+     "opening_proof" (flat FriProof words), "public_inputs_hash"}."""
+    w = np.asarray(words, dtype=np.uint64)
+    if w.size < HEADER_WORDS or int(w[0]) != CIRCUIT_MAGIC:
+        raise ValueError("not a B200PLK1 proof")
+    h = {k: int(v) for k, v in zip(CIRCUIT_HEADER_FIELDS, w[:len(CIRCUIT_HEADER_FIELDS)])}
+    if h["total_words"] != w.size:
+        raise ValueError("length mismatch")
+    pos = HEADER_WORDS
+    capw = 4 << h["cap_height"]
+
+    def take(n):
+        nonlocal pos
+        if pos + n > w.size:
+            raise ValueError("truncated proof")
+        out = w[pos:pos + n]
+        pos += n
+        return out
+
+    out = {"header": h}
+    for k in ("wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap"):
+        out[k] = take(capw).reshape(-1, 4).copy()
+    K = h["num_challenges"]
+    counts = (("constants", h["num_constants"]), ("plonk_sigmas", h["num_routed_wires"]), ("wires", h["num_wires"]), ("plonk_zs", K),
+              ("plonk_zs_next", K), ("partial_products", K * h["num_partial_products"]), ("quotient_polys", K * h["quotient_degree_factor"]))
+    out["openings"] = {k: take(2 * c).reshape(-1, 2).copy() for k, c in counts}
+    out["opening_proof"] = take(w.size - pos - 4).copy()
+    out["public_inputs_hash"] = take(4).copy()
+    return out

@@ -284,6 +284,37 @@ int etp_compute_quotient_polys_dev(etp_ctx *ctx, int table, etp_batch *trace, et
                                    const uint64_t *public_inputs, const uint64_t *alphas, int n_alphas,
                                    uint64_t *out_dev);
 
+/* ---- plonky2 circuit prover: plonk::prover::prove after witness generation (plonky2 0.2.2 src/plonk/prover.rs; what every
+ * shrink / root / aggregation / block proof of the reference runs: /root/reference/ops/src/lib.rs:52,72,95) ----------------
+ * etp_circuit = CommonCircuitData + ProverOnlyCircuitData as far as the device steps need them, built once per circuit:
+ *   vanishing_program : plonk/vanishing_poly.rs eval_vanishing_poly recorded as a constraint program (csrc/cprog.h) over the
+ *                       virtual columns [constants | sigmas | wires | Zs | partial products (challenge-major) | X], terms emitted
+ *                       in REVERSE order (reduce_with_powers weights term i with alpha^i), L_0(x)(Z - 1) as EMIT_FIRST_ROW,
+ *                       Z(g x) as NV of the Z columns; CH 0..k-1 = betas, CH k..2k-1 = gammas; PI 0..3 = public_inputs_hash
+ *   constants, sigmas : values on the subgroup, column-major (num_constants x n, num_routed_wires x n), host memory
+ *   k_is              : the coset shifts of the routed columns
+ *   fri_params        : e.g. etp_fri_params_make(degree_bits, 3, 4, 16, 28) for standard_recursion_config
+ *   circuit_digest    : 4 words, or NULL for a stand-in (hash_no_pad(constants_sigmas cap ++ degree_bits))
+ * etp_circuit_prove_*: wires = the witness, num_wires x n values column-major.  Transcript as upstream: circuit digest,
+ * public_inputs_hash, wires cap -> betas, gammas; Z / partial-products cap -> alphas; quotient cap -> zeta; openings -> FRI.
+ * Proof words "B200PLK1": header[24] = {magic, degree_bits, num_constants, num_routed_wires, num_wires, num_challenges,
+ * num_partial_products, quotient_degree_factor, rate_bits, cap_height, n_fri_layers, arity_bits, final_poly_len, num_queries,
+ * pow_bits, total_words}; wires_cap, plonk_zs_partial_products_cap, quotient_polys_cap; OpeningSet {constants, plonk_sigmas,
+ * wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys} (extension values); the flat FriProof over the oracles
+ * [constants_sigmas, wires, zs_partial_products, quotient]; public_inputs_hash. */
+typedef struct etp_circuit etp_circuit;
+int etp_circuit_create(etp_ctx *ctx, const uint64_t *vanishing_program, size_t n_words, const uint64_t *constants,
+                       int num_constants, const uint64_t *sigmas, const uint64_t *k_is, int num_routed_wires, int num_wires,
+                       int degree_bits, int quotient_degree_factor, int num_challenges, const etp_fri_params *fri_params,
+                       const uint64_t *circuit_digest, etp_circuit **out);
+void etp_circuit_free(etp_circuit *c);
+int etp_circuit_digest(const etp_circuit *c, uint64_t digest_out[4]);
+int etp_circuit_constants_sigmas_cap(const etp_circuit *c, uint64_t *cap_out);
+size_t etp_circuit_proof_words(const etp_circuit *c);
+int etp_circuit_prove_host(etp_circuit *c, const uint64_t *wires, const uint64_t public_inputs_hash[4], uint64_t *proof_out);
+int etp_circuit_prove_dev(etp_circuit *c, const uint64_t *wires_dev, size_t col_stride, const uint64_t public_inputs_hash[4],
+                          uint64_t *proof_out);
+
 /* Registers a constraint program that is NOT a starky table: constraint degree up to 9 (quotient degree factor up to 8), up
  * to 8 challenge scalars, no auxiliary polynomials, no StarkConfig limits — e.g. the vanishing polynomial of a plonky2
  * circuit (plonk/vanishing_poly.rs eval_vanishing_poly recorded over the virtual columns [constants | sigmas | wires | Zs |

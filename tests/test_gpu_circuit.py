@@ -78,32 +78,49 @@ def _python_quotient(circuit, wires, zs_pp, pi_hash, betas, gammas, alphas):
 
 
 def test_quotient_matches_python_and_proof_verifies_small(ctx):
+    """etp_program_register + etp_compute_quotient_polys_cols_dev on the committed oracles' LDE columns == the pure-Python
+    quotient, coefficient for coefficient; then the whole proof (one etp_circuit_prove_host call) is verified."""
+    import ctypes as C
+
+    import torch
+
+    import eth_tx_proof_b200 as etp
     import oracle
     import plonk_verifier
     from eth_tx_proof_b200 import circuit as cc
 
     circuit, wires, public_inputs = cc.hash_chain_circuit(5, seed=11)
-    prover = cc.CircuitProver(ctx, circuit)
-    proof = prover.prove(wires, public_inputs)
-    # replay the transcript to get the challenges the prover used
-    import eth_tx_proof_b200 as etp
-
-    ch = etp.Challenger()
-    ch.observe(prover.digest)
-    ch.observe(cc.hash_no_pad(public_inputs))
-    ch.observe_cap(proof["wires_cap"])
-    betas, gammas = ch.get_n_challenges(2), ch.get_n_challenges(2)
-    ch.observe_cap(proof["plonk_zs_partial_products_cap"])
-    alphas = ch.get_n_challenges(2)
-    zs_pp = oracle.plonk_partial_products_and_zs(wires[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
-    want = _python_quotient(circuit, wires, zs_pp, cc.hash_no_pad(public_inputs), betas, gammas, alphas)
-    got = proof["quotient_coeffs"]  # (16, n): challenge j, chunk k = coefficients [k n, (k+1) n)
     n = circuit.n
+    pi_hash = cc.hash_no_pad(public_inputs)
+    betas, gammas, alphas = [0x1111, 0x2222], [0x3333, 0x4444], [0x5555, 0x6666]
+    zs_pp = oracle.plonk_partial_products_and_zs(wires[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
+    x_coeffs = np.zeros((1, n), dtype=np.uint64)
+    x_coeffs[0, 1] = 1
+    batches = [etp.PolynomialBatch.from_values(ctx, np.concatenate([circuit.constants, circuit.sigmas]), 3, False, 4),
+               etp.PolynomialBatch.from_values(ctx, wires, 3, False, 4), etp.PolynomialBatch.from_values(ctx, zs_pp, 3, False, 4),
+               etp.PolynomialBatch.from_coeffs(ctx, x_coeffs, 3, False, 0)]
+    cols = []
+    for b in batches:
+        stride = C.c_size_t()
+        base = ctx.L.etp_batch_lde_dev(b.h, C.byref(stride))
+        cols += [int(base) + 8 * k * stride.value for k in range(b.n_cols)]
+    table = ctx.register_program(circuit.program)
+    d_q = torch.zeros((16, n), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.compute_quotient_polys_cols_dev(table, cols, circuit.degree_bits, 3, betas + gammas, pi_hash, alphas, d_q.data_ptr())
+    got = d_q.cpu().numpy().view(np.uint64)  # (16, n): challenge j, chunk k = coefficients [k n, (k+1) n)
+    want = _python_quotient(circuit, wires, zs_pp, pi_hash, betas, gammas, alphas)
     for j in range(2):
         assert all(c == 0 for c in want[j][8 * n - 8:]), "degree bound: deg(vanishing) <= 9 (n - 1), minus deg Z_H"
         for k in range(8):
             assert [int(v) for v in got[8 * j + k]] == want[j][k * n:(k + 1) * n], f"quotient chunk {j}/{k}"
-    plonk_verifier.verify(proof, circuit, prover.constants_sigmas.cap, prover.digest, max_queries=None)
+    # a standalone program is not a starky table
+    with pytest.raises(etp.EtpError):
+        ctx.stark_prove(table, np.zeros((circuit.program.n_trace, 32), dtype=np.uint64), [0, 0, 0, 0])
+    prover = cc.CircuitProver(ctx, circuit)
+    proof = prover.prove(wires, public_inputs)
+    assert proof["words"].size == prover.proof_words
+    plonk_verifier.verify(proof, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=None)
 
 
 @pytest.mark.parametrize("degree_bits", [7, 10, 12])
@@ -114,7 +131,7 @@ def test_circuit_proof_is_accepted_by_the_verifier(ctx, degree_bits):
     circuit, wires, public_inputs = cc.hash_chain_circuit(degree_bits, seed=degree_bits)
     prover = cc.CircuitProver(ctx, circuit)
     proof = prover.prove(wires, public_inputs)
-    plonk_verifier.verify(proof, circuit, prover.constants_sigmas.cap, prover.digest, max_queries=4 if degree_bits > 7 else None)
+    plonk_verifier.verify(proof, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=4 if degree_bits > 7 else None)
     # the same prover proves another witness of the same circuit (circuit state is reused)
     proof2 = prover.prove(wires, public_inputs)
     assert (proof2["opening_proof"] == proof["opening_proof"]).all()
@@ -130,13 +147,11 @@ def test_circuit_proof_equals_the_oracles_bit_for_bit(ctx, degree_bits):
     prover = cc.CircuitProver(ctx, circuit)
     got = prover.prove(wires, public_inputs)
     want = oracle.circuit_prove(circuit, wires, public_inputs, prover.digest)
-    assert (np.asarray(prover.constants_sigmas.cap) == want["constants_sigmas_cap"]).all()
+    assert (np.asarray(prover.constants_sigmas_cap) == want["constants_sigmas_cap"]).all()
     for k in ("wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap"):
         assert (np.asarray(got[k]) == want[k]).all(), k
     for k, v in want["openings"].items():
         assert (np.asarray(got["openings"][k]).reshape(-1) == np.asarray(v).reshape(-1)).all(), k
-    if got["quotient_coeffs"] is not None:
-        assert (got["quotient_coeffs"] == want["quotient_coeffs"]).all()
     assert got["opening_proof"].shape == want["opening_proof"].shape and (got["opening_proof"] == want["opening_proof"]).all()
 
 
@@ -155,7 +170,7 @@ def test_full_gate_set_proof_equals_oracle_and_verifies(ctx, degree_bits):
     for k in ("wires_cap", "plonk_zs_partial_products_cap", "quotient_polys_cap"):
         assert (np.asarray(got[k]) == want[k]).all(), k
     assert (got["opening_proof"] == want["opening_proof"]).all()
-    plonk_verifier.verify(got, circuit, prover.constants_sigmas.cap, prover.digest, max_queries=3)
+    plonk_verifier.verify(got, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=3)
 
 
 def test_invalid_witness_is_rejected(ctx):
@@ -177,4 +192,4 @@ def test_invalid_witness_is_rejected(ctx):
             pi[0] = (pi[0] + 1) % P
         proof = prover.prove(w, pi)
         with pytest.raises(plonk_verifier.VerifyError):
-            plonk_verifier.verify(proof, circuit, prover.constants_sigmas.cap, prover.digest, max_queries=1)
+            plonk_verifier.verify(proof, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=1)
