@@ -174,3 +174,90 @@ def parse_circuit_proof(words) -> Dict[str, Any]:
     out["opening_proof"] = take(w.size - pos - 4).copy()
     out["public_inputs_hash"] = take(4).copy()
     return out
+
+
+def _fri_to_serde(words, oracle_cols, h) -> Dict[str, Any]:
+    """Flat FriProof words -> plonky2's FriProof structure (as `parse` builds it for the STARK proofs)."""
+    w = [int(x) for x in words]
+    pos = 0
+    capw = 4 << h["cap_height"]
+
+    def take(n):
+        nonlocal pos
+        out = w[pos:pos + n]
+        if len(out) != n:
+            raise ValueError("truncated FRI proof")
+        pos += n
+        return out
+
+    hashes = lambda ws: [{"elements": ws[4 * i:4 * i + 4]} for i in range(len(ws) // 4)]
+    exts = lambda n: (lambda c: [[c[2 * i], c[2 * i + 1]] for i in range(n)])(take(2 * n))
+    log_lde = h["degree_bits"] + h["rate_bits"]
+    caps = [hashes(take(capw)) for _ in range(h["n_fri_layers"])]
+    rounds = []
+    for _ in range(h["num_queries"]):
+        evals_proofs = []
+        for ncols in oracle_cols:
+            leaf = take(ncols)
+            evals_proofs.append([leaf, {"siblings": hashes(take(4 * (log_lde - h["cap_height"])))}])
+        steps, bits = [], log_lde
+        for _l in range(h["n_fri_layers"]):
+            bits -= h["arity_bits"]
+            ev = exts(1 << h["arity_bits"])
+            steps.append({"evals": ev, "merkle_proof": {"siblings": hashes(take(4 * (bits - h["cap_height"])))}})
+        rounds.append({"initial_trees_proof": {"evals_proofs": evals_proofs}, "steps": steps})
+    final_poly = {"coeffs": exts(h["final_poly_len"])}
+    pow_witness = take(1)[0]
+    if pos != len(w):
+        raise ValueError("trailing words in the FRI proof")
+    return {"commit_phase_merkle_caps": caps, "query_round_proofs": rounds, "final_poly": final_poly, "pow_witness": pow_witness}
+
+
+def circuit_to_serde_json(words, public_inputs) -> str:
+    """serde_json::to_string(&ProofWithPublicInputs<GoldilocksField, PoseidonGoldilocksConfig, 2>) for a circuit proof — the
+    form in which the reference passes shrink / aggregation / block proofs around (PlonkyProofIntern,
+    /root/reference/ops/src/lib.rs:63-101).  Field names follow plonky2 0.2.2 plonk/proof.rs:
+      ProofWithPublicInputs { proof: Proof, public_inputs }
+      Proof { wires_cap, plonk_zs_partial_products_cap, quotient_polys_cap, openings: OpeningSet, opening_proof: FriProof }
+      OpeningSet { constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys,
+                   lookup_zs, lookup_zs_next }"""
+    p = parse_circuit_proof(words)
+    h = p["header"]
+    cap = lambda c: [{"elements": [int(x) for x in row]} for row in c]
+    ext = lambda a: [[int(x[0]), int(x[1])] for x in a]
+    op = {k: ext(v) for k, v in p["openings"].items()}
+    op["lookup_zs"], op["lookup_zs_next"] = [], []
+    K = h["num_challenges"]
+    oracle_cols = [h["num_constants"] + h["num_routed_wires"], h["num_wires"], K * (1 + h["num_partial_products"]), K * h["quotient_degree_factor"]]
+    proof = {"wires_cap": cap(p["wires_cap"]), "plonk_zs_partial_products_cap": cap(p["plonk_zs_partial_products_cap"]),
+             "quotient_polys_cap": cap(p["quotient_polys_cap"]), "openings": op, "opening_proof": _fri_to_serde(p["opening_proof"], oracle_cols, h)}
+    return json.dumps({"proof": proof, "public_inputs": [int(x) for x in public_inputs]}, separators=(",", ":"))
+
+
+def circuit_from_serde_json(text: str, degree_bits: int, public_inputs_hash, rate_bits: int = 3, pow_bits: int = 16) -> np.ndarray:
+    """The inverse of circuit_to_serde_json: flat "B200PLK1" words (the header facts JSON does not carry are arguments)."""
+    d = json.loads(text)
+    pr = d["proof"]
+    op, fri = pr["openings"], pr["opening_proof"]
+    flat_cap = lambda c: [x for hsh in c for x in hsh["elements"]]
+    flat_ext = lambda v: [x for e in v for x in e]
+    K = len(op["plonk_zs"])
+    cap_height = (len(pr["wires_cap"]) - 1).bit_length()
+    steps0 = fri["query_round_proofs"][0]["steps"] if fri["query_round_proofs"] else []
+    arity_bits = (len(steps0[0]["evals"]) - 1).bit_length() if steps0 else 4
+    body = flat_cap(pr["wires_cap"]) + flat_cap(pr["plonk_zs_partial_products_cap"]) + flat_cap(pr["quotient_polys_cap"])
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "plonk_zs_next", "partial_products", "quotient_polys"):
+        body += flat_ext(op[k])
+    for c in fri["commit_phase_merkle_caps"]:
+        body += flat_cap(c)
+    for r in fri["query_round_proofs"]:
+        for leaf, mp in r["initial_trees_proof"]["evals_proofs"]:
+            body += list(leaf) + flat_cap(mp["siblings"])
+        for st in r["steps"]:
+            body += flat_ext(st["evals"]) + flat_cap(st["merkle_proof"]["siblings"])
+    body += flat_ext(fri["final_poly"]["coeffs"]) + [fri["pow_witness"]] + [int(x) for x in public_inputs_hash]
+    hdr = [0] * HEADER_WORDS
+    hdr[:16] = [CIRCUIT_MAGIC, degree_bits, len(op["constants"]), len(op["plonk_sigmas"]), len(op["wires"]), K, len(op["partial_products"]) // K,
+                len(op["quotient_polys"]) // K, rate_bits, cap_height, len(fri["commit_phase_merkle_caps"]), arity_bits,
+                len(fri["final_poly"]["coeffs"]), len(fri["query_round_proofs"]), pow_bits, HEADER_WORDS + len(body)]
+    return np.array(hdr + body, dtype=np.uint64)

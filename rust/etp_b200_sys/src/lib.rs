@@ -185,3 +185,52 @@ pub fn register_table(ctx: &Ctx, program: &[u64], aux_spec: &[u64]) -> i32 {
     ctx.check(rc);
     id as i32
 }
+
+/// plonky2's circuit prover on the device (`plonk::prover::prove` after witness generation): built once per circuit from the
+/// recorded vanishing polynomial (run `eval_vanishing_poly` on `recorder::Sym` over the virtual columns constants, sigmas,
+/// wires, Zs, partial products, X — terms emitted in reverse — and take `recorder::finish()`), the constants and sigma
+/// polynomials' values and the coset shifts; `prove` is one call per proof.
+pub struct DeviceCircuit { pub raw: *mut etp_circuit, pub proof_words: usize }
+unsafe impl Send for DeviceCircuit {}
+
+impl DeviceCircuit {
+    /// `constants` / `sigmas`: values on the subgroup, column-major (`num_constants x n`, `num_routed_wires x n`).
+    #[allow(clippy::too_many_arguments)]
+    pub fn new(ctx: &Ctx, vanishing_program: &[u64], constants: &[u64], num_constants: usize, sigmas: &[u64], k_is: &[u64], num_wires: usize,
+               degree_bits: usize, quotient_degree_factor: usize, num_challenges: usize, fri_params: &etp_fri_params,
+               circuit_digest: Option<[u64; 4]>) -> Self {
+        let n = 1usize << degree_bits;
+        assert_eq!(constants.len(), num_constants * n);
+        assert_eq!(sigmas.len(), k_is.len() * n);
+        let mut raw: *mut etp_circuit = std::ptr::null_mut();
+        let digest_ptr = circuit_digest.as_ref().map_or(std::ptr::null(), |d| d.as_ptr());
+        let rc = unsafe {
+            etp_circuit_create(ctx.0, vanishing_program.as_ptr(), vanishing_program.len(), constants.as_ptr(), num_constants as c_int, sigmas.as_ptr(),
+                               k_is.as_ptr(), k_is.len() as c_int, num_wires as c_int, degree_bits as c_int, quotient_degree_factor as c_int,
+                               num_challenges as c_int, fri_params, digest_ptr, &mut raw)
+        };
+        ctx.check(rc);
+        let proof_words = unsafe { etp_circuit_proof_words(raw) };
+        DeviceCircuit { raw, proof_words }
+    }
+
+    /// `wires`: the witness, `num_wires x n` values column-major.  Returns the flat "B200PLK1" proof words
+    /// (include/etp_b200.h; `ProofWithPublicInputs` is rebuilt from them field by field).
+    pub fn prove(&self, ctx: &Ctx, wires: &[u64], public_inputs_hash: [u64; 4]) -> Vec<u64> {
+        let mut out = vec![0u64; self.proof_words];
+        let rc = unsafe { etp_circuit_prove_host(self.raw, wires.as_ptr(), public_inputs_hash.as_ptr(), out.as_mut_ptr()) };
+        ctx.check(rc);
+        out
+    }
+
+    pub fn digest(&self) -> [u64; 4] {
+        let mut d = [0u64; 4];
+        unsafe { etp_circuit_digest(self.raw, d.as_mut_ptr()) };
+        d
+    }
+}
+impl Drop for DeviceCircuit {
+    fn drop(&mut self) {
+        unsafe { etp_circuit_free(self.raw) }
+    }
+}

@@ -132,9 +132,13 @@ def test_circuit_proof_is_accepted_by_the_verifier(ctx, degree_bits):
     prover = cc.CircuitProver(ctx, circuit)
     proof = prover.prove(wires, public_inputs)
     plonk_verifier.verify(proof, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=4 if degree_bits > 7 else None)
-    # the same prover proves another witness of the same circuit (circuit state is reused)
+    # the same prover proves again (circuit state is reused): same words; and the serde-JSON form round-trips
     proof2 = prover.prove(wires, public_inputs)
-    assert (proof2["opening_proof"] == proof["opening_proof"]).all()
+    assert (proof2["words"] == proof["words"]).all()
+    from eth_tx_proof_b200 import wire
+
+    text = wire.circuit_to_serde_json(proof["words"], public_inputs)
+    assert (wire.circuit_from_serde_json(text, degree_bits, cc.hash_no_pad(public_inputs)) == proof["words"]).all()
 
 
 @pytest.mark.parametrize("degree_bits", [6, 9, 12])
