@@ -20,8 +20,9 @@ term i with alpha^i, the consumer of the quotient kernels weights emission i of 
 in reverse.
 
 Gates (constraints restated from plonky2/src/gates/*.rs): NoopGate, ConstantGate, PublicInputGate, ArithmeticGate,
-PoseidonGate (123 constraints of degree 7; the partial rounds are written with the plain round function — the same
-polynomials in the wires as upstream's fast partial rounds, which only re-factor the linear layers), ArithmeticExtensionGate,
+PoseidonGate (123 constraints of degree 7; the partial rounds in upstream's fast form — `partial_first_constant_layer`,
+`mds_partial_layer_init`, `mds_partial_layer_fast` — with the sparse matrices and moved constants derived here from the MDS matrix
+and the round constants, checked against the plain round function), ArithmeticExtensionGate,
 MulExtensionGate, BaseSumGate<2>, ReducingGate, ReducingExtensionGate, RandomAccessGate, ExponentiationGate, PoseidonMdsGate.
 Not built: CosetInterpolationGate, lookup tables / lookup gates, witness generation by generators (witnesses here are computed directly), zero-knowledge blinding
 (off in standard_recursion_config).  The circuit digest is a stand-in (hash of the constants/sigmas cap and degree_bits).
@@ -79,6 +80,128 @@ def mds_layer(state, add=None, mulc=None):
             acc = add(acc, mulc(state[r], diag[r]))
         out.append(acc)
     return out
+
+
+def mds_matrix() -> List[List[int]]:
+    """M[r][c]: out[r] = sum_c M[r][c] in[c] (column-vector form of mds_row_shf)."""
+    _, circ, diag = _pc()
+    m = [[0] * 12 for _ in range(12)]
+    for r in range(12):
+        for i in range(12):
+            m[r][(i + r) % 12] = (m[r][(i + r) % 12] + circ[i]) % P
+        m[r][r] = (m[r][r] + diag[r]) % P
+    return m
+
+
+def _mat_inv(a: List[List[int]]) -> List[List[int]]:
+    """Inverse of a square matrix over the field (Gauss-Jordan, Python ints)."""
+    n = len(a)
+    m = [list(row) + [1 if i == j else 0 for j in range(n)] for i, row in enumerate(a)]
+    for col in range(n):
+        piv = next(r for r in range(col, n) if m[r][col] % P)
+        m[col], m[piv] = m[piv], m[col]
+        inv = pow(m[col][col], P - 2, P)
+        m[col] = [x * inv % P for x in m[col]]
+        for r in range(n):
+            if r != col and m[r][col]:
+                f = m[r][col]
+                m[r] = [(x - f * y) % P for x, y in zip(m[r], m[col])]
+    return [row[n:] for row in m]
+
+
+def _mat_mul(a, b):
+    return [[sum(a[i][k] * b[k][j] for k in range(len(b))) % P for j in range(len(b[0]))] for i in range(len(a))]
+
+
+_FAST = None
+
+
+def fast_partial_round_constants():
+    """The partial rounds in the form of plonky2's `partial_first_constant_layer` / `mds_partial_layer_init` /
+    `mds_partial_layer_fast` (poseidon.rs; Poseidon paper, appendix B), derived here from the MDS matrix and the round
+    constants rather than copied:
+      constants: c_r = M d  =>  M S(x) + c_r = M (S(x) + d): d[1:] moves in front of the previous S-box, d[0] stays behind it;
+      matrices:  D M = S diag(1, H) with D = diag(1, A) the dense part pushed back from the next round, H = A M^, and the
+                 sparse S = [[m00, a^T H^-1], [A b, I]]; the last dense part, diag(1, H_0), is applied once before the first S-box.
+    -> (first_constants[12], scalar_constants[21], initial_matrix[11][11], w_hats[22][11], vs[22][11], m00)."""
+    global _FAST
+    if _FAST is not None:
+        return _FAST
+    rc, _, _ = _pc()
+    M = mds_matrix()
+    M_inv = _mat_inv(M)
+    c = [list(rc[4 + r]) for r in range(22)]
+    k = [0] * 22  # k[r]: added to element 0 after the S-box of partial round r - 1
+    for r in range(21, 0, -1):
+        d = [sum(M_inv[i][j] * c[r][j] for j in range(12)) % P for i in range(12)]
+        c[r - 1] = [c[r - 1][0]] + [(c[r - 1][i] + d[i]) % P for i in range(1, 12)]
+        k[r] = d[0]
+    m00 = M[0][0]
+    a = [M[0][j] for j in range(1, 12)]
+    b = [M[i][0] for i in range(1, 12)]
+    M_hat = [[M[i][j] for j in range(1, 12)] for i in range(1, 12)]
+    A = [[1 if i == j else 0 for j in range(11)] for i in range(11)]
+    w_hats, vs = [None] * 22, [None] * 22
+    for r in range(21, -1, -1):
+        H = _mat_mul(A, M_hat)
+        H_inv = _mat_inv(H)
+        w_hats[r] = [sum(a[i] * H_inv[i][j] for i in range(11)) % P for j in range(11)]
+        vs[r] = [sum(A[i][j] * b[j] for j in range(11)) % P for i in range(11)]
+        A = H
+    _FAST = (c[0], k[1:], A, w_hats, vs, m00)
+    return _FAST
+
+
+class _IntRing:
+    add = staticmethod(lambda x, y: (x + y) % P)
+    addc = staticmethod(lambda x, c: (x + c) % P)
+    mulc = staticmethod(lambda x, c: x * c % P)
+    mul = staticmethod(lambda x, y: x * y % P)
+
+
+class _ExprRing:
+    def __init__(self, b):
+        self.b = b
+
+    add = staticmethod(lambda x, y: x + y)
+    mul = staticmethod(lambda x, y: x * y)
+
+    def addc(self, x, c):
+        return x + self.b.const(c)
+
+    def mulc(self, x, c):
+        return x * self.b.const(c)
+
+
+def partial_rounds_fast(state, ring, sbox_in_hook=None):
+    """The 22 partial rounds in the fast form over a ring (_IntRing / _ExprRing).  sbox_in_hook(r, state0) -> the value whose 7th
+    power continues (the gate records `state0 - wire` and returns the wire); None: plain evaluation."""
+    first, ks, init, w_hats, vs, m00 = fast_partial_round_constants()
+
+    def sbox(x):
+        x2 = ring.mul(x, x)
+        x4 = ring.mul(x2, x2)
+        return ring.mul(x4, ring.mul(x2, x))
+
+    state = [ring.addc(x, first[i]) for i, x in enumerate(state)]  # partial_first_constant_layer
+    rest = []  # mds_partial_layer_init: element 0 untouched, diag(1, H_0) on the others
+    for i in range(11):
+        acc = None
+        for j in range(11):
+            t = ring.mulc(state[1 + j], init[i][j])
+            acc = t if acc is None else ring.add(acc, t)
+        rest.append(acc)
+    state = [state[0]] + rest
+    for r in range(22):
+        x0 = state[0] if sbox_in_hook is None else sbox_in_hook(r, state[0])
+        x0 = sbox(x0)
+        if r < 21:
+            x0 = ring.addc(x0, ks[r])
+        d = ring.mulc(x0, m00)  # mds_partial_layer_fast: d = [m00 | w_hat] . state ; state[i] += x0 * v[i]
+        for j in range(11):
+            d = ring.add(d, ring.mulc(state[1 + j], w_hats[r][j]))
+        state = [d] + [ring.add(state[1 + j], ring.mulc(x0, vs[r][j])) for j in range(11)]
+    return state
 
 
 def poseidon_gate_wires(inputs: Sequence[int], swap: int) -> List[int]:
@@ -186,6 +309,7 @@ class ArithmeticGate(Gate):
 class PoseidonGate(Gate):
     """gates/poseidon.rs: one permutation per row, with an optional swap of the two 4-element input halves (Merkle paths)."""
     name, degree, num_constants, num_constraints = "PoseidonGate", 7, 0, 123
+    fast_partial = True
     WIRE_SWAP = 24
     START_DELTA, START_FULL_0, START_PARTIAL, START_FULL_1 = 25, 29, 65, 87
 
@@ -236,13 +360,19 @@ class PoseidonGate(Gate):
                     state[i] = sbox_in
             state = mds([sbox(s) for s in state])
             rnd += 1
-        for r in range(22):
-            state = [s + b.const(c) for s, c in zip(state, rc[rnd])]
+        def partial_hook(r, state0):  # constraint on the S-box input of partial round r, then continue from the wire
             sbox_in = wire(self.wire_partial_sbox(r))
-            cons.append(state[0] - sbox_in)
-            state[0] = sbox(sbox_in)
-            state = mds(state)
-            rnd += 1
+            cons.append(state0 - sbox_in)
+            return sbox_in
+
+        if self.fast_partial:  # partial_first_constant_layer, mds_partial_layer_init, mds_partial_layer_fast (poseidon.rs)
+            state = partial_rounds_fast(state, _ExprRing(b), partial_hook)
+        else:  # the plain round function: the same polynomials, 6x the multiplications
+            for r in range(22):
+                state = [s + b.const(c) for s, c in zip(state, rc[rnd + r])]
+                state[0] = sbox(partial_hook(r, state[0]))
+                state = mds(state)
+        rnd += 22
         for r in range(4):
             state = [s + b.const(c) for s, c in zip(state, rc[rnd])]
             for i in range(12):

@@ -174,3 +174,34 @@ def test_oracle_proof_of_the_full_gate_set_verifies():
     digest = [5, 6, 7, 8]
     proof = oracle.circuit_prove(circuit, wires, public_inputs, digest)
     plonk_verifier.verify(proof, circuit, proof["constants_sigmas_cap"], digest, max_queries=2)
+
+
+def test_fast_partial_rounds_equal_the_plain_round_function():
+    """The derived sparse-matrix form of the 22 partial rounds (poseidon.rs partial_first_constant_layer / mds_partial_layer_init /
+    mds_partial_layer_fast) == the plain rounds, as a permutation and as POLYNOMIALS in the gate's wires: both forms of the
+    PoseidonGate program give the same 123 constraint values on random (non-witness) wire assignments."""
+    from eth_tx_proof_b200 import circuit as cc, cprog
+
+    rc, _, _ = cc._pc()
+    rng = np.random.default_rng(9)
+    for _ in range(4):
+        st = [int(x) % P for x in rng.integers(0, 2**63, 12)]
+        plain = list(st)
+        for r in range(22):
+            plain = [(s + c) % P for s, c in zip(plain, rc[4 + r])]
+            plain[0] = pow(plain[0], 7, P)
+            plain = cc.mds_layer(plain)
+        assert cc.partial_rounds_fast(list(st), cc._IntRing) == plain
+    progs = []
+    for fast in (True, False):
+        gate = cc.PoseidonGate()
+        gate.fast_partial = fast
+        b = cprog.ProgramBuilder(cc.NUM_WIRES, 0, 8)
+        for c in gate.eval(b, b.lv, None, None):
+            b.constraint(c)
+        progs.append(b.build())
+    assert len(progs[0].ops) < 0.6 * len(progs[1].ops)
+    for _ in range(3):
+        lv = [int(x) % P for x in rng.integers(0, 2**63, cc.NUM_WIRES)]
+        a, b_ = (p.evaluate(lv, lv) for p in progs)
+        assert [v % P for _, v in a] == [v % P for _, v in b_]
