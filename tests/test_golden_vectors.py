@@ -19,6 +19,16 @@ with open(os.path.join(ROOT, "tests", "golden", "path_vectors.json")) as _f:
     GOLD = json.load(_f)
 
 
+with open(os.path.join(ROOT, "tests", "golden", "circuit_vectors.json")) as _f:
+    GOLD_CIRCUITS = json.load(_f)
+
+
+@pytest.mark.parametrize("k", range(len(gg.CIRCUITS)))
+def test_oracle_reproduces_golden_circuit_proofs(k):
+    assert [tuple(c["shape"]) for c in GOLD_CIRCUITS["circuits"]] == gg.CIRCUITS
+    assert gg.circuit_case(*gg.CIRCUITS[k]) == GOLD_CIRCUITS["circuits"][k]
+
+
 def test_golden_file_covers_the_generator_cases():
     assert [tuple(c["shape"]) for c in GOLD["commits"]] == gg.COMMITS
     assert [(p["table"], p["log_n"], p["seed"]) for p in GOLD["proofs"]] == gg.PROOFS
@@ -75,3 +85,25 @@ def test_cuda_reproduces_golden_proofs(ctx, k):
     proof = ctx.stark_prove(tid, trace, pi) if len(pi) else ctx.stark_prove(tid, trace)
     assert int(proof.size) == g["words"]
     assert gg.sha(np.concatenate([proof[:1], proof[2:]])) == g["proof_sha256_without_table_id"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", range(len(gg.CIRCUITS)))
+def test_cuda_reproduces_golden_circuit_proofs(ctx, k):
+    """etp_circuit_create + etp_circuit_prove_host against the committed digests, the oracle not in the loop."""
+    from eth_tx_proof_b200 import circuit as cc
+
+    g = GOLD_CIRCUITS["circuits"][k]
+    circ, wires, pis = gg.circuit_inputs(*g["shape"])
+    assert len(circ.program.ops) == g["program_ops"] and circ.num_constants == g["num_constants"]
+    prover = cc.CircuitProver(ctx, circ)
+    assert [f"{x:016x}" for x in prover.digest] == g["digest"]
+    assert gg.sha(prover.constants_sigmas_cap) == g["constants_sigmas_cap_sha256"]
+    pr = prover.prove(wires, pis)
+    op = pr["openings"]
+    assert gg.sha(pr["wires_cap"]) == g["wires_cap_sha256"]
+    assert gg.sha(pr["plonk_zs_partial_products_cap"]) == g["zs_partial_products_cap_sha256"]
+    assert gg.sha(pr["quotient_polys_cap"]) == g["quotient_polys_cap_sha256"]
+    assert gg.sha(np.concatenate([np.asarray(op[k2]).reshape(-1) for k2 in
+                                  ("constants_sigmas", "wires", "zs_partial_products", "quotient_polys", "plonk_zs_next")])) == g["openings_sha256"]
+    assert int(pr["opening_proof"].size) == g["opening_proof_words"] and gg.sha(pr["opening_proof"]) == g["opening_proof_sha256"]

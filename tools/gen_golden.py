@@ -73,6 +73,42 @@ def proof_case(table, log_n, seed):
             "pow_witness": f"{int(proof[-1 - len(pi)]):016x}" if len(pi) else f"{int(proof[-1]):016x}"}
 
 
+CIRCUITS = [  # (degree_bits, seed, all thirteen gates?)
+    (5, 1, False), (7, 2, False), (6, 3, True),
+]
+
+
+def circuit_inputs(degree_bits, seed, all_gates):
+    from eth_tx_proof_b200 import circuit as cc
+
+    return cc.hash_chain_circuit(degree_bits, seed=seed, all_gates=all_gates)
+
+
+def circuit_case(degree_bits, seed, all_gates):
+    """A circuit proof (eth_tx_proof_b200/circuit.py; plonk::prover::prove restated): the oracle's proof with the stand-in digest
+    the library derives (hash_no_pad(constants_sigmas cap ++ degree_bits))."""
+    from eth_tx_proof_b200 import circuit as cc
+
+    circ, wires, pis = circuit_inputs(degree_bits, seed, all_gates)
+    cs = oracle.Batch.from_values(np.concatenate([circ.constants, circ.sigmas]), cc.RATE_BITS, cc.CAP_HEIGHT)
+    digest = [int(x) for x in oracle.hash_no_pad(np.concatenate([cs.cap.reshape(-1), np.array([degree_bits], dtype=np.uint64)]))]
+    pr = oracle.circuit_prove(circ, wires, pis, digest)
+    op = pr["openings"]
+    return {"shape": [degree_bits, seed, all_gates], "program_ops": len(circ.program.ops), "num_constants": circ.num_constants,
+            "digest": [f"{x:016x}" for x in digest], "constants_sigmas_cap_sha256": sha(pr["constants_sigmas_cap"]),
+            "wires_cap_sha256": sha(pr["wires_cap"]), "zs_partial_products_cap_sha256": sha(pr["plonk_zs_partial_products_cap"]),
+            "quotient_polys_cap_sha256": sha(pr["quotient_polys_cap"]),
+            "openings_sha256": sha(np.concatenate([np.asarray(op[k]).reshape(-1) for k in
+                                                   ("constants_sigmas", "wires", "zs_partial_products", "quotient_polys", "plonk_zs_next")])),
+            "opening_proof_sha256": sha(pr["opening_proof"]), "opening_proof_words": int(pr["opening_proof"].size),
+            "pow_witness": f"{int(pr['opening_proof'][-1]):016x}"}
+
+
+def generate_circuits():
+    return {"note": "oracle.circuit_prove outputs on seeded synthetic circuits; regression anchors, NOT upstream vectors",
+            "circuits": [circuit_case(*c) for c in CIRCUITS]}
+
+
 def generate():
     return {"note": "oracle outputs on seeded inputs; regression anchors, NOT upstream vectors (see tools/gen_golden.py)",
             "commits": [commit_case(*c) for c in COMMITS], "proofs": [proof_case(*p) for p in PROOFS]}
@@ -82,4 +118,8 @@ if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden", "path_vectors.json")
     with open(out, "w") as f:
         json.dump(generate(), f, indent=1)
+    print("wrote", out)
+    out = os.path.join(ROOT, "tests", "golden", "circuit_vectors.json")
+    with open(out, "w") as f:
+        json.dump(generate_circuits(), f, indent=1)
     print("wrote", out)
