@@ -197,3 +197,54 @@ def test_invalid_witness_is_rejected(ctx):
         proof = prover.prove(w, pi)
         with pytest.raises(plonk_verifier.VerifyError):
             plonk_verifier.verify(proof, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=1)
+
+
+def test_circuit_prove_dev_equals_prove_host_and_misuse_is_refused(ctx):
+    """etp_circuit_prove_dev (witness already on the device, any column stride) == etp_circuit_prove_host; malformed circuits
+    (wrong virtual column count, wrong degree, FRI parameters of another size) are refused at etp_circuit_create."""
+    import ctypes as C
+
+    import torch
+
+    import eth_tx_proof_b200 as etp
+    from eth_tx_proof_b200 import circuit as cc, cprog
+
+    circuit, wires, public_inputs = cc.hash_chain_circuit(6, seed=21)
+    prover = cc.CircuitProver(ctx, circuit)
+    want = prover.prove_words(wires, public_inputs)
+    n, stride = circuit.n, circuit.n + 24
+    padded = np.zeros((cc.NUM_WIRES, stride), dtype=np.uint64)
+    padded[:, :n] = wires
+    d = torch.from_numpy(padded.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    out = np.zeros(prover.proof_words, dtype=np.uint64)
+    ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint64))
+    pi_hash = np.array(cc.hash_no_pad(public_inputs), dtype=np.uint64)
+    ctx.check(ctx.L.etp_circuit_prove_dev(prover.h, C.c_void_p(d.data_ptr()), stride, ptr(pi_hash), ptr(out)))
+    assert (out == want).all()
+    with pytest.raises(etp.EtpError):
+        ctx.check(ctx.L.etp_circuit_prove_dev(prover.h, C.c_void_p(d.data_ptr()), n - 1, ptr(pi_hash), ptr(out)))
+    # an explicit digest changes the transcript (and only that)
+    other = cc.CircuitProver(ctx, circuit, circuit_digest=[1, 2, 3, 4])
+    assert other.digest == [1, 2, 3, 4] and (other.constants_sigmas_cap == prover.constants_sigmas_cap).all()
+    assert not (other.prove_words(wires, public_inputs) == want).all()
+
+    def create(program, consts=circuit.constants, fri=None, qdf=8):
+        u64 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+        prog, cs, sg, ks = u64(program.words), u64(consts), u64(circuit.sigmas), u64(circuit.k_is)
+        fp = fri or etp.FriParams.make(circuit.degree_bits, 3, 4, 16, 28)
+        h = C.c_void_p()
+        return ctx.L.etp_circuit_create(ctx.h, ptr(prog), prog.size, ptr(cs), cs.shape[0], ptr(sg), ptr(ks), 80, 135, circuit.degree_bits, qdf, 2,
+                                        C.byref(fp), None, C.byref(h)), h
+
+    b = cprog.ProgramBuilder(circuit.num_virtual_columns - 1, 4, 9)  # one virtual column short
+    b.constraint(b.lv(0))
+    assert create(b.build())[0] == -1 and "virtual columns" in ctx.L.etp_last_error(ctx.h).decode()
+    b = cprog.ProgramBuilder(circuit.num_virtual_columns, 4, 4)      # constraint degree 4 for a quotient degree factor of 8
+    b.constraint(b.lv(0))
+    assert create(b.build())[0] == -1
+    assert create(circuit.program, fri=etp.FriParams.make(circuit.degree_bits + 1, 3, 4, 16, 28))[0] == -1
+    assert create(circuit.program, fri=etp.FriParams.make(circuit.degree_bits, 1, 4, 16, 28))[0] == -1  # 2^rate_bits < quotient degree factor
+    rc, h = create(circuit.program)
+    assert rc == 0
+    ctx.L.etp_circuit_free(h)
