@@ -192,7 +192,15 @@ fn unwind(acc: Sym) -> Vec<(Op, Sym)> {
 /// emission order.  `acc` = the consumer's accumulator for the single symbolic alpha.
 pub fn finish(acc: Sym, n_trace_cols: usize, n_aux_cols: usize, n_public_inputs: usize, n_challenge_scalars: usize,
               constraint_degree: usize) -> Vec<u64> {
-    let constraints = unwind(acc);
+    finish_constraints(unwind(acc), n_trace_cols, n_aux_cols, n_public_inputs, n_challenge_scalars, constraint_degree)
+}
+
+/// The same for an explicit constraint list in emission order — the plonky2 circuit prover's vanishing polynomial
+/// (`plonk/vanishing_poly.rs`), whose terms are a `Vec` reduced with `reduce_with_powers` rather than folded by a consumer:
+/// pass them REVERSED (term i is weighted by alpha^i there, emission i of N by alpha^(N-1-i) here), the `L_0(x)(Z - 1)` terms
+/// as `(Op::EmitFirstRow, Z - 1)`.
+pub fn finish_constraints(constraints: Vec<(Op, Sym)>, n_trace_cols: usize, n_aux_cols: usize, n_public_inputs: usize,
+                          n_challenge_scalars: usize, constraint_degree: usize) -> Vec<u64> {
     // mark the sub-DAG reachable from the constraints (markers and accumulator nodes are not part of it)
     let n_nodes = ARENA.with(|a| a.borrow().ops.len());
     let mut live = vec![false; n_nodes];
