@@ -368,6 +368,28 @@ def main():
 
     pipe_rates = ctx.pipe_rates() if rank == 0 else None
 
+    # ---- SURVEY.md 8(d), config 2 "as concrete inputs": the other two sizes of the sweep (device-resident, same timing
+    # rule), rank 0 at N=1 only — the headline stays the 2^22 line above
+    sweep = None
+    if world == 1 and log_n == LOG_N:
+        sweep = {}
+        for ln in (20, 21):
+            m = 1 << ln
+            xs = x[:, :m].contiguous()
+            torch.cuda.synchronize()
+            bs = etp.PolynomialBatch.from_values_dev(ctx, xs.data_ptr(), m, cols, ln, RATE_BITS, False, CAP_HEIGHT)
+            for _ in range(3):
+                bs.recommit_values_dev(xs.data_ptr(), m)
+            ts = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                bs.recommit_values_dev(xs.data_ptr(), m)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ms = statistics.median(ts)
+            sweep[f"2^{ln}x{cols}"] = {"ms_per_commit": ms, "best_ms": min(ts), "value": commit_bytes(ln, cols) / (ms / 1e3) / 1e9, "unit": "GB/s",
+                                       "timed": "device-resident values -> coeffs + LDE + digests on the device, cap on the host (wall clock, median of 5)"}
+            del bs, xs
+
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.skip_e2e:
@@ -389,7 +411,18 @@ def main():
         ctx.synchronize()
         dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         assert (cap == cap_ref).all()
+        compat = None
+        if world == 1:  # the "plonky2-compatible" variant — every public field of PolynomialBatch back on the host
+            b2 = etp.PolynomialBatch.from_values(ctx, harr, RATE_BITS, False, CAP_HEIGHT)
+            t0 = time.perf_counter()
+            fields = (b2.polynomials, b2.leaves, b2.digests)  # pageable host arrays, plonky2 layouts
+            dl = time.perf_counter() - t0
+            compat = {"ms": (dt + dl) * 1e3, "download_ms": dl * 1e3, "d2h_bytes": int(sum(f.nbytes for f in fields)),
+                      "what": "from_values from pinned host columns + polynomials, merkle_tree.leaves and merkle_tree.digests copied back "
+                              "(pageable destination): what an UNPATCHED caller that reads those fields eagerly would pay; the fork reads them lazily"}
+            del fields, b2
         e2e = {"value": world * nbytes / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": 8 * cols * n,
+               "plonky2_compatible_full_download": compat,
                "h2d_gbs_aggregate": world * 8 * cols * n / dt / 1e9,  # all ranks pull from the same host: this is what caps e2e at large N
                "d2h_bytes_per_step": 32 << CAP_HEIGHT, "call": "etp_batch_from_values_host (pinned host columns) + etp_batch_cap"}
         del host, harr
@@ -704,7 +737,7 @@ def main():
         "data": "synthetic",
         "config": workload_config(log_n, cols),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "int_pipe": int_pipe,
-        "kernels": kernels, "phases_ms": phase, "cpu_baseline": cpu, "stark": stark, "tx": tx, "tx_with_recursion": tx_rec, "recursion_skeleton": recursion, "circuit_prover": circuit_leg, "column_split": split, "column_split_proof": split_proof,
+        "kernels": kernels, "phases_ms": phase, "config2_sweep": sweep, "cpu_baseline": cpu, "stark": stark, "tx": tx, "tx_with_recursion": tx_rec, "recursion_skeleton": recursion, "circuit_prover": circuit_leg, "column_split": split, "column_split_proof": split_proof,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
