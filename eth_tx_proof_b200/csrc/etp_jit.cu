@@ -3,6 +3,10 @@
 // library as source text by the Makefile (jit_headers.inc), so a registered table compiles with exactly the field
 // arithmetic of the built-in kernels.  Product code: if NVRTC or the device is missing the call fails loudly.
 #include <nvrtc.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include <mutex>
 #include <unordered_map>
@@ -25,6 +29,56 @@ std::mutex g_cubin_mutex;
 std::unordered_map<std::string, std::vector<char>> g_cubin_cache;
 }  // namespace
 
+// On-disk cache of compiled programs (the analogue of the reference's persisted prover state,
+// /root/reference/common/src/prover_state/persistence.rs:32-38: circuits are built once and reloaded at worker start): with
+// ETP_CUBIN_CACHE=<dir> a program compiled by any worker process is loaded from <dir>/etp_<key>.cubin by the next one instead
+// of going through NVRTC again (seconds for a 2400-column table).  Key = FNV-1a of the source, the NVRTC version and the
+// target; file = "ETPCUBN1", payload size, FNV-1a of the payload, payload — a truncated or foreign file is ignored.
+namespace {
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ULL) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ULL; }
+  return h;
+}
+std::string disk_cache_path(const std::string& source) {
+  const char* dir = getenv("ETP_CUBIN_CACHE");
+  if (!dir || !*dir) return "";
+  int major = 0, minor = 0;
+  nvrtcVersion(&major, &minor);
+  uint64_t h = fnv1a(source.data(), source.size());
+  const char target[] = "sm_100a";
+  h = fnv1a(target, sizeof target, h);
+  h = fnv1a(&major, sizeof major, h);
+  h = fnv1a(&minor, sizeof minor, h);
+  char name[64];
+  snprintf(name, sizeof name, "/etp_%016llx.cubin", (unsigned long long)h);
+  return std::string(dir) + name;
+}
+bool disk_cache_load(const std::string& path, std::vector<char>* cubin) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  uint64_t hdr[3] = {0, 0, 0};
+  bool ok = fread(hdr, 8, 3, f) == 3 && hdr[0] == 0x314E425543505445ULL && hdr[1] > 0 && hdr[1] < ((uint64_t)1 << 31);
+  if (ok) {
+    cubin->resize(hdr[1]);
+    ok = fread(cubin->data(), 1, hdr[1], f) == hdr[1] && fgetc(f) == EOF && fnv1a(cubin->data(), cubin->size()) == hdr[2];
+  }
+  fclose(f);
+  if (!ok) cubin->clear();
+  return ok;
+}
+void disk_cache_store(const std::string& path, const std::vector<char>& cubin) {
+  char tmp[32];
+  snprintf(tmp, sizeof tmp, ".tmp%ld", (long)getpid());
+  const std::string part = path + tmp;
+  FILE* f = fopen(part.c_str(), "wb");
+  if (!f) return;  // the cache is best effort: an unwritable directory only costs the next start-up its compile time
+  const uint64_t hdr[3] = {0x314E425543505445ULL, (uint64_t)cubin.size(), fnv1a(cubin.data(), cubin.size())};
+  const bool ok = fwrite(hdr, 8, 3, f) == 3 && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  if (fclose(f) != 0 || !ok || rename(part.c_str(), path.c_str()) != 0) remove(part.c_str());
+}
+}  // namespace
+
 int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubin_out, std::string* log_out) {
   {
     std::lock_guard<std::mutex> lock(g_cubin_mutex);
@@ -34,6 +88,13 @@ int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubi
       if (log_out) log_out->clear();
       return ETP_OK;
     }
+  }
+  const std::string disk = disk_cache_path(source);
+  if (!disk.empty() && disk_cache_load(disk, cubin_out)) {
+    if (log_out) log_out->clear();
+    std::lock_guard<std::mutex> lock(g_cubin_mutex);
+    g_cubin_cache.emplace(source, *cubin_out);
+    return ETP_OK;
   }
   nvrtcProgram prog;
   if (nvrtcCreateProgram(&prog, source.c_str(), "etp_cprog.cu", 3, kHeaderSources, kHeaderNames) != NVRTC_SUCCESS)
@@ -61,6 +122,7 @@ int jit_compile(etp_ctx* ctx, const std::string& source, std::vector<char>* cubi
     std::lock_guard<std::mutex> lock(g_cubin_mutex);
     g_cubin_cache.emplace(source, *cubin_out);
   }
+  if (!disk.empty()) disk_cache_store(disk, *cubin_out);
   return ETP_OK;
 }
 

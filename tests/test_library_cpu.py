@@ -158,3 +158,36 @@ def test_fri_params_standard_configs():
     fr = etp.FriParams.make(12, 3, 4, 16, 28)  # CircuitConfig::standard_recursion_config
     assert fr.n_reductions == 2
     assert etp.FriParams.make(5).n_reductions == 0 and etp.FriParams.make(6).n_reductions == 0 and etp.FriParams.make(8).n_reductions == 1
+
+
+def test_cubin_disk_cache_round_trip(tmp_path):
+    """ETP_CUBIN_CACHE: a compiled program is stored on disk and a FRESH process loads it instead of compiling (the analogue of
+    the reference's persisted prover state); a corrupted file is ignored and rewritten."""
+    import subprocess
+    import time
+
+    code = (
+        "import sys, time, ctypes as C, numpy as np; sys.path.insert(0, %r)\n"
+        "import eth_tx_proof_b200 as etp\n"
+        "from eth_tx_proof_b200 import cprog\n"
+        "L = etp.load_library(); w = np.ascontiguousarray(cprog.shape_program(300, 8).words)\n"
+        "size = C.c_size_t(); err = C.create_string_buffer(256); t0 = time.perf_counter()\n"
+        "rc = L.etp_cprog_compile_check(w.ctypes.data_as(C.POINTER(C.c_uint64)), w.size, C.byref(size), err, 256)\n"
+        "print(rc, size.value, time.perf_counter() - t0)\n") % ROOT
+    env = dict(os.environ, ETP_CUBIN_CACHE=str(tmp_path))
+
+    def run():
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        rc, size, secs = r.stdout.split()
+        assert rc == "0"
+        return int(size), float(secs)
+
+    size1, cold = run()
+    files = list(tmp_path.glob("etp_*.cubin"))
+    assert len(files) == 1 and files[0].stat().st_size == size1 + 24
+    size2, warm = run()
+    assert size2 == size1 and warm < cold / 3, (cold, warm)
+    files[0].write_bytes(files[0].read_bytes()[:-7])  # truncated: must be ignored, recompiled and replaced
+    size3, again = run()
+    assert size3 == size1 and again > warm and files[0].stat().st_size == size1 + 24
