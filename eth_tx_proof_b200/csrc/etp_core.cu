@@ -547,8 +547,15 @@ int batch_create(etp_ctx* ctx, size_t n_cols, int log_n, int rate_bits, int blin
 int launch_leaf_hash(etp_ctx* ctx, const merkle::LeafSrc& src, int c_begin, int c_end, int n_cols_total, uint32_t row0,
                      uint32_t n_rows, uint64_t* digests) {
   if (n_rows == 0) return ETP_OK;
-  merkle::hash_leaves_colmajor<<<(n_rows + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
-      src, c_begin, c_end, n_cols_total, row0, n_rows, digests);
+  static const bool no_coop = getenv("ETP_NO_COOP_LEAVES") != nullptr;  // A/B switch for tools/: thread-per-row kernel at every size
+  if (n_cols_total > 4 && n_rows <= merkle::COOP_LEAF_MAX_ROWS && !no_coop) {
+    const unsigned threads = n_rows * poseidon::COOP_GROUP;
+    merkle::hash_leaves_colmajor_coop<<<(threads + merkle::COOP_THREADS - 1) / merkle::COOP_THREADS, merkle::COOP_THREADS, 0, ctx->stream>>>(
+        src, c_begin, c_end, n_cols_total, row0, n_rows, digests);
+  } else {
+    merkle::hash_leaves_colmajor<<<(n_rows + merkle::HASH_THREADS - 1) / merkle::HASH_THREADS, merkle::HASH_THREADS, 0, ctx->stream>>>(
+        src, c_begin, c_end, n_cols_total, row0, n_rows, digests);
+  }
   ETP_LAUNCH_CHECK(ctx);
   return ETP_OK;
 }

@@ -281,6 +281,21 @@ struct PhaseTimer {
   ~PhaseTimer() { for (auto& m : marks) cudaEventDestroy(m.second); }
 };
 
+// ETP_TRACE=1: host clock between points of a host-heavy function
+struct HostTrace {
+  const char* what;
+  bool on;
+  double last;
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  explicit HostTrace(const char* w) : what(w), on(getenv("ETP_TRACE") != nullptr), last(on ? now() : 0) {}
+  void mark(const char* name) {
+    if (!on) return;
+    const double t = now();
+    fprintf(stderr, "[etp trace]   %s: %-34s host %8.3f ms\n", what, name, t - last);
+    last = t;
+  }
+};
+
 unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // ctx->d_pow_result[1] doubles as the "a batch inverse met a zero" flag of the call in flight
@@ -914,6 +929,7 @@ int combine_on_lde(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
   if (n_batches < 1 || n_batches > (size_t)stark::MAX_FRI_BATCHES) return etp_fail(ctx, ETP_ERR_INVALID, "between 1 and %d FRI batches are supported", stark::MAX_FRI_BATCHES);
   const int log_lde = log_n + rate_bits;
   const size_t lde_n = (size_t)1 << log_lde;
+  HostTrace ht("combine_on_lde");
   // unique columns in order of first appearance, with their alpha power per batch
   std::vector<stark::CombineCol> cols;
   std::map<std::pair<uint32_t, uint32_t>, int> where;
@@ -940,6 +956,7 @@ int combine_on_lde(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
       cols[u].idx[b] = (uint32_t)k;
     }
   }
+  ht.mark("unique columns");
   stark::CombineParams c{};
   c.n_cols = (int)cols.size(); c.n_batches = (int)n_batches; c.log_lde = log_lde;
   for (size_t b = 1; b < n_batches; b++) {  // prefix batches: unique column u carries power u in batch 0 and in batch b, for u < n_b
@@ -968,6 +985,7 @@ int combine_on_lde(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
       later += batches[b].n_polynomials;
     }
   }
+  ht.mark("alpha powers, reduced openings");
   DevBuf<uint64_t> d_apow(ctx), den(ctx), partial(ctx);
   DevBuf<stark::CombineCol> d_cols(ctx);
   ETP_TRY(d_apow.alloc(apow.size()));
@@ -977,6 +995,7 @@ int combine_on_lde(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
   ETP_CUDA(ctx, cudaMemcpyAsync(d_cols.p, cols.data(), cols.size() * sizeof(stark::CombineCol), cudaMemcpyHostToDevice, ctx->stream));
   ETP_TRY(get_pow_table(ctx, gl::root_of_unity(log_lde), log_lde, gl::GENERATOR, &c.coset));
   c.cols = d_cols.p; c.alpha_pows = d_apow.p; c.den = den.p; c.out = values;
+  ht.mark("buffers, uploads, tables");
   ETP_TRY(reset_zero_flag(ctx));
   stark::combine_norms<<<blocks_for(lde_n, 256), 256, 0, ctx->stream>>>(c);
   ETP_LAUNCH_CHECK(ctx);
@@ -993,7 +1012,10 @@ int combine_on_lde(etp_ctx* ctx, const etp_fri_batch* batches, size_t n_batches,
   }
   if (B == 2) launch_combine<2>(ctx, c, lde_n, false); else if (B == 3) launch_combine<3>(ctx, c, lde_n, false); else launch_combine<4>(ctx, c, lde_n, false);
   ETP_LAUNCH_CHECK(ctx);
-  return check_zero_flag(ctx, "an opening point lies on the LDE coset");  // also: apow / cols (host) stay alive until here
+  ht.mark("launches");
+  const int rc_zero = check_zero_flag(ctx, "an opening point lies on the LDE coset");
+  ht.mark("kernels (sync)");
+  return rc_zero;  // also: apow / cols (host) stay alive until here
 }
 
 // PolynomialBatch::prove_openings in evaluation form over the LDE coset, then fri_proof.  `ys`: the claimed value of every

@@ -164,6 +164,40 @@ static __global__ void __launch_bounds__(COOP_THREADS) hash_level_coop(const uin
   if (live && l < 4) parent[4 * (size_t)j + l] = gl::canon(x);
 }
 
+// hash_leaves_colmajor for batches with few rows (same arguments and sponge-resume semantics; n_cols_total > 4): one
+// 16-thread group per row.  The thread-per-row kernel above needs ceil(C / 8) permutation LATENCIES (33 us each) however few
+// rows there are — 0.56 ms for the 135 wire columns of a 2^12-row circuit, 10 ms for a 2400-column keccak table at 2^14 rows —
+// here a permutation takes ~7 us.  Throughput is another matter: the shuffle-bound cooperative form sustains ~0.23 G perm/s
+// against 1.5 G perm/s (measured: 2^15 rows x 135 columns 2.4 ms cooperative, 0.56 ms thread-per-row), so it pays only while
+// rows / 0.23e9 < 33 us, i.e. below ~7.7 k rows — the same crossover as COOP_MAX_PARENTS.
+constexpr uint32_t COOP_LEAF_MAX_ROWS = 4096;
+static __global__ void __launch_bounds__(COOP_THREADS) hash_leaves_colmajor_coop(const __grid_constant__ LeafSrc src, int c_begin, int c_end,
+                                                                          int n_cols_total, uint32_t row0, uint32_t n_rows,
+                                                                          uint64_t* __restrict__ digests) {
+  __shared__ uint64_t rc_s[360];
+  coop_load_rc(rc_s);
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) / poseidon::COOP_GROUP;
+  const int l = threadIdx.x % poseidon::COOP_GROUP;
+  const bool live = i < n_rows;  // whole groups are live or not; dead groups still take part in the warp's shuffles
+  const size_t row = (size_t)row0 + i;
+  uint64_t x = 0;
+  if (live && c_begin > 0 && l >= 8 && l < 12) x = digests[4 * (size_t)i + (l - 8)];  // resume: the parked capacity lanes
+  for (int c = c_begin; c < c_end; c += 8) {
+    const int cc = c + l;
+    if (live && l < 8 && cc < c_end) {
+      const int si = cc / src.cols_per_src;
+      x = __ldg(src.base[si] + (size_t)(cc - si * src.cols_per_src) * src.col_stride + row);
+    }
+    x = poseidon::permute_coop(x, l, rc_s);
+  }
+  if (!live) return;
+  if (c_end < n_cols_total) {
+    if (l >= 8 && l < 12) digests[4 * (size_t)i + (l - 8)] = x;  // park the capacity lanes (any u64 is a valid lane value)
+  } else if (l < 4) {
+    digests[4 * (size_t)i + l] = gl::canon(x);
+  }
+}
+
 // leaves stored row-major (n_leaves x leaf_len), leaf_len > 4: one 16-thread group per leaf, the sponge's
 // permutations in sequence (FRI layers: 32 words = 4 permutations)
 static __global__ void __launch_bounds__(COOP_THREADS) hash_leaves_rowmajor_coop(const uint64_t* __restrict__ rows, int leaf_len,
