@@ -23,8 +23,8 @@ Gates (constraints restated from plonky2/src/gates/*.rs): NoopGate, ConstantGate
 PoseidonGate (123 constraints of degree 7; the partial rounds in upstream's fast form — `partial_first_constant_layer`,
 `mds_partial_layer_init`, `mds_partial_layer_fast` — with the sparse matrices and moved constants derived here from the MDS matrix
 and the round constants, checked against the plain round function), ArithmeticExtensionGate,
-MulExtensionGate, BaseSumGate<2>, ReducingGate, ReducingExtensionGate, RandomAccessGate, ExponentiationGate, PoseidonMdsGate.
-Not built: CosetInterpolationGate, lookup tables / lookup gates, witness generation by generators (witnesses here are computed directly), zero-knowledge blinding
+MulExtensionGate, BaseSumGate<2>, ReducingGate, ReducingExtensionGate, RandomAccessGate, ExponentiationGate, PoseidonMdsGate,
+CosetInterpolationGate.  Not built: lookup tables / lookup gates, witness generation by generators (witnesses here are computed directly), zero-knowledge blinding
 (off in standard_recursion_config).  The circuit digest is a stand-in (hash of the constants/sigmas cap and degree_bits).
 Nothing here can be checked against real plonky2 offline: parity is against the pure-Python evaluation in the tests.
 """
@@ -641,6 +641,109 @@ class PoseidonMdsGate(Gate):
         return [v for x in ins for v in x] + [v for x in outs for v in x]
 
 
+class CosetInterpolationGate(Gate):
+    """gates/coset_interpolation.rs: the value at `evaluation_point` of the polynomial that interpolates 2^subgroup_bits
+    extension values on the coset shift * H — barycentric form without divisions, evaluated in chunks so that the constraint
+    degree stays `degree`: with x' = evaluation_point / shift (a wire, constrained by x' * shift = evaluation_point),
+        (eval, prod) <- (eval * (x' - x_i) + w_i v_i prod, prod * (x' - x_i))      for the points of a chunk,
+    the (eval, prod) pair after every chunk but the last stored in `intermediate` wires, the last eval = evaluation_value.
+    The FRI verifier inside the recursive circuits computes its `compute_evaluation` with this gate."""
+
+    @classmethod
+    def with_max_degree(cls, subgroup_bits: int, max_degree: int):
+        """The smallest degree that needs no more intermediates than max_degree does (a larger selector group fits then)."""
+        n_points = 1 << subgroup_bits
+        n_intermediates = (n_points - 2) // (max_degree - 1)
+        return cls(subgroup_bits, (n_points - 2) // (n_intermediates + 1) + 2)
+
+    def __init__(self, subgroup_bits: int = 4, degree: int = 6):
+        self.subgroup_bits, self.num_points, self.deg = subgroup_bits, 1 << subgroup_bits, degree
+        self.num_intermediates = (self.num_points - 2) // (degree - 1)
+        self.name = f"CosetInterpolationGate {{ subgroup_bits: {subgroup_bits}, degree: {degree} }}"
+        self.degree, self.num_constants, self.num_constraints = degree, 0, 2 + 2 * 2 * self.num_intermediates + 2
+        self.start_values = 1
+        self.start_point = 1 + 2 * self.num_points
+        self.start_value = self.start_point + 2
+        self.start_intermediates = self.start_value + 2
+        self.start_shifted = self.start_intermediates + 4 * self.num_intermediates
+        g = root_of_unity(subgroup_bits)
+        self.domain = [pow(g, i, P) for i in range(self.num_points)]
+        self.weights = []
+        for i, xi in enumerate(self.domain):  # barycentric weights 1 / prod_{j != i} (x_i - x_j)
+            d = 1
+            for j, xj in enumerate(self.domain):
+                if i != j:
+                    d = d * (xi - xj) % P
+            self.weights.append(pow(d, P - 2, P))
+
+    def _chunks(self):
+        out, start = [range(0, self.deg)], 0
+        for i in range(self.num_intermediates):
+            start = 1 + (self.deg - 1) * (i + 1)
+            out.append(range(start, min(start + self.deg - 1, self.num_points)))
+        return out
+
+    def _wire_eval(self, i):
+        return self.start_intermediates + 2 * i
+
+    def _wire_prod(self, i):
+        return self.start_intermediates + 2 * (self.num_intermediates + i)
+
+    def eval(self, b, wire, const, pi):
+        pair = lambda k: (wire(k), wire(k + 1))
+        seven = b.const(7)
+        shift, point, shifted = wire(0), pair(self.start_point), pair(self.start_shifted)
+        cons = [point[0] - shifted[0] * shift, point[1] - shifted[1] * shift]
+        values = [pair(self.start_values + 2 * i) for i in range(self.num_points)]
+        zero, one = b.const(0), b.const(1)
+
+        def partial(idx, ev, pr):
+            for i in idx:
+                term = (shifted[0] - b.const(self.domain[i]), shifted[1])
+                wv = (values[i][0] * b.const(self.weights[i]), values[i][1] * b.const(self.weights[i]))
+                ev = _e_add(_e_mul(ev, term, seven), _e_mul(wv, pr, seven))
+                pr = _e_mul(pr, term, seven)
+            return ev, pr
+
+        chunks = self._chunks()
+        ev, pr = partial(chunks[0], (zero, zero), (one, zero))
+        for i in range(self.num_intermediates):
+            iev, ipr = pair(self._wire_eval(i)), pair(self._wire_prod(i))
+            cons += [iev[0] - ev[0], iev[1] - ev[1], ipr[0] - pr[0], ipr[1] - pr[1]]
+            ev, pr = partial(chunks[i + 1], iev, ipr)
+        out_v = pair(self.start_value)
+        cons += [out_v[0] - ev[0], out_v[1] - ev[1]]
+        assert len(cons) == self.num_constraints
+        return cons
+
+    def witness(self, rnd):
+        w = [0] * NUM_WIRES
+        shift = rnd() or 1
+        values = [(rnd(), rnd()) for _ in range(self.num_points)]
+        point = (rnd(), rnd())
+        s_inv = pow(shift, P - 2, P)
+        shifted = (point[0] * s_inv % P, point[1] * s_inv % P)
+        w[0] = shift
+        for i, v in enumerate(values):
+            w[self.start_values + 2 * i], w[self.start_values + 2 * i + 1] = v
+        w[self.start_point], w[self.start_point + 1] = point
+        w[self.start_shifted], w[self.start_shifted + 1] = shifted
+        ev, pr = (0, 0), (1, 0)
+        chunks = self._chunks()
+        for ci, idx in enumerate(chunks):
+            for i in idx:
+                term = ((shifted[0] - self.domain[i]) % P, shifted[1])
+                wv = (values[i][0] * self.weights[i] % P, values[i][1] * self.weights[i] % P)
+                ev = _e_mod(_e_add(_e_mul(ev, term), _e_mul(wv, pr)))
+                pr = _e_mod(_e_mul(pr, term))
+            if ci < self.num_intermediates:
+                w[self._wire_eval(ci)], w[self._wire_eval(ci) + 1] = ev
+                w[self._wire_prod(ci)], w[self._wire_prod(ci) + 1] = pr
+        w[self.start_value], w[self.start_value + 1] = ev
+        self._last = (shift, values, point, ev)
+        return w
+
+
 # ---- selectors (gates/selectors.rs) -----------------------------------------------------------------------------------------------
 def selector_groups(gates: Sequence[Gate], max_degree: int) -> List[range]:
     """Greedy grouping of the (degree-sorted) gates: a group of `size` gates costs a filter of degree size - 1 (+ 1 for the
@@ -851,7 +954,8 @@ def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float
     row wired to the PublicInputGate), a Merkle-path-like chain of swapped PoseidonGates, chains of ArithmeticGate operations,
     constants through a ConstantGate — all linked by copy constraints — padded with NoopGates to 2^degree_bits rows.
     all_gates: also `extra_rows` rows of each of ArithmeticExtension, MulExtension, BaseSum, Exponentiation (its exponent bits wired
-    to the base-sum limbs), Reducing, ReducingExtension, RandomAccess and PoseidonMds gates (four selector groups instead of two).
+    to the base-sum limbs), Reducing, ReducingExtension, RandomAccess, PoseidonMds and CosetInterpolation gates (selector groups by
+upstream's greedy rule).
     -> (Circuit, wires (135, n), public_inputs)"""
     rng = np.random.default_rng(seed)
     n = 1 << degree_bits
@@ -870,7 +974,7 @@ def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float
         cb.connect((r_h, 12 + i), (r_pi, i))
         cb.connect((r_h, 8 + i), (r_const, 0))
     cb.connect((r_h, PoseidonGate.WIRE_SWAP), (r_const, 0))
-    budget = n - len(cb.rows) - (8 * extra_rows if all_gates else 0)
+    budget = n - len(cb.rows) - (9 * extra_rows if all_gates else 0)
     n_pos = max(int(budget * poseidon_fraction), 1)
     n_ar = max(int(budget * arithmetic_fraction), 1)
     prev_row, digest = r_h, w[12:16]
@@ -928,6 +1032,8 @@ def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float
             e0, e1 = rnd(), rnd()
             cb.add_gate(g, constants=[e0, e1], wires=g.witness(rnd, rng, [e0, e1]))
             cb.add_gate(PoseidonMdsGate(), wires=PoseidonMdsGate().witness(rnd))
+            g = CosetInterpolationGate.with_max_degree(4, QUOTIENT_DEGREE_FACTOR)  # degree 6, two intermediate (eval, prod) pairs
+            cb.add_gate(g, wires=g.witness(rnd))
     return (*cb.build(degree_bits), public_inputs)
 
 

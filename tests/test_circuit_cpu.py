@@ -138,21 +138,22 @@ def test_oracle_circuit_proof_is_accepted_and_tampering_is_not(degree_bits):
 
 
 def test_full_gate_set_constraints_hold_and_every_gate_bites():
-    """All thirteen gates (four selector groups): the vanishing program vanishes on the witness; corrupting one wire of a row of
+    """All fourteen gates (five selector groups): the vanishing program vanishes on the witness; corrupting one wire of a row of
     each gate type makes that gate's filtered constraints non-zero on that row."""
     import oracle
     from eth_tx_proof_b200 import circuit as cc
 
     circuit, wires, public_inputs = cc.hash_chain_circuit(6, seed=5, all_gates=True)
-    assert [list(g) for g in circuit.groups] == [[0, 1, 2, 3, 4, 5], [6, 7, 8, 9], [10, 11], [12]]
-    assert circuit.num_constants == 6 and len(circuit.gates) == 13
+    assert [list(g) for g in circuit.groups] == [[0, 1, 2, 3, 4, 5], [6, 7, 8, 9], [10, 11], [12], [13]]
+    assert circuit.num_constants == 7 and len(circuit.gates) == 14
     pi_hash = cc.hash_no_pad(public_inputs)
     betas, gammas = [3, 5], [7, 11]
     zs_pp = oracle.plonk_partial_products_and_zs(wires[:80], circuit.sigmas, circuit.k_is, 8, betas, gammas)
     assert _violations(circuit, wires, zs_pp, pi_hash, betas, gammas) == []
     # advice (non-routed or unconnected) wires: changing them cannot be absorbed by the permutation argument
     victims = {"ArithmeticExtensionGate": 15, "MulExtensionGate": 10, "BaseSumGate": 63, "ReducingExtensionGate": 80, "ReducingGate": 60,
-               "ExponentiationGate": 100, "RandomAccessGate": 75, "PoseidonMdsGate": 30, "ConstantGate": 1, "ArithmeticGate": 7}
+               "ExponentiationGate": 100, "RandomAccessGate": 75, "PoseidonMdsGate": 30, "ConstantGate": 1, "ArithmeticGate": 7,
+               "CosetInterpolationGate": 40}
     for gi, gate in enumerate(circuit.gates):
         key = gate.name.split(" ")[0]
         if key not in victims:
@@ -205,3 +206,26 @@ def test_fast_partial_rounds_equal_the_plain_round_function():
         lv = [int(x) % P for x in rng.integers(0, 2**63, cc.NUM_WIRES)]
         a, b_ = (p.evaluate(lv, lv) for p in progs)
         assert [v % P for _, v in a] == [v % P for _, v in b_]
+
+
+def test_coset_interpolation_gate_computes_the_lagrange_interpolant():
+    """The gate's evaluation_value == the value at evaluation_point of the degree-15 polynomial through the 16 extension
+    values on shift * H (independent O(n^2) Lagrange formula), for the degree with_max_degree(4, 8) picks (6)."""
+    from eth_tx_proof_b200 import circuit as cc
+
+    g = cc.CosetInterpolationGate.with_max_degree(4, 8)
+    assert (g.deg, g.num_intermediates, g.num_constraints) == (6, 2, 12)
+    rng = np.random.default_rng(3)
+    g.witness(lambda: int(rng.integers(0, 2**63)) % P)
+    shift, values, point, got = g._last
+    emul = lambda a, b: ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+    xs = [shift * d % P for d in g.domain]
+    total = (0, 0)
+    for i, xi in enumerate(xs):
+        num, den = (1, 0), 1
+        for j, xj in enumerate(xs):
+            if i != j:
+                num, den = emul(num, ((point[0] - xj) % P, point[1])), den * (xi - xj) % P
+        t = emul(values[i], emul(num, (pow(den, P - 2, P), 0)))
+        total = ((total[0] + t[0]) % P, (total[1] + t[1]) % P)
+    assert total == got

@@ -161,8 +161,8 @@ def test_circuit_proof_equals_the_oracles_bit_for_bit(ctx, degree_bits):
 
 @pytest.mark.parametrize("degree_bits", [6, 10])
 def test_full_gate_set_proof_equals_oracle_and_verifies(ctx, degree_bits):
-    """Thirteen gates in four selector groups (extension arithmetic, base sum, reducing, random access, exponentiation, MDS,
-    ...): same parity and acceptance as the Poseidon / arithmetic circuit."""
+    """Fourteen gates in five selector groups (extension arithmetic, base sum, reducing, random access, exponentiation, MDS,
+    coset interpolation, ...): same parity and acceptance as the Poseidon / arithmetic circuit."""
     import oracle
     import plonk_verifier
     from eth_tx_proof_b200 import circuit as cc

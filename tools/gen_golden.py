@@ -73,7 +73,7 @@ def proof_case(table, log_n, seed):
             "pow_witness": f"{int(proof[-1 - len(pi)]):016x}" if len(pi) else f"{int(proof[-1]):016x}"}
 
 
-CIRCUITS = [  # (degree_bits, seed, all thirteen gates?)
+CIRCUITS = [  # (degree_bits, seed, all fourteen gates?)
     (5, 1, False), (7, 2, False), (6, 3, True),
 ]
 
