@@ -1037,6 +1037,104 @@ upstream's greedy rule).
     return (*cb.build(degree_bits), public_inputs)
 
 
+def merkle_proof_circuit(leaf: Sequence[int], leaf_index: int, siblings: Sequence[Sequence[int]], cap: Sequence[Sequence[int]],
+                         min_degree_bits: int = 0):
+    """A fragment of the recursive verifier as a circuit: `verify_merkle_proof_to_cap` (plonky2 hash/merkle_proofs.rs, the gadget
+    every FRI query of a recursive proof runs) for ONE opening of a committed batch — real data in, e.g. a row, its path and the
+    cap of a PolynomialBatch committed on the device.
+      * the cap (2^h digests) is the public input: hashed in-circuit by a PoseidonGate sponge wired to the PublicInputGate;
+      * leaf_index is split into bits by a BaseSumGate; the leaf is hashed by a PoseidonGate sponge (hash_or_noop: no hash
+        for <= 4 elements); every path level is one PoseidonGate whose `swap` wire is the index bit of that level
+        (state = H(swap ? (sibling, state) : (state, sibling)));
+      * the cap entry is selected by a RandomAccessGate (one copy per digest element) indexed by the remaining high bits
+        (a second BaseSumGate ties them to the first) and must equal the final state — all by copy constraints.
+    -> (Circuit, wires, public_inputs).  Building fails (AssertionError in connect) when the path does not lead to the cap:
+    no witness exists."""
+    h = (len(cap) - 1).bit_length()
+    assert len(cap) == 1 << h == 16, "RandomAccessGate(bits = 4): cap_height 4"
+    levels = len(siblings)
+    cb = CircuitBuilder()
+    pos, bs, ra = PoseidonGate(), BaseSumGate(63), RandomAccessGate(4, 4, 2)
+    r_const = cb.add_gate(ConstantGate(2), constants=[0, 1], wires=[0, 1])
+    zero = (r_const, 0)
+
+    def sponge(elements, sources=None):
+        """hash_n_to_hash_no_pad over `elements` with PoseidonGate rows (overwrite mode: lanes a chunk does not overwrite keep
+        the previous output).  sources[i]: an existing wire to copy element i from, or None.  -> (row, first output wire) of the digest
+        and, per element, the wire it entered through."""
+        prev, entered = None, []
+        for off in range(0, len(elements), 8):
+            chunk = [int(x) % P for x in elements[off:off + 8]]
+            state = list(chunk) + ([0] * (8 - len(chunk)) if prev is None else cb.wires[prev][12 + len(chunk):20]) + \
+                ([0, 0, 0, 0] if prev is None else cb.wires[prev][20:24])
+            r = cb.add_gate(pos, wires=poseidon_gate_wires(state, 0))
+            cb.connect((r, PoseidonGate.WIRE_SWAP), zero)
+            for k in range(len(chunk), 12):
+                cb.connect((r, k), zero if prev is None else (prev, 12 + k))
+            for k in range(len(chunk)):
+                entered.append((r, k))
+                if sources is not None and sources[off + k] is not None:
+                    cb.connect((r, k), sources[off + k])
+            prev = r
+        return prev, entered
+
+    # ---- public inputs = the cap, hashed in-circuit
+    public_inputs = [int(x) % P for d in cap for x in d]
+    cb.public_inputs = list(public_inputs)
+    r_pi = cb.add_gate(PublicInputGate(), wires=hash_no_pad(public_inputs))
+    r_h, cap_wires = sponge(public_inputs)
+    for i in range(4):
+        cb.connect((r_h, 12 + i), (r_pi, i))
+    # ---- index bits
+    r_bits = cb.add_gate(bs, wires=bs.witness(leaf_index))
+    cap_index = leaf_index >> levels
+    assert cap_index < (1 << h)
+    r_hi = cb.add_gate(bs, wires=bs.witness(cap_index))
+    for j in range(63):
+        if j < h:
+            cb.connect((r_hi, 1 + j), (r_bits, 1 + levels + j))
+        else:
+            cb.connect((r_hi, 1 + j), zero)
+    for j in range(levels + h, 63):
+        cb.connect((r_bits, 1 + j), zero)
+    # ---- leaf digest: hash_or_noop
+    leaf = [int(x) % P for x in leaf]
+    if len(leaf) <= 4:  # no hash: the digest is the zero-padded leaf, held by a ConstantGate-free row of advice... use a noop row's wires
+        r_leaf = cb.add_gate(NoopGate(), wires=leaf + [0] * (4 - len(leaf)))
+        for k in range(len(leaf), 4):
+            cb.connect((r_leaf, k), zero)
+        cur = (r_leaf, 0)
+    else:
+        r_leaf, _ = sponge(leaf)
+        cur = (r_leaf, 12)
+    # ---- the path
+    digest = cb.wires[cur[0]][cur[1]:cur[1] + 4]
+    for lvl, sib in enumerate(siblings):
+        bit = (leaf_index >> lvl) & 1
+        r = cb.add_gate(pos, wires=poseidon_gate_wires(list(digest) + [int(x) % P for x in sib] + [0, 0, 0, 0], bit))
+        for k in range(4):
+            cb.connect((r, k), (cur[0], cur[1] + k))
+            cb.connect((r, 8 + k), zero)
+        cb.connect((r, PoseidonGate.WIRE_SWAP), (r_bits, 1 + lvl))
+        cur, digest = (r, 12), cb.wires[r][12:16]
+    # ---- the cap entry: one RandomAccess copy per digest element
+    w = [0] * NUM_WIRES
+    for c in range(4):
+        base = (2 + ra.vec) * c
+        w[base], w[base + 1] = cap_index, int(cap[cap_index][c]) % P
+        w[base + 2:base + 2 + ra.vec] = [int(cap[e][c]) % P for e in range(ra.vec)]
+        for j in range(ra.bits):
+            w[ra.num_routed + c * ra.bits + j] = (cap_index >> j) & 1
+    r_ra = cb.add_gate(ra, constants=[0, 0], wires=w)
+    for c in range(4):
+        base = (2 + ra.vec) * c
+        cb.connect((r_ra, base), (r_hi, 0))
+        cb.connect((r_ra, base + 1), (cur[0], cur[1] + c))  # fails unless the path leads to the cap
+        for e in range(ra.vec):
+            cb.connect((r_ra, base + 2 + e), cap_wires[4 * e + c])
+    return (*cb.build(min_degree_bits), public_inputs)
+
+
 # ---- the prover -----------------------------------------------------------------------------------------------------------------
 class CircuitProver:
     """etp_circuit (include/etp_b200.h): per-circuit state built once (ProverOnlyCircuitData / CommonCircuitData — the

@@ -229,3 +229,29 @@ def test_coset_interpolation_gate_computes_the_lagrange_interpolant():
         t = emul(values[i], emul(num, (pow(den, P - 2, P), 0)))
         total = ((total[0] + t[0]) % P, (total[1] + t[1]) % P)
     assert total == got
+
+
+@pytest.mark.parametrize("cols,log_n,idx", [(12, 6, 77), (3, 5, 5), (20, 7, 255)])
+def test_merkle_proof_circuit_on_a_real_opening(cols, log_n, idx):
+    """verify_merkle_proof_to_cap as a circuit (the gadget every FRI query of a recursive proof runs), fed with a real opening
+    of a committed batch: constraints hold, the oracle's proof verifies, a tampered path has no witness."""
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, synthetic as syn
+
+    b = oracle.Batch.from_values(syn.random_columns(cols, log_n, seed=cols), 1, 4)
+    sib = oracle.merkle_prove(b.digests, 2 << log_n, 4, idx)
+    leaf = b.leaves[idx]
+    assert oracle.merkle_verify(leaf, idx, sib, b.cap)
+    circuit, wires, public_inputs = cc.merkle_proof_circuit(leaf, idx, sib, b.cap)
+    assert public_inputs == [int(x) for x in b.cap.reshape(-1)]
+    zs_pp = oracle.plonk_partial_products_and_zs(wires[:80], circuit.sigmas, circuit.k_is, 8, [3, 5], [7, 11])
+    assert _violations(circuit, wires, zs_pp, cc.hash_no_pad(public_inputs), [3, 5], [7, 11]) == []
+    proof = oracle.circuit_prove(circuit, wires, public_inputs, [1, 2, 3, 4])
+    plonk_verifier.verify(proof, circuit, proof["constants_sigmas_cap"], [1, 2, 3, 4], max_queries=2)
+    bad = sib.copy()
+    bad[1, 2] ^= np.uint64(1)
+    with pytest.raises(AssertionError, match="copy constraint"):
+        cc.merkle_proof_circuit(leaf, idx, bad, b.cap)
+    with pytest.raises(AssertionError, match="copy constraint"):
+        cc.merkle_proof_circuit(leaf, idx ^ 1, sib, b.cap)  # the sibling's index: the swaps go the wrong way

@@ -248,3 +248,27 @@ def test_circuit_prove_dev_equals_prove_host_and_misuse_is_refused(ctx):
     rc, h = create(circuit.program)
     assert rc == 0
     ctx.L.etp_circuit_free(h)
+
+
+def test_merkle_proof_circuit_over_a_device_commitment(ctx):
+    """The recursive verifier's Merkle gadget as a circuit, fed with an opening of a batch committed ON THE DEVICE (row, path,
+    cap), proved on the device and verified; a prover that swaps in a wrong sibling afterwards is rejected."""
+    import eth_tx_proof_b200 as etp
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, synthetic as syn
+
+    b = etp.PolynomialBatch.from_values(ctx, syn.random_columns(21, 10, seed=5), 1, False, 4)
+    idx = 1234
+    leaf, sib, cap = b.leaves_at([idx])[0], b.prove(idx), b.cap
+    circuit, wires, public_inputs = cc.merkle_proof_circuit(leaf, idx, sib, cap)
+    prover = cc.CircuitProver(ctx, circuit)
+    proof = prover.prove(wires, public_inputs)
+    plonk_verifier.verify(proof, circuit, prover.constants_sigmas_cap, prover.digest, max_queries=3)
+    want = oracle.circuit_prove(circuit, wires, public_inputs, prover.digest)
+    assert (proof["opening_proof"] == want["opening_proof"]).all()
+    bad = wires.copy()
+    row = int(np.nonzero(circuit.gate_of_row == len(circuit.gates) - 1)[0][-1])  # the last PoseidonGate row: a path level
+    bad[5, row] = (int(bad[5, row]) + 1) % P  # a sibling element, the other wires of the row left as they were
+    with pytest.raises(plonk_verifier.VerifyError):
+        plonk_verifier.verify(prover.prove(bad, public_inputs), circuit, prover.constants_sigmas_cap, prover.digest, max_queries=1)
