@@ -1135,6 +1135,38 @@ def merkle_proof_circuit(leaf: Sequence[int], leaf_index: int, siblings: Sequenc
     return (*cb.build(min_degree_bits), public_inputs)
 
 
+def fri_fold_check_circuit(values: Sequence[Sequence[int]], coset_start: int, beta: Sequence[int], expected: Sequence[int],
+                           min_degree_bits: int = 0):
+    """Another fragment of the recursive verifier: one `compute_evaluation` of the FRI verifier (plonky2 fri/verifier.rs — the
+    arity-16 fold consistency check of a query step) as a circuit: a CosetInterpolationGate interpolates the 16 extension
+    values of a coset coset_start * <w16> (natural order) and evaluates at beta; the result must equal `expected` (the
+    next layer's opened value).  Public inputs: beta and expected, hashed in-circuit and wired to the PublicInputGate.
+    -> (Circuit, wires, public_inputs); AssertionError when the fold is inconsistent (no witness)."""
+    g = CosetInterpolationGate.with_max_degree(4, QUOTIENT_DEGREE_FACTOR)
+    assert len(values) == g.num_points
+    cb = CircuitBuilder()
+    r_const = cb.add_gate(ConstantGate(2), constants=[0, 1], wires=[0, 1])
+    zero = (r_const, 0)
+    public_inputs = [int(beta[0]) % P, int(beta[1]) % P, int(expected[0]) % P, int(expected[1]) % P]
+    cb.public_inputs = list(public_inputs)
+    r_pi = cb.add_gate(PublicInputGate(), wires=hash_no_pad(public_inputs))
+    r_h = cb.add_gate(PoseidonGate(), wires=poseidon_gate_wires(public_inputs + [0] * 8, 0))
+    cb.connect((r_h, PoseidonGate.WIRE_SWAP), zero)
+    for k in range(4, 12):
+        cb.connect((r_h, k), zero)
+    for i in range(4):
+        cb.connect((r_h, 12 + i), (r_pi, i))
+    vals = [(int(v[0]) % P, int(v[1]) % P) for v in values]
+    seq = iter([int(coset_start) % P] + [x for v in vals for x in v] + public_inputs[:2])
+    w = g.witness(lambda: next(seq))  # witness() draws shift, the 16 values, then the point, in this order
+    r_g = cb.add_gate(g, wires=w)
+    cb.connect((r_g, g.start_point), (r_h, 0))
+    cb.connect((r_g, g.start_point + 1), (r_h, 1))
+    cb.connect((r_g, g.start_value), (r_h, 2))       # fails unless interpolate(values)(beta) == expected
+    cb.connect((r_g, g.start_value + 1), (r_h, 3))
+    return (*cb.build(min_degree_bits), public_inputs)
+
+
 # ---- the prover -----------------------------------------------------------------------------------------------------------------
 class CircuitProver:
     """etp_circuit (include/etp_b200.h): per-circuit state built once (ProverOnlyCircuitData / CommonCircuitData — the

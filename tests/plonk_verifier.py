@@ -62,9 +62,10 @@ def parse_fri_proof(words, oracle_cols, degree_bits, rate_bits, cap_height, n_la
     return out
 
 
-def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_bits, num_queries, fast=True, max_queries=None):
+def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_bits, num_queries, fast=True, max_queries=None, folds=None):
     """verify_fri_proof.  batches: [(point (ext), [(oracle, poly)], [opened values (ext)])]; `ch`: the challenger after it
-    observed the openings."""
+    observed the openings.  folds: a list that receives every compute_evaluation instance
+    (values in natural order, coset start, beta, interpolated value) — inputs for the in-circuit fold check."""
     hash_or_noop, two_to_one, _ = V._hashers(fast)
     fri_alpha = ch.get_ext()
     betas = []
@@ -111,6 +112,8 @@ def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_b
             coset_start = subgroup_x * pow(ga, arity - rev_within, P) % P
             pts = [(R.e_from(coset_start * pow(ga, k, P) % P), ev[k]) for k in range(arity)]
             old_eval = V._interpolate(pts, betas[i])
+            if folds is not None:
+                folds.append((ev, coset_start, betas[i], old_eval))
             flat = [c for e in evals for c in e]
             V._merkle_verify(flat, coset_index, sib, fri["fri_caps"][i], hash_or_noop, two_to_one)
             subgroup_x = pow(subgroup_x, arity, P)
@@ -122,7 +125,7 @@ def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_b
             raise VerifyError("Final polynomial evaluation is invalid.")
 
 
-def verify(proof, circuit, constants_sigmas_cap, circuit_digest, fast=True, max_queries=None):
+def verify(proof, circuit, constants_sigmas_cap, circuit_digest, fast=True, max_queries=None, folds=None):
     """Raises VerifyError unless `proof` (CircuitProver.prove) is a valid proof for `circuit`."""
     from eth_tx_proof_b200 import circuit as cc
 
@@ -178,5 +181,5 @@ def verify(proof, circuit, constants_sigmas_cap, circuit_digest, fast=True, max_
         n_layers, bits = n_layers + 1, bits - 4
     fri = parse_fri_proof(proof["opening_proof"], shapes, db, cc.RATE_BITS, cc.CAP_HEIGHT, n_layers, 4, cc.NUM_QUERIES, 1 << bits)
     all_caps = [caps(constants_sigmas_cap), caps(proof["wires_cap"]), caps(proof["plonk_zs_partial_products_cap"]), caps(proof["quotient_polys_cap"])]
-    verify_fri(fri, all_caps, batches, ch, db, cc.RATE_BITS, 4, cc.POW_BITS, cc.NUM_QUERIES, fast, max_queries)
+    verify_fri(fri, all_caps, batches, ch, db, cc.RATE_BITS, 4, cc.POW_BITS, cc.NUM_QUERIES, fast, max_queries, folds)
     return True

@@ -255,3 +255,25 @@ def test_merkle_proof_circuit_on_a_real_opening(cols, log_n, idx):
         cc.merkle_proof_circuit(leaf, idx, bad, b.cap)
     with pytest.raises(AssertionError, match="copy constraint"):
         cc.merkle_proof_circuit(leaf, idx ^ 1, sib, b.cap)  # the sibling's index: the swaps go the wrong way
+
+
+def test_fri_fold_check_circuit_on_real_fri_data():
+    """compute_evaluation of the FRI verifier as a circuit (CosetInterpolationGate), fed with fold instances captured while
+    verifying a real circuit proof (16 opened values of a query step, the coset start, beta, the next layer's value)."""
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(7, seed=4)  # 2^7 rows: one FRI reduction layer
+    proof = oracle.circuit_prove(inner, wires, public_inputs, [9, 9, 9, 9])
+    folds = []
+    plonk_verifier.verify(proof, inner, proof["constants_sigmas_cap"], [9, 9, 9, 9], max_queries=2, folds=folds)
+    assert len(folds) == 2
+    for values, coset_start, beta, expected in folds:
+        circuit, w, pis = cc.fri_fold_check_circuit(values, coset_start, beta, expected)
+        zs_pp = oracle.plonk_partial_products_and_zs(w[:80], circuit.sigmas, circuit.k_is, 8, [3, 5], [7, 11])
+        assert _violations(circuit, w, zs_pp, cc.hash_no_pad(pis), [3, 5], [7, 11]) == []
+        outer = oracle.circuit_prove(circuit, w, pis, [1, 1, 1, 1])
+        plonk_verifier.verify(outer, circuit, outer["constants_sigmas_cap"], [1, 1, 1, 1], max_queries=1)
+        with pytest.raises(AssertionError, match="copy constraint"):
+            cc.fri_fold_check_circuit(values, coset_start, beta, (expected[0] ^ 1, expected[1]))

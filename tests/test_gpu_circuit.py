@@ -272,3 +272,20 @@ def test_merkle_proof_circuit_over_a_device_commitment(ctx):
     bad[5, row] = (int(bad[5, row]) + 1) % P  # a sibling element, the other wires of the row left as they were
     with pytest.raises(plonk_verifier.VerifyError):
         plonk_verifier.verify(prover.prove(bad, public_inputs), circuit, prover.constants_sigmas_cap, prover.digest, max_queries=1)
+
+
+def test_fri_fold_check_circuit_over_a_device_proof(ctx):
+    """A proof ABOUT a proof: fold instances of the FRI verification of a device-made circuit proof (compute_evaluation: 16
+    opened values, coset start, beta, next value) go through the CosetInterpolationGate circuit, proved on the device."""
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(7, seed=6)
+    p_in = cc.CircuitProver(ctx, inner)
+    proof = p_in.prove(wires, public_inputs)
+    folds = []
+    plonk_verifier.verify(proof, inner, p_in.constants_sigmas_cap, p_in.digest, max_queries=1, folds=folds)
+    values, coset_start, beta, expected = folds[0]
+    circuit, w, pis = cc.fri_fold_check_circuit(values, coset_start, beta, expected)
+    p_out = cc.CircuitProver(ctx, circuit)
+    plonk_verifier.verify(p_out.prove(w, pis), circuit, p_out.constants_sigmas_cap, p_out.digest, max_queries=2)
