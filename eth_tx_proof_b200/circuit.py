@@ -1037,102 +1037,118 @@ upstream's greedy rule).
     return (*cb.build(degree_bits), public_inputs)
 
 
-def merkle_proof_circuit(leaf: Sequence[int], leaf_index: int, siblings: Sequence[Sequence[int]], cap: Sequence[Sequence[int]],
-                         min_degree_bits: int = 0):
-    """A fragment of the recursive verifier as a circuit: `verify_merkle_proof_to_cap` (plonky2 hash/merkle_proofs.rs, the gadget
-    every FRI query of a recursive proof runs) for ONE opening of a committed batch — real data in, e.g. a row, its path and the
-    cap of a PolynomialBatch committed on the device.
-      * the cap (2^h digests) is the public input: hashed in-circuit by a PoseidonGate sponge wired to the PublicInputGate;
-      * leaf_index is split into bits by a BaseSumGate; the leaf is hashed by a PoseidonGate sponge (hash_or_noop: no hash
-        for <= 4 elements); every path level is one PoseidonGate whose `swap` wire is the index bit of that level
-        (state = H(swap ? (sibling, state) : (state, sibling)));
-      * the cap entry is selected by a RandomAccessGate (one copy per digest element) indexed by the remaining high bits
-        (a second BaseSumGate ties them to the first) and must equal the final state — all by copy constraints.
-    -> (Circuit, wires, public_inputs).  Building fails (AssertionError in connect) when the path does not lead to the cap:
-    no witness exists."""
-    h = (len(cap) - 1).bit_length()
-    assert len(cap) == 1 << h == 16, "RandomAccessGate(bits = 4): cap_height 4"
-    levels = len(siblings)
-    cb = CircuitBuilder()
-    pos, bs, ra = PoseidonGate(), BaseSumGate(63), RandomAccessGate(4, 4, 2)
-    r_const = cb.add_gate(ConstantGate(2), constants=[0, 1], wires=[0, 1])
-    zero = (r_const, 0)
+class _MerkleGadget:
+    """verify_merkle_proof_to_cap (plonky2 hash/merkle_proofs.rs) on a CircuitBuilder: shared gates, the constant-zero wire,
+    Poseidon sponges with overwrite-mode carry, and one opening = index bits (BaseSumGate) + leaf digest (hash_or_noop) + one
+    swapped PoseidonGate per level + RandomAccessGate selection of the cap entry, all tied by copy constraints."""
 
-    def sponge(elements, sources=None):
+    def __init__(self, cb: "CircuitBuilder"):
+        self.cb = cb
+        self.pos, self.bs, self.ra = PoseidonGate(), BaseSumGate(63), RandomAccessGate(4, 4, 2)
+        self.r_const = cb.add_gate(ConstantGate(2), constants=[0, 1], wires=[0, 1])
+        self.zero = (self.r_const, 0)
+
+    def sponge(self, elements):
         """hash_n_to_hash_no_pad over `elements` with PoseidonGate rows (overwrite mode: lanes a chunk does not overwrite keep
-        the previous output).  sources[i]: an existing wire to copy element i from, or None.  -> (row, first output wire) of the digest
-        and, per element, the wire it entered through."""
-        prev, entered = None, []
+        the previous output).  -> (row of the last permutation, the wire each element entered through)."""
+        cb, prev, entered = self.cb, None, []
         for off in range(0, len(elements), 8):
             chunk = [int(x) % P for x in elements[off:off + 8]]
             state = list(chunk) + ([0] * (8 - len(chunk)) if prev is None else cb.wires[prev][12 + len(chunk):20]) + \
                 ([0, 0, 0, 0] if prev is None else cb.wires[prev][20:24])
-            r = cb.add_gate(pos, wires=poseidon_gate_wires(state, 0))
-            cb.connect((r, PoseidonGate.WIRE_SWAP), zero)
+            r = cb.add_gate(self.pos, wires=poseidon_gate_wires(state, 0))
+            cb.connect((r, PoseidonGate.WIRE_SWAP), self.zero)
             for k in range(len(chunk), 12):
-                cb.connect((r, k), zero if prev is None else (prev, 12 + k))
-            for k in range(len(chunk)):
-                entered.append((r, k))
-                if sources is not None and sources[off + k] is not None:
-                    cb.connect((r, k), sources[off + k])
+                cb.connect((r, k), self.zero if prev is None else (prev, 12 + k))
+            entered += [(r, k) for k in range(len(chunk))]
             prev = r
         return prev, entered
 
-    # ---- public inputs = the cap, hashed in-circuit
-    public_inputs = [int(x) % P for d in cap for x in d]
-    cb.public_inputs = list(public_inputs)
-    r_pi = cb.add_gate(PublicInputGate(), wires=hash_no_pad(public_inputs))
-    r_h, cap_wires = sponge(public_inputs)
-    for i in range(4):
-        cb.connect((r_h, 12 + i), (r_pi, i))
-    # ---- index bits
-    r_bits = cb.add_gate(bs, wires=bs.witness(leaf_index))
-    cap_index = leaf_index >> levels
-    assert cap_index < (1 << h)
-    r_hi = cb.add_gate(bs, wires=bs.witness(cap_index))
-    for j in range(63):
-        if j < h:
-            cb.connect((r_hi, 1 + j), (r_bits, 1 + levels + j))
+    def public_inputs(self, values):
+        """Registers `values` as the public inputs: hashed in-circuit, the digest wired to a PublicInputGate.  -> their wires."""
+        cb = self.cb
+        cb.public_inputs = [int(x) % P for x in values]
+        r_pi = cb.add_gate(PublicInputGate(), wires=hash_no_pad(cb.public_inputs))
+        r_h, wires = self.sponge(cb.public_inputs)
+        for i in range(4):
+            cb.connect((r_h, 12 + i), (r_pi, i))
+        return wires
+
+    def opening(self, leaf, leaf_index, siblings, cap, cap_wires):
+        """One verify_merkle_proof_to_cap.  cap_wires[4 e + c]: the wire of element c of cap entry e (public-input wires)."""
+        cb, zero, bs, ra, pos = self.cb, self.zero, self.bs, self.ra, self.pos
+        h = (len(cap) - 1).bit_length()
+        assert len(cap) == 1 << h == 16, "RandomAccessGate(bits = 4): cap_height 4"
+        levels = len(siblings)
+        r_bits = cb.add_gate(bs, wires=bs.witness(leaf_index))
+        cap_index = leaf_index >> levels
+        assert cap_index < (1 << h)
+        r_hi = cb.add_gate(bs, wires=bs.witness(cap_index))
+        for j in range(63):
+            cb.connect((r_hi, 1 + j), (r_bits, 1 + levels + j) if j < h else zero)
+        for j in range(levels + h, 63):
+            cb.connect((r_bits, 1 + j), zero)
+        leaf = [int(x) % P for x in leaf]
+        if len(leaf) <= 4:  # hash_or_noop: the digest is the zero-padded leaf (advice wires of a NoopGate row)
+            r_leaf = cb.add_gate(NoopGate(), wires=leaf + [0] * (4 - len(leaf)))
+            for k in range(len(leaf), 4):
+                cb.connect((r_leaf, k), zero)
+            cur = (r_leaf, 0)
         else:
-            cb.connect((r_hi, 1 + j), zero)
-    for j in range(levels + h, 63):
-        cb.connect((r_bits, 1 + j), zero)
-    # ---- leaf digest: hash_or_noop
-    leaf = [int(x) % P for x in leaf]
-    if len(leaf) <= 4:  # no hash: the digest is the zero-padded leaf, held by a ConstantGate-free row of advice... use a noop row's wires
-        r_leaf = cb.add_gate(NoopGate(), wires=leaf + [0] * (4 - len(leaf)))
-        for k in range(len(leaf), 4):
-            cb.connect((r_leaf, k), zero)
-        cur = (r_leaf, 0)
-    else:
-        r_leaf, _ = sponge(leaf)
-        cur = (r_leaf, 12)
-    # ---- the path
-    digest = cb.wires[cur[0]][cur[1]:cur[1] + 4]
-    for lvl, sib in enumerate(siblings):
-        bit = (leaf_index >> lvl) & 1
-        r = cb.add_gate(pos, wires=poseidon_gate_wires(list(digest) + [int(x) % P for x in sib] + [0, 0, 0, 0], bit))
-        for k in range(4):
-            cb.connect((r, k), (cur[0], cur[1] + k))
-            cb.connect((r, 8 + k), zero)
-        cb.connect((r, PoseidonGate.WIRE_SWAP), (r_bits, 1 + lvl))
-        cur, digest = (r, 12), cb.wires[r][12:16]
-    # ---- the cap entry: one RandomAccess copy per digest element
-    w = [0] * NUM_WIRES
-    for c in range(4):
-        base = (2 + ra.vec) * c
-        w[base], w[base + 1] = cap_index, int(cap[cap_index][c]) % P
-        w[base + 2:base + 2 + ra.vec] = [int(cap[e][c]) % P for e in range(ra.vec)]
-        for j in range(ra.bits):
-            w[ra.num_routed + c * ra.bits + j] = (cap_index >> j) & 1
-    r_ra = cb.add_gate(ra, constants=[0, 0], wires=w)
-    for c in range(4):
-        base = (2 + ra.vec) * c
-        cb.connect((r_ra, base), (r_hi, 0))
-        cb.connect((r_ra, base + 1), (cur[0], cur[1] + c))  # fails unless the path leads to the cap
-        for e in range(ra.vec):
-            cb.connect((r_ra, base + 2 + e), cap_wires[4 * e + c])
-    return (*cb.build(min_degree_bits), public_inputs)
+            r_leaf, _ = self.sponge(leaf)
+            cur = (r_leaf, 12)
+        digest = cb.wires[cur[0]][cur[1]:cur[1] + 4]
+        for lvl, sib in enumerate(siblings):
+            bit = (leaf_index >> lvl) & 1
+            r = cb.add_gate(pos, wires=poseidon_gate_wires(list(digest) + [int(x) % P for x in sib] + [0, 0, 0, 0], bit))
+            for k in range(4):
+                cb.connect((r, k), (cur[0], cur[1] + k))
+                cb.connect((r, 8 + k), zero)
+            cb.connect((r, PoseidonGate.WIRE_SWAP), (r_bits, 1 + lvl))
+            cur, digest = (r, 12), cb.wires[r][12:16]
+        w = [0] * NUM_WIRES
+        for c in range(4):
+            base = (2 + ra.vec) * c
+            w[base], w[base + 1] = cap_index, int(cap[cap_index][c]) % P
+            w[base + 2:base + 2 + ra.vec] = [int(cap[e][c]) % P for e in range(ra.vec)]
+            for j in range(ra.bits):
+                w[ra.num_routed + c * ra.bits + j] = (cap_index >> j) & 1
+        r_ra = cb.add_gate(ra, constants=[0, 0], wires=w)
+        for c in range(4):
+            base = (2 + ra.vec) * c
+            cb.connect((r_ra, base), (r_hi, 0))
+            cb.connect((r_ra, base + 1), (cur[0], cur[1] + c))  # fails unless the path leads to the cap
+            for e in range(ra.vec):
+                cb.connect((r_ra, base + 2 + e), cap_wires[4 * e + c])
+
+
+def merkle_openings_circuit(openings: Sequence[tuple], min_degree_bits: int = 0):
+    """A fragment of the recursive verifier as a circuit: `verify_merkle_proof_to_cap` (plonky2 hash/merkle_proofs.rs, the gadget
+    every FRI query of a recursive proof runs) for a list of openings (leaf, leaf_index, siblings, cap) — real data in, e.g.
+    rows, paths and caps of batches committed on the device, or EVERY Merkle check of the FRI verification of an inner proof
+    (28 queries x (4 initial trees + the layer trees): the Poseidon-dominated bulk of a recursive verifier circuit).
+      * the distinct caps are the public inputs: hashed in-circuit by a PoseidonGate sponge wired to the PublicInputGate;
+      * per opening: see _MerkleGadget.opening.
+    -> (Circuit, wires, public_inputs).  Building fails (AssertionError in connect) when a path does not lead to its cap:
+    no witness exists."""
+    cb = CircuitBuilder()
+    gadget = _MerkleGadget(cb)
+    caps, cap_id = [], []
+    for _, _, _, cap in openings:
+        key = tuple(int(x) for d in cap for x in d)
+        if key not in caps:
+            caps.append(key)
+        cap_id.append(caps.index(key))
+    wires = gadget.public_inputs([x for key in caps for x in key])
+    for (leaf, index, siblings, cap), cid in zip(openings, cap_id):
+        gadget.opening(leaf, int(index), siblings, cap, wires[64 * cid:64 * (cid + 1)])
+    return (*cb.build(min_degree_bits), list(cb.public_inputs))
+
+
+def merkle_proof_circuit(leaf: Sequence[int], leaf_index: int, siblings: Sequence[Sequence[int]], cap: Sequence[Sequence[int]],
+                         min_degree_bits: int = 0):
+    """merkle_openings_circuit for ONE opening of a committed batch."""
+    return merkle_openings_circuit([(leaf, leaf_index, siblings, cap)], min_degree_bits)
 
 
 def fri_fold_check_circuit(values: Sequence[Sequence[int]], coset_start: int, beta: Sequence[int], expected: Sequence[int],
@@ -1230,3 +1246,88 @@ class CircuitProver:
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):
             self.ctx.L.etp_circuit_free(self.h)
             self.h = None
+
+
+# ---- recursion: the Merkle checks of the verification of an inner proof, as the witness of an outer circuit ----------------------
+def fri_query_openings(prover: CircuitProver, words: np.ndarray, public_inputs: Sequence[int]) -> List[tuple]:
+    """Replays the verifier's transcript of a circuit proof (plonk/get_challenges.rs) far enough to know the FRI query indices
+    and returns EVERY Merkle opening the FRI verifier checks: per query the rows of the four initial oracles and of every
+    commit-phase layer, with their paths and caps — [(leaf, leaf_index, siblings, cap)], the input of
+    `merkle_openings_circuit`.  This is witness generation for a recursive verifier circuit, not a verification: nothing is
+    checked here."""
+    from . import wire
+
+    c = prover.c
+    p = wire.parse_circuit_proof(words)
+    h = p["header"]
+    op = p["openings"]
+    ch = Challenger()
+    ch.observe(prover.digest)
+    ch.observe(hash_no_pad(public_inputs))
+    ch.observe_cap(p["wires_cap"])
+    ch.get_n_challenges(2 * NUM_CHALLENGES)
+    ch.observe_cap(p["plonk_zs_partial_products_cap"])
+    ch.get_n_challenges(NUM_CHALLENGES)
+    ch.observe_cap(p["quotient_polys_cap"])
+    ch.get_extension_challenge()
+    for k in ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys", "plonk_zs_next"):
+        ch.observe(op[k])
+    ch.get_extension_challenge()  # FRI alpha
+    fri = [int(x) for x in p["opening_proof"]]
+    capw = 4 << h["cap_height"]
+    n_layers, log_lde = h["n_fri_layers"], h["degree_bits"] + h["rate_bits"]
+    pos = 0
+
+    def take(n):
+        nonlocal pos
+        out = fri[pos:pos + n]
+        pos += n
+        return out
+
+    layer_caps = []
+    for _ in range(n_layers):
+        cap = take(capw)
+        layer_caps.append([cap[4 * i:4 * i + 4] for i in range(capw // 4)])
+        ch.observe(cap)
+        ch.get_extension_challenge()
+    shapes = [h["num_constants"] + h["num_routed_wires"], h["num_wires"], h["num_challenges"] * (1 + h["num_partial_products"]),
+              h["num_challenges"] * h["quotient_degree_factor"]]
+    per_query = sum(n + 4 * (log_lde - h["cap_height"]) for n in shapes)
+    bits = log_lde
+    for _ in range(n_layers):
+        bits -= h["arity_bits"]
+        per_query += 2 * (1 << h["arity_bits"]) + 4 * (bits - h["cap_height"])
+    queries_at = pos
+    pos += per_query * h["num_queries"]
+    ch.observe(take(2 * h["final_poly_len"]))
+    ch.observe(take(1))  # the proof-of-work witness
+    ch.get_challenge()   # the proof-of-work response
+    indices = [ch.get_challenge() % (1 << log_lde) for _ in range(h["num_queries"])]
+    caps = [[[int(x) for x in row] for row in np.asarray(cp).reshape(-1, 4)]
+            for cp in (prover.constants_sigmas_cap, p["wires_cap"], p["plonk_zs_partial_products_cap"], p["quotient_polys_cap"])]
+    pos = queries_at
+    out = []
+    quads = lambda ws: [ws[4 * i:4 * i + 4] for i in range(len(ws) // 4)]
+    for x in indices:
+        for n, cap in zip(shapes, caps):
+            leaf = take(n)
+            out.append((leaf, x, quads(take(4 * (log_lde - h["cap_height"]))), cap))
+        bits, idx = log_lde, x
+        for layer in range(n_layers):
+            bits -= h["arity_bits"]
+            idx >>= h["arity_bits"]
+            leaf = take(2 * (1 << h["arity_bits"]))
+            out.append((leaf, idx, quads(take(4 * (bits - h["cap_height"]))), layer_caps[layer]))
+    return out
+
+
+def recursive_merkle_verifier_circuit(inner: Sequence[tuple], min_degree_bits: int = 0):
+    """The Merkle part of a recursive verifier: one outer circuit that checks every Merkle opening of the FRI verification of the
+    inner proofs `[(CircuitProver, proof words, public inputs)]` — 28 queries x (4 initial trees + the layer trees) each.  A 2^12-row
+    inner proof gives ~3.2 k outer rows (2^12), two of them 2^13: the sizes, and the PoseidonGate share, of the reference's
+    shrinking / aggregation circuits.  Not the whole verifier: the FRI fold checks (`fri_fold_check_circuit`), fri_combine_initial,
+    the in-circuit challenger and the vanishing-polynomial check are not assembled into it."""
+    openings = []
+    for prover, words, public_inputs in inner:
+        openings += fri_query_openings(prover, words, public_inputs)
+    return merkle_openings_circuit(openings, min_degree_bits)

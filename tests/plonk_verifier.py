@@ -62,10 +62,11 @@ def parse_fri_proof(words, oracle_cols, degree_bits, rate_bits, cap_height, n_la
     return out
 
 
-def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_bits, num_queries, fast=True, max_queries=None, folds=None):
+def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_bits, num_queries, fast=True, max_queries=None, folds=None, merkle=None):
     """verify_fri_proof.  batches: [(point (ext), [(oracle, poly)], [opened values (ext)])]; `ch`: the challenger after it
     observed the openings.  folds: a list that receives every compute_evaluation instance
-    (values in natural order, coset start, beta, interpolated value) — inputs for the in-circuit fold check."""
+    (values in natural order, coset start, beta, interpolated value) — inputs for the in-circuit fold check; merkle: a list that
+    receives every Merkle check (leaf, index, siblings, cap) — inputs for the in-circuit Merkle verifications."""
     hash_or_noop, two_to_one, _ = V._hashers(fast)
     fri_alpha = ch.get_ext()
     betas = []
@@ -90,6 +91,8 @@ def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_b
         q = fri["queries"][qi]
         for (leaf, sib), cap in zip(q["initial"], caps):
             V._merkle_verify(leaf, x_index, sib, cap, hash_or_noop, two_to_one)
+            if merkle is not None:
+                merkle.append((leaf, x_index, sib, cap))
         subgroup_x = R.GENERATOR * pow(w_lde, R.bitrev(x_index, lde_bits), P) % P
         leaves = [lf for lf, _ in q["initial"]]
         sx = R.e_from(subgroup_x)
@@ -116,6 +119,8 @@ def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_b
                 folds.append((ev, coset_start, betas[i], old_eval))
             flat = [c for e in evals for c in e]
             V._merkle_verify(flat, coset_index, sib, fri["fri_caps"][i], hash_or_noop, two_to_one)
+            if merkle is not None:
+                merkle.append((flat, coset_index, sib, fri["fri_caps"][i]))
             subgroup_x = pow(subgroup_x, arity, P)
             x_index = coset_index
         acc = (0, 0)
@@ -125,7 +130,7 @@ def verify_fri(fri, caps, batches, ch, degree_bits, rate_bits, arity_bits, pow_b
             raise VerifyError("Final polynomial evaluation is invalid.")
 
 
-def verify(proof, circuit, constants_sigmas_cap, circuit_digest, fast=True, max_queries=None, folds=None):
+def verify(proof, circuit, constants_sigmas_cap, circuit_digest, fast=True, max_queries=None, folds=None, merkle=None):
     """Raises VerifyError unless `proof` (CircuitProver.prove) is a valid proof for `circuit`."""
     from eth_tx_proof_b200 import circuit as cc
 
@@ -181,5 +186,5 @@ def verify(proof, circuit, constants_sigmas_cap, circuit_digest, fast=True, max_
         n_layers, bits = n_layers + 1, bits - 4
     fri = parse_fri_proof(proof["opening_proof"], shapes, db, cc.RATE_BITS, cc.CAP_HEIGHT, n_layers, 4, cc.NUM_QUERIES, 1 << bits)
     all_caps = [caps(constants_sigmas_cap), caps(proof["wires_cap"]), caps(proof["plonk_zs_partial_products_cap"]), caps(proof["quotient_polys_cap"])]
-    verify_fri(fri, all_caps, batches, ch, db, cc.RATE_BITS, 4, cc.POW_BITS, cc.NUM_QUERIES, fast, max_queries, folds)
+    verify_fri(fri, all_caps, batches, ch, db, cc.RATE_BITS, 4, cc.POW_BITS, cc.NUM_QUERIES, fast, max_queries, folds, merkle)
     return True

@@ -289,3 +289,35 @@ def test_fri_fold_check_circuit_over_a_device_proof(ctx):
     circuit, w, pis = cc.fri_fold_check_circuit(values, coset_start, beta, expected)
     p_out = cc.CircuitProver(ctx, circuit)
     plonk_verifier.verify(p_out.prove(w, pis), circuit, p_out.constants_sigmas_cap, p_out.digest, max_queries=2)
+
+
+def test_recursive_merkle_verifier_chain(ctx):
+    """A recursion chain on the device: proof 0 of a base circuit; circuit 1 checks EVERY Merkle opening of proof 0's FRI
+    verification (transcript replayed by the product to get the query indices: the openings must be the ones the independent
+    verifier checks) and is proved; circuit 2 does the same for proof 1.  Each outer proof is verified; the outer circuit's
+    structure does not depend on the inner proof's data (same constants and sigmas for another inner proof)."""
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    base, wires, pis = cc.hash_chain_circuit(7, seed=8)
+    p0 = cc.CircuitProver(ctx, base)
+    w0 = p0.prove_words(wires, pis)
+    seen = []
+    plonk_verifier.verify(p0.prove(wires, pis), base, p0.constants_sigmas_cap, p0.digest, merkle=seen)
+    ops = cc.fri_query_openings(p0, w0, pis)
+    assert len(ops) == len(seen) == 28 * 5
+    for (l1, i1, s1, c1), (l2, i2, s2, c2) in zip(ops, seen):
+        assert list(l1) == list(l2) and i1 == i2 and s1 == s2 and c1 == c2
+    c1_, w1, pi1 = cc.recursive_merkle_verifier_circuit([(p0, w0, pis)])
+    p1 = cc.CircuitProver(ctx, c1_)
+    proof1 = p1.prove(w1, pi1)
+    plonk_verifier.verify(proof1, c1_, p1.constants_sigmas_cap, p1.digest, max_queries=2)
+    # the same outer circuit for ANOTHER inner proof of the same shape: only the witness changes
+    wires_b, pis_b = cc.hash_chain_circuit(7, seed=9)[1:]
+    c1b, w1b, pi1b = cc.recursive_merkle_verifier_circuit([(p0, p0.prove_words(wires_b, pis_b), pis_b)])
+    assert (c1b.constants == c1_.constants).all() and (c1b.sigmas == c1_.sigmas).all() and not (w1b == w1).all()
+    plonk_verifier.verify(p1.prove(w1b, pi1b), c1_, p1.constants_sigmas_cap, p1.digest, max_queries=1)
+    # one more layer: the outer proof is itself the inner proof of the next circuit
+    c2_, w2, pi2 = cc.recursive_merkle_verifier_circuit([(p1, proof1["words"], pi1)])
+    p2 = cc.CircuitProver(ctx, c2_)
+    plonk_verifier.verify(p2.prove(w2, pi2), c2_, p2.constants_sigmas_cap, p2.digest, max_queries=1)
