@@ -277,3 +277,48 @@ def test_fri_fold_check_circuit_on_real_fri_data():
         plonk_verifier.verify(outer, circuit, outer["constants_sigmas_cap"], [1, 1, 1, 1], max_queries=1)
         with pytest.raises(AssertionError, match="copy constraint"):
             cc.fri_fold_check_circuit(values, coset_start, beta, (expected[0] ^ 1, expected[1]))
+
+
+def _words_from_oracle_proof(circuit, proof, public_inputs):
+    """oracle.circuit_prove's dict -> flat "B200PLK1" words (the layout etp_circuit_prove_* writes)."""
+    from eth_tx_proof_b200 import circuit as cc, wire
+
+    op, nc, db = proof["openings"], circuit.num_constants, circuit.degree_bits
+    n_layers, bits = 0, db
+    while bits > 5:
+        n_layers, bits = n_layers + 1, bits - 4
+    body = np.concatenate([np.asarray(x, dtype=np.uint64).reshape(-1) for x in (
+        proof["wires_cap"], proof["plonk_zs_partial_products_cap"], proof["quotient_polys_cap"], op["constants_sigmas"], op["wires"],
+        op["zs_partial_products"][:2], op["plonk_zs_next"], op["zs_partial_products"][2:], op["quotient_polys"], proof["opening_proof"],
+        cc.hash_no_pad(public_inputs))])
+    hdr = np.zeros(wire.HEADER_WORDS, dtype=np.uint64)
+    hdr[:16] = [wire.CIRCUIT_MAGIC, db, nc, 80, 135, 2, 9, 8, 3, 4, n_layers, 4, 1 << bits, 28, 16, wire.HEADER_WORDS + body.size]
+    return np.concatenate([hdr, body])
+
+
+def test_product_transcript_replay_finds_the_openings_the_verifier_checks():
+    """circuit.fri_query_openings (product host logic: witness generation for a recursive verifier circuit) on a CPU-made proof:
+    the same (leaf, index, path, cap) list, in the same order, as the independent verifier's Merkle checks; and the outer
+    circuit built from it is satisfiable and its oracle proof verifies — a recursion step without a GPU."""
+    import types
+
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(7, seed=12)
+    digest = [4, 3, 2, 1]
+    proof = oracle.circuit_prove(inner, wires, public_inputs, digest)
+    seen = []
+    plonk_verifier.verify(proof, inner, proof["constants_sigmas_cap"], digest, merkle=seen)
+    fake_prover = types.SimpleNamespace(c=inner, digest=digest, constants_sigmas_cap=proof["constants_sigmas_cap"])
+    words = _words_from_oracle_proof(inner, proof, public_inputs)
+    ops = cc.fri_query_openings(fake_prover, words, public_inputs)
+    assert len(ops) == len(seen) == 28 * 5
+    for (l1, i1, s1, c1), (l2, i2, s2, c2) in zip(ops, seen):
+        assert [int(x) for x in l1] == [int(x) for x in l2] and i1 == i2 and s1 == s2 and c1 == c2
+    outer, w, pis = cc.merkle_openings_circuit(ops[:10])  # two queries' worth: keeps the pure-Python checks short
+    zs_pp = oracle.plonk_partial_products_and_zs(w[:80], outer.sigmas, outer.k_is, 8, [3, 5], [7, 11])
+    assert _violations(outer, w, zs_pp, cc.hash_no_pad(pis), [3, 5], [7, 11]) == []
+    proof2 = oracle.circuit_prove(outer, w, pis, digest)
+    plonk_verifier.verify(proof2, outer, proof2["constants_sigmas_cap"], digest, max_queries=1)
