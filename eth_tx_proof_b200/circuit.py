@@ -1075,7 +1075,8 @@ class _MerkleGadget:
         return wires
 
     def opening(self, leaf, leaf_index, siblings, cap, cap_wires):
-        """One verify_merkle_proof_to_cap.  cap_wires[4 e + c]: the wire of element c of cap entry e (public-input wires)."""
+        """One verify_merkle_proof_to_cap.  cap_wires[4 e + c]: the wire of element c of cap entry e (public-input wires).
+        -> (the wire holding leaf_index, the wires the leaf's elements entered through)."""
         cb, zero, bs, ra, pos = self.cb, self.zero, self.bs, self.ra, self.pos
         h = (len(cap) - 1).bit_length()
         assert len(cap) == 1 << h == 16, "RandomAccessGate(bits = 4): cap_height 4"
@@ -1093,9 +1094,9 @@ class _MerkleGadget:
             r_leaf = cb.add_gate(NoopGate(), wires=leaf + [0] * (4 - len(leaf)))
             for k in range(len(leaf), 4):
                 cb.connect((r_leaf, k), zero)
-            cur = (r_leaf, 0)
+            cur, leaf_wires = (r_leaf, 0), [(r_leaf, k) for k in range(len(leaf))]
         else:
-            r_leaf, _ = self.sponge(leaf)
+            r_leaf, leaf_wires = self.sponge(leaf)
             cur = (r_leaf, 12)
         digest = cb.wires[cur[0]][cur[1]:cur[1] + 4]
         for lvl, sib in enumerate(siblings):
@@ -1120,6 +1121,7 @@ class _MerkleGadget:
             cb.connect((r_ra, base + 1), (cur[0], cur[1] + c))  # fails unless the path leads to the cap
             for e in range(ra.vec):
                 cb.connect((r_ra, base + 2 + e), cap_wires[4 * e + c])
+        return (r_bits, 0), leaf_wires
 
 
 def merkle_openings_circuit(openings: Sequence[tuple], min_degree_bits: int = 0):

@@ -1,0 +1,424 @@
+"""The FRI verifier as a circuit (plonky2 0.2.2 fri/recursive_verifier.rs verify_fri_proof: the bulk of every shrinking /
+aggregation / block circuit of the reference, /root/reference/ops/src/lib.rs:52,72,95), assembled from the gates of circuit.py and
+fed with a REAL inner proof made on the device.  Per query round, for an inner circuit proof (four initial oracles):
+
+    fri_verify_initial_proof   Merkle openings of the four oracle rows            PoseidonGate sponges + swapped path levels,
+                                                                                  BaseSum index bits, RandomAccess cap entry
+    subgroup_x                 g * w^rev(x_index)                                 ExponentiationGate over the index bits
+    fri_combine_initial        sum_b alpha^.. (reduce(alpha, evals_b) - y_b) / (x - z_b)   ReducingGate rows, extension
+                                                                                  arithmetic (division = witnessed quotient)
+    per commit-phase layer     evals[x_index mod 16] == previous value            RandomAccessGate on the 16 opened values
+                               compute_evaluation at beta                         CosetInterpolationGate (coset start by an
+                                                                                  ExponentiationGate over the low index bits)
+                               Merkle opening of the layer row, x^16              as above; ArithmeticGate squarings
+    final polynomial           Horner at subgroup_x == last value                 ReducingExtensionGate
+
+The challenges (alpha, betas, zeta, the query indices), the reduced openings, the caps and the final polynomial are PUBLIC INPUTS
+of the outer circuit (hashed in-circuit): the in-circuit challenger that derives them from the transcript, the proof-of-work
+check and the vanishing-polynomial check of the inner circuit are the parts of plonky2's recursive verifier NOT assembled here.
+The builder assigns wire values directly while it places gates (no generators): witness generation and circuit construction
+are one pass, and the resulting circuit's structure (gates, constants, copy constraints) does not depend on the proof's data.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import circuit as cc
+from .circuit import (NUM_WIRES, P, ArithmeticExtensionGate, ArithmeticGate, BaseSumGate, CircuitBuilder, ConstantGate,
+                      CosetInterpolationGate, ExponentiationGate, RandomAccessGate, ReducingExtensionGate, ReducingGate, _MerkleGadget,
+                      _e_mod, _e_mul)
+
+Target = Tuple[int, int]          # (row, wire)
+ExtTarget = Tuple[Target, Target]
+
+
+def _bitrev(x: int, bits: int) -> int:
+    return int(format(x, f"0{bits}b")[::-1], 2) if bits else 0
+
+
+def _e_inv(a):
+    n = (a[0] * a[0] - 7 * a[1] * a[1]) % P
+    ni = pow(n, P - 2, P)
+    return (a[0] * ni % P, (P - a[1]) * ni % P)
+
+
+class GadgetBuilder(CircuitBuilder):
+    """Targets over a CircuitBuilder: every helper places (or reuses a free slot of) a gate row, assigns the wire values,
+    connects the operands by copy constraints and returns the target(s) of the result — plonky2's CircuitBuilder helpers
+    (arithmetic, arithmetic_extension, split_le, exp_from_bits, random_access, reduce_with_powers, interpolate_coset)."""
+
+    def __init__(self):
+        super().__init__()
+        self.merkle = _MerkleGadget(self)
+        self.zero, self.one = self.merkle.zero, (self.merkle.r_const, 1)
+        self._consts = {0: self.zero, 1: self.one}
+        self._const_row = None      # (row, next free slot) of a ConstantGate with free slots
+        self._arith = {}            # (c0, c1) -> (row, next op) of an ArithmeticGate row with free ops
+        self._arith_ext = {}
+        self.ar, self.are = ArithmeticGate(20), ArithmeticExtensionGate(10)
+        self.bs, self.exp, self.ra = BaseSumGate(63), ExponentiationGate(66), RandomAccessGate(4, 4, 2)
+        self.red, self.rede = ReducingGate(43), ReducingExtensionGate(32)
+        self.coset = CosetInterpolationGate.with_max_degree(4, cc.QUOTIENT_DEGREE_FACTOR)
+
+    # ---- values
+    def val(self, t: Target) -> int:
+        return self.wires[t[0]][t[1]]
+
+    def vale(self, t: ExtTarget):
+        return (self.val(t[0]), self.val(t[1]))
+
+    def _set(self, t: Target, v: int, src: Target = None):
+        self.wires[t[0]][t[1]] = int(v) % P
+        if src is not None:
+            self.connect(t, src)
+
+    def constant(self, v: int) -> Target:
+        v = int(v) % P
+        if v in self._consts:
+            return self._consts[v]
+        # ConstantGate rows hold two constants each; the gate's constants are per row, so a half-used row is completed in place
+        if self._const_row is None:
+            r = self.add_gate(ConstantGate(2), constants=[v, 0], wires=[v, 0])
+            self._const_row = r
+            t = (r, 0)
+        else:
+            r = self._const_row
+            self.rows[r] = (self.rows[r][0], [self.rows[r][1][0], v])
+            self.wires[r][1] = v
+            self._const_row = None
+            t = (r, 1)
+        self._consts[v] = t
+        return t
+
+    def constant_ext(self, v) -> ExtTarget:
+        return (self.constant(v[0]), self.constant(v[1]))
+
+    # ---- base-field arithmetic: output = c0 * m0 * m1 + c1 * addend (ArithmeticGate, 20 operations per row, constants per row)
+    def arith(self, m0: Target, m1: Target, addend: Target, c0: int = 1, c1: int = 1) -> Target:
+        key = (c0 % P, c1 % P)
+        slot = self._arith.get(key)
+        if slot is None or slot[1] == self.ar.num_ops:
+            slot = (self.add_gate(self.ar, constants=list(key)), 0)
+        r, i = slot
+        self._arith[key] = (r, i + 1)
+        for k, src in enumerate((m0, m1, addend)):
+            self._set((r, 4 * i + k), self.val(src), src)
+        out = (r, 4 * i + 3)
+        self._set(out, self.val(m0) * self.val(m1) % P * key[0] + self.val(addend) * key[1])
+        return out
+
+    def mul(self, a, b):
+        return self.arith(a, b, self.zero, 1, 0)
+
+    def sub(self, a, b):
+        return self.arith(a, self.one, b, 1, P - 1)
+
+    def mul_const(self, a, c):
+        return self.arith(a, self.one, self.zero, c, 0)
+
+    def neg(self, a):
+        return self.arith(self.zero, self.zero, a, 0, P - 1)
+
+    # ---- extension arithmetic (ArithmeticExtensionGate, 10 operations per row)
+    def arith_ext(self, m0: ExtTarget, m1: ExtTarget, addend: ExtTarget, c0: int = 1, c1: int = 1) -> ExtTarget:
+        key = (c0 % P, c1 % P)
+        slot = self._arith_ext.get(key)
+        if slot is None or slot[1] == self.are.num_ops:
+            slot = (self.add_gate(self.are, constants=list(key)), 0)
+        r, i = slot
+        self._arith_ext[key] = (r, i + 1)
+        for k, src in enumerate((m0, m1, addend)):
+            for comp in range(2):
+                self._set((r, 8 * i + 2 * k + comp), self.val(src[comp]), src[comp])
+        pr = _e_mod(_e_mul(self.vale(m0), self.vale(m1)))
+        ad = self.vale(addend)
+        out = ((r, 8 * i + 6), (r, 8 * i + 7))
+        self._set(out[0], pr[0] * key[0] + ad[0] * key[1])
+        self._set(out[1], pr[1] * key[0] + ad[1] * key[1])
+        return out
+
+    @property
+    def zero_ext(self) -> ExtTarget:
+        return (self.zero, self.zero)
+
+    @property
+    def one_ext(self) -> ExtTarget:
+        return (self.one, self.zero)
+
+    def mul_ext(self, a, b):
+        return self.arith_ext(a, b, self.zero_ext, 1, 0)
+
+    def sub_ext(self, a, b):
+        return self.arith_ext(a, self.one_ext, b, 1, P - 1)
+
+    def div_ext(self, num: ExtTarget, den: ExtTarget) -> ExtTarget:
+        """q with q * den == num: the quotient is witnessed (advice), one ArithmeticExtension operation constrains it
+        (div_add_extension's trick).  The quotient enters as m0 of a fresh operation whose output is connected to num."""
+        q = _e_mod(_e_mul(self.vale(num), _e_inv(self.vale(den))))
+        key = (1, 0)
+        slot = self._arith_ext.get(key)
+        if slot is None or slot[1] == self.are.num_ops:
+            slot = (self.add_gate(self.are, constants=list(key)), 0)
+        r, i = slot
+        self._arith_ext[key] = (r, i + 1)
+        qt = ((r, 8 * i), (r, 8 * i + 1))
+        self._set(qt[0], q[0])
+        self._set(qt[1], q[1])
+        for comp in range(2):
+            self._set((r, 8 * i + 2 + comp), self.val(den[comp]), den[comp])
+            self._set((r, 8 * i + 4 + comp), 0, self.zero)
+            self._set((r, 8 * i + 6 + comp), self.val(num[comp]), num[comp])
+        assert _e_mod(_e_mul(q, self.vale(den))) == self.vale(num)
+        return qt
+
+    def connect_ext(self, a: ExtTarget, b: ExtTarget):
+        self.connect(a[0], b[0])
+        self.connect(a[1], b[1])
+
+    # ---- bits (BaseSumGate: wire 0 = sum of limb_i 2^i, limbs boolean)
+    def split_bits(self, t: Target, n_bits: int) -> List[Target]:
+        r = self.add_gate(self.bs, wires=self.bs.witness(self.val(t)))
+        assert self.val(t) < (1 << n_bits)
+        self.connect((r, 0), t)
+        for j in range(n_bits, 63):
+            self.connect((r, 1 + j), self.zero)
+        return [(r, 1 + j) for j in range(n_bits)]
+
+    def bits_to_target(self, bits: Sequence[Target]) -> Target:
+        v = sum(self.val(b) << j for j, b in enumerate(bits))
+        r = self.add_gate(self.bs, wires=self.bs.witness(v))
+        for j in range(63):
+            self.connect((r, 1 + j), bits[j] if j < len(bits) else self.zero)
+        return (r, 0)
+
+    # ---- exp_from_bits (ExponentiationGate): base^(sum bits_j 2^j)
+    def exp_from_bits(self, base: Target, bits: Sequence[Target]) -> Target:
+        power = sum(self.val(b) << j for j, b in enumerate(bits))
+        r = self.add_gate(self.exp, wires=self.exp.witness(self.val(base), power))
+        self.connect((r, 0), base)
+        for j in range(self.exp.n_bits):
+            self.connect((r, 1 + j), bits[j] if j < len(bits) else self.zero)
+        return (r, 1 + self.exp.n_bits)
+
+    # ---- random access into 16 extension values (RandomAccessGate: copy 0 / 1 = the two components)
+    def random_access_ext(self, index: Target, items: Sequence[ExtTarget]) -> ExtTarget:
+        ra = self.ra
+        assert len(items) == ra.vec
+        idx = self.val(index)
+        w = [0] * NUM_WIRES
+        for c in range(ra.num_copies):
+            base = (2 + ra.vec) * c
+            comp = c if c < 2 else 0  # copies 2, 3 repeat component 0 (the gate has four copies)
+            w[base], w[base + 1] = idx, self.val(items[idx][comp])
+            w[base + 2:base + 2 + ra.vec] = [self.val(it[comp]) for it in items]
+            for j in range(ra.bits):
+                w[ra.num_routed + c * ra.bits + j] = (idx >> j) & 1
+        r = self.add_gate(ra, constants=[0, 0], wires=w)
+        for c in range(ra.num_copies):
+            base = (2 + ra.vec) * c
+            comp = c if c < 2 else 0
+            self.connect((r, base), index)
+            for e in range(ra.vec):
+                self.connect((r, base + 2 + e), items[e][comp])
+        return ((r, 1), (r, (2 + ra.vec) + 1))
+
+    # ---- reduce_with_powers: sum_k alpha^k coeff_k
+    def reduce_base(self, alpha: ExtTarget, coeffs: Sequence[Target]) -> ExtTarget:
+        """Base-field coefficients, extension alpha (ReducingGate rows chained through old_acc; Horner from the last coefficient,
+        leading slots of the first row padded with zeros)."""
+        g = self.red
+        seq = list(reversed(coeffs))
+        pad = (-len(seq)) % g.num_coeffs
+        seq = [self.zero] * pad + seq
+        acc_t, acc = self.zero_ext, (0, 0)
+        a = self.vale(alpha)
+        for off in range(0, len(seq), g.num_coeffs):
+            w = [0] * NUM_WIRES
+            w[2:6] = [*a, *acc]
+            chunk = seq[off:off + g.num_coeffs]
+            for i, ct in enumerate(chunk):
+                c = self.val(ct)
+                w[g.start_coeffs + i] = c
+                t = _e_mod(_e_mul(acc, a))
+                acc = ((t[0] + c) % P, t[1])
+                a0, a1 = g._acc(i)
+                w[a0], w[a1] = acc
+            r = self.add_gate(g, wires=w)
+            self.connect_ext(((r, 2), (r, 3)), alpha)
+            self.connect_ext(((r, 4), (r, 5)), acc_t)
+            for i, ct in enumerate(chunk):
+                self.connect((r, g.start_coeffs + i), ct)
+            acc_t = ((r, 0), (r, 1))
+        return acc_t
+
+    def reduce_ext(self, alpha: ExtTarget, coeffs: Sequence[ExtTarget]) -> ExtTarget:
+        g = self.rede
+        seq = list(reversed(coeffs))
+        pad = (-len(seq)) % g.num_coeffs
+        seq = [self.zero_ext] * pad + seq
+        acc_t, acc = self.zero_ext, (0, 0)
+        a = self.vale(alpha)
+        for off in range(0, len(seq), g.num_coeffs):
+            w = [0] * NUM_WIRES
+            w[2:6] = [*a, *acc]
+            chunk = seq[off:off + g.num_coeffs]
+            for i, ct in enumerate(chunk):
+                c = self.vale(ct)
+                w[g.start_coeffs + 2 * i], w[g.start_coeffs + 2 * i + 1] = c
+                t = _e_mod(_e_mul(acc, a))
+                acc = ((t[0] + c[0]) % P, (t[1] + c[1]) % P)
+                a0, a1 = g._acc(i)
+                w[a0], w[a1] = acc
+            r = self.add_gate(g, wires=w)
+            self.connect_ext(((r, 2), (r, 3)), alpha)
+            self.connect_ext(((r, 4), (r, 5)), acc_t)
+            for i, ct in enumerate(chunk):
+                self.connect_ext(((r, g.start_coeffs + 2 * i), (r, g.start_coeffs + 2 * i + 1)), ct)
+            acc_t = ((r, 0), (r, 1))
+        return acc_t
+
+    # ---- interpolate_coset (CosetInterpolationGate): the interpolant of 16 values on shift * <w16> at `point`
+    def interpolate_coset(self, shift: Target, values: Sequence[ExtTarget], point: ExtTarget) -> ExtTarget:
+        g = self.coset
+        seq = iter([self.val(shift)] + [x for v in values for x in self.vale(v)] + list(self.vale(point)))
+        r = self.add_gate(g, wires=g.witness(lambda: next(seq)))
+        self.connect((r, 0), shift)
+        for i, v in enumerate(values):
+            self.connect_ext(((r, g.start_values + 2 * i), (r, g.start_values + 2 * i + 1)), v)
+        self.connect_ext(((r, g.start_point), (r, g.start_point + 1)), point)
+        return ((r, g.start_value), (r, g.start_value + 1))
+
+
+def fri_challenges_and_openings(prover, words: np.ndarray, public_inputs: Sequence[int]) -> dict:
+    """Transcript replay of a circuit proof (witness generation for the outer circuit; nothing is checked): FRI alpha, betas,
+    zeta, query indices, the reduced openings of the two batches, the caps, the final polynomial and, per query, the opened rows
+    and paths.  See circuit.fri_query_openings for the Merkle part."""
+    from . import wire
+    from .api import Challenger
+
+    p = wire.parse_circuit_proof(words)
+    h = p["header"]
+    op = p["openings"]
+    ch = Challenger()
+    ch.observe(prover.digest)
+    ch.observe(cc.hash_no_pad(public_inputs))
+    ch.observe_cap(p["wires_cap"])
+    ch.get_n_challenges(2 * cc.NUM_CHALLENGES)
+    ch.observe_cap(p["plonk_zs_partial_products_cap"])
+    ch.get_n_challenges(cc.NUM_CHALLENGES)
+    ch.observe_cap(p["quotient_polys_cap"])
+    zeta = [int(x) for x in ch.get_extension_challenge()]
+    order = ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys")
+    for k in order + ("plonk_zs_next",):
+        ch.observe(op[k])
+    alpha = [int(x) for x in ch.get_extension_challenge()]
+    fri = [int(x) for x in p["opening_proof"]]
+    capw = 4 << h["cap_height"]
+    betas, pos = [], 0
+    for _ in range(h["n_fri_layers"]):
+        ch.observe(fri[pos:pos + capw])
+        pos += capw
+        betas.append([int(x) for x in ch.get_extension_challenge()])
+    final = fri[len(fri) - 1 - 2 * h["final_poly_len"]:len(fri) - 1]
+
+    def reduce(vals):
+        acc = (0, 0)
+        for v in reversed(vals):
+            acc = _e_mod(_e_mul(acc, alpha))
+            acc = ((acc[0] + int(v[0])) % P, (acc[1] + int(v[1])) % P)
+        return acc
+
+    batch0 = [v for k in order for v in op[k]]
+    return {"header": h, "alpha": alpha, "betas": betas, "zeta": zeta, "reduced": [reduce(batch0), reduce(list(op["plonk_zs_next"]))],
+            "final_poly": [(final[2 * i], final[2 * i + 1]) for i in range(h["final_poly_len"])],
+            "openings": cc.fri_query_openings(prover, words, public_inputs)}
+
+
+def fri_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, min_degree_bits: int = 0):
+    """verify_fri_proof of the inner circuit proofs `[(CircuitProver, proof words, public inputs)]` as ONE outer circuit (module
+    docstring): a 2^12-row inner proof costs ~3.8 k outer rows (2^12), two of them 2^13.  -> (Circuit, wires, public inputs of
+    the outer circuit).  Building fails (AssertionError in connect / div_ext) when an inner proof's FRI part is not valid: no
+    witness exists."""
+    if isinstance(inner, tuple) and not isinstance(inner[0], tuple):
+        inner = [inner]
+    datas = [fri_challenges_and_openings(*x) for x in inner]
+    b = GadgetBuilder()
+    # ---- public inputs, per inner proof: caps | alpha | zeta | betas | reduced openings | final polynomial | query indices
+    layouts, pi_values = [], []
+    for d in datas:
+        h = d["header"]
+        nq = h["num_queries"] if max_queries is None else min(max_queries, h["num_queries"])
+        per_query = 4 + h["n_fri_layers"]
+        openings = d["openings"][:nq * per_query]
+        caps = [tuple(int(x) for dg in openings[o][3] for x in dg) for o in range(per_query)]
+        indices = [openings[q * per_query][1] for q in range(nq)]
+        layouts.append((len(pi_values), nq, per_query, openings))
+        pi_values += [x for cp in caps for x in cp] + d["alpha"] + d["zeta"] + [x for be in d["betas"] for x in be] + \
+            [x for r in d["reduced"] for x in r] + [x for cf in d["final_poly"] for x in cf] + indices
+    all_pw = b.merkle.public_inputs(pi_values)
+    for d, (base, nq, per_query, openings) in zip(datas, layouts):
+        _verify_one(b, d, all_pw[base:], nq, per_query, openings)
+    circuit, wires = b.build(min_degree_bits)
+    return circuit, wires, list(b.public_inputs)
+
+
+def _verify_one(b: GadgetBuilder, d: dict, pw: Sequence[Target], nq: int, per_query: int, openings: Sequence[tuple]):
+    h = d["header"]
+    n_layers, arity_bits = h["n_fri_layers"], h["arity_bits"]
+    log_lde = h["degree_bits"] + h["rate_bits"]
+    at = 64 * per_query
+    ext_at = lambda k: (pw[k], pw[k + 1])
+    alpha_t, zeta_t = ext_at(at), ext_at(at + 2)
+    beta_t = [ext_at(at + 4 + 2 * i) for i in range(n_layers)]
+    at += 4 + 2 * n_layers
+    reduced_t = [ext_at(at), ext_at(at + 2)]
+    at += 4
+    final_t = [ext_at(at + 2 * i) for i in range(len(d["final_poly"]))]
+    at += 2 * len(d["final_poly"])
+    index_t = pw[at:at + nq]
+    # ---- per-proof values: zeta_next = g * zeta, alpha^2 (the shift of the first batch past the two openings of the second)
+    g = cc.root_of_unity(h["degree_bits"])
+    zeta_next_t = (b.mul_const(zeta_t[0], g), b.mul_const(zeta_t[1], g))
+    alpha2_t = b.mul_ext(alpha_t, alpha_t)
+    w_lde_t = b.constant(cc.root_of_unity(log_lde))
+    g16_inv_t = b.constant(pow(cc.root_of_unity(arity_bits), P - 2, P))
+    neg_z1 = [b.neg(zeta_t[1]), b.neg(zeta_next_t[1])]
+    points = [zeta_t, zeta_next_t]
+    for q in range(nq):
+        ops = openings[q * per_query:(q + 1) * per_query]
+        x_t = index_t[q]
+        bits = b.split_bits(x_t, log_lde)
+        # fri_verify_initial_proof
+        leaf_t = []
+        for o in range(4):
+            leaf, idx, sib, cap = ops[o]
+            it, lt = b.merkle.opening(leaf, idx, sib, cap, pw[64 * o:64 * (o + 1)])
+            b.connect(it, x_t)
+            leaf_t.append(lt)
+        # subgroup_x = g * w^rev(x_index)
+        sx_t = b.mul_const(b.exp_from_bits(w_lde_t, list(reversed(bits))), 7)
+        # fri_combine_initial: batch 0 = every polynomial of the four oracles at zeta, batch 1 = the Zs at g * zeta
+        evals = [[t for lt in leaf_t for t in lt], leaf_t[2][:cc.NUM_CHALLENGES]]
+        quot = []
+        for bi in range(2):
+            num = b.sub_ext(b.reduce_base(alpha_t, evals[bi]), reduced_t[bi])
+            den = (b.sub(sx_t, points[bi][0]), neg_z1[bi])
+            quot.append(b.div_ext(num, den))
+        old = b.arith_ext(quot[0], alpha2_t, quot[1], 1, 1)
+        for layer in range(n_layers):
+            leaf, idx, sib, cap = ops[4 + layer]
+            lo = arity_bits * layer
+            within_bits = bits[lo:lo + arity_bits]
+            it, lt = b.merkle.opening(leaf, idx, sib, cap, pw[64 * (4 + layer):64 * (5 + layer)])
+            b.connect(it, b.bits_to_target(bits[lo + arity_bits:]))
+            ev = [(lt[2 * k], lt[2 * k + 1]) for k in range(1 << arity_bits)]
+            b.connect_ext(b.random_access_ext(b.bits_to_target(within_bits), ev), old)  # evals[x_index mod 16] == the previous value
+            coset_start = b.mul(sx_t, b.exp_from_bits(g16_inv_t, list(reversed(within_bits))))
+            nat = [ev[_bitrev(k, arity_bits)] for k in range(1 << arity_bits)]
+            old = b.interpolate_coset(coset_start, nat, beta_t[layer])
+            for _ in range(arity_bits):
+                sx_t = b.mul(sx_t, sx_t)
+        # final polynomial at subgroup_x
+        b.connect_ext(b.reduce_ext((sx_t, b.zero), final_t), old)

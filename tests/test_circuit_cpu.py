@@ -322,3 +322,45 @@ def test_product_transcript_replay_finds_the_openings_the_verifier_checks():
     assert _violations(outer, w, zs_pp, cc.hash_no_pad(pis), [3, 5], [7, 11]) == []
     proof2 = oracle.circuit_prove(outer, w, pis, digest)
     plonk_verifier.verify(proof2, outer, proof2["constants_sigmas_cap"], digest, max_queries=1)
+
+
+def test_fri_verifier_circuit_on_a_real_proof():
+    """verify_fri_proof as a circuit (fri_circuit.py: Merkle openings, subgroup_x, fri_combine_initial, per-layer consistency +
+    compute_evaluation, final polynomial) over a CPU-made inner proof: it builds only because every in-circuit value meets the
+    proof's (the copy constraints assert equality while building), its constraints hold, the oracle proves it and the verifier
+    accepts; a tampered inner proof has no witness."""
+    import types
+
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(7, seed=12)
+    digest = [4, 3, 2, 1]
+    proof = oracle.circuit_prove(inner, wires, public_inputs, digest)
+    fake_prover = types.SimpleNamespace(c=inner, digest=digest, constants_sigmas_cap=proof["constants_sigmas_cap"])
+    words = _words_from_oracle_proof(inner, proof, public_inputs)
+    outer, w, pis = fc.fri_verifier_circuit([(fake_prover, words, public_inputs)], max_queries=2)
+    names = {g.name.split(" ")[0] for g in outer.gates}
+    assert {"PoseidonGate", "CosetInterpolationGate", "RandomAccessGate", "ExponentiationGate", "ReducingGate", "ReducingExtensionGate",
+            "ArithmeticExtensionGate", "ArithmeticGate", "BaseSumGate", "PublicInputGate"} <= names
+    zs_pp = oracle.plonk_partial_products_and_zs(w[:80], outer.sigmas, outer.k_is, 8, [3, 5], [7, 11])
+    assert _violations(outer, w, zs_pp, cc.hash_no_pad(pis), [3, 5], [7, 11]) == []
+    proof2 = oracle.circuit_prove(outer, w, pis, digest)
+    plonk_verifier.verify(proof2, outer, proof2["constants_sigmas_cap"], digest, max_queries=1)
+    # the structure does not depend on the data: another inner proof of the same circuit gives the same constants and sigmas
+    wires_b, pis_b = cc.hash_chain_circuit(7, seed=13)[1:]
+    proof_b = oracle.circuit_prove(inner, wires_b, pis_b, digest)
+    outer_b, w_b, _ = fc.fri_verifier_circuit([(fake_prover, _words_from_oracle_proof(inner, proof_b, pis_b), pis_b)], max_queries=2)
+    assert (outer_b.constants == outer.constants).all() and (outer_b.sigmas == outer.sigmas).all() and not (w_b == w).all()
+    # tampering: a final-polynomial coefficient, an opened row value, a layer value -> no witness
+    from eth_tx_proof_b200 import wire
+
+    fri_start = words.size - 4 - proof["opening_proof"].size
+    for offset in (words.size - 4 - 3,            # final polynomial
+                   fri_start + 64 + 5,            # a value of the first opened row (after the one layer cap)
+                   fri_start + 64 + 84 + 4 * 6 + 135 + 4 * 6 + 20 + 4 * 6 + 16 + 4 * 6 + 3):  # a value of the layer row
+        bad = words.copy()
+        bad[offset] ^= np.uint64(1)
+        with pytest.raises(AssertionError):
+            fc.fri_verifier_circuit([(fake_prover, bad, public_inputs)], max_queries=1)

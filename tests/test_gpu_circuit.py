@@ -321,3 +321,23 @@ def test_recursive_merkle_verifier_chain(ctx):
     c2_, w2, pi2 = cc.recursive_merkle_verifier_circuit([(p1, proof1["words"], pi1)])
     p2 = cc.CircuitProver(ctx, c2_)
     plonk_verifier.verify(p2.prove(w2, pi2), c2_, p2.constants_sigmas_cap, p2.digest, max_queries=1)
+
+
+def test_fri_verifier_circuit_over_a_device_proof(ctx):
+    """The whole FRI verification (28 queries: Merkle openings, combine, per-layer consistency + interpolation, final
+    polynomial) of a device-made inner proof as an outer circuit (~2.7 k rows -> 2^12), proved on the device and verified;
+    and one more layer: the FRI verifier circuit of THAT proof."""
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(7, seed=15)
+    p0 = cc.CircuitProver(ctx, inner)
+    w0 = p0.prove_words(wires, public_inputs)
+    c1, w1, pi1 = fc.fri_verifier_circuit([(p0, w0, public_inputs)])
+    assert c1.degree_bits == 12
+    p1 = cc.CircuitProver(ctx, c1)
+    proof1 = p1.prove(w1, pi1)
+    plonk_verifier.verify(proof1, c1, p1.constants_sigmas_cap, p1.digest, max_queries=2)
+    c2, w2, pi2 = fc.fri_verifier_circuit([(p1, proof1["words"], pi1)], max_queries=4)
+    p2 = cc.CircuitProver(ctx, c2)
+    plonk_verifier.verify(p2.prove(w2, pi2), c2, p2.constants_sigmas_cap, p2.digest, max_queries=1)
