@@ -10,17 +10,17 @@ import numpy as np
 import torch
 
 import eth_tx_proof_b200 as etp
-from eth_tx_proof_b200 import circuit as cc, cprog, parallel, prover
+from eth_tx_proof_b200 import circuit as cc, cprog, fri_circuit as fc, parallel, prover
 
 tables, ctls = cprog.evm_shaped_system()
 ctx0 = etp.Context(0)
 base_c, base_w, base_pi = cc.hash_chain_circuit(12, seed=12)
 p_base = cc.CircuitProver(ctx0, base_c)
 w_base = p_base.prove_words(base_w, base_pi)
-layer = cc.recursive_merkle_verifier_circuit([(p_base, w_base, base_pi)])
+layer = fc.fri_verifier_circuit([(p_base, w_base, base_pi)])
 p_layer = cc.CircuitProver(ctx0, layer[0])
 w_layer = p_layer.prove_words(layer[1], layer[2])
-root = cc.recursive_merkle_verifier_circuit([(p_base, w_base, base_pi), (p_layer, w_layer, layer[2])])
+root = fc.fri_verifier_circuit([(p_base, w_base, base_pi), (p_layer, w_layer, layer[2])])
 print(f"layer circuit 2^{layer[0].degree_bits} rows, root circuit 2^{root[0].degree_bits} rows", flush=True)
 del p_base, p_layer
 circuits = {"layer": layer, "root": root}
