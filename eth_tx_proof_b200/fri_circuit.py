@@ -305,9 +305,10 @@ def fri_challenges_and_openings(prover, words: np.ndarray, public_inputs: Sequen
     ch.observe(prover.digest)
     ch.observe(cc.hash_no_pad(public_inputs))
     ch.observe_cap(p["wires_cap"])
-    ch.get_n_challenges(2 * cc.NUM_CHALLENGES)
+    plonk_betas = [int(x) for x in ch.get_n_challenges(cc.NUM_CHALLENGES)]
+    plonk_gammas = [int(x) for x in ch.get_n_challenges(cc.NUM_CHALLENGES)]
     ch.observe_cap(p["plonk_zs_partial_products_cap"])
-    ch.get_n_challenges(cc.NUM_CHALLENGES)
+    plonk_alphas = [int(x) for x in ch.get_n_challenges(cc.NUM_CHALLENGES)]
     ch.observe_cap(p["quotient_polys_cap"])
     zeta = [int(x) for x in ch.get_extension_challenge()]
     order = ("constants", "plonk_sigmas", "wires", "plonk_zs", "partial_products", "quotient_polys")
@@ -332,15 +333,22 @@ def fri_challenges_and_openings(prover, words: np.ndarray, public_inputs: Sequen
 
     batch0 = [v for k in order for v in op[k]]
     return {"header": h, "alpha": alpha, "betas": betas, "zeta": zeta, "reduced": [reduce(batch0), reduce(list(op["plonk_zs_next"]))],
+            "plonk_betas": plonk_betas, "plonk_gammas": plonk_gammas, "plonk_alphas": plonk_alphas,
+            "batch0": [(int(v[0]), int(v[1])) for v in batch0], "zs_next": [(int(v[0]), int(v[1])) for v in op["plonk_zs_next"]],
+            "pi_hash": [int(x) for x in p["public_inputs_hash"]],
             "final_poly": [(final[2 * i], final[2 * i + 1]) for i in range(h["final_poly_len"])],
             "openings": cc.fri_query_openings(prover, words, public_inputs)}
 
 
-def fri_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, min_degree_bits: int = 0):
+def fri_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, min_degree_bits: int = 0, vanishing: bool = False):
     """verify_fri_proof of the inner circuit proofs `[(CircuitProver, proof words, public inputs)]` as ONE outer circuit (module
     docstring): a 2^12-row inner proof costs ~3.8 k outer rows (2^12), two of them 2^13.  -> (Circuit, wires, public inputs of
     the outer circuit).  Building fails (AssertionError in connect / div_ext) when an inner proof's FRI part is not valid: no
-    witness exists."""
+    witness exists.
+    vanishing=True adds the PLONK part of the verifier (plonk/recursive_verifier.rs verify_with_challenges_circuit): the openings
+    become public inputs, the reduced openings are computed from them in-circuit, and the inner circuit's vanishing polynomial
+    is evaluated at zeta over the extension field — the inner circuit's recorded constraint program re-interpreted with
+    ArithmeticExtension operations — and checked against Z_H(zeta) * the reduced quotient chunks."""
     if isinstance(inner, tuple) and not isinstance(inner[0], tuple):
         inner = [inner]
     datas = [fri_challenges_and_openings(*x) for x in inner]
@@ -357,9 +365,14 @@ def fri_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, min_de
         layouts.append((len(pi_values), nq, per_query, openings))
         pi_values += [x for cp in caps for x in cp] + d["alpha"] + d["zeta"] + [x for be in d["betas"] for x in be] + \
             [x for r in d["reduced"] for x in r] + [x for cf in d["final_poly"] for x in cf] + indices
+        if vanishing:
+            pi_values += d["plonk_betas"] + d["plonk_gammas"] + d["plonk_alphas"] + d["pi_hash"] + \
+                [x for v in d["batch0"] for x in v] + [x for v in d["zs_next"] for x in v]
     all_pw = b.merkle.public_inputs(pi_values)
-    for d, (base, nq, per_query, openings) in zip(datas, layouts):
-        _verify_one(b, d, all_pw[base:], nq, per_query, openings)
+    for (prover, _, _), d, (base, nq, per_query, openings) in zip(inner, datas, layouts):
+        at = _verify_one(b, d, all_pw[base:], nq, per_query, openings)
+        if vanishing:
+            _verify_vanishing(b, prover.c, d, all_pw[base:], at, per_query)
     circuit, wires = b.build(min_degree_bits)
     return circuit, wires, list(b.public_inputs)
 
@@ -422,3 +435,62 @@ def _verify_one(b: GadgetBuilder, d: dict, pw: Sequence[Target], nq: int, per_qu
                 sx_t = b.mul(sx_t, sx_t)
         # final polynomial at subgroup_x
         b.connect_ext(b.reduce_ext((sx_t, b.zero), final_t), old)
+    return at + nq
+
+
+def _verify_vanishing(b: GadgetBuilder, inner_circuit, d: dict, pw: Sequence[Target], at: int, per_query: int):
+    """verify_with_challenges_circuit's PLONK check for one inner proof.  pw[at:] = plonk betas, gammas, alphas | pi_hash | the
+    zeta-batch openings (constants, sigmas, wires, zs, partial products, quotient chunks) | zs_next."""
+    h = d["header"]
+    K, n_bits = cc.NUM_CHALLENGES, h["degree_bits"]
+    ext_at = lambda k: (pw[k], pw[k + 1])
+    lift = lambda t: (t, b.zero)
+    betas_t, gammas_t, alphas_t = pw[at:at + K], pw[at + K:at + 2 * K], pw[at + 2 * K:at + 3 * K]
+    pi_hash_t = pw[at + 3 * K:at + 3 * K + 4]
+    at += 3 * K + 4
+    n0 = len(d["batch0"])
+    batch0_t = [ext_at(at + 2 * i) for i in range(n0)]
+    zs_next_t = [ext_at(at + 2 * n0 + 2 * i) for i in range(K)]
+    # the FRI part took the reduced openings as inputs: tie them to the openings (reduce with the FRI alpha, in-circuit)
+    base = 64 * per_query
+    alpha_t, zeta_t = ext_at(base), ext_at(base + 2)
+    red_at = base + 4 + 2 * h["n_fri_layers"]
+    b.connect_ext(b.reduce_ext(alpha_t, batch0_t), ext_at(red_at))
+    b.connect_ext(b.reduce_ext(alpha_t, zs_next_t), ext_at(red_at + 2))
+    # eval_vanishing_poly at zeta: the inner circuit's program over extension targets
+    n_q = K * cc.QUOTIENT_DEGREE_FACTOR
+    lv = batch0_t[:n0 - n_q] + [zeta_t]
+    nv = [None] * len(lv)
+    for i in range(K):
+        nv[inner_circuit.col_z(i)] = zs_next_t[i]
+    consts = {}
+
+    def lift_const(c):
+        c = int(c) % P
+        if c not in consts:
+            consts[c] = lift(b.constant(c))
+        return consts[c]
+
+    # PI / CH operands arrive as targets already; Program.evaluate calls lift() on them as well as on immediates
+    ops_lift = lambda x: x if isinstance(x, tuple) else lift_const(x)
+    out = inner_circuit.program.evaluate(lv, nv, pi=[lift(t) for t in pi_hash_t], ch=[lift(t) for t in list(betas_t) + list(gammas_t)],
+                                         add=lambda x, y: b.arith_ext(x, b.one_ext, y, 1, 1), sub=lambda x, y: b.sub_ext(x, y),
+                                         mul=lambda x, y: b.mul_ext(x, y), lift=ops_lift)
+    # L_0(zeta) = Z_H(zeta) / (n (zeta - 1)), Z_H(zeta) = zeta^n - 1
+    zeta_n = zeta_t
+    for _ in range(n_bits):
+        zeta_n = b.mul_ext(zeta_n, zeta_n)
+    z_h = b.sub_ext(zeta_n, b.one_ext)
+    n_t = lift_const(1 << n_bits)
+    l_0 = b.div_ext(z_h, b.mul_ext(n_t, b.sub_ext(zeta_t, b.one_ext)))
+    quot_t = batch0_t[n0 - n_q:]
+    for j in range(K):
+        a = lift(alphas_t[j])
+        acc = b.zero_ext
+        for kind, c in out:  # the consumer's fold: acc <- acc * alpha + c * multiplier
+            if kind == cc.cprog.EMIT_FIRST_ROW:
+                c = b.mul_ext(c, l_0)
+            acc = b.arith_ext(acc, a, c, 1, 1)
+        f = cc.QUOTIENT_DEGREE_FACTOR
+        reduced_q = b.reduce_ext(zeta_n, quot_t[j * f:(j + 1) * f])
+        b.connect_ext(b.mul_ext(z_h, reduced_q), acc)  # vanishing(zeta) == Z_H(zeta) * sum_k zeta^(n k) q_k(zeta)

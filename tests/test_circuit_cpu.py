@@ -364,3 +364,33 @@ def test_fri_verifier_circuit_on_a_real_proof():
         bad[offset] ^= np.uint64(1)
         with pytest.raises(AssertionError):
             fc.fri_verifier_circuit([(fake_prover, bad, public_inputs)], max_queries=1)
+
+
+def test_verifier_circuit_with_the_vanishing_polynomial_check():
+    """fri_verifier_circuit(vanishing=True): besides the FRI verification, the inner circuit's vanishing polynomial is evaluated
+    at zeta IN-CIRCUIT (its recorded program over extension targets), combined with the alphas and checked against
+    Z_H(zeta) * the reduced quotient chunks; the reduced openings the FRI part uses are computed from the openings in-circuit.
+    A changed opening or a changed quotient chunk has no witness."""
+    import types
+
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(6, seed=21)
+    digest = [7, 7, 7, 7]
+    proof = oracle.circuit_prove(inner, wires, public_inputs, digest)
+    fake_prover = types.SimpleNamespace(c=inner, digest=digest, constants_sigmas_cap=proof["constants_sigmas_cap"])
+    words = _words_from_oracle_proof(inner, proof, public_inputs)
+    outer, w, pis = fc.fri_verifier_circuit([(fake_prover, words, public_inputs)], max_queries=1, vanishing=True)
+    zs_pp = oracle.plonk_partial_products_and_zs(w[:80], outer.sigmas, outer.k_is, 8, [3, 5], [7, 11])
+    assert _violations(outer, w, zs_pp, cc.hash_no_pad(pis), [3, 5], [7, 11]) == []
+    proof2 = oracle.circuit_prove(outer, w, pis, digest)
+    plonk_verifier.verify(proof2, outer, proof2["constants_sigmas_cap"], digest, max_queries=1)
+    # openings start after the header and the three caps: [constants 4 | sigmas 80 | wires 135 | zs 2 | zs_next 2 | pps 18 | quotient 16] ext
+    first_opening = 24 + 3 * 64
+    for ext_index in (4 + 80 + 17, 4 + 80 + 135 + 2 + 2 + 18 + 3):  # a wire opening, a quotient chunk opening
+        bad = words.copy()
+        bad[first_opening + 2 * ext_index] ^= np.uint64(1)
+        with pytest.raises(AssertionError):
+            fc.fri_verifier_circuit([(fake_prover, bad, public_inputs)], max_queries=1, vanishing=True)
