@@ -524,24 +524,25 @@ def main():
     # ---- BASELINE "tx proofs/min", shape of the WHOLE transaction job of the reference (ops/src/lib.rs:52 generate_txn_proof ->
     # prove_root): the seven table STARKs above, then per table a chain of recursive wrapper / shrinking circuit proofs down to
     # the threshold degree, then one root circuit proof.  The circuit proofs are eth_tx_proof_b200/circuit.py proofs of the
-    # FRI-verification part of a recursive verifier over real inner proofs (see below); the reference's full recursive
+    # recursive verifier of this prover's circuit proofs over real inner proofs (see below); the reference's STARK-verifier and
     # verifier circuits are not available offline, the number of layers is a placeholder, witness generation is not included.
     tx_rec = None
     if not args.skip_stark and not args.skip_tx:
         from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
 
-        # The recursion circuits are REAL verifier circuits over real proofs (fri_circuit.fri_verifier_circuit): a base proof P0
-        # (2^12 rows), the circuit C1 that runs the whole FRI verification of P0 — 28 queries: Merkle openings, fri_combine_initial,
-        # per-layer consistency + compute_evaluation, final polynomial: ~3.8 k rows -> 2^12 — with its proof P1, and the root-shaped
-        # circuit over [P0, P1] (2^13).  Built once here, outside the timed region; every job then proves them with these
+        # The recursion circuits are REAL recursive verifiers over real proofs (fri_circuit.recursive_verifier_circuit): a base proof
+        # P0 (2^12 rows), the circuit C1 that verifies P0 completely — in-circuit challenger, proof of work, vanishing-polynomial
+        # check at zeta, the 28 FRI queries (Merkle openings, fri_combine_initial, per-layer consistency + compute_evaluation, final
+        # polynomial): ~5.1 k rows -> 2^13, the fixed-point size of this recursion — with its proof P1, and the root-shaped circuit
+        # that verifies both P0 and P1 (2^14).  Built once here, outside the timed region; every job then proves them with these
         # witnesses (witness generation is not part of the measurement).
         base_c, base_w, base_pi = cc.hash_chain_circuit(12, seed=12)
         p_base = cc.CircuitProver(ctx, base_c)
         w_base = p_base.prove_words(base_w, base_pi)
-        layer = fc.fri_verifier_circuit([(p_base, w_base, base_pi)])
+        layer = fc.recursive_verifier_circuit([(p_base, w_base, base_pi)])
         p_layer = cc.CircuitProver(ctx, layer[0])
         w_layer = p_layer.prove_words(layer[1], layer[2])
-        root = fc.fri_verifier_circuit([(p_base, w_base, base_pi), (p_layer, w_layer, layer[2])])
+        root = fc.recursive_verifier_circuit([(p_base, w_base, base_pi), (p_layer, w_layer, layer[2])])
         del p_base, p_layer
         chain_bits, root_bits = (layer[0].degree_bits,) * 3, root[0].degree_bits
         circuits = {"layer": layer, "root": root}
@@ -599,10 +600,10 @@ def main():
                                           "block proof on rank 0; wall clock, max over ranks"},
                   "workload": "synthetic transaction WITH recursion layers: 7 table STARKs + CTLs (as `tx`) + per table a chain of circuit "
                               f"proofs at 2^{chain_bits} rows + one root circuit proof at 2^{root_bits} rows = {len(tables) * len(chain_bits) + 1} "
-                              "circuit proofs (standard_recursion_config).  The circuits are real verifier circuits: each runs the whole FRI "
-                              "verification (28 queries: Merkle openings, combine, per-layer consistency + interpolation, final polynomial) of the "
-                              "proof(s) below it — a base proof, a proof of that verification, and a root over both; the in-circuit challenger, the "
-                              "proof-of-work and the vanishing-polynomial check of a full recursive verifier are not in them, the "
+                              "circuit proofs (standard_recursion_config).  The circuits are real recursive verifiers: each verifies the proof(s) "
+                              "below it completely (in-circuit challenger, proof of work, vanishing-polynomial check, 28 FRI queries) — a base proof, "
+                              "the verifier of that proof, and a root that verifies both; they verify circuit proofs of this prover, not the table "
+                              "STARKs (the STARK-verifier circuits of the reference are not built), the "
                               f"number of layers per table is a placeholder, witnesses are given; {n_txr} transactions (8 per GPU) over {world} GPU(s), {rec_contexts} contexts per GPU",
                   "tx_ms": txr_ms, "tx_per_min": n_txr * 60.0 / dt, "transactions": n_txr,
                   "timed": "tx_ms: one whole job on one context (table traces resident in HBM, circuit witnesses uploaded from the host inside) "

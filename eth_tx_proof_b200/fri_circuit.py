@@ -335,62 +335,239 @@ def fri_challenges_and_openings(prover, words: np.ndarray, public_inputs: Sequen
     return {"header": h, "alpha": alpha, "betas": betas, "zeta": zeta, "reduced": [reduce(batch0), reduce(list(op["plonk_zs_next"]))],
             "plonk_betas": plonk_betas, "plonk_gammas": plonk_gammas, "plonk_alphas": plonk_alphas,
             "batch0": [(int(v[0]), int(v[1])) for v in batch0], "zs_next": [(int(v[0]), int(v[1])) for v in op["plonk_zs_next"]],
-            "pi_hash": [int(x) for x in p["public_inputs_hash"]],
+            "pi_hash": [int(x) for x in p["public_inputs_hash"]], "pow_witness": fri[-1],
             "final_poly": [(final[2 * i], final[2 * i + 1]) for i in range(h["final_poly_len"])],
             "openings": cc.fri_query_openings(prover, words, public_inputs)}
 
 
+class _T:
+    """The targets one inner proof's verification reads (public-input wires or in-circuit challenger outputs)."""
+
+
+def _pi_layout(b: GadgetBuilder, d: dict, nq: int, with_challenges: bool, with_openings: bool):
+    """The public-input values of one inner proof, and a function that maps the wires back into a _T.
+    caps | [alpha | zeta | betas | reduced | indices] | final polynomial | [plonk betas, gammas, alphas] | pi_hash | [openings] | pow."""
+    h = d["header"]
+    per_query = 4 + h["n_fri_layers"]
+    openings = d["openings"][:nq * per_query]
+    caps = [tuple(int(x) for dg in openings[o][3] for x in dg) for o in range(per_query)]
+    indices = [openings[q * per_query][1] for q in range(nq)]
+    vals = [x for cp in caps for x in cp] + [x for cf in d["final_poly"] for x in cf] + d["pi_hash"] + [d["pow_witness"]]
+    if with_challenges:
+        vals += d["alpha"] + d["zeta"] + [x for be in d["betas"] for x in be] + indices
+        if with_openings:
+            vals += d["plonk_betas"] + d["plonk_gammas"] + d["plonk_alphas"]
+        else:
+            vals += [x for r in d["reduced"] for x in r]
+    if with_openings:
+        vals += [x for v in d["batch0"] for x in v] + [x for v in d["zs_next"] for x in v]
+
+    def assign(pw: Sequence[Target]) -> _T:
+        T = _T()
+        ext_at = lambda k: (pw[k], pw[k + 1])
+        T.caps = [pw[64 * o:64 * (o + 1)] for o in range(per_query)]
+        at = 64 * per_query
+        T.final = [ext_at(at + 2 * i) for i in range(len(d["final_poly"]))]
+        at += 2 * len(d["final_poly"])
+        T.pi_hash = pw[at:at + 4]
+        T.pow_witness = pw[at + 4]
+        at += 5
+        if with_challenges:
+            T.alpha, T.zeta = ext_at(at), ext_at(at + 2)
+            T.betas = [ext_at(at + 4 + 2 * i) for i in range(h["n_fri_layers"])]
+            at += 4 + 2 * h["n_fri_layers"]
+            T.index_t = pw[at:at + nq]
+            at += nq
+            if with_openings:
+                K = cc.NUM_CHALLENGES
+                T.plonk_betas, T.plonk_gammas, T.plonk_alphas = pw[at:at + K], pw[at + K:at + 2 * K], pw[at + 2 * K:at + 3 * K]
+                at += 3 * K
+            else:
+                T.reduced = [ext_at(at), ext_at(at + 2)]
+                at += 4
+        if with_openings:
+            n0 = len(d["batch0"])
+            T.batch0 = [ext_at(at + 2 * i) for i in range(n0)]
+            T.zs_next = [ext_at(at + 2 * n0 + 2 * i) for i in range(cc.NUM_CHALLENGES)]
+        return T
+
+    return vals, assign, per_query, openings
+
+
 def fri_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, min_degree_bits: int = 0, vanishing: bool = False):
     """verify_fri_proof of the inner circuit proofs `[(CircuitProver, proof words, public inputs)]` as ONE outer circuit (module
-    docstring): a 2^12-row inner proof costs ~3.8 k outer rows (2^12), two of them 2^13.  -> (Circuit, wires, public inputs of
-    the outer circuit).  Building fails (AssertionError in connect / div_ext) when an inner proof's FRI part is not valid: no
-    witness exists.
+    docstring), the challenges given as public inputs: a 2^12-row inner proof costs ~3.8 k outer rows (2^12), two of them 2^13.
+    -> (Circuit, wires, public inputs of the outer circuit).  Building fails (AssertionError in connect / div_ext) when an inner
+    proof's FRI part is not valid: no witness exists.
     vanishing=True adds the PLONK part of the verifier (plonk/recursive_verifier.rs verify_with_challenges_circuit): the openings
     become public inputs, the reduced openings are computed from them in-circuit, and the inner circuit's vanishing polynomial
     is evaluated at zeta over the extension field — the inner circuit's recorded constraint program re-interpreted with
-    ArithmeticExtension operations — and checked against Z_H(zeta) * the reduced quotient chunks."""
+    ArithmeticExtension operations — and checked against Z_H(zeta) * the reduced quotient chunks.
+    recursive_verifier_circuit derives the challenges in-circuit as well."""
     if isinstance(inner, tuple) and not isinstance(inner[0], tuple):
         inner = [inner]
     datas = [fri_challenges_and_openings(*x) for x in inner]
     b = GadgetBuilder()
-    # ---- public inputs, per inner proof: caps | alpha | zeta | betas | reduced openings | final polynomial | query indices
     layouts, pi_values = [], []
     for d in datas:
         h = d["header"]
         nq = h["num_queries"] if max_queries is None else min(max_queries, h["num_queries"])
-        per_query = 4 + h["n_fri_layers"]
-        openings = d["openings"][:nq * per_query]
-        caps = [tuple(int(x) for dg in openings[o][3] for x in dg) for o in range(per_query)]
-        indices = [openings[q * per_query][1] for q in range(nq)]
-        layouts.append((len(pi_values), nq, per_query, openings))
-        pi_values += [x for cp in caps for x in cp] + d["alpha"] + d["zeta"] + [x for be in d["betas"] for x in be] + \
-            [x for r in d["reduced"] for x in r] + [x for cf in d["final_poly"] for x in cf] + indices
-        if vanishing:
-            pi_values += d["plonk_betas"] + d["plonk_gammas"] + d["plonk_alphas"] + d["pi_hash"] + \
-                [x for v in d["batch0"] for x in v] + [x for v in d["zs_next"] for x in v]
+        vals, assign, per_query, openings = _pi_layout(b, d, nq, True, vanishing)
+        layouts.append((len(pi_values), assign, nq, per_query, openings))
+        pi_values += vals
     all_pw = b.merkle.public_inputs(pi_values)
-    for (prover, _, _), d, (base, nq, per_query, openings) in zip(inner, datas, layouts):
-        at = _verify_one(b, d, all_pw[base:], nq, per_query, openings)
+    for (prover, _, _), d, (base, assign, nq, per_query, openings) in zip(inner, datas, layouts):
+        T = assign(all_pw[base:])
+        log_lde = d["header"]["degree_bits"] + d["header"]["rate_bits"]
+        T.index = lambda q, T=T, log_lde=log_lde: (T.index_t[q], b.split_bits(T.index_t[q], log_lde))
         if vanishing:
-            _verify_vanishing(b, prover.c, d, all_pw[base:], at, per_query)
+            T.reduced = [b.reduce_ext(T.alpha, T.batch0), b.reduce_ext(T.alpha, T.zs_next)]
+        _fri_part(b, d, T, nq, per_query, openings)
+        if vanishing:
+            _plonk_part(b, prover.c, d, T)
     circuit, wires = b.build(min_degree_bits)
     return circuit, wires, list(b.public_inputs)
 
 
-def _verify_one(b: GadgetBuilder, d: dict, pw: Sequence[Target], nq: int, per_query: int, openings: Sequence[tuple]):
+class CircuitChallenger:
+    """plonky2 iop/challenger.rs RecursiveChallenger: the duplex sponge of the transcript as PoseidonGate rows (overwrite mode,
+    rate 8, challenges popped from the end of the 8-word output buffer) — the in-circuit twin of api.Challenger."""
+
+    def __init__(self, b: GadgetBuilder):
+        self.b = b
+        self.state = [b.zero] * 12
+        self.inp: List[Target] = []
+        self.out: List[Target] = []
+
+    def observe(self, targets: Sequence[Target]):
+        for t in targets:
+            self.out = []
+            self.inp.append(t)
+            if len(self.inp) == 8:
+                self._duplex()
+
+    def observe_ext(self, ts: Sequence[ExtTarget]):
+        self.observe([c for t in ts for c in t])
+
+    def _duplex(self):
+        b = self.b
+        ins = self.inp + self.state[len(self.inp):]
+        r = b.add_gate(b.merkle.pos, wires=cc.poseidon_gate_wires([b.val(t) for t in ins], 0))
+        b.connect((r, cc.PoseidonGate.WIRE_SWAP), b.zero)
+        for k, t in enumerate(ins):
+            b.connect((r, k), t)
+        self.state = [(r, 12 + k) for k in range(12)]
+        self.inp = []
+        self.out = self.state[:8]
+
+    def get_challenge(self) -> Target:
+        if self.inp or not self.out:
+            self._duplex()
+        return self.out.pop()
+
+    def get_n(self, n: int) -> List[Target]:
+        return [self.get_challenge() for _ in range(n)]
+
+    def get_ext(self) -> ExtTarget:
+        a = self.get_challenge()
+        return (a, self.get_challenge())
+
+
+def recursive_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, min_degree_bits: int = 0):
+    """The recursive verifier of circuit proofs (plonky2 plonk/recursive_verifier.rs verify_proof): the transcript replayed by an
+    in-circuit challenger (get_challenges: circuit digest, public-input hash, caps, openings, FRI caps, final polynomial,
+    proof-of-work witness -> betas, gammas, alphas, zeta, FRI alpha, FRI betas, the proof-of-work response, the query indices),
+    the proof-of-work check, the vanishing-polynomial check at zeta and the whole FRI verification.  Public inputs of the outer
+    circuit: the inner proof's public-input hash, caps, openings, final polynomial and proof-of-work witness; the queried rows
+    and paths are advice.  A 2^12-row inner proof gives a 2^13-row outer circuit.  max_queries < 28 builds a partial verifier
+    (the transcript still draws all the indices).  Building fails when the inner proof is not valid: no witness exists."""
+    if isinstance(inner, tuple) and not isinstance(inner[0], tuple):
+        inner = [inner]
+    datas = [fri_challenges_and_openings(*x) for x in inner]
+    b = GadgetBuilder()
+    layouts, pi_values = [], []
+    for d in datas:
+        h = d["header"]
+        nq = h["num_queries"] if max_queries is None else min(max_queries, h["num_queries"])
+        vals, assign, per_query, openings = _pi_layout(b, d, nq, False, True)
+        layouts.append((len(pi_values), assign, nq, per_query, openings))
+        pi_values += vals
+    all_pw = b.merkle.public_inputs(pi_values)
+    for (prover, _, _), d, (base, assign, nq, per_query, openings) in zip(inner, datas, layouts):
+        T = assign(all_pw[base:])
+        h = d["header"]
+        K, log_lde = cc.NUM_CHALLENGES, h["degree_bits"] + h["rate_bits"]
+        # ---- get_challenges in-circuit
+        ch = CircuitChallenger(b)
+        ch.observe([b.constant(x) for x in prover.digest])  # the inner circuit's digest: a constant of the outer circuit
+        ch.observe(T.pi_hash)
+        ch.observe(T.caps[1])
+        T.plonk_betas, T.plonk_gammas = ch.get_n(K), ch.get_n(K)
+        ch.observe(T.caps[2])
+        T.plonk_alphas = ch.get_n(K)
+        ch.observe(T.caps[3])
+        T.zeta = ch.get_ext()
+        ch.observe_ext(T.batch0)
+        ch.observe_ext(T.zs_next)
+        T.alpha = ch.get_ext()
+        T.betas = []
+        for layer in range(h["n_fri_layers"]):
+            ch.observe(T.caps[4 + layer])
+            T.betas.append(ch.get_ext())
+        ch.observe_ext(T.final)
+        ch.observe([T.pow_witness])
+        pow_response = ch.get_challenge()
+        index_challenges = ch.get_n(h["num_queries"])
+        for name, want in (("alpha", d["alpha"]), ("zeta", d["zeta"])):  # the in-circuit transcript == the host's
+            assert list(b.vale(getattr(T, name))) == want, name
+        # ---- proof of work: the response's top pow_bits bits are zero
+        lo_bits, hi_bit = _split_64(b, pow_response)
+        for t in lo_bits[64 - h["pow_bits"]:] + [hi_bit]:
+            b.connect(t, b.zero)
+        # ---- query indices: the low log_lde bits of the index challenges
+        def index(q, index_challenges=index_challenges, log_lde=log_lde):
+            lo, _ = _split_64(b, index_challenges[q])
+            bits = lo[:log_lde]
+            return b.bits_to_target(bits), bits
+
+        T.index = index
+        T.reduced = [b.reduce_ext(T.alpha, T.batch0), b.reduce_ext(T.alpha, T.zs_next)]
+        _fri_part(b, d, T, nq, per_query, openings)
+        _plonk_part(b, prover.c, d, T)
+    circuit, wires = b.build(min_degree_bits)
+    return circuit, wires, list(b.public_inputs)
+
+
+def _split_64(b: GadgetBuilder, t: Target):
+    """split_le(x, 64): two BaseSumGates (63 limbs + 1) recombined as low + 2^63 * high == x.  -> (63 low bits, the top bit).
+    (As upstream, the decomposition is not forced to be the canonical one of the two that exist for x < 2^64 - p.)"""
+    v = b.val(t)
+    lo = b.split_bits(b_advice := _advice(b, v & ((1 << 63) - 1)), 63)
+    hi = b.split_bits(_advice(b, v >> 63), 1)
+    b.connect(b.arith(b.bits_to_target(hi), b.constant(1 << 63), b_advice, 1, 1), t)
+    return lo, hi[0]
+
+
+def _advice(b: GadgetBuilder, v: int) -> Target:
+    """A fresh routed wire holding v (an operand slot of an ArithmeticGate row: v = v * 1 + 0 is constrained, v itself is free)."""
+    key = (1, 0)
+    slot = b._arith.get(key)
+    if slot is None or slot[1] == b.ar.num_ops:
+        slot = (b.add_gate(b.ar, constants=list(key)), 0)
+    r, i = slot
+    b._arith[key] = (r, i + 1)
+    b._set((r, 4 * i), v)
+    b._set((r, 4 * i + 1), 1, b.one)
+    b._set((r, 4 * i + 2), 0, b.zero)
+    b._set((r, 4 * i + 3), v)
+    return (r, 4 * i)
+
+
+def _fri_part(b: GadgetBuilder, d: dict, T: _T, nq: int, per_query: int, openings: Sequence[tuple]):
     h = d["header"]
     n_layers, arity_bits = h["n_fri_layers"], h["arity_bits"]
     log_lde = h["degree_bits"] + h["rate_bits"]
-    at = 64 * per_query
-    ext_at = lambda k: (pw[k], pw[k + 1])
-    alpha_t, zeta_t = ext_at(at), ext_at(at + 2)
-    beta_t = [ext_at(at + 4 + 2 * i) for i in range(n_layers)]
-    at += 4 + 2 * n_layers
-    reduced_t = [ext_at(at), ext_at(at + 2)]
-    at += 4
-    final_t = [ext_at(at + 2 * i) for i in range(len(d["final_poly"]))]
-    at += 2 * len(d["final_poly"])
-    index_t = pw[at:at + nq]
+    alpha_t, zeta_t, beta_t, reduced_t, final_t = T.alpha, T.zeta, T.betas, T.reduced, T.final
     # ---- per-proof values: zeta_next = g * zeta, alpha^2 (the shift of the first batch past the two openings of the second)
     g = cc.root_of_unity(h["degree_bits"])
     zeta_next_t = (b.mul_const(zeta_t[0], g), b.mul_const(zeta_t[1], g))
@@ -401,13 +578,12 @@ def _verify_one(b: GadgetBuilder, d: dict, pw: Sequence[Target], nq: int, per_qu
     points = [zeta_t, zeta_next_t]
     for q in range(nq):
         ops = openings[q * per_query:(q + 1) * per_query]
-        x_t = index_t[q]
-        bits = b.split_bits(x_t, log_lde)
+        x_t, bits = T.index(q)
         # fri_verify_initial_proof
         leaf_t = []
         for o in range(4):
             leaf, idx, sib, cap = ops[o]
-            it, lt = b.merkle.opening(leaf, idx, sib, cap, pw[64 * o:64 * (o + 1)])
+            it, lt = b.merkle.opening(leaf, idx, sib, cap, T.caps[o])
             b.connect(it, x_t)
             leaf_t.append(lt)
         # subgroup_x = g * w^rev(x_index)
@@ -424,7 +600,7 @@ def _verify_one(b: GadgetBuilder, d: dict, pw: Sequence[Target], nq: int, per_qu
             leaf, idx, sib, cap = ops[4 + layer]
             lo = arity_bits * layer
             within_bits = bits[lo:lo + arity_bits]
-            it, lt = b.merkle.opening(leaf, idx, sib, cap, pw[64 * (4 + layer):64 * (5 + layer)])
+            it, lt = b.merkle.opening(leaf, idx, sib, cap, T.caps[4 + layer])
             b.connect(it, b.bits_to_target(bits[lo + arity_bits:]))
             ev = [(lt[2 * k], lt[2 * k + 1]) for k in range(1 << arity_bits)]
             b.connect_ext(b.random_access_ext(b.bits_to_target(within_bits), ev), old)  # evals[x_index mod 16] == the previous value
@@ -435,29 +611,17 @@ def _verify_one(b: GadgetBuilder, d: dict, pw: Sequence[Target], nq: int, per_qu
                 sx_t = b.mul(sx_t, sx_t)
         # final polynomial at subgroup_x
         b.connect_ext(b.reduce_ext((sx_t, b.zero), final_t), old)
-    return at + nq
 
 
-def _verify_vanishing(b: GadgetBuilder, inner_circuit, d: dict, pw: Sequence[Target], at: int, per_query: int):
-    """verify_with_challenges_circuit's PLONK check for one inner proof.  pw[at:] = plonk betas, gammas, alphas | pi_hash | the
-    zeta-batch openings (constants, sigmas, wires, zs, partial products, quotient chunks) | zs_next."""
+def _plonk_part(b: GadgetBuilder, inner_circuit, d: dict, T: _T):
+    """verify_with_challenges_circuit's PLONK check for one inner proof: eval_vanishing_poly at zeta (the inner circuit's
+    recorded program over extension targets), the consumer's fold with the alphas, L_0(zeta), and
+    vanishing(zeta) == Z_H(zeta) * sum_k zeta^(n k) q_k(zeta) per challenge."""
     h = d["header"]
     K, n_bits = cc.NUM_CHALLENGES, h["degree_bits"]
-    ext_at = lambda k: (pw[k], pw[k + 1])
     lift = lambda t: (t, b.zero)
-    betas_t, gammas_t, alphas_t = pw[at:at + K], pw[at + K:at + 2 * K], pw[at + 2 * K:at + 3 * K]
-    pi_hash_t = pw[at + 3 * K:at + 3 * K + 4]
-    at += 3 * K + 4
-    n0 = len(d["batch0"])
-    batch0_t = [ext_at(at + 2 * i) for i in range(n0)]
-    zs_next_t = [ext_at(at + 2 * n0 + 2 * i) for i in range(K)]
-    # the FRI part took the reduced openings as inputs: tie them to the openings (reduce with the FRI alpha, in-circuit)
-    base = 64 * per_query
-    alpha_t, zeta_t = ext_at(base), ext_at(base + 2)
-    red_at = base + 4 + 2 * h["n_fri_layers"]
-    b.connect_ext(b.reduce_ext(alpha_t, batch0_t), ext_at(red_at))
-    b.connect_ext(b.reduce_ext(alpha_t, zs_next_t), ext_at(red_at + 2))
-    # eval_vanishing_poly at zeta: the inner circuit's program over extension targets
+    zeta_t, batch0_t, zs_next_t = T.zeta, T.batch0, T.zs_next
+    n0 = len(batch0_t)
     n_q = K * cc.QUOTIENT_DEGREE_FACTOR
     lv = batch0_t[:n0 - n_q] + [zeta_t]
     nv = [None] * len(lv)
@@ -473,7 +637,7 @@ def _verify_vanishing(b: GadgetBuilder, inner_circuit, d: dict, pw: Sequence[Tar
 
     # PI / CH operands arrive as targets already; Program.evaluate calls lift() on them as well as on immediates
     ops_lift = lambda x: x if isinstance(x, tuple) else lift_const(x)
-    out = inner_circuit.program.evaluate(lv, nv, pi=[lift(t) for t in pi_hash_t], ch=[lift(t) for t in list(betas_t) + list(gammas_t)],
+    out = inner_circuit.program.evaluate(lv, nv, pi=[lift(t) for t in T.pi_hash], ch=[lift(t) for t in list(T.plonk_betas) + list(T.plonk_gammas)],
                                          add=lambda x, y: b.arith_ext(x, b.one_ext, y, 1, 1), sub=lambda x, y: b.sub_ext(x, y),
                                          mul=lambda x, y: b.mul_ext(x, y), lift=ops_lift)
     # L_0(zeta) = Z_H(zeta) / (n (zeta - 1)), Z_H(zeta) = zeta^n - 1
@@ -481,11 +645,10 @@ def _verify_vanishing(b: GadgetBuilder, inner_circuit, d: dict, pw: Sequence[Tar
     for _ in range(n_bits):
         zeta_n = b.mul_ext(zeta_n, zeta_n)
     z_h = b.sub_ext(zeta_n, b.one_ext)
-    n_t = lift_const(1 << n_bits)
-    l_0 = b.div_ext(z_h, b.mul_ext(n_t, b.sub_ext(zeta_t, b.one_ext)))
+    l_0 = b.div_ext(z_h, b.mul_ext(lift_const(1 << n_bits), b.sub_ext(zeta_t, b.one_ext)))
     quot_t = batch0_t[n0 - n_q:]
     for j in range(K):
-        a = lift(alphas_t[j])
+        a = lift(T.plonk_alphas[j])
         acc = b.zero_ext
         for kind, c in out:  # the consumer's fold: acc <- acc * alpha + c * multiplier
             if kind == cc.cprog.EMIT_FIRST_ROW:

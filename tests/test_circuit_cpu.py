@@ -394,3 +394,35 @@ def test_verifier_circuit_with_the_vanishing_polynomial_check():
         bad[first_opening + 2 * ext_index] ^= np.uint64(1)
         with pytest.raises(AssertionError):
             fc.fri_verifier_circuit([(fake_prover, bad, public_inputs)], max_queries=1, vanishing=True)
+
+
+def test_recursive_verifier_circuit_with_the_in_circuit_challenger():
+    """recursive_verifier_circuit: the whole verifier — transcript by an in-circuit challenger (its alpha and zeta equal the
+    host's, its query-index bits open the right leaves), proof-of-work check, vanishing-polynomial check, FRI — over a CPU-made
+    inner proof; constraints hold, the oracle proves the outer circuit and the verifier accepts it; a different proof-of-work
+    witness or inner public-input hash has no witness."""
+    import types
+
+    import oracle
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
+
+    inner, wires, public_inputs = cc.hash_chain_circuit(6, seed=31)
+    digest = [2, 4, 6, 8]
+    proof = oracle.circuit_prove(inner, wires, public_inputs, digest)
+    fake_prover = types.SimpleNamespace(c=inner, digest=digest, constants_sigmas_cap=proof["constants_sigmas_cap"])
+    words = _words_from_oracle_proof(inner, proof, public_inputs)
+    outer, w, pis = fc.recursive_verifier_circuit([(fake_prover, words, public_inputs)], max_queries=2)
+    # public inputs: caps | final polynomial | pi_hash | pow witness | openings — no challenge among them
+    assert len(pis) == 64 * 5 + 2 * 4 + 4 + 1 + 2 * (4 + 80 + 135 + 2 + 18 + 16 + 2)
+    zs_pp = oracle.plonk_partial_products_and_zs(w[:80], outer.sigmas, outer.k_is, 8, [3, 5], [7, 11])
+    assert _violations(outer, w, zs_pp, cc.hash_no_pad(pis), [3, 5], [7, 11]) == []
+    proof2 = oracle.circuit_prove(outer, w, pis, digest)
+    plonk_verifier.verify(proof2, outer, proof2["constants_sigmas_cap"], digest, max_queries=1)
+    bad = words.copy()
+    bad[words.size - 5] ^= np.uint64(1)  # the proof-of-work witness: the response loses its leading zeros (and the indices move)
+    with pytest.raises(AssertionError):
+        fc.recursive_verifier_circuit([(fake_prover, bad, public_inputs)], max_queries=1)
+    with pytest.raises(AssertionError):  # another circuit digest: the in-circuit transcript diverges from the proof's
+        other = types.SimpleNamespace(c=inner, digest=[1, 1, 1, 1], constants_sigmas_cap=proof["constants_sigmas_cap"])
+        fc.recursive_verifier_circuit([(other, words, public_inputs)], max_queries=1)

@@ -341,3 +341,33 @@ def test_fri_verifier_circuit_over_a_device_proof(ctx):
     c2, w2, pi2 = fc.fri_verifier_circuit([(p1, proof1["words"], pi1)], max_queries=4)
     p2 = cc.CircuitProver(ctx, c2)
     plonk_verifier.verify(p2.prove(w2, pi2), c2, p2.constants_sigmas_cap, p2.digest, max_queries=1)
+
+
+def test_recursive_verifier_chain_reaches_a_fixed_point_on_the_device(ctx):
+    """A complete recursion chain on the device: P0 proves a base circuit; C1 = the recursive verifier of P0 (in-circuit
+    challenger, proof-of-work, vanishing-polynomial check, all 28 FRI queries) is proved (P1); C2 = the recursive verifier of P1
+    is proved (P2) — C1 and C2 are both 2^13-row circuits (the size is a fixed point of the recursion).  Every proof is
+    accepted by the independent Python verifier."""
+    import plonk_verifier
+    from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
+
+    base, wires, public_inputs = cc.hash_chain_circuit(12, seed=41)
+    p0 = cc.CircuitProver(ctx, base)
+    w0 = p0.prove_words(wires, public_inputs)
+    c1, w1, pi1 = fc.recursive_verifier_circuit([(p0, w0, public_inputs)])
+    assert c1.degree_bits == 13
+    p1 = cc.CircuitProver(ctx, c1)
+    proof1 = p1.prove(w1, pi1)
+    plonk_verifier.verify(proof1, c1, p1.constants_sigmas_cap, p1.digest, max_queries=1)
+    c2, w2, pi2 = fc.recursive_verifier_circuit([(p1, proof1["words"], pi1)])
+    assert c2.degree_bits == 13
+    p2 = cc.CircuitProver(ctx, c2)
+    proof2 = p2.prove(w2, pi2)
+    plonk_verifier.verify(proof2, c2, p2.constants_sigmas_cap, p2.digest, max_queries=1)
+    # the layer's circuit is data-independent: the verifier of ANOTHER proof of C1 is the same circuit, so p2 proves it too
+    wires_b, pis_b = cc.hash_chain_circuit(12, seed=42)[1:]
+    c1b, w1b, pi1b = fc.recursive_verifier_circuit([(p0, p0.prove_words(wires_b, pis_b), pis_b)])
+    assert (c1b.constants == c1.constants).all() and (c1b.sigmas == c1.sigmas).all()
+    c2b, w2b, pi2b = fc.recursive_verifier_circuit([(p1, p1.prove_words(w1b, pi1b), pi1b)])
+    assert (c2b.constants == c2.constants).all() and (c2b.sigmas == c2.sigmas).all()
+    plonk_verifier.verify(p2.prove(w2b, pi2b), c2, p2.constants_sigmas_cap, p2.digest, max_queries=1)

@@ -17,10 +17,10 @@ ctx0 = etp.Context(0)
 base_c, base_w, base_pi = cc.hash_chain_circuit(12, seed=12)
 p_base = cc.CircuitProver(ctx0, base_c)
 w_base = p_base.prove_words(base_w, base_pi)
-layer = fc.fri_verifier_circuit([(p_base, w_base, base_pi)])
+layer = fc.recursive_verifier_circuit([(p_base, w_base, base_pi)])
 p_layer = cc.CircuitProver(ctx0, layer[0])
 w_layer = p_layer.prove_words(layer[1], layer[2])
-root = fc.fri_verifier_circuit([(p_base, w_base, base_pi), (p_layer, w_layer, layer[2])])
+root = fc.recursive_verifier_circuit([(p_base, w_base, base_pi), (p_layer, w_layer, layer[2])])
 print(f"layer circuit 2^{layer[0].degree_bits} rows, root circuit 2^{root[0].degree_bits} rows", flush=True)
 del p_base, p_layer
 circuits = {"layer": layer, "root": root}
