@@ -949,18 +949,22 @@ class CircuitBuilder:
 
 
 def hash_chain_circuit(degree_bits: int, seed: int = 1, poseidon_fraction: float = 0.6, arithmetic_fraction: float = 0.3, all_gates: bool = False,
-                       extra_rows: int = 1):
+                       extra_rows: int = 1, witness_seed: int = None):
     """A recursion-verifier-shaped synthetic circuit with its witness: the public inputs are hashed in-circuit (PoseidonGate
     row wired to the PublicInputGate), a Merkle-path-like chain of swapped PoseidonGates, chains of ArithmeticGate operations,
     constants through a ConstantGate — all linked by copy constraints — padded with NoopGates to 2^degree_bits rows.
     all_gates: also `extra_rows` rows of each of ArithmeticExtension, MulExtension, BaseSum, Exponentiation (its exponent bits wired
     to the base-sum limbs), Reducing, ReducingExtension, RandomAccess, PoseidonMds and CosetInterpolation gates (selector groups by
 upstream's greedy rule).
+    witness_seed: the gate constants (the circuit) come from `seed`, every witness value from `witness_seed` — different
+    witnesses of ONE circuit; None: one stream for both.
     -> (Circuit, wires (135, n), public_inputs)"""
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed if witness_seed is None else (seed, witness_seed))
+    rng_c = rng if witness_seed is None else np.random.default_rng(seed)
     n = 1 << degree_bits
     cb = CircuitBuilder()
     rnd = lambda: int(rng.integers(0, 2**63)) % P
+    rnd_c = lambda: int(rng_c.integers(0, 2**63)) % P
     public_inputs = [rnd() for _ in range(8)]
     cb.public_inputs = list(public_inputs)
     pi_hash = hash_no_pad(public_inputs)
@@ -990,7 +994,7 @@ upstream's greedy rule).
     ar = ArithmeticGate(20)
     prev = None
     for _ in range(n_ar):
-        c0, c1 = rnd(), rnd()
+        c0, c1 = rnd_c(), rnd_c()
         w = [0] * (4 * ar.num_ops)
         r = len(cb.rows)
         links = []
@@ -1007,7 +1011,7 @@ upstream's greedy rule).
             cb.connect(a, b_)
     if all_gates:  # a few rows of every other gate of the recursive verifier's gate set (CosetInterpolationGate excepted)
         for _ in range(extra_rows):
-            c0, c1 = rnd(), rnd()
+            c0, c1 = rnd_c(), rnd_c()
             g = ArithmeticExtensionGate(10)
             r_ae = cb.add_gate(g, constants=[c0, c1], wires=g.witness(rnd, c0, c1))
             g = MulExtensionGate(13)
@@ -1029,7 +1033,7 @@ upstream's greedy rule).
             cb.add_gate(ReducingGate(43), wires=ReducingGate(43).witness(rnd))
             cb.add_gate(ReducingExtensionGate(32), wires=ReducingExtensionGate(32).witness(rnd))
             g = RandomAccessGate(4, 4, 2)
-            e0, e1 = rnd(), rnd()
+            e0, e1 = rnd_c(), rnd_c()
             cb.add_gate(g, constants=[e0, e1], wires=g.witness(rnd, rng, [e0, e1]))
             cb.add_gate(PoseidonMdsGate(), wires=PoseidonMdsGate().witness(rnd))
             g = CosetInterpolationGate.with_max_degree(4, QUOTIENT_DEGREE_FACTOR)  # degree 6, two intermediate (eval, prod) pairs

@@ -351,7 +351,7 @@ def test_recursive_verifier_chain_reaches_a_fixed_point_on_the_device(ctx):
     import plonk_verifier
     from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
 
-    base, wires, public_inputs = cc.hash_chain_circuit(12, seed=41)
+    base, wires, public_inputs = cc.hash_chain_circuit(12, seed=41, witness_seed=1)
     p0 = cc.CircuitProver(ctx, base)
     w0 = p0.prove_words(wires, public_inputs)
     c1, w1, pi1 = fc.recursive_verifier_circuit([(p0, w0, public_inputs)])
@@ -365,9 +365,14 @@ def test_recursive_verifier_chain_reaches_a_fixed_point_on_the_device(ctx):
     proof2 = p2.prove(w2, pi2)
     plonk_verifier.verify(proof2, c2, p2.constants_sigmas_cap, p2.digest, max_queries=1)
     # the layer's circuit is data-independent: the verifier of ANOTHER proof of C1 is the same circuit, so p2 proves it too
-    wires_b, pis_b = cc.hash_chain_circuit(12, seed=42)[1:]
+    base_b, wires_b, pis_b = cc.hash_chain_circuit(12, seed=41, witness_seed=2)  # another witness of the SAME base circuit
+    assert (base_b.constants == base.constants).all() and (base_b.sigmas == base.sigmas).all() and not (wires_b == wires).all()
     c1b, w1b, pi1b = fc.recursive_verifier_circuit([(p0, p0.prove_words(wires_b, pis_b), pis_b)])
     assert (c1b.constants == c1.constants).all() and (c1b.sigmas == c1.sigmas).all()
     c2b, w2b, pi2b = fc.recursive_verifier_circuit([(p1, p1.prove_words(w1b, pi1b), pi1b)])
     assert (c2b.constants == c2.constants).all() and (c2b.sigmas == c2.sigmas).all()
     plonk_verifier.verify(p2.prove(w2b, pi2b), c2, p2.constants_sigmas_cap, p2.digest, max_queries=1)
+    # and an INVALID inner proof (a witness of a different circuit) is rejected by the recursive verifier: no witness
+    wrong = cc.hash_chain_circuit(12, seed=43)
+    with pytest.raises(AssertionError, match="copy constraint"):
+        fc.recursive_verifier_circuit([(p0, p0.prove_words(wrong[1], wrong[2]), wrong[2])])
