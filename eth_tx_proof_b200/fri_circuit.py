@@ -468,6 +468,13 @@ class CircuitChallenger:
     def get_n(self, n: int) -> List[Target]:
         return [self.get_challenge() for _ in range(n)]
 
+    def compact(self) -> List[Target]:
+        """RecursiveChallenger::compact: absorb what is buffered, drop the unused outputs -> the 12 sponge-state targets."""
+        if self.inp:
+            self._duplex()
+        self.out = []
+        return list(self.state)
+
     def get_ext(self) -> ExtTarget:
         a = self.get_challenge()
         return (a, self.get_challenge())
@@ -495,47 +502,54 @@ def recursive_verifier_circuit(inner: Sequence[tuple], max_queries: int = None, 
     all_pw = b.merkle.public_inputs(pi_values)
     for (prover, _, _), d, (base, assign, nq, per_query, openings) in zip(inner, datas, layouts):
         T = assign(all_pw[base:])
-        h = d["header"]
-        K, log_lde = cc.NUM_CHALLENGES, h["degree_bits"] + h["rate_bits"]
-        # ---- get_challenges in-circuit
-        ch = CircuitChallenger(b)
-        ch.observe([b.constant(x) for x in prover.digest])  # the inner circuit's digest: a constant of the outer circuit
-        ch.observe(T.pi_hash)
-        ch.observe(T.caps[1])
-        T.plonk_betas, T.plonk_gammas = ch.get_n(K), ch.get_n(K)
-        ch.observe(T.caps[2])
-        T.plonk_alphas = ch.get_n(K)
-        ch.observe(T.caps[3])
-        T.zeta = ch.get_ext()
-        ch.observe_ext(T.batch0)
-        ch.observe_ext(T.zs_next)
-        T.alpha = ch.get_ext()
-        T.betas = []
-        for layer in range(h["n_fri_layers"]):
-            ch.observe(T.caps[4 + layer])
-            T.betas.append(ch.get_ext())
-        ch.observe_ext(T.final)
-        ch.observe([T.pow_witness])
-        pow_response = ch.get_challenge()
-        index_challenges = ch.get_n(h["num_queries"])
-        for name, want in (("alpha", d["alpha"]), ("zeta", d["zeta"])):  # the in-circuit transcript == the host's
-            assert list(b.vale(getattr(T, name))) == want, name
-        # ---- proof of work: the response's top pow_bits bits are zero
-        lo_bits, hi_bit = _split_64(b, pow_response)
-        for t in lo_bits[64 - h["pow_bits"]:] + [hi_bit]:
-            b.connect(t, b.zero)
-        # ---- query indices: the low log_lde bits of the index challenges
-        def index(q, index_challenges=index_challenges, log_lde=log_lde):
-            lo, _ = _split_64(b, index_challenges[q])
-            bits = lo[:log_lde]
-            return b.bits_to_target(bits), bits
-
-        T.index = index
-        T.reduced = [b.reduce_ext(T.alpha, T.batch0), b.reduce_ext(T.alpha, T.zs_next)]
-        _fri_part(b, d, T, nq, per_query, openings)
-        _plonk_part(b, prover.c, d, T)
+        verify_circuit_proof_in_circuit(b, prover, d, T, nq, per_query, openings)
     circuit, wires = b.build(min_degree_bits)
     return circuit, wires, list(b.public_inputs)
+
+
+def verify_circuit_proof_in_circuit(b: "GadgetBuilder", prover, d: dict, T: "_T", nq: int, per_query: int, openings: Sequence[tuple]):
+    """verify_proof for ONE inner circuit proof on the builder `b`: T holds the targets of the proof's caps, openings, final
+    polynomial, public-input hash and proof-of-work witness (public inputs of the outer circuit, or advice when the caller
+    publishes something else — stark_circuit.root_circuit); everything else is derived in-circuit."""
+    h = d["header"]
+    K, log_lde = cc.NUM_CHALLENGES, h["degree_bits"] + h["rate_bits"]
+    # ---- get_challenges in-circuit
+    ch = CircuitChallenger(b)
+    ch.observe([b.constant(x) for x in prover.digest])  # the inner circuit's digest: a constant of the outer circuit
+    ch.observe(T.pi_hash)
+    ch.observe(T.caps[1])
+    T.plonk_betas, T.plonk_gammas = ch.get_n(K), ch.get_n(K)
+    ch.observe(T.caps[2])
+    T.plonk_alphas = ch.get_n(K)
+    ch.observe(T.caps[3])
+    T.zeta = ch.get_ext()
+    ch.observe_ext(T.batch0)
+    ch.observe_ext(T.zs_next)
+    T.alpha = ch.get_ext()
+    T.betas = []
+    for layer in range(h["n_fri_layers"]):
+        ch.observe(T.caps[4 + layer])
+        T.betas.append(ch.get_ext())
+    ch.observe_ext(T.final)
+    ch.observe([T.pow_witness])
+    pow_response = ch.get_challenge()
+    index_challenges = ch.get_n(h["num_queries"])
+    for name, want in (("alpha", d["alpha"]), ("zeta", d["zeta"])):  # the in-circuit transcript == the host's
+        assert list(b.vale(getattr(T, name))) == want, name
+    # ---- proof of work: the response's top pow_bits bits are zero
+    lo_bits, hi_bit = _split_64(b, pow_response)
+    for t in lo_bits[64 - h["pow_bits"]:] + [hi_bit]:
+        b.connect(t, b.zero)
+    # ---- query indices: the low log_lde bits of the index challenges
+    def index(q, index_challenges=index_challenges, log_lde=log_lde):
+        lo, _ = _split_64(b, index_challenges[q])
+        bits = lo[:log_lde]
+        return b.bits_to_target(bits), bits
+
+    T.index = index
+    T.reduced = [b.reduce_ext(T.alpha, T.batch0), b.reduce_ext(T.alpha, T.zs_next)]
+    _fri_part(b, d, T, nq, per_query, openings)
+    _plonk_part(b, prover.c, d, T)
 
 
 def _split_64(b: GadgetBuilder, t: Target):

@@ -54,7 +54,7 @@ static int fri_total_arities(const orc_fri_params *p) { int t = 0; for (int i = 
 /* Program-defined tables (constraint programs, format of eth_tx_proof_b200/csrc/cprog.h restated here): the oracle
  * INTERPRETS the program op by op; the product compiles it with NVRTC.  ids >= 16.
  * starky/src/lookup.rs Column / Filter / Lookup and starky/src/cross_table_lookup.rs CtlZData, as data: */
-#define ORC_MAX_TABLES 1024
+#define ORC_MAX_TABLES 8192
 #define CPROG_MAGIC 0x3147525043505445ULL
 #define AUXSPEC_MAGIC 0x3153585541505445ULL /* "ETPAUXS1" */
 enum { OP_CONST = 0, OP_LV, OP_NV, OP_LA, OP_NA, OP_PI, OP_CH, OP_ADD, OP_SUB, OP_MUL, OP_EMIT, OP_EMIT_TRANSITION, OP_EMIT_FIRST,
