@@ -125,6 +125,7 @@ def load_library():
         "etp_ctx_trim": (i32, [vp]),
         "etp_ctx_cached_bytes": (C.c_size_t, [vp]),
         "etp_host_poseidon_permute": (None, [C.POINTER(C.c_uint64)]),
+        "etp_host_poseidon_gate_wires": (None, [C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_uint64)]),
         "etp_bench_pipe_rates": (i32, [vp, C.POINTER(C.c_double)]),
         "etp_host_pin": (i32, [vp, vp, sz]),
         "etp_host_unpin": (i32, [vp, vp]),

@@ -206,7 +206,18 @@ def partial_rounds_fast(state, ring, sbox_in_hook=None):
 
 def poseidon_gate_wires(inputs: Sequence[int], swap: int) -> List[int]:
     """All 135 wires of one PoseidonGate row (gates/poseidon.rs PoseidonGenerator::run_once): inputs, outputs, swap, deltas
-    and the S-box inputs of every round after the first."""
+    and the S-box inputs of every round after the first.  Computed by the library's host code (etp_host_poseidon_gate_wires:
+    a recursion layer's witness is tens of thousands of these rows); poseidon_gate_wires_py is the same in Python integers."""
+    import ctypes as C
+
+    a = (C.c_uint64 * 12)(*[int(x) % P for x in inputs])
+    out = (C.c_uint64 * NUM_WIRES)()
+    load_library().etp_host_poseidon_gate_wires(a, int(swap), out)
+    return list(out)
+
+
+def poseidon_gate_wires_py(inputs: Sequence[int], swap: int) -> List[int]:
+    """poseidon_gate_wires restated with Python integers (the definition the C helper is tested against)."""
     rc, _, _ = _pc()
     w = [0] * NUM_WIRES
     inputs = [int(x) % P for x in inputs]

@@ -127,6 +127,49 @@ extern "C" void etp_host_poseidon_permute(uint64_t s[12]) {
   permute<mds_scalar>(s);
 }
 
+// Witness of one PoseidonGate row (plonky2/src/gates/poseidon.rs PoseidonGenerator::run_once; wire layout of
+// eth_tx_proof_b200/circuit.py PoseidonGate): inputs 0..11, outputs 12..23, swap 24, deltas 25..28, the S-box inputs of full
+// rounds 1..3 at 29 + 12 (r - 1) + i, of the 22 partial rounds at 65 + r, of the last four full rounds at 87 + 12 r + i.
+// The recursion layers' circuits are mostly PoseidonGate rows (Merkle paths, sponges, the in-circuit challenger), so their
+// witness generation is this function called a few ten thousand times.  All values canonical.
+extern "C" void etp_host_poseidon_gate_wires(const uint64_t inputs[12], int swap, uint64_t wires_out[135]) {
+  const auto canon = [](uint64_t x) { return x >= P ? x - P : x; };
+  uint64_t in[12], s[12];
+  memset(wires_out, 0, 135 * sizeof(uint64_t));
+  for (int i = 0; i < 12; i++) wires_out[i] = s[i] = in[i] = canon(inputs[i]);
+  wires_out[24] = swap ? 1 : 0;
+  for (int i = 0; i < 4; i++) {
+    const uint64_t delta = swap ? canon(add_canonical(in[i + 4], in[i] ? P - in[i] : 0)) : 0;
+    wires_out[25 + i] = delta;
+    s[i] = canon(add_canonical(in[i], delta));
+    s[i + 4] = canon(add_canonical(in[i + 4], delta ? P - delta : 0));
+  }
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+#else
+  const bool avx2 = false;
+#endif
+  const uint64_t* rc = RC;
+  for (int r = 0; r < 30; r++, rc += 12) {
+    for (int i = 0; i < 12; i++) s[i] = canon(add_canonical(s[i], rc[i]));
+    if (r < 4 || r >= 26) {
+      if (r >= 1 && r < 4)
+        for (int i = 0; i < 12; i++) wires_out[29 + 12 * (r - 1) + i] = s[i];
+      if (r >= 26)
+        for (int i = 0; i < 12; i++) wires_out[87 + 12 * (r - 26) + i] = s[i];
+      for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+    } else {
+      wires_out[65 + (r - 4)] = s[0];
+      s[0] = sbox7(s[0]);
+    }
+#if defined(__x86_64__)
+    if (avx2) mds_avx2(s); else
+#endif
+    mds_scalar(s);
+  }
+  for (int i = 0; i < 12; i++) wires_out[12 + i] = canon(s[i]);
+}
+
 // The parameters of the permutation, for callers that build circuits over it (plonky2's PoseidonGate evaluates the
 // permutation symbolically): ALL_ROUND_CONSTANTS (30 x 12), MDS_MATRIX_CIRC, MDS_MATRIX_DIAG.
 extern "C" void etp_poseidon_constants(uint64_t round_constants_out[360], uint64_t mds_circ_out[12], uint64_t mds_diag_out[12]) {

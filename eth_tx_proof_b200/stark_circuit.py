@@ -42,8 +42,8 @@ import numpy as np
 from . import circuit as cc
 from . import cprog, wire
 from .circuit import NoopGate, P
-from .fri_circuit import (CircuitChallenger, ExtTarget, GadgetBuilder, Target, _bitrev, _fri_part, _pi_layout, _plonk_part, _split_64,
-                          fri_challenges_and_openings, verify_circuit_proof_in_circuit)
+from .fri_circuit import (CircuitChallenger, ExtTarget, GadgetBuilder, Target, _bitrev, _pi_layout, _split_64, fri_challenges_and_openings,
+                          verify_circuit_proof_in_circuit)
 
 NUM_CHALLENGES = 2  # StarkConfig::standard_fast_config()
 
@@ -296,10 +296,7 @@ def stark_wrapper_circuit(program: cprog.Program, words, init_challenger_state=N
     -> (Circuit, wires, public inputs).  The structure (gates, constants, sigmas) depends on the table and the degree only."""
     b = GadgetBuilder()
     W = verify_stark_proof_in_circuit(b, program, words, init_challenger_state, ctl_challenges, max_queries)
-    targets = W.flat()
-    pw = b.merkle.public_inputs([b.val(t) for t in targets])
-    for w_, t in zip(pw, targets):
-        b.connect(w_, t)
+    _publish(b, W.flat())
     circuit, wires = b.build(min_degree_bits)
     return circuit, wires, list(b.public_inputs)
 
@@ -322,33 +319,55 @@ def verify_cross_table_lookups_circuit(b: GadgetBuilder, ctls: Sequence[tuple], 
         assert next(it, None) is None, "unused ctl_zs_first openings"
 
 
+def verify_circuit_proof_with_public_inputs(b: GadgetBuilder, prover, words, inner_pis: Sequence[int], max_queries: int = None) -> List[Target]:
+    """verify_proof of ONE inner circuit proof with the proof body as advice and the inner circuit's constants / sigmas cap as
+    constants of the outer circuit (verifier data); the inner public inputs become advice targets, re-hashed in-circuit and tied
+    to the proof's public-input hash.  -> the targets of the inner public inputs (for the caller to publish or to link)."""
+    d = fri_challenges_and_openings(prover, words, inner_pis)
+    nq = d["header"]["num_queries"] if max_queries is None else min(max_queries, d["header"]["num_queries"])
+    vals, assign, per_query, openings = _pi_layout(b, d, nq, False, True)
+    T = assign(advice(b, vals))
+    for t in T.caps[0]:
+        b.connect(t, b.constant(b.val(t)))
+    verify_circuit_proof_in_circuit(b, prover, d, T, nq, per_query, openings)
+    pis_t = advice(b, inner_pis)
+    r_h, entered = b.merkle.sponge([b.val(t) for t in pis_t])
+    for e, t in zip(entered, pis_t):
+        b.connect(e, t)
+    for i in range(4):
+        b.connect((r_h, 12 + i), T.pi_hash[i])
+    return pis_t
+
+
+def _publish(b: GadgetBuilder, targets: Sequence[Target]):
+    pw = b.merkle.public_inputs([b.val(t) for t in targets])
+    for w_, t in zip(pw, targets):
+        b.connect(w_, t)
+
+
+def shrink_circuit(inner: tuple, max_queries: int = None, min_degree_bits: int = 0):
+    """One shrinking step (fixed_recursive_verifier.rs shrinking_config wrappers: `add_virtual_proof_with_pis`, `verify_proof`,
+    `register_public_inputs(&proof_with_pis.public_inputs)`): verifies `(CircuitProver, proof words, public inputs)` and has the
+    SAME public inputs, so the chain wrapper -> shrink -> ... -> root keeps exposing trace cap, CTL openings and challenger
+    states.  Whatever the inner size, the result is a 2^13-row circuit (the recursion's fixed point)."""
+    b = GadgetBuilder()
+    _publish(b, verify_circuit_proof_with_public_inputs(b, inner[0], inner[1], inner[2], max_queries))
+    circuit, wires = b.build(min_degree_bits)
+    return circuit, wires, list(b.public_inputs)
+
+
 def root_circuit(wrappers: Sequence[tuple], layouts: Sequence[dict], ctls: Sequence[tuple], public_values: Sequence[int] = (),
                  max_queries: int = None, min_degree_bits: int = 0):
-    """create_root_circuit: verifies the wrapper proofs `[(CircuitProver, proof words, public inputs)]` of ALL tables of one
-    transaction (in table order) and links them (module docstring).  layouts[t] = wrapper_public_input_layout of table t
-    (multi-table form).  Public inputs of the root: every trace cap ++ public_values ++ the CTL challenges.
-    -> (Circuit, wires, public inputs)."""
+    """create_root_circuit: verifies the (wrapped and possibly shrunk) proofs `[(CircuitProver, proof words, public inputs)]` of
+    ALL tables of one transaction (in table order) and links them (module docstring).  layouts[t] =
+    wrapper_public_input_layout of table t (multi-table form).  Public inputs of the root: every trace cap ++ public_values ++
+    the CTL challenges.  -> (Circuit, wires, public inputs)."""
     b = GadgetBuilder()
-    datas = [fri_challenges_and_openings(*x) for x in wrappers]
-    # the wrapper proofs' bodies are advice here too; what the root publishes is assembled at the end
     Ws = []
-    for (prover, _, inner_pis), d, lay in zip(wrappers, datas, layouts):
-        nq = d["header"]["num_queries"] if max_queries is None else min(max_queries, d["header"]["num_queries"])
-        vals, assign, per_query, openings = _pi_layout(b, d, nq, False, True)
-        T = assign(advice(b, vals))
-        for t in T.caps[0]:  # the wrapper circuit's constants / sigmas cap is verifier data: a constant of the root
-            b.connect(t, b.constant(b.val(t)))
-        verify_circuit_proof_in_circuit(b, prover, d, T, nq, per_query, openings)
-        # the wrapper's public inputs: advice, re-hashed and tied to the proof's public-input hash
+    for (prover, words, inner_pis), lay in zip(wrappers, layouts):
         assert len(inner_pis) == lay["total"]
-        pis_t = advice(b, inner_pis)
-        r_h, entered = b.merkle.sponge([b.val(t) for t in pis_t])
-        for e, t in zip(entered, pis_t):
-            b.connect(e, t)
-        for i in range(4):
-            b.connect((r_h, 12 + i), T.pi_hash[i])
-        W = {k: pis_t[v[0]:v[0] + v[1]] for k, v in lay.items() if k != "total"}
-        Ws.append(W)
+        pis_t = verify_circuit_proof_with_public_inputs(b, prover, words, inner_pis, max_queries)
+        Ws.append({k: pis_t[v[0]:v[0] + v[1]] for k, v in lay.items() if k != "total"})
     # one transcript over all tables: trace caps, public values -> CTL challenges -> the first table's initial state
     pv_t = advice(b, public_values)
     ch = CircuitChallenger(b)
@@ -364,9 +383,6 @@ def root_circuit(wrappers: Sequence[tuple], layouts: Sequence[dict], ctls: Seque
             b.connect(a, c)
         state = W["state_out"]
     verify_cross_table_lookups_circuit(b, ctls, [W["ctl_zs_first"] for W in Ws])
-    targets = [t for W in Ws for t in W["trace_cap"]] + pv_t + ctl_ch
-    pw = b.merkle.public_inputs([b.val(t) for t in targets])
-    for w_, t in zip(pw, targets):
-        b.connect(w_, t)
+    _publish(b, [t for W in Ws for t in W["trace_cap"]] + pv_t + ctl_ch)
     circuit, wires = b.build(min_degree_bits)
     return circuit, wires, list(b.public_inputs)

@@ -60,6 +60,10 @@ void etp_host_poseidon_permute(uint64_t state[12]);
 /* ALL_ROUND_CONSTANTS (30 x 12), MDS_MATRIX_CIRC, MDS_MATRIX_DIAG of plonky2/src/hash/poseidon_goldilocks.rs — for callers
  * that build circuits over the permutation (PoseidonGate); any pointer may be NULL */
 void etp_poseidon_constants(uint64_t round_constants_out[360], uint64_t mds_circ_out[12], uint64_t mds_diag_out[12]);
+/* Witness of one PoseidonGate row (plonky2/src/gates/poseidon.rs PoseidonGenerator::run_once): the 135 wires — inputs,
+ * outputs, swap flag, deltas and the S-box inputs of every round after the first — for the given 12 inputs.  Host only;
+ * the witness generation of the recursion layers' circuits (Merkle paths, sponges, in-circuit challenger) is mostly this. */
+void etp_host_poseidon_gate_wires(const uint64_t inputs[12], int swap, uint64_t wires_out[135]);
 /* Device scratch of a context comes from a per-context block cache (a released block is reused by the next
  * allocation of about the same size, so proofs / commits of a shape seen before allocate nothing).
  * etp_ctx_trim returns the cached blocks to the CUDA runtime; etp_ctx_cached_bytes reports how much is held. */

@@ -45,6 +45,12 @@ def test_poseidon_gate_witness_matches_the_permutation():
         L.etp_host_poseidon_permute(a)
         assert w[12:24] == [int(x) for x in a]
     assert cc.hash_no_pad(list(range(8))) == cc.poseidon_gate_wires(list(range(8)) + [0] * 4, 0)[12:16]
+    # the library's witness helper (etp_host_poseidon_gate_wires) == the gate's definition in Python integers, edge lanes included
+    for k in range(40):
+        ins = [int(x) % P for x in rng.integers(0, 2**64, 12, dtype=np.uint64)]
+        ins[k % 12] = (0, P - 1, ins[(k + 4) % 12])[k % 3]
+        for swap in (0, 1):
+            assert cc.poseidon_gate_wires(ins, swap) == cc.poseidon_gate_wires_py(ins, swap)
 
 
 def test_selector_groups_follow_the_degree_rule():

@@ -132,6 +132,14 @@ def test_transaction_tables_wrapped_and_linked_by_the_root_circuit():
     assert len(pis) == 3 * 64 + 4 and pis[-4:] == [int(x) for x in ctl_ch]
     assert _constraints_hold(root, w, pis)
     _prove_and_verify(root, w, pis)
+    # one shrinking step per table (same public inputs) and the root over the SHRUNK proofs: the chain the reference runs
+    shrunk = []
+    for x in inner:
+        c, ws, ps = sc.shrink_circuit(x, max_queries=1)
+        assert ps == x[2]
+        shrunk.append(_prove_and_verify(c, ws, ps))
+    root2, w2, pis2 = sc.root_circuit(shrunk, [x[3] for x in wr], ctls, max_queries=1)
+    assert pis2 == pis and _constraints_hold(root2, w2, pis2)
     # tables in another order: the challenger chain breaks, the root has no witness
     with pytest.raises(AssertionError):
         sc.root_circuit([inner[1], inner[0], inner[2]], [wr[1][3], wr[0][3], wr[2][3]], ctls, max_queries=1)
