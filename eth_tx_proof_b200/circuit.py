@@ -883,6 +883,54 @@ class Circuit:
         return np.concatenate([self.constants, self.sigmas, wires, zs_pp, xs[None, :]], axis=0)
 
 
+def gl_mul_vec(a: np.ndarray, b) -> np.ndarray:
+    """Element-wise product mod p of canonical uint64 arrays (b: array or int), numpy only: 32-bit limbs, 2^64 = 2^32 - 1,
+    2^96 = -1 (mod p)."""
+    M, EPS = np.uint64(0xFFFFFFFF), np.uint64(0xFFFFFFFF)
+    a = np.asarray(a, dtype=np.uint64)
+    b = np.asarray(b, dtype=np.uint64) if isinstance(b, np.ndarray) else np.uint64(int(b) % P)
+    s32 = np.uint64(32)
+    with np.errstate(over="ignore"):
+        a0, a1, b0, b1 = a & M, a >> s32, b & M, b >> s32
+        ll, lh, hl, hh = a0 * b0, a0 * b1, a1 * b0, a1 * b1
+        mid = lh + hl
+        carry = (mid < lh).astype(np.uint64)
+        hi = hh + (mid >> s32) + (carry << s32)
+        lo = ((mid & M) << s32) + ll
+        hi = hi + (lo < ll).astype(np.uint64)
+        h0, h1 = hi & M, hi >> s32
+        t0 = lo - h1
+        t0 = t0 - np.where(lo < h1, EPS, np.uint64(0))
+        t1 = h0 * EPS
+        t2 = t0 + t1
+        t2 = t2 + np.where(t2 < t1, EPS, np.uint64(0))
+        return np.where(t2 >= np.uint64(P), t2 - np.uint64(P), t2)
+
+
+def _components(n_nodes: int, edges: np.ndarray) -> np.ndarray:
+    """Connected-component label of every node (scipy's union-find when available, a plain one otherwise)."""
+    try:
+        from scipy.sparse import coo_matrix
+        from scipy.sparse.csgraph import connected_components
+
+        m = coo_matrix((np.ones(len(edges), dtype=np.int8), (edges[:, 0], edges[:, 1])), shape=(n_nodes, n_nodes))
+        return connected_components(m, directed=False)[1].astype(np.int64)
+    except ImportError:
+        parent = list(range(n_nodes))
+
+        def find(u):
+            while parent[u] != u:
+                parent[u] = parent[parent[u]]
+                u = parent[u]
+            return u
+
+        for a, b_ in edges.tolist():
+            ra, rb = find(a), find(b_)
+            if ra != rb:
+                parent[ra] = rb
+        return np.array([find(u) for u in range(n_nodes)], dtype=np.int64)
+
+
 class CircuitBuilder:
     """Rows of gates with their constants, copy constraints between routed wires, direct wire assignment (no generators)."""
 
@@ -927,34 +975,25 @@ class CircuitBuilder:
             for j, c in enumerate(cs):
                 gate_constants[j, r] = c
         # copy constraints -> partition of the routed wire positions -> sigma: every position maps to the next of its set
-        parent = list(range(NUM_ROUTED * n))  # position = column * n + row
-
-        def find(u):
-            while parent[u] != u:
-                parent[u] = parent[parent[u]]
-                u = parent[u]
-            return u
-
-        for (r0, c0), (r1, c1) in self.copies:
-            a, b_ = find(c0 * n + r0), find(c1 * n + r1)
-            if a != b_:
-                parent[a] = b_
-        sets: Dict[int, List[int]] = {}
-        for pos in sorted({c * n + r for pair in self.copies for (r, c) in pair}):
-            sets.setdefault(find(pos), []).append(pos)
+        # (members in ascending position order, the last one back to the first).  position = column * n + row
         g = root_of_unity(degree_bits)
-        xs = [1]
-        for _ in range(n - 1):
-            xs.append(xs[-1] * g % P)
+        xs = np.ones(n, dtype=np.uint64)  # xs[i] = g^i, by doubling
+        for k in range(degree_bits):
+            xs[1 << k:2 << k] = gl_mul_vec(xs[:1 << k], pow(g, 1 << k, P))
         k_is = coset_shifts(NUM_ROUTED)
-        sig = np.zeros(NUM_ROUTED * n, dtype=np.uint64)
-        for c in range(NUM_ROUTED):
-            col = np.array([k_is[c] * x % P for x in xs], dtype=np.uint64)
-            sig[c * n:(c + 1) * n] = col
-        ident = lambda pos: k_is[pos // n] * xs[pos % n] % P
-        for members in sets.values():
-            for a, b_ in zip(members, members[1:] + members[:1]):
-                sig[a] = ident(b_)
+        ident = np.concatenate([gl_mul_vec(xs, k_is[c]) for c in range(NUM_ROUTED)])
+        sig = ident.copy()
+        if self.copies:
+            cp = np.array([(c0 * n + r0, c1 * n + r1) for (r0, c0), (r1, c1) in self.copies], dtype=np.int64)
+            pos, inv = np.unique(cp.ravel(), return_inverse=True)
+            label = _components(len(pos), inv.reshape(-1, 2))
+            order = np.lexsort((pos, label))
+            p_sorted, l_sorted = pos[order], label[order]
+            nxt = np.roll(p_sorted, -1)
+            last = np.nonzero(l_sorted != np.roll(l_sorted, -1))[0]          # last member of every set
+            first = np.concatenate([[0], last[:-1] + 1])                      # first member of every set
+            nxt[last] = p_sorted[first]
+            sig[p_sorted] = ident[nxt]
         circuit = Circuit(degree_bits, gates, gate_of_row, gate_constants, sig.reshape(NUM_ROUTED, n), len(self.public_inputs))
         return circuit, wires
 

@@ -386,3 +386,35 @@ def root_circuit(wrappers: Sequence[tuple], layouts: Sequence[dict], ctls: Seque
     _publish(b, [t for W in Ws for t in W["trace_cap"]] + pv_t + ctl_ch)
     circuit, wires = b.build(min_degree_bits)
     return circuit, wires, list(b.public_inputs)
+
+
+def transaction_recursion_plan(tables: Sequence[tuple], ctls: Sequence[tuple], all_proof, circuit_prove, threshold_degree_bits: int = 13,
+                               max_queries: int = None, log=None) -> List[dict]:
+    """The recursion layers of ONE transaction, built over its real table proofs in the order the reference proves them
+    (proof_gen::generate_txn_proof -> AllRecursiveCircuits::prove_root, /root/reference/ops/src/lib.rs:52): per table the
+    wrapper circuit of its STARK proof, then shrinking steps until the proof's circuit has at most 2^threshold_degree_bits rows
+    (at least one, as upstream's shrinking_config chain), then the root circuit over the seven shrunk proofs.
+    tables: [(name, Program, trace)]; all_proof: prover.AllProof-shaped (stark_proofs, init_challenger_states,
+    ctl_challenges); circuit_prove(circuit, wires, public_inputs) -> (prover-like with .c/.digest/.constants_sigmas_cap, proof
+    words).  -> [{"name", "kind", "circuit", "wires", "public_inputs", "prover", "words"}] in proving order: every later circuit
+    verifies the proof(s) produced before it, so proving the list again with the same witnesses reproduces the whole job."""
+    plan, tops, layouts = [], [], []
+
+    def step(name, kind, built):
+        circuit, wires, pis = built
+        prover, words = circuit_prove(circuit, wires, pis)
+        plan.append({"name": name, "kind": kind, "circuit": circuit, "wires": wires, "public_inputs": pis, "prover": prover, "words": words})
+        if log:
+            log(f"{name}: {kind} circuit 2^{circuit.degree_bits} rows")
+        return prover, words, pis
+
+    for (name, prog, _), words, state in zip(tables, all_proof.stark_proofs, all_proof.init_challenger_states):
+        cur = step(name, "wrapper", stark_wrapper_circuit(prog, words, state, all_proof.ctl_challenges, max_queries))
+        first = True
+        while first or cur[0].c.degree_bits > threshold_degree_bits:
+            cur = step(name, "shrink", shrink_circuit(cur, max_queries))
+            first = False
+        tops.append(cur)
+        layouts.append(wrapper_public_input_layout(prog, True))
+    step("root", "root", root_circuit(tops, layouts, ctls, max_queries=max_queries))
+    return plan
