@@ -328,6 +328,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def partial(leg, obj):
+        """ETP_BENCH_PARTIAL=<file>: append every finished leg as a JSON line (a run cut short keeps what it measured)."""
+        path = os.environ.get("ETP_BENCH_PARTIAL")
+        if path and rank == 0:
+            with open(path, "a") as f:
+                f.write(json.dumps({"leg": leg, "t": time.time(), "result": obj}) + "\n")
+
     ctx = etp.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream)
     # synthetic trace, uniform in [0, p): hi == 0xFFFFFFFF and lo != 0 would be >= p -> fold back
@@ -432,6 +439,7 @@ def main():
 
     # ---- BASELINE configs[2] / [4] shape: single-table STARK proofs (memory-shaped table), 8 independent
     # "segment" jobs sharded over the ranks with no collective (eth_tx_proof_b200/parallel.py)
+    partial("commit", {"ms_per_step": ms_per_step, "value": value, "phases_ms": phase, "e2e": e2e, "sweep": sweep})
     stark = None
     if not args.skip_stark:
         from eth_tx_proof_b200 import parallel, synthetic as syn
@@ -483,6 +491,7 @@ def main():
     # challenger, CTL challenges, then prove_with_commitment per table on that challenger (eth_tx_proof_b200/prover.py).
     # The constraint sets are shape stand-ins (the real ones are not available offline) and there are no recursion layers.
     # Tables are registered (NVRTC) once per context, outside the timed region, like the reference builds its circuits at start-up.
+    partial("stark", stark)
     tx = None
     if not args.skip_stark and not args.skip_tx:
         from eth_tx_proof_b200 import cprog, parallel, prover
@@ -527,6 +536,7 @@ def main():
     # the threshold degree, then one root circuit proof.  The circuit proofs are eth_tx_proof_b200/circuit.py proofs of the
     # recursive verifier of this prover's circuit proofs over real inner proofs (see below); the reference's STARK-verifier and
     # verifier circuits are not available offline, the number of layers is a placeholder, witness generation is not included.
+    partial("tx", tx)
     tx_rec = None
     if not args.skip_stark and not args.skip_tx:
         from eth_tx_proof_b200 import circuit as cc, fri_circuit as fc
@@ -613,6 +623,7 @@ def main():
     # ---- SURVEY.md 8(f3), first slice: the device skeleton of one recursion-layer proof (plonky2's circuit prover under
     # standard_recursion_config: wires / Z / quotient commits at rate_bits 3, openings, four-oracle FRI with 28 queries) on
     # stand-in polynomials of the shrink-circuit shapes; gate evaluation and witness generation are NOT included
+    partial("tx_with_recursion", tx_rec)
     recursion = None
     if not args.skip_stark and world == 1:
         from eth_tx_proof_b200 import recursion as rec
@@ -631,6 +642,7 @@ def main():
     # recursion-verifier-shaped synthetic circuit (PoseidonGate chain + ArithmeticGates + public-input hashing, copy constraints)
     # proved as plonk::prover::prove does; CPU arm: the oracle's restatement of the same steps on the host cores; the two proofs
     # must be equal word for word.
+    partial("recursion_skeleton", recursion)
     circuit_leg = None
     if not args.skip_stark and world == 1:
         from eth_tx_proof_b200 import circuit as cc
@@ -777,14 +789,15 @@ def main():
             from eth_tx_proof_b200 import circuit as cc, parallel, prover, stark_circuit as sc
 
             t_build = time.perf_counter()
-            real_contexts = int(os.environ.get("ETP_BENCH_REAL_CONTEXTS", 2))
+            real_contexts = int(os.environ.get("ETP_BENCH_REAL_CONTEXTS", REC_CONTEXTS_PER_GPU))
+            pv = [0xB200, 1, 2, 3] * 2  # public values: state before ++ state after, equal (the transactions of a block chain)
             pool = parallel.ProverPool(local_rank, real_contexts)
             ids = [[c.register_table(p) for _, p, _ in tables] for c in pool.contexts]
             dev = [torch.from_numpy(t.view(np.int64)).cuda() for _, _, t in tables]
             traces_dev = [(d.data_ptr(), t.shape[1], t.shape[0], int(t.shape[1]).bit_length() - 1) for d, (_, _, t) in zip(dev, tables)]
             torch.cuda.synchronize()
             c0 = pool.contexts[0]
-            first = prover.prove_with_traces(c0, ids[0], traces_dev)
+            first = prover.prove_with_traces(c0, ids[0], traces_dev, pv)
             provers0 = []
 
             def circuit_prove(circuit, wires, pis):
@@ -792,13 +805,16 @@ def main():
                 provers0.append(cp)
                 return cp, cp.prove_words(wires, pis)
 
-            plan = sc.transaction_recursion_plan(tables, ctls, first, circuit_prove)
-            cprovers = [provers0] + [[cc.CircuitProver(c, s["circuit"]) for s in plan] for c in pool.contexts[1:]]
+            plan = sc.transaction_recursion_plan(tables, ctls, first, circuit_prove, public_values=pv)
+            # the layers above: one aggregation circuit per tree level over two proofs of the level below, then the block circuit
+            block_plan = sc.block_recursion_plan(plan[-1], len(tables), circuit_prove, levels=3)
+            block_provers = provers0[len(plan):]
+            cprovers = [provers0[:len(plan)]] + [[cc.CircuitProver(c, s["circuit"]) for s in plan] for c in pool.contexts[1:]]
             build_s = time.perf_counter() - t_build
 
             def prove_tx_real(c, _job):
                 k = pool.contexts.index(c)
-                out = [prover.prove_with_traces(c, ids[k], traces_dev)]
+                out = [prover.prove_with_traces(c, ids[k], traces_dev, pv)]
                 for cp, s in zip(cprovers[k], plan):
                     out.append(cp.prove_words(s["wires"], s["public_inputs"]))
                 return out
@@ -815,7 +831,7 @@ def main():
                 t0 = time.perf_counter()
                 cp.prove_words(s["wires"], s["public_inputs"])
                 per_kind.setdefault(s["kind"], []).append((time.perf_counter() - t0) * 1e3)
-            n_real = 4 * world
+            n_real = 8 * world
         except Exception as e:  # the leg is additive: a failure here must not cost the bench line
             import traceback
 
@@ -829,27 +845,50 @@ def main():
             t0 = time.perf_counter()
             pool.map(prove_tx_real, list(parallel.shard_jobs(n_real, rank, world)))
             dt = max_over_ranks(time.perf_counter() - t0)
+            # BASELINE configs[4] shape with the real structure: a block of 8 segments — the 8 transaction jobs sharded over the ranks,
+            # then AggProof's binary fold (4 + 2 + 1 aggregation proofs, each verifying the two proofs below it; a level's proofs spread
+            # over the ranks, a barrier between levels) and the block proof on rank 0
+            barrier()
+            t0 = time.perf_counter()
+            pool.map(prove_tx_real, list(parallel.shard_jobs(8, rank, world)))
+            for level in range(3):
+                if world > 1:
+                    dist.barrier()
+                for j in range(4 >> level):
+                    if j % world == rank:
+                        block_provers[level].prove_words(block_plan[level]["wires"], block_plan[level]["public_inputs"])
+            if world > 1:
+                dist.barrier()
+            if rank == 0:
+                block_provers[3].prove_words(block_plan[3]["wires"], block_plan[3]["public_inputs"])
+            block_real_ms = max_over_ranks(time.perf_counter() - t0) * 1e3
             tx_real = {"workload": "synthetic transaction with the reference's proof structure: 7 table STARKs + CTLs (as `tx`), per table the "
                                    "wrapper circuit verifying THAT STARK proof (in-circuit transcript, constraints at zeta, all 84 FRI queries) and "
                                    "shrinking steps to 2^13 rows with the public inputs propagated, then the root circuit over the seven shrunk proofs "
                                    "(CTL challenges from the trace caps, challenger chain, cross-table lookup sums); every circuit verifies the real "
-                                   f"proof(s) below it; witnesses given; {n_real} transactions (4 per GPU) over {world} GPU(s), {real_contexts} contexts per GPU; "
+                                   f"proof(s) below it; witnesses given; {n_real} transactions (8 per GPU) over {world} GPU(s), {real_contexts} contexts per GPU; "
                                    "shape stand-in constraint sets (the real EVM tables are not available offline)",
                        "circuits": [{"name": s["name"], "kind": s["kind"], "degree_bits": int(s["circuit"].degree_bits),
                                      "gate_types": int(len(s["circuit"].gates)), "proof_bytes": int(s["words"].size * 8)} for s in plan],
+                       "block_of_8_segments": {"ms": block_real_ms, "scaling": "strong",
+                                               "circuits": [{"name": s["name"], "degree_bits": int(s["circuit"].degree_bits)} for s in block_plan],
+                                               "what": f"8 transaction jobs (each: 7 STARKs + {len(plan)} circuit proofs) sharded over {world} GPU(s) + "
+                                                       "4 + 2 + 1 aggregation proofs (each verifies the two proofs below it and chains their public "
+                                                       "values) + 1 block proof; wall clock, max over ranks"},
                        "circuit_proofs_per_tx": len(plan), "tx_ms": real_ms, "tx_per_min": n_real * 60.0 / dt, "transactions": n_real,
                        "circuit_prove_ms": {k: {"n": len(v), "sum": sum(v), "max": max(v)} for k, v in per_kind.items()},
                        "build_s": build_s,
                        "timed": "tx_ms: one whole job on one context (table traces resident in HBM, circuit witnesses uploaded from the host "
                                 "inside) -> all proofs on the host; tx_per_min: all jobs through the pool (wall clock, max over ranks); build_s "
                                 "(untimed setup): circuits, witnesses, per-context circuit data"}
-            del cprovers, provers0, plan, dev
+            del cprovers, provers0, block_provers, plan, block_plan, dev
             pool.close()
         except Exception as e:  # the leg is additive: a failure here must not cost the bench line
             import traceback
 
             tx_real = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1500:]}
 
+    partial("tx_real_recursion", tx_real)
     out = {
         "metric": "commit_hbm_gbs", "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",

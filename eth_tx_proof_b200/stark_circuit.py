@@ -389,7 +389,7 @@ def root_circuit(wrappers: Sequence[tuple], layouts: Sequence[dict], ctls: Seque
 
 
 def transaction_recursion_plan(tables: Sequence[tuple], ctls: Sequence[tuple], all_proof, circuit_prove, threshold_degree_bits: int = 13,
-                               max_queries: int = None, log=None) -> List[dict]:
+                               max_queries: int = None, log=None, public_values: Sequence[int] = ()) -> List[dict]:
     """The recursion layers of ONE transaction, built over its real table proofs in the order the reference proves them
     (proof_gen::generate_txn_proof -> AllRecursiveCircuits::prove_root, /root/reference/ops/src/lib.rs:52): per table the
     wrapper circuit of its STARK proof, then shrinking steps until the proof's circuit has at most 2^threshold_degree_bits rows
@@ -416,5 +416,79 @@ def transaction_recursion_plan(tables: Sequence[tuple], ctls: Sequence[tuple], a
             first = False
         tops.append(cur)
         layouts.append(wrapper_public_input_layout(prog, True))
-    step("root", "root", root_circuit(tops, layouts, ctls, max_queries=max_queries))
+    step("root", "root", root_circuit(tops, layouts, ctls, public_values=public_values, max_queries=max_queries))
+    return plan
+
+
+# ---- aggregation and block layers (/root/reference/ops/src/lib.rs:72 AggProof::combine -> generate_agg_proof, :95 BlockProof ->
+# generate_block_proof; evm_arithmetization fixed_recursive_verifier.rs create_aggregation_circuit / create_block_circuit).
+# Upstream's public values chain state: a child's "after" must be the next child's "before".  Here a transaction's
+# public_values are [before (STATE_WORDS) ++ after (STATE_WORDS)] (root public inputs: trace caps ++ public_values ++ CTL
+# challenges), an aggregation proof publishes [before ++ after] of its span, a block proof [before ++ after ++ block number].
+# Upstream's circuits are cyclic (one aggregation circuit verifies a root OR an aggregation proof; the block circuit verifies its
+# own previous proof); without cyclic recursion every level is its own circuit here — same checks, per-level verifier data.
+STATE_WORDS = 4
+
+
+def root_io(n_tables: int) -> tuple:
+    """(offset of `before`, offset of `after`) inside a root proof's public inputs."""
+    return 64 * n_tables, 64 * n_tables + STATE_WORDS
+
+
+def aggregation_circuit(lhs: tuple, rhs: tuple, lhs_io: tuple = (0, STATE_WORDS), rhs_io: tuple = (0, STATE_WORDS), max_queries: int = None,
+                        min_degree_bits: int = 0):
+    """create_aggregation_circuit: verifies two child proofs `(CircuitProver, words, public inputs)` — roots or aggregations,
+    `*_io` = (offset of before, offset of after) in the child's public inputs — and checks lhs.after == rhs.before.
+    Public inputs: lhs.before ++ rhs.after."""
+    b = GadgetBuilder()
+    lt = verify_circuit_proof_with_public_inputs(b, *lhs, max_queries)
+    rt = verify_circuit_proof_with_public_inputs(b, *rhs, max_queries)
+    for k in range(STATE_WORDS):
+        b.connect(lt[lhs_io[1] + k], rt[rhs_io[0] + k])  # "the state after the left child is the state before the right child"
+    _publish(b, lt[lhs_io[0]:lhs_io[0] + STATE_WORDS] + rt[rhs_io[1]:rhs_io[1] + STATE_WORDS])
+    circuit, wires = b.build(min_degree_bits)
+    return circuit, wires, list(b.public_inputs)
+
+
+def block_circuit(agg: tuple, prev_block: tuple = None, agg_io: tuple = (0, STATE_WORDS), genesis_number: int = 0, max_queries: int = None,
+                  min_degree_bits: int = 0):
+    """create_block_circuit: verifies the block's aggregation proof and, when there is one, the previous block proof (its `after`
+    must be this block's `before`, the block number increases by one).  Public inputs: before ++ after ++ block number."""
+    b = GadgetBuilder()
+    at = verify_circuit_proof_with_public_inputs(b, *agg, max_queries)
+    before, after = at[agg_io[0]:agg_io[0] + STATE_WORDS], at[agg_io[1]:agg_io[1] + STATE_WORDS]
+    if prev_block is None:
+        number = b.constant(genesis_number)
+    else:
+        pt = verify_circuit_proof_with_public_inputs(b, *prev_block, max_queries)
+        for k in range(STATE_WORDS):
+            b.connect(pt[STATE_WORDS + k], before[k])
+        number = b.arith(pt[2 * STATE_WORDS], b.one, b.one, 1, 1)
+        before = pt[:STATE_WORDS]  # the chain's public `before` stays the first block's (upstream: checkpoint state root)
+    _publish(b, before + after + [number])
+    circuit, wires = b.build(min_degree_bits)
+    return circuit, wires, list(b.public_inputs)
+
+
+def block_recursion_plan(root_step: dict, n_tables: int, circuit_prove, levels: int = 3, max_queries: int = None, log=None) -> List[dict]:
+    """The layers above 2^levels identical, chainable transactions (public values before == after): per level ONE aggregation
+    circuit over two proofs of the level below (AggProof::combine folds a binary tree, /root/reference/ops/src/lib.rs:64-76),
+    then the block circuit over the top aggregation proof (:95).  root_step: the last step of transaction_recursion_plan.
+    -> [{"name": "agg<level>" | "block", ...}] in proving order (one proof per circuit: the tree's 2^(levels - l) proofs of a
+    level re-prove the same circuit with the same witness)."""
+    plan = []
+    cur = (root_step["prover"], root_step["words"], root_step["public_inputs"])
+    io = root_io(n_tables)
+    for level in range(1, levels + 1):
+        circuit, wires, pis = aggregation_circuit(cur, cur, io, io, max_queries)
+        prover, words = circuit_prove(circuit, wires, pis)
+        plan.append({"name": f"agg{level}", "kind": "aggregation", "circuit": circuit, "wires": wires, "public_inputs": pis, "prover": prover, "words": words})
+        if log:
+            log(f"agg{level}: aggregation circuit 2^{circuit.degree_bits} rows")
+        cur, io = (prover, words, pis), (0, STATE_WORDS)
+    circuit, wires, pis = block_circuit(cur, max_queries=max_queries)
+    prover, words = circuit_prove(circuit, wires, pis)
+    plan.append({"name": "block", "kind": "block", "circuit": circuit, "wires": wires, "public_inputs": pis, "prover": prover, "words": words})
+    if log:
+        log(f"block: block circuit 2^{circuit.degree_bits} rows")
     return plan

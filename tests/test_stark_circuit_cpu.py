@@ -169,3 +169,50 @@ def test_wrapper_rejects_a_proof_under_other_ctl_challenges():
         sc.stark_wrapper_circuit(tables[0][1], proofs[0], states[0], other, max_queries=1)
     with pytest.raises(AssertionError):  # another initial state: the in-circuit transcript diverges from the proof's
         sc.stark_wrapper_circuit(tables[0][1], proofs[0], states[1], ctl_ch, max_queries=1)
+
+
+def test_aggregation_and_block_circuits_chain_the_public_values():
+    """The layers above the root (/root/reference/ops/src/lib.rs:72,95): two transactions whose public values chain
+    (s0 -> s1, s1 -> s2) are proven table by table, wrapped and rooted; the aggregation circuit verifies both root proofs and
+    publishes (s0, s2); the block circuit verifies the aggregation proof; a second block verifies the first block proof as well.
+    Two transactions that do NOT chain have no aggregation witness."""
+    tables, ctls = cprog.ctl_demo_tables(5, 4, 4)
+    s = [[11, 12, 13, 14], [21, 22, 23, 24], [31, 32, 33, 34]]
+
+    def root_of(before, after):
+        pv = before + after
+        tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tables]
+        batches = [oracle.Batch.from_values(t, 1, 4) for _, _, t in tables]
+        ch = oracle.HostChallenger()
+        for bb in batches:
+            ch.observe(bb.cap)
+        ch.observe(pv)
+        ctl_ch = ch.get_n(4)
+        proofs, states = [], []
+        for tid, (_, _, t), bb in zip(tids, tables, batches):
+            states.append(ch.compact())
+            proofs.append(oracle.prove_with_commitment(tid, t, bb, ch, ctl_ch))
+        wr = _wrappers(tables, proofs, states, ctl_ch)
+        inner = [_prove_and_verify(outer, w, pis) for outer, w, pis, _ in wr]
+        root, w, pis = sc.root_circuit(inner, [x[3] for x in wr], ctls, public_values=pv, max_queries=1)
+        assert pis[3 * 64:3 * 64 + 8] == pv
+        return _prove_and_verify(root, w, pis)
+
+    r01, r12 = root_of(s[0], s[1]), root_of(s[1], s[2])
+    io = sc.root_io(3)
+    agg, w, pis = sc.aggregation_circuit(r01, r12, io, io, max_queries=1)
+    assert pis == s[0] + s[2] and _constraints_hold(agg, w, pis)
+    a02 = _prove_and_verify(agg, w, pis)
+    with pytest.raises(AssertionError, match="copy constraint"):
+        sc.aggregation_circuit(r12, r01, io, io, max_queries=1)  # s2 != s0: the spans do not chain
+    blk, w, pis = sc.block_circuit(a02, genesis_number=7, max_queries=1)
+    assert pis == s[0] + s[2] + [7] and _constraints_hold(blk, w, pis)
+    b0 = _prove_and_verify(blk, w, pis)
+    # the next block: a span s2 -> s2 (the same transaction shape, chained), verified together with the previous block proof
+    r22 = root_of(s[2], s[2])
+    agg2, w, pis = sc.aggregation_circuit(r22, r22, io, io, max_queries=1)
+    a22 = _prove_and_verify(agg2, w, pis)
+    blk1, w, pis = sc.block_circuit(a22, prev_block=b0, max_queries=1)
+    assert pis == s[0] + s[2] + [8] and _constraints_hold(blk1, w, pis)
+    with pytest.raises(AssertionError, match="copy constraint"):
+        sc.block_circuit(a02, prev_block=b0, max_queries=1)  # the block's span must start where the previous block ended
