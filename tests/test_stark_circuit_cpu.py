@@ -216,3 +216,37 @@ def test_aggregation_and_block_circuits_chain_the_public_values():
     assert pis == s[0] + s[2] + [8] and _constraints_hold(blk1, w, pis)
     with pytest.raises(AssertionError, match="copy constraint"):
         sc.block_circuit(a02, prev_block=b0, max_queries=1)  # the block's span must start where the previous block ended
+
+
+def test_transaction_and_block_plans_assemble_the_whole_job():
+    """transaction_recursion_plan + block_recursion_plan (what bench.py's tx_real_recursion leg and tools/tx_recursion.py drive on
+    the device) with the oracle as the circuit prover: wrapper + shrink per table, root, two aggregation levels, block — every later
+    circuit is built from the proofs made before it; re-proving the list reproduces the proofs."""
+    tables, ctls = cprog.ctl_demo_tables(5, 4, 4)
+    pv = [5, 6, 7, 8, 5, 6, 7, 8]
+    tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tables]
+    batches = [oracle.Batch.from_values(t, 1, 4) for _, _, t in tables]
+    ch = oracle.HostChallenger()
+    for bb in batches:
+        ch.observe(bb.cap)
+    ch.observe(pv)
+    ctl_ch = ch.get_n(4)
+    proofs, states = [], []
+    for tid, (_, _, t), bb in zip(tids, tables, batches):
+        states.append(ch.compact())
+        proofs.append(oracle.prove_with_commitment(tid, t, bb, ch, ctl_ch))
+    ap = types.SimpleNamespace(stark_proofs=proofs, init_challenger_states=states, ctl_challenges=ctl_ch)
+
+    def circuit_prove(c, w, p):
+        fake, words, _ = _prove_and_verify(c, w, p)
+        return fake, words
+
+    plan = sc.transaction_recursion_plan(tables, ctls, ap, circuit_prove, max_queries=1, public_values=pv)
+    assert [(s["name"], s["kind"]) for s in plan] == [("ops", "wrapper"), ("ops", "shrink"), ("rom", "wrapper"), ("rom", "shrink"),
+                                                      ("extra", "wrapper"), ("extra", "shrink"), ("root", "root")]
+    assert plan[-1]["public_inputs"][3 * 64:3 * 64 + 8] == pv
+    blocks = sc.block_recursion_plan(plan[-1], len(tables), circuit_prove, levels=2, max_queries=1)
+    assert [s["name"] for s in blocks] == ["agg1", "agg2", "block"]
+    assert blocks[0]["public_inputs"] == pv and blocks[-1]["public_inputs"] == pv + [0]
+    again = _prove_and_verify(plan[-1]["circuit"], plan[-1]["wires"], plan[-1]["public_inputs"])[1]
+    assert (again == plan[-1]["words"]).all()
