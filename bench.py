@@ -831,6 +831,8 @@ def main():
                 t0 = time.perf_counter()
                 cp.prove_words(s["wires"], s["public_inputs"])
                 per_kind.setdefault(s["kind"], []).append((time.perf_counter() - t0) * 1e3)
+            k_big = max(range(len(plan)), key=lambda i: plan[i]["circuit"].degree_bits)
+            big_phases = {k: float(v) for k, v in cprovers[0][k_big].prove(plan[k_big]["wires"], plan[k_big]["public_inputs"])["ms"].items()}
             n_real = 8 * world
             # the CPU restatement on ONE recursion circuit of this chain (the first shrinking step, 2^13 rows), for scale and as a
             # parity check of a real recursion layer: the device proof equals the oracle's word for word
@@ -895,11 +897,13 @@ def main():
                                                        "values) + 1 block proof; wall clock, max over ranks"},
                        "circuit_proofs_per_tx": len(plan), "tx_ms": real_ms, "tx_per_min": n_real * 60.0 / dt, "transactions": n_real,
                        "circuit_prove_ms": {k: {"n": len(v), "sum": sum(v), "max": max(v)} for k, v in per_kind.items()},
+                       "largest_circuit": {"name": f"{plan[k_big]['name']} {plan[k_big]['kind']}", "degree_bits": int(plan[k_big]["circuit"].degree_bits),
+                                           "phases_ms": big_phases},
                        "build_s": build_s, "cpu_baseline": real_cpu,
                        "timed": "tx_ms: one whole job on one context (table traces resident in HBM, circuit witnesses uploaded from the host "
                                 "inside) -> all proofs on the host; tx_per_min: all jobs through the pool (wall clock, max over ranks); build_s "
                                 "(untimed setup): circuits, witnesses, per-context circuit data"}
-            del cprovers, provers0, block_provers, plan, block_plan, dev
+            del cprovers, provers0, block_provers, block_plan, dev
             pool.close()
         except Exception as e:  # the leg is additive: a failure here must not cost the bench line
             import traceback
