@@ -931,6 +931,10 @@ def _components(n_nodes: int, edges: np.ndarray) -> np.ndarray:
         return np.array([find(u) for u in range(n_nodes)], dtype=np.int64)
 
 
+class NoWitness(AssertionError):
+    """The circuit being built has no satisfying witness for the given data (e.g. the inner proof of a verifier circuit is invalid)."""
+
+
 class CircuitBuilder:
     """Rows of gates with their constants, copy constraints between routed wires, direct wire assignment (no generators)."""
 
@@ -949,8 +953,12 @@ class CircuitBuilder:
         return len(self.rows) - 1
 
     def connect(self, a: Tuple[int, int], b_: Tuple[int, int]):
-        assert a[1] < NUM_ROUTED and b_[1] < NUM_ROUTED, "only routed wires can be copy-constrained"
-        assert self.wires[a[0]][a[1]] == self.wires[b_[0]][b_[1]], f"copy constraint between different values {a} {b_}"
+        """Copy constraint a == b.  The values must already agree: this is how an invalid inner proof is rejected while a verifier
+        circuit is built (NoWitness is an AssertionError, raised explicitly so that `python -O` cannot strip the check)."""
+        if a[1] >= NUM_ROUTED or b_[1] >= NUM_ROUTED:
+            raise ValueError("only routed wires can be copy-constrained")
+        if self.wires[a[0]][a[1]] != self.wires[b_[0]][b_[1]]:
+            raise NoWitness(f"copy constraint between different values {a} {b_}")
         self.copies.append((a, b_))
 
     def build(self, min_degree_bits: int = 0):

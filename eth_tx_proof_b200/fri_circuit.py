@@ -170,7 +170,8 @@ class GadgetBuilder(CircuitBuilder):
             self._set((r, 8 * i + 2 + comp), self.val(den[comp]), den[comp])
             self._set((r, 8 * i + 4 + comp), 0, self.zero)
             self._set((r, 8 * i + 6 + comp), self.val(num[comp]), num[comp])
-        assert _e_mod(_e_mul(q, self.vale(den))) == self.vale(num)
+        if _e_mod(_e_mul(q, self.vale(den))) != self.vale(num):  # den == 0 and num != 0
+            raise cc.NoWitness("division by zero in a witnessed quotient")
         return qt
 
     def connect_ext(self, a: ExtTarget, b: ExtTarget):
@@ -180,7 +181,8 @@ class GadgetBuilder(CircuitBuilder):
     # ---- bits (BaseSumGate: wire 0 = sum of limb_i 2^i, limbs boolean)
     def split_bits(self, t: Target, n_bits: int) -> List[Target]:
         r = self.add_gate(self.bs, wires=self.bs.witness(self.val(t)))
-        assert self.val(t) < (1 << n_bits)
+        if self.val(t) >= (1 << n_bits):
+            raise cc.NoWitness(f"value does not fit {n_bits} bits")
         self.connect((r, 0), t)
         for j in range(n_bits, 63):
             self.connect((r, 1 + j), self.zero)
@@ -535,7 +537,8 @@ def verify_circuit_proof_in_circuit(b: "GadgetBuilder", prover, d: dict, T: "_T"
     pow_response = ch.get_challenge()
     index_challenges = ch.get_n(h["num_queries"])
     for name, want in (("alpha", d["alpha"]), ("zeta", d["zeta"])):  # the in-circuit transcript == the host's
-        assert list(b.vale(getattr(T, name))) == want, name
+        if list(b.vale(getattr(T, name))) != want:
+            raise cc.NoWitness(f"in-circuit transcript diverges from the host's at {name}")
     # ---- proof of work: the response's top pow_bits bits are zero
     lo_bits, hi_bit = _split_64(b, pow_response)
     for t in lo_bits[64 - h["pow_bits"]:] + [hi_bit]:

@@ -120,11 +120,13 @@ def verify_stark_proof_in_circuit(b: GadgetBuilder, program: cprog.Program, word
     op = pr["openings"]
     K, db, rate_bits = h["num_challenges"], h["degree_bits"], h["rate_bits"]
     n_trace, n_aux, n_quot, n_z = h["n_trace"], h["n_aux"], h["n_quot"], h["n_ctl_zs"]
-    assert K == NUM_CHALLENGES and h["cap_height"] == 4, "standard_fast_config"
-    assert (n_trace, n_aux) == (program.n_trace, program.n_aux) and n_z == len(program.ctl_zs), "the proof is not of this table"
     factor = max(1, program.degree - 1)
-    assert n_quot == factor * K
-    assert bool(n_z) <= multi, "a proof with CTL openings needs the CTL challenges"
+    if K != NUM_CHALLENGES or h["cap_height"] != 4:
+        raise ValueError("the wrapper circuit is built for StarkConfig::standard_fast_config()")
+    if (n_trace, n_aux, n_quot) != (program.n_trace, program.n_aux, factor * K) or n_z != len(program.ctl_zs):
+        raise ValueError("the proof is not of this table")
+    if n_z and not multi:
+        raise ValueError("a proof with CTL openings needs init_challenger_state and the CTL challenges")
     lde_bits = db + rate_bits
     flat_cap = lambda cap: [x for d in cap for x in d["elements"]]
     cap_rows = lambda cap: [[int(x) for x in d["elements"]] for d in cap]
@@ -147,7 +149,8 @@ def verify_stark_proof_in_circuit(b: GadgetBuilder, program: cprog.Program, word
     if multi:
         W.state_in = advice(b, init_challenger_state)
         W.ctl_challenges = advice(b, ctl_challenges)
-        assert len(W.state_in) == 12 and len(W.ctl_challenges) == 2 * K
+        if len(W.state_in) != 12 or len(W.ctl_challenges) != 2 * K:
+            raise ValueError("init_challenger_state has 12 words, ctl_challenges 2 per challenge")
 
     # ---- get_challenges_circuit
     ch = CircuitChallenger(b)
@@ -316,7 +319,8 @@ def verify_cross_table_lookups_circuit(b: GadgetBuilder, ctls: Sequence[tuple], 
                 total = b.arith(next(its[t]), b.one, total, 1, 1)
             b.connect(total, next(its[looked]))
     for it in its:
-        assert next(it, None) is None, "unused ctl_zs_first openings"
+        if next(it, None) is not None:
+            raise ValueError("unused ctl_zs_first openings")
 
 
 def verify_circuit_proof_with_public_inputs(b: GadgetBuilder, prover, words, inner_pis: Sequence[int], max_queries: int = None) -> List[Target]:
@@ -365,7 +369,8 @@ def root_circuit(wrappers: Sequence[tuple], layouts: Sequence[dict], ctls: Seque
     b = GadgetBuilder()
     Ws = []
     for (prover, words, inner_pis), lay in zip(wrappers, layouts):
-        assert len(inner_pis) == lay["total"]
+        if len(inner_pis) != lay["total"]:
+            raise ValueError("public inputs do not match the wrapper layout of the table")
         pis_t = verify_circuit_proof_with_public_inputs(b, prover, words, inner_pis, max_queries)
         Ws.append({k: pis_t[v[0]:v[0] + v[1]] for k, v in lay.items() if k != "total"})
     # one transcript over all tables: trace caps, public values -> CTL challenges -> the first table's initial state
