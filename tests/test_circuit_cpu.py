@@ -432,3 +432,32 @@ def test_recursive_verifier_circuit_with_the_in_circuit_challenger():
     with pytest.raises(AssertionError):  # another circuit digest: the in-circuit transcript diverges from the proof's
         other = types.SimpleNamespace(c=inner, digest=[1, 1, 1, 1], constants_sigmas_cap=proof["constants_sigmas_cap"])
         fc.recursive_verifier_circuit([(other, words, public_inputs)], max_queries=1)
+
+
+def test_vectorised_goldilocks_product_and_sigma_construction():
+    """circuit.gl_mul_vec (numpy, 32-bit limbs) against Python integers on random and edge operands, and the sigma polynomials of a
+    built circuit against the definition: every position of a copy set maps to the next one (ascending, cyclic), every other
+    position to itself."""
+    from eth_tx_proof_b200 import circuit as cc
+
+    rng = np.random.default_rng(9)
+    edge = [0, 1, 2, P - 1, P - 2, 2**32, 2**32 - 1, 2**32 + 1, 2**63, P // 2, 0xFFFFFFFF00000000]
+    a = np.array([int(x) % P for x in rng.integers(0, 2**64, 4000, dtype=np.uint64)] + edge * len(edge), dtype=np.uint64)
+    b = np.array([int(x) % P for x in rng.integers(0, 2**64, 4000, dtype=np.uint64)] + [y for y in edge for _ in edge], dtype=np.uint64)
+    assert (cc.gl_mul_vec(a, b) == np.array([int(x) * int(y) % P for x, y in zip(a, b)], dtype=np.uint64)).all()
+    for k in (0, 1, 7, P - 1, 2**32):
+        assert (cc.gl_mul_vec(a, k) == np.array([int(x) * k % P for x in a], dtype=np.uint64)).all()
+    b_ = cc.CircuitBuilder()
+    rows = [b_.add_gate(cc.NoopGate(), wires=[5, 5, 5, 9, 9, 1]) for _ in range(3)]
+    b_.connect((rows[2], 1), (rows[0], 0))
+    b_.connect((rows[0], 0), (rows[1], 2))
+    b_.connect((rows[1], 3), (rows[1], 4))
+    circuit, _ = b_.build(2)
+    n, g, k_is = circuit.n, cc.root_of_unity(circuit.degree_bits), cc.coset_shifts(cc.NUM_ROUTED)
+    ident = lambda row, col: k_is[col] * pow(g, row, P) % P
+    want = {(r, c): ident(r, c) for r in range(n) for c in range(cc.NUM_ROUTED)}
+    # position = column * n + row: (0,0)=0*n+0 < (2,1)=1*n+2 < (1,2)=2*n+1
+    want[(rows[0], 0)], want[(rows[2], 1)], want[(rows[1], 2)] = ident(rows[2], 1), ident(rows[1], 2), ident(rows[0], 0)
+    want[(rows[1], 3)], want[(rows[1], 4)] = ident(rows[1], 4), ident(rows[1], 3)
+    for (r, c), v in want.items():
+        assert int(circuit.sigmas[c, r]) == v, (r, c)
