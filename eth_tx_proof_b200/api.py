@@ -188,6 +188,7 @@ def load_library():
         "etp_table_quotient_degree_factor": (i32, [vp, i32]),
         "etp_table_register": (i32, [vp, _u64p, sz, C.POINTER(C.c_int32), sz, C.POINTER(i32)]),
         "etp_cprog_compile_check": (i32, [_u64p, sz, C.POINTER(sz), C.c_char_p, sz]),
+        "etp_cprog_generate_cuda": (C.c_int64, [_u64p, sz, C.c_char_p, sz]),
         "etp_lookup_helper_columns_dev": (i32, [vp, i32, i32, vp, sz, _u64p, i32, vp]),
         "etp_compute_quotient_polys_dev": (i32, [vp, i32, vp, vp, _u64p, i32, _u64p, _u64p, i32, vp]),
         "etp_pow_grind": (i32, [vp, _u64p, i32, i32, _u64p]),

@@ -15,9 +15,12 @@
 //            10 EMIT a (ConstraintConsumer::constraint) | 11 EMIT_TRANSITION a | 12 EMIT_FIRST_ROW a |
 //            13 EMIT_LAST_ROW a                      (emitted in the table's source order)
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace cprog {
@@ -85,9 +88,99 @@ inline uint64_t hash(const Program& p) {
   return h;
 }
 
+// ---- large programs ------------------------------------------------------------------------------------------------------
+// ptxas time is superlinear in the size of one function: a 50 k-op table (a bit-level Keccak-f round: 7 k constraints) does not
+// finish as ONE straight-line kernel.  Above SEGMENT_THRESHOLD_OPS the program is cut, at EMIT boundaries, into segments of about
+// `segment_ops` ops; every segment becomes a __noinline__ device function that contains the transitive dependencies of ITS emits
+// (loads, constants and shared subexpressions are re-materialised per segment — constraints are local, so little is duplicated)
+// and folds them into the consumer of the row context it receives by reference.  The kernel calls the segments in order, so the
+// consumer sees the emissions in the table's source order, exactly as in the one-function form.  Programs up to the threshold
+// (every table and circuit this repository ships today) keep the one-function form.  ETP_CPROG_SEGMENT_OPS overrides both the
+// threshold and the segment size (tests force the segmented form on small programs with it).
+constexpr uint32_t SEGMENT_THRESHOLD_OPS = 16384, SEGMENT_OPS = 3072;
+inline uint32_t segment_ops_override() {
+  const char* e = getenv("ETP_CPROG_SEGMENT_OPS");
+  if (!e || !*e) return 0;
+  const long v = strtol(e, nullptr, 10);
+  return v > 0 ? (uint32_t)v : 0;
+}
+
+inline void emit_op(std::string& s, const Program& p, uint32_t k) {
+  char buf[128];
+  const uint32_t a = p.a(k), b = p.b(k);
+  switch (p.opcode(k)) {
+    case CONST: snprintf(buf, sizeof buf, "  const uint64_t v%u = 0x%llxULL;\n", k, (unsigned long long)p.imm(k)); break;
+    case LV: snprintf(buf, sizeof buf, "  const uint64_t v%u = r.lv(q, %u);\n", k, a); break;
+    case NV: snprintf(buf, sizeof buf, "  const uint64_t v%u = r.nv(q, %u);\n", k, a); break;
+    case LA: snprintf(buf, sizeof buf, "  const uint64_t v%u = r.la(q, %u);\n", k, a); break;
+    case NA: snprintf(buf, sizeof buf, "  const uint64_t v%u = r.na(q, %u);\n", k, a); break;
+    case PI: snprintf(buf, sizeof buf, "  const uint64_t v%u = q.pi[%u];\n", k, a); break;
+    case CH: snprintf(buf, sizeof buf, "  const uint64_t v%u = q.lookup_ch[%u];\n", k, a); break;
+    case ADD: snprintf(buf, sizeof buf, "  const uint64_t v%u = gl::add(v%u, v%u);\n", k, a, b); break;
+    case SUB: snprintf(buf, sizeof buf, "  const uint64_t v%u = gl::sub(v%u, v%u);\n", k, a, b); break;
+    case MUL: snprintf(buf, sizeof buf, "  const uint64_t v%u = gl::mul(v%u, v%u);\n", k, a, b); break;
+    case EMIT: snprintf(buf, sizeof buf, "  r.cs.constraint(v%u);\n", a); break;
+    case EMIT_TRANSITION: snprintf(buf, sizeof buf, "  r.cs.transition(v%u);\n", a); break;
+    case EMIT_FIRST_ROW: snprintf(buf, sizeof buf, "  r.cs.first_row(v%u);\n", a); break;
+    case EMIT_LAST_ROW: snprintf(buf, sizeof buf, "  r.cs.last_row(v%u);\n", a); break;
+    default: buf[0] = 0;
+  }
+  s += buf;
+}
+
+inline std::string generate_cuda_segmented(const Program& p, bool split_columns, uint32_t segment_ops) {
+  std::string s;
+  s.reserve(80 * (size_t)p.n_ops + 4096);
+  s += "#define ETP_COMPACT_CODE 1\n";
+  if (split_columns) s += "#define ETP_SPLIT_COLUMNS 1\n";
+  s += "#include \"quotient_rt.cuh\"\n";
+  // segment boundaries: [begin, end) op ranges, cut after the first EMIT at or past the size limit
+  std::vector<std::pair<uint32_t, uint32_t>> segs;
+  uint32_t begin = 0;
+  for (uint32_t k = 0; k < p.n_ops; k++) {
+    const bool is_emit = p.opcode(k) >= EMIT;
+    if ((is_emit && k + 1 - begin >= segment_ops) || k + 1 == p.n_ops) {
+      segs.emplace_back(begin, k + 1);
+      begin = k + 1;
+    }
+  }
+  std::vector<uint8_t> need(p.n_ops);
+  std::string calls;
+  char buf[192];
+  for (size_t si = 0; si < segs.size(); si++) {
+    // transitive dependencies of this segment's emits (ops are in SSA order: one backward sweep)
+    std::fill(need.begin(), need.end(), 0);
+    bool any = false;
+    for (uint32_t k = segs[si].first; k < segs[si].second; k++)
+      if (p.opcode(k) >= EMIT) { need[k] = 1; any = true; }
+    if (!any) continue;  // trailing ops without an emit contribute nothing
+    for (uint32_t k = segs[si].second; k-- > 0;) {
+      if (!need[k]) continue;
+      const int op = p.opcode(k);
+      if (op >= EMIT) need[p.a(k)] = 1;
+      else if (op == ADD || op == SUB || op == MUL) need[p.a(k)] = need[p.b(k)] = 1;
+    }
+    snprintf(buf, sizeof buf, "static __device__ __noinline__ void etp_seg_%zu(const stark::QuotientParams& q, stark::RowCtx& r) {\n", si);
+    s += buf;
+    for (uint32_t k = 0; k < segs[si].second; k++)
+      if (need[k]) emit_op(s, p, k);
+    s += "}\n";
+    snprintf(buf, sizeof buf, "  etp_seg_%zu(q, r);\n", si);
+    calls += buf;
+  }
+  s += "extern \"C\" __global__ void __launch_bounds__(128) etp_cprog_quotient(const __grid_constant__ stark::QuotientParams q) {\n"
+       "  stark::RowCtx r;\n"
+       "  if (!stark::quotient_begin(q, r)) return;\n";
+  s += calls;
+  s += "  stark::quotient_end(q, r);\n}\n";
+  return s;
+}
+
 // CUDA source of the quotient kernel of this program (body between quotient_begin and quotient_end of
 // quotient_rt.cuh).  Straight-line SSA: register allocation and scheduling are ptxas's job.
 inline std::string generate_cuda(const Program& p, bool split_columns = false) {
+  const uint32_t forced = segment_ops_override();
+  if (forced ? p.n_ops > forced : p.n_ops > SEGMENT_THRESHOLD_OPS) return generate_cuda_segmented(p, split_columns, forced ? forced : SEGMENT_OPS);
   std::string s;
   s.reserve(64 * (size_t)p.n_ops + 1024);
   // small programs are fully inlined (as fast as a built-in table); large ones share one copy of the field

@@ -146,6 +146,21 @@ void jit_unload(JitKernel* k) {
   if (k) { k->library = nullptr; k->kernel = nullptr; }
 }
 
+// The CUDA source the library generates for a program (what NVRTC is given): for inspection and for tests that re-interpret the
+// generated code against the program.  Returns the source length (without the terminator) or a negative error; copies at most
+// cap - 1 bytes.
+extern "C" int64_t etp_cprog_generate_cuda(const uint64_t* program, size_t n_words, char* out, size_t cap) {
+  cprog::Program p;
+  if (!cprog::parse(program, n_words, 16, 8, &p).empty()) return ETP_ERR_INVALID;
+  const std::string src = cprog::generate_cuda(p);
+  if (out && cap) {
+    const size_t n = src.size() < cap - 1 ? src.size() : cap - 1;
+    memcpy(out, src.data(), n);
+    out[n] = 0;
+  }
+  return (int64_t)src.size();
+}
+
 // C ABI helper used by the CPU tests (no device needed): program words -> cubin size; proves that a table can be
 // compiled for sm_100a in this process.
 extern "C" int etp_cprog_compile_check(const uint64_t* program, size_t n_words, size_t* cubin_bytes_out, char* err, size_t err_len) {

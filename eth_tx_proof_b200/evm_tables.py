@@ -1,0 +1,370 @@
+"""EVM-style tables with REAL semantics, written as constraint programs for the generic table path (cprog.ProgramBuilder ->
+etp_table_register_ex / the oracle's interpreter).  The sources of evm_arithmetization 0.1.3's tables are not available offline
+(/root/reference/Cargo.lock:1675; SURVEY.md section 7, hard part 1), so these are NOT upstream's constraint lists: they are
+this repository's own layouts, built from the published designs the upstream tables follow, and their traces are checked
+against independent computations (Python integers, hashlib's SHA-3).  They show that the path proves real tables, not only
+shape stand-ins; `cprog.EVM_TABLE_SHAPES` keeps the stand-ins the benchmark's synthetic transaction uses.
+
+arithmetic   ADD, SUB, LT, GT, MUL on n_limbs x limb_bits-bit words (16 x 16 = 256 bits by default).
+             addcy (evm_arithmetization/src/arithmetic/addcy.rs, recalled design): with s_i = x_i + y_i - z_i and
+             t_i = s_i + cy_{i-1}, every t_i must be 0 or 2^w, and cy_i = t_i / 2^w is an EXPRESSION (no carry columns);
+             the last carry equals the CY column.  ADD: A + B = C + CY 2^W.  SUB / LT / GT: the same relation on permuted
+             operands (A - B = C with borrow CY; LT's result is CY).  MUL: schoolbook columns sum_{i+j=k} a_i b_j with
+             carries split into two range-checked limbs.  Every limb is range-checked by a logUp lookup into a counter column
+             (filters = the row's operation flags), and the table exposes (opcode, A, B, C / CY) as a CTL port.
+keccak       Keccak-f[1600], one round per row, bit columns (below).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+from .cprog import NUM_CHALLENGES, P, Column, Filter, Program, ProgramBuilder
+
+OP_ADD, OP_SUB, OP_LT, OP_GT, OP_MUL = range(5)
+
+
+def arithmetic_layout(n_limbs: int = 16, limb_bits: int = 16) -> dict:
+    L = {"FLAG": 0, "A": 5, "B": 5 + n_limbs, "C": 5 + 2 * n_limbs, "CY": 5 + 3 * n_limbs, "CARRY_LO": 6 + 3 * n_limbs,
+         "CARRY_HI": 6 + 4 * n_limbs, "COUNTER": 6 + 5 * n_limbs, "FREQ": 7 + 5 * n_limbs, "cols": 8 + 5 * n_limbs,
+         "n_limbs": n_limbs, "limb_bits": limb_bits}
+    return L
+
+
+def arithmetic_builder(n_limbs: int = 16, limb_bits: int = 16, with_ctl: bool = False, emit_lookups: bool = True) -> ProgramBuilder:
+    """Constraint degree 3.  with_ctl: the table is the LOOKED side of a CTL on the tuple (opcode = 1 + operation, A limbs,
+    B limbs, C limbs, CY) filtered by "the row holds an operation" (upstream opens the operands and the result to the CPU table
+    the same way).  emit_lookups=False: the table's own constraints only (Program.check_trace on the trace domain)."""
+    L = arithmetic_layout(n_limbs, limb_bits)
+    b = ProgramBuilder(L["cols"], 0, 3)
+    lv, nv = b.lv, b.nv
+    W = 1 << limb_bits
+    inv_w = pow(W, P - 2, P)
+    flags = [lv(L["FLAG"] + k) for k in range(5)]
+    for f in flags:
+        b.constraint(f * (f - 1))
+    fsum = flags[0] + flags[1] + flags[2] + flags[3] + flags[4]
+    b.constraint(fsum * (fsum - 1))  # at most one operation per row; none = padding row
+    A = [lv(L["A"] + i) for i in range(n_limbs)]
+    B = [lv(L["B"] + i) for i in range(n_limbs)]
+    C = [lv(L["C"] + i) for i in range(n_limbs)]
+    cy = lv(L["CY"])
+    b.constraint(cy * (cy - 1))
+
+    def addcy(filt, x, y, z):
+        """filt * [x + y == z + cy 2^(n w)], limb by limb without carry columns."""
+        carry = None
+        for i in range(n_limbs):
+            t = x[i] + y[i] - z[i]
+            if carry is not None:
+                t = t + carry
+            b.constraint(filt * (t * (t - W)))
+            carry = t * inv_w
+        b.constraint(filt * (carry - cy))
+
+    addcy(flags[OP_ADD], A, B, C)                       # A + B = C + cy 2^W
+    addcy(flags[OP_SUB] + flags[OP_LT], C, B, A)        # C + B = A + cy 2^W  <=>  A - B = C - cy 2^W: cy = [A < B]
+    addcy(flags[OP_GT], C, A, B)                        # B - A = C - cy 2^W: cy = [B < A] = [A > B]
+    # MUL: column k of the schoolbook product plus the incoming carry = c_k + 2^w * outgoing carry, carries = lo + 2^w hi
+    lo = [lv(L["CARRY_LO"] + i) for i in range(n_limbs)]
+    hi = [lv(L["CARRY_HI"] + i) for i in range(n_limbs)]
+    for k in range(n_limbs):
+        acc = None
+        for i in range(k + 1):
+            term = A[i] * B[k - i]
+            acc = term if acc is None else acc + term
+        if k:
+            acc = acc + lo[k - 1] + hi[k - 1] * W
+        b.constraint(flags[OP_MUL] * (acc - C[k] - (lo[k] + hi[k] * W) * W))
+    # range counter: 0, then +0 / +1 steps, ending at 2^w - 1: every w-bit value occurs
+    cnt, cnt_n = lv(L["COUNTER"]), nv(L["COUNTER"])
+    b.first_row(cnt)
+    d = cnt_n - cnt
+    b.transition(d * (d - 1))
+    b.last_row(cnt - (W - 1))
+    looking = [L["A"] + i for i in range(n_limbs)] + [L["B"] + i for i in range(n_limbs)] + [L["C"] + i for i in range(n_limbs)] + \
+              [L["CARRY_LO"] + i for i in range(n_limbs)] + [L["CARRY_HI"] + i for i in range(n_limbs)]
+    b.add_lookup(looking, L["COUNTER"], L["FREQ"])
+    if with_ctl:
+        opcode = Column([(L["FLAG"] + k, k + 1) for k in range(5)])
+        cols = [opcode] + [Column.single(L["A"] + i) for i in range(n_limbs)] + [Column.single(L["B"] + i) for i in range(n_limbs)] + \
+               [Column.single(L["C"] + i) for i in range(n_limbs)] + [Column.single(L["CY"])]
+        filt = Filter(constants=[Column([(L["FLAG"] + k, 1) for k in range(5)])])
+        for k in range(NUM_CHALLENGES):
+            b.add_ctl_z(k, [(cols, filt)])
+    if emit_lookups:
+        b.emit_lookup_constraints()
+        if with_ctl:
+            b.emit_ctl_constraints()
+    return b
+
+
+def arithmetic_program(n_limbs: int = 16, limb_bits: int = 16, with_ctl: bool = False, emit_lookups: bool = True) -> Program:
+    return arithmetic_builder(n_limbs, limb_bits, with_ctl, emit_lookups).build()
+
+
+def _limbs(v: int, n_limbs: int, limb_bits: int) -> List[int]:
+    return [(v >> (limb_bits * i)) & ((1 << limb_bits) - 1) for i in range(n_limbs)]
+
+
+def arithmetic_row(op: int, a: int, b_: int, n_limbs: int = 16, limb_bits: int = 16) -> Tuple[List[int], List[int], List[int], int, List[int], List[int]]:
+    """One operation computed with Python integers -> (A limbs, B limbs, C limbs, CY, carry lo limbs, carry hi limbs)."""
+    bits = n_limbs * limb_bits
+    M = 1 << bits
+    W = 1 << limb_bits
+    lo, hi = [0] * n_limbs, [0] * n_limbs
+    if op == OP_ADD:
+        c, cy = (a + b_) % M, (a + b_) >> bits
+    elif op in (OP_SUB, OP_LT):
+        c, cy = (a - b_) % M, int(a < b_)
+    elif op == OP_GT:
+        c, cy = (b_ - a) % M, int(b_ < a)
+    else:
+        c, cy = (a * b_) % M, 0
+        al, bl = _limbs(a, n_limbs, limb_bits), _limbs(b_, n_limbs, limb_bits)
+        carry = 0
+        for k in range(n_limbs):
+            s = sum(al[i] * bl[k - i] for i in range(k + 1)) + carry
+            carry = s >> limb_bits
+            assert carry < W * W
+            lo[k], hi[k] = carry % W, carry // W
+    return _limbs(a, n_limbs, limb_bits), _limbs(b_, n_limbs, limb_bits), _limbs(c, n_limbs, limb_bits), cy, lo, hi
+
+
+def arithmetic_trace(log_n: int, n_limbs: int = 16, limb_bits: int = 16, seed: int = 31, n_ops: int = None):
+    """-> (trace, ops): `ops` = [(opcode, a, b, result)] of the active rows (result = C, or CY for LT / GT) — what a looking
+    table would send through the CTL.  Needs 2^log_n >= 2^limb_bits rows (the range counter)."""
+    from .synthetic import _rand
+
+    L = arithmetic_layout(n_limbs, limb_bits)
+    n, W = 1 << log_n, 1 << limb_bits
+    assert n >= W, "the range counter needs 2^limb_bits rows"
+    n_ops = n - n // 4 if n_ops is None else n_ops
+    t = np.zeros((L["cols"], n), dtype=np.uint64)
+    words = [[int(x) for x in _rand(seed, k, n)] for k in range(2 * ((n_limbs * limb_bits + 63) // 64) + 1)]
+    per = (n_limbs * limb_bits + 63) // 64
+    M = 1 << (n_limbs * limb_bits)
+    freq = np.zeros(n, dtype=np.int64)
+    ops = []
+    for r in range(n):
+        if r < n_ops:
+            op = words[2 * per][r] % 5
+            a = sum(words[k][r] << (64 * k) for k in range(per)) % M
+            b_ = sum(words[per + k][r] << (64 * k) for k in range(per)) % M
+            if r % 7 == 3:
+                b_ = a  # equal operands: LT / GT give 0, SUB gives 0
+            if r % 11 == 5:
+                a, b_ = M - 1, M - 1 - (r % 3)  # carries ripple through every limb
+            al, bl, cl, cy, lo, hi = arithmetic_row(op, a, b_, n_limbs, limb_bits)
+            t[L["FLAG"] + op, r] = 1
+            ops.append((op, a, b_, cy if op in (OP_LT, OP_GT) else sum(c << (limb_bits * i) for i, c in enumerate(cl))))
+        else:
+            al = bl = cl = lo = hi = [0] * n_limbs
+            cy = 0
+        for i in range(n_limbs):
+            t[L["A"] + i, r], t[L["B"] + i, r], t[L["C"] + i, r] = al[i], bl[i], cl[i]
+            t[L["CARRY_LO"] + i, r], t[L["CARRY_HI"] + i, r] = lo[i], hi[i]
+        t[L["CY"], r] = cy
+        for v in list(al) + list(bl) + list(cl) + list(lo) + list(hi):
+            freq[v] += 1
+    # counter: 0 .. W - 1, then stays at W - 1; the multiplicity of a value sits on its FIRST row
+    cnt = np.minimum(np.arange(n), W - 1)
+    t[L["COUNTER"]] = cnt.astype(np.uint64)
+    fr = np.zeros(n, dtype=np.int64)
+    fr[:W] = freq[:W]
+    t[L["FREQ"]] = fr.astype(np.uint64)
+    return t, ops
+
+
+# ---- Keccak-f[1600]: one round per row, the state as 1600 bit columns ------------------------------------------------------------
+# FIPS 202 section 3.2 (theta, rho, pi, chi, iota), lane (x, y) bit z at A[64 (5 y + x) + z].  Own layout, degree 3 — the same
+# decomposition the upstream keccak table uses (evm_arithmetization/src/keccak/keccak_stark.rs, recalled: bit columns, XORs as
+# low-degree polynomials, round flags, 24 rows per permutation), with more committed intermediates to keep every step explicit:
+#   FLAG[24]  one-hot round flags, rotating
+#   ID        permutation index (constant over a permutation's 24 rows): ties the input port to the output port
+#   A[1600]   state before the round (boolean)
+#   T1[320]   xor3(A[x][0], A[x][1], A[x][2])            C[320]  xor3(T1[x], A[x][3], A[x][4])   (theta's column parities)
+#   AP[1600]  A xor D,  D[x][z] = C[x-1][z] xor C[x+1][z-1]                                     (after theta)
+#   AQ[64]    chi's output bit for lane (0, 0), before iota
+#   OUT[1600] the round's output: chi(pi(rho(AP))) and, for lane (0, 0), AQ xor RC[round]
+# next.A == OUT except across a permutation boundary (round 23 -> round 0 of the next permutation).
+# CTL ports (the looked side of keccak_sponge -> keccak in upstream): (ID, 50 input limbs of 32 bits) on round-0 rows and
+# (ID, 50 output limbs) on round-23 rows.
+KECCAK_ROUNDS = 24
+
+
+def _keccak_constants():
+    rc = []
+    r = 1
+    for _ in range(KECCAK_ROUNDS):  # rc(t) LFSR, FIPS 202 algorithm 5
+        v = 0
+        for j in range(7):
+            if r & 1:
+                v |= 1 << ((1 << j) - 1)
+            r <<= 1
+            if r & 0x100:
+                r ^= 0x171
+        rc.append(v)
+    rot = [[0] * 5 for _ in range(5)]  # rot[x][y], FIPS 202 algorithm 2
+    x, y = 1, 0
+    for t in range(24):
+        rot[x][y] = ((t + 1) * (t + 2) // 2) % 64
+        x, y = y, (2 * x + 3 * y) % 5
+    return rc, rot
+
+
+KECCAK_RC, KECCAK_ROT = _keccak_constants()
+
+
+def keccak_layout() -> dict:
+    L = {"FLAG": 0, "ID": 24, "A": 25, "T1": 1625, "C": 1945, "AP": 2265, "AQ": 3865, "OUT": 3929, "cols": 5529}
+    return L
+
+
+def _bit(base: int, x: int, y: int, z: int) -> int:
+    return base + 64 * (5 * y + x) + z
+
+
+def keccak_builder(with_ctl: bool = False, emit_lookups: bool = True) -> ProgramBuilder:
+    L = keccak_layout()
+    b = ProgramBuilder(L["cols"], 0, 3)
+    lv, nv = b.lv, b.nv
+    xor2 = lambda p, q: p + q - p * q * 2
+    xor3 = lambda p, q, r: p + q + r - (p * q + q * r + r * p) * 2 + p * q * r * 4
+    f = [lv(L["FLAG"] + r) for r in range(KECCAK_ROUNDS)]
+    fsum = None
+    for r in range(KECCAK_ROUNDS):
+        b.constraint(f[r] * (f[r] - 1))
+        fsum = f[r] if fsum is None else fsum + f[r]
+        b.transition(nv(L["FLAG"] + (r + 1) % KECCAK_ROUNDS) - f[r])
+    b.constraint(fsum - 1)
+    b.first_row(f[0] - 1)
+    not_last = b.const(1) - f[KECCAK_ROUNDS - 1]
+    b.transition(not_last * (nv(L["ID"]) - lv(L["ID"])))
+    A = lambda x, y, z: lv(_bit(L["A"], x, y, z))
+    AP = lambda x, y, z: lv(_bit(L["AP"], x, y, z))
+    OUT = lambda x, y, z: lv(_bit(L["OUT"], x, y, z))
+    for x in range(5):
+        for y in range(5):
+            for z in range(64):
+                a = A(x, y, z)
+                b.constraint(a * (a - 1))
+    # theta
+    C = [[None] * 64 for _ in range(5)]
+    for x in range(5):
+        for z in range(64):
+            t1, c = lv(L["T1"] + 64 * x + z), lv(L["C"] + 64 * x + z)
+            b.constraint(t1 - xor3(A(x, 0, z), A(x, 1, z), A(x, 2, z)))
+            b.constraint(c - xor3(t1, A(x, 3, z), A(x, 4, z)))
+            C[x][z] = c
+    for x in range(5):
+        for z in range(64):
+            d = xor2(C[(x + 4) % 5][z], C[(x + 1) % 5][(z + 63) % 64])
+            for y in range(5):
+                b.constraint(AP(x, y, z) - xor2(A(x, y, z), d))
+    # rho + pi: B[y][2x + 3y] = rot(AP[x][y], r[x][y]); bit z of a left rotation by r is bit z - r
+    B = [[None] * 5 for _ in range(5)]
+    for x in range(5):
+        for y in range(5):
+            r = KECCAK_ROT[x][y]
+            B[y][(2 * x + 3 * y) % 5] = [AP(x, y, (z - r) % 64) for z in range(64)]
+    # chi (+ iota on lane (0, 0))
+    for x in range(5):
+        for y in range(5):
+            for z in range(64):
+                e = xor2(B[x][y][z], (b.const(1) - B[(x + 1) % 5][y][z]) * B[(x + 2) % 5][y][z])
+                if (x, y) == (0, 0):
+                    aq = lv(L["AQ"] + z)
+                    b.constraint(aq - e)
+                    rc = None
+                    for r in range(KECCAK_ROUNDS):
+                        if (KECCAK_RC[r] >> z) & 1:
+                            rc = f[r] if rc is None else rc + f[r]
+                    b.constraint(OUT(0, 0, z) - (aq if rc is None else xor2(aq, rc)))
+                else:
+                    b.constraint(OUT(x, y, z) - e)
+    # the next row continues the permutation
+    for i in range(1600):
+        b.transition(not_last * (nv(L["A"] + i) - lv(L["OUT"] + i)))
+    if with_ctl:
+        def limbs(base):
+            return [Column.le_bits([base + 32 * k + j for j in range(32)]) for k in range(50)]
+
+        for k in range(NUM_CHALLENGES):  # CTL "inputs": looked on round-0 rows
+            b.add_ctl_z(k, [([Column.single(L["ID"])] + limbs(L["A"]), Filter(constants=[Column.single(L["FLAG"])]))])
+        for k in range(NUM_CHALLENGES):  # CTL "outputs": looked on round-23 rows
+            b.add_ctl_z(k, [([Column.single(L["ID"])] + limbs(L["OUT"]), Filter(constants=[Column.single(L["FLAG"] + KECCAK_ROUNDS - 1)]))])
+        if emit_lookups:
+            b.emit_lookup_constraints()
+            b.emit_ctl_constraints()
+    return b
+
+
+def keccak_program(with_ctl: bool = False, emit_lookups: bool = True) -> Program:
+    return keccak_builder(with_ctl, emit_lookups).build()
+
+
+def keccak_f(lanes: List[int]) -> List[int]:
+    """Keccak-f[1600] on 25 lanes (lane x + 5 y), plain Python — the definition the table is tested against."""
+    a = list(lanes)
+    M = (1 << 64) - 1
+    rotl = lambda v, r: ((v << r) | (v >> (64 - r))) & M if r else v
+    for rnd in range(KECCAK_ROUNDS):
+        c = [a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20] for x in range(5)]
+        d = [c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1) for x in range(5)]
+        a = [a[i] ^ d[i % 5] for i in range(25)]
+        bq = [0] * 25
+        for x in range(5):
+            for y in range(5):
+                bq[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(a[x + 5 * y], KECCAK_ROT[x][y])
+        a = [bq[x + 5 * y] ^ ((~bq[(x + 1) % 5 + 5 * y] & M) & bq[(x + 2) % 5 + 5 * y]) for y in range(5) for x in range(5)]
+        a[0] ^= KECCAK_RC[rnd]
+    return a
+
+
+def keccak_trace(log_n: int, inputs: List[List[int]] = None, seed: int = 17):
+    """-> (trace, io): one permutation per 24 rows (the last rows of the table hold the first rounds of one more permutation:
+    the round flags keep rotating); io = [(id, input lanes, output lanes)] of the COMPLETE permutations."""
+    from .synthetic import _rand
+
+    L = keccak_layout()
+    n = 1 << log_n
+    n_perm = -(-n // KECCAK_ROUNDS)
+    if inputs is None:
+        words = [_rand(seed, k, n_perm) for k in range(25)]
+        inputs = [[int(words[k][p]) for k in range(25)] for p in range(n_perm)]
+        inputs[0] = [0] * 25
+    t = np.zeros((L["cols"], n), dtype=np.uint64)
+    bits = lambda lanes: np.array([(lanes[i] >> z) & 1 for i in range(25) for z in range(64)], dtype=np.uint64)
+    io = []
+    M = (1 << 64) - 1
+    rotl = lambda v, r: ((v << r) | (v >> (64 - r))) & M if r else v
+    for p in range(n_perm):
+        a = list(inputs[p % len(inputs)])
+        for rnd in range(KECCAK_ROUNDS):
+            row = p * KECCAK_ROUNDS + rnd
+            if row >= n:
+                break
+            t[L["FLAG"] + rnd, row] = 1
+            t[L["ID"], row] = p + 1
+            t[L["A"]:L["A"] + 1600, row] = bits(a)
+            t1 = [a[x] ^ a[x + 5] ^ a[x + 10] for x in range(5)]
+            c = [t1[x] ^ a[x + 15] ^ a[x + 20] for x in range(5)]
+            t[L["T1"]:L["T1"] + 320, row] = np.array([(t1[x] >> z) & 1 for x in range(5) for z in range(64)], dtype=np.uint64)
+            t[L["C"]:L["C"] + 320, row] = np.array([(c[x] >> z) & 1 for x in range(5) for z in range(64)], dtype=np.uint64)
+            d = [c[(x + 4) % 5] ^ rotl(c[(x + 1) % 5], 1) for x in range(5)]
+            ap = [a[i] ^ d[i % 5] for i in range(25)]
+            t[L["AP"]:L["AP"] + 1600, row] = bits(ap)
+            bq = [0] * 25
+            for x in range(5):
+                for y in range(5):
+                    bq[y + 5 * ((2 * x + 3 * y) % 5)] = rotl(ap[x + 5 * y], KECCAK_ROT[x][y])
+            out = [bq[x + 5 * y] ^ ((~bq[(x + 1) % 5 + 5 * y] & M) & bq[(x + 2) % 5 + 5 * y]) for y in range(5) for x in range(5)]
+            t[L["AQ"]:L["AQ"] + 64, row] = np.array([(out[0] >> z) & 1 for z in range(64)], dtype=np.uint64)
+            out[0] ^= KECCAK_RC[rnd]
+            t[L["OUT"]:L["OUT"] + 1600, row] = bits(out)
+            a = out
+        else:
+            io.append((p + 1, list(inputs[p % len(inputs)]), a))
+    return t, io

@@ -250,6 +250,11 @@ int etp_table_register(etp_ctx *ctx, const uint64_t *program, size_t n_words, co
                        int *table_id_out);
 /* parse + NVRTC-compile a program without a device (CI / the Rust build): cubin size, or an error message */
 int etp_cprog_compile_check(const uint64_t *program, size_t n_words, size_t *cubin_bytes_out, char *err, size_t err_len);
+/* The CUDA source generated for a program (the text NVRTC compiles): one straight-line kernel, or — above 16384 ops, where ptxas
+ * time on one function explodes — a chain of __noinline__ segment functions, each holding the dependencies of its own
+ * constraints (ETP_CPROG_SEGMENT_OPS=<n> forces segments of n ops).  Returns the source length or a negative error; copies at
+ * most cap - 1 bytes + terminator into `out` (may be NULL to query the length). */
+int64_t etp_cprog_generate_cuda(const uint64_t *program, size_t n_words, char *out, size_t cap);
 
 /* General registration.  `aux_spec` describes every auxiliary polynomial the prover must generate for this table
  * (starky/src/lookup.rs Lookup / Column / Filter, starky/src/cross_table_lookup.rs CtlZData) as u64 words:

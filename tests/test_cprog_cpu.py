@@ -134,3 +134,97 @@ def test_evm_table_shapes_compile_for_sm100a():
         rc, size, err = _compile_check(prog.words)
         assert rc == 0 and size > 10000, (name, err)
     assert set(cprog.TX_TABLE_DEGREE_BITS) == set(cprog.EVM_TABLE_SHAPES) | {"logic", "memory"}
+
+
+def _generated_source(words):
+    import eth_tx_proof_b200 as etp
+
+    L = etp.load_library()
+    ptr = words.ctypes.data_as(C.POINTER(C.c_uint64))
+    n = L.etp_cprog_generate_cuda(ptr, words.size, None, 0)
+    assert n > 0
+    buf = C.create_string_buffer(n + 1)
+    assert L.etp_cprog_generate_cuda(ptr, words.size, buf, n + 1) == n
+    return buf.value.decode()
+
+
+def _interpret_generated(src, lv, nv, la, na, pi, ch):
+    """Re-interprets the CUDA text the library generates (one kernel, or segment functions called in order) with Python integers
+    -> [(kind, value)] in the order the consumer would see them."""
+    import re
+
+    val = re.compile(r"^\s*const uint64_t v(\d+) = (.+);$")
+    emit = re.compile(r"^\s*r\.cs\.(constraint|transition|first_row|last_row)\(v(\d+)\);$")
+    kinds = {"constraint": 10, "transition": 11, "first_row": 12, "last_row": 13}
+    funcs, cur, order = {}, None, []
+    for line in src.splitlines():
+        m = re.match(r"^static __device__ __noinline__ void (etp_seg_\d+)\(", line)
+        if m:
+            cur = funcs.setdefault(m.group(1), [])
+            continue
+        if "etp_cprog_quotient(" in line:
+            cur = funcs.setdefault("kernel", [])
+            continue
+        if line.strip() == "}":
+            cur = None
+            continue
+        m = re.match(r"^\s*(etp_seg_\d+)\(q, r\);$", line)
+        if m and cur is funcs.get("kernel"):
+            order.append(m.group(1))
+            continue
+        if cur is not None and (val.match(line) or emit.match(line)):
+            cur.append(line)
+    out = []
+
+    def run(lines):
+        v = {}
+        for line in lines:
+            m = val.match(line)
+            if m:
+                k, rhs = int(m.group(1)), m.group(2)
+                g = re.match(r"^gl::(add|sub|mul)\(v(\d+), v(\d+)\)$", rhs)
+                ld = re.match(r"^r\.(lv|nv|la|na)\(q, (\d+)\)$", rhs)
+                if g:
+                    a, b = v[int(g.group(2))], v[int(g.group(3))]  # KeyError = a value used in a segment that does not define it
+                    v[k] = {"add": a + b, "sub": a - b, "mul": a * b}[g.group(1)] % P
+                elif ld:
+                    v[k] = {"lv": lv, "nv": nv, "la": la, "na": na}[ld.group(1)][int(ld.group(2))] % P
+                elif rhs.startswith("q.pi["):
+                    v[k] = pi[int(rhs[5:-1])] % P
+                elif rhs.startswith("q.lookup_ch["):
+                    v[k] = ch[int(rhs[12:-1])] % P
+                else:
+                    v[k] = int(rhs.replace("ULL", ""), 16) % P
+            else:
+                m = emit.match(line)
+                out.append((kinds[m.group(1)], v[int(m.group(2))]))
+
+    run(funcs["kernel"])
+    for name in order:
+        run(funcs[name])
+    return out, len(order)
+
+
+@pytest.mark.parametrize("segment_ops", [0, 25, 300])
+def test_generated_cuda_is_the_program_also_when_segmented(segment_ops, monkeypatch):
+    """Large programs are emitted as a chain of segment functions (cprog.h: ptxas cannot digest a 50 k-op table as one
+    function): the generated text, re-interpreted with Python integers on random rows, produces exactly the program's
+    emissions in the program's order — for the one-function form and for forced segment sizes — and it compiles for sm_100a."""
+    from eth_tx_proof_b200 import cprog, evm_tables as et
+
+    if segment_ops:
+        monkeypatch.setenv("ETP_CPROG_SEGMENT_OPS", str(segment_ops))
+    else:
+        monkeypatch.delenv("ETP_CPROG_SEGMENT_OPS", raising=False)
+    rng = np.random.default_rng(segment_ops)
+    for prog in (cprog.memory_program(), et.arithmetic_program(4, 5, with_ctl=True), cprog.fibonacci_program()):
+        rnd = lambda n: [int(x) % P for x in rng.integers(0, 2**64, max(n, 1), dtype=np.uint64)]
+        lv, nv, la, na = rnd(prog.n_trace), rnd(prog.n_trace), rnd(prog.n_aux), rnd(prog.n_aux)
+        pi, ch = rnd(prog.n_pi), rnd(max(prog.n_ch, 8))
+        want = [(k, v % P) for k, v in prog.evaluate(lv, nv, la, na, pi, ch)]
+        got, n_seg = _interpret_generated(_generated_source(prog.words), lv, nv, la, na, pi, ch)
+        assert got == want
+        segmented = bool(segment_ops and len(prog.ops) > segment_ops)
+        assert (n_seg >= 1) == segmented and (not segmented or n_seg >= len(prog.ops) // (4 * segment_ops))
+        rc, size, err = _compile_check(prog.words)
+        assert rc == 0 and size > 1000, err

@@ -1,0 +1,146 @@
+"""CPU tests of the tables with real semantics (eth_tx_proof_b200/evm_tables.py: own layouts of an arithmetic table — ADD, SUB,
+LT, GT, MUL on 256-bit words through 16-bit limbs, addcy without carry columns, logUp range checks — and of a bit-level
+Keccak-f[1600] round table; evm_arithmetization 0.1.3's own sources are not available offline, /root/reference/Cargo.lock:1675).
+The traces are checked against independent computations (Python integers, hashlib's SHA-3), the constraint programs hold on them
+and only on them, the oracle proves the tables and the independent verifier accepts the proofs; the arithmetic table is the looked
+side of a cross-table lookup whose looking table lists operations and results."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+import stark_verifier as V
+from eth_tx_proof_b200 import cprog
+from eth_tx_proof_b200 import evm_tables as et
+
+P = cprog.P
+
+
+@pytest.mark.parametrize("n_limbs,limb_bits,log_n", [(4, 5, 6), (16, 6, 7)])
+def test_arithmetic_table_semantics_constraints_and_proof(n_limbs, limb_bits, log_n):
+    t, ops = et.arithmetic_trace(log_n, n_limbs, limb_bits)
+    M = 1 << (n_limbs * limb_bits)
+    seen = set()
+    for op, a, b, r in ops:
+        want = {et.OP_ADD: (a + b) % M, et.OP_SUB: (a - b) % M, et.OP_LT: int(a < b), et.OP_GT: int(a > b), et.OP_MUL: (a * b) % M}[op]
+        assert r == want
+        seen.add(op)
+    assert seen == {0, 1, 2, 3, 4}
+    own = et.arithmetic_program(n_limbs, limb_bits, emit_lookups=False)
+    assert own.check_trace(t) == -1
+    L = et.arithmetic_layout(n_limbs, limb_bits)
+    rows = {op: next(r for r in range(t.shape[1]) if t[L["FLAG"] + op, r]) for op in range(5)}
+    for op, col in ((et.OP_ADD, L["C"]), (et.OP_SUB, L["C"] + 1), (et.OP_LT, L["CY"]), (et.OP_GT, L["CY"]), (et.OP_MUL, L["C"] + n_limbs - 1)):
+        bad = t.copy()
+        bad[col, rows[op]] = np.uint64(int(bad[col, rows[op]]) ^ 1)  # a wrong result limb / comparison bit
+        assert own.check_trace(bad) // 1000 == rows[op]
+    prog = et.arithmetic_program(n_limbs, limb_bits)
+    tid = oracle.register_table_ex(prog, prog.aux_spec)
+    V.verify(oracle.stark_prove(tid, t), program=prog, max_queries=2)
+    # a limb outside the range: the row's arithmetic can be made consistent, the logUp range check cannot
+    bad = t.copy()
+    r = rows[et.OP_ADD]
+    W = 1 << limb_bits
+    bad[L["C"], r] = np.uint64(int(bad[L["C"], r]) + W)       # C_0 + 2^w ...
+    bad[L["C"] + 1, r] = np.uint64((int(bad[L["C"] + 1, r]) - 1) % P)  # ... and C_1 - 1: the same integer, limbs out of range
+    with pytest.raises((V.VerifyError, RuntimeError)):
+        V.verify(oracle.stark_prove(tid, bad), program=prog, max_queries=2)
+
+
+def test_arithmetic_table_as_the_looked_side_of_a_ctl():
+    """A looking table lists (opcode, A, B, C, CY) tuples with a filter; the arithmetic table opens the same tuple on its active
+    rows: both proofs verify on one transcript and the CTL sums match; a looking row with a wrong result breaks the sum."""
+    from test_ctl_oracle import verify_all
+
+    n_limbs, limb_bits, log_n = 4, 5, 6
+    L = et.arithmetic_layout(n_limbs, limb_bits)
+    t, _ = et.arithmetic_trace(log_n, n_limbs, limb_bits)
+    width = 2 + 3 * n_limbs + 1  # filter, opcode, A, B, C, CY
+
+    def looking_table(corrupt=False):
+        n = t.shape[1]
+        lt = np.zeros((width, n), dtype=np.uint64)
+        active = sum(t[L["FLAG"] + k] for k in range(5)).astype(np.uint64)
+        lt[0] = active
+        lt[1] = sum(t[L["FLAG"] + k] * np.uint64(k + 1) for k in range(5))
+        for i in range(n_limbs):
+            lt[2 + i], lt[2 + n_limbs + i], lt[2 + 2 * n_limbs + i] = t[L["A"] + i], t[L["B"] + i], t[L["C"] + i]
+        lt[2 + 3 * n_limbs] = t[L["CY"]]
+        lt = lt[:, ::-1].copy()  # another row order: a lookup is a multiset relation
+        if corrupt:
+            r = int(np.nonzero(lt[0])[0][0])
+            lt[2 + 2 * n_limbs, r] = np.uint64(int(lt[2 + 2 * n_limbs, r]) ^ 1)
+        b = cprog.ProgramBuilder(width, 0, 3)
+        b.constraint(b.lv(0) * (b.lv(0) - 1))
+        for k in range(cprog.NUM_CHALLENGES):
+            b.add_ctl_z(k, [(list(range(1, width)), cprog.Filter(constants=[cprog.Column.single(0)]))])
+        b.emit_lookup_constraints()
+        b.emit_ctl_constraints()
+        return b.build(), lt
+
+    def prove(tables):
+        tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tables]
+        batches = [oracle.Batch.from_values(tr, 1, 4) for _, _, tr in tables]
+        ch = oracle.HostChallenger()
+        for bb in batches:
+            ch.observe(bb.cap)
+        ctl_ch = ch.get_n(4)
+        proofs = []
+        for tid, (_, _, tr), bb in zip(tids, tables, batches):
+            ch.compact()
+            proofs.append(oracle.prove_with_commitment(tid, tr, bb, ch, ctl_ch))
+        return proofs, [bb.cap for bb in batches]
+
+    arith = et.arithmetic_program(n_limbs, limb_bits, with_ctl=True)
+    ctls = [([0], 1)]
+    lp, lt = looking_table()
+    tables = [("cpu_ops", lp, lt), ("arithmetic", arith, t)]
+    proofs, caps = prove(tables)
+    verify_all(tables, ctls, proofs, caps, max_queries=2)
+    lp, lt = looking_table(corrupt=True)
+    tables = [("cpu_ops", lp, lt), ("arithmetic", arith, t)]
+    proofs, caps = prove(tables)
+    with pytest.raises(V.VerifyError, match="Cross-table lookup"):
+        verify_all(tables, ctls, proofs, caps, max_queries=1)
+
+
+def _sha3_256(msg: bytes) -> bytes:
+    rate = 136
+    m = bytearray(msg) + b"\x06"
+    m += b"\x00" * (-len(m) % rate)
+    m[-1] |= 0x80
+    st = [0] * 25
+    for off in range(0, len(m), rate):
+        for i in range(rate // 8):
+            st[i] ^= int.from_bytes(m[off + 8 * i:off + 8 * i + 8], "little")
+        st = et.keccak_f(st)
+    return b"".join(x.to_bytes(8, "little") for x in st[:4])
+
+
+def test_keccak_table_against_sha3_constraints_and_proof():
+    """keccak_f (the definition the trace generator follows) reproduces hashlib's SHA3-256; the 5529-column trace — one round per
+    row — satisfies the 7155 constraints of the table's program, a flipped state bit does not; the oracle proves the table and the
+    verifier accepts; the input / output limbs the CTL ports open are the permutation's."""
+    for msg in (b"", b"abc", bytes(range(200))):
+        assert _sha3_256(msg) == hashlib.sha3_256(msg).digest()
+    assert et.KECCAK_RC[0] == 1 and et.KECCAK_RC[23] == 0x8000000080008008 and et.KECCAK_ROT[1][0] == 1 and et.KECCAK_ROT[3][2] == 25 and et.KECCAK_ROT[2][3] == 15
+    t, io = et.keccak_trace(6)
+    L = et.keccak_layout()
+    assert t.shape == (L["cols"], 64) and len(io) == 2
+    for pid, lanes_in, lanes_out in io:
+        assert et.keccak_f(lanes_in) == lanes_out
+        first, last = (pid - 1) * 24, (pid - 1) * 24 + 23
+        limb = lambda base, row, k: sum(int(t[base + 32 * k + j, row]) << j for j in range(32))
+        assert [limb(L["A"], first, k) for k in range(50)] == [(lanes_in[k // 2] >> (32 * (k % 2))) & 0xFFFFFFFF for k in range(50)]
+        assert [limb(L["OUT"], last, k) for k in range(50)] == [(lanes_out[k // 2] >> (32 * (k % 2))) & 0xFFFFFFFF for k in range(50)]
+    prog = et.keccak_program()
+    assert (prog.n_trace, prog.n_constraints, prog.degree) == (5529, 7155, 3)
+    assert prog.check_trace(t) == -1
+    bad = t.copy()
+    bad[L["AP"] + 700, 9] ^= np.uint64(1)
+    assert prog.check_trace(bad) != -1
+    tid = oracle.register_table_ex(prog, prog.aux_spec)
+    V.verify(oracle.stark_prove(tid, t), program=prog, max_queries=2)
+    with pytest.raises(V.VerifyError):
+        V.verify(oracle.stark_prove(tid, bad), program=prog, max_queries=2)
