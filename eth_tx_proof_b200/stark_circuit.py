@@ -37,8 +37,6 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
-import numpy as np
-
 from . import circuit as cc
 from . import cprog, wire
 from .circuit import NoopGate, P
@@ -171,10 +169,10 @@ def verify_stark_proof_in_circuit(b: GadgetBuilder, program: cprog.Program, word
     ch.observe(quot_cap_t)
     zeta = ch.get_ext()
     zeta_batch = local_t + aux_t + quot_t
-    next_batch = local_next = next_t + aux_next_t
+    next_batch = next_t + aux_next_t
     ctl_batch = [(t, b.zero) for t in W.ctl_zs_first]
     ch.observe_ext(zeta_batch)
-    ch.observe_ext(local_next)
+    ch.observe_ext(next_batch)
     ch.observe_ext(ctl_batch)
     fri_alpha = ch.get_ext()
     betas = []
