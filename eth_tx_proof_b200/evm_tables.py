@@ -13,6 +13,7 @@ arithmetic   ADD, SUB, LT, GT, MUL on n_limbs x limb_bits-bit words (16 x 16 = 2
              carries split into two range-checked limbs.  Every limb is range-checked by a logUp lookup into a counter column
              (filters = the row's operation flags), and the table exposes (opcode, A, B, C / CY) as a CTL port.
 keccak       Keccak-f[1600], one round per row, bit columns (below).
+keccak256    Keccak-256 (Ethereum's hash) of one-block messages: the looking side of the keccak table's input / output CTLs.
 """
 from __future__ import annotations
 
@@ -188,9 +189,10 @@ def arithmetic_trace(log_n: int, n_limbs: int = 16, limb_bits: int = 16, seed: i
 #   AP[1600]  A xor D,  D[x][z] = C[x-1][z] xor C[x+1][z-1]                                     (after theta)
 #   AQ[64]    chi's output bit for lane (0, 0), before iota
 #   OUT[1600] the round's output: chi(pi(rho(AP))) and, for lane (0, 0), AQ xor RC[round]
+#   REAL      1 on the rows of a permutation some other table asked for, 0 on padding permutations (constant over a permutation)
 # next.A == OUT except across a permutation boundary (round 23 -> round 0 of the next permutation).
-# CTL ports (the looked side of keccak_sponge -> keccak in upstream): (ID, 50 input limbs of 32 bits) on round-0 rows and
-# (ID, 50 output limbs) on round-23 rows.
+# CTL ports (the looked side of keccak_sponge -> keccak in upstream): (ID, 50 input limbs of 32 bits) on the round-0 rows and
+# (ID, 50 output limbs) on the round-23 rows of REAL permutations (filter = REAL * round flag).
 KECCAK_ROUNDS = 24
 
 
@@ -218,7 +220,7 @@ KECCAK_RC, KECCAK_ROT = _keccak_constants()
 
 
 def keccak_layout() -> dict:
-    L = {"FLAG": 0, "ID": 24, "A": 25, "T1": 1625, "C": 1945, "AP": 2265, "AQ": 3865, "OUT": 3929, "cols": 5529}
+    L = {"FLAG": 0, "ID": 24, "A": 25, "T1": 1625, "C": 1945, "AP": 2265, "AQ": 3865, "OUT": 3929, "REAL": 5529, "cols": 5530}
     return L
 
 
@@ -242,6 +244,9 @@ def keccak_builder(with_ctl: bool = False, emit_lookups: bool = True) -> Program
     b.first_row(f[0] - 1)
     not_last = b.const(1) - f[KECCAK_ROUNDS - 1]
     b.transition(not_last * (nv(L["ID"]) - lv(L["ID"])))
+    real = lv(L["REAL"])
+    b.constraint(real * (real - 1))
+    b.transition(not_last * (nv(L["REAL"]) - real))
     A = lambda x, y, z: lv(_bit(L["A"], x, y, z))
     AP = lambda x, y, z: lv(_bit(L["AP"], x, y, z))
     OUT = lambda x, y, z: lv(_bit(L["OUT"], x, y, z))
@@ -292,9 +297,9 @@ def keccak_builder(with_ctl: bool = False, emit_lookups: bool = True) -> Program
             return [Column.le_bits([base + 32 * k + j for j in range(32)]) for k in range(50)]
 
         for k in range(NUM_CHALLENGES):  # CTL "inputs": looked on round-0 rows
-            b.add_ctl_z(k, [([Column.single(L["ID"])] + limbs(L["A"]), Filter(constants=[Column.single(L["FLAG"])]))])
+            b.add_ctl_z(k, [([Column.single(L["ID"])] + limbs(L["A"]), Filter(products=[(L["REAL"], L["FLAG"])]))])
         for k in range(NUM_CHALLENGES):  # CTL "outputs": looked on round-23 rows
-            b.add_ctl_z(k, [([Column.single(L["ID"])] + limbs(L["OUT"]), Filter(constants=[Column.single(L["FLAG"] + KECCAK_ROUNDS - 1)]))])
+            b.add_ctl_z(k, [([Column.single(L["ID"])] + limbs(L["OUT"]), Filter(products=[(L["REAL"], L["FLAG"] + KECCAK_ROUNDS - 1)]))])
         if emit_lookups:
             b.emit_lookup_constraints()
             b.emit_ctl_constraints()
@@ -325,29 +330,35 @@ def keccak_f(lanes: List[int]) -> List[int]:
 
 def keccak_trace(log_n: int, inputs: List[List[int]] = None, seed: int = 17):
     """-> (trace, io): one permutation per 24 rows (the last rows of the table hold the first rounds of one more permutation:
-    the round flags keep rotating); io = [(id, input lanes, output lanes)] of the COMPLETE permutations."""
+    the round flags keep rotating); io = [(id, input lanes, output lanes)] of the COMPLETE permutations.  With `inputs` given,
+    permutation p < len(inputs) is REAL (id p + 1) and the rest of the table is padding (zero state, REAL = 0)."""
     from .synthetic import _rand
 
     L = keccak_layout()
     n = 1 << log_n
     n_perm = -(-n // KECCAK_ROUNDS)
+    n_real = n // KECCAK_ROUNDS if inputs is None else len(inputs)
+    assert n_real <= n // KECCAK_ROUNDS, "a real permutation needs its 24 rows"
     if inputs is None:
         words = [_rand(seed, k, n_perm) for k in range(25)]
         inputs = [[int(words[k][p]) for k in range(25)] for p in range(n_perm)]
         inputs[0] = [0] * 25
+    else:
+        inputs = [list(x) for x in inputs] + [[0] * 25] * (n_perm - len(inputs))
     t = np.zeros((L["cols"], n), dtype=np.uint64)
     bits = lambda lanes: np.array([(lanes[i] >> z) & 1 for i in range(25) for z in range(64)], dtype=np.uint64)
     io = []
     M = (1 << 64) - 1
     rotl = lambda v, r: ((v << r) | (v >> (64 - r))) & M if r else v
     for p in range(n_perm):
-        a = list(inputs[p % len(inputs)])
+        a = list(inputs[p])
         for rnd in range(KECCAK_ROUNDS):
             row = p * KECCAK_ROUNDS + rnd
             if row >= n:
                 break
             t[L["FLAG"] + rnd, row] = 1
             t[L["ID"], row] = p + 1
+            t[L["REAL"], row] = int(p < n_real)
             t[L["A"]:L["A"] + 1600, row] = bits(a)
             t1 = [a[x] ^ a[x + 5] ^ a[x + 10] for x in range(5)]
             c = [t1[x] ^ a[x + 15] ^ a[x + 20] for x in range(5)]
@@ -366,5 +377,116 @@ def keccak_trace(log_n: int, inputs: List[List[int]] = None, seed: int = 17):
             t[L["OUT"]:L["OUT"] + 1600, row] = bits(out)
             a = out
         else:
-            io.append((p + 1, list(inputs[p % len(inputs)]), a))
+            if p < n_real:
+                io.append((p + 1, list(inputs[p]), a))
     return t, io
+
+
+# ---- Keccak-256 of short messages: the looking side of the two keccak CTLs ---------------------------------------------------------
+# One row per message of at most 135 bytes (one rate block; upstream's keccak_sponge table absorbs any number of blocks and XORs them
+# into the state through the logic table — with one block and a zero initial state the XOR is the block itself).  Columns:
+#   F, ID, LEN, POS[136] (one-hot position of the first padding byte = LEN), BYTE[136] (the padded block: message bytes, 0x01 at LEN,
+#   zeros, 0x80 added to the last byte — Keccak's pad10*1 with the legacy 0x01 domain byte Ethereum uses), OUT[50] (the permutation's
+#   output as 32-bit limbs: OUT[0..8] is the digest), COUNTER / FREQ (every BYTE is range-checked to 8 bits by a logUp lookup).
+# CTLs: (ID, 34 block limbs, 16 zero capacity limbs) into the keccak table's inputs, (ID, OUT[50]) into its outputs, filter F.
+RATE_BYTES = 136
+
+
+def keccak256_layout() -> dict:
+    return {"F": 0, "ID": 1, "LEN": 2, "POS": 3, "BYTE": 3 + RATE_BYTES, "OUT": 3 + 2 * RATE_BYTES, "COUNTER": 53 + 2 * RATE_BYTES,
+            "FREQ": 54 + 2 * RATE_BYTES, "cols": 55 + 2 * RATE_BYTES}
+
+
+def keccak256_builder(with_ctl: bool = True, emit_lookups: bool = True) -> ProgramBuilder:
+    L = keccak256_layout()
+    b = ProgramBuilder(L["cols"], 0, 3)
+    lv, nv = b.lv, b.nv
+    f = lv(L["F"])
+    b.constraint(f * (f - 1))
+    pos = [lv(L["POS"] + i) for i in range(RATE_BYTES)]
+    byte = [lv(L["BYTE"] + i) for i in range(RATE_BYTES)]
+    total = length = None
+    for i in range(RATE_BYTES):
+        b.constraint(pos[i] * (pos[i] - 1))
+        total = pos[i] if total is None else total + pos[i]
+        if i:
+            length = pos[i] * i if length is None else length + pos[i] * i
+    b.constraint(total - f)                      # exactly one padding position on a message row, none on a padding row
+    b.constraint(lv(L["LEN"]) - length)
+    after = None                                 # after[i] = [LEN < i]
+    for i in range(RATE_BYTES - 1):
+        if after is not None:
+            b.constraint(after * byte[i])        # past the first padding byte: zero
+        b.constraint(pos[i] * (byte[i] - 1))     # the first padding byte: 0x01
+        after = pos[i] if after is None else after + pos[i]
+    b.constraint(byte[RATE_BYTES - 1] - (f * 0x80 + pos[RATE_BYTES - 1]))  # the last byte: 0x80, or 0x81 when LEN = 135
+    cnt = lv(L["COUNTER"])
+    b.first_row(cnt)
+    d = nv(L["COUNTER"]) - cnt
+    b.transition(d * (d - 1))
+    b.last_row(cnt - 255)
+    b.add_lookup([L["BYTE"] + i for i in range(RATE_BYTES)], L["COUNTER"], L["FREQ"])
+    if with_ctl:
+        block = [Column([(L["BYTE"] + 4 * k + j, 1 << (8 * j)) for j in range(4)]) for k in range(RATE_BYTES // 4)]
+        zero = [Column.constant_(0)] * (50 - len(block))
+        filt = Filter(constants=[Column.single(L["F"])])
+        for k in range(NUM_CHALLENGES):
+            b.add_ctl_z(k, [([Column.single(L["ID"])] + block + zero, filt)])
+        for k in range(NUM_CHALLENGES):
+            b.add_ctl_z(k, [([Column.single(L["ID"])] + [Column.single(L["OUT"] + i) for i in range(50)], filt)])
+    if emit_lookups:
+        b.emit_lookup_constraints()
+        if with_ctl:
+            b.emit_ctl_constraints()
+    return b
+
+
+def keccak256_program(with_ctl: bool = True, emit_lookups: bool = True) -> Program:
+    return keccak256_builder(with_ctl, emit_lookups).build()
+
+
+def keccak256(msg: bytes) -> bytes:
+    """Keccak-256 (the legacy 0x01 padding: Ethereum's hash) of a message of any length, by the plain-Python permutation."""
+    m = bytearray(msg) + b"\x01"
+    m += b"\x00" * (-len(m) % RATE_BYTES)
+    m[-1] |= 0x80
+    st = [0] * 25
+    for off in range(0, len(m), RATE_BYTES):
+        for i in range(RATE_BYTES // 8):
+            st[i] ^= int.from_bytes(m[off + 8 * i:off + 8 * i + 8], "little")
+        st = keccak_f(st)
+    return b"".join(x.to_bytes(8, "little") for x in st[:4])
+
+
+def keccak256_system(messages: List[bytes], log_n_sponge: int = 8, log_n_keccak: int = None):
+    """-> (tables, ctls, digests): the message table (looking) and the Keccak-f table (looked) linked by the input and output
+    CTLs; digests read from the message table's OUT limbs."""
+    L = keccak256_layout()
+    n = 1 << log_n_sponge
+    assert n >= 256 and len(messages) <= n and all(len(m) < RATE_BYTES for m in messages)
+    t = np.zeros((L["cols"], n), dtype=np.uint64)
+    lanes_in = []
+    freq = np.zeros(256, dtype=np.int64)
+    for r, msg in enumerate(messages):
+        blk = bytearray(msg) + b"\x01" + b"\x00" * (RATE_BYTES - len(msg) - 1)
+        blk[-1] |= 0x80
+        t[L["F"], r], t[L["ID"], r], t[L["LEN"], r] = 1, r + 1, len(msg)
+        t[L["POS"] + len(msg), r] = 1
+        t[L["BYTE"]:L["BYTE"] + RATE_BYTES, r] = np.frombuffer(bytes(blk), dtype=np.uint8)
+        lanes_in.append([int.from_bytes(blk[8 * i:8 * i + 8], "little") for i in range(17)] + [0] * 8)
+    for r in range(n):
+        for v in t[L["BYTE"]:L["BYTE"] + RATE_BYTES, r]:
+            freq[int(v)] += 1
+    t[L["COUNTER"]] = np.minimum(np.arange(n), 255).astype(np.uint64)
+    t[L["FREQ"], :256] = freq.astype(np.uint64)
+    if log_n_keccak is None:
+        log_n_keccak = max(5, (KECCAK_ROUNDS * len(messages) - 1).bit_length())
+    kt, io = keccak_trace(log_n_keccak, inputs=lanes_in)
+    digests = []
+    for r, (_, _, out) in enumerate(io):
+        for k in range(50):
+            t[L["OUT"] + k, r] = (out[k // 2] >> (32 * (k % 2))) & 0xFFFFFFFF
+        digests.append(b"".join(x.to_bytes(8, "little") for x in out[:4]))
+    tables = [("keccak256", keccak256_program(), t), ("keccak", keccak_program(with_ctl=True), kt)]
+    ctls = [([0], 1), ([0], 1)]
+    return tables, ctls, digests

@@ -119,8 +119,8 @@ def _sha3_256(msg: bytes) -> bytes:
 
 
 def test_keccak_table_against_sha3_constraints_and_proof():
-    """keccak_f (the definition the trace generator follows) reproduces hashlib's SHA3-256; the 5529-column trace — one round per
-    row — satisfies the 7155 constraints of the table's program, a flipped state bit does not; the oracle proves the table and the
+    """keccak_f (the definition the trace generator follows) reproduces hashlib's SHA3-256; the 5530-column trace — one round per
+    row — satisfies the 7157 constraints of the table's program, a flipped state bit does not; the oracle proves the table and the
     verifier accepts; the input / output limbs the CTL ports open are the permutation's."""
     for msg in (b"", b"abc", bytes(range(200))):
         assert _sha3_256(msg) == hashlib.sha3_256(msg).digest()
@@ -135,7 +135,7 @@ def test_keccak_table_against_sha3_constraints_and_proof():
         assert [limb(L["A"], first, k) for k in range(50)] == [(lanes_in[k // 2] >> (32 * (k % 2))) & 0xFFFFFFFF for k in range(50)]
         assert [limb(L["OUT"], last, k) for k in range(50)] == [(lanes_out[k // 2] >> (32 * (k % 2))) & 0xFFFFFFFF for k in range(50)]
     prog = et.keccak_program()
-    assert (prog.n_trace, prog.n_constraints, prog.degree) == (5529, 7155, 3)
+    assert (prog.n_trace, prog.n_constraints, prog.degree) == (5530, 7157, 3)
     assert prog.check_trace(t) == -1
     bad = t.copy()
     bad[L["AP"] + 700, 9] ^= np.uint64(1)
@@ -144,3 +144,49 @@ def test_keccak_table_against_sha3_constraints_and_proof():
     V.verify(oracle.stark_prove(tid, t), program=prog, max_queries=2)
     with pytest.raises(V.VerifyError):
         V.verify(oracle.stark_prove(tid, bad), program=prog, max_queries=2)
+
+
+def test_keccak256_of_messages_proven_by_two_tables_and_two_ctls():
+    """Keccak-256 (Ethereum's hash) of short messages: the message table pads the block (pad10*1, byte range checks by logUp) and
+    looks (id, 50 input limbs) and (id, 50 output limbs) up in the Keccak-f table — upstream's keccak_sponge -> keccak CTL pair.
+    The digest of the empty message is the well-known c5d246...a470; both tables prove on one transcript, the verifier accepts
+    and the CTL sums match; a wrong digest limb keeps both table proofs valid and breaks the cross-table lookup; a wrong padding
+    byte violates the message table's own constraints."""
+    from test_ctl_oracle import verify_all
+
+    msgs = [b"", b"abc", bytes(range(135)), b"The quick brown fox jumps over the lazy dog"]
+    tables, ctls, digests = et.keccak256_system(msgs)
+    assert digests[0].hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+    assert digests == [et.keccak256(m) for m in msgs]
+    L = et.keccak256_layout()
+    own = et.keccak256_program(with_ctl=False, emit_lookups=False)
+    assert own.check_trace(tables[0][2]) == -1
+
+    def prove(tabs):
+        tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tabs]
+        batches = [oracle.Batch.from_values(tr, 1, 4) for _, _, tr in tabs]
+        ch = oracle.HostChallenger()
+        for bb in batches:
+            ch.observe(bb.cap)
+        ctl_ch = ch.get_n(4)
+        proofs = []
+        for tid, (_, _, tr), bb in zip(tids, tabs, batches):
+            ch.compact()
+            proofs.append(oracle.prove_with_commitment(tid, tr, bb, ch, ctl_ch))
+        return proofs, [bb.cap for bb in batches]
+
+    proofs, caps = prove(tables)
+    zs = verify_all(tables, ctls, proofs, caps, max_queries=2)
+    assert [len(z) for z in zs] == [4, 4]
+    bad = tables[0][2].copy()
+    bad[L["OUT"] + 3, 1] ^= np.uint64(1)  # a digest limb of message 1
+    bad_tables = [(tables[0][0], tables[0][1], bad), tables[1]]
+    proofs, caps = prove(bad_tables)
+    with pytest.raises(V.VerifyError, match="Cross-table lookup"):
+        verify_all(bad_tables, ctls, proofs, caps, max_queries=1)
+    bad = tables[0][2].copy()
+    bad[L["BYTE"] + 3, 1] = 2  # message 1 = b"abc": byte 3 must be the 0x01 domain byte
+    assert own.check_trace(bad) // 1000 == 1
+    bad = tables[0][2].copy()
+    bad[L["BYTE"] + 135, 0] = 0  # the final 0x80 bit of pad10*1
+    assert own.check_trace(bad) // 1000 == 0
