@@ -8,7 +8,7 @@ pub mod sys;
 pub use sys::*;
 
 use std::ffi::CStr;
-use std::os::raw::c_int;
+use std::os::raw::{c_char, c_int};
 use std::ptr;
 
 /// One CUDA device + stream + scratch cache.  One per worker thread (`thread_local!`), like upstream's one tokio task per op
@@ -185,6 +185,26 @@ pub fn register_table(ctx: &Ctx, program: &[u64], aux_spec: &[u64]) -> i32 {
     ctx.check(rc);
     id as i32
 }
+
+/// Witness of one PoseidonGate row (`plonky2::gates::poseidon::PoseidonGenerator::run_once`): the 135 wires for the given inputs.
+/// The recursion layers' circuits are mostly PoseidonGate rows, so a generator in the fork can call this instead of the scalar
+/// permutation.
+pub fn poseidon_gate_wires(inputs: &[u64; 12], swap: bool) -> [u64; 135] {
+    let mut wires = [0u64; 135];
+    unsafe { etp_host_poseidon_gate_wires(inputs.as_ptr(), swap as c_int, wires.as_mut_ptr()) };
+    wires
+}
+
+/// The CUDA source the library generates for a constraint program (inspection / CI): one kernel, or segment functions above 16384 ops.
+pub fn generated_cuda(program: &[u64]) -> Option<String> {
+    let n = unsafe { etp_cprog_generate_cuda(program.as_ptr(), program.len(), std::ptr::null_mut(), 0) };
+    if n < 0 { return None; }
+    let mut buf = vec![0u8; n as usize + 1];
+    unsafe { etp_cprog_generate_cuda(program.as_ptr(), program.len(), buf.as_mut_ptr() as *mut c_char, buf.len()) };
+    buf.truncate(n as usize);
+    String::from_utf8(buf).ok()
+}
+
 
 /// plonky2's circuit prover on the device (`plonk::prover::prove` after witness generation): built once per circuit from the
 /// recorded vanishing polynomial (run `eval_vanishing_poly` on `recorder::Sym` over the virtual columns constants, sigmas,
