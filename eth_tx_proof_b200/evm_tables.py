@@ -140,7 +140,8 @@ def arithmetic_trace(log_n: int, n_limbs: int = 16, limb_bits: int = 16, seed: i
 
     L = arithmetic_layout(n_limbs, limb_bits)
     n, W = 1 << log_n, 1 << limb_bits
-    assert n >= W, "the range counter needs 2^limb_bits rows"
+    if n < W:
+        raise ValueError("the range counter needs 2^limb_bits rows")
     n_ops = n - n // 4 if n_ops is None else n_ops
     t = np.zeros((L["cols"], n), dtype=np.uint64)
     words = [[int(x) for x in _rand(seed, k, n)] for k in range(2 * ((n_limbs * limb_bits + 63) // 64) + 1)]
@@ -338,7 +339,8 @@ def keccak_trace(log_n: int, inputs: List[List[int]] = None, seed: int = 17):
     n = 1 << log_n
     n_perm = -(-n // KECCAK_ROUNDS)
     n_real = n // KECCAK_ROUNDS if inputs is None else len(inputs)
-    assert n_real <= n // KECCAK_ROUNDS, "a real permutation needs its 24 rows"
+    if n_real > n // KECCAK_ROUNDS:
+        raise ValueError("every real permutation needs its 24 rows")
     if inputs is None:
         words = [_rand(seed, k, n_perm) for k in range(25)]
         inputs = [[int(words[k][p]) for k in range(25)] for p in range(n_perm)]
@@ -463,7 +465,8 @@ def keccak256_system(messages: List[bytes], log_n_sponge: int = 8, log_n_keccak:
     CTLs; digests read from the message table's OUT limbs."""
     L = keccak256_layout()
     n = 1 << log_n_sponge
-    assert n >= 256 and len(messages) <= n and all(len(m) < RATE_BYTES for m in messages)
+    if n < 256 or len(messages) > n or any(len(m) >= RATE_BYTES for m in messages):
+        raise ValueError("the message table needs >= 256 rows (byte range counter), one row per message of at most 135 bytes")
     t = np.zeros((L["cols"], n), dtype=np.uint64)
     lanes_in = []
     freq = np.zeros(256, dtype=np.int64)
