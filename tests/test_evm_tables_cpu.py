@@ -190,3 +190,54 @@ def test_keccak256_of_messages_proven_by_two_tables_and_two_ctls():
     bad = tables[0][2].copy()
     bad[L["BYTE"] + 135, 0] = 0  # the final 0x80 bit of pad10*1
     assert own.check_trace(bad) // 1000 == 0
+
+
+def test_real_tables_through_the_recursion_layers():
+    """cpu_ops -> arithmetic (real semantics, one CTL) proven on one transcript, then wrapped, shrunk and rooted
+    (stark_circuit.transaction_recursion_plan with the oracle as the circuit prover): the root circuit's proof is accepted by the
+    Python verifier.  tools/real_tables_recursion_cpu.py runs the same with the Keccak-256 tables and the layers above."""
+    import types
+
+    import plonk_verifier
+    from eth_tx_proof_b200 import stark_circuit as sc
+    from test_circuit_cpu import _words_from_oracle_proof
+
+    n_limbs, limb_bits = 4, 5
+    L = et.arithmetic_layout(n_limbs, limb_bits)
+    at, _ = et.arithmetic_trace(6, n_limbs, limb_bits)
+    width = 2 + 3 * n_limbs + 1
+    lt = np.zeros((width, at.shape[1]), dtype=np.uint64)
+    lt[0] = sum(at[L["FLAG"] + k] for k in range(5)).astype(np.uint64)
+    lt[1] = sum(at[L["FLAG"] + k] * np.uint64(k + 1) for k in range(5))
+    for i in range(n_limbs):
+        lt[2 + i], lt[2 + n_limbs + i], lt[2 + 2 * n_limbs + i] = at[L["A"] + i], at[L["B"] + i], at[L["C"] + i]
+    lt[2 + 3 * n_limbs] = at[L["CY"]]
+    b = cprog.ProgramBuilder(width, 0, 3)
+    b.constraint(b.lv(0) * (b.lv(0) - 1))
+    for k in range(cprog.NUM_CHALLENGES):
+        b.add_ctl_z(k, [(list(range(1, width)), cprog.Filter(constants=[cprog.Column.single(0)]))])
+    b.emit_lookup_constraints()
+    b.emit_ctl_constraints()
+    tables = [("cpu_ops", b.build(), lt), ("arithmetic", et.arithmetic_program(n_limbs, limb_bits, with_ctl=True), at)]
+    ctls = [([0], 1)]
+    tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tables]
+    batches = [oracle.Batch.from_values(t, 1, 4) for _, _, t in tables]
+    ch = oracle.HostChallenger()
+    for bb in batches:
+        ch.observe(bb.cap)
+    ctl_ch = ch.get_n(4)
+    proofs, states = [], []
+    for tid, (_, _, t), bb in zip(tids, tables, batches):
+        states.append(ch.compact())
+        proofs.append(oracle.prove_with_commitment(tid, t, bb, ch, ctl_ch))
+    digest = [4, 3, 2, 1]
+
+    def circuit_prove(c, w, p):
+        pr = oracle.circuit_prove(c, w, p, digest)
+        plonk_verifier.verify(pr, c, pr["constants_sigmas_cap"], digest, max_queries=1)
+        return types.SimpleNamespace(c=c, digest=digest, constants_sigmas_cap=pr["constants_sigmas_cap"]), _words_from_oracle_proof(c, pr, p)
+
+    plan = sc.transaction_recursion_plan(tables, ctls, types.SimpleNamespace(stark_proofs=proofs, init_challenger_states=states, ctl_challenges=ctl_ch),
+                                         circuit_prove, max_queries=1)
+    assert [s["kind"] for s in plan] == ["wrapper", "shrink", "wrapper", "shrink", "root"]
+    assert plan[-1]["public_inputs"][-4:] == [int(x) for x in ctl_ch]
