@@ -14,6 +14,7 @@ arithmetic   ADD, SUB, LT, GT, MUL on n_limbs x limb_bits-bit words (16 x 16 = 2
              (filters = the row's operation flags), and the table exposes (opcode, A, B, C / CY) as a CTL port.
 keccak       Keccak-f[1600], one round per row, bit columns (below).
 keccak256    Keccak-256 (Ethereum's hash) of one-block messages: the looking side of the keccak table's input / output CTLs.
+byte_packing a 256-bit value <-> up to 32 bytes in memory: looked by a CPU-side port, looking into memory with 32 column sets.
 """
 from __future__ import annotations
 
@@ -493,3 +494,126 @@ def keccak256_system(messages: List[bytes], log_n_sponge: int = 8, log_n_keccak:
     tables = [("keccak256", keccak256_program(), t), ("keccak", keccak_program(with_ctl=True), kt)]
     ctls = [([0], 1), ([0], 1)]
     return tables, ctls, digests
+
+
+# ---- byte packing: between a 256-bit value and a byte sequence in memory ----------------------------------------------------------
+# evm_arithmetization/src/byte_packing/byte_packing_stark.rs, recalled design: one row per MLOAD_32BYTES / MSTORE_32BYTES-style
+# operation of LEN <= 32 bytes.  Columns: IS_READ, LEN_FLAG[32] (one-hot: LEN = i + 1), CTX, SEG, VIRT (address of the first byte),
+# TS, BYTE[32] (BYTE[0] = the LEAST significant byte of the value, i.e. the LAST byte in memory, as upstream stores them),
+# COUNTER / FREQ (bytes range-checked to 8 bits).  Constraints: the flags are boolean and at most one is set (none = padding row),
+# bytes at positions >= LEN are zero.  CTL ports:
+#   to the CPU table (looked by it here; upstream: cpu looks into byte packing): (IS_READ, CTX, SEG, VIRT, LEN, TS, 8 value limbs of
+#       32 bits = linear combinations of the bytes), filter = sum of the length flags;
+#   into MEMORY (looking, 32 column sets of ONE Z per challenge — the chunked-helper path): for byte i the tuple
+#       (IS_READ, CTX, SEG, VIRT + LEN - 1 - i, BYTE[i], TS), filter = [i < LEN] = sum_{j >= i} LEN_FLAG[j].
+NUM_PACK_BYTES = 32
+
+
+def byte_packing_layout() -> dict:
+    return {"IS_READ": 0, "LEN_FLAG": 1, "CTX": 33, "SEG": 34, "VIRT": 35, "TS": 36, "BYTE": 37, "COUNTER": 69, "FREQ": 70, "cols": 71}
+
+
+def byte_packing_builder(with_ctl: bool = True, emit_lookups: bool = True) -> ProgramBuilder:
+    L = byte_packing_layout()
+    b = ProgramBuilder(L["cols"], 0, 3)
+    lv, nv = b.lv, b.nv
+    is_read = lv(L["IS_READ"])
+    b.constraint(is_read * (is_read - 1))
+    flags = [lv(L["LEN_FLAG"] + i) for i in range(NUM_PACK_BYTES)]
+    total = None
+    for fl in flags:
+        b.constraint(fl * (fl - 1))
+        total = fl if total is None else total + fl
+    b.constraint(total * (total - 1))
+    b.constraint((b.const(1) - total) * is_read)          # a padding row carries no operation
+    covered = None                                        # [i < LEN] = sum_{j >= i} flag_j, built from the top
+    inside = [None] * NUM_PACK_BYTES
+    for i in reversed(range(NUM_PACK_BYTES)):
+        covered = flags[i] if covered is None else covered + flags[i]
+        inside[i] = covered
+    for i in range(NUM_PACK_BYTES):
+        b.constraint((b.const(1) - inside[i]) * lv(L["BYTE"] + i))  # bytes past the length are zero
+    cnt = lv(L["COUNTER"])
+    b.first_row(cnt)
+    d = nv(L["COUNTER"]) - cnt
+    b.transition(d * (d - 1))
+    b.last_row(cnt - 255)
+    b.add_lookup([L["BYTE"] + i for i in range(NUM_PACK_BYTES)], L["COUNTER"], L["FREQ"])
+    if with_ctl:
+        length = Column([(L["LEN_FLAG"] + i, i + 1) for i in range(NUM_PACK_BYTES)])
+        active = Column([(L["LEN_FLAG"] + i, 1) for i in range(NUM_PACK_BYTES)])
+        limbs = [Column([(L["BYTE"] + 4 * k + j, 1 << (8 * j)) for j in range(4)]) for k in range(8)]
+        cpu_cols = [Column.single(L[c]) for c in ("IS_READ", "CTX", "SEG", "VIRT")] + [length, Column.single(L["TS"])] + limbs
+        mem_sets = []
+        for i in range(NUM_PACK_BYTES):
+            # address of byte i = VIRT + LEN - 1 - i
+            addr = Column([(L["VIRT"], 1)] + [(L["LEN_FLAG"] + j, j + 1) for j in range(NUM_PACK_BYTES)], constant=P - 1 - i)
+            cols = [Column.single(L["IS_READ"]), Column.single(L["CTX"]), Column.single(L["SEG"]), addr, Column.single(L["BYTE"] + i),
+                    Column.single(L["TS"])]
+            mem_sets.append((cols, Filter(constants=[Column([(L["LEN_FLAG"] + j, 1) for j in range(i, NUM_PACK_BYTES)])])))
+        for k in range(NUM_CHALLENGES):  # CTL 0: the CPU side (this table is looked)
+            b.add_ctl_z(k, [(cpu_cols, Filter(constants=[active]))])
+        for k in range(NUM_CHALLENGES):  # CTL 1: 32 looking entries into memory
+            b.add_ctl_z(k, mem_sets)
+    if emit_lookups:
+        b.emit_lookup_constraints()
+        if with_ctl:
+            b.emit_ctl_constraints()
+    return b
+
+
+def byte_packing_program(with_ctl: bool = True, emit_lookups: bool = True) -> Program:
+    return byte_packing_builder(with_ctl, emit_lookups).build()
+
+
+def byte_packing_system(log_n: int = 8, n_ops: int = 24, seed: int = 41):
+    """-> (tables, ctls, ops): [cpu_side (looking CTL 0), byte_packing, memory_side (looked by CTL 1)] and the operations
+    [(is_read, ctx, seg, virt, len, ts, value)].  The two side tables are minimal port tables: a row of cpu_side lists one
+    operation with its 256-bit value as 8 limbs; a row of memory_side lists one (is_read, ctx, seg, addr, byte, ts) access."""
+    from .synthetic import _rand
+
+    L = byte_packing_layout()
+    n = 1 << log_n
+    if n < 256 or n_ops > n:
+        raise ValueError("the byte range counter needs >= 256 rows")
+    t = np.zeros((L["cols"], n), dtype=np.uint64)
+    r64 = [[int(x) for x in _rand(seed, k, n)] for k in range(8)]
+    ops, accesses = [], []
+    freq = np.zeros(256, dtype=np.int64)
+    for r in range(n_ops):
+        ln = 1 + r64[0][r] % NUM_PACK_BYTES if r % 5 else (NUM_PACK_BYTES if r % 10 else 1)
+        is_read, ctx, seg, virt, ts = r64[1][r] & 1, r64[2][r] % 7, r64[3][r] % 5, r64[4][r] % 1000, 1 + r
+        value = (r64[5][r] | (r64[6][r] << 64) | (r64[7][r] << 128) | (r64[0][r] << 192)) % (1 << (8 * ln))
+        t[L["IS_READ"], r], t[L["CTX"], r], t[L["SEG"], r], t[L["VIRT"], r], t[L["TS"], r] = is_read, ctx, seg, virt, ts
+        t[L["LEN_FLAG"] + ln - 1, r] = 1
+        for i in range(ln):
+            byte = (value >> (8 * i)) & 0xFF
+            t[L["BYTE"] + i, r] = byte
+            accesses.append((is_read, ctx, seg, virt + ln - 1 - i, byte, ts))
+        ops.append((is_read, ctx, seg, virt, ln, ts, value))
+    for r in range(n):
+        for v in t[L["BYTE"]:L["BYTE"] + NUM_PACK_BYTES, r]:
+            freq[int(v)] += 1
+    t[L["COUNTER"]] = np.minimum(np.arange(n), 255).astype(np.uint64)
+    t[L["FREQ"], :256] = freq.astype(np.uint64)
+
+    def port_table(rows, width):
+        m = 1 << max(5, (len(rows) - 1).bit_length())
+        pt = np.zeros((width + 1, m), dtype=np.uint64)
+        for r, row in enumerate(rows):
+            pt[0, r] = 1
+            pt[1:, r] = np.array(row, dtype=np.uint64)
+        pb = ProgramBuilder(width + 1, 0, 3)
+        pb.constraint(pb.lv(0) * (pb.lv(0) - 1))
+        for k in range(NUM_CHALLENGES):
+            pb.add_ctl_z(k, [(list(range(1, width + 1)), Filter(constants=[Column.single(0)]))])
+        pb.emit_lookup_constraints()
+        pb.emit_ctl_constraints()
+        return pb.build(), pt
+
+    cpu_rows = [[o[0], o[1], o[2], o[3], o[4], o[5]] + [(o[6] >> (32 * k)) & 0xFFFFFFFF for k in range(8)] for o in ops]
+    cpu_prog, cpu_t = port_table(cpu_rows, 14)
+    mem_prog, mem_t = port_table([list(a) for a in accesses], 6)
+    tables = [("cpu_side", cpu_prog, cpu_t), ("byte_packing", byte_packing_program(), t), ("memory_side", mem_prog, mem_t)]
+    ctls = [([0], 1), ([1], 2)]
+    return tables, ctls, ops

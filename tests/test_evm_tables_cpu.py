@@ -241,3 +241,50 @@ def test_real_tables_through_the_recursion_layers():
                                          circuit_prove, max_queries=1)
     assert [s["kind"] for s in plan] == ["wrapper", "shrink", "wrapper", "shrink", "root"]
     assert plan[-1]["public_inputs"][-4:] == [int(x) for x in ctl_ch]
+
+
+def test_byte_packing_table_with_thirty_two_looking_entries():
+    """Byte packing (own layout of the upstream design): one operation per row, bytes past the length are zero, every byte
+    range-checked; the table is looked by a CPU-side port on (is_read, address, length, timestamp, eight value limbs) and looks
+    into a memory-side port with 32 column sets in ONE Z per challenge (chunked helper columns) — address VIRT + LEN - 1 - i as a
+    linear-combination Column, filter [i < LEN] as a sum of flags.  Proven on one transcript, CTL sums verified; a memory access
+    with another byte breaks the lookup, a non-zero byte past the length breaks the table's own constraints."""
+    from test_ctl_oracle import verify_all
+
+    tables, ctls, ops = et.byte_packing_system()
+    L = et.byte_packing_layout()
+    t = tables[1][2]
+    for r, (is_read, ctx, seg, virt, ln, ts, value) in enumerate(ops):
+        assert sum(int(t[L["BYTE"] + i, r]) << (8 * i) for i in range(32)) == value < (1 << (8 * ln))
+    assert {o[4] for o in ops} >= {1, 32}
+    own = et.byte_packing_program(with_ctl=False, emit_lookups=False)
+    assert own.check_trace(t) == -1
+    bad = t.copy()
+    r = next(i for i, o in enumerate(ops) if o[4] < 32)
+    bad[L["BYTE"] + ops[r][4], r] = 7
+    assert own.check_trace(bad) // 1000 == r
+    prog = tables[1][1]
+    assert len(prog.ctl_zs) == 4 and [len(sets) for _, sets in prog.ctl_zs] == [1, 1, 32, 32] and prog.n_ctl_helper_cols == 32
+
+    def prove(tabs):
+        tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tabs]
+        batches = [oracle.Batch.from_values(tr, 1, 4) for _, _, tr in tabs]
+        ch = oracle.HostChallenger()
+        for bb in batches:
+            ch.observe(bb.cap)
+        ctl_ch = ch.get_n(4)
+        proofs = []
+        for tid, (_, _, tr), bb in zip(tids, tabs, batches):
+            ch.compact()
+            proofs.append(oracle.prove_with_commitment(tid, tr, bb, ch, ctl_ch))
+        return proofs, [bb.cap for bb in batches]
+
+    proofs, caps = prove(tables)
+    zs = verify_all(tables, ctls, proofs, caps, max_queries=2)
+    assert [len(z) for z in zs] == [2, 4, 2]
+    mem = tables[2][2].copy()
+    mem[5, 3] = np.uint64(int(mem[5, 3]) ^ 1)  # the byte of one memory access
+    bad_tables = [tables[0], tables[1], (tables[2][0], tables[2][1], mem)]
+    proofs, caps = prove(bad_tables)
+    with pytest.raises(V.VerifyError, match="Cross-table lookup 1"):
+        verify_all(bad_tables, ctls, proofs, caps, max_queries=1)
