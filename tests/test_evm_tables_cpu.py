@@ -288,3 +288,14 @@ def test_byte_packing_table_with_thirty_two_looking_entries():
     proofs, caps = prove(bad_tables)
     with pytest.raises(V.VerifyError, match="Cross-table lookup 1"):
         verify_all(bad_tables, ctls, proofs, caps, max_queries=1)
+
+
+def test_real_tables_compile_for_sm_100a():
+    """The product's NVRTC path accepts the real tables' programs (no GPU needed for the compile): full-width arithmetic with its
+    CTL port, byte packing with its 32 looking sets, the Keccak-256 message table.  (The Keccak-f table itself — 56 k ops — goes
+    through the segmented code generation and takes minutes: tests/test_cprog_cpu.py covers that path on small programs.)"""
+    from test_cprog_cpu import _compile_check
+
+    for prog in (et.arithmetic_program(16, 16, with_ctl=True), et.byte_packing_program(), et.keccak256_program()):
+        rc, size, err = _compile_check(prog.words)
+        assert rc == 0 and size > 100000, err
