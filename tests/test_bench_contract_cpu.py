@@ -51,3 +51,22 @@ def test_bench_script_parses_and_defaults():
     src = open(os.path.join(ROOT, "bench.py")).read()
     ast.parse(src)
     assert '"--impl"' in src and '"--gpus"' in src and '"--steps"' in src and '"--warmup"' in src
+
+
+def test_final_round2_line_carries_the_real_recursion_leg():
+    """profiles/r02_bench_2p22x128_v10_final.json (the default `python bench.py` at the end of round 2): the base contract keys,
+    and the tx_real_recursion leg — 7 table STARKs + 15 circuit proofs per transaction, every circuit over the real proof below it —
+    with its per-kind times adding up to less than the whole job, the in-run CPU parity figure, and the real block of 8."""
+    d = _load("r02_bench_2p22x128_v10_final.json")
+    assert d["metric"] == "commit_hbm_gbs" and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["e2e"]["value"] < d["value"]
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    r = d["tx_real_recursion"]
+    assert "error" not in r and r["circuit_proofs_per_tx"] == 15 and len(r["circuits"]) == 15
+    kinds = [c["kind"] for c in r["circuits"]]
+    assert kinds.count("wrapper") == 7 and kinds.count("shrink") == 7 and kinds[-1] == "root"
+    assert all(c["degree_bits"] == 13 for c in r["circuits"] if c["kind"] == "shrink")
+    per_kind = sum(v["sum"] for v in r["circuit_prove_ms"].values())
+    assert 0 < per_kind < r["tx_ms"] < 1000 and r["tx_per_min"] > 60000.0 / r["tx_ms"] * 0.9
+    assert r["cpu_baseline"]["parity"].startswith("FRI proof words ==") and r["cpu_baseline"]["cpu_ms"] > 50 * r["cpu_baseline"]["gpu_ms"]
+    assert [c["name"] for c in r["block_of_8_segments"]["circuits"]] == ["agg1", "agg2", "agg3", "block"]
+    assert r["block_of_8_segments"]["ms"] > 8 * r["tx_ms"] * 0.5
