@@ -617,3 +617,93 @@ def byte_packing_system(log_n: int = 8, n_ops: int = 24, seed: int = 41):
     tables = [("cpu_side", cpu_prog, cpu_t), ("byte_packing", byte_packing_program(), t), ("memory_side", mem_prog, mem_t)]
     ctls = [([0], 1), ([1], 2)]
     return tables, ctls, ops
+
+
+# ---- a transaction of seven tables with real semantics, wired like upstream's AllStark -----------------------------------------------
+# Table order = evm_arithmetization's Table::all(): arithmetic, byte_packing, cpu, keccak, keccak_sponge (here: the Keccak-256 message
+# table), logic, memory (here: a port table listing byte accesses; the recalled memory STARK of cprog.memory_program needs a
+# read-consistent access sequence, which random byte-packing operations are not).  Cross-table lookups, in upstream's order:
+#   cpu -> arithmetic | cpu -> byte_packing | cpu -> keccak_sponge | keccak_sponge -> keccak (inputs) | keccak_sponge -> keccak
+#   (outputs) | cpu -> logic | byte_packing -> memory
+# The cpu table is a DISPATCHER, not an interpreter: one row per operation with a one-hot family flag and a payload that is the
+# tuple the family's table opens — it stands where upstream's CPU table stands in the CTL graph, without its instruction semantics.
+REAL_TABLE_ORDER = ("arithmetic", "byte_packing", "cpu", "keccak", "keccak_sponge", "logic", "memory")
+REAL_CTLS = [([2], 0), ([2], 1), ([2], 4), ([4], 3), ([4], 3), ([2], 5), ([1], 6)]
+
+
+def _port_ctl(b: ProgramBuilder, cols, filt):
+    for k in range(NUM_CHALLENGES):
+        b.add_ctl_z(k, [(cols, filt)])
+
+
+def real_transaction_system(n_limbs: int = 4, limb_bits: int = 5, logic_limbs: int = 2, messages: List[bytes] = None, seed: int = 3):
+    """-> (tables, ctls): [(name, Program, trace)] in REAL_TABLE_ORDER and REAL_CTLS.  Small parameters keep the pure-Python
+    trace generators and the CPU oracle fast; n_limbs = 16, limb_bits = 16 is the 256-bit arithmetic (needs 2^16 rows)."""
+    from . import cprog as cp
+
+    messages = [b"", b"abc", b"eth-tx-proof on B200"] if messages is None else messages
+    # arithmetic (looked by cpu)
+    AL = arithmetic_layout(n_limbs, limb_bits)
+    log_a = max(6, limb_bits)
+    at, _ = arithmetic_trace(log_a, n_limbs, limb_bits, seed=seed)
+    arith = arithmetic_program(n_limbs, limb_bits, with_ctl=True)
+    a_rows = [[sum((k + 1) * int(at[AL["FLAG"] + k, r]) for k in range(5))] + [int(at[AL[c] + i, r]) for c in "ABC" for i in range(n_limbs)] +
+              [int(at[AL["CY"], r])] for r in range(at.shape[1]) if any(at[AL["FLAG"] + k, r] for k in range(5))]
+    # byte packing (looked by cpu, looking into memory)
+    ptables, _, pops = byte_packing_system(seed=seed + 1)
+    pack_t, mem_prog, mem_t = ptables[1][2], ptables[2][1], ptables[2][2]
+    p_rows = [[o[0], o[1], o[2], o[3], o[4], o[5]] + [(o[6] >> (32 * k)) & 0xFFFFFFFF for k in range(8)] for o in pops]
+    # Keccak-256 messages (looked by cpu, looking into keccak twice) and Keccak-f
+    ktables, _, digests = keccak256_system(messages)
+    KL = keccak256_layout()
+    kb = keccak256_builder(with_ctl=False, emit_lookups=False)  # own constraints + the byte lookup; ports added in CTL order below
+    _port_ctl(kb, [Column.single(KL["ID"]), Column.single(KL["LEN"])] + [Column.single(KL["OUT"] + i) for i in range(8)],
+              Filter(constants=[Column.single(KL["F"])]))
+    block = [Column([(KL["BYTE"] + 4 * k + j, 1 << (8 * j)) for j in range(4)]) for k in range(RATE_BYTES // 4)]
+    filt = Filter(constants=[Column.single(KL["F"])])
+    _port_ctl(kb, [Column.single(KL["ID"])] + block + [Column.constant_(0)] * (50 - len(block)), filt)
+    _port_ctl(kb, [Column.single(KL["ID"])] + [Column.single(KL["OUT"] + i) for i in range(50)], filt)
+    kb.emit_lookup_constraints()
+    kb.emit_ctl_constraints()
+    k_rows = [[r + 1, len(m)] + [int.from_bytes(d[4 * i:4 * i + 4], "little") for i in range(8)] for r, (m, d) in enumerate(zip(messages, digests))]
+    # logic (looked by cpu)
+    LL = cp.logic_layout(logic_limbs)
+    lt = cp.logic_trace(6, logic_limbs, seed=seed + 2)
+    lb = cp.logic_builder(logic_limbs)
+    limb = lambda base, k: Column.le_bits([base + 32 * k + j for j in range(32)])
+    l_cols = [Column([(LL["IS_AND"], 1), (LL["IS_OR"], 2), (LL["IS_XOR"], 3)])] + [limb(LL["X"], k) for k in range(logic_limbs)] + \
+             [limb(LL["Y"], k) for k in range(logic_limbs)] + [Column.single(LL["RES"] + k) for k in range(logic_limbs)]
+    _port_ctl(lb, l_cols, Filter(constants=[Column([(LL["IS_AND"], 1), (LL["IS_OR"], 1), (LL["IS_XOR"], 1)])]))
+    lb.emit_lookup_constraints()
+    lb.emit_ctl_constraints()
+    word = lambda base, k, r: sum(int(lt[base + 32 * k + j, r]) << j for j in range(32))
+    l_rows = [[int(lt[LL["IS_AND"], r]) + 2 * int(lt[LL["IS_OR"], r]) + 3 * int(lt[LL["IS_XOR"], r])] + [word(LL["X"], k, r) for k in range(logic_limbs)] +
+              [word(LL["Y"], k, r) for k in range(logic_limbs)] + [int(lt[LL["RES"] + k, r]) for k in range(logic_limbs)]
+              for r in range(lt.shape[1]) if lt[LL["IS_AND"], r] or lt[LL["IS_OR"], r] or lt[LL["IS_XOR"], r]]
+    # the cpu dispatcher: family flags + payload; CTL order: arithmetic, byte_packing, keccak_sponge, logic
+    families = [a_rows, p_rows, k_rows, l_rows]
+    width = max(len(rows[0]) for rows in families)
+    n_rows = sum(len(rows) for rows in families)
+    log_c = max(5, (n_rows - 1).bit_length())
+    ct = np.zeros((4 + width, 1 << log_c), dtype=np.uint64)
+    r = 0
+    for fam, rows in enumerate(families):
+        for row in rows:
+            ct[fam, r] = 1
+            ct[4:4 + len(row), r] = np.array(row, dtype=np.uint64)
+            r += 1
+    cb = ProgramBuilder(4 + width, 0, 3)
+    fsum = None
+    for fam in range(4):
+        fl = cb.lv(fam)
+        cb.constraint(fl * (fl - 1))
+        fsum = fl if fsum is None else fsum + fl
+    cb.constraint(fsum * (fsum - 1))
+    for fam, rows in enumerate(families):
+        _port_ctl(cb, list(range(4, 4 + len(rows[0]))), Filter(constants=[Column.single(fam)]))
+    cb.emit_lookup_constraints()
+    cb.emit_ctl_constraints()
+    tables = [("arithmetic", arith, at), ("byte_packing", byte_packing_program(), pack_t), ("cpu", cb.build(), ct),
+              ("keccak", keccak_program(with_ctl=True), ktables[1][2]), ("keccak_sponge", kb.build(), ktables[0][2]),
+              ("logic", lb.build(), lt), ("memory", mem_prog, mem_t)]
+    return tables, list(REAL_CTLS)

@@ -299,3 +299,43 @@ def test_real_tables_compile_for_sm_100a():
     for prog in (et.arithmetic_program(16, 16, with_ctl=True), et.byte_packing_program(), et.keccak256_program()):
         rc, size, err = _compile_check(prog.words)
         assert rc == 0 and size > 100000, err
+
+
+def test_seven_real_tables_wired_like_all_stark():
+    """evm_tables.real_transaction_system: arithmetic, byte packing, cpu (dispatcher), keccak, keccak sponge (Keccak-256 messages),
+    logic, memory (port) — upstream's table order and its seven cross-table lookups — proven on ONE transcript
+    (prove_with_traces' shape) and verified including every CTL sum.  tools/real_tables_recursion_cpu.py takes the same system
+    through the wrapper / shrink / root / aggregation / block circuits (profiles/r02_real_tables_recursion_cpu.log)."""
+    from test_ctl_oracle import verify_all
+
+    tables, ctls = et.real_transaction_system()
+    assert tuple(n for n, _, _ in tables) == et.REAL_TABLE_ORDER and ctls == et.REAL_CTLS
+    tids = [oracle.register_table_ex(p, p.aux_spec) for _, p, _ in tables]
+    batches = [oracle.Batch.from_values(tr, 1, 4) for _, _, tr in tables]
+    ch = oracle.HostChallenger()
+    for bb in batches:
+        ch.observe(bb.cap)
+    ctl_ch = ch.get_n(4)
+    proofs = []
+    for tid, (_, _, tr), bb in zip(tids, tables, batches):
+        ch.compact()
+        proofs.append(oracle.prove_with_commitment(tid, tr, bb, ch, ctl_ch))
+    zs = verify_all(tables, ctls, proofs, [bb.cap for bb in batches], max_queries=1)
+    assert [len(z) for z in zs] == [2, 4, 8, 4, 6, 2, 2]
+    # an operation the cpu table claims but the arithmetic table did not perform: every table proof stands, CTL 0 fails
+    bad = tables[2][2].copy()
+    r = int(np.nonzero(bad[0])[0][0])
+    bad[4 + 1, r] = np.uint64(int(bad[4 + 1, r]) ^ 1)
+    bad_tables = list(tables)
+    bad_tables[2] = (tables[2][0], tables[2][1], bad)
+    batches = [oracle.Batch.from_values(tr, 1, 4) for _, _, tr in bad_tables]
+    ch = oracle.HostChallenger()
+    for bb in batches:
+        ch.observe(bb.cap)
+    ctl_ch = ch.get_n(4)
+    proofs = []
+    for tid, (_, _, tr), bb in zip(tids, bad_tables, batches):
+        ch.compact()
+        proofs.append(oracle.prove_with_commitment(tid, tr, bb, ch, ctl_ch))
+    with pytest.raises(V.VerifyError, match="Cross-table lookup 0"):
+        verify_all(bad_tables, ctls, proofs, [bb.cap for bb in batches], max_queries=1)
