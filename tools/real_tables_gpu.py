@@ -5,9 +5,8 @@ prove_with_traces through the C ABI, every table proof compared word for word wi
 
 NOT run on a GPU in round 2 (the round's GPU budget was spent before this script existed); the pieces it uses were: the arithmetic
 table and the segmented kernels in tests/test_gpu_evm_tables.py, prove_with_traces in tests/test_gpu_ctl.py.  The Keccak-f table's
-56 k-op program takes ~9 minutes of NVRTC on first registration (segmented code generation, csrc/cprog.h); --skip-keccak proves
-the six other tables as a system of their own is NOT possible (the CTLs into keccak would dangle), so the flag only skips the
-device run of that one table's stand-alone quotient check."""
+56 k-op program takes ~9 minutes of NVRTC on first registration (segmented code generation, csrc/cprog.h; cached on disk with
+ETP_CUBIN_CACHE); --skip-keccak only registers (compiles) the six other tables and exits."""
 import argparse
 import os
 import sys
