@@ -16,8 +16,14 @@ divided by the device time (CUDA events on the library's stream, max over ranks)
   cpu_baseline  the oracle (C restatement, OpenMP, all host cores) on a bounded sample of the workload
   stark     BASELINE.json configs[2]: single-table STARK prove (memory-shaped table 2^22 rows): ms and
             proofs/min (whole job, all ranks; two prover contexts per GPU)
-  tx        synthetic transaction: seven table proofs of the evm_arithmetization shapes (BASELINE configs[3]/[4] shape
-            only: no CTLs, no recursion), ms per transaction and transactions/min (whole job, all ranks)
+  tx        synthetic transaction: seven table proofs of the evm_arithmetization shapes linked by upstream's seven CTLs on one
+            transcript (prove_with_traces' shape), ms per transaction and transactions/min (whole job, all ranks)
+  tx_with_recursion   the same + placeholder recursion layers (recursive verifiers of circuit proofs)
+  tx_real_recursion   BASELINE "tx proofs/min" on the reference's proof STRUCTURE: the seven table STARKs, per table the wrapper
+            circuit that verifies THAT proof + a shrinking step, the root circuit over the seven shrunk proofs; a block of 8
+            such segments with its aggregation tree and block proof (eth_tx_proof_b200/stark_circuit.py); witnesses given
+  recursion_skeleton, circuit_prover   the circuit prover by phase, with the CPU restatement beside it
+  column_split, column_split_proof (N > 1)   one table column-split across the GPUs, parity asserted in the run
 
 `--impl reference`: the CPU implementation of the same path on the host cores.  The reference's own
 prover is Rust in un-vendored crates and cannot be built here, so this arm runs the oracle
